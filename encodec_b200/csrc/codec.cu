@@ -1,0 +1,844 @@
+// C ABI + orchestration of the SEANet encoder / decoder / RVQ on one device (see include/encodec_b200.h).
+#include <stdarg.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/encodec_b200.h"
+#include "common.cuh"
+
+namespace ecb {
+
+static thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+}
+
+namespace {
+
+struct DevBuf {
+  float* p = nullptr;
+  long long n = 0;
+};
+
+struct ConvW {           // one SConv1d / SConvTranspose1d, prepared
+  std::string prefix;
+  int c_in = 0, c_out = 0, k = 0, stride = 1;
+  bool transposed = false, plain = false;
+  float* w = nullptr;     // packed [K][Ci][Co] (conv) / [2][Ci][s*Co] (convtr)
+  float* bias = nullptr;  // [Co] (conv) / [s*Co] (convtr)
+  float* gamma = nullptr; // GroupNorm affine (48 kHz model), [Co]
+  float* beta = nullptr;
+};
+
+struct ResW {
+  ConvW b1, b3, sc;
+  float* w_cat = nullptr;     // [c/2 + c][c]: block.3 stacked over the shortcut (weight-norm models)
+  float* bias_cat = nullptr;  // b3 + bs
+};
+
+struct LstmLayerW {
+  float* w_ih = nullptr;  // [H_in][4H] (K-major rows for the 1-tap GEMM)
+  float* bias = nullptr;  // b_ih + b_hh
+  float* w_hh = nullptr;  // packed per CTA (lstm.cu)
+};
+
+}  // namespace
+}  // namespace ecb
+
+using namespace ecb;
+
+struct ecb_codec {
+  ecb_spec spec;
+  bool finalized = false;
+  bool has_enc = false, has_dec = false, has_rvq = false;  // which sub-modules were loaded
+  std::map<std::string, DevBuf> raw;      // tensors as loaded (reference layout)
+  std::vector<float*> owned;              // prepared buffers
+  // encoder
+  ConvW enc_in, enc_out;
+  std::vector<ResW> enc_res;
+  std::vector<ConvW> enc_down;
+  std::vector<LstmLayerW> enc_lstm;
+  // decoder
+  ConvW dec_in, dec_out;
+  std::vector<ConvW> dec_up;
+  std::vector<ResW> dec_res;
+  std::vector<LstmLayerW> dec_lstm;
+  // quantiser
+  float* codebooks = nullptr;  // [n_q][bins][D]
+  float* e2 = nullptr;         // [n_q][bins]
+  int hop = 1;
+};
+
+namespace {
+
+int dev_alloc(ecb_codec* c, float** out, long long n) {
+  ECB_CUDA(cudaMalloc((void**)out, sizeof(float) * (size_t)(n > 0 ? n : 1)));
+  c->owned.push_back(*out);
+  return 0;
+}
+
+const DevBuf* find_raw(const ecb_codec* c, const std::string& key) {
+  auto it = c->raw.find(key);
+  return it == c->raw.end() ? nullptr : &it->second;
+}
+
+int need_raw(const ecb_codec* c, const std::string& key, long long numel, const float** out) {
+  const DevBuf* b = find_raw(c, key);
+  ECB_REQUIRE(b != nullptr, "finalize: tensor '%s' was never loaded", key.c_str());
+  ECB_REQUIRE(b->n == numel, "finalize: tensor '%s' has %lld elements, expected %lld", key.c_str(), b->n, numel);
+  *out = b->p;
+  return 0;
+}
+
+// Fold weight-norm if present and repack; reference modules/conv.py:26-35,109-163.
+int prepare_conv(ecb_codec* c, ConvW& cw, cudaStream_t st) {
+  const bool tr = cw.transposed;
+  const std::string base = cw.prefix + (tr ? ".convtr.convtr" : ".conv.conv");
+  const std::string normp = cw.prefix + (tr ? ".convtr.norm" : ".conv.norm");
+  const long long wn = (long long)cw.c_in * cw.c_out * cw.k;
+  const int dim0 = tr ? cw.c_in : cw.c_out;
+  const float *w = nullptr, *g = nullptr, *b = nullptr;
+  float* scale = nullptr;
+  if (find_raw(c, base + ".weight_g")) {
+    ECB_REQUIRE(!cw.plain && !c->spec.group_norm, "finalize: unexpected weight_g for '%s'", base.c_str());
+    if (need_raw(c, base + ".weight_g", dim0, &g)) return 1;
+    if (need_raw(c, base + ".weight_v", wn, &w)) return 1;
+    if (dev_alloc(c, &scale, dim0)) return 1;
+    if (launch_weight_scale(g, w, scale, dim0, (int)(wn / dim0), st)) return 1;
+  } else {
+    if (need_raw(c, base + ".weight", wn, &w)) return 1;
+  }
+  if (need_raw(c, base + ".bias", cw.c_out, &b)) return 1;
+  if (dev_alloc(c, &cw.w, wn)) return 1;
+  if (tr) {
+    ECB_REQUIRE(cw.k == 2 * cw.stride, "finalize: convtr '%s' needs kernel == 2*stride", base.c_str());
+    if (launch_pack_convtr(w, scale, cw.w, cw.c_in, cw.c_out, cw.stride, st)) return 1;
+    if (dev_alloc(c, &cw.bias, (long long)cw.c_out * cw.stride)) return 1;
+    if (launch_expand_bias(b, cw.bias, cw.c_out, cw.stride, st)) return 1;
+  } else {
+    if (launch_pack_conv(w, scale, cw.w, cw.c_out, cw.c_in, cw.k, st)) return 1;
+    if (dev_alloc(c, &cw.bias, cw.c_out)) return 1;
+    ECB_CUDA(cudaMemcpyAsync(cw.bias, b, sizeof(float) * cw.c_out, cudaMemcpyDeviceToDevice, st));
+  }
+  if (c->spec.group_norm && !cw.plain) {
+    const float *ga = nullptr, *be = nullptr;
+    if (need_raw(c, normp + ".weight", cw.c_out, &ga)) return 1;
+    if (need_raw(c, normp + ".bias", cw.c_out, &be)) return 1;
+    if (dev_alloc(c, &cw.gamma, cw.c_out)) return 1;
+    if (dev_alloc(c, &cw.beta, cw.c_out)) return 1;
+    ECB_CUDA(cudaMemcpyAsync(cw.gamma, ga, sizeof(float) * cw.c_out, cudaMemcpyDeviceToDevice, st));
+    ECB_CUDA(cudaMemcpyAsync(cw.beta, be, sizeof(float) * cw.c_out, cudaMemcpyDeviceToDevice, st));
+  }
+  return 0;
+}
+
+int prepare_res(ecb_codec* c, ResW& r, cudaStream_t st) {
+  if (prepare_conv(c, r.b1, st) || prepare_conv(c, r.b3, st) || prepare_conv(c, r.sc, st)) return 1;
+  ECB_REQUIRE(r.b3.k == 1 && r.sc.k == 1, "finalize: residual block expects 1x1 second conv and shortcut");
+  if (!c->spec.group_norm) {
+    const int dim = r.sc.c_out, hid = r.b3.c_in;
+    if (dev_alloc(c, &r.w_cat, (long long)(hid + dim) * dim)) return 1;
+    ECB_CUDA(cudaMemcpyAsync(r.w_cat, r.b3.w, sizeof(float) * hid * dim, cudaMemcpyDeviceToDevice, st));
+    ECB_CUDA(cudaMemcpyAsync(r.w_cat + (long long)hid * dim, r.sc.w, sizeof(float) * dim * dim,
+                             cudaMemcpyDeviceToDevice, st));
+    if (dev_alloc(c, &r.bias_cat, dim)) return 1;
+    if (launch_add_vec(r.b3.bias, r.sc.bias, r.bias_cat, dim, st)) return 1;
+  }
+  return 0;
+}
+
+int prepare_lstm(ecb_codec* c, const std::string& prefix, int H, std::vector<LstmLayerW>& out, cudaStream_t st) {
+  out.resize(c->spec.lstm_layers);
+  for (int l = 0; l < c->spec.lstm_layers; ++l) {
+    const std::string sfx = "_l" + std::to_string(l);
+    const float *wih, *whh, *bih, *bhh;
+    if (need_raw(c, prefix + ".lstm.weight_ih" + sfx, 4LL * H * H, &wih)) return 1;
+    if (need_raw(c, prefix + ".lstm.weight_hh" + sfx, 4LL * H * H, &whh)) return 1;
+    if (need_raw(c, prefix + ".lstm.bias_ih" + sfx, 4LL * H, &bih)) return 1;
+    if (need_raw(c, prefix + ".lstm.bias_hh" + sfx, 4LL * H, &bhh)) return 1;
+    LstmLayerW& lw = out[l];
+    if (dev_alloc(c, &lw.w_ih, 4LL * H * H)) return 1;
+    if (launch_transpose(wih, lw.w_ih, 1, 4 * H, H, st)) return 1;  // [4H][H] -> [H][4H]
+    if (dev_alloc(c, &lw.bias, 4LL * H)) return 1;
+    if (launch_add_vec(bih, bhh, lw.bias, 4 * H, st)) return 1;
+    if (dev_alloc(c, &lw.w_hh, 4LL * H * H)) return 1;
+    if (launch_pack_lstm_whh(whh, lw.w_hh, H, st)) return 1;
+  }
+  return 0;
+}
+
+void make_conv(ConvW& cw, const std::string& prefix, int ci, int co, int k, int stride, bool tr = false,
+               bool plain = false) {
+  cw.prefix = prefix;
+  cw.c_in = ci;
+  cw.c_out = co;
+  cw.k = k;
+  cw.stride = stride;
+  cw.transposed = tr;
+  cw.plain = plain;
+}
+
+void make_res(ResW& r, const std::string& prefix, int dim, const ecb_spec& s) {
+  const int hid = dim / s.compress;
+  make_conv(r.b1, prefix + ".block.1", dim, hid, s.residual_kernel_size, 1);
+  make_conv(r.b3, prefix + ".block.3", hid, dim, 1, 1);
+  make_conv(r.sc, prefix + ".shortcut", dim, dim, 1, 1);
+}
+
+// Module indices follow nn.Sequential order, reference modules/seanet.py:108-143 and :197-235.
+void build_layout(ecb_codec* c) {
+  const ecb_spec& s = c->spec;
+  const int nf = s.n_filters;
+  int mult = 1, idx = 1;
+  make_conv(c->enc_in, "encoder.model.0", s.channels, nf, s.kernel_size, 1);
+  c->enc_res.resize(s.n_ratios);
+  c->enc_down.resize(s.n_ratios);
+  c->hop = 1;
+  for (int i = 0; i < s.n_ratios; ++i) {
+    const int ratio = s.ratios[s.n_ratios - 1 - i];
+    c->hop *= ratio;
+    make_res(c->enc_res[i], "encoder.model." + std::to_string(idx), mult * nf, s);
+    make_conv(c->enc_down[i], "encoder.model." + std::to_string(idx + 2), mult * nf, mult * nf * 2, 2 * ratio, ratio);
+    idx += 3;
+    mult *= 2;
+  }
+  if (s.lstm_layers) idx += 1;
+  make_conv(c->enc_out, "encoder.model." + std::to_string(idx + 1), mult * nf, s.dimension, s.last_kernel_size, 1);
+
+  make_conv(c->dec_in, "decoder.model.0", s.dimension, mult * nf, s.kernel_size, 1);
+  idx = 1;
+  if (s.lstm_layers) idx += 1;
+  c->dec_up.resize(s.n_ratios);
+  c->dec_res.resize(s.n_ratios);
+  for (int i = 0; i < s.n_ratios; ++i) {
+    const int ratio = s.ratios[i];
+    make_conv(c->dec_up[i], "decoder.model." + std::to_string(idx + 1), mult * nf, mult * nf / 2, 2 * ratio, ratio, true);
+    make_res(c->dec_res[i], "decoder.model." + std::to_string(idx + 2), mult * nf / 2, s);
+    idx += 3;
+    mult /= 2;
+  }
+  make_conv(c->dec_out, "decoder.model." + std::to_string(idx + 1), nf, s.channels, s.last_kernel_size, 1, false, true);
+}
+
+inline int pad_left_of(const ecb_spec& s, int k, int stride) {
+  // SConv1d padding rules, reference modules/conv.py:207-219
+  const int total = k - stride;
+  return s.causal ? total : total - total / 2;
+}
+
+inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
+
+// Workspace carving -----------------------------------------------------------------------------------
+struct Arena {
+  char* base;
+  size_t size, off = 0;
+  bool ok = true;
+  template <typename T>
+  T* take(size_t count) {
+    off = (off + 255) & ~(size_t)255;
+    T* p = reinterpret_cast<T*>(base + off);
+    off += count * sizeof(T);
+    if (off > size) ok = false;
+    return p;
+  }
+};
+
+struct Plan {
+  size_t act_floats;    // one full-resolution activation buffer
+  size_t stat_doubles;  // one statistics region
+  size_t lstm_floats;
+  int n_act;
+  size_t total_bytes;
+};
+
+Plan make_plan(const ecb_codec* c, long long n_items, long long length) {
+  Plan p;
+  const long long t_pad = length + 2LL * c->hop;
+  p.act_floats = (size_t)n_items * t_pad * c->spec.n_filters;
+  p.n_act = c->spec.group_norm ? 4 : 3;
+  p.stat_doubles = c->spec.group_norm ? (size_t)n_items * (ceil_div_ll(length, 128) + 64) * 2 : 0;
+  p.lstm_floats = (size_t)lstm_recurrent_workspace_floats((int)n_items);
+  p.total_bytes = (p.act_floats * p.n_act + p.lstm_floats) * sizeof(float) + 2 * p.stat_doubles * sizeof(double) +
+                  256 * 16;
+  return p;
+}
+
+struct Ctx {
+  ecb_codec* c;
+  cudaStream_t st;
+  int n_items;
+  float* buf[4];
+  double* stat[2];
+  float* lstm_ws;
+};
+
+ConvSrc src_of(const float* ptr, int C, int taps, long long T, int elu) {
+  ConvSrc s;
+  s.ptr = ptr;
+  s.item_stride = T * C;
+  s.C = C;
+  s.taps = taps;
+  s.T = (int)T;
+  s.elu = elu;
+  return s;
+}
+
+ConvSrc no_src() {
+  ConvSrc s;
+  s.ptr = nullptr;
+  s.item_stride = 0;
+  s.C = 16;
+  s.taps = 0;
+  s.T = 0;
+  s.elu = 0;
+  return s;
+}
+
+// One strided / 1x1 SConv1d through the GEMM kernel. in: [item][T_in][c_in] -> out: [item][T_out][c_out].
+// With GroupNorm the raw result is normalised in place afterwards (out_elu moves to that pass).
+int run_conv(Ctx& x, const ConvW& cw, const float* in, long long T_in, int in_elu, float* out, int out_elu,
+             long long* T_out_p) {
+  const ecb_spec& s = x.c->spec;
+  const long long T_out = ceil_div_ll(T_in, cw.stride);
+  ConvParams p;
+  p.s0 = src_of(in, cw.c_in, cw.k, T_in, in_elu);
+  p.s1 = no_src();
+  p.w = cw.w;
+  p.bias = cw.bias;
+  p.out = out;
+  p.out_item_stride = T_out * cw.c_out;
+  p.out_lo = 0;
+  p.out_hi = T_out * cw.c_out;
+  p.N = cw.c_out;
+  p.M = (int)T_out;
+  p.n_items = x.n_items;
+  p.stride = cw.stride;
+  p.pad_left = pad_left_of(s, cw.k, cw.stride);
+  p.pad_zero = 0;
+  p.out_elu = s.group_norm ? 0 : out_elu;
+  p.stats = s.group_norm ? x.stat[0] : nullptr;
+  if (launch_conv_gemm(p, x.st)) return 1;
+  if (s.group_norm) {
+    GnSrc a;
+    a.x = out;
+    a.partial = x.stat[0];
+    a.slots = conv_gemm_stat_slots(p);
+    a.count = (double)T_out * cw.c_out;
+    a.gamma = cw.gamma;
+    a.beta = cw.beta;
+    if (launch_gn_apply(a, nullptr, out, x.n_items, T_out, cw.c_out, out_elu, 1e-5f, x.st)) return 1;
+  }
+  if (T_out_p) *T_out_p = T_out;
+  return 0;
+}
+
+// SEANetResnetBlock (reference modules/seanet.py:37-64): in X (raw) -> out Y = ELU(shortcut(X) + block(X)).
+// The trailing ELU belongs to the next module of the Sequential; every consumer of a block output applies
+// it, so it is folded into this epilogue. tmp0/tmp1 are scratch; out may not alias in.
+int run_res(Ctx& x, const ResW& r, const float* in, long long T, float* tmp0, float* tmp1, float* out) {
+  const ecb_spec& s = x.c->spec;
+  const int dim = r.sc.c_out, hid = r.b1.c_out;
+  if (run_conv(x, r.b1, in, T, /*in_elu=*/1, tmp0, /*out_elu=*/1, nullptr)) return 1;
+  if (!s.group_norm) {
+    ConvParams p;
+    p.s0 = src_of(tmp0, hid, 1, T, 0);
+    p.s1 = src_of(in, dim, 1, T, 0);
+    p.w = r.w_cat;
+    p.bias = r.bias_cat;
+    p.out = out;
+    p.out_item_stride = T * dim;
+    p.out_lo = 0;
+    p.out_hi = T * dim;
+    p.N = dim;
+    p.M = (int)T;
+    p.n_items = x.n_items;
+    p.stride = 1;
+    p.pad_left = 0;
+    p.pad_zero = 0;
+    p.out_elu = 1;
+    p.stats = nullptr;
+    return launch_conv_gemm(p, x.st);
+  }
+  // GroupNorm variant: both branches are normalised separately before the add (conv.py:125)
+  ConvParams p;
+  p.s0 = src_of(in, dim, 1, T, 0);
+  p.s1 = no_src();
+  p.w = r.sc.w;
+  p.bias = r.sc.bias;
+  p.out = out;
+  p.out_item_stride = T * dim;
+  p.out_lo = 0;
+  p.out_hi = T * dim;
+  p.N = dim;
+  p.M = (int)T;
+  p.n_items = x.n_items;
+  p.stride = 1;
+  p.pad_left = 0;
+  p.pad_zero = 0;
+  p.out_elu = 0;
+  p.stats = x.stat[0];
+  if (launch_conv_gemm(p, x.st)) return 1;
+  GnSrc a;
+  a.x = out;
+  a.partial = x.stat[0];
+  a.slots = conv_gemm_stat_slots(p);
+  a.count = (double)T * dim;
+  a.gamma = r.sc.gamma;
+  a.beta = r.sc.beta;
+  ConvParams p2 = p;
+  p2.s0 = src_of(tmp0, hid, 1, T, 0);
+  p2.w = r.b3.w;
+  p2.bias = r.b3.bias;
+  p2.out = tmp1;
+  p2.stats = x.stat[1];
+  if (launch_conv_gemm(p2, x.st)) return 1;
+  GnSrc b;
+  b.x = tmp1;
+  b.partial = x.stat[1];
+  b.slots = conv_gemm_stat_slots(p2);
+  b.count = (double)T * dim;
+  b.gamma = r.b3.gamma;
+  b.beta = r.b3.beta;
+  return launch_gn_apply(a, &b, out, x.n_items, T, dim, /*out_elu=*/1, 1e-5f, x.st);
+}
+
+// SLSTM (reference modules/lstm.py:22-28): in X [item][T][H] raw -> out = ELU(lstm(X) + X); tmp is scratch.
+int run_lstm(Ctx& x, const std::vector<LstmLayerW>& layers, int H, const float* in, long long T, float* tmp,
+             float* out) {
+  const int L = (int)layers.size();
+  const float* cur = in;
+  for (int l = 0; l < L; ++l) {
+    ConvParams p;
+    p.s0 = src_of(cur, H, 1, (long long)x.n_items * T, 0);
+    p.s1 = no_src();
+    p.w = layers[l].w_ih;
+    p.bias = layers[l].bias;
+    p.out = tmp;
+    p.out_item_stride = 0;
+    p.out_lo = 0;
+    p.out_hi = (long long)x.n_items * T * 4 * H;
+    p.N = 4 * H;
+    p.M = (int)((long long)x.n_items * T);
+    p.n_items = 1;
+    p.stride = 1;
+    p.pad_left = 0;
+    p.pad_zero = 1;
+    p.out_elu = 0;
+    p.stats = nullptr;
+    if (launch_conv_gemm(p, x.st)) return 1;
+    const bool last = (l == L - 1);
+    if (launch_lstm_recurrent(tmp, layers[l].w_hh, last ? in : nullptr, out, x.n_items, (int)T, H, last ? 1 : 0,
+                              x.lstm_ws, x.st))
+      return 1;
+    cur = out;
+  }
+  return 0;
+}
+
+// SConvTranspose1d (reference modules/conv.py:241-263): in Y [item][L][c_in] (already ELU'd) -> out raw
+// [item][L*s][c_out], as a 2-tap GEMM over frames with N = s*c_out and the trim as an element window.
+int run_convtr(Ctx& x, const ConvW& cw, const float* in, long long L, float* out) {
+  const ecb_spec& s = x.c->spec;
+  const int sN = cw.stride * cw.c_out;
+  const int total = cw.k - cw.stride;
+  const int trim_right = s.causal ? total : total / 2;
+  const int trim_left = total - trim_right;
+  const long long M = (s.group_norm || trim_left > 0) ? L + 1 : L;  // frame L is fully trimmed when causal
+  ConvParams p;
+  p.s0 = src_of(in, cw.c_in, 2, L, 0);
+  p.s1 = no_src();
+  p.w = cw.w;
+  p.bias = cw.bias;
+  p.out = out;
+  p.out_item_stride = L * sN;
+  p.out_lo = (long long)trim_left * cw.c_out;
+  p.out_hi = p.out_lo + L * sN;
+  p.N = sN;
+  p.M = (int)M;
+  p.n_items = x.n_items;
+  p.stride = 1;
+  p.pad_left = 1;
+  p.pad_zero = 1;
+  p.out_elu = 0;
+  p.stats = s.group_norm ? x.stat[0] : nullptr;
+  if (launch_conv_gemm(p, x.st)) return 1;
+  if (s.group_norm) {
+    GnSrc a;
+    a.x = out;
+    a.partial = x.stat[0];
+    a.slots = conv_gemm_stat_slots(p);
+    a.count = (double)(L + 1) * sN;  // statistics cover the UNtrimmed output (norm before unpad1d)
+    a.gamma = cw.gamma;
+    a.beta = cw.beta;
+    if (launch_gn_apply(a, nullptr, out, x.n_items, L * cw.stride, cw.c_out, 0, 1e-5f, x.st)) return 1;
+  }
+  return 0;
+}
+
+int setup_ctx(Ctx& x, ecb_codec* c, long long n_items, long long length, void* workspace, size_t ws_bytes,
+              void* stream) {
+  ECB_REQUIRE(c && c->finalized, "codec is not finalized");
+  ECB_REQUIRE(n_items > 0 && n_items <= 65535, "n_items=%lld out of range (1..65535); split the batch", n_items);
+  Plan pl = make_plan(c, n_items, length);
+  ECB_REQUIRE(workspace && ws_bytes >= pl.total_bytes, "workspace too small: %zu < %zu bytes", ws_bytes, pl.total_bytes);
+  Arena a{reinterpret_cast<char*>(workspace), ws_bytes};
+  for (int i = 0; i < 4; ++i) x.buf[i] = i < pl.n_act ? a.take<float>(pl.act_floats) : nullptr;
+  x.stat[0] = a.take<double>(pl.stat_doubles);
+  x.stat[1] = a.take<double>(pl.stat_doubles);
+  x.lstm_ws = a.take<float>(pl.lstm_floats);
+  ECB_REQUIRE(a.ok, "internal: workspace plan overflow");
+  x.c = c;
+  x.st = reinterpret_cast<cudaStream_t>(stream);
+  x.n_items = (int)n_items;
+  return 0;
+}
+
+}  // namespace
+
+// ====================================================================================================
+// C ABI
+// ====================================================================================================
+extern "C" {
+
+const char* ecb_last_error(void) { return g_err.c_str(); }
+int ecb_version(void) { return 1; }
+int64_t ecb_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int ecb_codec_create(const ecb_spec* spec, ecb_codec** out) {
+  ECB_REQUIRE(spec && out, "null argument");
+  ECB_REQUIRE(spec->channels >= 1 && spec->channels <= 2, "channels=%d unsupported", spec->channels);
+  ECB_REQUIRE(spec->n_filters == 32, "n_filters=%d unsupported (32 only)", spec->n_filters);
+  ECB_REQUIRE(spec->dimension == 128, "dimension=%d unsupported (128 only)", spec->dimension);
+  ECB_REQUIRE(spec->n_ratios >= 1 && spec->n_ratios <= ECB_MAX_RATIOS, "n_ratios=%d unsupported", spec->n_ratios);
+  ECB_REQUIRE(spec->compress == 2 && spec->residual_kernel_size == 3, "only compress=2, residual_kernel_size=3");
+  ECB_REQUIRE(spec->kernel_size == 7 && spec->last_kernel_size == 7, "only kernel_size=last_kernel_size=7");
+  ECB_REQUIRE(!(spec->group_norm && spec->causal), "GroupNorm doesn't support causal evaluation.");
+  ECB_REQUIRE(spec->lstm_layers >= 0 && spec->lstm_layers <= 4, "lstm_layers=%d unsupported", spec->lstm_layers);
+  int top = spec->n_filters;
+  for (int i = 0; i < spec->n_ratios; ++i) {
+    ECB_REQUIRE(spec->ratios[i] >= 2 && spec->ratios[i] <= 16, "ratio %d unsupported", spec->ratios[i]);
+    top *= 2;
+  }
+  ECB_REQUIRE(spec->lstm_layers == 0 || top == 512, "LSTM width %d unsupported (512 only)", top);
+  ECB_REQUIRE(spec->bins % 128 == 0 && spec->n_q >= 1, "bins=%d must be a multiple of 128", spec->bins);
+  ecb_codec* c = new ecb_codec();
+  c->spec = *spec;
+  build_layout(c);
+  *out = c;
+  return 0;
+}
+
+void ecb_codec_destroy(ecb_codec* c) {
+  if (!c) return;
+  for (auto& kv : c->raw) cudaFree(kv.second.p);
+  for (float* p : c->owned) cudaFree(p);
+  delete c;
+}
+
+int ecb_codec_load_tensor(ecb_codec* c, const char* key, const float* data, int64_t numel, void* stream) {
+  ECB_REQUIRE(c && key && data && numel > 0, "load_tensor: bad argument");
+  std::string k(key);
+  auto ends_with = [&](const char* sfx) {
+    const size_t n = strlen(sfx);
+    return k.size() >= n && k.compare(k.size() - n, n, sfx) == 0;
+  };
+  if (ends_with("._codebook.inited") || ends_with("._codebook.cluster_size") || ends_with("._codebook.embed_avg"))
+    return 0;  // training-only state (core_vq.py:132-135)
+  const bool known = k.rfind("encoder.model.", 0) == 0 || k.rfind("decoder.model.", 0) == 0 ||
+                     (k.rfind("quantizer.vq.layers.", 0) == 0 && ends_with("._codebook.embed"));
+  ECB_REQUIRE(known, "load_tensor: unexpected key '%s'", key);
+  DevBuf& b = c->raw[k];
+  if (b.p && b.n != numel) {
+    cudaFree(b.p);
+    b.p = nullptr;
+  }
+  if (!b.p) ECB_CUDA(cudaMalloc((void**)&b.p, sizeof(float) * (size_t)numel));
+  b.n = numel;
+  ECB_CUDA(cudaMemcpyAsync(b.p, data, sizeof(float) * (size_t)numel, cudaMemcpyDeviceToDevice,
+                           reinterpret_cast<cudaStream_t>(stream)));
+  c->finalized = false;
+  return 0;
+}
+
+int ecb_codec_finalize(ecb_codec* c, void* stream) {
+  ECB_REQUIRE(c, "null codec");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  for (float* p : c->owned) cudaFree(p);
+  c->owned.clear();
+  const ecb_spec& s = c->spec;
+  c->has_enc = c->has_dec = c->has_rvq = false;
+  for (auto& kv : c->raw) {
+    if (kv.first.rfind("encoder.", 0) == 0) c->has_enc = true;
+    if (kv.first.rfind("decoder.", 0) == 0) c->has_dec = true;
+    if (kv.first.rfind("quantizer.", 0) == 0) c->has_rvq = true;
+  }
+  ECB_REQUIRE(c->has_enc || c->has_dec || c->has_rvq, "finalize: no tensors loaded");
+  if (c->has_enc) {
+    if (prepare_conv(c, c->enc_in, st) || prepare_conv(c, c->enc_out, st)) return 1;
+    for (int i = 0; i < s.n_ratios; ++i)
+      if (prepare_res(c, c->enc_res[i], st) || prepare_conv(c, c->enc_down[i], st)) return 1;
+    if (s.lstm_layers &&
+        prepare_lstm(c, "encoder.model." + std::to_string(1 + 3 * s.n_ratios), 512, c->enc_lstm, st))
+      return 1;
+  }
+  if (c->has_dec) {
+    if (prepare_conv(c, c->dec_in, st) || prepare_conv(c, c->dec_out, st)) return 1;
+    for (int i = 0; i < s.n_ratios; ++i)
+      if (prepare_conv(c, c->dec_up[i], st) || prepare_res(c, c->dec_res[i], st)) return 1;
+    if (s.lstm_layers && prepare_lstm(c, "decoder.model.1", 512, c->dec_lstm, st)) return 1;
+  }
+  if (c->has_rvq) {
+    // codebooks (quantization/core_vq.py:128-135); layers may alias (fork delta D6) -- each is copied
+    const long long per = (long long)s.bins * s.dimension;
+    if (dev_alloc(c, &c->codebooks, per * s.n_q)) return 1;
+    if (dev_alloc(c, &c->e2, (long long)s.bins * s.n_q)) return 1;
+    for (int i = 0; i < s.n_q; ++i) {
+      const float* e;
+      if (need_raw(c, "quantizer.vq.layers." + std::to_string(i) + "._codebook.embed", per, &e)) return 1;
+      ECB_CUDA(cudaMemcpyAsync(c->codebooks + per * i, e, sizeof(float) * per, cudaMemcpyDeviceToDevice, st));
+    }
+    if (launch_rvq_prepare(c->codebooks, s.n_q, s.bins, s.dimension, c->e2, st)) return 1;
+  }
+  // conv_in / conv_out use their own packings: [K][C_in][32] is what pack_conv produced; conv_out wants
+  // [K][32][C_out], which is also pack_conv's [K][Ci][Co] -- nothing more to do.
+  c->finalized = true;
+  return 0;
+}
+
+size_t ecb_encoder_workspace_bytes(const ecb_codec* c, int64_t n_items, int64_t length) {
+  if (!c || n_items <= 0 || length <= 0) return 0;
+  return make_plan(c, n_items, length).total_bytes;
+}
+
+int ecb_encoder_forward(ecb_codec* c, const float* xin, int64_t n_items, int64_t n_seg, int64_t length,
+                        int64_t x_batch_stride, int64_t x_seg_stride, int64_t x_chan_stride, float* scale_out,
+                        float* emb_out, float* emb_frames_out, void* workspace, size_t workspace_bytes,
+                        void* stream) {
+  Ctx x;
+  ECB_REQUIRE(xin && (emb_out || emb_frames_out), "encoder_forward: null argument");
+  ECB_REQUIRE(n_seg >= 1 && length > 0 && length < (1LL << 30), "encoder_forward: bad n_seg/length");
+  if (setup_ctx(x, c, n_items, length, workspace, workspace_bytes, stream)) return 1;
+  ECB_REQUIRE(c->has_enc, "encoder_forward: no encoder weights were loaded into this codec");
+  const ecb_spec& s = c->spec;
+  float *A = x.buf[0], *B = x.buf[1], *C = x.buf[2], *D = x.buf[3];
+
+  if (scale_out) {
+    if (launch_segment_scale(xin, x_batch_stride, x_seg_stride, x_chan_stride, (int)n_seg, (int)n_items, (int)length,
+                             s.channels, scale_out, x.st))
+      return 1;
+  }
+  ConvInParams ci;
+  ci.x = xin;
+  ci.batch_stride = x_batch_stride;
+  ci.seg_stride = x_seg_stride;
+  ci.chan_stride = x_chan_stride;
+  ci.n_seg = (int)n_seg;
+  ci.n_items = (int)n_items;
+  ci.T = (int)length;
+  ci.C_in = s.channels;
+  ci.K = c->enc_in.k;
+  ci.pad_left = pad_left_of(s, c->enc_in.k, 1);
+  ci.scale = scale_out;
+  ci.w = c->enc_in.w;
+  ci.bias = c->enc_in.bias;
+  ci.out = A;
+  ci.stats = s.group_norm ? x.stat[0] : nullptr;
+  if (launch_conv_in(ci, x.st)) return 1;
+  if (s.group_norm) {
+    GnSrc a;
+    a.x = A;
+    a.partial = x.stat[0];
+    a.slots = conv_in_stat_slots(ci);
+    a.count = (double)length * s.n_filters;
+    a.gamma = c->enc_in.gamma;
+    a.beta = c->enc_in.beta;
+    if (launch_gn_apply(a, nullptr, A, x.n_items, length, s.n_filters, 0, 1e-5f, x.st)) return 1;
+  }
+  long long T = length;
+  for (int i = 0; i < s.n_ratios; ++i) {
+    if (run_res(x, c->enc_res[i], A, T, B, D, C)) return 1;              // A -> C (post-ELU)
+    if (run_conv(x, c->enc_down[i], C, T, 0, A, 0, &T)) return 1;        // C -> A (raw)
+  }
+  const float* top = A;
+  int top_elu_pending = 1;  // the ELU before the last conv (seanet.py:138)
+  if (s.lstm_layers) {
+    if (run_lstm(x, c->enc_lstm, 512, A, T, B, C)) return 1;             // A -> C = ELU(lstm(A) + A)
+    top = C;
+    top_elu_pending = 0;
+  }
+  float* frames = emb_frames_out ? emb_frames_out : B;
+  if (run_conv(x, c->enc_out, top, T, top_elu_pending, frames, 0, nullptr)) return 1;
+  if (emb_out) {
+    if (launch_transpose(frames, emb_out, n_items, (int)T, s.dimension, x.st)) return 1;
+  }
+  return 0;
+}
+
+size_t ecb_decoder_workspace_bytes(const ecb_codec* c, int64_t n_items, int64_t n_frames) {
+  if (!c || n_items <= 0 || n_frames <= 0) return 0;
+  return make_plan(c, n_items, n_frames * c->hop).total_bytes;
+}
+
+int ecb_decoder_forward(ecb_codec* c, const float* z, const float* z_frames, int64_t n_items, int64_t n_frames,
+                        const float* scale, float* out, void* workspace, size_t workspace_bytes, void* stream) {
+  Ctx x;
+  ECB_REQUIRE((z != nullptr) != (z_frames != nullptr) && out, "decoder_forward: give exactly one of z / z_frames");
+  ECB_REQUIRE(n_frames > 0 && n_frames < (1LL << 24), "decoder_forward: bad n_frames");
+  if (c == nullptr) {
+    set_error("null codec");
+    return 1;
+  }
+  if (setup_ctx(x, c, n_items, n_frames * c->hop, workspace, workspace_bytes, stream)) return 1;
+  ECB_REQUIRE(c->has_dec, "decoder_forward: no decoder weights were loaded into this codec");
+  const ecb_spec& s = c->spec;
+  float *A = x.buf[0], *B = x.buf[1], *C = x.buf[2], *D = x.buf[3];
+  long long T = n_frames;
+  if (z) {
+    if (launch_transpose(z, C, n_items, s.dimension, (int)T, x.st)) return 1;  // [D][T] -> [T][D]
+    z_frames = C;
+  }
+  if (run_conv(x, c->dec_in, z_frames, T, 0, A, 0, nullptr)) return 1;        // -> A raw [T][512]
+  const float* cur = A;
+  if (s.lstm_layers) {
+    if (run_lstm(x, c->dec_lstm, 512, A, T, B, C)) return 1;                  // -> C = ELU(lstm(A) + A)
+    cur = C;
+  } else {
+    // no LSTM: the ELU before the first transposed conv still has to happen; fold it into a copy-free path
+    set_error("decoder without LSTM is not supported yet");
+    return 1;
+  }
+  for (int i = 0; i < s.n_ratios; ++i) {
+    float* up = (cur == A) ? C : A;
+    if (run_convtr(x, c->dec_up[i], cur, T, up)) return 1;                    // cur -> up (raw)
+    T *= c->dec_up[i].stride;
+    float* res_out = (up == A) ? C : A;
+    if (run_res(x, c->dec_res[i], up, T, B, D, res_out)) return 1;            // up -> res_out (post-ELU)
+    cur = res_out;
+  }
+  ConvOutParams co;
+  co.in = cur;
+  co.n_items = (int)n_items;
+  co.T = (int)T;
+  co.C_out = s.channels;
+  co.K = c->dec_out.k;
+  co.pad_left = pad_left_of(s, c->dec_out.k, 1);
+  co.w = c->dec_out.w;
+  co.bias = c->dec_out.bias;
+  co.scale = scale;
+  co.out = out;
+  return launch_conv_out(co, x.st);
+}
+
+int ecb_rvq_prepare(const float* codebooks, int64_t n_q, int64_t bins, int64_t dim, float* e2, void* stream) {
+  ECB_REQUIRE(codebooks && e2 && n_q > 0 && bins > 0, "rvq_prepare: bad argument");
+  return launch_rvq_prepare(codebooks, n_q, bins, (int)dim, e2, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ecb_rvq_encode_frames(const float* frames, int64_t n, int64_t dim, const float* codebooks, const float* e2,
+                          int64_t n_q, int64_t bins, int64_t* codes, float* quantized, float* quantized_stack,
+                          void* stream) {
+  ECB_REQUIRE(frames && codebooks && e2 && codes, "rvq_encode: null argument");
+  ECB_REQUIRE(dim == 128, "rvq_encode: dimension %lld unsupported (128 only)", (long long)dim);
+  return launch_rvq_encode(frames, n, codebooks, e2, (int)n_q, (int)bins, reinterpret_cast<long long*>(codes),
+                           quantized, quantized_stack, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ecb_rvq_decode_frames(const int64_t* codes, int64_t n, int64_t dim, const float* codebooks, int64_t n_q,
+                          int64_t bins, float* quantized, void* stream) {
+  ECB_REQUIRE(codes && codebooks && quantized, "rvq_decode: null argument");
+  ECB_REQUIRE(dim == 128, "rvq_decode: dimension %lld unsupported (128 only)", (long long)dim);
+  return launch_rvq_decode(reinterpret_cast<const long long*>(codes), n, codebooks, (int)n_q, (int)bins, quantized,
+                           reinterpret_cast<cudaStream_t>(stream));
+}
+
+size_t ecb_codec_rvq_workspace_bytes(const ecb_codec* c, int64_t batch, int64_t n_frames) {
+  if (!c || batch <= 0 || n_frames <= 0) return 0;
+  return (size_t)batch * n_frames * c->spec.dimension * sizeof(float) * 2 + 1024;
+}
+
+int ecb_codec_rvq_forward(ecb_codec* c, const float* xin, const float* x_frames, int64_t batch, int64_t n_frames,
+                          int64_t n_q, int64_t* codes, float* quantized, float* quantized_frames,
+                          float* quantized_stack, void* workspace, size_t workspace_bytes, void* stream) {
+  ECB_REQUIRE(c && c->finalized && c->has_rvq, "codec is not finalized or holds no codebooks");
+  ECB_REQUIRE((xin != nullptr) != (x_frames != nullptr) && codes, "rvq_forward: give exactly one of x / x_frames");
+  ECB_REQUIRE(n_q >= 1 && n_q <= c->spec.n_q, "rvq_forward: n_q=%lld out of range 1..%d", (long long)n_q, c->spec.n_q);
+  ECB_REQUIRE(workspace_bytes >= ecb_codec_rvq_workspace_bytes(c, batch, n_frames), "rvq_forward: workspace too small");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int D = c->spec.dimension;
+  const long long n = batch * n_frames;
+  Arena a{reinterpret_cast<char*>(workspace), workspace_bytes};
+  float* w0 = a.take<float>((size_t)n * D);
+  float* w1 = a.take<float>((size_t)n * D);
+  if (xin) {
+    if (launch_transpose(xin, w0, batch, D, (int)n_frames, st)) return 1;
+    x_frames = w0;
+  }
+  float* qf = quantized_frames ? quantized_frames : (quantized ? w1 : nullptr);
+  // the stack is produced frames-major, then transposed in place chunk by chunk is not possible -> reuse w0/w1
+  float* stack_tmp = nullptr;
+  if (quantized_stack) {
+    // write frames-major stack straight into the caller's buffer, transpose per (layer, batch) through w0 later
+    stack_tmp = quantized_stack;
+  }
+  if (launch_rvq_encode(x_frames, n, c->codebooks, c->e2, (int)n_q, c->spec.bins, reinterpret_cast<long long*>(codes),
+                        qf, stack_tmp, st))
+    return 1;
+  if (quantized) {
+    if (launch_transpose(qf, quantized, batch, (int)n_frames, D, st)) return 1;
+  }
+  if (quantized_stack) {
+    // [n_q][B][T][D] -> [n_q][B][D][T], one layer at a time through w0 (x_frames is dead by now)
+    for (int l = 0; l < n_q; ++l) {
+      float* slab = quantized_stack + (size_t)l * n * D;
+      ECB_CUDA(cudaMemcpyAsync(w0, slab, sizeof(float) * (size_t)n * D, cudaMemcpyDeviceToDevice, st));
+      if (launch_transpose(w0, slab, batch, (int)n_frames, D, st)) return 1;
+    }
+  }
+  return 0;
+}
+
+int ecb_codec_rvq_decode(ecb_codec* c, const int64_t* codes, int64_t batch, int64_t n_frames, int64_t n_q,
+                         float* quantized, float* quantized_frames, void* stream) {
+  ECB_REQUIRE(c && c->finalized && c->has_rvq, "codec is not finalized or holds no codebooks");
+  ECB_REQUIRE(codes && quantized_frames, "rvq_decode: codes and quantized_frames are required");
+  ECB_REQUIRE(n_q >= 1 && n_q <= c->spec.n_q, "rvq_decode: n_q=%lld out of range 1..%d", (long long)n_q, c->spec.n_q);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const long long n = batch * n_frames;
+  if (launch_rvq_decode(reinterpret_cast<const long long*>(codes), n, c->codebooks, (int)n_q, c->spec.bins,
+                        quantized_frames, st))
+    return 1;
+  if (quantized) {
+    if (launch_transpose(quantized_frames, quantized, batch, (int)n_frames, c->spec.dimension, st)) return 1;
+  }
+  return 0;
+}
+
+int ecb_overlap_add(const float* frames, const int32_t* seg_lens, int64_t batch, int64_t channels, int64_t n_seg,
+                    int64_t seg_len, int64_t stride, float* out, int64_t total, void* stream) {
+  ECB_REQUIRE(out && frames && seg_lens && batch > 0 && channels > 0 && n_seg > 0, "overlap_add: bad argument");
+  ECB_REQUIRE(stride > 0 && stride * 2 >= seg_len, "overlap_add: more than two frames per sample not supported");
+  ECB_REQUIRE(total > stride * (n_seg - 1) && total <= stride * (n_seg - 1) + seg_len, "overlap_add: bad total");
+  return launch_overlap_add(frames, seg_lens, batch, (int)channels, (int)n_seg, (int)seg_len, (int)stride, out, total,
+                            reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ecb_transpose_bct_to_btc(const float* in, float* out, int64_t batch, int64_t chans, int64_t len, void* stream) {
+  ECB_REQUIRE(in && out, "transpose: null argument");
+  return launch_transpose(in, out, batch, (int)chans, (int)len, reinterpret_cast<cudaStream_t>(stream));
+}
+int ecb_transpose_btc_to_bct(const float* in, float* out, int64_t batch, int64_t len, int64_t chans, void* stream) {
+  ECB_REQUIRE(in && out, "transpose: null argument");
+  return launch_transpose(in, out, batch, (int)len, (int)chans, reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

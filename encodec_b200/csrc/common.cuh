@@ -1,0 +1,166 @@
+// Shared helpers for the encodec_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+#include <string>
+
+namespace ecb {
+
+void set_error(const char* fmt, ...);
+extern std::atomic<long long> g_launches;
+
+#define ECB_CUDA(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t e__ = (expr);                                                                       \
+    if (e__ != cudaSuccess) {                                                                       \
+      ::ecb::set_error("%s: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__);       \
+      return 1;                                                                                     \
+    }                                                                                               \
+  } while (0)
+
+#define ECB_LAUNCHED()                                                                              \
+  do {                                                                                              \
+    ::ecb::g_launches.fetch_add(1, std::memory_order_relaxed);                                      \
+    cudaError_t e__ = cudaGetLastError();                                                           \
+    if (e__ != cudaSuccess) {                                                                       \
+      ::ecb::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return 1;                                                                                     \
+    }                                                                                               \
+  } while (0)
+
+#define ECB_REQUIRE(cond, ...)                                                                      \
+  do {                                                                                              \
+    if (!(cond)) {                                                                                  \
+      ::ecb::set_error(__VA_ARGS__);                                                                \
+      return 1;                                                                                     \
+    }                                                                                               \
+  } while (0)
+
+__device__ __forceinline__ float elu1(float v) { return v > 0.f ? v : expm1f(v); }
+
+// index of a reflect-padded signal of length T (valid while the pad is < T); conv.py:80-97
+__device__ __forceinline__ int reflect_index(int r, int T) {
+  if (r < 0) r = -r;
+  if (r >= T) r = 2 * (T - 1) - r;
+  return r;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+static inline long long cdiv(long long a, long long b) { return (a + b - 1) / b; }
+
+// ------------------------------------------------------------------------------------------------
+// Generic channels-last implicit-GEMM convolution (conv_gemm.cu)
+// ------------------------------------------------------------------------------------------------
+struct ConvSrc {
+  const float* ptr;       // channels-last [item][T][C]
+  long long item_stride;  // floats between items
+  int C;                  // channels, multiple of 16
+  int taps;               // kernel taps (0: source unused)
+  int T;                  // valid rows per item
+  int elu;                // apply ELU while loading
+};
+
+struct ConvParams {
+  ConvSrc s0;             // main source: strided window, reflect / zero padding
+  ConvSrc s1;             // optional second source (1 tap, stride 1, no padding): fused 1x1 shortcut
+  const float* w;         // [taps0*C0 + taps1*C1][N], N contiguous
+  const float* bias;      // [N] or nullptr
+  float* out;             // item i: elements [out_lo, out_hi) of the virtual row-major [M][N] matrix,
+                          // stored at out + i*out_item_stride + (m*N + n - out_lo)
+  long long out_item_stride;
+  long long out_lo, out_hi;
+  int N;                  // output columns (multiple of 16)
+  int M;                  // output rows computed per item
+  int n_items;
+  int stride;             // s0 window start for row m: m*stride - pad_left
+  int pad_left;
+  int pad_zero;           // 0: reflect padding, 1: zero padding
+  int out_elu;            // apply ELU to the output
+  double* stats;          // nullptr, or [item][gridDim.x*gridDim.y][2] partial (sum, sum of squares)
+};
+
+int launch_conv_gemm(const ConvParams& p, cudaStream_t stream);
+int conv_gemm_stat_slots(const ConvParams& p);  // gridDim.x*gridDim.y the launch will use
+
+// ------------------------------------------------------------------------------------------------
+// Edge convolutions (conv_edge.cu): audio [B,C,T] channels-first <-> 32-channel channels-last
+// ------------------------------------------------------------------------------------------------
+struct ConvInParams {
+  const float* x;
+  long long batch_stride, seg_stride, chan_stride;
+  int n_seg, n_items, T, C_in, K, pad_left;
+  const float* scale;     // per item divisor or nullptr
+  const float* w;         // [K*C_in][32]
+  const float* bias;      // [32]
+  float* out;             // [item][T][32]
+  double* stats;          // nullptr or [item][gridDim.x][2]
+};
+int launch_conv_in(const ConvInParams& p, cudaStream_t stream);
+int conv_in_stat_slots(const ConvInParams& p);
+
+struct ConvOutParams {
+  const float* in;        // [item][T][32]
+  int n_items, T, C_out, K, pad_left;
+  const float* w;         // [K][32][C_out]
+  const float* bias;      // [C_out]
+  const float* scale;     // per item multiplier or nullptr
+  float* out;             // [item][C_out][T]
+};
+int launch_conv_out(const ConvOutParams& p, cudaStream_t stream);
+
+// ------------------------------------------------------------------------------------------------
+// misc.cu
+// ------------------------------------------------------------------------------------------------
+int launch_weight_scale(const float* g, const float* v, float* scale, int dim0, int inner, cudaStream_t s);
+// conv weight [Co][Ci][K] (optionally scaled per Co) -> packed [K][Ci][Co]
+int launch_pack_conv(const float* w, const float* scale, float* out, int Co, int Ci, int K, cudaStream_t s);
+// convtr weight [Ci][Co][K=2s] (optionally scaled per Ci) -> packed [2][Ci][s*Co]; tap 0 pairs with frame q-1
+int launch_pack_convtr(const float* w, const float* scale, float* out, int Ci, int Co, int s, cudaStream_t st);
+int launch_expand_bias(const float* b, float* out, int Co, int reps, cudaStream_t s);
+int launch_add_vec(const float* a, const float* b, float* out, int n, cudaStream_t s);
+int launch_transpose(const float* in, float* out, long long batch, int rows, int cols, cudaStream_t s);  // [b][rows][cols]->[b][cols][rows]
+int launch_segment_scale(const float* x, long long batch_stride, long long seg_stride, long long chan_stride,
+                         int n_seg, int n_items, int T, int C, float* scale, cudaStream_t s);
+struct GnSrc {
+  const float* x;         // [item][rows][C] raw conv output (stored region)
+  const double* partial;  // [item][slots][2]
+  int slots;
+  double count;           // elements the statistics cover (untrimmed length * C)
+  const float* gamma;     // [C]
+  const float* beta;      // [C]
+};
+// out = act(GN(a) [+ GN(b)]), elementwise over [n_items][rows][C]
+int launch_gn_apply(const GnSrc& a, const GnSrc* b, float* out, int n_items, long long rows, int C, int out_elu,
+                    float eps, cudaStream_t s);
+int launch_overlap_add(const float* frames, const int* seg_lens, long long batch, int channels, int n_seg,
+                       int seg_len, int stride, float* out, long long total, cudaStream_t s);
+
+// ------------------------------------------------------------------------------------------------
+// lstm.cu
+// ------------------------------------------------------------------------------------------------
+// Pre-gates pre[b][t][4H] (input projection + both biases already added) -> h sequence.
+// w_hh_packed: per-CTA slices prepared by launch_pack_lstm_whh. If skip != nullptr the written output is
+// act(h + skip) (SLSTM skip connection, lstm.py:25-26) and the raw h stays in the recurrent state only.
+int lstm_recurrent_workspace_floats(int batch);
+int launch_pack_lstm_whh(const float* w_hh, float* packed, int H, cudaStream_t s);
+int launch_lstm_recurrent(const float* pre, const float* w_hh_packed, const float* skip, float* out, int batch,
+                          int T, int H, int out_elu, float* workspace, cudaStream_t s);
+
+// ------------------------------------------------------------------------------------------------
+// rvq.cu
+// ------------------------------------------------------------------------------------------------
+int launch_rvq_prepare(const float* codebooks, long long n_q, long long bins, int dim, float* e2, cudaStream_t s);
+int launch_rvq_encode(const float* frames, long long n, const float* codebooks, const float* e2, int n_q, int bins,
+                      long long* codes, float* quantized, float* stack, cudaStream_t s);
+int launch_rvq_decode(const long long* codes, long long n, const float* codebooks, int n_q, int bins,
+                      float* quantized, cudaStream_t s);
+
+}  // namespace ecb

@@ -1,0 +1,139 @@
+/*
+ * encodec_b200.h -- C ABI of the B200-native EnCodec codec forward pass.
+ *
+ * The reference (ellen660/encodec, a fork of facebookresearch/encodec 0.1.2a3) is 100% Python: it has
+ * no FFI / plugin interface for this path. The drop-in boundary is therefore its
+ * Python nn.Module surface, mirrored by the `encodec_b200` package, which binds the entry points below
+ * with ctypes (see INTEGRATION.md for the stub a reference maintainer would add). Each entry point
+ * cites the reference code whose arithmetic it replaces (paths relative to /root/reference/encodec).
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; `ecb_last_error()` then returns a
+ *     thread-local message. Nothing here calls exit()/abort().
+ *   - all tensor pointers are DEVICE pointers on the current CUDA device, fp32 unless noted,
+ *     contiguous, in the REFERENCE's boundary layouts ([B, C, T] channels-first; codes int64).
+ *     Channels-last layouts are internal to the library.
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises.
+ *   - `workspace` is caller-owned scratch of at least the size the matching *_workspace_bytes query
+ *     returned; it may be reused across calls on the same stream.
+ */
+#ifndef ENCODEC_B200_H
+#define ENCODEC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ECB_MAX_RATIOS 8
+
+/* Hyper-parameters of SEANetEncoder/SEANetDecoder (modules/seanet.py:92-96,176-182) and
+ * ResidualVectorQuantizer (quantization/vq.py:46-56) that reach the kernels. */
+typedef struct ecb_spec {
+  int32_t channels;             /* audio channels, 1 or 2 */
+  int32_t causal;               /* 1: causal padding/trim rules, 0: asymmetric (conv.py:211-219,252-262) */
+  int32_t group_norm;           /* 0: weight_norm (folded at load), 1: time_group_norm = GroupNorm(1, C) */
+  int32_t n_filters;            /* 32 */
+  int32_t dimension;            /* latent dimension, 128 */
+  int32_t n_ratios;             /* number of up/down-sampling stages */
+  int32_t ratios[ECB_MAX_RATIOS]; /* decoder order, e.g. {8,5,4,2}; the encoder uses them reversed */
+  int32_t kernel_size;          /* 7 */
+  int32_t last_kernel_size;     /* 7 */
+  int32_t residual_kernel_size; /* 3 */
+  int32_t compress;             /* 2 */
+  int32_t lstm_layers;          /* 2 (0 disables the SLSTM) */
+  int32_t bins;                 /* codebook size, 1024 */
+  int32_t n_q;                  /* number of RVQ layers held (n_q_max) */
+} ecb_spec;
+
+typedef struct ecb_codec ecb_codec; /* opaque: prepared (folded, repacked) weights on one device */
+
+const char* ecb_last_error(void);
+int ecb_version(void);
+
+/* ---- lifetime ------------------------------------------------------------------------------- */
+int ecb_codec_create(const ecb_spec* spec, ecb_codec** out);
+void ecb_codec_destroy(ecb_codec* codec);
+
+/* ---- weights: replaces nn.Module.load_state_dict + the per-forward weight_norm hook ----------------
+ * `key` is a reference state_dict key, e.g. "encoder.model.3.conv.conv.weight_g",
+ * "decoder.model.6.convtr.convtr.weight_v", "encoder.model.13.lstm.weight_hh_l0",
+ * "decoder.model.15.conv.conv.weight", "encoder.model.0.conv.norm.weight",
+ * "quantizer.vq.layers.7._codebook.embed". `data` is a device pointer holding `numel` floats in the
+ * reference's shape. Unknown keys that belong to training state (cluster_size, embed_avg, inited)
+ * are accepted and ignored; any other unknown key is an error. */
+int ecb_codec_load_tensor(ecb_codec* codec, const char* key, const float* data, int64_t numel, void* stream);
+/* Folds weight-norm (conv.py:28-29: w = g * v / ||v||, norm over all dims but 0), repacks every
+ * conv / convtr / LSTM weight into the kernels' layouts and precomputes ||E||^2 per codebook entry.
+ * Fails if a tensor the spec requires was never loaded. */
+int ecb_codec_finalize(ecb_codec* codec, void* stream);
+
+/* ---- SEANetEncoder.forward (modules/seanet.py:145-146; SConv1d conv.py:202-221; SLSTM lstm.py:22-28)
+ * x: `n_items` items; item i starts at x + (i / n_seg) * x_batch_stride + (i % n_seg) * x_seg_stride,
+ * channel c at + c * x_chan_stride, `length` samples each (this is how the 48 kHz model's overlapping
+ * segments, model.py:168-170, are read in place). If `scale_out` != NULL the per-item loudness scale of
+ * EncodecModel._encode_frame (model.py:180-185) is computed, written to scale_out[n_items] and the input
+ * is divided by it on the fly. emb_out: [n_items, dimension, T_f] channels-first, T_f = ceil(length/hop).
+ * If emb_frames_out != NULL the same values are also written frames-major [n_items * T_f, dimension]. */
+size_t ecb_encoder_workspace_bytes(const ecb_codec* codec, int64_t n_items, int64_t length);
+int ecb_encoder_forward(ecb_codec* codec, const float* x, int64_t n_items, int64_t n_seg, int64_t length,
+                        int64_t x_batch_stride, int64_t x_seg_stride, int64_t x_chan_stride,
+                        float* scale_out, float* emb_out, float* emb_frames_out,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- SEANetDecoder.forward (modules/seanet.py:242-253; SConvTranspose1d conv.py:241-263) -----------
+ * Exactly one of z ([n_items, dimension, T_f] channels-first) / z_frames ([n_items*T_f, dimension]) is
+ * non-NULL. out: [n_items, channels, T_f * hop]. If `scale` != NULL, out[i] *= scale[i]
+ * (EncodecModel._decode_frame, model.py:244-245). */
+size_t ecb_decoder_workspace_bytes(const ecb_codec* codec, int64_t n_items, int64_t n_frames);
+int ecb_decoder_forward(ecb_codec* codec, const float* z, const float* z_frames, int64_t n_items,
+                        int64_t n_frames, const float* scale, float* out,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- ResidualVectorQuantization.forward / encode (quantization/core_vq.py:385-432) with
+ *      EuclideanCodebook.quantize / dequantize (core_vq.py:178-202) fused per layer ------------------
+ * Stand-alone form: frames [n, dim] (frames-major), codebooks [n_q, bins, dim], e2 [n_q, bins] = ||E||^2
+ * (from ecb_rvq_prepare). codes [n_q, n] int64; quantized [n, dim] or NULL; quantized_stack
+ * [n_q, n, dim] or NULL (vq.py:80-89 intermediate_results). dim must be 128. */
+int ecb_rvq_prepare(const float* codebooks, int64_t n_q, int64_t bins, int64_t dim, float* e2, void* stream);
+int ecb_rvq_encode_frames(const float* frames, int64_t n, int64_t dim, const float* codebooks, const float* e2,
+                          int64_t n_q, int64_t bins, int64_t* codes, float* quantized, float* quantized_stack,
+                          void* stream);
+/* ResidualVectorQuantization.decode (core_vq.py:434-445): quantized[n, dim] = sum_i E_i[codes[i, n]],
+ * summed in layer order. */
+int ecb_rvq_decode_frames(const int64_t* codes, int64_t n, int64_t dim, const float* codebooks, int64_t n_q,
+                          int64_t bins, float* quantized, void* stream);
+/* Same, on a codec's own codebooks (loaded through ecb_codec_load_tensor), in the reference's layouts:
+ * x [B, dim, T] -> codes [n_q, B, T] int64, quantized [B, dim, T]; optional frames-major copy of
+ * quantized for the decoder; optional stack [n_q, B, dim, T]. x_frames (frames-major) may be given
+ * instead of x. */
+size_t ecb_codec_rvq_workspace_bytes(const ecb_codec* codec, int64_t batch, int64_t n_frames);
+int ecb_codec_rvq_forward(ecb_codec* codec, const float* x, const float* x_frames, int64_t batch,
+                          int64_t n_frames, int64_t n_q, int64_t* codes, float* quantized,
+                          float* quantized_frames, float* quantized_stack,
+                          void* workspace, size_t workspace_bytes, void* stream);
+int ecb_codec_rvq_decode(ecb_codec* codec, const int64_t* codes, int64_t batch, int64_t n_frames, int64_t n_q,
+                         float* quantized, float* quantized_frames, void* stream);
+
+/* ---- utils._linear_overlap_add (utils.py:17-56) ------------------------------------------------------
+ * frames: [batch, n_seg, channels, seg_len]; segment s holds seg_lens[s] <= seg_len valid samples (the
+ * rest of its row is ignored) and starts at output offset s * stride. seg_lens is a DEVICE int32 array.
+ * The triangle weight is built for seg_len (the first frame's length), a shorter frame uses its head,
+ * exactly as utils.py:45-54. out: [batch, channels, total],
+ * total = stride * (n_seg - 1) + seg_lens[n_seg - 1]. Requires stride * 2 >= seg_len. */
+int ecb_overlap_add(const float* frames, const int32_t* seg_lens, int64_t batch, int64_t channels, int64_t n_seg,
+                    int64_t seg_len, int64_t stride, float* out, int64_t total, void* stream);
+
+/* ---- layout helpers ([B, C, T] <-> [B, T, C]) -------------------------------------------------------- */
+int ecb_transpose_bct_to_btc(const float* in, float* out, int64_t batch, int64_t chans, int64_t len, void* stream);
+int ecb_transpose_btc_to_bct(const float* in, float* out, int64_t batch, int64_t len, int64_t chans, void* stream);
+
+/* Number of kernel launches issued by this library since process start (bench.py's gpu_launches). */
+int64_t ecb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ENCODEC_B200_H */
