@@ -31,6 +31,7 @@ SIGNATURES = {
     "ecb_last_error": (C.c_char_p, []),
     "ecb_version": (C.c_int, []),
     "ecb_launch_count": (C.c_int64, []),
+    "ecb_debug_tap": (None, [C.c_void_p, C.c_int64, C.c_int32]),
     "ecb_codec_create": (C.c_int, [C.POINTER(EcbSpec), C.POINTER(C.c_void_p)]),
     "ecb_codec_destroy": (None, [C.c_void_p]),
     "ecb_codec_load_tensor": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_void_p]),

@@ -273,6 +273,22 @@ Plan make_plan(const ecb_codec* c, long long n_items, long long length) {
   return p;
 }
 
+// Diagnostic tap (tests only): copy the activation produced by one stage into a caller buffer.
+struct Tap {
+  float* buf = nullptr;
+  long long cap = 0;
+  int stage = -1;
+};
+Tap g_tap;
+
+int tap(cudaStream_t st, int stage, const float* act, long long n) {
+  if (g_tap.buf && g_tap.stage == stage) {
+    const long long m = n < g_tap.cap ? n : g_tap.cap;
+    ECB_CUDA(cudaMemcpyAsync(g_tap.buf, act, sizeof(float) * (size_t)m, cudaMemcpyDeviceToDevice, st));
+  }
+  return 0;
+}
+
 struct Ctx {
   ecb_codec* c;
   cudaStream_t st;
@@ -513,6 +529,11 @@ extern "C" {
 const char* ecb_last_error(void) { return g_err.c_str(); }
 int ecb_version(void) { return 1; }
 int64_t ecb_launch_count(void) { return (int64_t)g_launches.load(); }
+void ecb_debug_tap(float* buf, int64_t capacity, int32_t stage) {
+  g_tap.buf = buf;
+  g_tap.cap = capacity;
+  g_tap.stage = buf ? stage : -1;
+}
 
 int ecb_codec_create(const ecb_spec* spec, ecb_codec** out) {
   ECB_REQUIRE(spec && out, "null argument");
@@ -665,9 +686,14 @@ int ecb_encoder_forward(ecb_codec* c, const float* xin, int64_t n_items, int64_t
     if (launch_gn_apply(a, nullptr, A, x.n_items, length, s.n_filters, 0, 1e-5f, x.st)) return 1;
   }
   long long T = length;
+  if (tap(x.st, 0, A, n_items * T * s.n_filters)) return 1;
+  int ch = s.n_filters;
   for (int i = 0; i < s.n_ratios; ++i) {
     if (run_res(x, c->enc_res[i], A, T, B, D, C)) return 1;              // A -> C (post-ELU)
+    if (tap(x.st, 1 + 2 * i, C, n_items * T * ch)) return 1;
     if (run_conv(x, c->enc_down[i], C, T, 0, A, 0, &T)) return 1;        // C -> A (raw)
+    ch *= 2;
+    if (tap(x.st, 2 + 2 * i, A, n_items * T * ch)) return 1;
   }
   const float* top = A;
   int top_elu_pending = 1;  // the ELU before the last conv (seanet.py:138)
@@ -675,6 +701,7 @@ int ecb_encoder_forward(ecb_codec* c, const float* xin, int64_t n_items, int64_t
     if (run_lstm(x, c->enc_lstm, 512, A, T, B, C)) return 1;             // A -> C = ELU(lstm(A) + A)
     top = C;
     top_elu_pending = 0;
+    if (tap(x.st, 50, C, n_items * T * ch)) return 1;
   }
   float* frames = emb_frames_out ? emb_frames_out : B;
   if (run_conv(x, c->enc_out, top, T, top_elu_pending, frames, 0, nullptr)) return 1;
@@ -708,10 +735,12 @@ int ecb_decoder_forward(ecb_codec* c, const float* z, const float* z_frames, int
     z_frames = C;
   }
   if (run_conv(x, c->dec_in, z_frames, T, 0, A, 0, nullptr)) return 1;        // -> A raw [T][512]
+  if (tap(x.st, 100, A, n_items * T * c->dec_in.c_out)) return 1;
   const float* cur = A;
   if (s.lstm_layers) {
     if (run_lstm(x, c->dec_lstm, 512, A, T, B, C)) return 1;                  // -> C = ELU(lstm(A) + A)
     cur = C;
+    if (tap(x.st, 101, C, n_items * T * 512)) return 1;
   } else {
     // no LSTM: the ELU before the first transposed conv still has to happen; fold it into a copy-free path
     set_error("decoder without LSTM is not supported yet");
@@ -721,8 +750,10 @@ int ecb_decoder_forward(ecb_codec* c, const float* z, const float* z_frames, int
     float* up = (cur == A) ? C : A;
     if (run_convtr(x, c->dec_up[i], cur, T, up)) return 1;                    // cur -> up (raw)
     T *= c->dec_up[i].stride;
+    if (tap(x.st, 102 + 2 * i, up, n_items * T * c->dec_up[i].c_out)) return 1;
     float* res_out = (up == A) ? C : A;
     if (run_res(x, c->dec_res[i], up, T, B, D, res_out)) return 1;            // up -> res_out (post-ELU)
+    if (tap(x.st, 103 + 2 * i, res_out, n_items * T * c->dec_up[i].c_out)) return 1;
     cur = res_out;
   }
   ConvOutParams co;

@@ -130,6 +130,12 @@ int ecb_overlap_add(const float* frames, const int32_t* seg_lens, int64_t batch,
 int ecb_transpose_bct_to_btc(const float* in, float* out, int64_t batch, int64_t chans, int64_t len, void* stream);
 int ecb_transpose_btc_to_bct(const float* in, float* out, int64_t batch, int64_t len, int64_t chans, void* stream);
 
+/* Diagnostic (tests only): the next encoder/decoder forward copies the channels-last activation produced by
+ * `stage` (encoder: 0 first conv, 1+2i residual block i (after ELU), 2+2i down-sampling conv i, 50 LSTM (after
+ * skip + ELU); decoder: 100 first conv, 101 LSTM, 102+2i transposed conv i, 103+2i residual block i) into
+ * buf (at most `capacity` floats). buf == NULL disables the tap. */
+void ecb_debug_tap(float* buf, int64_t capacity, int32_t stage);
+
 /* Number of kernel launches issued by this library since process start (bench.py's gpu_launches). */
 int64_t ecb_launch_count(void);
 

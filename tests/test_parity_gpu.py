@@ -1,0 +1,271 @@
+"""GPU parity: the CUDA path (through the C ABI) against the reference's golden outputs and the oracle.
+
+Tolerances (BASELINE.json north_star): RVQ codes bit-exact except fp64-verified near-ties with relative
+distance gap < 1e-5 (counted); decoded audio within 1e-3 max-abs / 1e-4 RMS of the reference.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import encodec_oracle as orc
+from tests import golden_cases as gc
+from tests import util_gpu as ug
+
+pytestmark = pytest.mark.gpu
+
+AUDIO_MAX_ABS = 1e-3
+AUDIO_RMS = 1e-4
+
+
+def _oracle_elu(x):
+    return orc.elu(x.astype(np.float32))
+
+
+@pytest.mark.parametrize("name", gc.MODEL_CASES)
+def test_encoder_stages_match_oracle(name):
+    """Every stage of the encoder stack against the oracle's taps (first segment only, for speed)."""
+    case = gc.load_model_case(name)
+    spec = case["spec"]
+    m = ug.build_model(spec, case["sd"], case["bandwidth"], case["distinct"])
+    seg = spec.segment_length or case["x"].shape[-1]
+    x = case["x"][:, :, :seg]
+    if spec.normalize:
+        mono = x.mean(axis=1, keepdims=True)
+        x = (x / (1e-8 + np.sqrt((mono ** 2).mean(axis=2, keepdims=True)))).astype(np.float32)
+    taps = {}
+    p = orc.Params(case["sd"], np.float32)
+    emb_o = orc.seanet_encoder(x, p, spec, taps)
+    xt = torch.from_numpy(x).cuda()
+    bsz = x.shape[0]
+    stages = []
+    idx = 1
+    for i in range(len(spec.ratios)):
+        stages.append((1 + 2 * i, f"encoder.model.{idx}", True))
+        stages.append((2 + 2 * i, f"encoder.model.{idx + 2}", False))
+        idx += 3
+    stages.append((50, f"encoder.model.{idx}", True))
+    worst = 0.0
+    for stage, key, post_elu in stages:
+        ref = taps[key]
+        if post_elu:
+            ref = _oracle_elu(ref)
+        ref_cl = np.ascontiguousarray(np.transpose(ref, (0, 2, 1)))  # channels-last
+        got = ug.tap_stage(lambda: m.encoder(xt), stage, ref_cl.size).reshape(ref_cl.shape)
+        err = ug.rel_err(got, ref_cl)
+        worst = max(worst, err)
+        assert err < 2e-5, (name, stage, key, err)
+    emb = m.encoder(xt).cpu().numpy()
+    assert ug.rel_err(emb, emb_o) < 2e-5
+    assert emb.shape == (bsz, spec.dimension, -(-seg // spec.hop_length))
+
+
+@pytest.mark.parametrize("name", gc.MODEL_CASES)
+def test_decoder_stages_match_oracle(name):
+    case = gc.load_model_case(name)
+    spec = case["spec"]
+    m = ug.build_model(spec, case["sd"], case["bandwidth"], case["distinct"])
+    t_f = -(-(spec.segment_length or case["x"].shape[-1]) // spec.hop_length)
+    z = np.ascontiguousarray(case["quantized"][:, :, :t_f])
+    taps = {}
+    p = orc.Params(case["sd"], np.float32)
+    out_o = orc.seanet_decoder(z, p, spec, taps)
+    zt = torch.from_numpy(z).cuda()
+    stages = [(101, "decoder.model.1", True)]
+    idx = 2
+    for i in range(len(spec.ratios)):
+        stages.append((102 + 2 * i, f"decoder.model.{idx + 1}", False))
+        stages.append((103 + 2 * i, f"decoder.model.{idx + 2}", True))
+        idx += 3
+    for stage, key, post_elu in stages:
+        ref = taps[key]
+        if post_elu:
+            ref = _oracle_elu(ref)
+        ref_cl = np.ascontiguousarray(np.transpose(ref, (0, 2, 1)))
+        got = ug.tap_stage(lambda: m.decoder(zt), stage, ref_cl.size).reshape(ref_cl.shape)
+        err = ug.rel_err(got, ref_cl)
+        assert err < 5e-5, (name, stage, key, err)
+    out = m.decoder(zt).cpu().numpy()
+    assert out.shape == out_o.shape
+    assert np.abs(out - out_o).max() < 1e-4
+
+
+@pytest.mark.parametrize("name", gc.MODEL_CASES)
+def test_forward_matches_reference_golden(name):
+    """EncodecModel.forward against the unmodified reference's outputs."""
+    case = gc.load_model_case(name)
+    spec = case["spec"]
+    m = ug.build_model(spec, case["sd"], case["bandwidth"], case["distinct"])
+    x = torch.from_numpy(case["x"]).cuda()
+    audio, codes, commit, cbl = m(x)
+    torch.cuda.synchronize()
+    assert audio.shape == x.shape and audio.dtype == torch.float32
+    assert tuple(codes.shape) == case["codes"].shape and codes.dtype == torch.int64
+    assert tuple(commit.shape) == case["commit_loss_shape"] and float(commit.abs().sum()) == 0.0
+    assert commit.shape == cbl.shape
+    n_q = case["n_q"]
+    ref_c = np.transpose(case["codes"], (1, 0, 2)).reshape(n_q, -1)
+    got_c = np.transpose(codes.cpu().numpy(), (1, 0, 2)).reshape(n_q, -1)
+    score = orc.score_codes(gc.frames_of(case["emb"]), orc.codebooks_from_state_dict(case["sd"], n_q), ref_c, got_c)
+    print(f"\n[{name}] code score vs reference: {score}")
+    assert score["hard"] == 0, score
+    assert score["near_tie"] <= max(2, 1e-3 * score["compared"]), score
+    diff = np.abs(audio.cpu().numpy() - case["audio"])
+    if score["mismatched"] == 0:
+        print(f"[{name}] audio max-abs {diff.max():.3e} rms {np.sqrt((diff ** 2).mean()):.3e}")
+        assert diff.max() < AUDIO_MAX_ABS
+        assert np.sqrt((diff ** 2).mean()) < AUDIO_RMS
+    # decoder on the REFERENCE's quantized latents (teacher-forced audio check), all segments
+    frames = m.encode(x)
+    off = 0
+    forced = []
+    for f in frames:
+        t_f = f["quantized"].shape[-1]
+        g = dict(f)
+        g["quantized"] = torch.from_numpy(np.ascontiguousarray(case["quantized"][:, :, off:off + t_f])).cuda()
+        if spec.normalize:
+            g["scale"] = torch.from_numpy(np.ascontiguousarray(case["scale"][:, len(forced):len(forced) + 1])).cuda()
+        forced.append(g)
+        off += t_f
+    audio_tf = m.decode(forced)[:, :, :x.shape[-1]].cpu().numpy()
+    d2 = np.abs(audio_tf - case["audio"])
+    print(f"[{name}] teacher-forced audio max-abs {d2.max():.3e} rms {np.sqrt((d2 ** 2).mean()):.3e}")
+    assert d2.max() < AUDIO_MAX_ABS and np.sqrt((d2 ** 2).mean()) < AUDIO_RMS
+    if spec.normalize:
+        scale = torch.cat([f["scale"] for f in frames], dim=-1).cpu().numpy()
+        np.testing.assert_allclose(scale, case["scale"], rtol=2e-6)
+
+
+def test_rvq_c_abi_matches_core_vq_golden():
+    """ecb_rvq_encode_frames / decode against core_vq.ResidualVectorQuantization.encode (config-4 shape)."""
+    from encodec_b200 import _native as nat
+    case = gc.load_rvq_case()
+    n, d = case["frames"].shape
+    n_q, bins = case["n_q"], case["bins"]
+    frames = torch.from_numpy(case["frames"]).cuda()
+    cbs = torch.from_numpy(case["codebooks"]).cuda()
+    e2 = torch.empty((n_q, bins), device="cuda")
+    codes = torch.empty((n_q, n), dtype=torch.int64, device="cuda")
+    quant = torch.empty((n, d), device="cuda")
+    stack = torch.empty((n_q, n, d), device="cuda")
+    st = nat.stream_ptr(frames.device)
+    nat.check(nat.lib.ecb_rvq_prepare(cbs.data_ptr(), n_q, bins, d, e2.data_ptr(), st))
+    nat.check(nat.lib.ecb_rvq_encode_frames(frames.data_ptr(), n, d, cbs.data_ptr(), e2.data_ptr(), n_q, bins,
+                                            codes.data_ptr(), quant.data_ptr(), stack.data_ptr(), st))
+    torch.cuda.synchronize()
+    got = codes.cpu().numpy()
+    score = orc.score_codes(case["frames"], case["codebooks"], case["codes"], got)
+    print(f"\n[rvq] code score vs core_vq: {score}")
+    assert score["hard"] == 0, score
+    assert score["mismatched"] <= 8, score
+    same = (got == case["codes"]).all(axis=0)
+    q = quant.cpu().numpy()
+    head = np.nonzero(same[:256])[0]
+    np.testing.assert_array_equal(q[head], case["quantized_head"].T[head])
+    # gather-sum identity: decode(codes) == quantized bit-for-bit, and the stack sums to it in layer order
+    dec = torch.empty((n, d), device="cuda")
+    nat.check(nat.lib.ecb_rvq_decode_frames(codes.data_ptr(), n, d, cbs.data_ptr(), n_q, bins, dec.data_ptr(), st))
+    torch.cuda.synchronize()
+    assert torch.equal(dec, quant)
+    acc = torch.zeros_like(quant)
+    for l in range(n_q):
+        acc = acc + stack[l]
+    assert torch.equal(acc, quant)
+    # decode of the REFERENCE codes equals the reference's decode
+    ref_codes = torch.from_numpy(case["codes"]).cuda()
+    nat.check(nat.lib.ecb_rvq_decode_frames(ref_codes.data_ptr(), n, d, cbs.data_ptr(), n_q, bins, dec.data_ptr(), st))
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(dec.cpu().numpy()[:256], case["decoded_head"].T)
+
+
+def test_quantizer_module_api():
+    import encodec_b200 as eb
+    case = gc.load_rvq_case()
+    n_q, bins, d = 8, case["bins"], case["dim"]
+    q = eb.ResidualVectorQuantizer(dimension=d, n_q=n_q, bins=bins, codebook_dim=d, share_codebook=False)
+    with pytest.raises(RuntimeError):
+        q.cuda().encode(torch.zeros(1, d, 4, device="cuda"), 75, None)  # inited == 0 -> no silent k-means
+    for i, layer in enumerate(q.vq.layers):
+        layer._codebook.embed.copy_(torch.from_numpy(case["codebooks"][i]))
+        layer._codebook.inited.fill_(1)
+    q = q.cuda()
+    x = torch.from_numpy(np.ascontiguousarray(case["frames"][:600].T.reshape(1, d, 600))).cuda()
+    x = torch.cat([x[:, :, :300], x[:, :, 300:]], dim=0)  # [2, D, 300]
+    res = q(x, 75, 3.0)  # 3 kbps at 75 fps -> n_q = 4
+    assert res.codes.shape == (4, 2, 300) and res.quantized.shape == (2, d, 300)
+    assert res.commit_loss.shape == (4, 1) and res.codebook_loss is res.commit_loss
+    assert float(res.bandwidth) == pytest.approx(4 * 10 * 75)
+    o_q, o_codes, o_stack = orc.rvq_forward(x.cpu().numpy(), case["codebooks"], 4)
+    assert (res.codes.cpu().numpy() == o_codes).mean() > 0.999
+    codes = q.encode(x, 75, None)
+    assert codes.shape == (n_q, 2, 300)
+    dec = q.decode(codes)
+    full = q(x, 75, None)
+    assert torch.equal(dec, full.quantized)
+    inter = q.intermediate_results(x, 4)
+    assert inter["quantized_stack"].shape == (4, 2, d, 300)
+    assert torch.equal(inter["quantized"], res.quantized) and torch.equal(inter["codes"], res.codes)
+    if (res.codes.cpu().numpy() == o_codes).all():
+        np.testing.assert_array_equal(inter["quantized_stack"].cpu().numpy(), o_stack)
+
+
+def test_model_api_contract():
+    """Fork API (SURVEY deltas D1-D4) + the upstream tuple superset on decode."""
+    case = gc.load_model_case("cfg1_24k_6kbps_shared")
+    spec = case["spec"]
+    m = ug.build_model(spec, case["sd"], case["bandwidth"], case["distinct"])
+    x = torch.from_numpy(case["x"]).cuda()
+    frames = m.encode(x)
+    assert isinstance(frames, list) and len(frames) == 1
+    f = frames[0]
+    assert set(f.keys()) == {"quantized", "codes", "soft_targets", "commit_loss", "codebook_loss", "scale"}
+    assert f["codes"].shape == (1, 8, 75) and f["quantized"].shape == (1, 128, 75)
+    assert f["soft_targets"] is None and f["scale"] is None and f["codebook_loss"] is f["commit_loss"]
+    a1 = m.decode(frames)
+    a2 = m.decode([dict(f)])  # a plain dict copy (slow path) must give the same audio
+    assert torch.equal(a1, a2)
+    a3 = m.decode([(f["codes"], None)])  # upstream tuple API: decode from codes
+    assert torch.equal(a1, a3)
+    with pytest.raises(ValueError):
+        m.set_target_bandwidth(7.0)
+    with pytest.raises(RuntimeError):
+        m(case["x"] if isinstance(case["x"], torch.Tensor) else torch.from_numpy(case["x"]))  # CPU tensor: no fallback
+    assert m.frame_rate == 75 and m.bits_per_codebook == 10 and m.segment_length is None
+
+
+def test_batch_invariance_and_determinism():
+    """Size-independent properties at a larger size: an item's result does not depend on its batch mates,
+    and two runs are bit-identical."""
+    case = gc.load_model_case("24k_24kbps_ragged")
+    spec = case["spec"]
+    m = ug.build_model(spec, case["sd"], 6.0, case["distinct"])
+    from encodec_b200 import synth
+    x = torch.from_numpy(synth.make_audio(77, 6, 1, 48000)).cuda()
+    a, c, _, _ = m(x)
+    a2, c2, _, _ = m(x)
+    assert torch.equal(a, a2) and torch.equal(c, c2)
+    a1, c1, _, _ = m(x[2:3])
+    assert torch.equal(c1, c[2:3])
+    assert torch.equal(a1, a[2:3])
+
+
+def test_48k_segment_edge_cases():
+    """One exact segment, a length that gives two trailing short segments, and mono-compatible stereo input."""
+    case = gc.load_model_case("48k_24kbps_3seg")
+    spec = case["spec"]
+    m = ug.build_model(spec, case["sd"], 6.0, case["distinct"])
+    from encodec_b200 import synth
+    for length in (48000, 95500, 47520 * 2 + 700):
+        xn = synth.make_audio(5, 1, 2, length)
+        audio, codes, commit, _ = m(torch.from_numpy(xn).cuda())
+        o_audio, o_codes, o_frames = orc.forward(xn, case["sd"], spec, 6.0, np.float32)
+        assert audio.shape == (1, 2, length) and tuple(codes.shape) == o_codes.shape
+        assert commit.shape == (4, len(o_frames))
+        n_q = 4
+        emb_o = np.concatenate([f["emb"] for f in o_frames], axis=-1)
+        score = orc.score_codes(gc.frames_of(emb_o), orc.codebooks_from_state_dict(case["sd"], n_q),
+                                np.transpose(o_codes, (1, 0, 2)).reshape(n_q, -1),
+                                np.transpose(codes.cpu().numpy(), (1, 0, 2)).reshape(n_q, -1))
+        assert score["hard"] == 0, (length, score)
+        if score["mismatched"] == 0:
+            d = np.abs(audio.cpu().numpy() - o_audio)
+            assert d.max() < AUDIO_MAX_ABS and np.sqrt((d ** 2).mean()) < AUDIO_RMS, (length, d.max())
