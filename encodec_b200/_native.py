@@ -26,12 +26,19 @@ class EcbSpec(C.Structure):
     ]
 
 
+class EcbProfEntry(C.Structure):
+    _fields_ = [("name", C.c_char * 32), ("launches", C.c_int64), ("ms", C.c_double), ("flops", C.c_double),
+                ("bytes", C.c_double)]
+
+
 # name -> (restype, argtypes); kept in one table so tests can check it against the header
 SIGNATURES = {
     "ecb_last_error": (C.c_char_p, []),
     "ecb_version": (C.c_int, []),
     "ecb_launch_count": (C.c_int64, []),
     "ecb_debug_tap": (None, [C.c_void_p, C.c_int64, C.c_int32]),
+    "ecb_profile_begin": (None, []),
+    "ecb_profile_end": (C.c_int, [C.POINTER(EcbProfEntry), C.c_int]),
     "ecb_codec_create": (C.c_int, [C.POINTER(EcbSpec), C.POINTER(C.c_void_p)]),
     "ecb_codec_destroy": (None, [C.c_void_p]),
     "ecb_codec_load_tensor": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_void_p]),
@@ -185,3 +192,15 @@ def shared_workspace(device: torch.device, nbytes: int) -> torch.Tensor:
 
 def release_workspaces() -> None:
     _WORKSPACES.clear()
+
+
+def profile_begin() -> None:
+    lib.ecb_profile_begin()
+
+
+def profile_end() -> dict:
+    """name -> dict(launches, ms, flops, bytes), summed over the launches since profile_begin()."""
+    arr = (EcbProfEntry * 16)()
+    n = lib.ecb_profile_end(arr, 16)
+    return {arr[i].name.decode(): dict(launches=int(arr[i].launches), ms=float(arr[i].ms), flops=float(arr[i].flops),
+                                       bytes=float(arr[i].bytes)) for i in range(n)}

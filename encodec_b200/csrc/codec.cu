@@ -23,6 +23,29 @@ void set_error(const char* fmt, ...) {
   g_err = buf;
 }
 
+// ---- per-kernel-class profiler -------------------------------------------------------------------
+struct ProfRec {
+  int cat;
+  cudaEvent_t a, b;
+  double flops, bytes;
+};
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static const char* kProfNames[PROF_NCAT] = {"conv_gemm", "conv_in", "conv_out", "lstm_recurrent", "rvq_encode",
+                                            "gn_apply", "misc"};
+bool prof_enabled() { return g_prof_on; }
+void prof_begin(int cat, cudaStream_t st, double flops, double bytes) {
+  ProfRec r;
+  r.cat = cat;
+  r.flops = flops;
+  r.bytes = bytes;
+  cudaEventCreate(&r.a);
+  cudaEventCreate(&r.b);
+  cudaEventRecord(r.a, st);
+  g_prof.push_back(r);
+}
+void prof_end(cudaStream_t st) { cudaEventRecord(g_prof.back().b, st); }
+
 namespace {
 
 struct DevBuf {
@@ -305,6 +328,7 @@ ConvSrc src_of(const float* ptr, int C, int taps, long long T, int elu) {
   s.C = C;
   s.taps = taps;
   s.T = (int)T;
+  s.T_ref = (int)T;
   s.elu = elu;
   return s;
 }
@@ -316,6 +340,7 @@ ConvSrc no_src() {
   s.C = 16;
   s.taps = 0;
   s.T = 0;
+  s.T_ref = 0;
   s.elu = 0;
   return s;
 }
@@ -341,6 +366,8 @@ int run_conv(Ctx& x, const ConvW& cw, const float* in, long long T_in, int in_el
   p.stride = cw.stride;
   p.pad_left = pad_left_of(s, cw.k, cw.stride);
   p.pad_zero = 0;
+  // right padding incl. the "extra" of get_extra_padding_for_conv1d (conv.py:55-62)
+  p.s0.T_ref = reflect_length(T_in, p.pad_left, (T_out - 1) * cw.stride + cw.k - p.pad_left - T_in);
   p.out_elu = s.group_norm ? 0 : out_elu;
   p.stats = s.group_norm ? x.stat[0] : nullptr;
   if (launch_conv_gemm(p, x.st)) return 1;
@@ -529,6 +556,37 @@ extern "C" {
 const char* ecb_last_error(void) { return g_err.c_str(); }
 int ecb_version(void) { return 1; }
 int64_t ecb_launch_count(void) { return (int64_t)g_launches.load(); }
+void ecb_profile_begin(void) {
+  for (auto& r : g_prof) {
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  g_prof.clear();
+  g_prof_on = true;
+}
+int ecb_profile_end(ecb_prof_entry* out, int capacity) {
+  g_prof_on = false;
+  ecb_prof_entry acc[PROF_NCAT];
+  for (int i = 0; i < PROF_NCAT; ++i) {
+    memset(&acc[i], 0, sizeof(acc[i]));
+    strncpy(acc[i].name, kProfNames[i], sizeof(acc[i].name) - 1);
+  }
+  for (auto& r : g_prof) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(r.b) == cudaSuccess) cudaEventElapsedTime(&ms, r.a, r.b);
+    acc[r.cat].launches += 1;
+    acc[r.cat].ms += ms;
+    acc[r.cat].flops += r.flops;
+    acc[r.cat].bytes += r.bytes;
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  g_prof.clear();
+  int n = 0;
+  for (int i = 0; i < PROF_NCAT && n < capacity; ++i)
+    if (acc[i].launches) out[n++] = acc[i];
+  return n;
+}
 void ecb_debug_tap(float* buf, int64_t capacity, int32_t stage) {
   g_tap.buf = buf;
   g_tap.cap = capacity;
@@ -669,6 +727,7 @@ int ecb_encoder_forward(ecb_codec* c, const float* xin, int64_t n_items, int64_t
   ci.C_in = s.channels;
   ci.K = c->enc_in.k;
   ci.pad_left = pad_left_of(s, c->enc_in.k, 1);
+  ci.T_ref = reflect_length(length, ci.pad_left, c->enc_in.k - 1 - ci.pad_left);
   ci.scale = scale_out;
   ci.w = c->enc_in.w;
   ci.bias = c->enc_in.bias;
@@ -763,6 +822,7 @@ int ecb_decoder_forward(ecb_codec* c, const float* z, const float* z_frames, int
   co.C_out = s.channels;
   co.K = c->dec_out.k;
   co.pad_left = pad_left_of(s, c->dec_out.k, 1);
+  co.T_ref = reflect_length(T, co.pad_left, c->dec_out.k - 1 - co.pad_left);
   co.w = c->dec_out.w;
   co.bias = c->dec_out.bias;
   co.scale = scale;

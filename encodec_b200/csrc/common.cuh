@@ -21,6 +21,23 @@ extern std::atomic<long long> g_launches;
     }                                                                                               \
   } while (0)
 
+// Optional per-kernel-class timing (bench.py's roofline leg): CUDA events recorded on the launching stream
+// around every launch while enabled; off by default (no events, no overhead).
+enum ProfCat { PROF_CONV_GEMM = 0, PROF_CONV_IN, PROF_CONV_OUT, PROF_LSTM_REC, PROF_RVQ, PROF_GN_APPLY, PROF_MISC, PROF_NCAT };
+bool prof_enabled();
+void prof_begin(int cat, cudaStream_t st, double flops, double bytes);
+void prof_end(cudaStream_t st);
+struct ProfScope {
+  cudaStream_t st;
+  bool on;
+  ProfScope(int cat, cudaStream_t s, double flops, double bytes) : st(s), on(prof_enabled()) {
+    if (on) prof_begin(cat, st, flops, bytes);
+  }
+  ~ProfScope() {
+    if (on) prof_end(st);
+  }
+};
+
 #define ECB_LAUNCHED()                                                                              \
   do {                                                                                              \
     ::ecb::g_launches.fetch_add(1, std::memory_order_relaxed);                                      \
@@ -56,6 +73,12 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 static inline long long cdiv(long long a, long long b) { return (a + b - 1) / b; }
 
+// Reflection length for a signal of T samples padded by (left, right): pad1d, reference conv.py:80-97.
+static inline int reflect_length(long long T, long long left, long long right) {
+  const long long max_pad = left > right ? left : right;
+  return (int)(T > max_pad ? T : max_pad + 1);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Generic channels-last implicit-GEMM convolution (conv_gemm.cu)
 // ------------------------------------------------------------------------------------------------
@@ -65,6 +88,8 @@ struct ConvSrc {
   int C;                  // channels, multiple of 16
   int taps;               // kernel taps (0: source unused)
   int T;                  // valid rows per item
+  int T_ref;              // reflection length: T, or max_pad + 1 when T <= max_pad (the reference then
+                          // zero-extends before reflecting, conv.py:88-95); rows in [T, T_ref) read as 0
   int elu;                // apply ELU while loading
 };
 
@@ -96,7 +121,7 @@ int conv_gemm_stat_slots(const ConvParams& p);  // gridDim.x*gridDim.y the launc
 struct ConvInParams {
   const float* x;
   long long batch_stride, seg_stride, chan_stride;
-  int n_seg, n_items, T, C_in, K, pad_left;
+  int n_seg, n_items, T, T_ref, C_in, K, pad_left;
   const float* scale;     // per item divisor or nullptr
   const float* w;         // [K*C_in][32]
   const float* bias;      // [32]
@@ -108,7 +133,7 @@ int conv_in_stat_slots(const ConvInParams& p);
 
 struct ConvOutParams {
   const float* in;        // [item][T][32]
-  int n_items, T, C_out, K, pad_left;
+  int n_items, T, T_ref, C_out, K, pad_left;
   const float* w;         // [K][32][C_out]
   const float* bias;      // [C_out]
   const float* scale;     // per item multiplier or nullptr

@@ -38,10 +38,12 @@ conv_in_kernel(const ConvInParams p) {
     for (int i = tid; i < span; i += EDGE_TILE) {
       int r = t0 + i - p.pad_left;
       float v = 0.f;
-      if (r - (p.T - 1) < p.T) {  // beyond that the row is out of this tile's valid outputs anyway
-        r = reflect_index(r, p.T);
-        v = __ldg(xb + (long long)c * p.chan_stride + r);
-        if (p.scale) v = v / sc;  // true division, as model.py:184
+      if (r - (p.T_ref - 1) < p.T_ref) {  // beyond that the row is out of this tile's valid outputs anyway
+        r = reflect_index(r, p.T_ref);
+        if (r < p.T) {
+          v = __ldg(xb + (long long)c * p.chan_stride + r);
+          if (p.scale) v = v / sc;  // true division, as model.py:184
+        }
       }
       xs[c][i] = v;
     }
@@ -129,9 +131,9 @@ conv_out_kernel(const ConvOutParams p) {
     const int q = f & 7;
     int r = t0 + i - p.pad_left;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (r - (p.T - 1) < p.T) {
-      r = reflect_index(r, p.T);
-      v = __ldg(reinterpret_cast<const float4*>(ib + (long long)r * NF + q * 4));
+    if (r - (p.T_ref - 1) < p.T_ref) {
+      r = reflect_index(r, p.T_ref);
+      if (r < p.T) v = __ldg(reinterpret_cast<const float4*>(ib + (long long)r * NF + q * 4));
     }
     *reinterpret_cast<float4*>(&xs[i * OUT_LD + q * 4]) = v;
   }
@@ -182,9 +184,11 @@ int conv_in_stat_slots(const ConvInParams& p) { return (int)cdiv(p.T, EDGE_TILE)
 int launch_conv_in(const ConvInParams& p, cudaStream_t stream) {
   ECB_REQUIRE(p.C_in >= 1 && p.C_in <= 2 && p.K * p.C_in <= MAX_TAPS && p.K <= 16,
               "conv_in: unsupported C_in=%d K=%d", p.C_in, p.K);
-  ECB_REQUIRE(p.T > p.K, "conv_in: input of %d samples is shorter than the reflect padding", p.T);
+  ECB_REQUIRE(p.T >= 1 && p.T_ref >= p.T && p.T_ref > p.K - 1, "conv_in: bad reflection length %d for T=%d", p.T_ref, p.T);
   ECB_REQUIRE(p.n_items > 0 && p.n_items <= 65535, "conv_in: bad item count %d", p.n_items);
   dim3 grid((unsigned)cdiv(p.T, EDGE_TILE), (unsigned)p.n_items);
+  const double rows_in = (double)p.T * p.n_items;
+  ProfScope prof(PROF_CONV_IN, stream, 2.0 * rows_in * NF * p.K * p.C_in, 4.0 * rows_in * (p.C_in + NF));
   conv_in_kernel<<<grid, EDGE_TILE, 0, stream>>>(p);
   ECB_LAUNCHED();
   return 0;
@@ -192,9 +196,11 @@ int launch_conv_in(const ConvInParams& p, cudaStream_t stream) {
 
 int launch_conv_out(const ConvOutParams& p, cudaStream_t stream) {
   ECB_REQUIRE(p.C_out >= 1 && p.C_out <= 2 && p.K <= 8, "conv_out: unsupported C_out=%d K=%d", p.C_out, p.K);
-  ECB_REQUIRE(p.T > p.K, "conv_out: input of %d samples is shorter than the reflect padding", p.T);
+  ECB_REQUIRE(p.T >= 1 && p.T_ref >= p.T && p.T_ref > p.K - 1, "conv_out: bad reflection length %d for T=%d", p.T_ref, p.T);
   ECB_REQUIRE(p.n_items > 0 && p.n_items <= 65535, "conv_out: bad item count %d", p.n_items);
   dim3 grid((unsigned)cdiv(p.T, EDGE_TILE), (unsigned)p.n_items);
+  const double rows_out = (double)p.T * p.n_items;
+  ProfScope prof(PROF_CONV_OUT, stream, 2.0 * rows_out * NF * p.K * p.C_out, 4.0 * rows_out * (p.C_out + NF));
   conv_out_kernel<<<grid, EDGE_TILE, 0, stream>>>(p);
   ECB_LAUNCHED();
   return 0;

@@ -91,7 +91,8 @@ conv_gemm_kernel(const ConvParams p) {
             if (p.pad_zero) {
               ok = (r >= 0) && (r < p.s0.T);
             } else {
-              r = reflect_index(r, p.s0.T);
+              r = reflect_index(r, p.s0.T_ref);
+              ok = r < p.s0.T;
             }
             if (ok) {
               v = __ldg(reinterpret_cast<const float4*>(in0 + (long long)r * p.s0.C + ci0 + c4 * 4));
@@ -266,13 +267,17 @@ int launch_conv_gemm(const ConvParams& p, cudaStream_t stream) {
   ECB_REQUIRE(p.M > 0 && p.n_items > 0 && p.n_items <= 65535, "conv_gemm: bad M=%d / items=%d", p.M, p.n_items);
   ECB_REQUIRE(p.out_lo % 4 == 0 && p.out_hi % 4 == 0, "conv_gemm: output window must be float4 aligned");
   if (!p.pad_zero) {
-    // reflect padding needs pad < T (the reference zero-extends shorter inputs, conv.py:88-95; unsupported here)
     const long long last = (long long)(p.M - 1) * p.stride + p.s0.taps - 1 - p.pad_left;
-    ECB_REQUIRE(p.pad_left < p.s0.T && last - (p.s0.T - 1) < p.s0.T,
-                "conv_gemm: input of %d samples is shorter than the reflect padding", p.s0.T);
+    ECB_REQUIRE(p.pad_left < p.s0.T_ref && last - (p.s0.T_ref - 1) < p.s0.T_ref && p.s0.T_ref >= p.s0.T,
+                "conv_gemm: reflection length %d too short for T=%d", p.s0.T_ref, p.s0.T);
   }
   Pick t = pick_tile(p);
   dim3 grid((unsigned)cdiv(p.M, t.bm), (unsigned)(p.N / t.bn), (unsigned)p.n_items);
+  const double kt = (double)p.s0.taps * p.s0.C + (double)p.s1.taps * p.s1.C;
+  const double rows = (double)p.M * p.n_items;
+  ProfScope prof(PROF_CONV_GEMM, stream, 2.0 * rows * p.N * kt,
+                 4.0 * (rows * p.stride * p.s0.C + rows * p.s1.taps * p.s1.C + kt * p.N +
+                        (double)(p.out_hi - p.out_lo) * p.n_items));
   if (t.bn == 128) {
     conv_gemm_kernel<128, 128, 8, 8><<<grid, TileCfg<128, 128, 8, 8>::THREADS, 0, stream>>>(p);
   } else if (t.bn == 64) {

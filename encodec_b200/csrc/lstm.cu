@@ -222,6 +222,8 @@ int launch_lstm_recurrent(const float* pre, const float* w_hh_packed, const floa
   // zero h_{-1} and the barrier counter
   ECB_CUDA(cudaMemsetAsync(workspace, 0, sizeof(float) * (size_t)batch * LH, s));
   ECB_CUDA(cudaMemsetAsync(p.bar, 0, 64 * sizeof(float), s));
+  const double bt = (double)batch * T;
+  ProfScope prof(PROF_LSTM_REC, s, 2.0 * bt * 4 * H * H, 4.0 * (bt * 4 * H + bt * H * (skip ? 2 : 1) + 4.0 * H * H));
   void* args[] = {(void*)&p};
   ECB_CUDA(cudaLaunchCooperativeKernel((void*)lstm_recurrent_kernel, dim3(L_CTAS), dim3(L_THREADS), args, smem, s));
   ECB_LAUNCHED();

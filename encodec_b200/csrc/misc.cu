@@ -240,12 +240,14 @@ int launch_transpose(const float* in, float* out, long long batch, int rows, int
   ECB_REQUIRE(batch > 0 && batch <= 65535, "transpose: bad batch %lld", batch);
   dim3 grid((unsigned)cdiv(cols, 32), (unsigned)cdiv(rows, 32), (unsigned)batch);
   ECB_REQUIRE(grid.y <= 65535, "transpose: too many rows");
+  ProfScope prof(PROF_MISC, s, 0.0, 8.0 * (double)batch * rows * cols);
   transpose_kernel<<<grid, dim3(32, 8), 0, s>>>(in, out, rows, cols);
   ECB_LAUNCHED();
   return 0;
 }
 int launch_segment_scale(const float* x, long long batch_stride, long long seg_stride, long long chan_stride,
                          int n_seg, int n_items, int T, int C, float* scale, cudaStream_t s) {
+  ProfScope prof(PROF_MISC, s, 0.0, 4.0 * (double)n_items * T * C);
   segment_scale_kernel<<<n_items, 512, 0, s>>>(x, batch_stride, seg_stride, chan_stride, n_seg, T, C, scale);
   ECB_LAUNCHED();
   return 0;
@@ -255,6 +257,7 @@ int launch_gn_apply(const GnSrc& a, const GnSrc* b, float* out, int n_items, lon
   ECB_REQUIRE(C % 4 == 0, "gn_apply: C=%d", C);
   const long long n4 = rows * C / 4;
   dim3 grid((unsigned)min(cdiv(n4, 256 * 4), 4096LL), (unsigned)n_items);
+  ProfScope prof(PROF_GN_APPLY, s, 0.0, 4.0 * (double)rows * C * n_items * (b ? 3 : 2));
   gn_apply_kernel<<<grid, 256, 0, s>>>(a, b ? *b : a, b ? 1 : 0, out, rows, C, out_elu, eps);
   ECB_LAUNCHED();
   return 0;
@@ -263,6 +266,7 @@ int launch_overlap_add(const float* frames, const int* seg_lens, long long batch
                        int seg_len, int stride, float* out, long long total, cudaStream_t s) {
   ECB_REQUIRE(batch * channels <= 65535, "overlap_add: batch*channels too large");
   dim3 grid((unsigned)min(cdiv(total, 256), 8192LL), (unsigned)(batch * channels));
+  ProfScope prof(PROF_MISC, s, 0.0, 8.0 * (double)batch * channels * total);
   overlap_add_kernel<<<grid, 256, 0, s>>>(frames, seg_lens, channels, n_seg, seg_len, stride, out, total);
   ECB_LAUNCHED();
   return 0;

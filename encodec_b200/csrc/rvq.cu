@@ -262,6 +262,8 @@ int launch_rvq_encode(const float* frames, long long n, const float* codebooks, 
   p.n = n;
   p.n_q = n_q;
   p.bins = bins;
+  ProfScope prof(PROF_RVQ, s, 2.0 * (double)n * n_q * bins * RD,
+                 4.0 * ((double)n * RD * (quantized ? 2 : 1) + (double)n_q * bins * RD) + 8.0 * (double)n * n_q);
   rvq_encode_kernel<<<(unsigned)cdiv(n, R_FT), R_THREADS, RVQ_SMEM, s>>>(p);
   ECB_LAUNCHED();
   return 0;

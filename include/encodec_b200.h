@@ -136,6 +136,21 @@ int ecb_transpose_btc_to_bct(const float* in, float* out, int64_t batch, int64_t
  * buf (at most `capacity` floats). buf == NULL disables the tap. */
 void ecb_debug_tap(float* buf, int64_t capacity, int32_t stage);
 
+/* Per-kernel-class timing for bench.py's roofline leg. Between ecb_profile_begin() and ecb_profile_end()
+ * every launch of this library is bracketed by CUDA events on its stream; ecb_profile_end() synchronises
+ * them and returns one entry per kernel class that ran: launch count, summed device milliseconds, and the
+ * summed ALGORITHMIC flops / bytes of those launches (2*M*N*K of the dense contraction; activations +
+ * weights read once, outputs written once). Returns the number of entries written. */
+typedef struct ecb_prof_entry {
+  char name[32];
+  int64_t launches;
+  double ms;
+  double flops;
+  double bytes;
+} ecb_prof_entry;
+void ecb_profile_begin(void);
+int ecb_profile_end(ecb_prof_entry* out, int capacity);
+
 /* Number of kernel launches issued by this library since process start (bench.py's gpu_launches). */
 int64_t ecb_launch_count(void);
 

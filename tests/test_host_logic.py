@@ -1,0 +1,100 @@
+"""Host-side logic of the drop-in classes (no GPU): key layout, bandwidth -> n_q, segmenting, errors."""
+import numpy as np
+import pytest
+import torch
+
+import encodec_b200 as eb
+from encodec_b200 import dist as ebdist
+from encodec_b200 import synth
+
+
+def _model(spec, **kw):
+    return eb.EncodecModel._get_model(spec.target_bandwidths, spec.sample_rate, spec.channels, causal=spec.causal,
+                                      model_norm=spec.norm, audio_normalize=spec.normalize, segment=spec.segment,
+                                      name="unset", ratios=spec.ratios, bins=spec.bins, dimension=spec.dimension, **kw)
+
+
+@pytest.mark.parametrize("spec", [synth.spec_24khz(), synth.spec_48khz()], ids=["24k", "48k"])
+def test_state_dict_layout_matches_reference(spec):
+    """synth.make_state_dict was loaded with strict=True into the reference (oracle/make_golden.py); the
+    drop-in must accept exactly the same keys and shapes."""
+    sd = synth.make_state_dict(spec, seed=3)
+    m = _model(spec, share_codebook=False)
+    own = m.state_dict()
+    assert set(own) == set(sd)
+    for k, v in sd.items():
+        assert tuple(own[k].shape) == tuple(v.shape), k
+    res = m.load_state_dict({k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in sd.items()}, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    assert len(sd) == (251 if spec.channels == 1 else 222)  # SURVEY.md section 8b [measured]
+
+
+def test_shared_codebook_aliases_like_the_fork():
+    m = _model(synth.spec_24khz())  # default share_codebook=True, fork delta D6
+    layers = m.quantizer.vq.layers
+    assert all(l is layers[0] for l in layers) and len(layers) == 32
+    assert len(m.state_dict()) == 251
+
+
+def test_bandwidth_to_n_q_and_attributes():
+    m24, m48 = _model(synth.spec_24khz()), _model(synth.spec_48khz())
+    assert (m24.frame_rate, m24.n_q, m24.bits_per_codebook) == (75, 32, 10)
+    assert (m48.frame_rate, m48.n_q, m48.segment_length, m48.segment_stride) == (150, 16, 48000, 47520)
+    got = [m24.quantizer.get_num_quantizers_for_bandwidth(75, bw) for bw in (1.5, 3., 6., 12., 24.)]
+    assert got == [2, 4, 8, 16, 32]  # README.md:167-171
+    assert [m48.quantizer.get_num_quantizers_for_bandwidth(150, bw) for bw in (3., 6., 12., 24.)] == [2, 4, 8, 16]
+    assert m24.quantizer.get_num_quantizers_for_bandwidth(75, None) == 32
+    with pytest.raises(ValueError):
+        m24.set_target_bandwidth(5.0)
+    m24.set_target_bandwidth(6)
+    assert m24.bandwidth == 6
+    assert m24.encoder.hop_length == 320 and m24.encoder.ratios == [2, 4, 5, 8] and m24.decoder.ratios == [8, 5, 4, 2]
+    stock = eb.EncodecModel.encodec_model_24khz()  # fork delta D5: 256-entry codebooks, 6 kbps -> n_q 10
+    assert stock.quantizer.bins == 256 and stock.quantizer.get_num_quantizers_for_bandwidth(75, 6.0) == 10
+
+
+def test_segmenting_matches_reference_loop():
+    m48 = _model(synth.spec_48khz())
+    segs, stride = m48._segments(1_440_000)  # BASELINE config 3: 30 s
+    assert stride == 47520 and len(segs) == 31 and segs[-1] == (30 * 47520, 14400)
+    assert all(l == 48000 for _, l in segs[:-1])
+    segs, _ = m48._segments(95500)  # two trailing short segments
+    assert segs == [(0, 48000), (47520, 47980), (95040, 460)]
+    m24 = _model(synth.spec_24khz())
+    assert m24._segments(24077) == ([(0, 24077)], 24077)
+
+
+def test_no_cpu_fallback_and_unsupported_hyperparameters():
+    m = _model(synth.spec_24khz())
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.zeros(1, 1, 24000))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m.encoder(torch.zeros(1, 1, 24000))
+    with pytest.raises(NotImplementedError):
+        eb.SEANetEncoder(norm="layer_norm")
+    with pytest.raises(NotImplementedError):
+        eb.SEANetEncoder(n_filters=64)
+    with pytest.raises(ValueError):
+        eb.SEANetEncoder(norm="time_group_norm", causal=True)  # reference conv.py:47-48
+    with pytest.raises(NotImplementedError):
+        eb.ResidualVectorQuantizer(dimension=128, codebook_dim=8)
+
+
+def test_shard_range_covers_everything():
+    for n in (1, 7, 64, 8192):
+        for world in (1, 2, 3, 8):
+            spans = [ebdist.shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [b - a for a, b in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_synth_is_reproducible():
+    a = synth.hash_normal(5, "x", (1000,))
+    b = synth.hash_normal(5, "x", (1000,))
+    np.testing.assert_array_equal(a, b)
+    assert abs(float(a.mean())) < 0.15 and 0.85 < float(a.std()) < 1.15
+    assert float(np.abs(a - synth.hash_normal(6, "x", (1000,))).max()) > 0.1
+    # pinned values: the golden fixtures depend on this generator never changing
+    np.testing.assert_allclose(synth.hash_uniform(1, "k", 3), [0.8444156203852584, 0.19804137564799584, 0.39455054998759187], rtol=0, atol=0)
