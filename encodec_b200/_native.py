@@ -37,6 +37,10 @@ SIGNATURES = {
     "ecb_version": (C.c_int, []),
     "ecb_launch_count": (C.c_int64, []),
     "ecb_debug_tap": (None, [C.c_void_p, C.c_int64, C.c_int32]),
+    "ecb_debug_tc_conv": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
+                                    C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p,
+                                    C.c_int32, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32,
+                                    C.c_int32, C.c_int32, C.c_void_p]),
     "ecb_profile_begin": (None, []),
     "ecb_profile_end": (C.c_int, [C.POINTER(EcbProfEntry), C.c_int]),
     "ecb_codec_create": (C.c_int, [C.POINTER(EcbSpec), C.POINTER(C.c_void_p)]),

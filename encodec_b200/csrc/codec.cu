@@ -1,5 +1,6 @@
 // C ABI + orchestration of the SEANet encoder / decoder / RVQ on one device (see include/encodec_b200.h).
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -32,7 +33,7 @@ struct ProfRec {
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;
 static const char* kProfNames[PROF_NCAT] = {"conv_gemm", "conv_in", "conv_out", "lstm_recurrent", "rvq_encode",
-                                            "gn_apply", "misc"};
+                                            "gn_apply", "misc", "tc_conv"};
 bool prof_enabled() { return g_prof_on; }
 void prof_begin(int cat, cudaStream_t st, double flops, double bytes) {
   ProfRec r;
@@ -61,18 +62,29 @@ struct ConvW {           // one SConv1d / SConvTranspose1d, prepared
   float* bias = nullptr;  // [Co] (conv) / [s*Co] (convtr)
   float* gamma = nullptr; // GroupNorm affine (48 kHz model), [Co]
   float* beta = nullptr;
+  // tensor-core path (tc_conv.cu): K-major split weights [t_N][t_K] and the bias padded to t_N
+  float* t_hi = nullptr;
+  float* t_lo = nullptr;
+  float* t_bias = nullptr;
+  int t_K = 0, t_N = 0;
 };
 
 struct ResW {
   ConvW b1, b3, sc;
   float* w_cat = nullptr;     // [c/2 + c][c]: block.3 stacked over the shortcut (weight-norm models)
   float* bias_cat = nullptr;  // b3 + bs
+  // tensor-core path: block.3 stacked over the shortcut with the hidden width padded to a multiple of 32
+  float* c_hi = nullptr;
+  float* c_lo = nullptr;
+  int hid_pad = 0;
 };
 
 struct LstmLayerW {
   float* w_ih = nullptr;  // [H_in][4H] (K-major rows for the 1-tap GEMM)
   float* bias = nullptr;  // b_ih + b_hh
   float* w_hh = nullptr;  // packed per CTA (lstm.cu)
+  float* t_hi = nullptr;  // tensor-core input projection: [4H][H_in] K-major split weights
+  float* t_lo = nullptr;
 };
 
 }  // namespace
@@ -100,6 +112,7 @@ struct ecb_codec {
   float* codebooks = nullptr;  // [n_q][bins][D]
   float* e2 = nullptr;         // [n_q][bins]
   int hop = 1;
+  bool tc_ready = false;       // tensor-core weights prepared (weight-norm / plain models)
 };
 
 namespace {
@@ -180,6 +193,9 @@ int prepare_res(ecb_codec* c, ResW& r, cudaStream_t st) {
   return 0;
 }
 
+int prepare_tc(ecb_codec* c, const float* w, const float* bias, int K, int N, int n_pad, float** hi, float** lo,
+               float** bias_pad, cudaStream_t st);
+
 int prepare_lstm(ecb_codec* c, const std::string& prefix, int H, std::vector<LstmLayerW>& out, cudaStream_t st) {
   out.resize(c->spec.lstm_layers);
   for (int l = 0; l < c->spec.lstm_layers; ++l) {
@@ -196,8 +212,48 @@ int prepare_lstm(ecb_codec* c, const std::string& prefix, int H, std::vector<Lst
     if (launch_add_vec(bih, bhh, lw.bias, 4 * H, st)) return 1;
     if (dev_alloc(c, &lw.w_hh, 4LL * H * H)) return 1;
     if (launch_pack_lstm_whh(whh, lw.w_hh, H, st)) return 1;
+    if (!c->spec.group_norm && prepare_tc(c, lw.w_ih, nullptr, H, 4 * H, 4 * H, &lw.t_hi, &lw.t_lo, nullptr, st)) return 1;
   }
   return 0;
+}
+
+inline int round_up32(int v) { return (v + 31) / 32 * 32; }
+
+// Split weights for the tensor-core kernel from the CUDA-core packing w [K][N] (+ bias [N]); N padded to n_pad
+// with zero rows (a 16-wide hidden layer runs as 32 columns whose upper half is exactly zero).
+int prepare_tc(ecb_codec* c, const float* w, const float* bias, int K, int N, int n_pad, float** hi, float** lo,
+               float** bias_pad, cudaStream_t st) {
+  if (dev_alloc(c, hi, (long long)K * n_pad) || dev_alloc(c, lo, (long long)K * n_pad)) return 1;
+  if (launch_split_weights(w, *hi, *lo, K, N, K, n_pad, st)) return 1;
+  if (bias_pad) {
+    if (dev_alloc(c, bias_pad, n_pad)) return 1;
+    ECB_CUDA(cudaMemsetAsync(*bias_pad, 0, sizeof(float) * n_pad, st));
+    ECB_CUDA(cudaMemcpyAsync(*bias_pad, bias, sizeof(float) * N, cudaMemcpyDeviceToDevice, st));
+  }
+  return 0;
+}
+
+int prepare_conv_tc(ecb_codec* c, ConvW& cw, cudaStream_t st) {
+  const int K = cw.transposed ? 2 * cw.c_in : cw.k * cw.c_in;
+  const int N = cw.transposed ? cw.stride * cw.c_out : cw.c_out;
+  ECB_REQUIRE(K % 32 == 0, "finalize: '%s' has K=%d, not a multiple of 32", cw.prefix.c_str(), K);
+  cw.t_K = K;
+  cw.t_N = round_up32(N);
+  return prepare_tc(c, cw.w, cw.bias, K, N, cw.t_N, &cw.t_hi, &cw.t_lo, &cw.t_bias, st);
+}
+
+int prepare_res_tc(ecb_codec* c, ResW& r, cudaStream_t st) {
+  if (prepare_conv_tc(c, r.b1, st)) return 1;
+  const int dim = r.sc.c_out, hid = r.b3.c_in;
+  r.hid_pad = round_up32(hid);
+  // [hid_pad + dim][dim]: block.3 rows, zero rows for the padded hidden channels, shortcut rows
+  float* cat = nullptr;
+  const long long rows = r.hid_pad + dim;
+  if (dev_alloc(c, &cat, rows * dim)) return 1;
+  ECB_CUDA(cudaMemsetAsync(cat, 0, sizeof(float) * rows * dim, st));
+  ECB_CUDA(cudaMemcpyAsync(cat, r.b3.w, sizeof(float) * hid * dim, cudaMemcpyDeviceToDevice, st));
+  ECB_CUDA(cudaMemcpyAsync(cat + (long long)r.hid_pad * dim, r.sc.w, sizeof(float) * dim * dim, cudaMemcpyDeviceToDevice, st));
+  return prepare_tc(c, cat, nullptr, (int)rows, dim, dim, &r.c_hi, &r.c_lo, nullptr, st);
 }
 
 void make_conv(ConvW& cw, const std::string& prefix, int ci, int co, int k, int stride, bool tr = false,
@@ -288,7 +344,7 @@ Plan make_plan(const ecb_codec* c, long long n_items, long long length) {
   Plan p;
   const long long t_pad = length + 2LL * c->hop;
   p.act_floats = (size_t)n_items * t_pad * c->spec.n_filters;
-  p.n_act = c->spec.group_norm ? 4 : 3;
+  p.n_act = 4;
   p.stat_doubles = c->spec.group_norm ? (size_t)n_items * (ceil_div_ll(length, 128) + 64) * 2 : 0;
   p.lstm_floats = (size_t)lstm_recurrent_workspace_floats((int)n_items);
   p.total_bytes = (p.act_floats * p.n_act + p.lstm_floats) * sizeof(float) + 2 * p.stat_doubles * sizeof(double) +
@@ -480,7 +536,7 @@ int run_lstm(Ctx& x, const std::vector<LstmLayerW>& layers, int H, const float* 
     p.stats = nullptr;
     if (launch_conv_gemm(p, x.st)) return 1;
     const bool last = (l == L - 1);
-    if (launch_lstm_recurrent(tmp, layers[l].w_hh, last ? in : nullptr, out, x.n_items, (int)T, H, last ? 1 : 0,
+    if (launch_lstm_recurrent(tmp, layers[l].w_hh, last ? in : nullptr, 0, out, 0, x.n_items, (int)T, H, last ? 1 : 0,
                               x.lstm_ws, x.st))
       return 1;
     cur = out;
@@ -544,6 +600,270 @@ int setup_ctx(Ctx& x, ecb_codec* c, long long n_items, long long length, void* w
   x.st = reinterpret_cast<cudaStream_t>(stream);
   x.n_items = (int)n_items;
   return 0;
+}
+
+
+// ====================================================================================================
+// Tensor-core path (weight-norm / plain-weight models): every GEMM-shaped conv runs in tc_conv.cu on
+// halo-padded channels-last activations.
+// ====================================================================================================
+struct Act {          // halo-padded channels-last activation: (item i, row r) at row0() + i*stride() + r*C
+  float* base = nullptr;
+  int C = 0;
+  long long T = 0;
+  int halo = 0;
+  long long stride() const { return (T + 2LL * halo) * C; }
+  float* row0() const { return base + (long long)halo * C; }
+};
+
+Act act_of(float* buf, int C, long long T, int halo) {
+  Act a;
+  a.base = buf;
+  a.C = C;
+  a.T = T;
+  a.halo = halo;
+  return a;
+}
+
+bool tc_disabled_by_env() {
+  static int off = -1;
+  if (off < 0) {
+    const char* e = getenv("ECB_TC");   // diagnostic switch: ECB_TC=0 keeps every conv on the CUDA-core kernels
+    off = (e && e[0] == '0') ? 1 : 0;
+  }
+  return off == 1;
+}
+
+int tc_split(bool decoder) {
+  static int dec = -1;
+  if (dec < 0) {
+    const char* e = getenv("ECB_DEC_SPLIT");   // 1: single-pass TF32 in the decoder (default 3: fp32-accurate everywhere)
+    dec = (e && e[0] == '1') ? 1 : 3;
+  }
+  return decoder ? dec : 3;
+}
+
+// frames at the top of the stack needed for the tensor-core path: every halo-padded tensor must be longer than its halo
+bool use_tc(const ecb_codec* c, long long n_frames) {
+  return c->tc_ready && !tc_disabled_by_env() && n_frames >= 2 * ACT_HALO;
+}
+
+int tap_act(cudaStream_t st, int stage, const Act& a, int n_items) {
+  if (g_tap.buf && g_tap.stage == stage) {
+    const long long row = a.T * a.C;
+    long long items = n_items;
+    if (items * row > g_tap.cap) items = g_tap.cap / row;
+    if (items > 0)
+      ECB_CUDA(cudaMemcpy2DAsync(g_tap.buf, sizeof(float) * row, a.row0(), sizeof(float) * a.stride(), sizeof(float) * row,
+                                 (size_t)items, cudaMemcpyDeviceToDevice, st));
+  }
+  return 0;
+}
+
+// One conv through the tensor-core kernel. `in` is read with reflect padding through its halo (zero_pad: plain
+// rows, out-of-range reads are zero); in1 is the optional fused 1x1 shortcut source. out_raw / out_elu are views
+// [M][N] per item that share one layout; with mirror_halo their reflected halo rows are written too.
+int tc_run(Ctx& x, const float* hi, const float* lo, const float* bias, int K, int N, const Act& in, int C0, int taps,
+           int stride, int pad_left, bool zero_pad, const Act* in1, float* out_raw, float* out_elu,
+           long long out_item_stride, long long M, int mirror_halo, int split, int round_out) {
+  TcConvParams p;
+  p.C0 = C0;
+  p.taps = taps;
+  p.stride = stride;
+  p.pad_left = pad_left;
+  p.a0_item_stride = in.stride();
+  if (zero_pad) {
+    p.a0 = in.row0();
+    p.a0_first = 0;
+    p.a0_rows = in.T;
+  } else {
+    p.a0 = in.base;
+    p.a0_first = -in.halo;
+    p.a0_rows = in.T + 2LL * in.halo;
+    const long long last = (M - 1) * stride + taps - 1 - pad_left;   // last sample the conv reads
+    ECB_REQUIRE(pad_left <= in.halo && last < in.T + in.halo, "tc_run: halo of %d rows is too small (pad %d, last %lld, T %lld)",
+                in.halo, pad_left, last, in.T);
+  }
+  p.a1 = in1 ? in1->row0() : nullptr;
+  p.a1_item_stride = in1 ? in1->stride() : 0;
+  p.C1 = in1 ? in1->C : 0;
+  p.a1_rows = in1 ? in1->T : 0;
+  ECB_REQUIRE(K == taps * C0 + p.C1, "tc_run: weight K=%d does not match taps*C0 + C1 = %d", K, taps * C0 + p.C1);
+  p.w_hi = hi;
+  p.w_lo = lo;
+  p.bias = bias;
+  p.out_raw = out_raw;
+  p.out_elu = out_elu;
+  p.out_item_stride = out_item_stride;
+  p.N = N;
+  p.M = M;
+  p.n_items = x.n_items;
+  p.halo = mirror_halo;
+  p.round_out = round_out;
+  p.split = split;
+  return launch_tc_conv(p, x.st);
+}
+
+// SEANetResnetBlock (modules/seanet.py:37-64) on the tensor cores: X (raw) and E = ELU(X) in, Y = ELU(shortcut(X) +
+// block(X)) out (halo-padded). H is scratch for the hidden activation.
+int tc_res(Ctx& x, const ResW& r, const Act& X, const Act& E, float* hbuf, Act& Y, int split) {
+  const ecb_spec& s = x.c->spec;
+  const int dim = r.sc.c_out;
+  Act H = act_of(hbuf, r.hid_pad, X.T, 0);
+  if (tc_run(x, r.b1.t_hi, r.b1.t_lo, r.b1.t_bias, r.b1.t_K, r.b1.t_N, E, dim, r.b1.k, 1, pad_left_of(s, r.b1.k, 1), false,
+             nullptr, nullptr, H.row0(), H.stride(), X.T, 0, split, split == 1))
+    return 1;
+  return tc_run(x, r.c_hi, r.c_lo, r.bias_cat, r.hid_pad + dim, dim, H, r.hid_pad, 1, 1, 0, true, &X, nullptr, Y.row0(),
+                Y.stride(), X.T, Y.halo, split, split == 1);
+}
+
+// SLSTM (modules/lstm.py:22-28): X raw [item][T][512] -> out = ELU(lstm(X) + X). pre / h0 are plain scratch.
+int tc_lstm(Ctx& x, const std::vector<LstmLayerW>& layers, const Act& X, float* pre_buf, float* h0_buf, Act& out, int split) {
+  const int H = 512, L = (int)layers.size();
+  Act pre = act_of(pre_buf, 4 * H, X.T, 0);
+  Act h0 = act_of(h0_buf, H, X.T, 0);
+  const Act* cur = &X;
+  for (int l = 0; l < L; ++l) {
+    if (tc_run(x, layers[l].t_hi, layers[l].t_lo, layers[l].bias, H, 4 * H, *cur, H, 1, 1, 0, true, nullptr, pre.row0(), nullptr,
+               pre.stride(), X.T, 0, split, 0))
+      return 1;
+    const bool last = (l == L - 1);
+    Act& dst = last ? out : h0;
+    if (launch_lstm_recurrent(pre.row0(), layers[l].w_hh, last ? X.row0() : nullptr, X.stride(), dst.row0(), dst.stride(),
+                              x.n_items, (int)X.T, H, last ? 1 : 0, x.lstm_ws, x.st))
+      return 1;
+    cur = &h0;
+  }
+  if (out.halo > 0 && launch_halo_fill(nullptr, out.row0(), out.stride(), out.T, out.C, x.n_items, out.halo, 0, x.st)) return 1;
+  return 0;
+}
+
+int encoder_forward_tc(Ctx& x, const float* xin, int64_t n_seg, int64_t length, int64_t x_batch_stride, int64_t x_seg_stride,
+                       int64_t x_chan_stride, float* emb_out, float* emb_frames_out) {
+  ecb_codec* c = x.c;
+  const ecb_spec& s = c->spec;
+  const int split = tc_split(false);
+  float *A = x.buf[0], *B = x.buf[1], *Cb = x.buf[2], *D = x.buf[3];
+  long long T = length;
+  int ch = s.n_filters;
+  Act X = act_of(A, ch, T, ACT_HALO), E = act_of(B, ch, T, ACT_HALO);
+  ConvInParams ci;
+  ci.x = xin;
+  ci.batch_stride = x_batch_stride;
+  ci.seg_stride = x_seg_stride;
+  ci.chan_stride = x_chan_stride;
+  ci.n_seg = (int)n_seg;
+  ci.n_items = x.n_items;
+  ci.T = (int)length;
+  ci.C_in = s.channels;
+  ci.K = c->enc_in.k;
+  ci.pad_left = pad_left_of(s, c->enc_in.k, 1);
+  ci.T_ref = reflect_length(length, ci.pad_left, c->enc_in.k - 1 - ci.pad_left);
+  ci.scale = nullptr;
+  ci.w = c->enc_in.w;
+  ci.bias = c->enc_in.bias;
+  ci.out = X.row0();
+  ci.out_elu = E.row0();
+  ci.out_item_stride = X.stride();
+  ci.halo = ACT_HALO;
+  ci.stats = nullptr;
+  if (launch_conv_in(ci, x.st)) return 1;
+  if (tap_act(x.st, 0, X, x.n_items)) return 1;
+  for (int i = 0; i < s.n_ratios; ++i) {
+    Act Y = act_of(D, ch, T, ACT_HALO);
+    if (tc_res(x, c->enc_res[i], X, E, Cb, Y, split)) return 1;
+    if (tap_act(x.st, 1 + 2 * i, Y, x.n_items)) return 1;
+    const ConvW& dw = c->enc_down[i];
+    const long long T2 = ceil_div_ll(T, dw.stride);
+    const bool last = (i == s.n_ratios - 1);
+    Act X2 = act_of(A, dw.c_out, T2, last ? 0 : ACT_HALO), E2 = act_of(B, dw.c_out, T2, ACT_HALO);
+    if (tc_run(x, dw.t_hi, dw.t_lo, dw.t_bias, dw.t_K, dw.t_N, Y, ch, dw.k, dw.stride, pad_left_of(s, dw.k, dw.stride), false,
+               nullptr, X2.row0(), last ? nullptr : E2.row0(), X2.stride(), T2, last ? 0 : ACT_HALO, split, 0))
+      return 1;
+    X = X2;
+    E = E2;
+    T = T2;
+    ch = dw.c_out;
+    if (tap_act(x.st, 2 + 2 * i, X, x.n_items)) return 1;
+  }
+  // X: raw top activation in A (no halo). LSTM -> D (halo-padded, post-ELU); without LSTM the ELU is applied by a copy.
+  Act top = act_of(D, ch, T, ACT_HALO);
+  if (s.lstm_layers) {
+    if (tc_lstm(x, c->enc_lstm, X, B, Cb, top, split)) return 1;
+    if (tap_act(x.st, 50, top, x.n_items)) return 1;
+  } else {
+    if (launch_halo_fill(X.row0(), top.row0(), top.stride(), T, ch, x.n_items, ACT_HALO, /*apply_elu=*/1, x.st)) return 1;
+  }
+  const ConvW& ow = c->enc_out;
+  float* frames = emb_frames_out ? emb_frames_out : B;
+  if (tc_run(x, ow.t_hi, ow.t_lo, ow.t_bias, ow.t_K, ow.t_N, top, ch, ow.k, 1, pad_left_of(s, ow.k, 1), false, nullptr, frames,
+             nullptr, T * s.dimension, T, 0, split, 0))
+    return 1;
+  if (emb_out && launch_transpose(frames, emb_out, x.n_items, (int)T, s.dimension, x.st)) return 1;
+  return 0;
+}
+
+int decoder_forward_tc(Ctx& x, const float* z_frames, int64_t n_frames, const float* scale, float* out) {
+  ecb_codec* c = x.c;
+  const ecb_spec& s = c->spec;
+  const int split = tc_split(true);
+  float *A = x.buf[0], *B = x.buf[1], *Cb = x.buf[2], *D = x.buf[3];
+  long long T = n_frames;
+  Act Q = act_of(A, s.dimension, T, ACT_HALO);
+  if (launch_halo_fill(z_frames, Q.row0(), Q.stride(), T, s.dimension, x.n_items, ACT_HALO, 0, x.st)) return 1;
+  const ConvW& iw = c->dec_in;
+  int ch = iw.c_out;
+  Act X = act_of(B, ch, T, 0);
+  // the first conv always runs split-operand: its input (the quantised latent) is not TF32-rounded
+  if (tc_run(x, iw.t_hi, iw.t_lo, iw.t_bias, iw.t_K, iw.t_N, Q, s.dimension, iw.k, 1, pad_left_of(s, iw.k, 1), false, nullptr,
+             X.row0(), nullptr, X.stride(), T, 0, 3, split == 1))
+    return 1;
+  if (tap_act(x.st, 100, X, x.n_items)) return 1;
+  Act cur = act_of(A, ch, T, 0);
+  if (s.lstm_layers) {
+    if (tc_lstm(x, c->dec_lstm, X, Cb, D, cur, split)) return 1;
+    if (tap_act(x.st, 101, cur, x.n_items)) return 1;
+  } else {
+    if (launch_halo_fill(X.row0(), cur.row0(), cur.stride(), T, ch, x.n_items, 0, /*apply_elu=*/1, x.st)) return 1;
+  }
+  for (int i = 0; i < s.n_ratios; ++i) {
+    const ConvW& uw = c->dec_up[i];
+    const int st = uw.stride;
+    const int total = uw.k - st;
+    const int trim_right = s.causal ? total : total / 2;
+    const int trim_left = total - trim_right;
+    const long long T2 = T * st;
+    Act X2 = act_of(B, uw.c_out, T2, ACT_HALO), E2 = act_of(Cb, uw.c_out, T2, ACT_HALO);
+    // [M][s*Co] row-major == [M*s][Co]; the left trim is a shift of the store base (the spill-over lands in halo rows
+    // that halo_fill rewrites below), the right trim is the row count
+    const long long M = trim_left > 0 ? T + 1 : T;
+    const long long shift = (long long)trim_left * uw.c_out;
+    if (tc_run(x, uw.t_hi, uw.t_lo, uw.t_bias, uw.t_K, uw.t_N, cur, ch, 2, 1, 1, true, nullptr, X2.row0() - shift,
+               E2.row0() - shift, X2.stride(), M, 0, split, split == 1))
+      return 1;
+    if (launch_halo_fill(nullptr, E2.row0(), E2.stride(), T2, uw.c_out, x.n_items, ACT_HALO, 0, x.st)) return 1;
+    T = T2;
+    ch = uw.c_out;
+    if (tap_act(x.st, 102 + 2 * i, X2, x.n_items)) return 1;
+    Act Y = act_of(A, ch, T, 0);
+    if (tc_res(x, c->dec_res[i], X2, E2, D, Y, split)) return 1;
+    if (tap_act(x.st, 103 + 2 * i, Y, x.n_items)) return 1;
+    cur = Y;
+  }
+  ConvOutParams co;
+  co.in = cur.row0();
+  co.in_item_stride = cur.stride();
+  co.n_items = x.n_items;
+  co.T = (int)T;
+  co.C_out = s.channels;
+  co.K = c->dec_out.k;
+  co.pad_left = pad_left_of(s, c->dec_out.k, 1);
+  co.T_ref = reflect_length(T, co.pad_left, c->dec_out.k - 1 - co.pad_left);
+  co.w = c->dec_out.w;
+  co.bias = c->dec_out.bias;
+  co.scale = scale;
+  co.out = out;
+  return launch_conv_out(co, x.st);
 }
 
 }  // namespace
@@ -676,6 +996,21 @@ int ecb_codec_finalize(ecb_codec* c, void* stream) {
       if (prepare_conv(c, c->dec_up[i], st) || prepare_res(c, c->dec_res[i], st)) return 1;
     if (s.lstm_layers && prepare_lstm(c, "decoder.model.1", 512, c->dec_lstm, st)) return 1;
   }
+  c->tc_ready = false;
+  if (!s.group_norm) {
+    // tensor-core path (tc_conv.cu): every GEMM-shaped conv gets K-major split (hi, lo) weights
+    if (c->has_enc) {
+      if (prepare_conv_tc(c, c->enc_out, st)) return 1;
+      for (int i = 0; i < s.n_ratios; ++i)
+        if (prepare_res_tc(c, c->enc_res[i], st) || prepare_conv_tc(c, c->enc_down[i], st)) return 1;
+    }
+    if (c->has_dec) {
+      if (prepare_conv_tc(c, c->dec_in, st)) return 1;
+      for (int i = 0; i < s.n_ratios; ++i)
+        if (prepare_conv_tc(c, c->dec_up[i], st) || prepare_res_tc(c, c->dec_res[i], st)) return 1;
+    }
+    c->tc_ready = true;
+  }
   if (c->has_rvq) {
     // codebooks (quantization/core_vq.py:128-135); layers may alias (fork delta D6) -- each is copied
     const long long per = (long long)s.bins * s.dimension;
@@ -709,6 +1044,8 @@ int ecb_encoder_forward(ecb_codec* c, const float* xin, int64_t n_items, int64_t
   if (setup_ctx(x, c, n_items, length, workspace, workspace_bytes, stream)) return 1;
   ECB_REQUIRE(c->has_enc, "encoder_forward: no encoder weights were loaded into this codec");
   const ecb_spec& s = c->spec;
+  if (!scale_out && use_tc(c, ceil_div_ll(length, c->hop)))
+    return encoder_forward_tc(x, xin, n_seg, length, x_batch_stride, x_seg_stride, x_chan_stride, emb_out, emb_frames_out);
   float *A = x.buf[0], *B = x.buf[1], *C = x.buf[2], *D = x.buf[3];
 
   if (scale_out) {
@@ -732,6 +1069,9 @@ int ecb_encoder_forward(ecb_codec* c, const float* xin, int64_t n_items, int64_t
   ci.w = c->enc_in.w;
   ci.bias = c->enc_in.bias;
   ci.out = A;
+  ci.out_elu = nullptr;
+  ci.out_item_stride = 0;
+  ci.halo = 0;
   ci.stats = s.group_norm ? x.stat[0] : nullptr;
   if (launch_conv_in(ci, x.st)) return 1;
   if (s.group_norm) {
@@ -793,6 +1133,13 @@ int ecb_decoder_forward(ecb_codec* c, const float* z, const float* z_frames, int
     if (launch_transpose(z, C, n_items, s.dimension, (int)T, x.st)) return 1;  // [D][T] -> [T][D]
     z_frames = C;
   }
+  if (use_tc(c, n_frames)) {
+    if (z) {  // keep the transposed latent out of the tensor-core path's buffers: it is consumed by the first launch
+      ECB_CUDA(cudaMemcpyAsync(D, C, sizeof(float) * (size_t)n_items * T * s.dimension, cudaMemcpyDeviceToDevice, x.st));
+      z_frames = D;
+    }
+    return decoder_forward_tc(x, z_frames, n_frames, scale, out);
+  }
   if (run_conv(x, c->dec_in, z_frames, T, 0, A, 0, nullptr)) return 1;        // -> A raw [T][512]
   if (tap(x.st, 100, A, n_items * T * c->dec_in.c_out)) return 1;
   const float* cur = A;
@@ -817,6 +1164,7 @@ int ecb_decoder_forward(ecb_codec* c, const float* z, const float* z_frames, int
   }
   ConvOutParams co;
   co.in = cur;
+  co.in_item_stride = 0;
   co.n_items = (int)n_items;
   co.T = (int)T;
   co.C_out = s.channels;
@@ -921,6 +1269,38 @@ int ecb_overlap_add(const float* frames, const int32_t* seg_lens, int64_t batch,
   ECB_REQUIRE(total > stride * (n_seg - 1) && total <= stride * (n_seg - 1) + seg_len, "overlap_add: bad total");
   return launch_overlap_add(frames, seg_lens, batch, (int)channels, (int)n_seg, (int)seg_len, (int)stride, out, total,
                             reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ecb_debug_tc_conv(const float* a0, int64_t a0_item_stride, int32_t C0, int64_t a0_first, int64_t a0_rows,
+                      int32_t taps, int32_t stride, int32_t pad_left, const float* a1, int64_t a1_item_stride,
+                      int32_t C1, int64_t a1_rows, const float* w, const float* bias, int32_t N, int64_t M,
+                      int32_t n_items, float* out_raw, float* out_elu, int64_t out_item_stride, int32_t halo,
+                      int32_t round_out, int32_t split, void* stream) {
+  ECB_REQUIRE(a0 && w && (out_raw || out_elu), "debug_tc_conv: null argument");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int ktot = taps * C0 + (a1 ? C1 : 0);
+  float *hi = nullptr, *lo = nullptr;
+  ECB_CUDA(cudaMalloc((void**)&hi, sizeof(float) * (size_t)ktot * N));
+  ECB_CUDA(cudaMalloc((void**)&lo, sizeof(float) * (size_t)ktot * N));
+  int rc = launch_split_weights(w, hi, lo, ktot, N, ktot, N, st);
+  if (!rc) {
+    TcConvParams p;
+    p.a0 = a0; p.a0_item_stride = a0_item_stride; p.C0 = C0; p.a0_first = a0_first; p.a0_rows = a0_rows;
+    p.taps = taps; p.stride = stride; p.pad_left = pad_left;
+    p.a1 = a1; p.a1_item_stride = a1_item_stride; p.C1 = C1; p.a1_rows = a1_rows;
+    p.w_hi = hi; p.w_lo = lo; p.bias = bias;
+    p.out_raw = out_raw; p.out_elu = out_elu; p.out_item_stride = out_item_stride;
+    p.N = N; p.M = M; p.n_items = n_items; p.halo = halo; p.round_out = round_out; p.split = split;
+    rc = launch_tc_conv(p, st);
+  }
+  cudaError_t e = cudaStreamSynchronize(st);
+  cudaFree(hi);
+  cudaFree(lo);
+  if (!rc && e != cudaSuccess) {
+    set_error("debug_tc_conv: %s", cudaGetErrorString(e));
+    rc = 1;
+  }
+  return rc;
 }
 
 int ecb_transpose_bct_to_btc(const float* in, float* out, int64_t batch, int64_t chans, int64_t len, void* stream) {

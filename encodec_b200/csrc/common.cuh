@@ -23,7 +23,7 @@ extern std::atomic<long long> g_launches;
 
 // Optional per-kernel-class timing (bench.py's roofline leg): CUDA events recorded on the launching stream
 // around every launch while enabled; off by default (no events, no overhead).
-enum ProfCat { PROF_CONV_GEMM = 0, PROF_CONV_IN, PROF_CONV_OUT, PROF_LSTM_REC, PROF_RVQ, PROF_GN_APPLY, PROF_MISC, PROF_NCAT };
+enum ProfCat { PROF_CONV_GEMM = 0, PROF_CONV_IN, PROF_CONV_OUT, PROF_LSTM_REC, PROF_RVQ, PROF_GN_APPLY, PROF_MISC, PROF_TC_CONV, PROF_NCAT };
 bool prof_enabled();
 void prof_begin(int cat, cudaStream_t st, double flops, double bytes);
 void prof_end(cudaStream_t st);
@@ -56,7 +56,26 @@ struct ProfScope {
     }                                                                                               \
   } while (0)
 
-__device__ __forceinline__ float elu1(float v) { return v > 0.f ? v : expm1f(v); }
+// ELU(alpha = 1) (reference modules/seanet.py:43: nn.ELU): v > 0 ? v : expm1(v). expm1 by range reduction
+// v = n ln2 + r, |r| <= ln2/2: expm1(v) = 2^n (expm1(r) + 1) - 1 with a degree-7 polynomial for expm1(r);
+// about 1 ulp, no cancellation near 0, ~16 instructions (the epilogues apply it to every stored element).
+__device__ __forceinline__ float elu1(float v) {
+  const float x = fmaxf(v, -20.f);                       // exp(-20) - 1 == -1 in fp32
+  const float t = fmaf(x, 1.4426950408889634f, 12582912.f);
+  const float n = t - 12582912.f;                        // rint(x / ln2)
+  float r = fmaf(n, -0.693145751953125f, x);             // ln2 high part: exact product
+  r = fmaf(n, -1.428606765330187e-06f, r);               // ln2 low part
+  float q = 1.9841270e-4f;
+  q = fmaf(q, r, 1.3888889e-3f);
+  q = fmaf(q, r, 8.3333333e-3f);
+  q = fmaf(q, r, 4.1666667e-2f);
+  q = fmaf(q, r, 1.6666667e-1f);
+  q = fmaf(q, r, 0.5f);
+  q = fmaf(q * r, r, r);                                 // expm1(r)
+  const float s = __int_as_float((__float_as_int(t) << 23) + 0x3f800000);  // 2^n
+  const float e = fmaf(q, s, s - 1.f);
+  return v > 0.f ? v : e;
+}
 
 // index of a reflect-padded signal of length T (valid while the pad is < T); conv.py:80-97
 __device__ __forceinline__ int reflect_index(int r, int T) {
@@ -116,6 +135,41 @@ int launch_conv_gemm(const ConvParams& p, cudaStream_t stream);
 int conv_gemm_stat_slots(const ConvParams& p);  // gridDim.x*gridDim.y the launch will use
 
 // ------------------------------------------------------------------------------------------------
+// Tensor-core implicit-GEMM convolution (tc_conv.cu): tcgen05 / TMEM / TMA, halo-padded activations
+// ------------------------------------------------------------------------------------------------
+constexpr int ACT_HALO = 16;  // reflected rows kept before and after every item of a halo-padded activation
+
+struct TcConvParams {
+  // source 0: channels-last rows; a0 points at (item 0, sample a0_first, channel 0) and a0_rows samples are
+  // addressable from there (reads outside are zero). Output row m reads samples m*stride - pad_left ... + taps - 1.
+  const float* a0;
+  long long a0_item_stride;   // floats
+  int C0;                     // multiple of 32
+  long long a0_first, a0_rows;
+  int taps, stride, pad_left;
+  // optional source 1 (1 tap, stride 1, row m <-> output row m): fused 1x1 shortcut; nullptr if unused
+  const float* a1;
+  long long a1_item_stride;
+  int C1;
+  long long a1_rows;
+  const float* w_hi;          // [N][Ktot] K-major, Ktot = taps*C0 + C1 (from launch_split_weights)
+  const float* w_lo;          // remainder (split == 3)
+  const float* bias;          // [N] or nullptr
+  float* out_raw;             // (item 0, row 0) of the raw output [M][N], or nullptr
+  float* out_elu;             // same for ELU(output), or nullptr
+  long long out_item_stride;  // floats (both outputs)
+  int N;                      // multiple of 32
+  long long M;                // output rows per item
+  int n_items;
+  int halo;                   // also write the reflected rows -1..-halo and M..M+halo-1 of each output (0: none)
+  int round_out;              // round stored values to TF32 (for split == 1 consumers)
+  int split;                  // 3: fp32-accurate split operands; 1: single TF32 pass
+};
+int launch_tc_conv(const TcConvParams& p, cudaStream_t stream);
+int launch_split_weights(const float* w, float* hi, float* lo, int K, int N, int K_pad, int N_pad, cudaStream_t s);
+int tc_pick_bn(int N, int split);
+
+// ------------------------------------------------------------------------------------------------
 // Edge convolutions (conv_edge.cu): audio [B,C,T] channels-first <-> 32-channel channels-last
 // ------------------------------------------------------------------------------------------------
 struct ConvInParams {
@@ -125,14 +179,18 @@ struct ConvInParams {
   const float* scale;     // per item divisor or nullptr
   const float* w;         // [K*C_in][32]
   const float* bias;      // [32]
-  float* out;             // [item][T][32]
+  float* out;             // raw output: (item i, row t) at out + i*out_item_stride + t*32, or nullptr
+  float* out_elu;         // same layout, ELU(output), or nullptr
+  long long out_item_stride;  // floats; 0 means the dense T*32
+  int halo;               // also write the reflected rows -1..-halo and T..T+halo-1 of every item
   double* stats;          // nullptr or [item][gridDim.x][2]
 };
 int launch_conv_in(const ConvInParams& p, cudaStream_t stream);
 int conv_in_stat_slots(const ConvInParams& p);
 
 struct ConvOutParams {
-  const float* in;        // [item][T][32]
+  const float* in;        // (item i, row t) at in + i*in_item_stride + t*32
+  long long in_item_stride;   // floats; 0 means the dense T*32
   int n_items, T, T_ref, C_out, K, pad_left;
   const float* w;         // [K][32][C_out]
   const float* bias;      // [C_out]
@@ -152,6 +210,8 @@ int launch_pack_convtr(const float* w, const float* scale, float* out, int Ci, i
 int launch_expand_bias(const float* b, float* out, int Co, int reps, cudaStream_t s);
 int launch_add_vec(const float* a, const float* b, float* out, int n, cudaStream_t s);
 int launch_transpose(const float* in, float* out, long long batch, int rows, int cols, cudaStream_t s);  // [b][rows][cols]->[b][cols][rows]
+int launch_halo_fill(const float* src, float* row0, long long item_stride, long long T, int C, int n_items, int halo,
+                     int apply_elu, cudaStream_t s);
 int launch_segment_scale(const float* x, long long batch_stride, long long seg_stride, long long chan_stride,
                          int n_seg, int n_items, int T, int C, float* scale, cudaStream_t s);
 struct GnSrc {
@@ -176,8 +236,10 @@ int launch_overlap_add(const float* frames, const int* seg_lens, long long batch
 // act(h + skip) (SLSTM skip connection, lstm.py:25-26) and the raw h stays in the recurrent state only.
 int lstm_recurrent_workspace_floats(int batch);
 int launch_pack_lstm_whh(const float* w_hh, float* packed, int H, cudaStream_t s);
-int launch_lstm_recurrent(const float* pre, const float* w_hh_packed, const float* skip, float* out, int batch,
-                          int T, int H, int out_elu, float* workspace, cudaStream_t s);
+// skip / out rows of item b start at + b*skip_item_stride / + b*out_item_stride floats (0 means the dense T*H).
+int launch_lstm_recurrent(const float* pre, const float* w_hh_packed, const float* skip, long long skip_item_stride,
+                          float* out, long long out_item_stride, int batch, int T, int H, int out_elu,
+                          float* workspace, cudaStream_t s);
 
 // ------------------------------------------------------------------------------------------------
 // rvq.cu

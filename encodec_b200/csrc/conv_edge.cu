@@ -102,13 +102,29 @@ conv_in_kernel(const ConvInParams p) {
     p.stats[slot] = s;
     p.stats[slot + 1] = sq;
   }
-  float* __restrict__ ob = p.out + ((long long)item * p.T + t0) * NF;
+  const long long ostride = p.out_item_stride ? p.out_item_stride : (long long)p.T * NF;
   const int rows = min(EDGE_TILE, p.T - t0);
   for (int f = tid; f < rows * (NF / 4); f += EDGE_TILE) {
     const int t = f >> 3;
     const int q = f & 7;
     const float4 v = *reinterpret_cast<const float4*>(&os[t * NF + ((q ^ (t & 7)) << 2)]);
-    *reinterpret_cast<float4*>(ob + (long long)f * 4) = v;
+    const float4 e = make_float4(elu1(v.x), elu1(v.y), elu1(v.z), elu1(v.w));
+    const int g = t0 + t;   // row inside the item
+    int mir[2] = {0x7fffffff, 0x7fffffff};
+    if (p.halo > 0) {
+      if (g >= 1 && g <= p.halo) mir[0] = -g;
+      if (g <= p.T - 2 && g >= p.T - 1 - p.halo) mir[1] = 2 * (p.T - 1) - g;
+    }
+#pragma unroll
+    for (int o = 0; o < 2; ++o) {
+      float* base = o == 0 ? p.out : p.out_elu;
+      if (!base) continue;
+      base += (long long)item * ostride + q * 4;
+      const float4 w = o == 0 ? v : e;
+      *reinterpret_cast<float4*>(base + (long long)g * NF) = w;
+      if (mir[0] != 0x7fffffff) *reinterpret_cast<float4*>(base + (long long)mir[0] * NF) = w;
+      if (mir[1] != 0x7fffffff) *reinterpret_cast<float4*>(base + (long long)mir[1] * NF) = w;
+    }
   }
 }
 
@@ -122,7 +138,7 @@ conv_out_kernel(const ConvOutParams p) {
   const int tid = threadIdx.x;
   const int item = blockIdx.y;
   const int t0 = blockIdx.x * EDGE_TILE;
-  const float* __restrict__ ib = p.in + (long long)item * p.T * NF;
+  const float* __restrict__ ib = p.in + (long long)item * (p.in_item_stride ? p.in_item_stride : (long long)p.T * NF);
   const int span = EDGE_TILE + p.K - 1;
 
   for (int i = tid; i < p.K * NF * p.C_out; i += EDGE_TILE) ws[i] = p.w[i];
@@ -186,9 +202,11 @@ int launch_conv_in(const ConvInParams& p, cudaStream_t stream) {
               "conv_in: unsupported C_in=%d K=%d", p.C_in, p.K);
   ECB_REQUIRE(p.T >= 1 && p.T_ref >= p.T && p.T_ref > p.K - 1, "conv_in: bad reflection length %d for T=%d", p.T_ref, p.T);
   ECB_REQUIRE(p.n_items > 0 && p.n_items <= 65535, "conv_in: bad item count %d", p.n_items);
+  ECB_REQUIRE(p.out || p.out_elu, "conv_in: no output");
+  ECB_REQUIRE(p.halo == 0 || p.T > p.halo, "conv_in: %d samples are too few for a %d-row halo", p.T, p.halo);
   dim3 grid((unsigned)cdiv(p.T, EDGE_TILE), (unsigned)p.n_items);
   const double rows_in = (double)p.T * p.n_items;
-  ProfScope prof(PROF_CONV_IN, stream, 2.0 * rows_in * NF * p.K * p.C_in, 4.0 * rows_in * (p.C_in + NF));
+  ProfScope prof(PROF_CONV_IN, stream, 2.0 * rows_in * NF * p.K * p.C_in, 4.0 * rows_in * (p.C_in + NF * ((p.out ? 1 : 0) + (p.out_elu ? 1 : 0))));
   conv_in_kernel<<<grid, EDGE_TILE, 0, stream>>>(p);
   ECB_LAUNCHED();
   return 0;

@@ -30,6 +30,7 @@ struct LstmParams {
   float* out;          // [B][T][H]
   float* hbuf;         // [2][B][H] recurrent state, hbuf[0] zeroed by the host
   unsigned int* bar;   // grid barrier counter, zeroed by the host
+  long long skip_stride, out_stride;  // floats between items
   int B, T, out_elu;
 };
 
@@ -93,7 +94,7 @@ lstm_recurrent_kernel(const LstmParams p) {
         const float* pr = p.pre + ((long long)bg * p.T + t) * (4 * LH) + unit;
 #pragma unroll
         for (int q = 0; q < 4; ++q) pg[q] = __ldg(pr + q * LH);
-        if (p.skip) skipv = __ldg(p.skip + ((long long)bg * p.T + t) * LH + unit);
+        if (p.skip) skipv = __ldg(p.skip + (long long)bg * p.skip_stride + (long long)t * LH + unit);
       }
       // h_{t-1} tile -> shared (L2 only: other CTAs wrote it during the previous step)
       for (int f = tid; f < L_BT * (LH / 4); f += L_THREADS) {
@@ -160,7 +161,7 @@ lstm_recurrent_kernel(const LstmParams p) {
         float y = h_new;
         if (p.skip) y += skipv;
         if (p.out_elu) y = elu1(y);
-        p.out[((long long)bg * p.T + t) * LH + unit] = y;
+        p.out[(long long)bg * p.out_stride + (long long)t * LH + unit] = y;
       }
       // `part` and `hs` are rewritten only after the next tile's barriers
     }
@@ -198,8 +199,9 @@ int launch_pack_lstm_whh(const float* w_hh, float* packed, int H, cudaStream_t s
   return 0;
 }
 
-int launch_lstm_recurrent(const float* pre, const float* w_hh_packed, const float* skip, float* out, int batch,
-                          int T, int H, int out_elu, float* workspace, cudaStream_t s) {
+int launch_lstm_recurrent(const float* pre, const float* w_hh_packed, const float* skip, long long skip_item_stride,
+                          float* out, long long out_item_stride, int batch, int T, int H, int out_elu,
+                          float* workspace, cudaStream_t s) {
   ECB_REQUIRE(H == LH, "lstm: hidden size %d unsupported (only %d)", H, LH);
   ECB_REQUIRE(batch > 0 && T > 0, "lstm: bad batch %d / T %d", batch, T);
   const size_t smem = lstm_smem_bytes(batch);
@@ -214,6 +216,8 @@ int launch_lstm_recurrent(const float* pre, const float* w_hh_packed, const floa
   p.wp = w_hh_packed;
   p.skip = skip;
   p.out = out;
+  p.skip_stride = skip_item_stride ? skip_item_stride : (long long)T * LH;
+  p.out_stride = out_item_stride ? out_item_stride : (long long)T * LH;
   p.hbuf = workspace;
   p.bar = reinterpret_cast<unsigned int*>(workspace + 2 * (size_t)batch * LH);
   p.B = batch;

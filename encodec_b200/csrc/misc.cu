@@ -84,6 +84,35 @@ __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict
   }
 }
 
+// Halo-padded activation layout of the tensor-core path: (item i, row r) at row0 + i*item_stride + r*C with
+// r in [-halo, T + halo); rows outside [0, T) hold the reflected samples of pad1d (reference modules/conv.py:80-97):
+// row -j = row j, row T-1+j = row T-1-j. With src != nullptr the interior is first copied from a plain
+// [item][T][C] tensor; with src == nullptr only the halo rows are (re)written from the interior in place.
+__global__ void halo_fill_kernel(const float* __restrict__ src, float* __restrict__ row0, long long item_stride, int T,
+                                 int C, int halo, int apply_elu) {
+  const int item = blockIdx.y;
+  const int c4n = C >> 2;
+  const int rows = src ? T + 2 * halo : 2 * halo;
+  float* ob = row0 + (long long)item * item_stride;
+  for (long long f = blockIdx.x * (long long)blockDim.x + threadIdx.x; f < (long long)rows * c4n;
+       f += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(f % c4n);
+    int r = (int)(f / c4n);
+    if (src) r -= halo;                               // r in [-halo, T + halo)
+    else r = r < halo ? r - halo : T + (r - halo);    // halo rows only
+    int sr = r < 0 ? -r : (r >= T ? 2 * (T - 1) - r : r);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (sr >= 0 && sr < T) {
+      v = src ? __ldg(reinterpret_cast<const float4*>(src + ((long long)item * T + sr) * C) + c4)
+              : *(reinterpret_cast<const float4*>(ob + (long long)sr * C) + c4);
+      if (apply_elu) {
+        v.x = elu1(v.x); v.y = elu1(v.y); v.z = elu1(v.z); v.w = elu1(v.w);
+      }
+    }
+    *(reinterpret_cast<float4*>(ob + (long long)r * C) + c4) = v;
+  }
+}
+
 // scale = 1e-8 + sqrt(mean_t(mean_c(x)^2))  -- EncodecModel._encode_frame, reference model.py:180-185
 __global__ void segment_scale_kernel(const float* __restrict__ x, long long batch_stride, long long seg_stride,
                                      long long chan_stride, int n_seg, int T, int C, float* __restrict__ scale) {
@@ -245,6 +274,18 @@ int launch_transpose(const float* in, float* out, long long batch, int rows, int
   ECB_LAUNCHED();
   return 0;
 }
+int launch_halo_fill(const float* src, float* row0, long long item_stride, long long T, int C, int n_items, int halo,
+                     int apply_elu, cudaStream_t s) {
+  ECB_REQUIRE(C % 4 == 0 && T >= 2 && n_items > 0 && n_items <= 65535, "halo_fill: bad shape T=%lld C=%d", T, C);
+  const long long rows = src ? T + 2 * halo : 2 * halo;
+  const long long work = rows * (C / 4);
+  dim3 grid((unsigned)(cdiv(work, 256) < 1024 ? cdiv(work, 256) : 1024), (unsigned)n_items);
+  ProfScope prof(PROF_MISC, s, 0.0, 8.0 * rows * C * n_items);
+  halo_fill_kernel<<<grid, 256, 0, s>>>(src, row0, item_stride, (int)T, C, halo, apply_elu);
+  ECB_LAUNCHED();
+  return 0;
+}
+
 int launch_segment_scale(const float* x, long long batch_stride, long long seg_stride, long long chan_stride,
                          int n_seg, int n_items, int T, int C, float* scale, cudaStream_t s) {
   ProfScope prof(PROF_MISC, s, 0.0, 4.0 * (double)n_items * T * C);

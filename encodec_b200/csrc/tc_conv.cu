@@ -1,0 +1,655 @@
+// tcgen05 / TMEM / TMA implicit-GEMM convolution for sm_100a (tensor-core path of the SEANet stacks).
+//
+// GEMM view (same as conv_gemm.cu): per item, out[M][N] = A[M][Ktot] * W + bias, where row m of A is the
+// window of a channels-last activation [T][C] that starts at sample m*stride - pad_left and spans `taps`
+// samples (reference modules/conv.py:202-221 SConv1d, :241-263 SConvTranspose1d as a 2-tap GEMM over frames,
+// modules/lstm.py:24 input projection as a 1-tap GEMM), optionally followed by the columns of a second
+// 1-tap source (the 1x1 shortcut of SEANetResnetBlock, modules/seanet.py:63-64, fused into the block's last
+// conv).
+//
+// What is different from the CUDA-core kernel:
+//   * activations live in HALO-PADDED buffers: HALO rows before and after each item hold the reflected
+//     samples (conv.py:80-97 pad1d), written by the producer. Every A tile is then a plain box: one TMA
+//     load (cp.async.bulk.tensor, SWIZZLE_128B) of [128 rows x 32 channels] per K chunk, straight into the
+//     K-major canonical layout tcgen05.mma reads. A strided k = 2s conv addresses its input through the folded
+//     view [T/s][s*C], so its window is two consecutive folded rows. Zero padding (transposed convs) is TMA
+//     out-of-bounds fill.
+//   * products run on the 5th-generation tensor cores: tcgen05.mma.cta_group::1.kind::tf32, M = 128, N = BN,
+//     K = 8 per instruction, fp32 accumulators in TMEM, issued by one elected thread.
+//   * fp32-level accuracy with split operands (SPLIT = 3): a = a_hi + a_lo with a_hi = the TF32 truncation
+//     the tensor core applies itself and a_lo = rn_tf32(a - a_hi) computed on chip by two transform warps;
+//     w = w_hi + w_lo with w_hi = rn_tf32(w), w_lo = rn_tf32(w - w_hi) computed once at load.
+//     D += a*w_hi + a_lo*w_hi + a*w_lo; the dropped a_lo*w_lo term is zero-mean (w_lo is symmetric) and
+//     below 2^-22 relative. SPLIT = 1 issues the first product only (operands rounded to TF32 by their
+//     producers).
+//   * persistent, warp-specialised: warp 0 TMA producer, warp 1 MMA issuer (owns TMEM), warps 2-3 transform,
+//     warps 4-7 epilogue. Two TMEM accumulator buffers let the epilogue of tile i overlap the main loop of
+//     tile i+1. The epilogue reads TMEM (tcgen05.ld 32x32b), adds the bias, optionally applies ELU, stages
+//     32x32 blocks in swizzled shared memory and writes them with TMA stores (row clipping by the tensor map);
+//     an output may be written raw, ELU'd or both (a residual block consumes x through its shortcut and
+//     ELU(x) through its first conv) and its reflected halo rows are written directly.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace ecb {
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 32;                      // fp32 per K chunk = one 128-byte swizzle row
+constexpr int A_BYTES = BM * BK * 4;        // 16 KB
+constexpr int TC_THREADS = 256;              // 8 warps: TMA, MMA, 2 x transform, 4 x epilogue
+constexpr int STAGING_BYTES = 4 * 2 * 4096; // 4 epilogue warps x 2 slots x [32 rows x 128 B]
+
+template <int BN, int SPLIT>
+struct Cfg {
+  static constexpr int B_BYTES = BN * BK * 4;
+  static constexpr int STAGE_BYTES = (SPLIT == 3) ? 2 * A_BYTES + 2 * B_BYTES : A_BYTES + B_BYTES;
+  static constexpr int BUDGET = 227 * 1024 - STAGING_BYTES - 1024 - 512;
+  static constexpr int S0 = BUDGET / STAGE_BYTES;
+  static constexpr int STAGES = S0 > 6 ? 6 : S0;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 512;
+  static constexpr int TMEM_COLS = (SPLIT == 3) ? 4 * BN : 2 * BN;   // two main (+ two correction) accumulators
+  static_assert(STAGES >= 2, "pipeline too shallow");
+  static_assert(TMEM_COLS <= 512, "TMEM overflow");
+};
+
+struct TcArgs {
+  const float* bias;        // [N] or nullptr
+  float* mir_raw;           // direct-store base (item 0, row 0) for the reflected halo rows, or nullptr
+  float* mir_elu;
+  long long out_item_stride;
+  int N, M, n_items;
+  int tiles_m, tiles_n, total_tiles;
+  int nch0, nch1;           // K chunks of source 0 / source 1
+  int rowlen0;              // floats per folded row of source 0 (stride * C0)
+  int row_base0, row_base1; // row coordinate of output row 0's first chunk in each source's map
+  int store_raw, store_elu, round_out, halo;
+  int group;                // K chunks per main-accumulator group (SPLIT == 1: all of them)
+};
+
+// ---------------------------------------------------------------------------------------------- PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y, int z) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y), "r"(z)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int x, int y, int z) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(src),
+               "r"(x), "r"(y), "r"(z)
+               : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tcgen05_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ float rn_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100): start address >> 4 in
+// bits [0,14), LBO (unused for swizzled K-major) = 1 in [16,30), SBO = 1024 B (8 rows x 128 B) >> 4 in [32,46),
+// version = 1 in [46,48), layout type SWIZZLE_128B = 2 in [61,64).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// kind::tf32 instruction descriptor (cute::UMMA::InstrDescriptor): D fp32 (bits [4,6) = 1), A/B TF32 ([7,10) = [10,13) = 2),
+// both K-major, N >> 3 in [17,23), M >> 4 in [24,29).
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int m, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+template <int BN, int SPLIT>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_conv_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
+               const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
+               const __grid_constant__ CUtensorMap map_raw, const __grid_constant__ CUtensorMap map_elu,
+               const TcArgs p) {
+  using C = Cfg<BN, SPLIT>;
+  constexpr int STAGES = C::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B tiles need 1024-byte alignment
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t staging_base = smem_base + STAGES * C::STAGE_BYTES;
+  const uint32_t bar_base = staging_base + STAGING_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto ready_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+  auto mainf_bar = [&](int b) { return bar_base + 8u * (3 * STAGES + b); };       // main accumulator b holds a finished K group
+  auto maine_bar = [&](int b) { return bar_base + 8u * (3 * STAGES + 2 + b); };   // ... has been drained by the epilogue
+  auto corrf_bar = [&](int b) { return bar_base + 8u * (3 * STAGES + 4 + b); };   // correction accumulator b is complete (tile end)
+  auto corre_bar = [&](int b) { return bar_base + 8u * (3 * STAGES + 6 + b); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + STAGES * C::STAGE_BYTES + STAGING_BYTES + 8 * (3 * STAGES + 8));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nch = p.nch0 + p.nch1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(ready_bar(s), 2);   // one arrive per transform warp
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(mainf_bar(b), 1);
+      mbar_init(maine_bar(b), 4);   // one arrive per epilogue warp
+      mbar_init(corrf_bar(b), 1);
+      mbar_init(corre_bar(b), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(C::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  // TMEM columns: main accumulators [0, 2 BN), correction accumulators [2 BN, 4 BN) (SPLIT == 3 only)
+  auto main_col = [&](int b) { return (uint32_t)(b * BN); };
+  auto corr_col = [&](int b) { return (uint32_t)(2 * BN + b * BN); };
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int nt = tile % p.tiles_n;
+        const int mt_all = tile / p.tiles_n;
+        const int mt = mt_all % p.tiles_m;
+        const int item = mt_all / p.tiles_m;
+        for (int c = 0; c < nch; ++c, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          const uint32_t a_dst = smem_base + s * C::STAGE_BYTES;
+          const uint32_t bhi_dst = a_dst + (SPLIT == 3 ? 2 : 1) * A_BYTES;
+          mbar_expect_tx(full_bar(s), A_BYTES + (SPLIT == 3 ? 2 : 1) * C::B_BYTES);
+          if (c < p.nch0) {
+            const int k0 = c * BK;
+            const int r = k0 / p.rowlen0;
+            tma_load_3d(a_dst, &map_a0, full_bar(s), k0 - r * p.rowlen0, mt * BM + p.row_base0 + r, item);
+          } else {
+            tma_load_3d(a_dst, &map_a1, full_bar(s), (c - p.nch0) * BK, mt * BM + p.row_base1, item);
+          }
+          tma_load_2d(bhi_dst, &map_bhi, full_bar(s), c * BK, nt * BN);
+          if (SPLIT == 3) tma_load_2d(bhi_dst + C::B_BYTES, &map_blo, full_bar(s), c * BK, nt * BN);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    // The tensor core truncates when it adds into the fp32 accumulator, a bias of ~1.7e-8 per accumulation step.
+    // The large a*w_hi products therefore go to a MAIN accumulator that the epilogue drains and re-accumulates in
+    // registers (round-to-nearest) every `group` K chunks, alternating between two TMEM buffers; the small
+    // correction products (2^-11 of the result, their truncation is irrelevant) accumulate over the whole tile.
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_tf32(BM, BN);
+      int it = 0, tl = 0;
+      uint32_t gcount = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl) {
+        const int cb = tl & 1;
+        if (SPLIT == 3) {
+          mbar_wait(corre_bar(cb), (((uint32_t)tl >> 1) & 1u) ^ 1u);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        const uint32_t d_corr = tmem_base + corr_col(cb);
+        for (int c0 = 0; c0 < nch; c0 += p.group, ++gcount) {
+          const int c1 = min(c0 + p.group, nch);
+          const int mb = (int)(gcount & 1u);
+          mbar_wait(maine_bar(mb), ((gcount >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t d_main = tmem_base + main_col(mb);
+          for (int c = c0; c < c1; ++c, ++it) {
+            const int s = it % STAGES;
+            const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+            mbar_wait(full_bar(s), ph);
+            if (SPLIT == 3) mbar_wait(ready_bar(s), ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a_addr = smem_base + s * C::STAGE_BYTES;
+            const uint32_t alo_addr = a_addr + A_BYTES;
+            const uint32_t bhi_addr = a_addr + (SPLIT == 3 ? 2 : 1) * A_BYTES;
+            const uint32_t blo_addr = bhi_addr + C::B_BYTES;
+#pragma unroll
+            for (int k = 0; k < BK / 8; ++k) {
+              const uint64_t da = umma_desc_sw128(a_addr + k * 32);
+              const uint64_t dbh = umma_desc_sw128(bhi_addr + k * 32);
+              tcgen05_mma_tf32(d_main, da, dbh, idesc, (c > c0 || k > 0) ? 1u : 0u);
+              if (SPLIT == 3) {
+                const uint64_t dal = umma_desc_sw128(alo_addr + k * 32);
+                const uint64_t dbl = umma_desc_sw128(blo_addr + k * 32);
+                tcgen05_mma_tf32(d_corr, dal, dbh, idesc, (c > 0 || k > 0) ? 1u : 0u);
+                tcgen05_mma_tf32(d_corr, da, dbl, idesc, 1u);
+              }
+            }
+            tcgen05_commit(empty_bar(s));   // frees the stage once these MMAs have read it
+          }
+          tcgen05_commit(mainf_bar(mb));    // K group complete -> epilogue
+        }
+        if (SPLIT == 3) tcgen05_commit(corrf_bar(cb));
+      }
+    }
+  } else if (warp < 4) {
+    // ================================ transform: a_lo = rn_tf32(a - trunc_tf32(a)) ================================
+    if (SPLIT == 3) {
+      const int tt = threadIdx.x - 64;  // 0..63
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        for (int c = 0; c < nch; ++c, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+          mbar_wait(full_bar(s), ph);
+          const float4* a = reinterpret_cast<const float4*>(smem_gen + s * C::STAGE_BYTES);
+          float4* alo = reinterpret_cast<float4*>(smem_gen + s * C::STAGE_BYTES + A_BYTES);
+#pragma unroll
+          for (int i = 0; i < A_BYTES / 16 / 64; ++i) {
+            const float4 v = a[tt + i * 64];
+            float4 r;
+            r.x = rn_tf32(v.x - trunc_tf32(v.x));
+            r.y = rn_tf32(v.y - trunc_tf32(v.y));
+            r.z = rn_tf32(v.z - trunc_tf32(v.z));
+            r.w = rn_tf32(v.w - trunc_tf32(v.w));
+            alo[tt + i * 64] = r;   // same offset => same swizzled position
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
+          __syncwarp();
+          if (lane == 0) mbar_arrive(ready_bar(s));
+        }
+      }
+    }
+  } else {
+    // ================================ epilogue: TMEM -> registers -> swizzled smem -> TMA store ================================
+    const int quad = warp & 3;                 // TMEM lane quadrant this warp may read
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
+    const uint32_t slot_base = staging_base + (uint32_t)(warp - 4) * 8192u;
+    uint8_t* slot_gen = smem_gen + STAGES * C::STAGE_BYTES + (warp - 4) * 8192;
+    int tl = 0, n_store = 0;
+    uint32_t gcount = 0;
+    constexpr int NO_ROW = 0x7fffffff;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl) {
+      const int nt = tile % p.tiles_n;
+      const int mt_all = tile / p.tiles_n;
+      const int mt = mt_all % p.tiles_m;
+      const int item = mt_all / p.tiles_m;
+      const int cb = tl & 1;
+      const int m = mt * BM + quad * 32 + lane;      // output row of this thread inside the item
+      // reflected halo copies of this row (conv.py:80-97): row -m for 1 <= m <= halo, row 2(M-1)-m near the end
+      int mir_a = NO_ROW, mir_b = NO_ROW;
+      if (p.halo > 0 && m < p.M) {
+        if (m >= 1 && m <= p.halo) mir_a = -m;
+        if (m <= p.M - 2 && m >= p.M - 1 - p.halo) mir_b = 2 * (p.M - 1) - m;
+      }
+      // one 32-column block of one output: (optionally TF32-rounded) values -> swizzled staging slot -> TMA store,
+      // plus the reflected rows
+      auto emit = [&](const float* o, int n0, const CUtensorMap* map, float* mir) {
+        auto pack = [&](int g) {
+          return p.round_out ? make_float4(rn_tf32(o[g * 4 + 0]), rn_tf32(o[g * 4 + 1]), rn_tf32(o[g * 4 + 2]), rn_tf32(o[g * 4 + 3]))
+                             : make_float4(o[g * 4 + 0], o[g * 4 + 1], o[g * 4 + 2], o[g * 4 + 3]);
+        };
+        const int slot = n_store & 1;
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // slot's previous store has read it
+        __syncwarp();
+        float4* dst = reinterpret_cast<float4*>(slot_gen + slot * 4096 + lane * 128);
+#pragma unroll
+        for (int g = 0; g < 8; ++g) dst[g ^ (lane & 7)] = pack(g);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(map, slot_base + slot * 4096, n0, mt * BM + quad * 32, item);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        ++n_store;
+        if (mir) {
+#pragma unroll 1
+          for (int e = 0; e < 2; ++e) {
+            const int mr = e ? mir_b : mir_a;
+            if (mr == NO_ROW) continue;
+            float4* mp = reinterpret_cast<float4*>(mir + (long long)item * p.out_item_stride + (long long)mr * p.N + n0);
+#pragma unroll
+            for (int g = 0; g < 8; ++g) mp[g] = pack(g);
+          }
+        }
+      };
+      auto finish_block = [&](float* o, int cc) {
+        const int n0 = nt * BN + cc;
+        if (p.bias) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + g * 4));
+            o[g * 4 + 0] += bb.x; o[g * 4 + 1] += bb.y; o[g * 4 + 2] += bb.z; o[g * 4 + 3] += bb.w;
+          }
+        }
+        if (p.store_raw) emit(o, n0, &map_raw, p.mir_raw);
+        if (p.store_elu) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = elu1(o[i]);
+          emit(o, n0, &map_elu, p.mir_elu);
+        }
+      };
+
+      if (SPLIT == 3) {
+        float acc[BN];
+        bool first = true;
+        for (int c0 = 0; c0 < nch; c0 += p.group, ++gcount) {
+          const int mb = (int)(gcount & 1u);
+          mbar_wait(mainf_bar(mb), (gcount >> 1) & 1u);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+          for (int cc = 0; cc < BN; cc += 16) {
+            uint32_t v[16];
+            tcgen05_ld16(lane_base + main_col(mb) + (uint32_t)cc, v);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[cc + i] = first ? __uint_as_float(v[i]) : acc[cc + i] + __uint_as_float(v[i]);
+          }
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(maine_bar(mb));
+          first = false;
+        }
+        mbar_wait(corrf_bar(cb), ((uint32_t)tl >> 1) & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+        for (int cc = 0; cc < BN; cc += 16) {
+          uint32_t v[16];
+          tcgen05_ld16(lane_base + corr_col(cb) + (uint32_t)cc, v);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int i = 0; i < 16; ++i) acc[cc + i] += __uint_as_float(v[i]);
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(corre_bar(cb));
+#pragma unroll
+        for (int cc = 0; cc < BN; cc += 32) {
+          finish_block(acc + cc, cc);
+        }
+      } else {
+        // single pass: one K group per tile, stream the accumulator 32 columns at a time
+        const int mb = (int)(gcount & 1u);
+        mbar_wait(mainf_bar(mb), (gcount >> 1) & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+        for (int cc = 0; cc < BN; cc += 32) {
+          uint32_t v[32];
+          tcgen05_ld32(lane_base + main_col(mb) + (uint32_t)cc, v);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          float o[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(v[i]);
+          if (cc + 32 >= BN) {   // accumulator fully read: hand it back before the stores
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(maine_bar(mb));
+          }
+          finish_block(o, cc);
+        }
+        ++gcount;
+      }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    __syncwarp();
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C::TMEM_COLS) : "memory");
+  }
+}
+
+// w [Ktot][N_src] (the CUDA-core packing, N contiguous) -> hi = rn_tf32(w), lo = rn_tf32(w - hi), both [N_pad][K_pad]
+// (K contiguous: the K-major B operand); rows n >= N_src and columns k >= Ktot are zero.
+__global__ void split_weights_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, int K,
+                                     int N, int K_pad, int N_pad) {
+  __shared__ float tile[32][33];
+  const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int k = k0 + i, n = n0 + threadIdx.x;
+    tile[i][threadIdx.x] = (k < K && n < N) ? w[(long long)k * N + n] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int n = n0 + i, k = k0 + threadIdx.x;
+    if (n < N_pad && k < K_pad) {
+      const float v = tile[threadIdx.x][i];
+      const float h = rn_tf32(v);
+      hi[(long long)n * K_pad + k] = h;
+      lo[(long long)n * K_pad + k] = rn_tf32(v - h);
+    }
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int make_map(CUtensorMap* map, const float* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+             const cuuint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  ECB_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(base), dims, strides_bytes,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  ECB_REQUIRE(r == CUDA_SUCCESS,
+              "cuTensorMapEncodeTiled failed with CUresult %d (rank %d, base %p, dims %llu x %llu x %llu, strides %llu, %llu)",
+              (int)r, rank, (const void*)base, (unsigned long long)dims[0], (unsigned long long)dims[1],
+              (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)strides_bytes[0],
+              (unsigned long long)(rank > 2 ? strides_bytes[1] : 0));
+  return 0;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BN, int SPLIT>
+int launch_one(const CUtensorMap* maps, const TcArgs& a, int grid, cudaStream_t stream) {
+  using C = Cfg<BN, SPLIT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ECB_CUDA(cudaFuncSetAttribute(tc_conv_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  tc_conv_kernel<BN, SPLIT><<<grid, TC_THREADS, C::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], a);
+  ECB_LAUNCHED();
+  return 0;
+}
+
+}  // namespace
+
+int launch_split_weights(const float* w, float* hi, float* lo, int K, int N, int K_pad, int N_pad, cudaStream_t s) {
+  dim3 grid((unsigned)cdiv(K_pad, 32), (unsigned)cdiv(N_pad, 32));
+  split_weights_kernel<<<grid, dim3(32, 8), 0, s>>>(w, hi, lo, K, N, K_pad, N_pad);
+  ECB_LAUNCHED();
+  return 0;
+}
+
+int tc_pick_bn(int N, int split) {
+  if (split == 3) return N % 128 == 0 ? 128 : (N % 64 == 0 ? 64 : 32);
+  return N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : (N % 64 == 0 ? 64 : 32));
+}
+
+int launch_tc_conv(const TcConvParams& p, cudaStream_t stream) {
+  ECB_REQUIRE(p.split == 1 || p.split == 3, "tc_conv: split must be 1 or 3");
+  ECB_REQUIRE(p.N % 32 == 0 && p.N > 0, "tc_conv: N=%d must be a multiple of 32", p.N);
+  ECB_REQUIRE(p.C0 % 32 == 0 && p.taps >= 1 && p.stride >= 1, "tc_conv: C0=%d must be a multiple of 32", p.C0);
+  ECB_REQUIRE(p.a1 == nullptr || p.C1 % 32 == 0, "tc_conv: C1=%d must be a multiple of 32", p.C1);
+  ECB_REQUIRE(p.M > 0 && p.n_items > 0, "tc_conv: bad M=%lld / items=%d", p.M, p.n_items);
+  ECB_REQUIRE(p.out_raw || p.out_elu, "tc_conv: no output");
+  ECB_REQUIRE(p.halo == 0 || p.M > p.halo, "tc_conv: %lld rows are too few for a %d-row reflected halo", p.M, p.halo);
+  const int bn = tc_pick_bn(p.N, p.split);
+  const int s = p.stride;
+  const int ktot = p.taps * p.C0 + (p.a1 ? p.C1 : 0);
+  CUtensorMap maps[6];
+  TcArgs a;
+  {
+    // folded view of source 0: rows of s*C0 floats; the fold is aligned so that output row 0's window starts a folded
+    // row: first mapped sample b0 = smallest sample >= a0_first congruent to -pad_left (mod s)
+    long long d = (-(long long)p.pad_left - p.a0_first) % s;
+    if (d < 0) d += s;
+    const long long b0 = p.a0_first + d;
+    const long long rows = (p.a0_first + p.a0_rows - b0) / s;
+    ECB_REQUIRE(rows > 0, "tc_conv: empty source");
+    a.row_base0 = (int)((-(long long)p.pad_left - b0) / s);   // exact; may be negative (TMA zero fill)
+    a.rowlen0 = s * p.C0;
+    const cuuint64_t dims[3] = {(cuuint64_t)s * p.C0, (cuuint64_t)rows, (cuuint64_t)p.n_items};
+    const cuuint64_t strides[2] = {(cuuint64_t)s * p.C0 * 4, (cuuint64_t)p.a0_item_stride * 4};
+    const cuuint32_t box[3] = {BK, BM, 1};
+    if (make_map(&maps[0], p.a0 + d * p.C0, 3, dims, strides, box)) return 1;
+  }
+  if (p.a1) {
+    const cuuint64_t dims[3] = {(cuuint64_t)p.C1, (cuuint64_t)p.a1_rows, (cuuint64_t)p.n_items};
+    const cuuint64_t strides[2] = {(cuuint64_t)p.C1 * 4, (cuuint64_t)p.a1_item_stride * 4};
+    const cuuint32_t box[3] = {BK, BM, 1};
+    if (make_map(&maps[1], p.a1, 3, dims, strides, box)) return 1;
+  } else {
+    maps[1] = maps[0];
+  }
+  {
+    const cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)p.N};
+    const cuuint64_t strides[1] = {(cuuint64_t)ktot * 4};
+    const cuuint32_t box[2] = {BK, (cuuint32_t)bn};
+    if (make_map(&maps[2], p.w_hi, 2, dims, strides, box)) return 1;
+    if (make_map(&maps[3], p.split == 3 ? p.w_lo : p.w_hi, 2, dims, strides, box)) return 1;
+  }
+  {
+    const cuuint64_t dims[3] = {(cuuint64_t)p.N, (cuuint64_t)p.M, (cuuint64_t)p.n_items};
+    const cuuint64_t strides[2] = {(cuuint64_t)p.N * 4, (cuuint64_t)p.out_item_stride * 4};
+    const cuuint32_t box[3] = {32, 32, 1};
+    float* raw = p.out_raw ? p.out_raw : p.out_elu;
+    float* elu = p.out_elu ? p.out_elu : p.out_raw;
+    if (make_map(&maps[4], raw, 3, dims, strides, box)) return 1;
+    if (make_map(&maps[5], elu, 3, dims, strides, box)) return 1;
+  }
+  a.bias = p.bias;
+  a.mir_raw = p.halo > 0 ? p.out_raw : nullptr;
+  a.mir_elu = p.halo > 0 ? p.out_elu : nullptr;
+  a.out_item_stride = p.out_item_stride;
+  a.N = p.N;
+  a.M = (int)p.M;
+  a.n_items = p.n_items;
+  a.tiles_m = (int)cdiv(p.M, BM);
+  a.tiles_n = p.N / bn;
+  const long long total = (long long)a.tiles_m * a.tiles_n * p.n_items;
+  ECB_REQUIRE(total < (1LL << 31), "tc_conv: too many tiles");
+  a.total_tiles = (int)total;
+  a.nch0 = p.taps * p.C0 / BK;
+  a.nch1 = p.a1 ? p.C1 / BK : 0;
+  a.row_base1 = 0;
+  a.store_raw = p.out_raw != nullptr;
+  a.store_elu = p.out_elu != nullptr;
+  a.round_out = p.round_out;
+  a.halo = p.halo;
+  {
+    const int nch = a.nch0 + a.nch1;
+    a.group = (p.split == 3 && nch > 6) ? 4 : nch;   // <= 24 truncating accumulation steps per group
+  }
+  const int grid = (int)(total < sm_count() ? total : sm_count());
+  const double rows = (double)p.M * p.n_items;
+  ProfScope prof(PROF_TC_CONV, stream, 2.0 * rows * p.N * ktot,
+                 4.0 * (rows * s * p.C0 + (p.a1 ? rows * p.C1 : 0.0) + (double)ktot * p.N +
+                        rows * p.N * (a.store_raw + a.store_elu)));
+#define ECB_TC_CASE(BN_, SP_) \
+  if (bn == BN_ && p.split == SP_) return launch_one<BN_, SP_>(maps, a, grid, stream);
+  ECB_TC_CASE(32, 3)
+  ECB_TC_CASE(64, 3)
+  ECB_TC_CASE(128, 3)
+  ECB_TC_CASE(32, 1)
+  ECB_TC_CASE(64, 1)
+  ECB_TC_CASE(128, 1)
+  ECB_TC_CASE(256, 1)
+#undef ECB_TC_CASE
+  set_error("tc_conv: no kernel for BN=%d split=%d", bn, p.split);
+  return 1;
+}
+
+}  // namespace ecb

@@ -136,6 +136,18 @@ int ecb_transpose_btc_to_bct(const float* in, float* out, int64_t batch, int64_t
  * buf (at most `capacity` floats). buf == NULL disables the tap. */
 void ecb_debug_tap(float* buf, int64_t capacity, int32_t stage);
 
+/* Diagnostic (tests only): one launch of the tensor-core implicit-GEMM convolution (csrc/tc_conv.cu) on caller
+ * buffers. a0 points at (item 0, sample a0_first, channel 0) of a channels-last activation from which a0_rows
+ * samples per item are addressable (reads outside are zero); output row m reads samples
+ * m*stride - pad_left ... + taps - 1 of source 0, then row m of the optional 1-tap source a1. w is [taps*C0 + C1][N]
+ * (N contiguous). out_raw / out_elu point at (item 0, row 0) of [M][N] outputs with `halo` reflected rows written
+ * before and after each item. split = 3: fp32-accurate split-operand TF32, 1: single TF32 pass. Synchronises. */
+int ecb_debug_tc_conv(const float* a0, int64_t a0_item_stride, int32_t C0, int64_t a0_first, int64_t a0_rows,
+                      int32_t taps, int32_t stride, int32_t pad_left, const float* a1, int64_t a1_item_stride,
+                      int32_t C1, int64_t a1_rows, const float* w, const float* bias, int32_t N, int64_t M,
+                      int32_t n_items, float* out_raw, float* out_elu, int64_t out_item_stride, int32_t halo,
+                      int32_t round_out, int32_t split, void* stream);
+
 /* Per-kernel-class timing for bench.py's roofline leg. Between ecb_profile_begin() and ecb_profile_end()
  * every launch of this library is bracketed by CUDA events on its stream; ecb_profile_end() synchronises
  * them and returns one entry per kernel class that ran: launch count, summed device milliseconds, and the
