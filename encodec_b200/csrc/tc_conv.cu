@@ -38,8 +38,8 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 32;                      // fp32 per K chunk = one 128-byte swizzle row
 constexpr int A_BYTES = BM * BK * 4;        // 16 KB
-constexpr int TC_THREADS = 256;              // 8 warps: TMA, MMA, 2 x transform, 4 x epilogue
-constexpr int STAGING_BYTES = 4 * 2 * 4096; // 4 epilogue warps x 2 slots x [32 rows x 128 B]
+constexpr int TC_THREADS = 384;              // 12 warps: TMA, MMA, 2 x transform, 8 x epilogue
+constexpr int STAGING_BYTES = 8 * 2048;     // 8 epilogue warps x [32 rows x 64 B]
 
 template <int BN, int SPLIT>
 struct Cfg {
@@ -56,15 +56,15 @@ struct Cfg {
 
 struct TcArgs {
   const float* bias;        // [N] or nullptr
-  float* mir_raw;           // direct-store base (item 0, row 0) for the reflected halo rows, or nullptr
-  float* mir_elu;
+  float* out_raw;           // (item 0, row 0) of the raw output, or nullptr
+  float* out_elu;           // same for the ELU output
   long long out_item_stride;
   int N, M, n_items;
   int tiles_m, tiles_n, total_tiles;
   int nch0, nch1;           // K chunks of source 0 / source 1
   int rowlen0;              // floats per folded row of source 0 (stride * C0)
   int row_base0, row_base1; // row coordinate of output row 0's first chunk in each source's map
-  int store_raw, store_elu, round_out, halo;
+  int round_out, halo;
   int group;                // K chunks per main-accumulator group (SPLIT == 1: all of them)
 };
 
@@ -143,11 +143,16 @@ __device__ __forceinline__ void tcgen05_ld16(uint32_t taddr, uint32_t (&v)[16]) 
       : "r"(taddr)
       : "memory");
 }
-__device__ __forceinline__ float rn_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+__device__ __forceinline__ void tcgen05_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
 }
+// round-to-nearest (ties away from zero, as cvt.rna.tf32.f32) in two integer instructions: add half an ulp of the
+// 10-bit mantissa and truncate. Inputs are finite activations / weights (no NaN / Inf handling needed).
+__device__ __forceinline__ float rn_tf32(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
 __device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100): start address >> 4 in
@@ -163,11 +168,38 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32(int m, int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
+
+// Copy one staged [32 rows x 64 B] half block out of shared memory with coalesced 16-byte stores (four lanes per
+// 64-byte row segment, 8 rows per warp instruction): raw output as is, ELU output through elu1. The output modes are
+// template parameters so that the loop body is nothing but LDS -> (ELU) -> STG.
+template <bool RAW, bool ELU, bool ROUND>
+__device__ __forceinline__ void copy_out_rows(const uint8_t* slot, int lane, float* praw, float* pelu, long long row_step,
+                                              int rows_left) {
+  const int c16 = lane & 3;
+  int rr = lane >> 2;
+  praw += (long long)rr * (row_step >> 3);
+  pelu += (long long)rr * (row_step >> 3);
+#pragma unroll 2
+  for (int i = 0; i < 4; ++i, rr += 8) {
+    if (rr >= rows_left) break;
+    const float4 v = *reinterpret_cast<const float4*>(slot + rr * 64 + ((c16 ^ ((rr >> 1) & 3)) << 4));
+    if (RAW) {
+      *reinterpret_cast<float4*>(praw) = ROUND ? make_float4(rn_tf32(v.x), rn_tf32(v.y), rn_tf32(v.z), rn_tf32(v.w)) : v;
+      praw += row_step;
+    }
+    if (ELU) {
+      float4 w = make_float4(elu1(v.x), elu1(v.y), elu1(v.z), elu1(v.w));
+      if (ROUND) w = make_float4(rn_tf32(w.x), rn_tf32(w.y), rn_tf32(w.z), rn_tf32(w.w));
+      *reinterpret_cast<float4*>(pelu) = w;
+      pelu += row_step;
+    }
+  }
+}
+
 template <int BN, int SPLIT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
-               const __grid_constant__ CUtensorMap map_raw, const __grid_constant__ CUtensorMap map_elu,
                const TcArgs p) {
   using C = Cfg<BN, SPLIT>;
   constexpr int STAGES = C::STAGES;
@@ -197,9 +229,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(mainf_bar(b), 1);
-      mbar_init(maine_bar(b), 4);   // one arrive per epilogue warp
+      mbar_init(maine_bar(b), 8);   // one arrive per epilogue warp
       mbar_init(corrf_bar(b), 1);
-      mbar_init(corre_bar(b), 4);
+      mbar_init(corre_bar(b), 8);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -326,137 +358,167 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       }
     }
   } else {
-    // ================================ epilogue: TMEM -> registers -> swizzled smem -> TMA store ================================
-    const int quad = warp & 3;                 // TMEM lane quadrant this warp may read
-    const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
-    const uint32_t slot_base = staging_base + (uint32_t)(warp - 4) * 8192u;
-    uint8_t* slot_gen = smem_gen + STAGES * C::STAGE_BYTES + (warp - 4) * 8192;
-    int tl = 0, n_store = 0;
+    // ================================ epilogue: TMEM -> registers -> staging slot -> coalesced global stores ================================
+    // Eight warps: warp w reads TMEM lane quadrant w % 4 (hardware rule) and, of every 32-column block, the 16-column
+    // half (w - 4) / 4. The element-wise work (bias, ELU, optional TF32 rounding) is ~20 instructions per output
+    // element, which is what sizes this warp group.
+    const int quad = warp & 3;
+    const int half = (warp - 4) >> 2;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 16);
+    uint8_t* slot_gen = smem_gen + STAGES * C::STAGE_BYTES + (warp - 4) * 2048;   // this warp's [32 rows x 64 B] staging slot
+    int tl = 0;
     uint32_t gcount = 0;
-    constexpr int NO_ROW = 0x7fffffff;
+    const int out_mode = (p.out_raw ? 1 : 0) | (p.out_elu ? 2 : 0) | (p.round_out ? 4 : 0);
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl) {
       const int nt = tile % p.tiles_n;
       const int mt_all = tile / p.tiles_n;
       const int mt = mt_all % p.tiles_m;
       const int item = mt_all / p.tiles_m;
       const int cb = tl & 1;
-      const int m = mt * BM + quad * 32 + lane;      // output row of this thread inside the item
-      // reflected halo copies of this row (conv.py:80-97): row -m for 1 <= m <= halo, row 2(M-1)-m near the end
-      int mir_a = NO_ROW, mir_b = NO_ROW;
-      if (p.halo > 0 && m < p.M) {
-        if (m >= 1 && m <= p.halo) mir_a = -m;
-        if (m <= p.M - 2 && m >= p.M - 1 - p.halo) mir_b = 2 * (p.M - 1) - m;
-      }
-      // one 32-column block of one output: (optionally TF32-rounded) values -> swizzled staging slot -> TMA store,
-      // plus the reflected rows
-      auto emit = [&](const float* o, int n0, const CUtensorMap* map, float* mir) {
-        auto pack = [&](int g) {
-          return p.round_out ? make_float4(rn_tf32(o[g * 4 + 0]), rn_tf32(o[g * 4 + 1]), rn_tf32(o[g * 4 + 2]), rn_tf32(o[g * 4 + 3]))
-                             : make_float4(o[g * 4 + 0], o[g * 4 + 1], o[g * 4 + 2], o[g * 4 + 3]);
-        };
-        const int slot = n_store & 1;
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // slot's previous store has read it
-        __syncwarp();
-        float4* dst = reinterpret_cast<float4*>(slot_gen + slot * 4096 + lane * 128);
+      const int m_warp = mt * BM + quad * 32;       // first output row of this warp
+      // does this warp hold rows whose reflected copies (conv.py:80-97) must be written too?
+      const bool mirrors = p.halo > 0 && (m_warp <= p.halo || m_warp + 31 >= p.M - 1 - p.halo);
+
+      // One 16-column half block: the bias-added values go to this warp's staging slot in a chunk-swizzled layout, then
+      // the warp copies the slot out with coalesced 16-byte stores (four lanes per 64-byte row segment): the raw
+      // output as is, the ELU output through elu1 in the same pass, plus the reflected halo rows where they exist.
+      auto finish_block = [&](const float* o, int cc) {
+        const int n0 = nt * BN + cc + half * 16;
+        __syncwarp();   // the previous block's copy-out is done with the slot
+        float4* s0 = reinterpret_cast<float4*>(slot_gen + lane * 64);
 #pragma unroll
-        for (int g = 0; g < 8; ++g) dst[g ^ (lane & 7)] = pack(g);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_3d(map, slot_base + slot * 4096, n0, mt * BM + quad * 32, item);
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        }
-        ++n_store;
-        if (mir) {
-#pragma unroll 1
-          for (int e = 0; e < 2; ++e) {
-            const int mr = e ? mir_b : mir_a;
-            if (mr == NO_ROW) continue;
-            float4* mp = reinterpret_cast<float4*>(mir + (long long)item * p.out_item_stride + (long long)mr * p.N + n0);
-#pragma unroll
-            for (int g = 0; g < 8; ++g) mp[g] = pack(g);
-          }
-        }
-      };
-      auto finish_block = [&](float* o, int cc) {
-        const int n0 = nt * BN + cc;
-        if (p.bias) {
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
+        for (int g = 0; g < 4; ++g) {
+          float4 v = make_float4(o[g * 4 + 0], o[g * 4 + 1], o[g * 4 + 2], o[g * 4 + 3]);
+          if (p.bias) {
             const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + g * 4));
-            o[g * 4 + 0] += bb.x; o[g * 4 + 1] += bb.y; o[g * 4 + 2] += bb.z; o[g * 4 + 3] += bb.w;
+            v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w;
           }
+          s0[g ^ ((lane >> 1) & 3)] = v;
         }
-        if (p.store_raw) emit(o, n0, &map_raw, p.mir_raw);
-        if (p.store_elu) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = elu1(o[i]);
-          emit(o, n0, &map_elu, p.mir_elu);
+        __syncwarp();
+        const long long base = (long long)item * p.out_item_stride + (long long)m_warp * p.N + n0 + (lane & 3) * 4;
+        const int rows_left = p.M - m_warp;
+        if (!mirrors) {
+          const long long step = 8LL * p.N;
+          float* praw = p.out_raw + base;   // only dereferenced when the mode says so
+          float* pelu = p.out_elu + base;
+          switch (out_mode) {
+            case 1: copy_out_rows<true, false, false>(slot_gen, lane, praw, pelu, step, rows_left); break;
+            case 2: copy_out_rows<false, true, false>(slot_gen, lane, praw, pelu, step, rows_left); break;
+            case 3: copy_out_rows<true, true, false>(slot_gen, lane, praw, pelu, step, rows_left); break;
+            case 5: copy_out_rows<true, false, true>(slot_gen, lane, praw, pelu, step, rows_left); break;
+            case 6: copy_out_rows<false, true, true>(slot_gen, lane, praw, pelu, step, rows_left); break;
+            default: copy_out_rows<true, true, true>(slot_gen, lane, praw, pelu, step, rows_left); break;
+          }
+        } else {
+          // first / last rows of an item: also write the reflected copies (conv.py:80-97); rare, generic loop
+          const int c16 = lane & 3;
+#pragma unroll 1
+          for (int i = 0; i < 4; ++i) {
+            const int rr = (lane >> 2) + 8 * i;
+            const int m = m_warp + rr;
+            if (rr >= rows_left) break;
+            const float4 v = *reinterpret_cast<const float4*>(slot_gen + rr * 64 + ((c16 ^ ((rr >> 1) & 3)) << 4));
+            long long d1 = 0, d2 = 0;
+            if (m >= 1 && m <= p.halo) d1 = -2LL * m * p.N;
+            if (m <= p.M - 2 && m >= p.M - 1 - p.halo) d2 = 2LL * (p.M - 1 - m) * p.N;
+            const long long off = base + (long long)rr * p.N;
+            if (p.out_raw) {
+              const float4 w = p.round_out ? make_float4(rn_tf32(v.x), rn_tf32(v.y), rn_tf32(v.z), rn_tf32(v.w)) : v;
+              *reinterpret_cast<float4*>(p.out_raw + off) = w;
+              if (d1) *reinterpret_cast<float4*>(p.out_raw + off + d1) = w;
+              if (d2) *reinterpret_cast<float4*>(p.out_raw + off + d2) = w;
+            }
+            if (p.out_elu) {
+              float4 w = make_float4(elu1(v.x), elu1(v.y), elu1(v.z), elu1(v.w));
+              if (p.round_out) w = make_float4(rn_tf32(w.x), rn_tf32(w.y), rn_tf32(w.z), rn_tf32(w.w));
+              *reinterpret_cast<float4*>(p.out_elu + off) = w;
+              if (d1) *reinterpret_cast<float4*>(p.out_elu + off + d1) = w;
+              if (d2) *reinterpret_cast<float4*>(p.out_elu + off + d2) = w;
+            }
+          }
         }
       };
 
-      if (SPLIT == 3) {
-        float acc[BN];
-        bool first = true;
-        for (int c0 = 0; c0 < nch; c0 += p.group, ++gcount) {
+      // Where the finished fp32 tile is read from: TMEM columns src_col (+ add_col when the correction accumulator
+      // still has to be added), this warp's 16 columns of every 32-column block.
+      const uint32_t g_first = gcount;
+      const int n_groups = (nch + p.group - 1) / p.group;
+      const int mb_last = (int)((g_first + (uint32_t)n_groups - 1u) & 1u);
+      const uint32_t src_col = main_col(mb_last);
+      uint32_t add_col = 0xffffffffu;
+      if (SPLIT == 3 && n_groups > 1) {
+        // several K groups: re-accumulate the main accumulator in registers (round-to-nearest), add the corrections,
+        // park the sum back in the last group's TMEM buffer and stream it out from there
+        float acc[BN / 2];
+        for (int g = 0; g < n_groups; ++g, ++gcount) {
           const int mb = (int)(gcount & 1u);
           mbar_wait(mainf_bar(mb), (gcount >> 1) & 1u);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-          for (int cc = 0; cc < BN; cc += 16) {
+          for (int cc = 0; cc < BN; cc += 32) {
             uint32_t v[16];
             tcgen05_ld16(lane_base + main_col(mb) + (uint32_t)cc, v);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-            for (int i = 0; i < 16; ++i) acc[cc + i] = first ? __uint_as_float(v[i]) : acc[cc + i] + __uint_as_float(v[i]);
+            for (int i = 0; i < 16; ++i)
+              acc[cc / 2 + i] = g == 0 ? __uint_as_float(v[i]) : acc[cc / 2 + i] + __uint_as_float(v[i]);
           }
-          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          __syncwarp();
-          if (lane == 0) mbar_arrive(maine_bar(mb));
-          first = false;
-        }
-        mbar_wait(corrf_bar(cb), ((uint32_t)tl >> 1) & 1u);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-        for (int cc = 0; cc < BN; cc += 16) {
-          uint32_t v[16];
-          tcgen05_ld16(lane_base + corr_col(cb) + (uint32_t)cc, v);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-          for (int i = 0; i < 16; ++i) acc[cc + i] += __uint_as_float(v[i]);
-        }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) mbar_arrive(corre_bar(cb));
-#pragma unroll
-        for (int cc = 0; cc < BN; cc += 32) {
-          finish_block(acc + cc, cc);
-        }
-      } else {
-        // single pass: one K group per tile, stream the accumulator 32 columns at a time
-        const int mb = (int)(gcount & 1u);
-        mbar_wait(mainf_bar(mb), (gcount >> 1) & 1u);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll 1
-        for (int cc = 0; cc < BN; cc += 32) {
-          uint32_t v[32];
-          tcgen05_ld32(lane_base + main_col(mb) + (uint32_t)cc, v);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          float o[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(v[i]);
-          if (cc + 32 >= BN) {   // accumulator fully read: hand it back before the stores
+          if (g + 1 < n_groups) {
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(maine_bar(mb));
           }
-          finish_block(o, cc);
         }
+        mbar_wait(corrf_bar(cb), ((uint32_t)tl >> 1) & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+        for (int cc = 0; cc < BN; cc += 32) {
+          uint32_t v[16];
+          tcgen05_ld16(lane_base + corr_col(cb) + (uint32_t)cc, v);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(acc[cc / 2 + i] + __uint_as_float(v[i]));
+          tcgen05_st16(lane_base + src_col + (uint32_t)cc, v);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(corre_bar(cb));
+      } else {
+        mbar_wait(mainf_bar(mb_last), (gcount >> 1) & 1u);
         ++gcount;
+        if (SPLIT == 3) {
+          mbar_wait(corrf_bar(cb), ((uint32_t)tl >> 1) & 1u);
+          add_col = corr_col(cb);
+        }
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      }
+#pragma unroll 1
+      for (int cc = 0; cc < BN; cc += 32) {
+        uint32_t v[16];
+        float o[16];
+        tcgen05_ld16(lane_base + src_col + (uint32_t)cc, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o[i] = __uint_as_float(v[i]);
+        if (add_col != 0xffffffffu) {
+          tcgen05_ld16(lane_base + add_col + (uint32_t)cc, v);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int i = 0; i < 16; ++i) o[i] += __uint_as_float(v[i]);
+        }
+        if (cc + 32 >= BN) {   // accumulators fully read: hand them back before the stores
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(maine_bar(mb_last));
+            if (add_col != 0xffffffffu) mbar_arrive(corre_bar(cb));
+          }
+        }
+        finish_block(o, cc);
       }
     }
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-    __syncwarp();
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -539,7 +601,7 @@ int launch_one(const CUtensorMap* maps, const TcArgs& a, int grid, cudaStream_t 
     ECB_CUDA(cudaFuncSetAttribute(tc_conv_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
-  tc_conv_kernel<BN, SPLIT><<<grid, TC_THREADS, C::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], a);
+  tc_conv_kernel<BN, SPLIT><<<grid, TC_THREADS, C::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], a);
   ECB_LAUNCHED();
   return 0;
 }
@@ -569,7 +631,7 @@ int launch_tc_conv(const TcConvParams& p, cudaStream_t stream) {
   const int bn = tc_pick_bn(p.N, p.split);
   const int s = p.stride;
   const int ktot = p.taps * p.C0 + (p.a1 ? p.C1 : 0);
-  CUtensorMap maps[6];
+  CUtensorMap maps[4];
   TcArgs a;
   {
     // folded view of source 0: rows of s*C0 floats; the fold is aligned so that output row 0's window starts a folded
@@ -601,18 +663,9 @@ int launch_tc_conv(const TcConvParams& p, cudaStream_t stream) {
     if (make_map(&maps[2], p.w_hi, 2, dims, strides, box)) return 1;
     if (make_map(&maps[3], p.split == 3 ? p.w_lo : p.w_hi, 2, dims, strides, box)) return 1;
   }
-  {
-    const cuuint64_t dims[3] = {(cuuint64_t)p.N, (cuuint64_t)p.M, (cuuint64_t)p.n_items};
-    const cuuint64_t strides[2] = {(cuuint64_t)p.N * 4, (cuuint64_t)p.out_item_stride * 4};
-    const cuuint32_t box[3] = {32, 32, 1};
-    float* raw = p.out_raw ? p.out_raw : p.out_elu;
-    float* elu = p.out_elu ? p.out_elu : p.out_raw;
-    if (make_map(&maps[4], raw, 3, dims, strides, box)) return 1;
-    if (make_map(&maps[5], elu, 3, dims, strides, box)) return 1;
-  }
   a.bias = p.bias;
-  a.mir_raw = p.halo > 0 ? p.out_raw : nullptr;
-  a.mir_elu = p.halo > 0 ? p.out_elu : nullptr;
+  a.out_raw = p.out_raw;
+  a.out_elu = p.out_elu;
   a.out_item_stride = p.out_item_stride;
   a.N = p.N;
   a.M = (int)p.M;
@@ -625,8 +678,6 @@ int launch_tc_conv(const TcConvParams& p, cudaStream_t stream) {
   a.nch0 = p.taps * p.C0 / BK;
   a.nch1 = p.a1 ? p.C1 / BK : 0;
   a.row_base1 = 0;
-  a.store_raw = p.out_raw != nullptr;
-  a.store_elu = p.out_elu != nullptr;
   a.round_out = p.round_out;
   a.halo = p.halo;
   {
@@ -637,7 +688,7 @@ int launch_tc_conv(const TcConvParams& p, cudaStream_t stream) {
   const double rows = (double)p.M * p.n_items;
   ProfScope prof(PROF_TC_CONV, stream, 2.0 * rows * p.N * ktot,
                  4.0 * (rows * s * p.C0 + (p.a1 ? rows * p.C1 : 0.0) + (double)ktot * p.N +
-                        rows * p.N * (a.store_raw + a.store_elu)));
+                        rows * p.N * ((p.out_raw ? 1 : 0) + (p.out_elu ? 1 : 0))));
 #define ECB_TC_CASE(BN_, SP_) \
   if (bn == BN_ && p.split == SP_) return launch_one<BN_, SP_>(maps, a, grid, stream);
   ECB_TC_CASE(32, 3)
