@@ -211,11 +211,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto ready_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto empty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
-  auto mainf_bar = [&](int b) { return bar_base + 8u * (3 * STAGES + b); };       // main accumulator b holds a finished K group
+  auto mainf_bar = [&](int b) { return bar_base + 8u * (3 * STAGES + b); };       // accumulator b holds a finished K group
   auto maine_bar = [&](int b) { return bar_base + 8u * (3 * STAGES + 2 + b); };   // ... has been drained by the epilogue
-  auto corrf_bar = [&](int b) { return bar_base + 8u * (3 * STAGES + 4 + b); };   // correction accumulator b is complete (tile end)
-  auto corre_bar = [&](int b) { return bar_base + 8u * (3 * STAGES + 6 + b); };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + STAGES * C::STAGE_BYTES + STAGING_BYTES + 8 * (3 * STAGES + 8));
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + STAGES * C::STAGE_BYTES + STAGING_BYTES + 8 * (3 * STAGES + 4));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -230,8 +228,6 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     for (int b = 0; b < 2; ++b) {
       mbar_init(mainf_bar(b), 1);
       mbar_init(maine_bar(b), 8);   // one arrive per epilogue warp
-      mbar_init(corrf_bar(b), 1);
-      mbar_init(corre_bar(b), 8);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -245,9 +241,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
-  // TMEM columns: main accumulators [0, 2 BN), correction accumulators [2 BN, 4 BN) (SPLIT == 3 only)
-  auto main_col = [&](int b) { return (uint32_t)(b * BN); };
-  auto corr_col = [&](int b) { return (uint32_t)(2 * BN + b * BN); };
+  // TMEM columns of accumulator buffer b: SPLIT == 3: [main | correction] = 2 BN columns, SPLIT == 1: BN columns
+  constexpr int ACC_COLS = (SPLIT == 3) ? 2 * BN : BN;
+  auto main_col = [&](int b) { return (uint32_t)(b * ACC_COLS); };
 
   if (warp == 0) {
     // ================================ TMA producer ================================
@@ -280,20 +276,17 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
     // The tensor core truncates when it adds into the fp32 accumulator, a bias of ~1.7e-8 per accumulation step.
-    // The large a*w_hi products therefore go to a MAIN accumulator that the epilogue drains and re-accumulates in
-    // registers (round-to-nearest) every `group` K chunks, alternating between two TMEM buffers; the small
-    // correction products (2^-11 of the result, their truncation is irrelevant) accumulate over the whole tile.
+    // The large a*w_hi products therefore go to a MAIN accumulator and the small correction products (2^-11 of the
+    // result: their truncation is irrelevant) to a CORRECTION accumulator in the adjacent TMEM columns; the epilogue
+    // drains both every `group` K chunks and re-accumulates in registers (round-to-nearest), alternating between two
+    // TMEM buffers. Per K step: D[main | corr] (+)= a * [w_hi | w_lo] (one MMA, N = 2 BN: w_lo's tile follows w_hi's
+    // in shared memory) and D[corr] += a_lo * w_hi.
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_tf32(BM, BN);
-      int it = 0, tl = 0;
+      constexpr uint32_t idesc2 = umma_idesc_tf32(BM, SPLIT == 3 ? 2 * BN : BN);
+      int it = 0;
       uint32_t gcount = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl) {
-        const int cb = tl & 1;
-        if (SPLIT == 3) {
-          mbar_wait(corre_bar(cb), (((uint32_t)tl >> 1) & 1u) ^ 1u);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        }
-        const uint32_t d_corr = tmem_base + corr_col(cb);
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         for (int c0 = 0; c0 < nch; c0 += p.group, ++gcount) {
           const int c1 = min(c0 + p.group, nch);
           const int mb = (int)(gcount & 1u);
@@ -309,24 +302,20 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             const uint32_t a_addr = smem_base + s * C::STAGE_BYTES;
             const uint32_t alo_addr = a_addr + A_BYTES;
             const uint32_t bhi_addr = a_addr + (SPLIT == 3 ? 2 : 1) * A_BYTES;
-            const uint32_t blo_addr = bhi_addr + C::B_BYTES;
 #pragma unroll
             for (int k = 0; k < BK / 8; ++k) {
               const uint64_t da = umma_desc_sw128(a_addr + k * 32);
               const uint64_t dbh = umma_desc_sw128(bhi_addr + k * 32);
-              tcgen05_mma_tf32(d_main, da, dbh, idesc, (c > c0 || k > 0) ? 1u : 0u);
+              tcgen05_mma_tf32(d_main, da, dbh, idesc2, (c > c0 || k > 0) ? 1u : 0u);
               if (SPLIT == 3) {
                 const uint64_t dal = umma_desc_sw128(alo_addr + k * 32);
-                const uint64_t dbl = umma_desc_sw128(blo_addr + k * 32);
-                tcgen05_mma_tf32(d_corr, dal, dbh, idesc, (c > 0 || k > 0) ? 1u : 0u);
-                tcgen05_mma_tf32(d_corr, da, dbl, idesc, 1u);
+                tcgen05_mma_tf32(d_main + BN, dal, dbh, idesc, 1u);
               }
             }
             tcgen05_commit(empty_bar(s));   // frees the stage once these MMAs have read it
           }
           tcgen05_commit(mainf_bar(mb));    // K group complete -> epilogue
         }
-        if (SPLIT == 3) tcgen05_commit(corrf_bar(cb));
       }
     }
   } else if (warp < 4) {
@@ -366,15 +355,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     const int half = (warp - 4) >> 2;
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 16);
     uint8_t* slot_gen = smem_gen + STAGES * C::STAGE_BYTES + (warp - 4) * 2048;   // this warp's [32 rows x 64 B] staging slot
-    int tl = 0;
     uint32_t gcount = 0;
     const int out_mode = (p.out_raw ? 1 : 0) | (p.out_elu ? 2 : 0) | (p.round_out ? 4 : 0);
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tl) {
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int nt = tile % p.tiles_n;
       const int mt_all = tile / p.tiles_n;
       const int mt = mt_all % p.tiles_m;
       const int item = mt_all / p.tiles_m;
-      const int cb = tl & 1;
       const int m_warp = mt * BM + quad * 32;       // first output row of this warp
       // does this warp hold rows whose reflected copies (conv.py:80-97) must be written too?
       const bool mirrors = p.halo > 0 && (m_warp <= p.halo || m_warp + 31 >= p.M - 1 - p.halo);
@@ -440,16 +427,15 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         }
       };
 
-      // Where the finished fp32 tile is read from: TMEM columns src_col (+ add_col when the correction accumulator
-      // still has to be added), this warp's 16 columns of every 32-column block.
-      const uint32_t g_first = gcount;
+      // Where the finished fp32 tile is read from: TMEM columns src_col (+ the correction columns BN further when
+      // they still have to be added), this warp's 16 columns of every 32-column block.
       const int n_groups = (nch + p.group - 1) / p.group;
-      const int mb_last = (int)((g_first + (uint32_t)n_groups - 1u) & 1u);
+      const int mb_last = (int)((gcount + (uint32_t)n_groups - 1u) & 1u);
       const uint32_t src_col = main_col(mb_last);
-      uint32_t add_col = 0xffffffffu;
+      bool add_corr = (SPLIT == 3);
       if (SPLIT == 3 && n_groups > 1) {
-        // several K groups: re-accumulate the main accumulator in registers (round-to-nearest), add the corrections,
-        // park the sum back in the last group's TMEM buffer and stream it out from there
+        // several K groups: re-accumulate main + correction in registers (round-to-nearest), park the sum back in the
+        // last group's TMEM buffer and stream it out from there
         float acc[BN / 2];
         for (int g = 0; g < n_groups; ++g, ++gcount) {
           const int mb = (int)(gcount & 1u);
@@ -457,12 +443,15 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
           for (int cc = 0; cc < BN; cc += 32) {
-            uint32_t v[16];
+            uint32_t v[16], w[16];
             tcgen05_ld16(lane_base + main_col(mb) + (uint32_t)cc, v);
+            tcgen05_ld16(lane_base + main_col(mb) + (uint32_t)(BN + cc), w);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-              acc[cc / 2 + i] = g == 0 ? __uint_as_float(v[i]) : acc[cc / 2 + i] + __uint_as_float(v[i]);
+            for (int i = 0; i < 16; ++i) {
+              const float t = __uint_as_float(v[i]) + __uint_as_float(w[i]);
+              acc[cc / 2 + i] = g == 0 ? t : acc[cc / 2 + i] + t;
+            }
           }
           if (g + 1 < n_groups) {
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -470,28 +459,18 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             if (lane == 0) mbar_arrive(maine_bar(mb));
           }
         }
-        mbar_wait(corrf_bar(cb), ((uint32_t)tl >> 1) & 1u);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
         for (int cc = 0; cc < BN; cc += 32) {
           uint32_t v[16];
-          tcgen05_ld16(lane_base + corr_col(cb) + (uint32_t)cc, v);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(acc[cc / 2 + i] + __uint_as_float(v[i]));
+          for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(acc[cc / 2 + i]);
           tcgen05_st16(lane_base + src_col + (uint32_t)cc, v);
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) mbar_arrive(corre_bar(cb));
+        add_corr = false;
       } else {
         mbar_wait(mainf_bar(mb_last), (gcount >> 1) & 1u);
         ++gcount;
-        if (SPLIT == 3) {
-          mbar_wait(corrf_bar(cb), ((uint32_t)tl >> 1) & 1u);
-          add_col = corr_col(cb);
-        }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       }
 #pragma unroll 1
@@ -502,19 +481,16 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
         for (int i = 0; i < 16; ++i) o[i] = __uint_as_float(v[i]);
-        if (add_col != 0xffffffffu) {
-          tcgen05_ld16(lane_base + add_col + (uint32_t)cc, v);
+        if (add_corr) {
+          tcgen05_ld16(lane_base + src_col + (uint32_t)(BN + cc), v);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
           for (int i = 0; i < 16; ++i) o[i] += __uint_as_float(v[i]);
         }
-        if (cc + 32 >= BN) {   // accumulators fully read: hand them back before the stores
+        if (cc + 32 >= BN) {   // accumulator fully read: hand it back before the stores
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
-          if (lane == 0) {
-            mbar_arrive(maine_bar(mb_last));
-            if (add_col != 0xffffffffu) mbar_arrive(corre_bar(cb));
-          }
+          if (lane == 0) mbar_arrive(maine_bar(mb_last));
         }
         finish_block(o, cc);
       }
