@@ -82,7 +82,7 @@ struct ResW {
 struct LstmLayerW {
   float* w_ih = nullptr;  // [H_in][4H] (K-major rows for the 1-tap GEMM)
   float* bias = nullptr;  // b_ih + b_hh
-  float* w_hh = nullptr;  // packed per CTA (lstm.cu)
+  float* w_hh = nullptr;  // [4H][H]
   float* t_hi = nullptr;  // tensor-core input projection: [4H][H_in] K-major split weights
   float* t_lo = nullptr;
 };
@@ -210,8 +210,8 @@ int prepare_lstm(ecb_codec* c, const std::string& prefix, int H, std::vector<Lst
     if (launch_transpose(wih, lw.w_ih, 1, 4 * H, H, st)) return 1;  // [4H][H] -> [H][4H]
     if (dev_alloc(c, &lw.bias, 4LL * H)) return 1;
     if (launch_add_vec(bih, bhh, lw.bias, 4 * H, st)) return 1;
-    if (dev_alloc(c, &lw.w_hh, 4LL * H * H)) return 1;
-    if (launch_pack_lstm_whh(whh, lw.w_hh, H, st)) return 1;
+    if (dev_alloc(c, &lw.w_hh, 4LL * H * H)) return 1;   // reference layout [4H][H]; the kernel slices it itself
+    ECB_CUDA(cudaMemcpyAsync(lw.w_hh, whh, sizeof(float) * 4 * H * H, cudaMemcpyDeviceToDevice, st));
     if (!c->spec.group_norm && prepare_tc(c, lw.w_ih, nullptr, H, 4 * H, 4 * H, &lw.t_hi, &lw.t_lo, nullptr, st)) return 1;
   }
   return 0;

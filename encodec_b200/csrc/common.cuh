@@ -231,11 +231,10 @@ int launch_overlap_add(const float* frames, const int* seg_lens, long long batch
 // ------------------------------------------------------------------------------------------------
 // lstm.cu
 // ------------------------------------------------------------------------------------------------
-// Pre-gates pre[b][t][4H] (input projection + both biases already added) -> h sequence.
-// w_hh_packed: per-CTA slices prepared by launch_pack_lstm_whh. If skip != nullptr the written output is
-// act(h + skip) (SLSTM skip connection, lstm.py:25-26) and the raw h stays in the recurrent state only.
+// Pre-gates pre[b][t][4H] (input projection + both biases already added) -> h sequence. w_hh is the reference's
+// [4H][H] tensor. If skip != nullptr the written output is act(h + skip) (SLSTM skip connection, lstm.py:25-26) and
+// the raw h stays in the recurrent state only.
 int lstm_recurrent_workspace_floats(int batch);
-int launch_pack_lstm_whh(const float* w_hh, float* packed, int H, cudaStream_t s);
 // skip / out rows of item b start at + b*skip_item_stride / + b*out_item_stride floats (0 means the dense T*H).
 int launch_lstm_recurrent(const float* pre, const float* w_hh_packed, const float* skip, long long skip_item_stride,
                           float* out, long long out_item_stride, int batch, int T, int H, int out_elu,

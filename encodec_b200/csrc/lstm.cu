@@ -1,231 +1,335 @@
 // SLSTM recurrence (reference modules/lstm.py:12-28 -> nn.LSTM(512, 512, 2), gates i,f,g,o, zero state).
 //
-// The input projection W_ih x_t + b_ih + b_hh of ALL time steps is one GEMM (conv_gemm.cu, 1 tap);
+// The input projection W_ih x_t + b_ih + b_hh of ALL time steps is one tensor-core GEMM (tc_conv.cu, 1 tap);
 // this file holds the part that is sequential in time: gates_t = pre_t + W_hh h_{t-1}, the cell update
-// and the skip connection y = h + x (lstm.py:25-26).
+// and the skip connection y = h + x (lstm.py:25-26). It is latency-bound (T dependent steps), so the design
+// goal is to keep every step short and to hide the inter-CTA exchange of h behind independent work:
 //
-// One persistent cooperative kernel per LSTM layer: 128 CTAs, CTA c owns hidden units 4c..4c+3 (16 gate
-// rows of W_hh, 32 KB, resident in shared memory for the whole sequence). Per step every CTA pulls
-// h_{t-1} (batch tile x 512) from L2 into shared memory, computes its 64 x 16 gate block with K split over
-// 4 warp pairs, reduces, applies the cell non-linearity with one (batch, unit) pair per thread, publishes
-// its 4 columns of h_t and joins a grid-wide barrier (one atomic counter).
-#include <cooperative_groups.h>
-
+//   * one persistent cooperative kernel per LSTM layer, 128 CTAs = 32 unit blocks x 4 batch quarters. CTA
+//     (ub, q) owns hidden units 16 ub .. 16 ub + 15 (64 gate rows of W_hh) for the items of batch quarter q.
+//   * its 64 x 512 slice of W_hh lives in REGISTERS for the whole sequence (128 per thread: thread (rg, ks)
+//     holds 4 rows x 32 k); per step only h_{t-1} moves. fp32 FFMA, fp32 accumulate: no precision trade.
+//   * a quarter is processed as independent SUB-GROUPS of 4 items, and the CTA is warp-specialised so that the
+//     L2 round trips of one sub-group (poll the arrival counter, fetch h_{t-1}, publish h_t, fence) overlap the
+//     FFMA work of the others:
+//       warps 0-7   compute: gates = W_hh_slice . h_{t-1} for one sub-group, K split over 16 lanes, butterfly
+//                   reduction, result to shared memory (setmaxnreg raises their budget for the resident weights);
+//       warps 8-11  cell teams (team = sub-group index mod 4): add the pre-gates, apply the cell non-linearity,
+//                   store h_t (L2) and the layer output, fence, release-increment the sub-group's counter;
+//       warp 12     loader: polls the counter of the sub-group it needs next and cp.async's its h_{t-1}
+//                   into a 4-deep shared-memory ring.
+//     mbarriers connect the three roles; nobody ever waits on a whole-grid barrier.
 #include "common.cuh"
 
 namespace ecb {
 namespace {
 
-constexpr int LH = 512;             // hidden size
-constexpr int L_UNITS = 4;          // hidden units per CTA
-constexpr int L_CTAS = LH / L_UNITS;  // 128
-constexpr int L_BT = 64;            // batch tile
-constexpr int L_HLD = LH + 4;       // padded h row in smem (floats)
-constexpr int L_THREADS = 256;
+constexpr int LH = 512;               // hidden size
+constexpr int L_UNITS = 16;           // hidden units per CTA
+constexpr int L_UB = LH / L_UNITS;    // 32 unit blocks
+constexpr int L_NQ = 4;               // batch quarters
+constexpr int L_CTAS = L_UB * L_NQ;   // 128
+constexpr int L_SB = 4;               // items per sub-group
+constexpr int L_THREADS = 512;        // 4 warpgroups: 2 x compute, cell teams, loader
+constexpr int L_HLD = LH + 4;         // padded h row in smem (floats)
+constexpr int L_STAGES = 4;           // h ring depth
+constexpr int L_TEAMS = 4;
 
 struct LstmParams {
   const float* pre;    // [B][T][4H]
-  const float* wp;     // packed W_hh: [CTA][k4=128][gate=4][unit=4][4]
-  const float* skip;   // [B][T][H] or nullptr
-  float* out;          // [B][T][H]
-  float* hbuf;         // [2][B][H] recurrent state, hbuf[0] zeroed by the host
-  unsigned int* bar;   // grid barrier counter, zeroed by the host
-  long long skip_stride, out_stride;  // floats between items
+  const float* w_hh;   // [4H][H] (reference layout, rows i,f,g,o)
+  const float* skip;   // item b at skip + b*skip_stride, [T][H], or nullptr
+  float* out;          // item b at out + b*out_stride, [T][H]
+  float* hbuf;         // [2][B_pad][H] recurrent state exchange (L2)
+  unsigned int* cnt;   // one arrival counter per sub-group, zeroed by the host
+  long long skip_stride, out_stride;
   int B, T, out_elu;
+  int q_items;         // items per batch quarter (multiple of L_SB)
 };
 
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.f / (1.f + expf(-x)); }
-
-__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int target) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(bar, 1u);
-    unsigned int v;
-    do {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
-    } while (v < target);
-  }
-  __syncthreads();
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
 }
 
 __global__ void __launch_bounds__(L_THREADS, 1)
 lstm_recurrent_kernel(const LstmParams p) {
   extern __shared__ __align__(16) float smem[];
-  float* ws = smem;                              // [128][4][4][4] = 8192 floats
-  float* hs = ws + 8192;                         // [64][516]
-  float* part = hs + L_BT * L_HLD;               // [4 ksplit][4 i][64][4] = 4096 floats
-  float* cs = part + 4096;                       // [n_btiles][256] cell state
+  float* hs = smem;                                   // [L_STAGES][L_SB][L_HLD]  h_{t-1} ring
+  float* gs = hs + L_STAGES * L_SB * L_HLD;           // [L_TEAMS][L_SB][64]      reduced gate pre-activations
+  float* cs = gs + L_TEAMS * L_SB * 64;               // [q_items][16]            cell state of this CTA's (items, units)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(cs + p.q_items * L_UNITS);   // 8-byte aligned: all counts above are even
+  const uint32_t bar0 = smem_addr(bars);
+  auto h_full = [&](int s) { return bar0 + 8u * s; };
+  auto h_empty = [&](int s) { return bar0 + 8u * (L_STAGES + s); };
+  auto g_full = [&](int k) { return bar0 + 8u * (2 * L_STAGES + k); };
+  auto g_empty = [&](int k) { return bar0 + 8u * (2 * L_STAGES + L_TEAMS + k); };
 
   const int tid = threadIdx.x;
-  const int cta = blockIdx.x;
-  const int n_bt = (p.B + L_BT - 1) / L_BT;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+  const int ub = blockIdx.x % L_UB;
+  const int q = blockIdx.x / L_UB;
+  const int b_first = q * p.q_items;
+  const int n_items = max(0, min(p.q_items, p.B - b_first));
+  const int n_sub = (n_items + L_SB - 1) / L_SB;
+  if (n_sub == 0) return;                    // empty quarter: nobody waits for this CTA
 
-  {  // resident W_hh slice
-    const float4* src = reinterpret_cast<const float4*>(p.wp + (long long)cta * 8192);
-    float4* dst = reinterpret_cast<float4*>(ws);
-    for (int i = tid; i < 2048; i += L_THREADS) dst[i] = __ldg(src + i);
-    for (int i = tid; i < n_bt * 256; i += L_THREADS) cs[i] = 0.f;
+  if (tid == 0) {
+    for (int s = 0; s < L_STAGES; ++s) {
+      mbar_init(h_full(s), 32);              // one (async) arrive per loader lane
+      mbar_init(h_empty(s), 8);              // one arrive per compute warp
+    }
+    for (int k = 0; k < L_TEAMS; ++k) {
+      mbar_init(g_full(k), 8);
+      mbar_init(g_empty(k), 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  for (int i = tid; i < p.q_items * L_UNITS; i += L_THREADS) cs[i] = 0.f;
   __syncthreads();
+  const long long B_pad = (long long)L_NQ * p.q_items;
+  unsigned int* cnt_q = p.cnt + q * (p.q_items / L_SB);
 
-  // GEMM-phase role: K split ks, thread slot t64 = (w2, g, u): rows b = 32*w2 + g + 8*i, unit u
-  const int ks = tid >> 6;
-  const int t64 = tid & 63;
-  const int w2 = t64 >> 5;
-  const int g = (t64 & 31) >> 2;
-  const int u = t64 & 3;
-  // cell-phase role: one (row, unit) pair per thread: i_c = tid / 64 selects which of the slot's 4 rows
-  const int i_c = tid >> 6;
-  const int b_c = 32 * w2 + g + 8 * i_c;          // row inside the batch tile
-  const int unit = cta * L_UNITS + u;
+  // register budget: the compute warpgroups hold the weights, the helper warpgroups give registers up
+  if (warp < 8) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 200;" ::: "memory");
+  } else {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;" ::: "memory");
+  }
 
-  unsigned int bar_target = 0;
-  for (int t = 0; t < p.T; ++t) {
-    const float* hprev = p.hbuf + (long long)(t & 1) * p.B * LH;
-    float* hnext = p.hbuf + (long long)((t + 1) & 1) * p.B * LH;
-    for (int bt = 0; bt < n_bt; ++bt) {
-      const int b0 = bt * L_BT;
-      // prefetch this thread's pre-gates (read-only input, independent of the recurrence)
-      const int bg = b0 + b_c;
-      float pg[4] = {0.f, 0.f, 0.f, 0.f};
-      float skipv = 0.f;
-      if (bg < p.B) {
-        const float* pr = p.pre + ((long long)bg * p.T + t) * (4 * LH) + unit;
+  if (warp < 8) {
+    // ================================ compute warps ================================
+    // row group rg (4 gate rows: gate rg >> 2, units 4 (rg & 3) .. + 3), k split ks (k = (16 j + ks) 4 + e)
+    const int ks = lane & 15;
+    const int rg = warp * 2 + (lane >> 4);
+    const int gate = rg >> 2;
+    const int uq = rg & 3;
+    float w[4][8][4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) pg[q] = __ldg(pr + q * LH);
-        if (p.skip) skipv = __ldg(p.skip + (long long)bg * p.skip_stride + (long long)t * LH + unit);
+    for (int r = 0; r < 4; ++r) {
+      const float* wr = p.w_hh + ((long long)gate * LH + ub * L_UNITS + uq * 4 + r) * LH;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(wr + (j * 16 + ks) * 4));
+        w[r][j][0] = v.x; w[r][j][1] = v.y; w[r][j][2] = v.z; w[r][j][3] = v.w;
       }
-      // h_{t-1} tile -> shared (L2 only: other CTAs wrote it during the previous step)
-      for (int f = tid; f < L_BT * (LH / 4); f += L_THREADS) {
-        const int r = f >> 7;
-        const int c4 = f & 127;
-        float* dst = hs + r * L_HLD + c4 * 4;
-        if (b0 + r < p.B) {
-          const float* src = hprev + (long long)(b0 + r) * LH + c4 * 4;
-          const unsigned int sa = (unsigned int)__cvta_generic_to_shared(dst);
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src) : "memory");
+    }
+    uint32_t n = 0;                 // running (t, sg) index -> h ring stage and phase
+    uint32_t team_use[L_TEAMS] = {0, 0, 0, 0};
+    for (int t = 0; t < p.T; ++t) {
+      for (int sg = 0; sg < n_sub; ++sg, ++n) {
+        const int st = (int)(n % L_STAGES);
+        mbar_wait(h_full(st), (n / L_STAGES) & 1u);
+        const float* hsg = hs + st * (L_SB * L_HLD);
+        float acc[4][L_SB];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int i = 0; i < L_SB; ++i) acc[r][i] = 0.f;
+#pragma unroll
+        for (int i = 0; i < L_SB; ++i) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 hv = *reinterpret_cast<const float4*>(hsg + i * L_HLD + (j * 16 + ks) * 4);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+              acc[r][i] = fmaf(w[r][j][0], hv.x, acc[r][i]);
+              acc[r][i] = fmaf(w[r][j][1], hv.y, acc[r][i]);
+              acc[r][i] = fmaf(w[r][j][2], hv.z, acc[r][i]);
+              acc[r][i] = fmaf(w[r][j][3], hv.w, acc[r][i]);
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(h_empty(st));   // this warp is done reading the ring slot
+        // butterfly over the 16 k splits (lanes ks): after 4 exchange steps lane ks holds the complete sum of
+        // value index ks (= r * 4 + i) -- 15 shuffles instead of 64
+        float v16[16];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int i = 0; i < L_SB; ++i) v16[r * 4 + i] = acc[r][i];
+#pragma unroll
+        for (int step = 0; step < 4; ++step) {
+          const int m = 8 >> step;
+          const bool upper = (ks & m) != 0;      // lanes with the bit set keep values [m, 2m), the others [0, m)
+#pragma unroll
+          for (int k = 0; k < m; ++k) {
+            const float send = upper ? v16[k] : v16[k + m];
+            const float recv = __shfl_xor_sync(0xffffffffu, send, m);
+            v16[k] = (upper ? v16[k + m] : v16[k]) + recv;
+          }
+        }
+        const int team = sg % L_TEAMS;
+        mbar_wait(g_empty(team), (team_use[team] & 1u) ^ 1u);   // the team has consumed its previous gates
+        // lane ks holds value index ks: row r = ks >> 2 of the row group, item i = ks & 3
+        gs[team * (L_SB * 64) + (ks & 3) * 64 + gate * 16 + uq * 4 + (ks >> 2)] = v16[0];
+        __syncwarp();
+        if (lane == 0) mbar_arrive(g_full(team));
+        ++team_use[team];
+      }
+    }
+  } else if (warp < 12) {
+    // ================================ cell teams ================================
+    const int team = warp - 8;
+    uint32_t use = 0;
+    for (int t = 0; t < p.T; ++t) {
+      float* hnext = p.hbuf + (long long)((t + 1) & 1) * B_pad * LH;
+      for (int sg = team; sg < n_sub; sg += L_TEAMS, ++use) {
+        const int b0 = b_first + sg * L_SB;
+        // this lane's two (item, unit) pairs; their pre-gates / skip inputs do not depend on the recurrence
+        float pg[2][4], skipv[2];
+        bool valid[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int pi = lane + 32 * e;
+          const int bg = b0 + (pi >> 4);
+          const int unit = ub * L_UNITS + (pi & 15);
+          valid[e] = bg < p.B;
+          skipv[e] = 0.f;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) pg[e][g] = 0.f;
+          if (valid[e]) {
+            const float* pr = p.pre + ((long long)bg * p.T + t) * (4 * LH) + unit;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) pg[e][g] = __ldg(pr + g * LH);
+            if (p.skip) skipv[e] = __ldg(p.skip + (long long)bg * p.skip_stride + (long long)t * LH + unit);
+          }
+        }
+        mbar_wait(g_full(team), use & 1u);
+        const float* g4 = gs + team * (L_SB * 64);
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int pi = lane + 32 * e;
+          const int ci = pi >> 4, cu = pi & 15;
+          const int bg = b0 + ci;
+          const int unit = ub * L_UNITS + cu;
+          const float gi = sigmoidf_acc(pg[e][0] + g4[ci * 64 + 0 * 16 + cu]);
+          const float gf = sigmoidf_acc(pg[e][1] + g4[ci * 64 + 1 * 16 + cu]);
+          const float gg = tanhf(pg[e][2] + g4[ci * 64 + 2 * 16 + cu]);
+          const float go = sigmoidf_acc(pg[e][3] + g4[ci * 64 + 3 * 16 + cu]);
+          if (valid[e]) {
+            float* cptr = cs + (sg * L_SB + ci) * L_UNITS + cu;
+            const float c_new = gf * (*cptr) + gi * gg;
+            *cptr = c_new;
+            const float h_new = go * tanhf(c_new);
+            asm volatile("st.global.cg.f32 [%0], %1;" ::"l"(hnext + (long long)bg * LH + unit), "f"(h_new) : "memory");
+            float y = h_new;
+            if (p.skip) y += skipv[e];
+            if (p.out_elu) y = elu1(y);
+            p.out[(long long)bg * p.out_stride + (long long)t * LH + unit] = y;
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(g_empty(team));   // gates consumed: the compute warps may refill the slot
+        __threadfence();                              // this lane's h_t stores are visible device-wide ...
+        __syncwarp();
+        if (lane == 0 && t + 1 < p.T)                 // ... before the sub-group's arrival counter moves
+          asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(cnt_q + sg) : "memory");   // ordered by the fences above
+      }
+    }
+  } else if (warp == 12) {
+    // ================================ loader ================================
+    uint32_t n = 0;
+    for (int t = 0; t < p.T; ++t) {
+      const float* hprev = p.hbuf + (long long)(t & 1) * B_pad * LH;
+      for (int sg = 0; sg < n_sub; ++sg, ++n) {
+        const int st = (int)(n % L_STAGES);
+        mbar_wait(h_empty(st), ((n / L_STAGES) & 1u) ^ 1u);
+        float* dst = hs + st * (L_SB * L_HLD);
+        const int b0 = b_first + sg * L_SB;
+        if (t == 0) {
+          for (int f = lane; f < L_SB * (LH / 4); f += 32)
+            *reinterpret_cast<float4*>(dst + (f >> 7) * L_HLD + (f & 127) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+          mbar_arrive(h_full(st));
         } else {
-          *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (lane == 0) {
+            // all 32 unit blocks have published h_{t-1} of this sub-group once the counter reaches 32 t
+            const unsigned int target = (unsigned int)L_UB * (unsigned int)t;
+            unsigned int v, spins = 0;
+            do {
+              asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(cnt_q + sg) : "memory");
+              if (++spins > (1u << 28)) __trap();   // a lost arrival must not hang the device
+            } while (v < target);
+          }
+          __syncwarp();
+          for (int f = lane; f < L_SB * (LH / 4); f += 32) {
+            const float* src = hprev + (long long)(b0 + (f >> 7)) * LH + (f & 127) * 4;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst + (f >> 7) * L_HLD + (f & 127) * 4)),
+                         "l"(src)
+                         : "memory");
+          }
+          asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(h_full(st)) : "memory");
         }
       }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-      __syncthreads();
-
-      float acc[4][4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) acc[i][q] = 0.f;
-      const float* hrow = hs + (32 * w2 + g) * L_HLD;
-#pragma unroll 4
-      for (int k4 = ks * 32; k4 < ks * 32 + 32; ++k4) {
-        float4 hv[4], wv[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) hv[i] = *reinterpret_cast<const float4*>(hrow + (8 * i) * L_HLD + k4 * 4);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) wv[q] = *reinterpret_cast<const float4*>(ws + ((k4 * 4 + q) * 4 + u) * 4);
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            acc[i][q] = fmaf(hv[i].x, wv[q].x, acc[i][q]);
-            acc[i][q] = fmaf(hv[i].y, wv[q].y, acc[i][q]);
-            acc[i][q] = fmaf(hv[i].z, wv[q].z, acc[i][q]);
-            acc[i][q] = fmaf(hv[i].w, wv[q].w, acc[i][q]);
-          }
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        *reinterpret_cast<float4*>(part + ((ks * 4 + i) * 64 + t64) * 4) =
-            make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-      __syncthreads();
-
-      // cell update for (row b_c, unit u)
-      float4 s = *reinterpret_cast<const float4*>(part + ((0 * 4 + i_c) * 64 + t64) * 4);
-#pragma unroll
-      for (int k = 1; k < 4; ++k) {
-        const float4 v = *reinterpret_cast<const float4*>(part + ((k * 4 + i_c) * 64 + t64) * 4);
-        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-      }
-      if (bg < p.B) {
-        const float gi = sigmoidf_acc(pg[0] + s.x);
-        const float gf = sigmoidf_acc(pg[1] + s.y);
-        const float gg = tanhf(pg[2] + s.z);
-        const float go = sigmoidf_acc(pg[3] + s.w);
-        const float c_new = gf * cs[bt * 256 + tid] + gi * gg;
-        cs[bt * 256 + tid] = c_new;
-        const float h_new = go * tanhf(c_new);
-        hnext[(long long)bg * LH + unit] = h_new;
-        float y = h_new;
-        if (p.skip) y += skipv;
-        if (p.out_elu) y = elu1(y);
-        p.out[(long long)bg * p.out_stride + (long long)t * LH + unit] = y;
-      }
-      // `part` and `hs` are rewritten only after the next tile's barriers
     }
-    bar_target += L_CTAS;
-    grid_barrier(p.bar, bar_target);
   }
 }
 
-// W_hh [4H][H] -> [CTA][k4][gate][unit][4]
-__global__ void pack_whh_kernel(const float* __restrict__ w, float* __restrict__ out) {
-  const int n = L_CTAS * 8192;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const int e = i & 3;
-    const int uu = (i >> 2) & 3;
-    const int q = (i >> 4) & 3;
-    const int k4 = (i >> 6) & 127;
-    const int cta = i >> 13;
-    out[i] = w[((long long)q * LH + cta * L_UNITS + uu) * LH + k4 * 4 + e];
-  }
+size_t lstm_smem_bytes(int q_items) {
+  return sizeof(float) * (size_t)(L_STAGES * L_SB * L_HLD + L_TEAMS * L_SB * 64 + q_items * L_UNITS) +
+         8 * (2 * L_STAGES + 2 * L_TEAMS);
 }
 
-size_t lstm_smem_bytes(int batch) {
-  const int n_bt = (batch + L_BT - 1) / L_BT;
-  return sizeof(float) * (size_t)(8192 + L_BT * L_HLD + 4096 + n_bt * 256);
+int quarter_items(int batch) {
+  const int per = (batch + L_NQ - 1) / L_NQ;
+  return (per + L_SB - 1) / L_SB * L_SB;
 }
 
 }  // namespace
 
-int lstm_recurrent_workspace_floats(int batch) { return 2 * batch * LH + 64; }
-
-int launch_pack_lstm_whh(const float* w_hh, float* packed, int H, cudaStream_t s) {
-  ECB_REQUIRE(H == LH, "lstm: hidden size %d unsupported (only %d)", H, LH);
-  pack_whh_kernel<<<512, 256, 0, s>>>(w_hh, packed);
-  ECB_LAUNCHED();
-  return 0;
+// 2 x B_pad x H state + one counter per sub-group
+int lstm_recurrent_workspace_floats(int batch) {
+  const int qi = quarter_items(batch);
+  return 2 * L_NQ * qi * LH + L_NQ * qi / L_SB + 64;
 }
 
-int launch_lstm_recurrent(const float* pre, const float* w_hh_packed, const float* skip, long long skip_item_stride,
-                          float* out, long long out_item_stride, int batch, int T, int H, int out_elu,
-                          float* workspace, cudaStream_t s) {
+int launch_lstm_recurrent(const float* pre, const float* w_hh, const float* skip, long long skip_item_stride, float* out,
+                          long long out_item_stride, int batch, int T, int H, int out_elu, float* workspace,
+                          cudaStream_t s) {
   ECB_REQUIRE(H == LH, "lstm: hidden size %d unsupported (only %d)", H, LH);
   ECB_REQUIRE(batch > 0 && T > 0, "lstm: bad batch %d / T %d", batch, T);
-  const size_t smem = lstm_smem_bytes(batch);
-  ECB_REQUIRE(smem <= 227 * 1024, "lstm: batch %d needs %zu bytes of shared memory; split the batch", batch, smem);
+  const int qi = quarter_items(batch);
+  const size_t smem = lstm_smem_bytes(qi);
+  ECB_REQUIRE(smem <= 200 * 1024, "lstm: batch %d needs %zu bytes of shared memory; split the batch", batch, smem);
   static bool attr_set = false;
   if (!attr_set) {
-    ECB_CUDA(cudaFuncSetAttribute(lstm_recurrent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    ECB_CUDA(cudaFuncSetAttribute(lstm_recurrent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
   LstmParams p;
   p.pre = pre;
-  p.wp = w_hh_packed;
+  p.w_hh = w_hh;
   p.skip = skip;
   p.out = out;
   p.skip_stride = skip_item_stride ? skip_item_stride : (long long)T * LH;
   p.out_stride = out_item_stride ? out_item_stride : (long long)T * LH;
   p.hbuf = workspace;
-  p.bar = reinterpret_cast<unsigned int*>(workspace + 2 * (size_t)batch * LH);
+  p.cnt = reinterpret_cast<unsigned int*>(workspace + 2LL * L_NQ * qi * LH);
   p.B = batch;
   p.T = T;
   p.out_elu = out_elu;
-  // zero h_{-1} and the barrier counter
-  ECB_CUDA(cudaMemsetAsync(workspace, 0, sizeof(float) * (size_t)batch * LH, s));
-  ECB_CUDA(cudaMemsetAsync(p.bar, 0, 64 * sizeof(float), s));
+  p.q_items = qi;
+  ECB_CUDA(cudaMemsetAsync(p.cnt, 0, sizeof(unsigned int) * (size_t)(L_NQ * qi / L_SB + 64), s));
   const double bt = (double)batch * T;
   ProfScope prof(PROF_LSTM_REC, s, 2.0 * bt * 4 * H * H, 4.0 * (bt * 4 * H + bt * H * (skip ? 2 : 1) + 4.0 * H * H));
   void* args[] = {(void*)&p};
