@@ -111,6 +111,8 @@ struct ecb_codec {
   // quantiser
   float* codebooks = nullptr;  // [n_q][bins][D]
   float* e2 = nullptr;         // [n_q][bins]
+  float* cb_hi = nullptr;      // TF32 split of the codebooks for the tensor-core quantiser
+  float* cb_lo = nullptr;
   int hop = 1;
   bool tc_ready = false;       // tensor-core weights prepared (weight-norm / plain models)
 };
@@ -1022,6 +1024,8 @@ int ecb_codec_finalize(ecb_codec* c, void* stream) {
       ECB_CUDA(cudaMemcpyAsync(c->codebooks + per * i, e, sizeof(float) * per, cudaMemcpyDeviceToDevice, st));
     }
     if (launch_rvq_prepare(c->codebooks, s.n_q, s.bins, s.dimension, c->e2, st)) return 1;
+    if (dev_alloc(c, &c->cb_hi, per * s.n_q) || dev_alloc(c, &c->cb_lo, per * s.n_q)) return 1;
+    if (launch_rvq_split(c->codebooks, c->cb_hi, c->cb_lo, per * s.n_q, st)) return 1;
   }
   // conv_in / conv_out use their own packings: [K][C_in][32] is what pack_conv produced; conv_out wants
   // [K][32][C_out], which is also pack_conv's [K][Ci][Co] -- nothing more to do.
@@ -1229,9 +1233,14 @@ int ecb_codec_rvq_forward(ecb_codec* c, const float* xin, const float* x_frames,
     // write frames-major stack straight into the caller's buffer, transpose per (layer, batch) through w0 later
     stack_tmp = quantized_stack;
   }
-  if (launch_rvq_encode(x_frames, n, c->codebooks, c->e2, (int)n_q, c->spec.bins, reinterpret_cast<long long*>(codes),
-                        qf, stack_tmp, st))
+  if (!tc_disabled_by_env() && c->spec.bins % 128 == 0 && D == 128) {
+    if (launch_rvq_encode_tc(x_frames, n, c->codebooks, c->cb_hi, c->cb_lo, c->e2, c->spec.n_q, (int)n_q, c->spec.bins,
+                             reinterpret_cast<long long*>(codes), qf, stack_tmp, st))
+      return 1;
+  } else if (launch_rvq_encode(x_frames, n, c->codebooks, c->e2, (int)n_q, c->spec.bins, reinterpret_cast<long long*>(codes),
+                               qf, stack_tmp, st)) {
     return 1;
+  }
   if (quantized) {
     if (launch_transpose(qf, quantized, batch, (int)n_frames, D, st)) return 1;
   }

@@ -246,6 +246,11 @@ int launch_lstm_recurrent(const float* pre, const float* w_hh_packed, const floa
 int launch_rvq_prepare(const float* codebooks, long long n_q, long long bins, int dim, float* e2, cudaStream_t s);
 int launch_rvq_encode(const float* frames, long long n, const float* codebooks, const float* e2, int n_q, int bins,
                       long long* codes, float* quantized, float* stack, cudaStream_t s);
+// tensor-core variant (rvq_tc.cu): cb_hi / cb_lo = split codebooks from launch_rvq_split, [n_q_total][bins][128]
+int launch_rvq_split(const float* codebooks, float* hi, float* lo, long long numel, cudaStream_t s);
+int launch_rvq_encode_tc(const float* frames, long long n, const float* codebooks, const float* cb_hi, const float* cb_lo,
+                         const float* e2, int n_q_total, int n_q, int bins, long long* codes, float* quantized, float* stack,
+                         cudaStream_t s);
 int launch_rvq_decode(const long long* codes, long long n, const float* codebooks, int n_q, int bins,
                       float* quantized, cudaStream_t s);
 

@@ -31,6 +31,7 @@
 #include <cuda.h>
 
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace ecb {
 namespace {
@@ -68,106 +69,7 @@ struct TcArgs {
   int group;                // K chunks per main-accumulator group (SPLIT == 1: all of them)
 };
 
-// ---------------------------------------------------------------------------------------------- PTX
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-  } while (!done);
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y, int z) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y), "r"(z)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y)
-      : "memory");
-}
-__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, uint32_t src, int x, int y, int z) {
-  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map), "r"(src),
-               "r"(x), "r"(y), "r"(z)
-               : "memory");
-}
-__device__ __forceinline__ void tcgen05_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                                 uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tcgen05_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tcgen05_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tcgen05_st16(uint32_t taddr, const uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
-        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
-      : "memory");
-}
-// round-to-nearest (ties away from zero, as cvt.rna.tf32.f32) in two integer instructions: add half an ulp of the
-// 10-bit mantissa and truncate. Inputs are finite activations / weights (no NaN / Inf handling needed).
-__device__ __forceinline__ float rn_tf32(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
-__device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, sm_100): start address >> 4 in
-// bits [0,14), LBO (unused for swizzled K-major) = 1 in [16,30), SBO = 1024 B (8 rows x 128 B) >> 4 in [32,46),
-// version = 1 in [46,48), layout type SWIZZLE_128B = 2 in [61,64).
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-  return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-
-// kind::tf32 instruction descriptor (cute::UMMA::InstrDescriptor): D fp32 (bits [4,6) = 1), A/B TF32 ([7,10) = [10,13) = 2),
-// both K-major, N >> 3 in [17,23), M >> 4 in [24,29).
-__host__ __device__ constexpr uint32_t umma_idesc_tf32(int m, int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
-}
-
+using namespace tc;
 
 // Copy one staged [32 rows x 64 B] half block out of shared memory with coalesced 16-byte stores (four lanes per
 // 64-byte row segment, 8 rows per warp instruction): raw output as is, ELU output through elu1. The output modes are
@@ -526,6 +428,22 @@ __global__ void split_weights_kernel(const float* __restrict__ w, float* __restr
   }
 }
 
+template <int BN, int SPLIT>
+int launch_one(const CUtensorMap* maps, const TcArgs& a, int grid, cudaStream_t stream) {
+  using C = Cfg<BN, SPLIT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ECB_CUDA(cudaFuncSetAttribute(tc_conv_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  tc_conv_kernel<BN, SPLIT><<<grid, TC_THREADS, C::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], a);
+  ECB_LAUNCHED();
+  return 0;
+}
+
+}  // namespace
+
+namespace {
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -542,8 +460,10 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-int make_map(CUtensorMap* map, const float* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-             const cuuint32_t* box) {
+}  // namespace
+
+int make_tensor_map(CUtensorMap* map, const float* base, int rank, const cuuint64_t* dims,
+                    const cuuint64_t* strides_bytes, const cuuint32_t* box) {
   EncodeTiledFn fn = get_encode_fn();
   ECB_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint32_t estr[3] = {1, 1, 1};
@@ -569,20 +489,6 @@ int sm_count() {
   return n;
 }
 
-template <int BN, int SPLIT>
-int launch_one(const CUtensorMap* maps, const TcArgs& a, int grid, cudaStream_t stream) {
-  using C = Cfg<BN, SPLIT>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    ECB_CUDA(cudaFuncSetAttribute(tc_conv_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_set = true;
-  }
-  tc_conv_kernel<BN, SPLIT><<<grid, TC_THREADS, C::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], a);
-  ECB_LAUNCHED();
-  return 0;
-}
-
-}  // namespace
 
 int launch_split_weights(const float* w, float* hi, float* lo, int K, int N, int K_pad, int N_pad, cudaStream_t s) {
   dim3 grid((unsigned)cdiv(K_pad, 32), (unsigned)cdiv(N_pad, 32));
@@ -622,13 +528,13 @@ int launch_tc_conv(const TcConvParams& p, cudaStream_t stream) {
     const cuuint64_t dims[3] = {(cuuint64_t)s * p.C0, (cuuint64_t)rows, (cuuint64_t)p.n_items};
     const cuuint64_t strides[2] = {(cuuint64_t)s * p.C0 * 4, (cuuint64_t)p.a0_item_stride * 4};
     const cuuint32_t box[3] = {BK, BM, 1};
-    if (make_map(&maps[0], p.a0 + d * p.C0, 3, dims, strides, box)) return 1;
+    if (make_tensor_map(&maps[0], p.a0 + d * p.C0, 3, dims, strides, box)) return 1;
   }
   if (p.a1) {
     const cuuint64_t dims[3] = {(cuuint64_t)p.C1, (cuuint64_t)p.a1_rows, (cuuint64_t)p.n_items};
     const cuuint64_t strides[2] = {(cuuint64_t)p.C1 * 4, (cuuint64_t)p.a1_item_stride * 4};
     const cuuint32_t box[3] = {BK, BM, 1};
-    if (make_map(&maps[1], p.a1, 3, dims, strides, box)) return 1;
+    if (make_tensor_map(&maps[1], p.a1, 3, dims, strides, box)) return 1;
   } else {
     maps[1] = maps[0];
   }
@@ -636,8 +542,8 @@ int launch_tc_conv(const TcConvParams& p, cudaStream_t stream) {
     const cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)p.N};
     const cuuint64_t strides[1] = {(cuuint64_t)ktot * 4};
     const cuuint32_t box[2] = {BK, (cuuint32_t)bn};
-    if (make_map(&maps[2], p.w_hi, 2, dims, strides, box)) return 1;
-    if (make_map(&maps[3], p.split == 3 ? p.w_lo : p.w_hi, 2, dims, strides, box)) return 1;
+    if (make_tensor_map(&maps[2], p.w_hi, 2, dims, strides, box)) return 1;
+    if (make_tensor_map(&maps[3], p.split == 3 ? p.w_lo : p.w_hi, 2, dims, strides, box)) return 1;
   }
   a.bias = p.bias;
   a.out_raw = p.out_raw;
