@@ -8,7 +8,7 @@
 //   * one persistent cooperative kernel per LSTM layer, 128 CTAs = 32 unit blocks x 4 batch quarters. CTA
 //     (ub, q) owns hidden units 16 ub .. 16 ub + 15 (64 gate rows of W_hh) for the items of batch quarter q.
 //   * its 64 x 512 slice of W_hh lives in REGISTERS for the whole sequence (128 per thread: thread (rg, ks)
-//     holds 4 rows x 32 k); per step only h_{t-1} moves. fp32 FFMA, fp32 accumulate: no precision trade.
+//     holds 4 rows x 32 k); per step only h_{t-1} moves. fp32 FMA (packed fma.rn.f32x2), fp32 accumulate: no precision trade.
 //   * a quarter is processed as independent SUB-GROUPS of 4 items, and the CTA is warp-specialised so that the
 //     L2 round trips of one sub-group (poll the arrival counter, fetch h_{t-1}, publish h_t, fence) overlap the
 //     FFMA work of the others:
@@ -16,8 +16,8 @@
 //                   reduction, result to shared memory (setmaxnreg raises their budget for the resident weights);
 //       warps 8-11  cell teams (team = sub-group index mod 4): add the pre-gates, apply the cell non-linearity,
 //                   store h_t (L2) and the layer output, fence, release-increment the sub-group's counter;
-//       warp 12     loader: polls the counter of the sub-group it needs next and cp.async's its h_{t-1}
-//                   into a 4-deep shared-memory ring.
+//       warps 12-15 loaders (two stages each of an 8-deep shared-memory ring): poll the counter of the sub-group
+//                   the stage is for and cp.async its h_{t-1} in.
 //     mbarriers connect the three roles; nobody ever waits on a whole-grid barrier.
 #include "common.cuh"
 
@@ -32,7 +32,8 @@ constexpr int L_CTAS = L_UB * L_NQ;   // 128
 constexpr int L_SB = 4;               // items per sub-group
 constexpr int L_THREADS = 512;        // 4 warpgroups: 2 x compute, cell teams, loader
 constexpr int L_HLD = LH + 4;         // padded h row in smem (floats)
-constexpr int L_STAGES = 4;           // h ring depth
+constexpr int L_STAGES = 8;           // h ring depth
+constexpr int L_LOADERS = 4;          // loader warps; loader k fills the stages of running indices n = k (mod 4)
 constexpr int L_TEAMS = 4;
 
 struct LstmParams {
@@ -123,14 +124,17 @@ lstm_recurrent_kernel(const LstmParams p) {
     const int rg = warp * 2 + (lane >> 4);
     const int gate = rg >> 2;
     const int uq = rg & 3;
-    float w[4][8][4];
+    // weights as packed fp32 pairs (k, k+1): the dot products run on fma.rn.f32x2 (two FMAs per issue slot), which
+    // keeps even-k and odd-k partial sums in the two halves of a 64-bit accumulator
+    unsigned long long w2[4][8][2];
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       const float* wr = p.w_hh + ((long long)gate * LH + ub * L_UNITS + uq * 4 + r) * LH;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(wr + (j * 16 + ks) * 4));
-        w[r][j][0] = v.x; w[r][j][1] = v.y; w[r][j][2] = v.z; w[r][j][3] = v.w;
+        const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(wr + (j * 16 + ks) * 4));
+        w2[r][j][0] = v.x;
+        w2[r][j][1] = v.y;
       }
     }
     uint32_t n = 0;                 // running (t, sg) index -> h ring stage and phase
@@ -140,25 +144,29 @@ lstm_recurrent_kernel(const LstmParams p) {
         const int st = (int)(n % L_STAGES);
         mbar_wait(h_full(st), (n / L_STAGES) & 1u);
         const float* hsg = hs + st * (L_SB * L_HLD);
-        float acc[4][L_SB];
+        unsigned long long acc2[4][L_SB];
 #pragma unroll
         for (int r = 0; r < 4; ++r)
 #pragma unroll
-          for (int i = 0; i < L_SB; ++i) acc[r][i] = 0.f;
+          for (int i = 0; i < L_SB; ++i) acc2[r][i] = 0ull;
 #pragma unroll
         for (int i = 0; i < L_SB; ++i) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float4 hv = *reinterpret_cast<const float4*>(hsg + i * L_HLD + (j * 16 + ks) * 4);
+            const ulonglong2 hv = *reinterpret_cast<const ulonglong2*>(hsg + i * L_HLD + (j * 16 + ks) * 4);
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
-              acc[r][i] = fmaf(w[r][j][0], hv.x, acc[r][i]);
-              acc[r][i] = fmaf(w[r][j][1], hv.y, acc[r][i]);
-              acc[r][i] = fmaf(w[r][j][2], hv.z, acc[r][i]);
-              acc[r][i] = fmaf(w[r][j][3], hv.w, acc[r][i]);
+              asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2[r][i]) : "l"(w2[r][j][0]), "l"(hv.x));
+              asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2[r][i]) : "l"(w2[r][j][1]), "l"(hv.y));
             }
           }
         }
+        float acc[4][L_SB];
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int i = 0; i < L_SB; ++i)
+            acc[r][i] = __uint_as_float((unsigned int)(acc2[r][i] & 0xffffffffull)) + __uint_as_float((unsigned int)(acc2[r][i] >> 32));
         __syncwarp();
         if (lane == 0) mbar_arrive(h_empty(st));   // this warp is done reading the ring slot
         // butterfly over the 16 k splits (lanes ks): after 4 exchange steps lane ks holds the complete sum of
@@ -247,39 +255,42 @@ lstm_recurrent_kernel(const LstmParams p) {
           asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(cnt_q + sg) : "memory");   // ordered by the fences above
       }
     }
-  } else if (warp == 12) {
-    // ================================ loader ================================
-    uint32_t n = 0;
-    for (int t = 0; t < p.T; ++t) {
+  } else {
+    // ================================ loaders ================================
+    // Four loader warps, loader k owns ring stage k, i.e. the running (t, sg) indices n = k (mod 4): each poll of an
+    // arrival counter is a blocking L2 round trip, so four of them have to be in flight to keep the compute warps fed.
+    const uint32_t k = (uint32_t)(warp - 12);
+    const uint32_t total = (uint32_t)p.T * (uint32_t)n_sub;
+    for (uint32_t n = k; n < total; n += L_LOADERS) {
+      const int t = (int)(n / (uint32_t)n_sub);
+      const int sg = (int)(n - (uint32_t)t * (uint32_t)n_sub);
       const float* hprev = p.hbuf + (long long)(t & 1) * B_pad * LH;
-      for (int sg = 0; sg < n_sub; ++sg, ++n) {
-        const int st = (int)(n % L_STAGES);
-        mbar_wait(h_empty(st), ((n / L_STAGES) & 1u) ^ 1u);
-        float* dst = hs + st * (L_SB * L_HLD);
-        const int b0 = b_first + sg * L_SB;
-        if (t == 0) {
-          for (int f = lane; f < L_SB * (LH / 4); f += 32)
-            *reinterpret_cast<float4*>(dst + (f >> 7) * L_HLD + (f & 127) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
-          mbar_arrive(h_full(st));
-        } else {
-          if (lane == 0) {
-            // all 32 unit blocks have published h_{t-1} of this sub-group once the counter reaches 32 t
-            const unsigned int target = (unsigned int)L_UB * (unsigned int)t;
-            unsigned int v, spins = 0;
-            do {
-              asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(cnt_q + sg) : "memory");
-              if (++spins > (1u << 28)) __trap();   // a lost arrival must not hang the device
-            } while (v < target);
-          }
-          __syncwarp();
-          for (int f = lane; f < L_SB * (LH / 4); f += 32) {
-            const float* src = hprev + (long long)(b0 + (f >> 7)) * LH + (f & 127) * 4;
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst + (f >> 7) * L_HLD + (f & 127) * 4)),
-                         "l"(src)
-                         : "memory");
-          }
-          asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(h_full(st)) : "memory");
+      const int st = (int)(n % L_STAGES);
+      mbar_wait(h_empty(st), ((n / L_STAGES) & 1u) ^ 1u);
+      float* dst = hs + st * (L_SB * L_HLD);
+      const int b0 = b_first + sg * L_SB;
+      if (t == 0) {
+        for (int f = lane; f < L_SB * (LH / 4); f += 32)
+          *reinterpret_cast<float4*>(dst + (f >> 7) * L_HLD + (f & 127) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        mbar_arrive(h_full(st));
+      } else {
+        if (lane == 0) {
+          // all 32 unit blocks have published h_{t-1} of this sub-group once the counter reaches 32 t
+          const unsigned int target = (unsigned int)L_UB * (unsigned int)t;
+          unsigned int v, spins = 0;
+          do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(cnt_q + sg) : "memory");
+            if (++spins > (1u << 28)) __trap();   // a lost arrival must not hang the device
+          } while (v < target);
         }
+        __syncwarp();
+        for (int f = lane; f < L_SB * (LH / 4); f += 32) {
+          const float* src = hprev + (long long)(b0 + (f >> 7)) * LH + (f & 127) * 4;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst + (f >> 7) * L_HLD + (f & 127) * 4)),
+                       "l"(src)
+                       : "memory");
+        }
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(h_full(st)) : "memory");
       }
     }
   }
