@@ -66,6 +66,8 @@ struct ConvW {           // one SConv1d / SConvTranspose1d, prepared
   float* t_hi = nullptr;
   float* t_lo = nullptr;
   float* t_bias = nullptr;
+  float* t_gamma = nullptr;   // GroupNorm affine padded to t_N (zeros beyond c_out)
+  float* t_beta = nullptr;
   int t_K = 0, t_N = 0;
 };
 
@@ -214,7 +216,7 @@ int prepare_lstm(ecb_codec* c, const std::string& prefix, int H, std::vector<Lst
     if (launch_add_vec(bih, bhh, lw.bias, 4 * H, st)) return 1;
     if (dev_alloc(c, &lw.w_hh, 4LL * H * H)) return 1;   // reference layout [4H][H]; the kernel slices it itself
     ECB_CUDA(cudaMemcpyAsync(lw.w_hh, whh, sizeof(float) * 4 * H * H, cudaMemcpyDeviceToDevice, st));
-    if (!c->spec.group_norm && prepare_tc(c, lw.w_ih, nullptr, H, 4 * H, 4 * H, &lw.t_hi, &lw.t_lo, nullptr, st)) return 1;
+    if (prepare_tc(c, lw.w_ih, nullptr, H, 4 * H, 4 * H, &lw.t_hi, &lw.t_lo, nullptr, st)) return 1;
   }
   return 0;
 }
@@ -238,16 +240,35 @@ int prepare_tc(ecb_codec* c, const float* w, const float* bias, int K, int N, in
 int prepare_conv_tc(ecb_codec* c, ConvW& cw, cudaStream_t st) {
   const int K = cw.transposed ? 2 * cw.c_in : cw.k * cw.c_in;
   const int N = cw.transposed ? cw.stride * cw.c_out : cw.c_out;
-  ECB_REQUIRE(K % 32 == 0, "finalize: '%s' has K=%d, not a multiple of 32", cw.prefix.c_str(), K);
-  cw.t_K = K;
+  const int Kp = round_up32(K);   // a 16-channel 1x1 input (hidden layer of the 32-channel block) is zero-padded to 32
+  ECB_REQUIRE(Kp == K || cw.k == 1, "finalize: '%s' has K=%d, not a multiple of 32", cw.prefix.c_str(), K);
+  cw.t_K = Kp;
   cw.t_N = round_up32(N);
-  return prepare_tc(c, cw.w, cw.bias, K, N, cw.t_N, &cw.t_hi, &cw.t_lo, &cw.t_bias, st);
+  const float* w = cw.w;
+  if (Kp != K) {
+    float* wp = nullptr;
+    if (dev_alloc(c, &wp, (long long)Kp * N)) return 1;
+    ECB_CUDA(cudaMemsetAsync(wp, 0, sizeof(float) * (size_t)Kp * N, st));
+    ECB_CUDA(cudaMemcpyAsync(wp, cw.w, sizeof(float) * (size_t)K * N, cudaMemcpyDeviceToDevice, st));
+    w = wp;
+  }
+  if (prepare_tc(c, w, cw.bias, Kp, N, cw.t_N, &cw.t_hi, &cw.t_lo, &cw.t_bias, st)) return 1;
+  if (cw.gamma) {
+    if (dev_alloc(c, &cw.t_gamma, cw.t_N) || dev_alloc(c, &cw.t_beta, cw.t_N)) return 1;
+    ECB_CUDA(cudaMemsetAsync(cw.t_gamma, 0, sizeof(float) * cw.t_N, st));
+    ECB_CUDA(cudaMemsetAsync(cw.t_beta, 0, sizeof(float) * cw.t_N, st));
+    ECB_CUDA(cudaMemcpyAsync(cw.t_gamma, cw.gamma, sizeof(float) * cw.c_out, cudaMemcpyDeviceToDevice, st));
+    ECB_CUDA(cudaMemcpyAsync(cw.t_beta, cw.beta, sizeof(float) * cw.c_out, cudaMemcpyDeviceToDevice, st));
+  }
+  return 0;
 }
 
 int prepare_res_tc(ecb_codec* c, ResW& r, cudaStream_t st) {
   if (prepare_conv_tc(c, r.b1, st)) return 1;
   const int dim = r.sc.c_out, hid = r.b3.c_in;
   r.hid_pad = round_up32(hid);
+  if (c->spec.group_norm)   // the two branches are normalised separately (conv.py:125): no fused weights
+    return prepare_conv_tc(c, r.b3, st) || prepare_conv_tc(c, r.sc, st);
   // [hid_pad + dim][dim]: block.3 rows, zero rows for the padded hidden channels, shortcut rows
   float* cat = nullptr;
   const long long rows = r.hid_pad + dim;
@@ -346,8 +367,8 @@ Plan make_plan(const ecb_codec* c, long long n_items, long long length) {
   Plan p;
   const long long t_pad = length + 2LL * c->hop;
   p.act_floats = (size_t)n_items * t_pad * c->spec.n_filters;
-  p.n_act = 4;
-  p.stat_doubles = c->spec.group_norm ? (size_t)n_items * (ceil_div_ll(length, 128) + 64) * 2 : 0;
+  p.n_act = c->spec.group_norm ? 5 : 4;
+  p.stat_doubles = c->spec.group_norm ? (size_t)n_items * (ceil_div_ll(length, 128) + 64) * 16 : 0;
   p.lstm_floats = (size_t)lstm_recurrent_workspace_floats((int)n_items);
   p.total_bytes = (p.act_floats * p.n_act + p.lstm_floats) * sizeof(float) + 2 * p.stat_doubles * sizeof(double) +
                   256 * 16;
@@ -374,7 +395,7 @@ struct Ctx {
   ecb_codec* c;
   cudaStream_t st;
   int n_items;
-  float* buf[4];
+  float* buf[5];
   double* stat[2];
   float* lstm_ws;
 };
@@ -431,6 +452,8 @@ int run_conv(Ctx& x, const ConvW& cw, const float* in, long long T_in, int in_el
   if (launch_conv_gemm(p, x.st)) return 1;
   if (s.group_norm) {
     GnSrc a;
+  a.item_stride = 0;
+    a.item_stride = 0;
     a.x = out;
     a.partial = x.stat[0];
     a.slots = conv_gemm_stat_slots(p);
@@ -490,6 +513,7 @@ int run_res(Ctx& x, const ResW& r, const float* in, long long T, float* tmp0, fl
   p.stats = x.stat[0];
   if (launch_conv_gemm(p, x.st)) return 1;
   GnSrc a;
+  a.item_stride = 0;
   a.x = out;
   a.partial = x.stat[0];
   a.slots = conv_gemm_stat_slots(p);
@@ -504,6 +528,7 @@ int run_res(Ctx& x, const ResW& r, const float* in, long long T, float* tmp0, fl
   p2.stats = x.stat[1];
   if (launch_conv_gemm(p2, x.st)) return 1;
   GnSrc b;
+  b.item_stride = 0;
   b.x = tmp1;
   b.partial = x.stat[1];
   b.slots = conv_gemm_stat_slots(p2);
@@ -575,6 +600,8 @@ int run_convtr(Ctx& x, const ConvW& cw, const float* in, long long L, float* out
   if (launch_conv_gemm(p, x.st)) return 1;
   if (s.group_norm) {
     GnSrc a;
+  a.item_stride = 0;
+    a.item_stride = 0;
     a.x = out;
     a.partial = x.stat[0];
     a.slots = conv_gemm_stat_slots(p);
@@ -593,7 +620,7 @@ int setup_ctx(Ctx& x, ecb_codec* c, long long n_items, long long length, void* w
   Plan pl = make_plan(c, n_items, length);
   ECB_REQUIRE(workspace && ws_bytes >= pl.total_bytes, "workspace too small: %zu < %zu bytes", ws_bytes, pl.total_bytes);
   Arena a{reinterpret_cast<char*>(workspace), ws_bytes};
-  for (int i = 0; i < 4; ++i) x.buf[i] = i < pl.n_act ? a.take<float>(pl.act_floats) : nullptr;
+  for (int i = 0; i < 5; ++i) x.buf[i] = i < pl.n_act ? a.take<float>(pl.act_floats) : nullptr;
   x.stat[0] = a.take<double>(pl.stat_doubles);
   x.stat[1] = a.take<double>(pl.stat_doubles);
   x.lstm_ws = a.take<float>(pl.lstm_floats);
@@ -667,7 +694,8 @@ int tap_act(cudaStream_t st, int stage, const Act& a, int n_items) {
 // [M][N] per item that share one layout; with mirror_halo their reflected halo rows are written too.
 int tc_run(Ctx& x, const float* hi, const float* lo, const float* bias, int K, int N, const Act& in, int C0, int taps,
            int stride, int pad_left, bool zero_pad, const Act* in1, float* out_raw, float* out_elu,
-           long long out_item_stride, long long M, int mirror_halo, int split, int round_out) {
+           long long out_item_stride, long long M, int mirror_halo, int split, int round_out, double* stats = nullptr,
+           int* stat_slots = nullptr) {
   TcConvParams p;
   p.C0 = C0;
   p.taps = taps;
@@ -703,6 +731,8 @@ int tc_run(Ctx& x, const float* hi, const float* lo, const float* bias, int K, i
   p.halo = mirror_halo;
   p.round_out = round_out;
   p.split = split;
+  p.stats = stats;
+  if (stat_slots) *stat_slots = tc_stat_slots(p);
   return launch_tc_conv(p, x.st);
 }
 
@@ -741,7 +771,7 @@ int tc_lstm(Ctx& x, const std::vector<LstmLayerW>& layers, const Act& X, float* 
 }
 
 int encoder_forward_tc(Ctx& x, const float* xin, int64_t n_seg, int64_t length, int64_t x_batch_stride, int64_t x_seg_stride,
-                       int64_t x_chan_stride, float* emb_out, float* emb_frames_out) {
+                       int64_t x_chan_stride, const float* scale, float* emb_out, float* emb_frames_out) {
   ecb_codec* c = x.c;
   const ecb_spec& s = c->spec;
   const int split = tc_split(false);
@@ -761,7 +791,7 @@ int encoder_forward_tc(Ctx& x, const float* xin, int64_t n_seg, int64_t length, 
   ci.K = c->enc_in.k;
   ci.pad_left = pad_left_of(s, c->enc_in.k, 1);
   ci.T_ref = reflect_length(length, ci.pad_left, c->enc_in.k - 1 - ci.pad_left);
-  ci.scale = nullptr;
+  ci.scale = scale;
   ci.w = c->enc_in.w;
   ci.bias = c->enc_in.bias;
   ci.out = X.row0();
@@ -849,6 +879,188 @@ int decoder_forward_tc(Ctx& x, const float* z_frames, int64_t n_frames, const fl
     if (tap_act(x.st, 102 + 2 * i, X2, x.n_items)) return 1;
     Act Y = act_of(A, ch, T, 0);
     if (tc_res(x, c->dec_res[i], X2, E2, D, Y, split)) return 1;
+    if (tap_act(x.st, 103 + 2 * i, Y, x.n_items)) return 1;
+    cur = Y;
+  }
+  ConvOutParams co;
+  co.in = cur.row0();
+  co.in_item_stride = cur.stride();
+  co.n_items = x.n_items;
+  co.T = (int)T;
+  co.C_out = s.channels;
+  co.K = c->dec_out.k;
+  co.pad_left = pad_left_of(s, c->dec_out.k, 1);
+  co.T_ref = reflect_length(T, co.pad_left, c->dec_out.k - 1 - co.pad_left);
+  co.w = c->dec_out.w;
+  co.bias = c->dec_out.bias;
+  co.scale = scale;
+  co.out = out;
+  return launch_conv_out(co, x.st);
+}
+
+
+// ---- GroupNorm models (48 kHz: norm='time_group_norm' = GroupNorm(1, C), conv.py:50,125,162) on the tensor-core path.
+// Every conv writes its raw output plus per-warp partial (sum, sumsq); gn_apply (misc.cu) reduces them per item and
+// normalises in place, producing the raw / ELU tensors the next layer reads; halo rows are filled afterwards.
+GnSrc gn_src(const float* x, long long item_stride, const double* partial, int slots, double count, const float* gamma,
+             const float* beta) {
+  GnSrc g;
+  g.x = x;
+  g.item_stride = item_stride;
+  g.partial = partial;
+  g.slots = slots;
+  g.count = count;
+  g.gamma = gamma;
+  g.beta = beta;
+  return g;
+}
+
+// conv (+ bias) -> GroupNorm -> {raw, ELU} for a plain (non-transposed) conv. The raw conv output goes to `dst`'s
+// layout first (dst = out_raw if given, else out_elu) and is normalised in place.
+int tc_conv_gn(Ctx& x, const ConvW& cw, const Act& in, int C0, bool zero_pad, long long M, Act* out_raw, Act* out_elu,
+               int stat_idx = 0) {
+  const ecb_spec& s = x.c->spec;
+  Act& dst = out_raw ? *out_raw : *out_elu;
+  int slots = 0;
+  if (tc_run(x, cw.t_hi, cw.t_lo, cw.t_bias, cw.t_K, cw.t_N, in, C0, cw.k, cw.stride, pad_left_of(s, cw.k, cw.stride), zero_pad,
+             nullptr, dst.row0(), nullptr, dst.stride(), M, 0, 3, 0, x.stat[stat_idx], &slots))
+    return 1;
+  GnSrc a = gn_src(dst.row0(), dst.stride(), x.stat[stat_idx], slots, (double)M * cw.c_out, cw.t_gamma, cw.t_beta);
+  if (launch_gn_apply2(a, nullptr, out_raw ? out_raw->row0() : nullptr, out_elu ? out_elu->row0() : nullptr, dst.stride(),
+                       x.n_items, M, cw.t_N, 1e-5f, x.st))
+    return 1;
+  if (out_elu && out_elu->halo > 0 &&
+      launch_halo_fill(nullptr, out_elu->row0(), out_elu->stride(), out_elu->T, out_elu->C, x.n_items, out_elu->halo, 0, x.st))
+    return 1;
+  return 0;
+}
+
+// SEANetResnetBlock with GroupNorm: Y = ELU(GN(shortcut(X)) + GN(block3(ELU(GN(block1(E)))))). hbuf / sbuf are scratch.
+int tc_res_gn(Ctx& x, const ResW& r, const Act& X, const Act& E, float* hbuf, float* sbuf, Act& Y) {
+  const int dim = r.sc.c_out;
+  Act H = act_of(hbuf, r.hid_pad, X.T, 0);
+  if (tc_conv_gn(x, r.b1, E, dim, false, X.T, nullptr, &H, 0)) return 1;
+  Act S = act_of(sbuf, dim, X.T, 0);
+  int slots3 = 0, slots_s = 0;
+  if (tc_run(x, r.b3.t_hi, r.b3.t_lo, r.b3.t_bias, r.b3.t_K, r.b3.t_N, H, r.hid_pad, 1, 1, 0, true, nullptr, Y.row0(), nullptr,
+             Y.stride(), X.T, 0, 3, 0, x.stat[0], &slots3))
+    return 1;
+  if (tc_run(x, r.sc.t_hi, r.sc.t_lo, r.sc.t_bias, r.sc.t_K, r.sc.t_N, X, dim, 1, 1, 0, true, nullptr, S.row0(), nullptr,
+             S.stride(), X.T, 0, 3, 0, x.stat[1], &slots_s))
+    return 1;
+  GnSrc a = gn_src(S.row0(), S.stride(), x.stat[1], slots_s, (double)X.T * dim, r.sc.t_gamma, r.sc.t_beta);
+  GnSrc b = gn_src(Y.row0(), Y.stride(), x.stat[0], slots3, (double)X.T * dim, r.b3.t_gamma, r.b3.t_beta);
+  if (launch_gn_apply2(a, &b, nullptr, Y.row0(), Y.stride(), x.n_items, X.T, dim, 1e-5f, x.st)) return 1;   // shortcut + block
+  if (Y.halo > 0 && launch_halo_fill(nullptr, Y.row0(), Y.stride(), Y.T, Y.C, x.n_items, Y.halo, 0, x.st)) return 1;
+  return 0;
+}
+
+int encoder_forward_tc_gn(Ctx& x, const float* xin, int64_t n_seg, int64_t length, int64_t x_batch_stride,
+                          int64_t x_seg_stride, int64_t x_chan_stride, const float* scale, float* emb_out,
+                          float* emb_frames_out) {
+  ecb_codec* c = x.c;
+  const ecb_spec& s = c->spec;
+  float *A = x.buf[0], *B = x.buf[1], *Cb = x.buf[2], *D = x.buf[3], *F = x.buf[4];
+  long long T = length;
+  int ch = s.n_filters;
+  Act X = act_of(A, ch, T, ACT_HALO), E = act_of(B, ch, T, ACT_HALO);
+  ConvInParams ci;
+  ci.x = xin;
+  ci.batch_stride = x_batch_stride;
+  ci.seg_stride = x_seg_stride;
+  ci.chan_stride = x_chan_stride;
+  ci.n_seg = (int)n_seg;
+  ci.n_items = x.n_items;
+  ci.T = (int)length;
+  ci.C_in = s.channels;
+  ci.K = c->enc_in.k;
+  ci.pad_left = pad_left_of(s, c->enc_in.k, 1);
+  ci.T_ref = reflect_length(length, ci.pad_left, c->enc_in.k - 1 - ci.pad_left);
+  ci.scale = scale;
+  ci.w = c->enc_in.w;
+  ci.bias = c->enc_in.bias;
+  ci.out = X.row0();
+  ci.out_elu = nullptr;
+  ci.out_item_stride = X.stride();
+  ci.halo = 0;
+  ci.stats = x.stat[0];
+  if (launch_conv_in(ci, x.st)) return 1;
+  {
+    GnSrc a = gn_src(X.row0(), X.stride(), x.stat[0], conv_in_stat_slots(ci), (double)length * ch, c->enc_in.gamma, c->enc_in.beta);
+    if (launch_gn_apply2(a, nullptr, X.row0(), E.row0(), X.stride(), x.n_items, length, ch, 1e-5f, x.st)) return 1;
+    if (launch_halo_fill(nullptr, E.row0(), E.stride(), T, ch, x.n_items, ACT_HALO, 0, x.st)) return 1;
+  }
+  if (tap_act(x.st, 0, X, x.n_items)) return 1;
+  for (int i = 0; i < s.n_ratios; ++i) {
+    Act Y = act_of(D, ch, T, ACT_HALO);
+    if (tc_res_gn(x, c->enc_res[i], X, E, Cb, F, Y)) return 1;
+    if (tap_act(x.st, 1 + 2 * i, Y, x.n_items)) return 1;
+    const ConvW& dw = c->enc_down[i];
+    const long long T2 = ceil_div_ll(T, dw.stride);
+    const bool last = (i == s.n_ratios - 1);
+    Act X2 = act_of(A, dw.c_out, T2, ACT_HALO), E2 = act_of(B, dw.c_out, T2, ACT_HALO);
+    if (tc_conv_gn(x, dw, Y, ch, false, T2, &X2, last ? nullptr : &E2, 0)) return 1;
+    X = X2;
+    E = E2;
+    T = T2;
+    ch = dw.c_out;
+    if (tap_act(x.st, 2 + 2 * i, X, x.n_items)) return 1;
+  }
+  Act top = act_of(D, ch, T, ACT_HALO);
+  if (s.lstm_layers) {
+    if (tc_lstm(x, c->enc_lstm, X, B, Cb, top, 3)) return 1;
+    if (tap_act(x.st, 50, top, x.n_items)) return 1;
+  } else {
+    if (launch_halo_fill(X.row0(), top.row0(), top.stride(), T, ch, x.n_items, ACT_HALO, 1, x.st)) return 1;
+  }
+  Act fr = act_of(emb_frames_out ? emb_frames_out : B, s.dimension, T, 0);
+  if (tc_conv_gn(x, c->enc_out, top, ch, false, T, &fr, nullptr, 0)) return 1;
+  if (emb_out && launch_transpose(fr.row0(), emb_out, x.n_items, (int)T, s.dimension, x.st)) return 1;
+  return 0;
+}
+
+int decoder_forward_tc_gn(Ctx& x, const float* z_frames, int64_t n_frames, const float* scale, float* out) {
+  ecb_codec* c = x.c;
+  const ecb_spec& s = c->spec;
+  float *A = x.buf[0], *B = x.buf[1], *Cb = x.buf[2], *D = x.buf[3], *F = x.buf[4];
+  long long T = n_frames;
+  Act Q = act_of(A, s.dimension, T, ACT_HALO);
+  if (launch_halo_fill(z_frames, Q.row0(), Q.stride(), T, s.dimension, x.n_items, ACT_HALO, 0, x.st)) return 1;
+  int ch = c->dec_in.c_out;
+  Act X = act_of(B, ch, T, 0);
+  if (tc_conv_gn(x, c->dec_in, Q, s.dimension, false, T, &X, nullptr, 0)) return 1;
+  if (tap_act(x.st, 100, X, x.n_items)) return 1;
+  Act cur = act_of(A, ch, T, 0);
+  if (s.lstm_layers) {
+    if (tc_lstm(x, c->dec_lstm, X, Cb, D, cur, 3)) return 1;
+    if (tap_act(x.st, 101, cur, x.n_items)) return 1;
+  } else {
+    if (launch_halo_fill(X.row0(), cur.row0(), cur.stride(), T, ch, x.n_items, 0, 1, x.st)) return 1;
+  }
+  for (int i = 0; i < s.n_ratios; ++i) {
+    const ConvW& uw = c->dec_up[i];
+    const int st = uw.stride;
+    const int sN = st * uw.c_out;
+    const int total = uw.k - st;
+    const int trim_right = s.causal ? total : total / 2;
+    const int trim_left = total - trim_right;
+    const long long T2 = T * st;
+    // untrimmed transposed conv [T + 1][s*Co] -> scratch (statistics cover all of it: the norm precedes unpad1d, conv.py:162)
+    Act R = act_of(Cb, sN, T + 1, 0);
+    int slots = 0;
+    if (tc_run(x, uw.t_hi, uw.t_lo, uw.t_bias, uw.t_K, uw.t_N, cur, ch, 2, 1, 1, true, nullptr, R.row0(), nullptr, R.stride(),
+               T + 1, 0, 3, 0, x.stat[0], &slots))
+      return 1;
+    Act X2 = act_of(B, uw.c_out, T2, ACT_HALO), E2 = act_of(D, uw.c_out, T2, ACT_HALO);
+    GnSrc a = gn_src(R.row0() + (long long)trim_left * uw.c_out, R.stride(), x.stat[0], slots, (double)(T + 1) * sN, uw.t_gamma,
+                     uw.t_beta);
+    if (launch_gn_apply2(a, nullptr, X2.row0(), E2.row0(), X2.stride(), x.n_items, T2, uw.c_out, 1e-5f, x.st)) return 1;
+    if (launch_halo_fill(nullptr, E2.row0(), E2.stride(), T2, uw.c_out, x.n_items, ACT_HALO, 0, x.st)) return 1;
+    T = T2;
+    ch = uw.c_out;
+    if (tap_act(x.st, 102 + 2 * i, X2, x.n_items)) return 1;
+    Act Y = act_of(A, ch, T, 0);
+    if (tc_res_gn(x, c->dec_res[i], X2, E2, Cb, F, Y)) return 1;
     if (tap_act(x.st, 103 + 2 * i, Y, x.n_items)) return 1;
     cur = Y;
   }
@@ -999,7 +1211,7 @@ int ecb_codec_finalize(ecb_codec* c, void* stream) {
     if (s.lstm_layers && prepare_lstm(c, "decoder.model.1", 512, c->dec_lstm, st)) return 1;
   }
   c->tc_ready = false;
-  if (!s.group_norm) {
+  {
     // tensor-core path (tc_conv.cu): every GEMM-shaped conv gets K-major split (hi, lo) weights
     if (c->has_enc) {
       if (prepare_conv_tc(c, c->enc_out, st)) return 1;
@@ -1048,8 +1260,16 @@ int ecb_encoder_forward(ecb_codec* c, const float* xin, int64_t n_items, int64_t
   if (setup_ctx(x, c, n_items, length, workspace, workspace_bytes, stream)) return 1;
   ECB_REQUIRE(c->has_enc, "encoder_forward: no encoder weights were loaded into this codec");
   const ecb_spec& s = c->spec;
-  if (!scale_out && use_tc(c, ceil_div_ll(length, c->hop)))
-    return encoder_forward_tc(x, xin, n_seg, length, x_batch_stride, x_seg_stride, x_chan_stride, emb_out, emb_frames_out);
+  if (use_tc(c, ceil_div_ll(length, c->hop))) {
+    if (scale_out &&
+        launch_segment_scale(xin, x_batch_stride, x_seg_stride, x_chan_stride, (int)n_seg, (int)n_items, (int)length, s.channels,
+                             scale_out, x.st))
+      return 1;
+    return s.group_norm ? encoder_forward_tc_gn(x, xin, n_seg, length, x_batch_stride, x_seg_stride, x_chan_stride, scale_out,
+                                                emb_out, emb_frames_out)
+                        : encoder_forward_tc(x, xin, n_seg, length, x_batch_stride, x_seg_stride, x_chan_stride, scale_out,
+                                             emb_out, emb_frames_out);
+  }
   float *A = x.buf[0], *B = x.buf[1], *C = x.buf[2], *D = x.buf[3];
 
   if (scale_out) {
@@ -1080,6 +1300,8 @@ int ecb_encoder_forward(ecb_codec* c, const float* xin, int64_t n_items, int64_t
   if (launch_conv_in(ci, x.st)) return 1;
   if (s.group_norm) {
     GnSrc a;
+  a.item_stride = 0;
+    a.item_stride = 0;
     a.x = A;
     a.partial = x.stat[0];
     a.slots = conv_in_stat_slots(ci);
@@ -1142,7 +1364,8 @@ int ecb_decoder_forward(ecb_codec* c, const float* z, const float* z_frames, int
       ECB_CUDA(cudaMemcpyAsync(D, C, sizeof(float) * (size_t)n_items * T * s.dimension, cudaMemcpyDeviceToDevice, x.st));
       z_frames = D;
     }
-    return decoder_forward_tc(x, z_frames, n_frames, scale, out);
+    return s.group_norm ? decoder_forward_tc_gn(x, z_frames, n_frames, scale, out)
+                        : decoder_forward_tc(x, z_frames, n_frames, scale, out);
   }
   if (run_conv(x, c->dec_in, z_frames, T, 0, A, 0, nullptr)) return 1;        // -> A raw [T][512]
   if (tap(x.st, 100, A, n_items * T * c->dec_in.c_out)) return 1;
@@ -1300,6 +1523,7 @@ int ecb_debug_tc_conv(const float* a0, int64_t a0_item_stride, int32_t C0, int64
     p.w_hi = hi; p.w_lo = lo; p.bias = bias;
     p.out_raw = out_raw; p.out_elu = out_elu; p.out_item_stride = out_item_stride;
     p.N = N; p.M = M; p.n_items = n_items; p.halo = halo; p.round_out = round_out; p.split = split;
+    p.stats = nullptr;
     rc = launch_tc_conv(p, st);
   }
   cudaError_t e = cudaStreamSynchronize(st);

@@ -164,7 +164,10 @@ struct TcConvParams {
   int halo;                   // also write the reflected rows -1..-halo and M..M+halo-1 of each output (0: none)
   int round_out;              // round stored values to TF32 (for split == 1 consumers)
   int split;                  // 3: fp32-accurate split operands; 1: single TF32 pass
+  double* stats;              // nullptr, or [item][tc_stat_slots(p)][2] partial (sum, sum of squares) of the raw output
+                              // (GroupNorm statistics; requires out_elu == nullptr, halo == 0, round_out == 0)
 };
+int tc_stat_slots(const TcConvParams& p);   // partial-statistics slots per item a launch writes
 int launch_tc_conv(const TcConvParams& p, cudaStream_t stream);
 int launch_split_weights(const float* w, float* hi, float* lo, int K, int N, int K_pad, int N_pad, cudaStream_t s);
 int tc_pick_bn(int N, int split);
@@ -216,6 +219,7 @@ int launch_segment_scale(const float* x, long long batch_stride, long long seg_s
                          int n_seg, int n_items, int T, int C, float* scale, cudaStream_t s);
 struct GnSrc {
   const float* x;         // [item][rows][C] raw conv output (stored region)
+  long long item_stride;  // floats between items; 0 means the dense rows*C
   const double* partial;  // [item][slots][2]
   int slots;
   double count;           // elements the statistics cover (untrimmed length * C)
@@ -225,6 +229,9 @@ struct GnSrc {
 // out = act(GN(a) [+ GN(b)]), elementwise over [n_items][rows][C]
 int launch_gn_apply(const GnSrc& a, const GnSrc* b, float* out, int n_items, long long rows, int C, int out_elu,
                     float eps, cudaStream_t s);
+// general form: strided items, raw and/or ELU output (either may alias a.x / b->x element for element)
+int launch_gn_apply2(const GnSrc& a, const GnSrc* b, float* out_raw, float* out_elu, long long out_item_stride, int n_items,
+                     long long rows, int C, float eps, cudaStream_t s);
 int launch_overlap_add(const float* frames, const int* seg_lens, long long batch, int channels, int n_seg,
                        int seg_len, int stride, float* out, long long total, cudaStream_t s);
 

@@ -171,17 +171,19 @@ __device__ __forceinline__ void gn_coeffs(const GnSrc& s, int item, float eps, f
 }
 
 __global__ void __launch_bounds__(256)
-gn_apply_kernel(const GnSrc a, const GnSrc b, int has_b, float* __restrict__ out, long long rows, int C, int out_elu,
-                float eps) {
+gn_apply_kernel(const GnSrc a, const GnSrc b, int has_b, float* __restrict__ out_raw, float* __restrict__ out_elu,
+                long long out_item_stride, long long rows, int C, float eps) {
   __shared__ double red[16];
   const int item = blockIdx.y;
   float mean_a, rstd_a, mean_b = 0.f, rstd_b = 0.f;
   gn_coeffs(a, item, eps, &mean_a, &rstd_a, red);
   if (has_b) gn_coeffs(b, item, eps, &mean_b, &rstd_b, red);
   const long long n4 = rows * C / 4;
-  const float4* xa = reinterpret_cast<const float4*>(a.x + (long long)item * rows * C);
-  const float4* xb = has_b ? reinterpret_cast<const float4*>(b.x + (long long)item * rows * C) : nullptr;
-  float4* o = reinterpret_cast<float4*>(out + (long long)item * rows * C);
+  const float4* xa = reinterpret_cast<const float4*>(a.x + (long long)item * (a.item_stride ? a.item_stride : rows * C));
+  const float4* xb = has_b ? reinterpret_cast<const float4*>(b.x + (long long)item * (b.item_stride ? b.item_stride : rows * C)) : nullptr;
+  const long long ostride = out_item_stride ? out_item_stride : rows * C;
+  float4* o_raw = out_raw ? reinterpret_cast<float4*>(out_raw + (long long)item * ostride) : nullptr;
+  float4* o_elu = out_elu ? reinterpret_cast<float4*>(out_elu + (long long)item * ostride) : nullptr;
   const int c4n = C / 4;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % c4n) * 4;
@@ -201,10 +203,8 @@ gn_apply_kernel(const GnSrc a, const GnSrc b, int has_b, float* __restrict__ out
       v.z += (u.z - mean_b) * rstd_b * g2.z + b2.z;
       v.w += (u.w - mean_b) * rstd_b * g2.w + b2.w;
     }
-    if (out_elu) {
-      v.x = elu1(v.x); v.y = elu1(v.y); v.z = elu1(v.z); v.w = elu1(v.w);
-    }
-    o[i] = v;
+    if (o_raw) o_raw[i] = v;
+    if (o_elu) o_elu[i] = make_float4(elu1(v.x), elu1(v.y), elu1(v.z), elu1(v.w));
   }
 }
 
@@ -293,15 +293,20 @@ int launch_segment_scale(const float* x, long long batch_stride, long long seg_s
   ECB_LAUNCHED();
   return 0;
 }
-int launch_gn_apply(const GnSrc& a, const GnSrc* b, float* out, int n_items, long long rows, int C, int out_elu,
-                    float eps, cudaStream_t s) {
-  ECB_REQUIRE(C % 4 == 0, "gn_apply: C=%d", C);
+int launch_gn_apply2(const GnSrc& a, const GnSrc* b, float* out_raw, float* out_elu, long long out_item_stride, int n_items,
+                     long long rows, int C, float eps, cudaStream_t s) {
+  ECB_REQUIRE(C % 4 == 0 && (out_raw || out_elu), "gn_apply: C=%d", C);
   const long long n4 = rows * C / 4;
   dim3 grid((unsigned)min(cdiv(n4, 256 * 4), 4096LL), (unsigned)n_items);
-  ProfScope prof(PROF_GN_APPLY, s, 0.0, 4.0 * (double)rows * C * n_items * (b ? 3 : 2));
-  gn_apply_kernel<<<grid, 256, 0, s>>>(a, b ? *b : a, b ? 1 : 0, out, rows, C, out_elu, eps);
+  ProfScope prof(PROF_GN_APPLY, s, 0.0,
+                 4.0 * (double)rows * C * n_items * ((b ? 2 : 1) + (out_raw ? 1 : 0) + (out_elu ? 1 : 0)));
+  gn_apply_kernel<<<grid, 256, 0, s>>>(a, b ? *b : a, b ? 1 : 0, out_raw, out_elu, out_item_stride, rows, C, eps);
   ECB_LAUNCHED();
   return 0;
+}
+int launch_gn_apply(const GnSrc& a, const GnSrc* b, float* out, int n_items, long long rows, int C, int out_elu,
+                    float eps, cudaStream_t s) {
+  return launch_gn_apply2(a, b, out_elu ? nullptr : out, out_elu ? out : nullptr, 0, n_items, rows, C, eps, s);
 }
 int launch_overlap_add(const float* frames, const int* seg_lens, long long batch, int channels, int n_seg,
                        int seg_len, int stride, float* out, long long total, cudaStream_t s) {

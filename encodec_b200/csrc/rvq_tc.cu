@@ -63,15 +63,16 @@ rvq_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
   const uint32_t b_ring = smem_base + 2 * NKC * A_TILE;
   uint8_t* misc = smem_gen + 2 * NKC * A_TILE + STAGES * STAGE_BYTES;
   float* x2s = reinterpret_cast<float*>(misc);                 // [2][128] partial |x|^2 of the two dim halves
-  float* cand_d = x2s + 2 * FT;                                // [2][128] arg-min candidates of the two entry halves
-  int* cand_i = reinterpret_cast<int*>(cand_d + 2 * FT);       // [2][128]
-  const uint32_t bar_base = smem_base + 2 * NKC * A_TILE + STAGES * STAGE_BYTES + 4096;
+  float* cand_d = x2s + 2 * FT;                                // [4][128] best / runner-up of the two entry halves
+  int* cand_i = reinterpret_cast<int*>(cand_d + 4 * FT);       // [4][128]
+  float* ex_d = reinterpret_cast<float*>(cand_i + 4 * FT);     // [2][128] exact distances of re-ranked candidates
+  const uint32_t bar_base = smem_base + 2 * NKC * A_TILE + STAGES * STAGE_BYTES + 7168;   // after the 6 KB of arrays above
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto accf_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };
   auto acce_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
   const uint32_t rready_bar = bar_base + 8u * (2 * STAGES + 4);   // residual tile (re)written for the next layer
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 4096 + 8 * (2 * STAGES + 5));
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 7168 + 8 * (2 * STAGES + 5));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -192,8 +193,8 @@ rvq_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
       for (int layer = 0; layer < p.n_q; ++layer) {
         const float x2 = x2s[f] + x2s[FT + f];
         const float* e2 = p.e2 + (long long)layer * p.bins;
-        float best_d = INFINITY;
-        int best_i = 0;
+        float best_d = INFINITY, sec_d = INFINITY;   // best and runner-up of this thread's entries
+        int best_i = 0, sec_i = 0;
         for (int blk = 0; blk < n_blocks; ++blk, ++bc) {
           const int ab = (int)(bc & 1u);
           mbar_wait(accf_bar(ab), (bc >> 1) & 1u);
@@ -211,9 +212,12 @@ rvq_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
               const float dot = __uint_as_float(vm[i]) + __uint_as_float(vc[i]);
               const float t = __fsub_rn(x2, 2.f * dot);                 // core_vq.py:183-187 association order
               const float d = __fadd_rn(t, __ldg(e2 + j0 + i));
-              if (d < best_d) {
-                best_d = d;
-                best_i = j0 + i;
+              if (d < sec_d) {
+                const bool nb = d < best_d;        // strict: entries ascend, so ties keep the lowest index in front
+                sec_d = nb ? best_d : d;
+                sec_i = nb ? best_i : j0 + i;
+                best_d = nb ? d : best_d;
+                best_i = nb ? j0 + i : best_i;
               }
             }
           }
@@ -221,13 +225,59 @@ rvq_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
           __syncwarp();
           if (lane == 0) mbar_arrive(acce_bar(ab));
         }
-        // ---- arg-min across the two entry halves (lowest index on ties), then gather / update
-        cand_d[half * FT + f] = best_d;
-        cand_i[half * FT + f] = best_i;
+        // ---- arg-min across the two entry halves (lowest index on ties). The tensor-core distances carry ~1e-6
+        // relative error after the |x|^2 - 2 x.e + |e|^2 cancellation; when the two leading candidates are closer than
+        // 1e-4 relative they are re-ranked with an exact fp32 evaluation (sequential fmaf over the 128 dims, the
+        // arithmetic of the CUDA-core kernel), so near-ties resolve the way an fp32 implementation resolves them.
+        cand_d[(half * 2 + 0) * FT + f] = best_d;
+        cand_i[(half * 2 + 0) * FT + f] = best_i;
+        cand_d[(half * 2 + 1) * FT + f] = sec_d;
+        cand_i[(half * 2 + 1) * FT + f] = sec_i;
         asm volatile("bar.sync 1, 256;" ::: "memory");
-        const float d0 = cand_d[f], d1 = cand_d[FT + f];
-        const int i0 = cand_i[f], i1 = cand_i[FT + f];
-        const int code = (d1 < d0 || (d1 == d0 && i1 < i0)) ? i1 : i0;
+        float td[4];
+        int ti[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          td[c] = cand_d[c * FT + f];
+          ti[c] = cand_i[c * FT + f];
+        }
+        // top two of the four candidates, ordered by (distance, index)
+        float d0 = INFINITY, d1 = INFINITY;
+        int i0 = 0x7fffffff, i1 = 0x7fffffff;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const bool lt1 = td[c] < d1 || (td[c] == d1 && ti[c] < i1);
+          if (lt1) {
+            const bool lt0 = td[c] < d0 || (td[c] == d0 && ti[c] < i0);
+            d1 = lt0 ? d0 : td[c];
+            i1 = lt0 ? i0 : ti[c];
+            d0 = lt0 ? td[c] : d0;
+            i0 = lt0 ? ti[c] : i0;
+          }
+        }
+        const bool rerank = (d1 - d0) <= 1e-4f * fabsf(d0) && i1 != 0x7fffffff && i1 < p.bins;
+        if (rerank) {
+          // thread `half` evaluates candidate `half` exactly
+          const int ci = half == 0 ? i0 : i1;
+          const float4* e4 = reinterpret_cast<const float4*>(p.codebooks + ((long long)layer * p.bins + ci) * RD);
+          float dot = 0.f;
+#pragma unroll 8
+          for (int d4 = 0; d4 < 32; ++d4) {
+            const float4 rv = *reinterpret_cast<const float4*>(smem_gen + r_off(d4));
+            const float4 ev = __ldg(e4 + d4);
+            dot = fmaf(rv.x, ev.x, dot);
+            dot = fmaf(rv.y, ev.y, dot);
+            dot = fmaf(rv.z, ev.z, dot);
+            dot = fmaf(rv.w, ev.w, dot);
+          }
+          ex_d[half * FT + f] = __fadd_rn(__fsub_rn(x2, 2.f * dot), __ldg(e2 + ci));
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        int code = i0;
+        if (rerank) {
+          const float e0 = ex_d[f], e1 = ex_d[FT + f];
+          code = (e1 < e0 || (e1 == e0 && i1 < i0)) ? i1 : i0;
+        }
         if (half == 0 && live) p.codes[(long long)layer * p.n + fg] = (long long)code;
         const float4* q4 = reinterpret_cast<const float4*>(p.codebooks + ((long long)layer * p.bins + code) * RD) + half * 16;
         float x2n = 0.f;

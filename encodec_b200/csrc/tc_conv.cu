@@ -66,6 +66,7 @@ struct TcArgs {
   int rowlen0;              // floats per folded row of source 0 (stride * C0)
   int row_base0, row_base1; // row coordinate of output row 0's first chunk in each source's map
   int round_out, halo;
+  double* stats;            // [item][tiles_m][tiles_n][8 warps][2] or nullptr
   int group;                // K chunks per main-accumulator group (SPLIT == 1: all of them)
 };
 
@@ -74,9 +75,9 @@ using namespace tc;
 // Copy one staged [32 rows x 64 B] half block out of shared memory with coalesced 16-byte stores (four lanes per
 // 64-byte row segment, 8 rows per warp instruction): raw output as is, ELU output through elu1. The output modes are
 // template parameters so that the loop body is nothing but LDS -> (ELU) -> STG.
-template <bool RAW, bool ELU, bool ROUND>
+template <bool RAW, bool ELU, bool ROUND, bool STATS>
 __device__ __forceinline__ void copy_out_rows(const uint8_t* slot, int lane, float* praw, float* pelu, long long row_step,
-                                              int rows_left) {
+                                              int rows_left, float& st_sum, float& st_sq) {
   const int c16 = lane & 3;
   int rr = lane >> 2;
   praw += (long long)rr * (row_step >> 3);
@@ -85,6 +86,10 @@ __device__ __forceinline__ void copy_out_rows(const uint8_t* slot, int lane, flo
   for (int i = 0; i < 4; ++i, rr += 8) {
     if (rr >= rows_left) break;
     const float4 v = *reinterpret_cast<const float4*>(slot + rr * 64 + ((c16 ^ ((rr >> 1) & 3)) << 4));
+    if (STATS) {
+      st_sum += (v.x + v.y) + (v.z + v.w);
+      st_sq += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+    }
     if (RAW) {
       *reinterpret_cast<float4*>(praw) = ROUND ? make_float4(rn_tf32(v.x), rn_tf32(v.y), rn_tf32(v.z), rn_tf32(v.w)) : v;
       praw += row_step;
@@ -267,6 +272,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       const int m_warp = mt * BM + quad * 32;       // first output row of this warp
       // does this warp hold rows whose reflected copies (conv.py:80-97) must be written too?
       const bool mirrors = p.halo > 0 && (m_warp <= p.halo || m_warp + 31 >= p.M - 1 - p.halo);
+      float st_sum = 0.f, st_sq = 0.f;   // GroupNorm partial statistics of this warp's part of the tile (p.stats only)
 
       // One 16-column half block: the bias-added values go to this warp's staging slot in a chunk-swizzled layout, then
       // the warp copies the slot out with coalesced 16-byte stores (four lanes per 64-byte row segment): the raw
@@ -292,12 +298,15 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           float* praw = p.out_raw + base;   // only dereferenced when the mode says so
           float* pelu = p.out_elu + base;
           switch (out_mode) {
-            case 1: copy_out_rows<true, false, false>(slot_gen, lane, praw, pelu, step, rows_left); break;
-            case 2: copy_out_rows<false, true, false>(slot_gen, lane, praw, pelu, step, rows_left); break;
-            case 3: copy_out_rows<true, true, false>(slot_gen, lane, praw, pelu, step, rows_left); break;
-            case 5: copy_out_rows<true, false, true>(slot_gen, lane, praw, pelu, step, rows_left); break;
-            case 6: copy_out_rows<false, true, true>(slot_gen, lane, praw, pelu, step, rows_left); break;
-            default: copy_out_rows<true, true, true>(slot_gen, lane, praw, pelu, step, rows_left); break;
+            case 1:
+              if (p.stats) copy_out_rows<true, false, false, true>(slot_gen, lane, praw, pelu, step, rows_left, st_sum, st_sq);
+              else copy_out_rows<true, false, false, false>(slot_gen, lane, praw, pelu, step, rows_left, st_sum, st_sq);
+              break;
+            case 2: copy_out_rows<false, true, false, false>(slot_gen, lane, praw, pelu, step, rows_left, st_sum, st_sq); break;
+            case 3: copy_out_rows<true, true, false, false>(slot_gen, lane, praw, pelu, step, rows_left, st_sum, st_sq); break;
+            case 5: copy_out_rows<true, false, true, false>(slot_gen, lane, praw, pelu, step, rows_left, st_sum, st_sq); break;
+            case 6: copy_out_rows<false, true, true, false>(slot_gen, lane, praw, pelu, step, rows_left, st_sum, st_sq); break;
+            default: copy_out_rows<true, true, true, false>(slot_gen, lane, praw, pelu, step, rows_left, st_sum, st_sq); break;
           }
         } else {
           // first / last rows of an item: also write the reflected copies (conv.py:80-97); rare, generic loop
@@ -395,6 +404,20 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           if (lane == 0) mbar_arrive(maine_bar(mb_last));
         }
         finish_block(o, cc);
+      }
+      if (p.stats) {
+        // deterministic two-stage reduction: per-warp partials here, summed per item in gn_apply (misc.cu)
+        double ds = (double)st_sum, dq = (double)st_sq;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+          ds += __shfl_xor_sync(0xffffffffu, ds, off);
+          dq += __shfl_xor_sync(0xffffffffu, dq, off);
+        }
+        if (lane == 0) {
+          double* sp = p.stats + (((long long)item * p.tiles_m + mt) * p.tiles_n + nt) * 16 + (warp - 4) * 2;
+          sp[0] = ds;
+          sp[1] = dq;
+        }
       }
     }
   }
@@ -502,6 +525,10 @@ int tc_pick_bn(int N, int split) {
   return N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : (N % 64 == 0 ? 64 : 32));
 }
 
+int tc_stat_slots(const TcConvParams& p) {
+  return (int)(cdiv(p.M, BM) * (p.N / tc_pick_bn(p.N, p.split)) * 8);
+}
+
 int launch_tc_conv(const TcConvParams& p, cudaStream_t stream) {
   ECB_REQUIRE(p.split == 1 || p.split == 3, "tc_conv: split must be 1 or 3");
   ECB_REQUIRE(p.N % 32 == 0 && p.N > 0, "tc_conv: N=%d must be a multiple of 32", p.N);
@@ -510,6 +537,7 @@ int launch_tc_conv(const TcConvParams& p, cudaStream_t stream) {
   ECB_REQUIRE(p.M > 0 && p.n_items > 0, "tc_conv: bad M=%lld / items=%d", p.M, p.n_items);
   ECB_REQUIRE(p.out_raw || p.out_elu, "tc_conv: no output");
   ECB_REQUIRE(p.halo == 0 || p.M > p.halo, "tc_conv: %lld rows are too few for a %d-row reflected halo", p.M, p.halo);
+  ECB_REQUIRE(!p.stats || (p.out_raw && !p.out_elu && p.halo == 0 && !p.round_out), "tc_conv: statistics need a plain raw output");
   const int bn = tc_pick_bn(p.N, p.split);
   const int s = p.stride;
   const int ktot = p.taps * p.C0 + (p.a1 ? p.C1 : 0);
@@ -562,6 +590,7 @@ int launch_tc_conv(const TcConvParams& p, cudaStream_t stream) {
   a.row_base1 = 0;
   a.round_out = p.round_out;
   a.halo = p.halo;
+  a.stats = p.stats;
   {
     const int nch = a.nch0 + a.nch1;
     a.group = (p.split == 3 && nch > 6) ? 4 : nch;   // <= 24 truncating accumulation steps per group
