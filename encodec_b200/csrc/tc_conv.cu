@@ -597,7 +597,9 @@ int launch_tc_conv(const TcConvParams& p, cudaStream_t stream) {
   }
   const int grid = (int)(total < sm_count() ? total : sm_count());
   const double rows = (double)p.M * p.n_items;
-  ProfScope prof(PROF_TC_CONV, stream, 2.0 * rows * p.N * ktot,
+  // narrow layers (<= 64 channels on every side) are HBM-bound, the others tensor-bound
+  const bool narrow = p.C0 <= 64 && p.N <= 64 && (!p.a1 || p.C1 <= 64);
+  ProfScope prof(narrow ? PROF_TC_CONV_NARROW : PROF_TC_CONV_WIDE, stream, 2.0 * rows * p.N * ktot,
                  4.0 * (rows * s * p.C0 + (p.a1 ? rows * p.C1 : 0.0) + (double)ktot * p.N +
                         rows * p.N * ((p.out_raw ? 1 : 0) + (p.out_elu ? 1 : 0))));
 #define ECB_TC_CASE(BN_, SP_) \

@@ -70,7 +70,8 @@ def main():
             nat.profile_begin()
             for _ in range(args.reps):
                 run()
-            prof = nat.profile_end()["tc_conv"]
+            res = nat.profile_end()
+            prof = res.get("tc_conv_narrow") or res["tc_conv_wide"]
             ms = prof["ms"] / args.reps
             print(f"{name:14s} {split:5d} {ms:8.3f} {prof['flops'] / args.reps / ms / 1e9:8.1f} "
                   f"{prof['bytes'] / args.reps / ms / 1e6:8.0f}", flush=True)
