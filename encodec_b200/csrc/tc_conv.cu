@@ -29,6 +29,7 @@
 //     an output may be written raw, ELU'd or both (a residual block consumes x through its shortcut and
 //     ELU(x) through its first conv) and its reflected halo rows are written directly.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -38,20 +39,25 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 32;                      // fp32 per K chunk = one 128-byte swizzle row
-constexpr int A_BYTES = BM * BK * 4;        // 16 KB
 constexpr int TC_THREADS = 384;              // 12 warps: TMA, MMA, 2 x transform, 8 x epilogue
 constexpr int STAGING_BYTES = 8 * 2048;     // 8 epilogue warps x [32 rows x 64 B]
+
+constexpr int A_ROWS = BM + 8;               // an A tile carries up to 8 extra rows: the taps of a conv are row shifts of it
+constexpr int A_TILE = A_ROWS * BK * 4;      // 17 KB
 
 template <int BN, int SPLIT>
 struct Cfg {
   static constexpr int B_BYTES = BN * BK * 4;
-  static constexpr int STAGE_BYTES = (SPLIT == 3) ? 2 * A_BYTES + 2 * B_BYTES : A_BYTES + B_BYTES;
+  static constexpr int A_STAGE = (SPLIT == 3) ? 2 * A_TILE : A_TILE;     // a (+ a_lo)
+  static constexpr int B_STAGE = (SPLIT == 3) ? 2 * B_BYTES : B_BYTES;   // w_hi (+ w_lo, directly behind it)
   static constexpr int BUDGET = 227 * 1024 - STAGING_BYTES - 1024 - 512;
-  static constexpr int S0 = BUDGET / STAGE_BYTES;
-  static constexpr int STAGES = S0 > 6 ? 6 : S0;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + STAGING_BYTES + 1024 + 512;
+  // A ring: 3 stages with wide tiles, 4 otherwise; the B ring takes what is left (at most 8 stages)
+  static constexpr int A_STAGES = (BN >= 128) ? 3 : 4;
+  static constexpr int SB0 = (BUDGET - A_STAGES * A_STAGE) / B_STAGE;
+  static constexpr int B_STAGES = SB0 > 8 ? 8 : SB0;
+  static constexpr int SMEM_BYTES = A_STAGES * A_STAGE + B_STAGES * B_STAGE + STAGING_BYTES + 1024 + 512;
   static constexpr int TMEM_COLS = (SPLIT == 3) ? 4 * BN : 2 * BN;   // two main (+ two correction) accumulators
-  static_assert(STAGES >= 2, "pipeline too shallow");
+  static_assert(B_STAGES >= 2, "pipeline too shallow");
   static_assert(TMEM_COLS <= 512, "TMEM overflow");
 };
 
@@ -62,9 +68,10 @@ struct TcArgs {
   long long out_item_stride;
   int N, M, n_items;
   int tiles_m, tiles_n, total_tiles;
-  int nch0, nch1;           // K chunks of source 0 / source 1
-  int rowlen0;              // floats per folded row of source 0 (stride * C0)
-  int row_base0, row_base1; // row coordinate of output row 0's first chunk in each source's map
+  int n_cb0, n_cb1;         // 32-channel column blocks of source 0 (of its folded row) / source 1: one A tile each
+  int shifts;               // row shifts per source-0 tile (taps of a stride-1 conv, 2 folded rows of a strided one)
+  int a_rows;               // rows per A tile box: BM (+ 8 when shifts > 1)
+  int row_base0, row_base1; // row coordinate of output row 0's window start in each source's map
   int round_out, halo;
   double* stats;            // [item][tiles_m][tiles_n][8 warps][2] or nullptr
   int group;                // K chunks per main-accumulator group (SPLIT == 1: all of them)
@@ -109,28 +116,41 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
                const TcArgs p) {
   using C = Cfg<BN, SPLIT>;
-  constexpr int STAGES = C::STAGES;
+  constexpr int SA = C::A_STAGES, SB = C::B_STAGES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t staging_base = smem_base + STAGES * C::STAGE_BYTES;
-  const uint32_t bar_base = staging_base + STAGING_BYTES;
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto ready_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
-  auto mainf_bar = [&](int b) { return bar_base + 8u * (3 * STAGES + b); };       // accumulator b holds a finished K group
-  auto maine_bar = [&](int b) { return bar_base + 8u * (3 * STAGES + 2 + b); };   // ... has been drained by the epilogue
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + STAGES * C::STAGE_BYTES + STAGING_BYTES + 8 * (3 * STAGES + 4));
+  // layout: A ring [SA][a | a_lo] | B ring [SB][w_hi | w_lo] | epilogue staging | barriers
+  const uint32_t a_ring = smem_base;
+  const uint32_t b_ring = smem_base + SA * C::A_STAGE;
+  constexpr int STAGING_OFF = SA * C::A_STAGE + SB * C::B_STAGE;
+  const uint32_t bar_base = smem_base + STAGING_OFF + STAGING_BYTES;
+  auto afull_bar = [&](int s) { return bar_base + 8u * s; };                 // TMA landed the A tile
+  auto aready_bar = [&](int s) { return bar_base + 8u * (SA + s); };         // transform wrote a_lo
+  auto aempty_bar = [&](int s) { return bar_base + 8u * (2 * SA + s); };     // MMAs have read the A tile
+  auto bfull_bar = [&](int s) { return bar_base + 8u * (3 * SA + s); };
+  auto bempty_bar = [&](int s) { return bar_base + 8u * (3 * SA + SB + s); };
+  auto mainf_bar = [&](int b) { return bar_base + 8u * (3 * SA + 2 * SB + b); };       // accumulator b holds a finished K group
+  auto maine_bar = [&](int b) { return bar_base + 8u * (3 * SA + 2 * SB + 2 + b); };   // ... has been drained by the epilogue
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + STAGING_OFF + STAGING_BYTES + 8 * (3 * SA + 2 * SB + 4));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int nch = p.nch0 + p.nch1;
+  // K chunk sequence of a tile: for every source-0 column block its `shifts` row shifts, then the source-1 blocks.
+  // Chunk c reads A tile (group) ag at row shift j and weight columns [k0, k0 + 32).
+  const int nch0 = p.n_cb0 * p.shifts;
+  const int nch = nch0 + p.n_cb1;
+  const int n_groups_a = p.n_cb0 + p.n_cb1;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(ready_bar(s), 2);   // one arrive per transform warp
-      mbar_init(empty_bar(s), 1);
+    for (int s = 0; s < SA; ++s) {
+      mbar_init(afull_bar(s), 1);
+      mbar_init(aready_bar(s), 2);   // one arrive per transform warp
+      mbar_init(aempty_bar(s), 1);
+    }
+    for (int s = 0; s < SB; ++s) {
+      mbar_init(bfull_bar(s), 1);
+      mbar_init(bempty_bar(s), 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(mainf_bar(b), 1);
@@ -154,29 +174,40 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 
   if (warp == 0) {
     // ================================ TMA producer ================================
-    if (lane == 0) {
-      int it = 0;
+    // Every A tile ([a_rows x 32 channels]) is loaded ONCE per output tile; the taps of the conv read it at different
+    // row offsets. Weight chunks stream through their own ring.
+    {
+      uint32_t ia = 0, ib = 0;
+      const uint32_t a_bytes = (uint32_t)p.a_rows * BK * 4;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int nt = tile % p.tiles_n;
         const int mt_all = tile / p.tiles_n;
         const int mt = mt_all % p.tiles_m;
         const int item = mt_all / p.tiles_m;
-        for (int c = 0; c < nch; ++c, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-          mbar_wait(empty_bar(s), ph ^ 1u);
-          const uint32_t a_dst = smem_base + s * C::STAGE_BYTES;
-          const uint32_t bhi_dst = a_dst + (SPLIT == 3 ? 2 : 1) * A_BYTES;
-          mbar_expect_tx(full_bar(s), A_BYTES + (SPLIT == 3 ? 2 : 1) * C::B_BYTES);
-          if (c < p.nch0) {
-            const int k0 = c * BK;
-            const int r = k0 / p.rowlen0;
-            tma_load_3d(a_dst, &map_a0, full_bar(s), k0 - r * p.rowlen0, mt * BM + p.row_base0 + r, item);
-          } else {
-            tma_load_3d(a_dst, &map_a1, full_bar(s), (c - p.nch0) * BK, mt * BM + p.row_base1, item);
+        for (int ag = 0; ag < n_groups_a; ++ag, ++ia) {
+          const int sa = (int)(ia % SA);
+          mbar_wait(aempty_bar(sa), ((ia / SA) & 1u) ^ 1u);
+          if (elect_one()) {
+            mbar_expect_tx(afull_bar(sa), a_bytes);
+            if (ag < p.n_cb0)
+              tma_load_3d(a_ring + sa * C::A_STAGE, &map_a0, afull_bar(sa), ag * BK, mt * BM + p.row_base0, item);
+            else
+              tma_load_3d(a_ring + sa * C::A_STAGE, &map_a1, afull_bar(sa), (ag - p.n_cb0) * BK, mt * BM + p.row_base1, item);
           }
-          tma_load_2d(bhi_dst, &map_bhi, full_bar(s), c * BK, nt * BN);
-          if (SPLIT == 3) tma_load_2d(bhi_dst + C::B_BYTES, &map_blo, full_bar(s), c * BK, nt * BN);
+          __syncwarp();
+          const int nj = ag < p.n_cb0 ? p.shifts : 1;
+          for (int j = 0; j < nj; ++j, ++ib) {
+            const int sb = (int)(ib % SB);
+            mbar_wait(bempty_bar(sb), ((ib / SB) & 1u) ^ 1u);
+            const int k0 = ag < p.n_cb0 ? (j * p.n_cb0 + ag) * BK : (nch0 + (ag - p.n_cb0)) * BK;
+            const uint32_t dst = b_ring + sb * C::B_STAGE;
+            if (elect_one()) {
+              mbar_expect_tx(bfull_bar(sb), C::B_STAGE);
+              tma_load_2d(dst, &map_bhi, bfull_bar(sb), k0, nt * BN);
+              if (SPLIT == 3) tma_load_2d(dst + C::B_BYTES, &map_blo, bfull_bar(sb), k0, nt * BN);
+            }
+            __syncwarp();
+          }
         }
       }
     }
@@ -187,41 +218,54 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     // result: their truncation is irrelevant) to a CORRECTION accumulator in the adjacent TMEM columns; the epilogue
     // drains both every `group` K chunks and re-accumulates in registers (round-to-nearest), alternating between two
     // TMEM buffers. Per K step: D[main | corr] (+)= a * [w_hi | w_lo] (one MMA, N = 2 BN: w_lo's tile follows w_hi's
-    // in shared memory) and D[corr] += a_lo * w_hi.
-    if (lane == 0) {
+    // in shared memory) and D[corr] += a_lo * w_hi. The whole warp stays converged and one elected lane issues.
+    {
       constexpr uint32_t idesc = umma_idesc_tf32(BM, BN);
       constexpr uint32_t idesc2 = umma_idesc_tf32(BM, SPLIT == 3 ? 2 * BN : BN);
-      int it = 0;
-      uint32_t gcount = 0;
+      // descriptors: constant high word (SBO, version, SWIZZLE_128B) + start address >> 4 in the low word
+      constexpr uint32_t DESC_HI = 64u | (1u << 14) | (2u << 29);
+      auto mk_desc = [](uint32_t addr, uint32_t hi) { return ((uint64_t)hi << 32) | (uint64_t)(((addr & 0x3FFFFu) >> 4) | (1u << 16)); };
+      uint32_t ia = 0, ib = 0, gcount = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        for (int c0 = 0; c0 < nch; c0 += p.group, ++gcount) {
-          const int c1 = min(c0 + p.group, nch);
-          const int mb = (int)(gcount & 1u);
-          mbar_wait(maine_bar(mb), ((gcount >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t d_main = tmem_base + main_col(mb);
-          for (int c = c0; c < c1; ++c, ++it) {
-            const int s = it % STAGES;
-            const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-            mbar_wait(full_bar(s), ph);
-            if (SPLIT == 3) mbar_wait(ready_bar(s), ph);
+        int c = 0;         // chunk index inside the tile
+        int in_group = 0;  // chunks accumulated into the current accumulator
+        for (int ag = 0; ag < n_groups_a; ++ag, ++ia) {
+          const int sa = (int)(ia % SA);
+          mbar_wait(afull_bar(sa), (ia / SA) & 1u);
+          if (SPLIT == 3) mbar_wait(aready_bar(sa), (ia / SA) & 1u);
+          const uint32_t a_addr = a_ring + sa * C::A_STAGE;
+          const int nj = ag < p.n_cb0 ? p.shifts : 1;
+          for (int j = 0; j < nj; ++j, ++ib, ++c) {
+            if (in_group == 0) mbar_wait(maine_bar((int)(gcount & 1u)), ((gcount >> 1) & 1u) ^ 1u);   // accumulator drained
+            const uint32_t d_main = tmem_base + main_col((int)(gcount & 1u));
+            const int sb = (int)(ib % SB);
+            mbar_wait(bfull_bar(sb), (ib / SB) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t a_addr = smem_base + s * C::STAGE_BYTES;
-            const uint32_t alo_addr = a_addr + A_BYTES;
-            const uint32_t bhi_addr = a_addr + (SPLIT == 3 ? 2 : 1) * A_BYTES;
+            const bool close_group = (in_group + 1 == p.group) || (c + 1 == nch);
+            if (elect_one()) {
+              // tap j of the conv = the A tile read j rows further down: the start moves by j * 128 bytes. The 128-byte
+              // swizzle is a function of the absolute shared-memory address (verified on B200: with the descriptor's
+              // base-offset field left 0 every row shift reads the rows TMA wrote), so nothing else changes.
+              const uint32_t a_sh = a_addr + (uint32_t)j * 128u;
+              const uint64_t da0 = mk_desc(a_sh, DESC_HI);
+              const uint64_t dal0 = mk_desc(a_sh + A_TILE, DESC_HI);
+              const uint64_t db0 = mk_desc(b_ring + sb * C::B_STAGE, DESC_HI);
 #pragma unroll
-            for (int k = 0; k < BK / 8; ++k) {
-              const uint64_t da = umma_desc_sw128(a_addr + k * 32);
-              const uint64_t dbh = umma_desc_sw128(bhi_addr + k * 32);
-              tcgen05_mma_tf32(d_main, da, dbh, idesc2, (c > c0 || k > 0) ? 1u : 0u);
-              if (SPLIT == 3) {
-                const uint64_t dal = umma_desc_sw128(alo_addr + k * 32);
-                tcgen05_mma_tf32(d_main + BN, dal, dbh, idesc, 1u);
+              for (int k = 0; k < BK / 8; ++k) {
+                tcgen05_mma_tf32(d_main, da0 + 2u * k, db0 + 2u * k, idesc2, (in_group > 0 || k > 0) ? 1u : 0u);
+                if (SPLIT == 3) tcgen05_mma_tf32(d_main + BN, dal0 + 2u * k, db0 + 2u * k, idesc, 1u);
               }
+              tcgen05_commit(bempty_bar(sb));                                  // weight stage free once these MMAs have read it
+              if (close_group) tcgen05_commit(mainf_bar((int)(gcount & 1u)));  // K group complete -> epilogue
+              if (j + 1 == nj) tcgen05_commit(aempty_bar(sa));                 // A tile free once all its taps are done
             }
-            tcgen05_commit(empty_bar(s));   // frees the stage once these MMAs have read it
+            __syncwarp();
+            ++in_group;
+            if (close_group) {
+              ++gcount;
+              in_group = 0;
+            }
           }
-          tcgen05_commit(mainf_bar(mb));    // K group complete -> epilogue
         }
       }
     }
@@ -229,27 +273,27 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     // ================================ transform: a_lo = rn_tf32(a - trunc_tf32(a)) ================================
     if (SPLIT == 3) {
       const int tt = threadIdx.x - 64;  // 0..63
-      int it = 0;
+      const int n4 = p.a_rows * (BK / 4);   // float4 per A tile (a multiple of 64)
+      uint32_t ia = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        for (int c = 0; c < nch; ++c, ++it) {
-          const int s = it % STAGES;
-          const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-          mbar_wait(full_bar(s), ph);
-          const float4* a = reinterpret_cast<const float4*>(smem_gen + s * C::STAGE_BYTES);
-          float4* alo = reinterpret_cast<float4*>(smem_gen + s * C::STAGE_BYTES + A_BYTES);
-#pragma unroll
-          for (int i = 0; i < A_BYTES / 16 / 64; ++i) {
-            const float4 v = a[tt + i * 64];
+        for (int ag = 0; ag < n_groups_a; ++ag, ++ia) {
+          const int sa = (int)(ia % SA);
+          mbar_wait(afull_bar(sa), (ia / SA) & 1u);
+          const float4* a = reinterpret_cast<const float4*>(smem_gen + sa * C::A_STAGE);
+          float4* alo = reinterpret_cast<float4*>(smem_gen + sa * C::A_STAGE + A_TILE);
+#pragma unroll 4
+          for (int i = tt; i < n4; i += 64) {
+            const float4 v = a[i];
             float4 r;
             r.x = rn_tf32(v.x - trunc_tf32(v.x));
             r.y = rn_tf32(v.y - trunc_tf32(v.y));
             r.z = rn_tf32(v.z - trunc_tf32(v.z));
             r.w = rn_tf32(v.w - trunc_tf32(v.w));
-            alo[tt + i * 64] = r;   // same offset => same swizzled position
+            alo[i] = r;   // same offset => same swizzled position
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
           __syncwarp();
-          if (lane == 0) mbar_arrive(ready_bar(s));
+          if (lane == 0) mbar_arrive(aready_bar(sa));
         }
       }
     }
@@ -261,7 +305,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     const int quad = warp & 3;
     const int half = (warp - 4) >> 2;
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 16);
-    uint8_t* slot_gen = smem_gen + STAGES * C::STAGE_BYTES + (warp - 4) * 2048;   // this warp's [32 rows x 64 B] staging slot
+    uint8_t* slot_gen = smem_gen + STAGING_OFF + (warp - 4) * 2048;   // this warp's [32 rows x 64 B] staging slot
     uint32_t gcount = 0;
     const int out_mode = (p.out_raw ? 1 : 0) | (p.out_elu ? 2 : 0) | (p.round_out ? 4 : 0);
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -541,8 +585,15 @@ int launch_tc_conv(const TcConvParams& p, cudaStream_t stream) {
   const int bn = tc_pick_bn(p.N, p.split);
   const int s = p.stride;
   const int ktot = p.taps * p.C0 + (p.a1 ? p.C1 : 0);
+  ECB_REQUIRE(p.taps % s == 0, "tc_conv: kernel size %d must be a multiple of the stride %d", p.taps, s);
   CUtensorMap maps[4];
   TcArgs a;
+  // the taps of the conv are row shifts of one [a_rows x 32] tile per 32-channel block of the (folded) input row
+  a.shifts = p.taps / s;
+  a.n_cb0 = s * p.C0 / BK;
+  a.n_cb1 = p.a1 ? p.C1 / BK : 0;
+  a.a_rows = a.shifts > 1 ? A_ROWS : BM;
+  ECB_REQUIRE(a.shifts - 1 <= A_ROWS - BM, "tc_conv: %d taps exceed the %d-row tile halo", a.shifts, A_ROWS - BM);
   {
     // folded view of source 0: rows of s*C0 floats; the fold is aligned so that output row 0's window starts a folded
     // row: first mapped sample b0 = smallest sample >= a0_first congruent to -pad_left (mod s)
@@ -552,16 +603,15 @@ int launch_tc_conv(const TcConvParams& p, cudaStream_t stream) {
     const long long rows = (p.a0_first + p.a0_rows - b0) / s;
     ECB_REQUIRE(rows > 0, "tc_conv: empty source");
     a.row_base0 = (int)((-(long long)p.pad_left - b0) / s);   // exact; may be negative (TMA zero fill)
-    a.rowlen0 = s * p.C0;
     const cuuint64_t dims[3] = {(cuuint64_t)s * p.C0, (cuuint64_t)rows, (cuuint64_t)p.n_items};
     const cuuint64_t strides[2] = {(cuuint64_t)s * p.C0 * 4, (cuuint64_t)p.a0_item_stride * 4};
-    const cuuint32_t box[3] = {BK, BM, 1};
+    const cuuint32_t box[3] = {BK, (cuuint32_t)a.a_rows, 1};
     if (make_tensor_map(&maps[0], p.a0 + d * p.C0, 3, dims, strides, box)) return 1;
   }
   if (p.a1) {
     const cuuint64_t dims[3] = {(cuuint64_t)p.C1, (cuuint64_t)p.a1_rows, (cuuint64_t)p.n_items};
     const cuuint64_t strides[2] = {(cuuint64_t)p.C1 * 4, (cuuint64_t)p.a1_item_stride * 4};
-    const cuuint32_t box[3] = {BK, BM, 1};
+    const cuuint32_t box[3] = {BK, (cuuint32_t)a.a_rows, 1};
     if (make_tensor_map(&maps[1], p.a1, 3, dims, strides, box)) return 1;
   } else {
     maps[1] = maps[0];
@@ -585,14 +635,12 @@ int launch_tc_conv(const TcConvParams& p, cudaStream_t stream) {
   const long long total = (long long)a.tiles_m * a.tiles_n * p.n_items;
   ECB_REQUIRE(total < (1LL << 31), "tc_conv: too many tiles");
   a.total_tiles = (int)total;
-  a.nch0 = p.taps * p.C0 / BK;
-  a.nch1 = p.a1 ? p.C1 / BK : 0;
   a.row_base1 = 0;
   a.round_out = p.round_out;
   a.halo = p.halo;
   a.stats = p.stats;
   {
-    const int nch = a.nch0 + a.nch1;
+    const int nch = a.n_cb0 * a.shifts + a.n_cb1;
     a.group = (p.split == 3 && nch > 6) ? 4 : nch;   // <= 24 truncating accumulation steps per group
   }
   const int grid = (int)(total < sm_count() ? total : sm_count());

@@ -100,6 +100,20 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
 
+// One lane of a converged warp (elect.sync): the idiom the compiler turns into uniform-datapath code for the
+// single-thread tcgen05 / TMA instructions (a plain `lane == 0` branch makes it wrap each of them in a vote loop).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // kind::tf32 instruction descriptor (cute::UMMA::InstrDescriptor): D fp32 (bits [4,6) = 1), A/B TF32 ([7,10) = [10,13) = 2),
 // both K-major, N >> 3 in [17,23), M >> 4 in [24,29).
 __host__ __device__ constexpr uint32_t umma_idesc_tf32(int m, int n) {
