@@ -47,6 +47,7 @@ SIGNATURES = {
     "ecb_codec_destroy": (None, [C.c_void_p]),
     "ecb_codec_load_tensor": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "ecb_codec_finalize": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ecb_codec_set_decoder_precision": (C.c_int, [C.c_void_p, C.c_int32]),
     "ecb_encoder_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int64, C.c_int64]),
     "ecb_encoder_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                       C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,

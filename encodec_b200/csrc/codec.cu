@@ -116,7 +116,8 @@ struct ecb_codec {
   float* cb_hi = nullptr;      // TF32 split of the codebooks for the tensor-core quantiser
   float* cb_lo = nullptr;
   int hop = 1;
-  bool tc_ready = false;       // tensor-core weights prepared (weight-norm / plain models)
+  bool tc_ready = false;       // tensor-core weights prepared
+  int dec_split = 0;           // decoder operand scheme: 0 = default (env ECB_DEC_SPLIT or 3), 3 = split operands, 1 = one TF32 pass
 };
 
 namespace {
@@ -663,13 +664,14 @@ bool tc_disabled_by_env() {
   return off == 1;
 }
 
-int tc_split(bool decoder) {
+int tc_split(const ecb_codec* c, bool decoder) {
   static int dec = -1;
   if (dec < 0) {
     const char* e = getenv("ECB_DEC_SPLIT");   // 1: single-pass TF32 in the decoder (default 3: fp32-accurate everywhere)
     dec = (e && e[0] == '1') ? 1 : 3;
   }
-  return decoder ? dec : 3;
+  if (!decoder) return 3;   // the encoder feeds the quantiser: always fp32-accurate
+  return c->dec_split ? c->dec_split : dec;
 }
 
 // frames at the top of the stack needed for the tensor-core path: every halo-padded tensor must be longer than its halo
@@ -774,7 +776,7 @@ int encoder_forward_tc(Ctx& x, const float* xin, int64_t n_seg, int64_t length, 
                        int64_t x_chan_stride, const float* scale, float* emb_out, float* emb_frames_out) {
   ecb_codec* c = x.c;
   const ecb_spec& s = c->spec;
-  const int split = tc_split(false);
+  const int split = tc_split(c, false);
   float *A = x.buf[0], *B = x.buf[1], *Cb = x.buf[2], *D = x.buf[3];
   long long T = length;
   int ch = s.n_filters;
@@ -838,7 +840,7 @@ int encoder_forward_tc(Ctx& x, const float* xin, int64_t n_seg, int64_t length, 
 int decoder_forward_tc(Ctx& x, const float* z_frames, int64_t n_frames, const float* scale, float* out) {
   ecb_codec* c = x.c;
   const ecb_spec& s = c->spec;
-  const int split = tc_split(true);
+  const int split = tc_split(c, true);
   float *A = x.buf[0], *B = x.buf[1], *Cb = x.buf[2], *D = x.buf[3];
   long long T = n_frames;
   Act Q = act_of(A, s.dimension, T, ACT_HALO);
@@ -1180,6 +1182,12 @@ int ecb_codec_load_tensor(ecb_codec* c, const char* key, const float* data, int6
   ECB_CUDA(cudaMemcpyAsync(b.p, data, sizeof(float) * (size_t)numel, cudaMemcpyDeviceToDevice,
                            reinterpret_cast<cudaStream_t>(stream)));
   c->finalized = false;
+  return 0;
+}
+
+int ecb_codec_set_decoder_precision(ecb_codec* c, int32_t tf32_single_pass) {
+  ECB_REQUIRE(c, "null codec");
+  c->dec_split = tf32_single_pass ? 1 : 3;
   return 0;
 }
 

@@ -290,10 +290,15 @@ class SEANetDecoder(_NativeStack):
         self.model = nn.ModuleDict(model)
         self._init_native()
 
+    #: ``True`` runs the decoder convs as one TF32 pass instead of fp32-accurate split operands (weight-norm models):
+    #: ~1.6x faster decoder convs, audio within ~1e-4 max-abs of the fp32 result (see ecb_codec_set_decoder_precision).
+    tf32 = False
+
     @torch.no_grad()
     def decode_items(self, z: tp.Optional[torch.Tensor], z_frames: tp.Optional[torch.Tensor], n_items: int,
                      n_frames: int, scale: tp.Optional[torch.Tensor], out: tp.Optional[torch.Tensor] = None):
         codec = self.native()
+        nat.check(nat.lib.ecb_codec_set_decoder_precision(codec.handle, 1 if self.tf32 else 0))
         src = z if z is not None else z_frames
         dev = src.device
         if out is None:

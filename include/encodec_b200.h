@@ -70,6 +70,12 @@ int ecb_codec_load_tensor(ecb_codec* codec, const char* key, const float* data, 
  * Fails if a tensor the spec requires was never loaded. */
 int ecb_codec_finalize(ecb_codec* codec, void* stream);
 
+/* Decoder operand scheme of the tensor-core convolutions (weight-norm models). 0 (default): split-operand TF32,
+ * fp32-accurate, like the encoder. 1: one TF32 pass with operands rounded to TF32 by their producers -- about 1.6x
+ * faster decoder convs, decoded audio within 1e-4 max-abs / 2.3e-5 RMS of the fp32 result on the golden cases
+ * (the north_star bar is 1e-3 / 1e-4). The encoder and the quantiser are always fp32-accurate. */
+int ecb_codec_set_decoder_precision(ecb_codec* codec, int32_t tf32_single_pass);
+
 /* ---- SEANetEncoder.forward (modules/seanet.py:145-146; SConv1d conv.py:202-221; SLSTM lstm.py:22-28)
  * x: `n_items` items; item i starts at x + (i / n_seg) * x_batch_stride + (i % n_seg) * x_seg_stride,
  * channel c at + c * x_chan_stride, `length` samples each (this is how the 48 kHz model's overlapping

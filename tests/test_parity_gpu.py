@@ -177,6 +177,58 @@ def test_rvq_c_abi_matches_core_vq_golden():
     np.testing.assert_array_equal(dec.cpu().numpy()[:256], case["decoded_head"].T)
 
 
+def test_rvq_tensor_core_kernel_matches_core_vq_golden():
+    """The tcgen05 quantiser (the path ResidualVectorQuantizer takes: ecb_codec_rvq_forward) against
+    core_vq.ResidualVectorQuantization.encode on the config-4-shaped golden case (8192 frames x 32 layers)."""
+    import encodec_b200 as eb
+    case = gc.load_rvq_case()
+    n, d = case["frames"].shape
+    n_q, bins = case["n_q"], case["bins"]
+    q = eb.ResidualVectorQuantizer(dimension=d, n_q=n_q, bins=bins, codebook_dim=d, share_codebook=False)
+    for i, layer in enumerate(q.vq.layers):
+        layer._codebook.embed.copy_(torch.from_numpy(case["codebooks"][i]))
+        layer._codebook.inited.fill_(1)
+    q = q.cuda()
+    x = torch.from_numpy(np.ascontiguousarray(case["frames"].T.reshape(1, d, n))).cuda()
+    res = q(x, 75, None)
+    got = res.codes.cpu().numpy().reshape(n_q, n)
+    score = orc.score_codes(case["frames"], case["codebooks"], case["codes"], got)
+    print(f"\n[rvq tensor-core] code score vs core_vq: {score}")
+    assert score["hard"] == 0, score
+    assert score["mismatched"] <= 8, score
+    # quantized == decode(codes) bit for bit (both sum the same fp32 codebook rows in layer order)
+    assert torch.equal(q.decode(res.codes), res.quantized)
+    same = (got == case["codes"]).all(axis=0)
+    head = np.nonzero(same[:256])[0]
+    np.testing.assert_array_equal(res.quantized.cpu().numpy()[0].T[head], case["quantized_head"].T[head])
+    # ragged frame count (partial last tile of 128 frames) gives the same codes for the frames it has
+    res2 = q(x[:, :, :1000], 75, None)
+    assert torch.equal(res2.codes, res.codes[:, :, :1000])
+
+
+def test_decoder_tf32_mode_within_audio_tolerance():
+    """Opt-in single-pass TF32 decoder (SEANetDecoder.tf32 = True): decoded audio must stay inside the north_star bar."""
+    for name in gc.MODEL_CASES:
+        case = gc.load_model_case(name)
+        spec = case["spec"]
+        if spec.norm != "weight_norm":
+            continue
+        m = ug.build_model(spec, case["sd"], case["bandwidth"], case["distinct"])
+        z = torch.from_numpy(np.ascontiguousarray(case["quantized"])).cuda()
+        ref = m.decoder(z).cpu().numpy()
+        m.decoder.tf32 = True
+        got = m.decoder(z).cpu().numpy()
+        m.decoder.tf32 = False
+        again = m.decoder(z).cpu().numpy()
+        np.testing.assert_array_equal(again, ref)
+        d1 = np.abs(got - ref)
+        d2 = np.abs(got[:, :, :case["audio"].shape[-1]] - case["audio"])
+        print(f"[{name}] tf32 decoder vs fp32-accurate decoder: max-abs {d1.max():.3e} rms {np.sqrt((d1 ** 2).mean()):.3e}; "
+              f"vs reference: max-abs {d2.max():.3e} rms {np.sqrt((d2 ** 2).mean()):.3e}")
+        assert d1.max() > 0, "the switch had no effect"
+        assert d2.max() < AUDIO_MAX_ABS and np.sqrt((d2 ** 2).mean()) < AUDIO_RMS
+
+
 def test_quantizer_module_api():
     import encodec_b200 as eb
     case = gc.load_rvq_case()
