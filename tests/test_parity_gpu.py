@@ -177,6 +177,32 @@ def test_rvq_c_abi_matches_core_vq_golden():
     np.testing.assert_array_equal(dec.cpu().numpy()[:256], case["decoded_head"].T)
 
 
+def test_config2_full_size_properties():
+    """BASELINE config 2 at full size (24 kHz, 24 kbps, 64 x 10 s): too big for the CPU oracle, so it is checked through
+    size-independent properties -- batch invariance (any split of the batch gives bit-identical codes and audio, although
+    the persistent kernels then schedule different tiles on different SMs), run-to-run determinism, and the gather-sum
+    identity quantized == decode(codes)."""
+    from encodec_b200 import synth
+    spec = synth.spec_24khz()
+    sd = synth.make_state_dict(spec, seed=5)
+    m = ug.build_model(spec, sd, 24.0, True)
+    g = torch.Generator(device="cuda").manual_seed(99)
+    x = (0.3 * torch.randn(64, 1, 240000, generator=g, device="cuda")).clamp_(-1, 1)
+    with torch.no_grad():
+        audio, codes, _, _ = m(x)
+        audio2, codes2, _, _ = m(x)
+        assert torch.equal(codes, codes2) and torch.equal(audio, audio2)
+        assert codes.shape == (64, 32, 750) and audio.shape == x.shape and codes.dtype == torch.int64
+        assert int(codes.min()) >= 0 and int(codes.max()) < spec.bins and torch.isfinite(audio).all()
+        for lo, hi in ((0, 24), (24, 64), (63, 64)):
+            a, c, _, _ = m(x[lo:hi])
+            assert torch.equal(c, codes[lo:hi]) and torch.equal(a, audio[lo:hi]), (lo, hi)
+        frames = m.encode(x)
+        q = frames[0]["quantized"]
+        assert torch.equal(m.quantizer.decode(frames[0]["codes"].transpose(0, 1).contiguous()), q)
+        assert torch.equal(m.decode(frames), audio)
+
+
 def test_rvq_tensor_core_kernel_matches_core_vq_golden():
     """The tcgen05 quantiser (the path ResidualVectorQuantizer takes: ecb_codec_rvq_forward) against
     core_vq.ResidualVectorQuantization.encode on the config-4-shaped golden case (8192 frames x 32 layers)."""
