@@ -8,9 +8,10 @@ collective, and the only exchange is an NCCL gather of codes and audio to rank 0
 timed region. Rank 0 prints ONE JSON line (see the task contract): `value` is measured with inputs
 resident in HBM, `e2e` through the public API from pinned host buffers with H2D/D2H copies inside the
 timed region, `roofline` describes the dominant kernel class (timed with CUDA events on its stream by the
-library's own profiler hooks), `cpu_baseline` is the numpy oracle port timed on the host cores.
-`--impl reference` times that CPU port alone (the reference is pure Python/PyTorch and is not present on
-the GPU box; oracle/encodec_oracle.py restates it and is pinned to its outputs by tests/golden).
+library's own profiler hooks), `cpu_baseline` is the ATen port of the reference timed on the host cores.
+`--impl reference` times the CPU port alone (the reference is pure Python/PyTorch and is not present on the GPU box;
+oracle/torch_port.py restates its forward on the same ATen CPU kernels and is pinned, through the numpy oracle, to the
+reference's own outputs in tests/golden).
 """
 from __future__ import annotations
 
@@ -94,16 +95,23 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
+_PORT_PARAMS = {}
+
+
 def cpu_port_throughput(spec, sd, bandwidth, clips, seconds, repeats=1):
-    """Oracle port (numpy, all BLAS threads) on a bounded sample; returns (audio-s/s, seconds spent)."""
+    """The reference's forward restated on the ATen CPU kernels the reference itself uses (oracle/torch_port.py: mkldnn
+    conv / RNN, MKL sgemm, all host threads), on a bounded sample; returns (audio-s/s, seconds spent)."""
+    import torch
     from encodec_b200 import synth
-    from oracle import encodec_oracle as orc
+    from oracle import torch_port as port
+    torch.set_num_threads(os.cpu_count() or 1)
     length = int(seconds * spec.sample_rate)
     x = synth.make_audio(999, clips, spec.channels, length)
+    params = _PORT_PARAMS.setdefault(id(sd), port.TorchParams(sd))   # weight-norm folded once, outside the timed call
     best = None
     for _ in range(repeats):
         t0 = time.perf_counter()
-        orc.forward(x, sd, spec, bandwidth, np.float32)
+        port.forward(x, sd, spec, bandwidth, params)
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
     return clips * seconds / best, best
@@ -116,16 +124,18 @@ def run_reference_arm(args, wl, rank, world):
     from encodec_b200 import synth
     spec = make_spec(wl["model"])
     sd = synth.make_state_dict(spec, seed=0)
-    clips, seconds = (1, min(wl["seconds"], 10.0)) if wl["model"] == "24k" else (1, min(wl["seconds"], 3.0))
+    clips, seconds = (8, min(wl["seconds"], 10.0)) if wl["model"] == "24k" else (2, min(wl["seconds"], 10.0))
+    clips = min(clips, wl["batch"])
     for _ in range(args.warmup):
-        cpu_port_throughput(spec, sd, wl["bandwidth"], clips, min(seconds, 1.0))
+        cpu_port_throughput(spec, sd, wl["bandwidth"], 1, min(seconds, 1.0))
     t0 = time.perf_counter()
     for _ in range(args.steps):
         cpu_port_throughput(spec, sd, wl["bandwidth"], clips, seconds)
     dt = (time.perf_counter() - t0) / args.steps
     value = clips * seconds / dt
     cores = os.cpu_count() or 1
-    sample = f"{clips} clip x {seconds:g} s of the {args.workload} workload per step (numpy oracle port, BLAS threads)"
+    sample = (f"{clips} clip(s) x {seconds:g} s of the {args.workload} workload per step (oracle/torch_port.py: the reference's "
+              f"forward on the ATen CPU kernels it uses, {cores} threads)")
     line = {
         "impl": "reference", "metric": "audio-sec/sec encode+decode", "value": value, "unit": "audio-s/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
@@ -361,12 +371,14 @@ def main():
                 roofline = roof(top_name)
         cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline:
-            clips, seconds = (2, min(wl["seconds"], 10.0)) if wl["model"] == "24k" else (1, min(wl["seconds"], 3.0))
+            clips, seconds = (8, min(wl["seconds"], 10.0)) if wl["model"] == "24k" else (2, min(wl["seconds"], 10.0))
+            clips = min(clips, wl["batch"])
             cpu_port_throughput(spec, sd, wl["bandwidth"], 1, 1.0)  # warm-up
             v, spent = cpu_port_throughput(spec, sd, wl["bandwidth"], clips, seconds)
             cpu_baseline = {"value": v, "unit": "audio-s/s", "cores": os.cpu_count() or 1, "kind": "port",
                             "sample": f"{clips} clip(s) x {seconds:g} s of the same workload, {spent:.1f} s of CPU work "
-                                      "(numpy oracle port, BLAS threads)"}
+                                      "(oracle/torch_port.py: the reference's forward restated on the ATen CPU kernels the "
+                                      "reference itself calls -- mkldnn conv / RNN, MKL sgemm -- all host threads)"}
         line = {
             "metric": "audio-sec/sec encode+decode", "value": value, "unit": "audio-s/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
