@@ -68,6 +68,10 @@ SIGNATURES = {
                                        C.c_void_p, C.c_void_p]),
     "ecb_overlap_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                   C.c_void_p, C.c_int64, C.c_void_p]),
+    "ecb_packed_bytes": (C.c_int64, [C.c_int64, C.c_int64, C.c_int32]),
+    "ecb_pack_codes": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
+    "ecb_unpack_codes": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_int64,
+                                   C.c_void_p]),
     "ecb_transpose_bct_to_btc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p]),
     "ecb_transpose_btc_to_bct": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p]),
 }

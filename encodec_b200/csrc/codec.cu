@@ -1544,6 +1544,24 @@ int ecb_debug_tc_conv(const float* a0, int64_t a0_item_stride, int32_t C0, int64
   return rc;
 }
 
+int64_t ecb_packed_bytes(int64_t n_codebooks, int64_t n_frames, int32_t bits) {
+  return (n_codebooks * n_frames * bits + 7) / 8;
+}
+
+int ecb_pack_codes(const int64_t* codes, int64_t k_stride, int64_t t_stride, int64_t n_codebooks, int64_t n_frames,
+                   int32_t bits, uint8_t* out, void* stream) {
+  ECB_REQUIRE(codes && out, "pack_codes: null argument");
+  return launch_pack_codes(reinterpret_cast<const long long*>(codes), k_stride, t_stride, (int)n_codebooks, n_frames, bits,
+                           out, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ecb_unpack_codes(const uint8_t* in, int64_t n_bytes, int64_t n_codebooks, int64_t n_frames, int32_t bits, int64_t* codes,
+                     int64_t k_stride, int64_t t_stride, void* stream) {
+  ECB_REQUIRE(codes && in, "unpack_codes: null argument");
+  return launch_unpack_codes(in, n_bytes, (int)n_codebooks, n_frames, bits, reinterpret_cast<long long*>(codes), k_stride,
+                             t_stride, reinterpret_cast<cudaStream_t>(stream));
+}
+
 int ecb_transpose_bct_to_btc(const float* in, float* out, int64_t batch, int64_t chans, int64_t len, void* stream) {
   ECB_REQUIRE(in && out, "transpose: null argument");
   return launch_transpose(in, out, batch, (int)chans, (int)len, reinterpret_cast<cudaStream_t>(stream));

@@ -236,6 +236,14 @@ int launch_overlap_add(const float* frames, const int* seg_lens, long long batch
                        int seg_len, int stride, float* out, long long total, cudaStream_t s);
 
 // ------------------------------------------------------------------------------------------------
+// bitpack.cu: .ecdc code stream without entropy coding (binary.py:55-122)
+// ------------------------------------------------------------------------------------------------
+int launch_pack_codes(const long long* codes, long long k_stride, long long t_stride, int K, long long T, int bits,
+                      unsigned char* out, cudaStream_t s);
+int launch_unpack_codes(const unsigned char* in, long long n_bytes, int K, long long T, int bits, long long* codes,
+                        long long k_stride, long long t_stride, cudaStream_t s);
+
+// ------------------------------------------------------------------------------------------------
 // lstm.cu
 // ------------------------------------------------------------------------------------------------
 // Pre-gates pre[b][t][4H] (input projection + both biases already added) -> h sequence. w_hh is the reference's

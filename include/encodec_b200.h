@@ -132,6 +132,17 @@ int ecb_codec_rvq_decode(ecb_codec* codec, const int64_t* codes, int64_t batch, 
 int ecb_overlap_add(const float* frames, const int32_t* seg_lens, int64_t batch, int64_t channels, int64_t n_seg,
                     int64_t seg_len, int64_t stride, float* out, int64_t total, void* stream);
 
+/* ---- .ecdc code stream without entropy coding: binary.BitPacker / BitUnpacker (binary.py:55-122) as used by
+ * compress_to_file / decompress_from_file with use_lm=False (compress.py:66-89,130-155) ---------------------------
+ * One frame: values are pushed time-major (for t: for k: codes[k][t]), `bits` each, least-significant bit first; the last
+ * partial byte is zero-padded. codes element (k, t) is at codes[k * k_stride + t * t_stride] (int64, DEVICE). out / in are
+ * DEVICE byte buffers of ecb_packed_bytes(...) bytes. Byte-exact with the reference's BitPacker. 1 <= bits <= 24. */
+int64_t ecb_packed_bytes(int64_t n_codebooks, int64_t n_frames, int32_t bits);
+int ecb_pack_codes(const int64_t* codes, int64_t k_stride, int64_t t_stride, int64_t n_codebooks, int64_t n_frames,
+                   int32_t bits, uint8_t* out, void* stream);
+int ecb_unpack_codes(const uint8_t* in, int64_t n_bytes, int64_t n_codebooks, int64_t n_frames, int32_t bits, int64_t* codes,
+                     int64_t k_stride, int64_t t_stride, void* stream);
+
 /* ---- layout helpers ([B, C, T] <-> [B, T, C]) -------------------------------------------------------- */
 int ecb_transpose_bct_to_btc(const float* in, float* out, int64_t batch, int64_t chans, int64_t len, void* stream);
 int ecb_transpose_btc_to_bct(const float* in, float* out, int64_t batch, int64_t len, int64_t chans, void* stream);
