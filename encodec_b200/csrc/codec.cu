@@ -33,7 +33,7 @@ struct ProfRec {
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;
 static const char* kProfNames[PROF_NCAT] = {"conv_gemm", "conv_in", "conv_out", "lstm_recurrent", "rvq_encode",
-                                            "gn_apply", "misc", "tc_conv_narrow", "tc_conv_wide"};
+                                            "gn_apply", "misc", "tc_conv_narrow", "tc_conv_wide", "tc_res"};
 bool prof_enabled() { return g_prof_on; }
 void prof_begin(int cat, cudaStream_t st, double flops, double bytes) {
   ProfRec r;
@@ -740,9 +740,44 @@ int tc_run(Ctx& x, const float* hi, const float* lo, const float* bias, int K, i
 
 // SEANetResnetBlock (modules/seanet.py:37-64) on the tensor cores: X (raw) and E = ELU(X) in, Y = ELU(shortcut(X) +
 // block(X)) out (halo-padded). H is scratch for the hidden activation.
+bool fused_res32_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("ECB_FUSED_RES");   // diagnostic switch: ECB_FUSED_RES=0 keeps the two-kernel residual block
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
+
+// true when the residual block of this width runs as ONE kernel that reads only X (no ELU(X) tensor needed)
+bool res_is_fused(const ecb_codec* c, int dim, int split) {
+  return fused_res32_enabled() && !c->spec.group_norm && dim == 32 && split == 3 && c->spec.residual_kernel_size == 3 &&
+         c->spec.compress == 2;
+}
+
 int tc_res(Ctx& x, const ResW& r, const Act& X, const Act& E, float* hbuf, Act& Y, int split) {
   const ecb_spec& s = x.c->spec;
   const int dim = r.sc.c_out;
+  if (res_is_fused(x.c, dim, split)) {
+    TcResParams p;
+    p.x = X.base;
+    p.x_item_stride = X.stride();
+    p.x_first = -X.halo;
+    p.x_rows = X.T + 2LL * X.halo;
+    p.pad_left = pad_left_of(s, r.b1.k, 1);
+    p.w1_hi = r.b1.t_hi;
+    p.w1_lo = r.b1.t_lo;
+    p.wc_hi = r.c_hi;
+    p.wc_lo = r.c_lo;
+    p.b1 = r.b1.t_bias;
+    p.bcat = r.bias_cat;
+    p.out = Y.row0();
+    p.out_item_stride = Y.stride();
+    p.M = X.T;
+    p.n_items = x.n_items;
+    p.halo = Y.halo;
+    return launch_tc_res32(p, x.st);
+  }
   Act H = act_of(hbuf, r.hid_pad, X.T, 0);
   if (tc_run(x, r.b1.t_hi, r.b1.t_lo, r.b1.t_bias, r.b1.t_K, r.b1.t_N, E, dim, r.b1.k, 1, pad_left_of(s, r.b1.k, 1), false,
              nullptr, nullptr, H.row0(), H.stride(), X.T, 0, split, split == 1))
@@ -797,7 +832,7 @@ int encoder_forward_tc(Ctx& x, const float* xin, int64_t n_seg, int64_t length, 
   ci.w = c->enc_in.w;
   ci.bias = c->enc_in.bias;
   ci.out = X.row0();
-  ci.out_elu = E.row0();
+  ci.out_elu = res_is_fused(c, ch, split) ? nullptr : E.row0();   // the fused block reads only X (through its halo)
   ci.out_item_stride = X.stride();
   ci.halo = ACT_HALO;
   ci.stats = nullptr;
@@ -872,10 +907,12 @@ int decoder_forward_tc(Ctx& x, const float* z_frames, int64_t n_frames, const fl
     // that halo_fill rewrites below), the right trim is the row count
     const long long M = trim_left > 0 ? T + 1 : T;
     const long long shift = (long long)trim_left * uw.c_out;
+    const bool fused = res_is_fused(c, uw.c_out, split);   // then the block reads only X2 (through its halo)
     if (tc_run(x, uw.t_hi, uw.t_lo, uw.t_bias, uw.t_K, uw.t_N, cur, ch, 2, 1, 1, true, nullptr, X2.row0() - shift,
-               E2.row0() - shift, X2.stride(), M, 0, split, split == 1))
+               fused ? nullptr : E2.row0() - shift, X2.stride(), M, 0, split, split == 1))
       return 1;
-    if (launch_halo_fill(nullptr, E2.row0(), E2.stride(), T2, uw.c_out, x.n_items, ACT_HALO, 0, x.st)) return 1;
+    const Act& padded = fused ? X2 : E2;
+    if (launch_halo_fill(nullptr, padded.row0(), padded.stride(), T2, uw.c_out, x.n_items, ACT_HALO, 0, x.st)) return 1;
     T = T2;
     ch = uw.c_out;
     if (tap_act(x.st, 102 + 2 * i, X2, x.n_items)) return 1;

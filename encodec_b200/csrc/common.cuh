@@ -23,7 +23,7 @@ extern std::atomic<long long> g_launches;
 
 // Optional per-kernel-class timing (bench.py's roofline leg): CUDA events recorded on the launching stream
 // around every launch while enabled; off by default (no events, no overhead).
-enum ProfCat { PROF_CONV_GEMM = 0, PROF_CONV_IN, PROF_CONV_OUT, PROF_LSTM_REC, PROF_RVQ, PROF_GN_APPLY, PROF_MISC, PROF_TC_CONV_NARROW, PROF_TC_CONV_WIDE, PROF_NCAT };
+enum ProfCat { PROF_CONV_GEMM = 0, PROF_CONV_IN, PROF_CONV_OUT, PROF_LSTM_REC, PROF_RVQ, PROF_GN_APPLY, PROF_MISC, PROF_TC_CONV_NARROW, PROF_TC_CONV_WIDE, PROF_TC_RES, PROF_NCAT };
 bool prof_enabled();
 void prof_begin(int cat, cudaStream_t st, double flops, double bytes);
 void prof_end(cudaStream_t st);
@@ -75,6 +75,37 @@ __device__ __forceinline__ float elu1(float v) {
   const float s = __int_as_float((__float_as_int(t) << 23) + 0x3f800000);  // 2^n
   const float e = fmaf(q, s, s - 1.f);
   return v > 0.f ? v : e;
+}
+
+// ELU over N independent values, stage by stage across all of them: the ~14 dependent operations of one elu1 then
+// overlap N-fold instead of waiting on each other (the epilogues are otherwise bound by that dependency chain).
+template <int N>
+__device__ __forceinline__ void elu_vec(float (&v)[N]) {
+  float t[N], r[N], q[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) t[i] = fmaf(fmaxf(v[i], -20.f), 1.4426950408889634f, 12582912.f);
+#pragma unroll
+  for (int i = 0; i < N; ++i) r[i] = fmaf(t[i] - 12582912.f, -0.693145751953125f, fmaxf(v[i], -20.f));
+#pragma unroll
+  for (int i = 0; i < N; ++i) r[i] = fmaf(t[i] - 12582912.f, -1.428606765330187e-06f, r[i]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) q[i] = fmaf(1.9841270e-4f, r[i], 1.3888889e-3f);
+#pragma unroll
+  for (int i = 0; i < N; ++i) q[i] = fmaf(q[i], r[i], 8.3333333e-3f);
+#pragma unroll
+  for (int i = 0; i < N; ++i) q[i] = fmaf(q[i], r[i], 4.1666667e-2f);
+#pragma unroll
+  for (int i = 0; i < N; ++i) q[i] = fmaf(q[i], r[i], 1.6666667e-1f);
+#pragma unroll
+  for (int i = 0; i < N; ++i) q[i] = fmaf(q[i], r[i], 0.5f);
+#pragma unroll
+  for (int i = 0; i < N; ++i) q[i] = fmaf(q[i] * r[i], r[i], r[i]);
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const float s = __int_as_float((__float_as_int(t[i]) << 23) + 0x3f800000);
+    const float e = fmaf(q[i], s, s - 1.f);
+    v[i] = v[i] > 0.f ? v[i] : e;
+  }
 }
 
 // index of a reflect-padded signal of length T (valid while the pad is < T); conv.py:80-97
@@ -171,6 +202,26 @@ int tc_stat_slots(const TcConvParams& p);   // partial-statistics slots per item
 int launch_tc_conv(const TcConvParams& p, cudaStream_t stream);
 int launch_split_weights(const float* w, float* hi, float* lo, int K, int N, int K_pad, int N_pad, cudaStream_t s);
 int tc_pick_bn(int N, int split);
+
+// Fused SEANetResnetBlock at 32 channels (tc_res.cu): Y = ELU(shortcut(X) + block3(ELU(block1(ELU(X))))), X read once.
+struct TcResParams {
+  const float* x;             // (item 0, sample x_first, channel 0) of the halo-padded raw input [T][32]
+  long long x_item_stride;
+  long long x_first, x_rows;  // first addressable sample (<= -pad_left) and number of addressable samples
+  int pad_left;               // left padding of the k3 conv: 2 causal, 1 otherwise
+  const float* w1_hi;         // block.1 weights [32 (hidden, zero-padded)][96] K-major split (launch_split_weights)
+  const float* w1_lo;
+  const float* wc_hi;         // [block.3 ; shortcut] weights [32][32 + 32] K-major split
+  const float* wc_lo;
+  const float* b1;            // [32] hidden bias, zero-padded
+  const float* bcat;          // [32] b3 + bs
+  float* out;                 // (item 0, row 0) of Y [M][32]
+  long long out_item_stride;
+  long long M;
+  int n_items;
+  int halo;                   // reflected rows to write around Y
+};
+int launch_tc_res32(const TcResParams& p, cudaStream_t stream);
 
 // ------------------------------------------------------------------------------------------------
 // Edge convolutions (conv_edge.cu): audio [B,C,T] channels-first <-> 32-channel channels-last

@@ -86,27 +86,45 @@ template <bool RAW, bool ELU, bool ROUND, bool STATS>
 __device__ __forceinline__ void copy_out_rows(const uint8_t* slot, int lane, float* praw, float* pelu, long long row_step,
                                               int rows_left, float& st_sum, float& st_sq) {
   const int c16 = lane & 3;
-  int rr = lane >> 2;
-  praw += (long long)rr * (row_step >> 3);
-  pelu += (long long)rr * (row_step >> 3);
-#pragma unroll 2
-  for (int i = 0; i < 4; ++i, rr += 8) {
-    if (rr >= rows_left) break;
-    const float4 v = *reinterpret_cast<const float4*>(slot + rr * 64 + ((c16 ^ ((rr >> 1) & 3)) << 4));
-    if (STATS) {
-      st_sum += (v.x + v.y) + (v.z + v.w);
-      st_sq += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+  const int rr0 = lane >> 2;
+  praw += (long long)rr0 * (row_step >> 3);
+  pelu += (long long)rr0 * (row_step >> 3);
+  float4 v[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int rr = rr0 + 8 * i;
+    v[i] = *reinterpret_cast<const float4*>(slot + rr * 64 + ((c16 ^ ((rr >> 1) & 3)) << 4));
+  }
+  if (STATS) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (rr0 + 8 * i < rows_left) {
+        st_sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        st_sq += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+      }
+  }
+  if (RAW) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (rr0 + 8 * i < rows_left)
+        *reinterpret_cast<float4*>(praw + i * row_step) =
+            ROUND ? make_float4(rn_tf32(v[i].x), rn_tf32(v[i].y), rn_tf32(v[i].z), rn_tf32(v[i].w)) : v[i];
+  }
+  if (ELU) {
+    // the 16 ELUs of this lane run interleaved (elu_vec): one elu1 is a chain of ~14 dependent operations
+    float e[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      e[i * 4 + 0] = v[i].x; e[i * 4 + 1] = v[i].y; e[i * 4 + 2] = v[i].z; e[i * 4 + 3] = v[i].w;
     }
-    if (RAW) {
-      *reinterpret_cast<float4*>(praw) = ROUND ? make_float4(rn_tf32(v.x), rn_tf32(v.y), rn_tf32(v.z), rn_tf32(v.w)) : v;
-      praw += row_step;
-    }
-    if (ELU) {
-      float4 w = make_float4(elu1(v.x), elu1(v.y), elu1(v.z), elu1(v.w));
-      if (ROUND) w = make_float4(rn_tf32(w.x), rn_tf32(w.y), rn_tf32(w.z), rn_tf32(w.w));
-      *reinterpret_cast<float4*>(pelu) = w;
-      pelu += row_step;
-    }
+    elu_vec<16>(e);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (rr0 + 8 * i < rows_left) {
+        float4 w = make_float4(e[i * 4 + 0], e[i * 4 + 1], e[i * 4 + 2], e[i * 4 + 3]);
+        if (ROUND) w = make_float4(rn_tf32(w.x), rn_tf32(w.y), rn_tf32(w.z), rn_tf32(w.w));
+        *reinterpret_cast<float4*>(pelu + i * row_step) = w;
+      }
   }
 }
 
