@@ -146,9 +146,6 @@ tc_res_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
     mbar_wait(w_full, 0);
     auto gemm1 = [&](int i) {
       const int s = i & 1;
-      const uint32_t ph = ((uint32_t)i >> 1) & 1u;
-      mbar_wait(p_ready(s), ph);
-      mbar_wait(a1_empty(s), ph ^ 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (elect_one()) {
         const uint32_t d = tmem_base + (uint32_t)(s * 32);
@@ -169,9 +166,6 @@ tc_res_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
     auto gemm2 = [&](int i) {
       const int s = i & 1;
       const int r = i % NRAW;
-      const uint32_t ph = ((uint32_t)i >> 1) & 1u;
-      mbar_wait(h_full, (uint32_t)i & 1u);
-      mbar_wait(a2_empty(s), ph ^ 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (elect_one()) {
         const uint32_t d = tmem_base + (uint32_t)(64 + s * 64);
@@ -195,10 +189,20 @@ tc_res_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
       }
       __syncwarp();
     };
-    if (n_my > 0) gemm1(0);
-    for (int i = 0; i < n_my; ++i) {
-      if (i + 1 < n_my) gemm1(i + 1);   // keeps the tensor core busy while tile i is in its mid epilogue
-      gemm2(i);
+    // Two queues, served in whichever order their inputs arrive: GEMM 2 of tile i (needs the mid epilogue's H) and GEMM 1
+    // of the next tile (needs the transform). A fixed order would make the transform of tile i+2 wait for GEMM 2 of tile
+    // i+1 behind GEMM 1 of tile i+2, i.e. serialise transform and tensor work.
+    int i1 = 0, i2 = 0;
+    while (i2 < n_my) {
+      bool go2 = false, go1 = false;
+      if (lane == 0) {
+        if (i2 < i1) go2 = mbar_test(h_full, (uint32_t)i2 & 1u) && mbar_test(a2_empty(i2 & 1), (((uint32_t)i2 >> 1) & 1u) ^ 1u);
+        if (!go2 && i1 < n_my && i1 < i2 + 2)
+          go1 = mbar_test(p_ready(i1 & 1), ((uint32_t)i1 >> 1) & 1u) && mbar_test(a1_empty(i1 & 1), (((uint32_t)i1 >> 1) & 1u) ^ 1u);
+      }
+      const int sel = __shfl_sync(0xffffffffu, go2 ? 2 : (go1 ? 1 : 0), 0);
+      if (sel == 2) gemm2(i2++);
+      else if (sel == 1) gemm1(i1++);
     }
   } else if (warp < 6) {
     // ================================ transform: x -> x_lo, e = ELU(x), e_lo ================================
