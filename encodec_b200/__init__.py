@@ -14,6 +14,7 @@ _LAZY = {
     "SEANetDecoder": ("modules", "SEANetDecoder"),
     "ResidualVectorQuantizer": ("quantization", "ResidualVectorQuantizer"),
     "QuantizedResult": ("quantization", "QuantizedResult"),
+    "HostPipeline": ("pipeline", "HostPipeline"),
 }
 
 

@@ -347,3 +347,26 @@ def test_48k_segment_edge_cases():
         if score["mismatched"] == 0:
             d = np.abs(audio.cpu().numpy() - o_audio)
             assert d.max() < AUDIO_MAX_ABS and np.sqrt((d ** 2).mean()) < AUDIO_RMS, (length, d.max())
+
+
+def test_host_pipeline_matches_direct_forward():
+    """HostPipeline overlaps copies with kernels on three streams; results must be exactly model(x) for every batch,
+    in order, also when the ring of buffers wraps (5 batches through depth 2)."""
+    from encodec_b200 import synth
+    from encodec_b200.pipeline import HostPipeline
+    case = gc.load_model_case("24k_24kbps_ragged")
+    spec = case["spec"]
+    m = ug.build_model(spec, case["sd"], 6.0, case["distinct"])
+    batches = [torch.from_numpy(synth.make_audio(100 + i, 3, 1, 24000 + 320 * i)).pin_memory() for i in range(5)]
+    want = []
+    for xb in batches:
+        a, c, _, _ = m(xb.cuda())
+        want.append((a.cpu(), c.cpu()))
+    got = []
+    for a, c in HostPipeline(m, depth=2).run(batches):
+        got.append((a.clone(), c.clone()))      # the yielded buffers are a ring
+    assert len(got) == len(want)
+    for (a, c), (wa, wc) in zip(got, want):
+        assert torch.equal(a, wa) and torch.equal(c, wc)
+    with pytest.raises(ValueError):
+        list(HostPipeline(m).run([batches[0].cuda()]))
