@@ -137,74 +137,99 @@ __global__ void segment_scale_kernel(const float* __restrict__ x, long long batc
   }
 }
 
-// nn.GroupNorm(1, C) applied after the fact (reference modules/conv.py:50,125,162): the conv kernels emit
-// per-CTA partial (sum, sumsq); every CTA here re-reduces its item's partials (a few hundred doubles).
-__device__ __forceinline__ void gn_coeffs(const GnSrc& s, int item, float eps, float* mean_out, float* rstd_out,
-                                          double* red) {
-  double a = 0.0, b = 0.0;
-  const double* pp = s.partial + (long long)item * s.slots * 2;
+// nn.GroupNorm(1, C) applied after the fact (reference modules/conv.py:50,125,162): the conv kernels emit per-CTA partial
+// (sum, sumsq) in fp64; gn_finalize reduces an item's partials ONCE (one CTA per item and source) and leaves (mean, rstd)
+// in the first slot, which the streaming apply kernel then reads -- two doubles per CTA instead of the whole partial list.
+__global__ void __launch_bounds__(256) gn_finalize_kernel(GnSrc a, GnSrc b, float eps) {
+  __shared__ double red[16];
+  const GnSrc& s = blockIdx.y ? b : a;
+  const int item = blockIdx.x;
+  double* pp = const_cast<double*>(s.partial) + (long long)item * s.slots * 2;
+  double u = 0.0, v = 0.0;
   for (int i = threadIdx.x; i < s.slots; i += blockDim.x) {
-    a += pp[2 * i];
-    b += pp[2 * i + 1];
+    u += pp[2 * i];
+    v += pp[2 * i + 1];
   }
   for (int o = 16; o > 0; o >>= 1) {
-    a += __shfl_xor_sync(0xffffffffu, a, o);
-    b += __shfl_xor_sync(0xffffffffu, b, o);
+    u += __shfl_xor_sync(0xffffffffu, u, o);
+    v += __shfl_xor_sync(0xffffffffu, v, o);
   }
-  __syncthreads();
   if ((threadIdx.x & 31) == 0) {
-    red[(threadIdx.x >> 5) * 2] = a;
-    red[(threadIdx.x >> 5) * 2 + 1] = b;
+    red[(threadIdx.x >> 5) * 2] = u;
+    red[(threadIdx.x >> 5) * 2 + 1] = v;
   }
-  __syncthreads();
-  a = 0.0;
-  b = 0.0;
-  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) {
-    a += red[2 * i];
-    b += red[2 * i + 1];
+  __syncthreads();   // also: every partial of this item has been read before slot 0 is overwritten
+  if (threadIdx.x == 0) {
+    u = 0.0;
+    v = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) {
+      u += red[2 * i];
+      v += red[2 * i + 1];
+    }
+    const double mean = u / s.count;
+    double var = v / s.count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    pp[0] = mean;
+    pp[1] = 1.0 / sqrt(var + (double)eps);
   }
-  const double mean = a / s.count;
-  double var = b / s.count - mean * mean;
-  if (var < 0.0) var = 0.0;
-  *mean_out = (float)mean;
-  *rstd_out = (float)(1.0 / sqrt(var + (double)eps));
 }
 
+__device__ __forceinline__ float4 gn_affine(const float4& v, float mean, float rstd, const float4& g, const float4& be) {
+  return make_float4((v.x - mean) * rstd * g.x + be.x, (v.y - mean) * rstd * g.y + be.y, (v.z - mean) * rstd * g.z + be.z,
+                     (v.w - mean) * rstd * g.w + be.w);
+}
+
+template <bool HAS_B, bool RAW, bool ELU>
 __global__ void __launch_bounds__(256)
-gn_apply_kernel(const GnSrc a, const GnSrc b, int has_b, float* __restrict__ out_raw, float* __restrict__ out_elu,
-                long long out_item_stride, long long rows, int C, float eps) {
-  __shared__ double red[16];
+gn_apply_kernel(const GnSrc a, const GnSrc b, float* __restrict__ out_raw, float* __restrict__ out_elu,
+                long long out_item_stride, long long rows, int C) {
   const int item = blockIdx.y;
-  float mean_a, rstd_a, mean_b = 0.f, rstd_b = 0.f;
-  gn_coeffs(a, item, eps, &mean_a, &rstd_a, red);
-  if (has_b) gn_coeffs(b, item, eps, &mean_b, &rstd_b, red);
+  const float mean_a = (float)a.partial[(long long)item * a.slots * 2], rstd_a = (float)a.partial[(long long)item * a.slots * 2 + 1];
+  const float mean_b = HAS_B ? (float)b.partial[(long long)item * b.slots * 2] : 0.f;
+  const float rstd_b = HAS_B ? (float)b.partial[(long long)item * b.slots * 2 + 1] : 0.f;
   const long long n4 = rows * C / 4;
   const float4* xa = reinterpret_cast<const float4*>(a.x + (long long)item * (a.item_stride ? a.item_stride : rows * C));
-  const float4* xb = has_b ? reinterpret_cast<const float4*>(b.x + (long long)item * (b.item_stride ? b.item_stride : rows * C)) : nullptr;
+  const float4* xb = HAS_B ? reinterpret_cast<const float4*>(b.x + (long long)item * (b.item_stride ? b.item_stride : rows * C)) : nullptr;
   const long long ostride = out_item_stride ? out_item_stride : rows * C;
-  float4* o_raw = out_raw ? reinterpret_cast<float4*>(out_raw + (long long)item * ostride) : nullptr;
-  float4* o_elu = out_elu ? reinterpret_cast<float4*>(out_elu + (long long)item * ostride) : nullptr;
+  float4* o_raw = RAW ? reinterpret_cast<float4*>(out_raw + (long long)item * ostride) : nullptr;
+  float4* o_elu = ELU ? reinterpret_cast<float4*>(out_elu + (long long)item * ostride) : nullptr;
   const int c4n = C / 4;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % c4n) * 4;
-    float4 v = xa[i];
-    const float4 g = __ldg(reinterpret_cast<const float4*>(a.gamma + c));
-    const float4 be = __ldg(reinterpret_cast<const float4*>(a.beta + c));
-    v.x = (v.x - mean_a) * rstd_a * g.x + be.x;
-    v.y = (v.y - mean_a) * rstd_a * g.y + be.y;
-    v.z = (v.z - mean_a) * rstd_a * g.z + be.z;
-    v.w = (v.w - mean_a) * rstd_a * g.w + be.w;
-    if (has_b) {
-      float4 u = xb[i];
-      const float4 g2 = __ldg(reinterpret_cast<const float4*>(b.gamma + c));
-      const float4 b2 = __ldg(reinterpret_cast<const float4*>(b.beta + c));
-      v.x += (u.x - mean_b) * rstd_b * g2.x + b2.x;
-      v.y += (u.y - mean_b) * rstd_b * g2.y + b2.y;
-      v.z += (u.z - mean_b) * rstd_b * g2.z + b2.z;
-      v.w += (u.w - mean_b) * rstd_b * g2.w + b2.w;
+  constexpr int U = 4;   // independent 16-byte loads in flight per thread and source
+  for (long long base = (long long)blockIdx.x * (256 * U); base < n4; base += (long long)gridDim.x * (256 * U)) {
+    float4 v[U], u[U];
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const long long i = base + threadIdx.x + k * 256;
+      if (i < n4) {
+        v[k] = __ldcs(xa + i);
+        if (HAS_B) u[k] = __ldcs(xb + i);
+      }
     }
-    if (o_raw) o_raw[i] = v;
-    if (o_elu) o_elu[i] = make_float4(elu1(v.x), elu1(v.y), elu1(v.z), elu1(v.w));
+    float e[4 * U];
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const long long i = base + threadIdx.x + k * 256;
+      if (i < n4) {
+        const int c = (int)(i % c4n) * 4;
+        v[k] = gn_affine(v[k], mean_a, rstd_a, __ldg(reinterpret_cast<const float4*>(a.gamma + c)),
+                         __ldg(reinterpret_cast<const float4*>(a.beta + c)));
+        if (HAS_B) {
+          const float4 w = gn_affine(u[k], mean_b, rstd_b, __ldg(reinterpret_cast<const float4*>(b.gamma + c)),
+                                     __ldg(reinterpret_cast<const float4*>(b.beta + c)));
+          v[k].x += w.x; v[k].y += w.y; v[k].z += w.z; v[k].w += w.w;
+        }
+        if (RAW) o_raw[i] = v[k];
+      }
+      e[4 * k + 0] = v[k].x; e[4 * k + 1] = v[k].y; e[4 * k + 2] = v[k].z; e[4 * k + 3] = v[k].w;
+    }
+    if (ELU) {
+      elu_vec<4 * U>(e);
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        const long long i = base + threadIdx.x + k * 256;
+        if (i < n4) o_elu[i] = make_float4(e[4 * k + 0], e[4 * k + 1], e[4 * k + 2], e[4 * k + 3]);
+      }
+    }
   }
 }
 
@@ -300,7 +325,19 @@ int launch_gn_apply2(const GnSrc& a, const GnSrc* b, float* out_raw, float* out_
   dim3 grid((unsigned)min(cdiv(n4, 256 * 4), 4096LL), (unsigned)n_items);
   ProfScope prof(PROF_GN_APPLY, s, 0.0,
                  4.0 * (double)rows * C * n_items * ((b ? 2 : 1) + (out_raw ? 1 : 0) + (out_elu ? 1 : 0)));
-  gn_apply_kernel<<<grid, 256, 0, s>>>(a, b ? *b : a, b ? 1 : 0, out_raw, out_elu, out_item_stride, rows, C, eps);
+  gn_finalize_kernel<<<dim3((unsigned)n_items, b ? 2 : 1), 256, 0, s>>>(a, b ? *b : a, eps);
+  const GnSrc bb = b ? *b : a;
+#define ECB_GN_LAUNCH(HB, R, E) gn_apply_kernel<HB, R, E><<<grid, 256, 0, s>>>(a, bb, out_raw, out_elu, out_item_stride, rows, C)
+  if (b) {
+    if (out_raw && out_elu) ECB_GN_LAUNCH(true, true, true);
+    else if (out_raw) ECB_GN_LAUNCH(true, true, false);
+    else ECB_GN_LAUNCH(true, false, true);
+  } else {
+    if (out_raw && out_elu) ECB_GN_LAUNCH(false, true, true);
+    else if (out_raw) ECB_GN_LAUNCH(false, true, false);
+    else ECB_GN_LAUNCH(false, false, true);
+  }
+#undef ECB_GN_LAUNCH
   ECB_LAUNCHED();
   return 0;
 }
