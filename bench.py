@@ -352,7 +352,17 @@ def main():
             sec = v["ms"] * 1e-3
             if name in tensor_classes:
                 achieved = v["flops"] / sec / 1e12
-                return {"kernel": name, "bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                if name == "lstm_recurrent":
+                    # the recurrence is fp32 CUDA-core work by design (W_hh lives in registers; a tensor-core version would
+                    # have to re-read it from shared memory every step): its practical roof is the packed-FFMA2 issue rate
+                    # measured on this pool with tools/fma_probe.cu (54 TFLOP/s at 2 warps per scheduler, register operands)
+                    extra = {"also": {"bound": "fp32_fma", "achieved": achieved, "peak": 54.2, "unit": "TFLOP/s",
+                                      "frac": achieved / 54.2,
+                                      "note": "peak = measured fma.rn.f32x2 rate with register operands (tools/fma_probe.cu, "
+                                              "profiles/r01_fma_probe.txt); nominal 2*128 lanes*148 SMs*1.9 GHz = 72 TFLOP/s"}}
+                else:
+                    extra = {}
+                return {**extra, "kernel": name, "bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
                         "frac": achieved / peaks["tflops"], "traffic": None,
                         "peak_source": f"{peaks['source']} bf16 dense (sustained); algorithmic FLOPs, computed as 3xTF32 split "
                                        "operands on tcgen05 (fp32 FFMA for the LSTM recurrence)",

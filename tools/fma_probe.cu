@@ -3,8 +3,8 @@
 #include <cstdio>
 #include <cuda_runtime.h>
 
-template <int MODE>
-__global__ void __launch_bounds__(256, 1) probe(float* out, const float* in, int iters) {
+template <int MODE, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) probe(float* out, const float* in, int iters) {
   // 4 rows x 8 k-pairs of weights (64 regs), 4 items
   float2 w[4][8];
   for (int r = 0; r < 4; ++r)
@@ -17,11 +17,16 @@ __global__ void __launch_bounds__(256, 1) probe(float* out, const float* in, int
     for (int k = 0; k < 8; ++k) h[i][k] = make_float2(in[64 + i * 8 + k + threadIdx.x % 3], in[100 + i * 8 + k]);
   for (int it = 0; it < iters; ++it) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k)
+    for (int kk = 0; kk < 8; ++kk)
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int ii = 0; ii < 4; ++ii)
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
+        for (int rr = 0; rr < 4; ++rr) {
+          // MODE 0/1: row innermost (h operand repeats); MODE 2: item innermost (w operand repeats);
+          // MODE 3: k innermost (accumulator chain, nothing repeats)
+          const int k = MODE == 3 ? rr * 2 + (ii & 1) : kk;
+          const int i = MODE == 2 ? rr : (MODE == 3 ? (kk & 3) : ii);
+          const int r = MODE == 2 ? ii : (MODE == 3 ? (ii >> 1) + 2 * (kk >> 2) : rr);
           if (MODE == 0) {
             acc[r][i].x = fmaf(w[r][k].x, h[i][k].x, acc[r][i].x);
             acc[r][i].y = fmaf(w[r][k].y, h[i][k].y, acc[r][i].y);
@@ -36,7 +41,7 @@ __global__ void __launch_bounds__(256, 1) probe(float* out, const float* in, int
         }
     // perturb h slightly so nothing is hoisted
 #pragma unroll
-    for (int i = 0; i < 4; ++i) h[i][it & 7].x += 1e-9f;
+    for (int i = 0; i < 4; ++i) h[i][0].x += 1e-9f;
   }
   float s = 0.f;
   for (int r = 0; r < 4; ++r)
@@ -44,8 +49,9 @@ __global__ void __launch_bounds__(256, 1) probe(float* out, const float* in, int
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
-template <int MODE>
-void run(const char* name, int threads) {
+template <int MODE, int MAXT>
+void run(const char* name) {
+  const int threads = MAXT;
   float *out, *in;
   cudaMalloc(&out, 148 * 1024 * 4);
   cudaMalloc(&in, 4096);
@@ -54,9 +60,9 @@ void run(const char* name, int threads) {
   cudaEvent_t a, b;
   cudaEventCreate(&a);
   cudaEventCreate(&b);
-  probe<MODE><<<148, threads>>>(out, in, 100);
+  probe<MODE, MAXT><<<148, threads>>>(out, in, 100);
   cudaEventRecord(a);
-  probe<MODE><<<148, threads>>>(out, in, iters);
+  probe<MODE, MAXT><<<148, threads>>>(out, in, iters);
   cudaEventRecord(b);
   cudaEventSynchronize(b);
   float ms;
@@ -69,9 +75,14 @@ void run(const char* name, int threads) {
 }
 
 int main() {
-  for (int t : {128, 256}) {
-    run<0>("FFMA", t);
-    run<1>("FFMA2", t);
-  }
+#define PROBE_ALL(T)           \
+  run<0, T>("FFMA");           \
+  run<1, T>("FFMA2");          \
+  run<2, T>("FFMA2-i");        \
+  run<3, T>("FFMA2-k");
+  PROBE_ALL(128)
+  PROBE_ALL(256)
+  PROBE_ALL(384)
+  PROBE_ALL(512)
   return 0;
 }
