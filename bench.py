@@ -355,9 +355,9 @@ def main():
                 if name == "lstm_recurrent":
                     # the recurrence is fp32 CUDA-core work by design (W_hh lives in registers; a tensor-core version would
                     # have to re-read it from shared memory every step): its practical roof is the packed-FFMA2 issue rate
-                    # measured on this pool with tools/fma_probe.cu (54 TFLOP/s at 2 warps per scheduler, register operands)
-                    extra = {"also": {"bound": "fp32_fma", "achieved": achieved, "peak": 54.2, "unit": "TFLOP/s",
-                                      "frac": achieved / 54.2,
+                    # measured on this pool with tools/fma_probe.cu (62 TFLOP/s on 148 SMs, register operands)
+                    extra = {"also": {"bound": "fp32_fma", "achieved": achieved, "peak": 62.0, "unit": "TFLOP/s",
+                                      "frac": achieved / 62.0,
                                       "note": "peak = measured fma.rn.f32x2 rate with register operands (tools/fma_probe.cu, "
                                               "profiles/r01_fma_probe.txt); nominal 2*128 lanes*148 SMs*1.9 GHz = 72 TFLOP/s"}}
                 else:

@@ -68,7 +68,7 @@ class CodecSpec:
     sample_rate: int = 24000
     channels: int = 1
     causal: bool = True
-    norm: str = "weight_norm"  # or "time_group_norm"
+    norm: str = "weight_norm"  # or "time_group_norm" (48 kHz model) or "layer_norm" (the fork's 10 Hz configs)
     normalize: bool = False
     segment: Optional[float] = None
     overlap: float = 0.01
@@ -121,6 +121,13 @@ def spec_24khz() -> CodecSpec:
 def spec_48khz() -> CodecSpec:
     return CodecSpec(sample_rate=48000, channels=2, causal=False, norm="time_group_norm", normalize=True,
                      segment=1.0, target_bandwidths=[3.0, 6.0, 12.0, 24.0])
+
+
+def spec_fork10hz(ratios=(6, 5, 5, 2, 1)) -> CodecSpec:
+    """The fork's own training configuration (reference ``params/091224_l1.yaml:65-92``): 10 Hz mono signals, causal,
+    ``norm='layer_norm'`` (ConvLayerNorm), ratios incl. a stride-1 stage, dimension 256, 1024 bins, 0.08 kbps (n_q 8)."""
+    return CodecSpec(sample_rate=10, channels=1, causal=True, norm="layer_norm", ratios=list(ratios), dimension=256,
+                     bins=1024, target_bandwidths=[0.08])
 
 
 def conv_layout(spec: CodecSpec):

@@ -96,15 +96,33 @@ def group_norm1(x: np.ndarray, gamma: np.ndarray, beta: np.ndarray, eps: float =
     return (y * gamma[None, :, None] + beta[None, :, None]).astype(x.dtype)
 
 
+def layer_norm_c(x: np.ndarray, gamma: np.ndarray, beta: np.ndarray, eps: float = 1e-5) -> np.ndarray:
+    """ConvLayerNorm -- modules/norm.py:16-30 (used by modules/conv.py:44-46 for norm='layer_norm'): nn.LayerNorm over the
+    channel axis of every time step separately (``b c t -> b t c``, normalise, back), biased variance, eps 1e-5."""
+    xd = x.astype(np.float64)
+    mean = xd.mean(axis=1, keepdims=True)
+    var = xd.var(axis=1, keepdims=True)
+    y = (xd - mean) / np.sqrt(var + eps)
+    return (y * gamma[None, :, None] + beta[None, :, None]).astype(x.dtype)
+
+
+def apply_norm(y: np.ndarray, gamma, beta, kind: str) -> np.ndarray:
+    """get_norm_module -- modules/conv.py:38-52: Identity (weight_norm / none), GroupNorm(1, C) or ConvLayerNorm."""
+    if gamma is None:
+        return y
+    return layer_norm_c(y, gamma, beta) if kind == "layer_norm" else group_norm1(y, gamma, beta)
+
+
 # ----------------------------------------------------------------------------------------------
 # parameter access in the reference state_dict layout
 # ----------------------------------------------------------------------------------------------
 class Params:
     """Folds weight-norm once and hands out (w, b, gamma, beta) per conv prefix."""
 
-    def __init__(self, sd: Dict[str, np.ndarray], dtype=np.float32):
+    def __init__(self, sd: Dict[str, np.ndarray], dtype=np.float32, norm: str = "time_group_norm"):
         self.sd = {k: np.asarray(v) for k, v in sd.items()}
         self.dtype = dtype
+        self.norm = norm   # which module a '<conv>.norm.weight' entry belongs to (only matters when such entries exist)
 
     def conv(self, prefix: str, transposed: bool = False):
         base = f"{prefix}.convtr.convtr" if transposed else f"{prefix}.conv.conv"
@@ -142,9 +160,7 @@ def sconv1d(x: np.ndarray, p: Params, prefix: str, stride: int, causal: bool) ->
         pl = padding_total - pr
         xp = pad1d_reflect(x, pl, pr + extra)
     y = conv1d(xp, w, b, stride)
-    if gamma is not None:
-        y = group_norm1(y, gamma, beta)
-    return y
+    return apply_norm(y, gamma, beta, p.norm)
 
 
 def sconvtr1d(x: np.ndarray, p: Params, prefix: str, stride: int, causal: bool,
@@ -154,8 +170,7 @@ def sconvtr1d(x: np.ndarray, p: Params, prefix: str, stride: int, causal: bool,
     k = w.shape[-1]
     padding_total = k - stride
     y = conv_transpose1d(x, w, b, stride)
-    if gamma is not None:
-        y = group_norm1(y, gamma, beta)
+    y = apply_norm(y, gamma, beta, p.norm)
     if causal:
         pr = math.ceil(padding_total * trim_right_ratio)
         pl = padding_total - pr
@@ -360,7 +375,7 @@ def decode_frame(frame: dict, p: Params, spec, taps=None) -> np.ndarray:
 def encode(x: np.ndarray, sd: Dict[str, np.ndarray], spec, bandwidth: Optional[float], dtype=np.float32) -> List[dict]:
     """EncodecModel.encode -- model.py:146-173."""
     assert x.ndim == 3 and 0 < x.shape[1] <= 2
-    p = Params(sd, dtype)
+    p = Params(sd, dtype, spec.norm)
     n_q = spec.n_q_for_bandwidth(bandwidth)
     codebooks = codebooks_from_state_dict(sd, n_q)
     x = x.astype(dtype)
@@ -375,7 +390,7 @@ def encode(x: np.ndarray, sd: Dict[str, np.ndarray], spec, bandwidth: Optional[f
 
 def decode(frames: List[dict], sd: Dict[str, np.ndarray], spec, dtype=np.float32) -> np.ndarray:
     """EncodecModel.decode -- model.py:212-227."""
-    p = Params(sd, dtype)
+    p = Params(sd, dtype, spec.norm)
     if spec.segment_length is None:
         assert len(frames) == 1
         return decode_frame(frames[0], p, spec)

@@ -193,3 +193,7 @@ if __name__ == "__main__":
     run_case("48k_24kbps_3seg", s48, 2, 2 * 47520 + 14400, 24.0, True, 300)
     # config 4 shape at a CPU-friendly size
     run_rvq_case("rvq_nq32_8k", 8192, 32, 1024, 128, 400)
+    # SURVEY 8f row 3 -- the fork's own 10 Hz configurations (params/091224_l1.yaml): ConvLayerNorm, a stride-1 stage,
+    # dimension 256, 0.08 kbps (n_q 8). A 4-ratio variant the yaml lists (512-wide LSTM) and the active 5-ratio one (1024).
+    run_case("fork10hz_ln_r5541", synth.spec_fork10hz((5, 5, 4, 1)), 2, 4033, 0.08, True, 500)
+    run_case("fork10hz_ln_r65521", synth.spec_fork10hz((6, 5, 5, 2, 1)), 2, 12100, 0.08, True, 600)

@@ -28,8 +28,9 @@ def _t(a: np.ndarray) -> torch.Tensor:
 class TorchParams:
     """Weight-norm folded once (the reference re-folds on every forward, conv.py:28-29: ~3 % of its CPU time)."""
 
-    def __init__(self, sd: Dict[str, np.ndarray]):
+    def __init__(self, sd: Dict[str, np.ndarray], norm: str = "time_group_norm"):
         self.sd = sd
+        self.norm = norm
         self._conv = {}
         self._lstm = {}
 
@@ -74,6 +75,15 @@ def pad1d_reflect(x: torch.Tensor, left: int, right: int) -> torch.Tensor:
     return padded[..., :padded.shape[-1] - extra]
 
 
+def _norm(y, gamma, beta, kind: str):
+    """get_norm_module -- modules/conv.py:38-52; ConvLayerNorm = LayerNorm over channels per time step (norm.py:16-30)."""
+    if gamma is None:
+        return y
+    if kind == "layer_norm":
+        return F.layer_norm(y.transpose(1, 2), (y.shape[1],), gamma, beta, 1e-5).transpose(1, 2)
+    return F.group_norm(y, 1, gamma, beta, 1e-5)
+
+
 def sconv1d(x, p: TorchParams, prefix: str, stride: int, causal: bool):
     """SConv1d.forward -- modules/conv.py:202-221."""
     w, b, gamma, beta = p.conv(prefix)
@@ -87,9 +97,7 @@ def sconv1d(x, p: TorchParams, prefix: str, stride: int, causal: bool):
         pr = padding_total // 2
         xp = pad1d_reflect(x, padding_total - pr, pr + extra)
     y = F.conv1d(xp, w, b, stride=stride)
-    if gamma is not None:
-        y = F.group_norm(y, 1, gamma, beta, 1e-5)
-    return y
+    return _norm(y, gamma, beta, p.norm)
 
 
 def sconvtr1d(x, p: TorchParams, prefix: str, stride: int, causal: bool):
@@ -97,8 +105,7 @@ def sconvtr1d(x, p: TorchParams, prefix: str, stride: int, causal: bool):
     w, b, gamma, beta = p.conv(prefix, transposed=True)
     padding_total = w.shape[-1] - stride
     y = F.conv_transpose1d(x, w, b, stride=stride)
-    if gamma is not None:
-        y = F.group_norm(y, 1, gamma, beta, 1e-5)
+    y = _norm(y, gamma, beta, p.norm)
     pr = padding_total if causal else padding_total // 2
     pl = padding_total - pr
     return y[..., pl: y.shape[-1] - pr]
@@ -186,7 +193,7 @@ def linear_overlap_add(frames: List[torch.Tensor], stride: int):
 @torch.no_grad()
 def forward(x: np.ndarray, sd: Dict[str, np.ndarray], spec, bandwidth: Optional[float], params: Optional[TorchParams] = None):
     """EncodecModel.forward -- model.py:146-257. Returns (audio [B,C,T], codes [B,n_q,sum T_f]) as numpy arrays."""
-    p = params or TorchParams(sd)
+    p = params or TorchParams(sd, spec.norm)
     n_q = spec.n_q_for_bandwidth(bandwidth)
     cbs = [_t(sd[f"quantizer.vq.layers.{i}._codebook.embed"]) for i in range(n_q)]
     xt = _t(x)

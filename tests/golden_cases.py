@@ -12,10 +12,13 @@ from encodec_b200 import synth
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 MODEL_CASES = ["cfg1_24k_6kbps_shared", "24k_24kbps_ragged", "48k_24kbps_3seg"]
+FORK_CASES = ["fork10hz_ln_r5541", "fork10hz_ln_r65521"]   # layer_norm, stride-1 stage, dimension 256
 RVQ_CASE = "rvq_nq32_8k"
 
 
 def spec_for(name):
+    if name.startswith("fork10hz"):
+        return synth.spec_fork10hz(tuple(int(ch) for ch in name.rsplit("_r", 1)[1]))
     return synth.spec_48khz() if name.startswith("48k") else synth.spec_24khz()
 
 

@@ -6,7 +6,7 @@ from oracle import encodec_oracle as orc
 from tests import golden_cases as gc
 
 
-@pytest.mark.parametrize("name", gc.MODEL_CASES)
+@pytest.mark.parametrize("name", gc.MODEL_CASES + gc.FORK_CASES)
 def test_oracle_forward_matches_reference(name):
     case = gc.load_model_case(name)
     spec = case["spec"]

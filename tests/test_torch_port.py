@@ -8,7 +8,7 @@ from oracle import torch_port as tp
 from tests import golden_cases as gc
 
 
-@pytest.mark.parametrize("name", gc.MODEL_CASES)
+@pytest.mark.parametrize("name", gc.MODEL_CASES + gc.FORK_CASES)
 def test_torch_port_matches_reference_golden(name):
     case = gc.load_model_case(name)
     spec = case["spec"]
