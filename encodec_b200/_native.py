@@ -122,13 +122,13 @@ def require_cuda(t: torch.Tensor, what: str, dtype=torch.float32) -> None:
         raise RuntimeError(f"encodec_b200: {what} must be {dtype}, got {t.dtype}")
 
 
-def make_spec(channels: int, causal: bool, group_norm: bool, n_filters: int, dimension: int, ratios, kernel_size: int,
+def make_spec(channels: int, causal: bool, group_norm: int, n_filters: int, dimension: int, ratios, kernel_size: int,
               last_kernel_size: int, residual_kernel_size: int, compress: int, lstm_layers: int, bins: int,
               n_q: int) -> EcbSpec:
     if len(ratios) > MAX_RATIOS:
         raise NotImplementedError(f"at most {MAX_RATIOS} ratios are supported")
     s = EcbSpec()
-    s.channels, s.causal, s.group_norm = int(channels), int(bool(causal)), int(bool(group_norm))
+    s.channels, s.causal, s.group_norm = int(channels), int(bool(causal)), int(group_norm)   # 0 wn, 1 GroupNorm, 2 LayerNorm
     s.n_filters, s.dimension, s.n_ratios = int(n_filters), int(dimension), len(ratios)
     for i, r in enumerate(ratios):
         s.ratios[i] = int(r)

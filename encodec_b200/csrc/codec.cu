@@ -367,9 +367,22 @@ struct Plan {
 Plan make_plan(const ecb_codec* c, long long n_items, long long length) {
   Plan p;
   const long long t_pad = length + 2LL * c->hop;
-  p.act_floats = (size_t)n_items * t_pad * c->spec.n_filters;
+  long long per_item = t_pad * c->spec.n_filters;
+  {
+    // the widest level: with a stride-1 stage (the fork's ratios end in 1) the 64-channel level runs at the full rate
+    long long T = length;
+    long long ch = c->spec.n_filters;
+    for (int i = c->spec.n_ratios - 1; i >= 0; --i) {
+      const int r = c->spec.ratios[i];
+      T = ceil_div_ll(T, r);
+      ch *= 2;
+      const long long need = (T + 2LL * ACT_HALO + 16 + 2LL * r) * ch;
+      if (need > per_item) per_item = need;
+    }
+  }
+  p.act_floats = (size_t)n_items * per_item;
   p.n_act = c->spec.group_norm ? 5 : 4;
-  p.stat_doubles = c->spec.group_norm ? (size_t)n_items * (ceil_div_ll(length, 128) + 64) * 16 : 0;
+  p.stat_doubles = c->spec.group_norm == 1 ? (size_t)n_items * (ceil_div_ll(length, 128) + 64) * 16 : 0;
   p.lstm_floats = (size_t)lstm_recurrent_workspace_floats((int)n_items);
   p.total_bytes = (p.act_floats * p.n_act + p.lstm_floats) * sizeof(float) + 2 * p.stat_doubles * sizeof(double) +
                   256 * 16;
@@ -954,6 +967,16 @@ GnSrc gn_src(const float* x, long long item_stride, const double* partial, int s
   return g;
 }
 
+inline bool norm_is_ln(const ecb_spec& s) { return s.group_norm == 2; }   // ConvLayerNorm (norm='layer_norm', conv.py:44-46)
+
+// GroupNorm(1, C) over the whole item, or LayerNorm over the channels of each row, of one or two raw conv outputs.
+int norm_apply(Ctx& x, const GnSrc& a, const GnSrc* b, float* out_raw, float* out_elu, long long out_item_stride, long long rows,
+               int C, int c_real = 0) {
+  if (norm_is_ln(x.c->spec))
+    return launch_ln_apply2(a, b, out_raw, out_elu, out_item_stride, x.n_items, rows, C, c_real ? c_real : C, 1e-5f, x.st);
+  return launch_gn_apply2(a, b, out_raw, out_elu, out_item_stride, x.n_items, rows, C, 1e-5f, x.st);
+}
+
 // conv (+ bias) -> GroupNorm -> {raw, ELU} for a plain (non-transposed) conv. The raw conv output goes to `dst`'s
 // layout first (dst = out_raw if given, else out_elu) and is normalised in place.
 int tc_conv_gn(Ctx& x, const ConvW& cw, const Act& in, int C0, bool zero_pad, long long M, Act* out_raw, Act* out_elu,
@@ -962,11 +985,11 @@ int tc_conv_gn(Ctx& x, const ConvW& cw, const Act& in, int C0, bool zero_pad, lo
   Act& dst = out_raw ? *out_raw : *out_elu;
   int slots = 0;
   if (tc_run(x, cw.t_hi, cw.t_lo, cw.t_bias, cw.t_K, cw.t_N, in, C0, cw.k, cw.stride, pad_left_of(s, cw.k, cw.stride), zero_pad,
-             nullptr, dst.row0(), nullptr, dst.stride(), M, 0, 3, 0, x.stat[stat_idx], &slots))
+             nullptr, dst.row0(), nullptr, dst.stride(), M, 0, 3, 0, norm_is_ln(s) ? nullptr : x.stat[stat_idx], &slots))
     return 1;
   GnSrc a = gn_src(dst.row0(), dst.stride(), x.stat[stat_idx], slots, (double)M * cw.c_out, cw.t_gamma, cw.t_beta);
-  if (launch_gn_apply2(a, nullptr, out_raw ? out_raw->row0() : nullptr, out_elu ? out_elu->row0() : nullptr, dst.stride(),
-                       x.n_items, M, cw.t_N, 1e-5f, x.st))
+  if (norm_apply(x, a, nullptr, out_raw ? out_raw->row0() : nullptr, out_elu ? out_elu->row0() : nullptr, dst.stride(), M, cw.t_N,
+                 cw.c_out))
     return 1;
   if (out_elu && out_elu->halo > 0 &&
       launch_halo_fill(nullptr, out_elu->row0(), out_elu->stride(), out_elu->T, out_elu->C, x.n_items, out_elu->halo, 0, x.st))
@@ -977,19 +1000,20 @@ int tc_conv_gn(Ctx& x, const ConvW& cw, const Act& in, int C0, bool zero_pad, lo
 // SEANetResnetBlock with GroupNorm: Y = ELU(GN(shortcut(X)) + GN(block3(ELU(GN(block1(E)))))). hbuf / sbuf are scratch.
 int tc_res_gn(Ctx& x, const ResW& r, const Act& X, const Act& E, float* hbuf, float* sbuf, Act& Y) {
   const int dim = r.sc.c_out;
+  const bool ln = norm_is_ln(x.c->spec);
   Act H = act_of(hbuf, r.hid_pad, X.T, 0);
   if (tc_conv_gn(x, r.b1, E, dim, false, X.T, nullptr, &H, 0)) return 1;
   Act S = act_of(sbuf, dim, X.T, 0);
   int slots3 = 0, slots_s = 0;
   if (tc_run(x, r.b3.t_hi, r.b3.t_lo, r.b3.t_bias, r.b3.t_K, r.b3.t_N, H, r.hid_pad, 1, 1, 0, true, nullptr, Y.row0(), nullptr,
-             Y.stride(), X.T, 0, 3, 0, x.stat[0], &slots3))
+             Y.stride(), X.T, 0, 3, 0, ln ? nullptr : x.stat[0], &slots3))
     return 1;
   if (tc_run(x, r.sc.t_hi, r.sc.t_lo, r.sc.t_bias, r.sc.t_K, r.sc.t_N, X, dim, 1, 1, 0, true, nullptr, S.row0(), nullptr,
-             S.stride(), X.T, 0, 3, 0, x.stat[1], &slots_s))
+             S.stride(), X.T, 0, 3, 0, ln ? nullptr : x.stat[1], &slots_s))
     return 1;
   GnSrc a = gn_src(S.row0(), S.stride(), x.stat[1], slots_s, (double)X.T * dim, r.sc.t_gamma, r.sc.t_beta);
   GnSrc b = gn_src(Y.row0(), Y.stride(), x.stat[0], slots3, (double)X.T * dim, r.b3.t_gamma, r.b3.t_beta);
-  if (launch_gn_apply2(a, &b, nullptr, Y.row0(), Y.stride(), x.n_items, X.T, dim, 1e-5f, x.st)) return 1;   // shortcut + block
+  if (norm_apply(x, a, &b, nullptr, Y.row0(), Y.stride(), X.T, dim)) return 1;   // shortcut + block
   if (Y.halo > 0 && launch_halo_fill(nullptr, Y.row0(), Y.stride(), Y.T, Y.C, x.n_items, Y.halo, 0, x.st)) return 1;
   return 0;
 }
@@ -1022,11 +1046,11 @@ int encoder_forward_tc_gn(Ctx& x, const float* xin, int64_t n_seg, int64_t lengt
   ci.out_elu = nullptr;
   ci.out_item_stride = X.stride();
   ci.halo = 0;
-  ci.stats = x.stat[0];
+  ci.stats = norm_is_ln(s) ? nullptr : x.stat[0];
   if (launch_conv_in(ci, x.st)) return 1;
   {
     GnSrc a = gn_src(X.row0(), X.stride(), x.stat[0], conv_in_stat_slots(ci), (double)length * ch, c->enc_in.gamma, c->enc_in.beta);
-    if (launch_gn_apply2(a, nullptr, X.row0(), E.row0(), X.stride(), x.n_items, length, ch, 1e-5f, x.st)) return 1;
+    if (norm_apply(x, a, nullptr, X.row0(), E.row0(), X.stride(), length, ch)) return 1;
     if (launch_halo_fill(nullptr, E.row0(), E.stride(), T, ch, x.n_items, ACT_HALO, 0, x.st)) return 1;
   }
   if (tap_act(x.st, 0, X, x.n_items)) return 1;
@@ -1088,12 +1112,12 @@ int decoder_forward_tc_gn(Ctx& x, const float* z_frames, int64_t n_frames, const
     Act R = act_of(Cb, sN, T + 1, 0);
     int slots = 0;
     if (tc_run(x, uw.t_hi, uw.t_lo, uw.t_bias, uw.t_K, uw.t_N, cur, ch, 2, 1, 1, true, nullptr, R.row0(), nullptr, R.stride(),
-               T + 1, 0, 3, 0, x.stat[0], &slots))
+               T + 1, 0, 3, 0, norm_is_ln(s) ? nullptr : x.stat[0], &slots))
       return 1;
     Act X2 = act_of(B, uw.c_out, T2, ACT_HALO), E2 = act_of(D, uw.c_out, T2, ACT_HALO);
     GnSrc a = gn_src(R.row0() + (long long)trim_left * uw.c_out, R.stride(), x.stat[0], slots, (double)(T + 1) * sN, uw.t_gamma,
                      uw.t_beta);
-    if (launch_gn_apply2(a, nullptr, X2.row0(), E2.row0(), X2.stride(), x.n_items, T2, uw.c_out, 1e-5f, x.st)) return 1;
+    if (norm_apply(x, a, nullptr, X2.row0(), E2.row0(), X2.stride(), T2, uw.c_out)) return 1;
     if (launch_halo_fill(nullptr, E2.row0(), E2.stride(), T2, uw.c_out, x.n_items, ACT_HALO, 0, x.st)) return 1;
     T = T2;
     ch = uw.c_out;
@@ -1170,15 +1194,18 @@ int ecb_codec_create(const ecb_spec* spec, ecb_codec** out) {
   ECB_REQUIRE(spec && out, "null argument");
   ECB_REQUIRE(spec->channels >= 1 && spec->channels <= 2, "channels=%d unsupported", spec->channels);
   ECB_REQUIRE(spec->n_filters == 32, "n_filters=%d unsupported (32 only)", spec->n_filters);
-  ECB_REQUIRE(spec->dimension == 128, "dimension=%d unsupported (128 only)", spec->dimension);
+  ECB_REQUIRE(spec->dimension == 128 || spec->dimension == 256, "dimension=%d unsupported (128 or 256)", spec->dimension);
+  ECB_REQUIRE(spec->group_norm >= 0 && spec->group_norm <= 2, "norm code %d unsupported (0 weight_norm, 1 GroupNorm, 2 LayerNorm)",
+              spec->group_norm);
   ECB_REQUIRE(spec->n_ratios >= 1 && spec->n_ratios <= ECB_MAX_RATIOS, "n_ratios=%d unsupported", spec->n_ratios);
   ECB_REQUIRE(spec->compress == 2 && spec->residual_kernel_size == 3, "only compress=2, residual_kernel_size=3");
   ECB_REQUIRE(spec->kernel_size == 7 && spec->last_kernel_size == 7, "only kernel_size=last_kernel_size=7");
-  ECB_REQUIRE(!(spec->group_norm && spec->causal), "GroupNorm doesn't support causal evaluation.");
+  ECB_REQUIRE(!(spec->group_norm == 1 && spec->causal), "GroupNorm doesn't support causal evaluation.");
   ECB_REQUIRE(spec->lstm_layers >= 0 && spec->lstm_layers <= 4, "lstm_layers=%d unsupported", spec->lstm_layers);
   int top = spec->n_filters;
   for (int i = 0; i < spec->n_ratios; ++i) {
-    ECB_REQUIRE(spec->ratios[i] >= 2 && spec->ratios[i] <= 16, "ratio %d unsupported", spec->ratios[i]);
+    ECB_REQUIRE(spec->ratios[i] >= 1 && spec->ratios[i] <= 16, "ratio %d unsupported", spec->ratios[i]);
+    ECB_REQUIRE(spec->ratios[i] >= 2 || spec->group_norm == 2, "a stride-1 stage is only implemented for layer_norm models");
     top *= 2;
   }
   ECB_REQUIRE(spec->lstm_layers == 0 || top == 512, "LSTM width %d unsupported (512 only)", top);
@@ -1315,6 +1342,8 @@ int ecb_encoder_forward(ecb_codec* c, const float* xin, int64_t n_items, int64_t
                         : encoder_forward_tc(x, xin, n_seg, length, x_batch_stride, x_seg_stride, x_chan_stride, scale_out,
                                              emb_out, emb_frames_out);
   }
+  ECB_REQUIRE(s.group_norm != 2, "layer_norm models need at least %d latent frames per item (got %lld)", 2 * ACT_HALO,
+              (long long)ceil_div_ll(length, c->hop));
   float *A = x.buf[0], *B = x.buf[1], *C = x.buf[2], *D = x.buf[3];
 
   if (scale_out) {
@@ -1412,6 +1441,8 @@ int ecb_decoder_forward(ecb_codec* c, const float* z, const float* z_frames, int
     return s.group_norm ? decoder_forward_tc_gn(x, z_frames, n_frames, scale, out)
                         : decoder_forward_tc(x, z_frames, n_frames, scale, out);
   }
+  ECB_REQUIRE(s.group_norm != 2, "layer_norm models need at least %d latent frames per item (got %lld)", 2 * ACT_HALO,
+              (long long)n_frames);
   if (run_conv(x, c->dec_in, z_frames, T, 0, A, 0, nullptr)) return 1;        // -> A raw [T][512]
   if (tap(x.st, 100, A, n_items * T * c->dec_in.c_out)) return 1;
   const float* cur = A;
@@ -1459,16 +1490,16 @@ int ecb_rvq_encode_frames(const float* frames, int64_t n, int64_t dim, const flo
                           int64_t n_q, int64_t bins, int64_t* codes, float* quantized, float* quantized_stack,
                           void* stream) {
   ECB_REQUIRE(frames && codebooks && e2 && codes, "rvq_encode: null argument");
-  ECB_REQUIRE(dim == 128, "rvq_encode: dimension %lld unsupported (128 only)", (long long)dim);
-  return launch_rvq_encode(frames, n, codebooks, e2, (int)n_q, (int)bins, reinterpret_cast<long long*>(codes),
+  ECB_REQUIRE(dim == 128 || dim == 256, "rvq_encode: dimension %lld unsupported (128 or 256)", (long long)dim);
+  return launch_rvq_encode(frames, n, codebooks, e2, (int)n_q, (int)bins, (int)dim, reinterpret_cast<long long*>(codes),
                            quantized, quantized_stack, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int ecb_rvq_decode_frames(const int64_t* codes, int64_t n, int64_t dim, const float* codebooks, int64_t n_q,
                           int64_t bins, float* quantized, void* stream) {
   ECB_REQUIRE(codes && codebooks && quantized, "rvq_decode: null argument");
-  ECB_REQUIRE(dim == 128, "rvq_decode: dimension %lld unsupported (128 only)", (long long)dim);
-  return launch_rvq_decode(reinterpret_cast<const long long*>(codes), n, codebooks, (int)n_q, (int)bins, quantized,
+  ECB_REQUIRE(dim == 128 || dim == 256, "rvq_decode: dimension %lld unsupported (128 or 256)", (long long)dim);
+  return launch_rvq_decode(reinterpret_cast<const long long*>(codes), n, codebooks, (int)n_q, (int)bins, (int)dim, quantized,
                            reinterpret_cast<cudaStream_t>(stream));
 }
 
@@ -1505,7 +1536,7 @@ int ecb_codec_rvq_forward(ecb_codec* c, const float* xin, const float* x_frames,
     if (launch_rvq_encode_tc(x_frames, n, c->codebooks, c->cb_hi, c->cb_lo, c->e2, c->spec.n_q, (int)n_q, c->spec.bins,
                              reinterpret_cast<long long*>(codes), qf, stack_tmp, st))
       return 1;
-  } else if (launch_rvq_encode(x_frames, n, c->codebooks, c->e2, (int)n_q, c->spec.bins, reinterpret_cast<long long*>(codes),
+  } else if (launch_rvq_encode(x_frames, n, c->codebooks, c->e2, (int)n_q, c->spec.bins, D, reinterpret_cast<long long*>(codes),
                                qf, stack_tmp, st)) {
     return 1;
   }
@@ -1530,7 +1561,7 @@ int ecb_codec_rvq_decode(ecb_codec* c, const int64_t* codes, int64_t batch, int6
   ECB_REQUIRE(n_q >= 1 && n_q <= c->spec.n_q, "rvq_decode: n_q=%lld out of range 1..%d", (long long)n_q, c->spec.n_q);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const long long n = batch * n_frames;
-  if (launch_rvq_decode(reinterpret_cast<const long long*>(codes), n, c->codebooks, (int)n_q, c->spec.bins,
+  if (launch_rvq_decode(reinterpret_cast<const long long*>(codes), n, c->codebooks, (int)n_q, c->spec.bins, c->spec.dimension,
                         quantized_frames, st))
     return 1;
   if (quantized) {

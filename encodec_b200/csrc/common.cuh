@@ -283,6 +283,11 @@ int launch_gn_apply(const GnSrc& a, const GnSrc* b, float* out, int n_items, lon
 // general form: strided items, raw and/or ELU output (either may alias a.x / b->x element for element)
 int launch_gn_apply2(const GnSrc& a, const GnSrc* b, float* out_raw, float* out_elu, long long out_item_stride, int n_items,
                      long long rows, int C, float eps, cudaStream_t s);
+// ConvLayerNorm (reference modules/norm.py:16-30, conv.py:44-46): LayerNorm over the C channels of every time step.
+// out = act(LN(a) [+ LN(b)]) over [n_items][rows][C]; GnSrc::partial / slots / count are unused. C in {32,...,1024} is
+// the stored row width, c_real <= C the channels that exist (the rest is zero padding, kept zero).
+int launch_ln_apply2(const GnSrc& a, const GnSrc* b, float* out_raw, float* out_elu, long long out_item_stride, int n_items,
+                     long long rows, int C, int c_real, float eps, cudaStream_t s);
 int launch_overlap_add(const float* frames, const int* seg_lens, long long batch, int channels, int n_seg,
                        int seg_len, int stride, float* out, long long total, cudaStream_t s);
 
@@ -310,14 +315,14 @@ int launch_lstm_recurrent(const float* pre, const float* w_hh_packed, const floa
 // rvq.cu
 // ------------------------------------------------------------------------------------------------
 int launch_rvq_prepare(const float* codebooks, long long n_q, long long bins, int dim, float* e2, cudaStream_t s);
-int launch_rvq_encode(const float* frames, long long n, const float* codebooks, const float* e2, int n_q, int bins,
+int launch_rvq_encode(const float* frames, long long n, const float* codebooks, const float* e2, int n_q, int bins, int dim,
                       long long* codes, float* quantized, float* stack, cudaStream_t s);
 // tensor-core variant (rvq_tc.cu): cb_hi / cb_lo = split codebooks from launch_rvq_split, [n_q_total][bins][128]
 int launch_rvq_split(const float* codebooks, float* hi, float* lo, long long numel, cudaStream_t s);
 int launch_rvq_encode_tc(const float* frames, long long n, const float* codebooks, const float* cb_hi, const float* cb_lo,
                          const float* e2, int n_q_total, int n_q, int bins, long long* codes, float* quantized, float* stack,
                          cudaStream_t s);
-int launch_rvq_decode(const long long* codes, long long n, const float* codebooks, int n_q, int bins,
+int launch_rvq_decode(const long long* codes, long long n, const float* codebooks, int n_q, int bins, int dim,
                       float* quantized, cudaStream_t s);
 
 }  // namespace ecb

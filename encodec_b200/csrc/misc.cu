@@ -233,6 +233,93 @@ gn_apply_kernel(const GnSrc a, const GnSrc b, float* __restrict__ out_raw, float
   }
 }
 
+// ConvLayerNorm = nn.LayerNorm over channels, per time step (reference modules/norm.py:16-30): one row of the channels-last
+// activation is one normalisation group. LPR lanes share a row (16 bytes per lane and step, V steps), so a warp covers
+// 32 / LPR rows at once; mean, then the centred second moment (two passes over registers), biased variance.
+template <int C>
+__global__ void __launch_bounds__(256)
+ln_apply_kernel(const GnSrc a, const GnSrc b, int has_b, float* __restrict__ out_raw, float* __restrict__ out_elu,
+                long long out_item_stride, long long rows, int c_real, float eps) {
+  // c_real <= C: channels that exist in the model; [c_real, C) is zero padding of the stored row (the 16-channel hidden
+  // layer of the 32-channel residual block is stored 32 wide) and takes no part in the statistics
+  constexpr int LPR = C / 4 < 32 ? C / 4 : 32;   // lanes per row
+  constexpr int V = C / (4 * LPR);               // float4 per lane
+  constexpr int RPW = 32 / LPR;                  // rows per warp step
+  const int item = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR, li = lane % LPR;
+  const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long n_warps = (long long)gridDim.x * (blockDim.x >> 5);
+  const float* xa = a.x + (long long)item * (a.item_stride ? a.item_stride : rows * C);
+  const float* xb = has_b ? b.x + (long long)item * (b.item_stride ? b.item_stride : rows * C) : nullptr;
+  const long long ostride = out_item_stride ? out_item_stride : rows * C;
+  float* o_raw = out_raw ? out_raw + (long long)item * ostride : nullptr;
+  float* o_elu = out_elu ? out_elu + (long long)item * ostride : nullptr;
+  float4 ga[V], ba[V], gb[V], bb[V];
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    const int c = (li + v * LPR) * 4;
+    ga[v] = __ldg(reinterpret_cast<const float4*>(a.gamma + c));
+    ba[v] = __ldg(reinterpret_cast<const float4*>(a.beta + c));
+    if (has_b) {
+      gb[v] = __ldg(reinterpret_cast<const float4*>(b.gamma + c));
+      bb[v] = __ldg(reinterpret_cast<const float4*>(b.beta + c));
+    }
+  }
+  auto normalise = [&](float4 (&x)[V], const float4 (&g)[V], const float4 (&be)[V]) {
+    float s = 0.f;
+#pragma unroll
+    for (int v = 0; v < V; ++v) s += (x[v].x + x[v].y) + (x[v].z + x[v].w);
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float inv_c = 1.f / (float)c_real;
+    const float mean = s * inv_c;
+    float q = 0.f;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const int c = (li + v * LPR) * 4;
+      x[v].x = c + 0 < c_real ? x[v].x - mean : 0.f;
+      x[v].y = c + 1 < c_real ? x[v].y - mean : 0.f;
+      x[v].z = c + 2 < c_real ? x[v].z - mean : 0.f;
+      x[v].w = c + 3 < c_real ? x[v].w - mean : 0.f;
+      q += (x[v].x * x[v].x + x[v].y * x[v].y) + (x[v].z * x[v].z + x[v].w * x[v].w);
+    }
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = 1.f / sqrtf(q * inv_c + eps);
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      x[v].x = x[v].x * rstd * g[v].x + be[v].x;
+      x[v].y = x[v].y * rstd * g[v].y + be[v].y;
+      x[v].z = x[v].z * rstd * g[v].z + be[v].z;
+      x[v].w = x[v].w * rstd * g[v].w + be[v].w;
+    }
+  };
+  for (long long r0 = warp * RPW; r0 < rows; r0 += n_warps * RPW) {
+    const long long r = r0 + sub;
+    const bool live = r < rows;   // whole sub-groups go idle together, the shuffles below stay inside a sub-group
+    float4 x[V], y[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      x[v] = live ? __ldcs(reinterpret_cast<const float4*>(xa + r * C) + li + v * LPR) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (has_b) y[v] = live ? __ldcs(reinterpret_cast<const float4*>(xb + r * C) + li + v * LPR) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    normalise(x, ga, ba);
+    if (has_b) {
+      normalise(y, gb, bb);
+#pragma unroll
+      for (int v = 0; v < V; ++v) { x[v].x += y[v].x; x[v].y += y[v].y; x[v].z += y[v].z; x[v].w += y[v].w; }
+    }
+    if (!live) continue;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      if (o_raw) *(reinterpret_cast<float4*>(o_raw + r * C) + li + v * LPR) = x[v];
+      if (o_elu)
+        *(reinterpret_cast<float4*>(o_elu + r * C) + li + v * LPR) = make_float4(elu1(x[v].x), elu1(x[v].y), elu1(x[v].z), elu1(x[v].w));
+    }
+  }
+}
+
 // utils._linear_overlap_add, reference utils.py:17-56. weight(i) = 0.5 - |t_i - 0.5| with
 // t = linspace(0, 1, seg_len + 2)[1:-1]; a shorter last frame uses the head of the same triangle.
 __device__ __forceinline__ float ola_weight(int i, int seg_len) {
@@ -344,6 +431,31 @@ int launch_gn_apply2(const GnSrc& a, const GnSrc* b, float* out_raw, float* out_
 int launch_gn_apply(const GnSrc& a, const GnSrc* b, float* out, int n_items, long long rows, int C, int out_elu,
                     float eps, cudaStream_t s) {
   return launch_gn_apply2(a, b, out_elu ? nullptr : out, out_elu ? out : nullptr, 0, n_items, rows, C, eps, s);
+}
+int launch_ln_apply2(const GnSrc& a, const GnSrc* b, float* out_raw, float* out_elu, long long out_item_stride, int n_items,
+                     long long rows, int C, int c_real, float eps, cudaStream_t s) {
+  ECB_REQUIRE((out_raw || out_elu) && c_real >= 1 && c_real <= C, "ln_apply: bad argument (C=%d, real %d)", C, c_real);
+  const int lpr = C / 4 < 32 ? C / 4 : 32;
+  const long long warps = cdiv(rows, 32 / lpr);
+  dim3 grid((unsigned)min(cdiv(warps, 8), 2048LL), (unsigned)n_items);
+  ProfScope prof(PROF_GN_APPLY, s, 0.0,
+                 4.0 * (double)rows * C * n_items * ((b ? 2 : 1) + (out_raw ? 1 : 0) + (out_elu ? 1 : 0)));
+  const GnSrc bb = b ? *b : a;
+#define ECB_LN_CASE(CC) \
+  case CC: ln_apply_kernel<CC><<<grid, 256, 0, s>>>(a, bb, b ? 1 : 0, out_raw, out_elu, out_item_stride, rows, c_real, eps); break;
+  switch (C) {
+    ECB_LN_CASE(32)
+    ECB_LN_CASE(64)
+    ECB_LN_CASE(128)
+    ECB_LN_CASE(256)
+    ECB_LN_CASE(512)
+    ECB_LN_CASE(1024)
+    default:
+      ECB_REQUIRE(false, "ln_apply: C=%d unsupported (32, 64, ..., 1024)", C);
+  }
+#undef ECB_LN_CASE
+  ECB_LAUNCHED();
+  return 0;
 }
 int launch_overlap_add(const float* frames, const int* seg_lens, long long batch, int channels, int n_seg,
                        int seg_len, int stride, float* out, long long total, cudaStream_t s) {

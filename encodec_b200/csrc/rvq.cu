@@ -14,22 +14,20 @@
 namespace ecb {
 namespace {
 
-constexpr int RD = 128;        // frame dimension
 constexpr int R_FT = 64;       // frames per CTA
 constexpr int R_EC = 128;      // codebook entries per slab
 constexpr int R_DC = 32;       // dims per slab
-constexpr int R_LD = RD + 4;   // residual row stride (floats)
 constexpr int E_LD = R_DC + 4; // slab row stride (floats)
 constexpr int R_THREADS = 256;
 constexpr int SLAB_FLOATS = R_EC * E_LD;
 
 struct RvqParams {
-  const float* frames;     // [n][128]
-  const float* codebooks;  // [n_q][bins][128]
+  const float* frames;     // [n][D]
+  const float* codebooks;  // [n_q][bins][D]
   const float* e2;         // [n_q][bins]
   long long* codes;        // [n_q][n]
-  float* quantized;        // [n][128] or nullptr
-  float* stack;            // [n_q][n][128] or nullptr
+  float* quantized;        // [n][D] or nullptr
+  float* stack;            // [n_q][n][D] or nullptr
   long long n;
   int n_q, bins;
 };
@@ -39,10 +37,16 @@ __device__ __forceinline__ void cp_async16(float* dst, const float* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(src) : "memory");
 }
 
-__global__ void __launch_bounds__(R_THREADS, 2)
+// RD = frame dimension: 128 (EnCodec 24 / 48 kHz) or 256 (the fork's 10 Hz models). A warp owns whole frames
+// (RD / 128 float4 per lane), 8 frames per warp.
+template <int RD>
+__global__ void __launch_bounds__(R_THREADS, RD == 128 ? 2 : 1)
 rvq_encode_kernel(const RvqParams p) {
+  constexpr int R_LD = RD + 4;               // residual row stride (floats)
+  constexpr int V = RD / 128;                // float4 per lane and frame
+  constexpr int DCH = RD / R_DC;             // dim chunks per entry slab row
   extern __shared__ __align__(16) float smem[];
-  float* Rs = smem;                          // [64][132]
+  float* Rs = smem;                          // [64][RD + 4]
   float* Es = Rs + R_FT * R_LD;              // [2][128][36]
   float* x2s = Es + 2 * SLAB_FLOATS;         // [64]
   int* code_s = reinterpret_cast<int*>(x2s + R_FT);  // [64]
@@ -51,14 +55,15 @@ rvq_encode_kernel(const RvqParams p) {
   const int tx = tid & 15;   // entries tx + 16 j
   const int ty = tid >> 4;   // frames  ty + 16 i
   const long long n0 = (long long)blockIdx.x * R_FT;
-  const int chunks_per_layer = (p.bins / R_EC) * (RD / R_DC);
+  const int chunks_per_layer = (p.bins / R_EC) * DCH;
+  const int wid = tid >> 5, lane = tid & 31;
   const int n_stage = p.n_q * chunks_per_layer;
 
   auto issue_slab = [&](int s, int buf) {
     const int layer = s / chunks_per_layer;
     const int r = s - layer * chunks_per_layer;
-    const int ec = r >> 2;
-    const int dc = r & 3;
+    const int ec = r / DCH;
+    const int dc = r % DCH;
     const float* src = p.codebooks + ((long long)layer * p.bins + ec * R_EC) * RD + dc * R_DC;
     float* dst = Es + buf * SLAB_FLOATS;
 #pragma unroll
@@ -73,20 +78,23 @@ rvq_encode_kernel(const RvqParams p) {
 
   issue_slab(0, 0);
 
-  // residual tile + |x|^2; thread owns elements idx = tid + 256 k -> (frame idx/32, float4 idx%32)
-  float4 qacc[8];
+  // residual tile + |x|^2; warp w owns frames w + 8 k, lane l the float4 l + 32 v of each
+  float4 qacc[8][V];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    const int idx = tid + k * R_THREADS;
-    const int f = idx >> 5;
-    const int d4 = idx & 31;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (n0 + f < p.n) v = __ldg(reinterpret_cast<const float4*>(p.frames + (n0 + f) * RD + d4 * 4));
-    *reinterpret_cast<float4*>(Rs + f * R_LD + d4 * 4) = v;
-    qacc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    float s = (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+    const int f = wid + 8 * k;
+    float s = 0.f;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const int d4 = lane + 32 * v;
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (n0 + f < p.n) x = __ldg(reinterpret_cast<const float4*>(p.frames + (n0 + f) * RD + d4 * 4));
+      *reinterpret_cast<float4*>(Rs + f * R_LD + d4 * 4) = x;
+      qacc[k][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+      s += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);
+    }
     s = warp_sum(s);
-    if ((tid & 31) == 0) x2s[f] = s;
+    if (lane == 0) x2s[f] = s;
   }
 
   float acc[4][8];
@@ -102,8 +110,8 @@ rvq_encode_kernel(const RvqParams p) {
     const int buf = s & 1;
     const int layer = s / chunks_per_layer;
     const int r = s - layer * chunks_per_layer;
-    const int ec = r >> 2;
-    const int dc = r & 3;
+    const int ec = r / DCH;
+    const int dc = r % DCH;
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();  // slab s landed for everyone; everyone is done with slab s-1 (and with Rs updates)
     if (s + 1 < n_stage) issue_slab(s + 1, buf ^ 1);
@@ -133,7 +141,7 @@ rvq_encode_kernel(const RvqParams p) {
           acc[i][j] = fmaf(rv[i].w, ev[j].w, acc[i][j]);
         }
     }
-    if (dc == 3) {
+    if (dc == DCH - 1) {
       // distances of this slab of entries, running arg-min (strict < keeps the lowest index)
       const float* e2 = p.e2 + (long long)layer * p.bins + ec * R_EC;
 #pragma unroll
@@ -175,19 +183,22 @@ rvq_encode_kernel(const RvqParams p) {
         const float* cb = p.codebooks + (long long)layer * p.bins * RD;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          const int idx = tid + k * R_THREADS;
-          const int f = idx >> 5;
-          const int d4 = idx & 31;
-          const float4 q = __ldg(reinterpret_cast<const float4*>(cb + (long long)code_s[f] * RD + d4 * 4));
-          float4 v = *reinterpret_cast<float4*>(Rs + f * R_LD + d4 * 4);
-          v.x -= q.x; v.y -= q.y; v.z -= q.z; v.w -= q.w;           // core_vq.py:402
-          *reinterpret_cast<float4*>(Rs + f * R_LD + d4 * 4) = v;
-          qacc[k].x += q.x; qacc[k].y += q.y; qacc[k].z += q.z; qacc[k].w += q.w;  // core_vq.py:404
-          if (p.stack && n0 + f < p.n)
-            *reinterpret_cast<float4*>(p.stack + ((long long)layer * p.n + n0 + f) * RD + d4 * 4) = q;
-          float sq = (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+          const int f = wid + 8 * k;
+          float sq = 0.f;
+#pragma unroll
+          for (int v = 0; v < V; ++v) {
+            const int d4 = lane + 32 * v;
+            const float4 q = __ldg(reinterpret_cast<const float4*>(cb + (long long)code_s[f] * RD + d4 * 4));
+            float4 x = *reinterpret_cast<float4*>(Rs + f * R_LD + d4 * 4);
+            x.x -= q.x; x.y -= q.y; x.z -= q.z; x.w -= q.w;           // core_vq.py:402
+            *reinterpret_cast<float4*>(Rs + f * R_LD + d4 * 4) = x;
+            qacc[k][v].x += q.x; qacc[k][v].y += q.y; qacc[k][v].z += q.z; qacc[k][v].w += q.w;  // core_vq.py:404
+            if (p.stack && n0 + f < p.n)
+              *reinterpret_cast<float4*>(p.stack + ((long long)layer * p.n + n0 + f) * RD + d4 * 4) = q;
+            sq += (x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w);
+          }
           sq = warp_sum(sq);
-          if ((tid & 31) == 0) x2s[f] = sq;
+          if (lane == 0) x2s[f] = sq;
         }
         // the __syncthreads at the top of the next stage orders these writes before the next reads
       }
@@ -196,30 +207,34 @@ rvq_encode_kernel(const RvqParams p) {
   if (p.quantized) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const int idx = tid + k * R_THREADS;
-      const int f = idx >> 5;
-      const int d4 = idx & 31;
-      if (n0 + f < p.n) *reinterpret_cast<float4*>(p.quantized + (n0 + f) * RD + d4 * 4) = qacc[k];
+      const int f = wid + 8 * k;
+#pragma unroll
+      for (int v = 0; v < V; ++v)
+        if (n0 + f < p.n) *reinterpret_cast<float4*>(p.quantized + (n0 + f) * RD + (lane + 32 * v) * 4) = qacc[k][v];
     }
   }
 }
 
 // |E|^2 per entry, one warp per entry
-__global__ void rvq_e2_kernel(const float* __restrict__ cb, float* __restrict__ e2, long long rows) {
+__global__ void rvq_e2_kernel(const float* __restrict__ cb, float* __restrict__ e2, long long rows, int dim) {
   const long long row = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   if (row >= rows) return;
-  const float4 v = __ldg(reinterpret_cast<const float4*>(cb + row * RD) + (threadIdx.x & 31));
-  float s = (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+  float s = 0.f;
+  for (int d4 = threadIdx.x & 31; d4 < dim / 4; d4 += 32) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(cb + row * dim) + d4);
+    s += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+  }
   s = warp_sum(s);
   if ((threadIdx.x & 31) == 0) e2[row] = s;
 }
 
 // ResidualVectorQuantization.decode (core_vq.py:434-445): out = ((E_0[c0] + E_1[c1]) + ...)
 __global__ void rvq_decode_kernel(const long long* __restrict__ codes, long long n, const float* __restrict__ cb,
-                                  int n_q, int bins, float* __restrict__ out) {
+                                  int n_q, int bins, int RD, float* __restrict__ out) {
   const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  const long long f = idx >> 5;
-  const int d4 = (int)(idx & 31);
+  const int D4 = RD / 4;
+  const long long f = idx / D4;
+  const int d4 = (int)(idx % D4);
   if (f >= n) return;
   float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int l = 0; l < n_q; ++l) {
@@ -231,25 +246,28 @@ __global__ void rvq_decode_kernel(const long long* __restrict__ codes, long long
   *reinterpret_cast<float4*>(out + f * RD + d4 * 4) = a;
 }
 
-constexpr size_t RVQ_SMEM = sizeof(float) * (R_FT * R_LD + 2 * SLAB_FLOATS + R_FT) + sizeof(int) * R_FT;
+constexpr size_t rvq_smem(int rd) { return sizeof(float) * (R_FT * (rd + 4) + 2 * SLAB_FLOATS + R_FT) + sizeof(int) * R_FT; }
 
 }  // namespace
 
 int launch_rvq_prepare(const float* codebooks, long long n_q, long long bins, int dim, float* e2, cudaStream_t s) {
-  ECB_REQUIRE(dim == RD, "rvq: dimension %d unsupported (only %d)", dim, RD);
+  ECB_REQUIRE(dim == 128 || dim == 256, "rvq: dimension %d unsupported (128 or 256)", dim);
   const long long rows = n_q * bins;
-  rvq_e2_kernel<<<(unsigned)cdiv(rows * 32, 256), 256, 0, s>>>(codebooks, e2, rows);
+  rvq_e2_kernel<<<(unsigned)cdiv(rows * 32, 256), 256, 0, s>>>(codebooks, e2, rows, dim);
   ECB_LAUNCHED();
   return 0;
 }
 
-int launch_rvq_encode(const float* frames, long long n, const float* codebooks, const float* e2, int n_q, int bins,
+int launch_rvq_encode(const float* frames, long long n, const float* codebooks, const float* e2, int n_q, int bins, int dim,
                       long long* codes, float* quantized, float* stack, cudaStream_t s) {
+  ECB_REQUIRE(dim == 128 || dim == 256, "rvq: dimension %d unsupported (128 or 256)", dim);
+  const int RD = dim;
   ECB_REQUIRE(n > 0 && n_q > 0, "rvq: empty input (n=%lld, n_q=%d)", n, n_q);
   ECB_REQUIRE(bins % R_EC == 0, "rvq: bins=%d must be a multiple of %d", bins, R_EC);
   static bool attr_set = false;
   if (!attr_set) {
-    ECB_CUDA(cudaFuncSetAttribute(rvq_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RVQ_SMEM));
+    ECB_CUDA(cudaFuncSetAttribute(rvq_encode_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rvq_smem(128)));
+    ECB_CUDA(cudaFuncSetAttribute(rvq_encode_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rvq_smem(256)));
     attr_set = true;
   }
   RvqParams p;
@@ -264,15 +282,16 @@ int launch_rvq_encode(const float* frames, long long n, const float* codebooks, 
   p.bins = bins;
   ProfScope prof(PROF_RVQ, s, 2.0 * (double)n * n_q * bins * RD,
                  4.0 * ((double)n * RD * (quantized ? 2 : 1) + (double)n_q * bins * RD) + 8.0 * (double)n * n_q);
-  rvq_encode_kernel<<<(unsigned)cdiv(n, R_FT), R_THREADS, RVQ_SMEM, s>>>(p);
+  if (dim == 128) rvq_encode_kernel<128><<<(unsigned)cdiv(n, R_FT), R_THREADS, rvq_smem(128), s>>>(p);
+  else rvq_encode_kernel<256><<<(unsigned)cdiv(n, R_FT), R_THREADS, rvq_smem(256), s>>>(p);
   ECB_LAUNCHED();
   return 0;
 }
 
-int launch_rvq_decode(const long long* codes, long long n, const float* codebooks, int n_q, int bins,
+int launch_rvq_decode(const long long* codes, long long n, const float* codebooks, int n_q, int bins, int dim,
                       float* quantized, cudaStream_t s) {
-  ECB_REQUIRE(n > 0 && n_q > 0, "rvq decode: empty input");
-  rvq_decode_kernel<<<(unsigned)cdiv(n * 32, 256), 256, 0, s>>>(codes, n, codebooks, n_q, bins, quantized);
+  ECB_REQUIRE(n > 0 && n_q > 0 && dim % 4 == 0, "rvq decode: empty input");
+  rvq_decode_kernel<<<(unsigned)cdiv(n * (dim / 4), 256), 256, 0, s>>>(codes, n, codebooks, n_q, bins, dim, quantized);
   ECB_LAUNCHED();
   return 0;
 }

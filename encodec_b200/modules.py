@@ -17,7 +17,9 @@ from torch import nn
 
 from . import _native as nat
 
-_SUPPORTED_NORMS = ("weight_norm", "time_group_norm")
+_SUPPORTED_NORMS = ("weight_norm", "time_group_norm", "layer_norm")
+_AFFINE_NORMS = ("time_group_norm", "layer_norm")
+_NORM_CODE = {"weight_norm": 0, "time_group_norm": 1, "layer_norm": 2}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -42,7 +44,7 @@ class _ConvParams(nn.Module):
 
 
 class _AffineParams(nn.Module):
-    """nn.GroupNorm(1, C) affine parameters (reference conv.py:50)."""
+    """Affine parameters of nn.GroupNorm(1, C) (reference conv.py:50) or ConvLayerNorm (conv.py:44-46, norm.py:16-30)."""
 
     def __init__(self, channels: int):
         super().__init__()
@@ -54,7 +56,7 @@ class NormConv1d(nn.Module):
     def __init__(self, c_in, c_out, k, norm: str):
         super().__init__()
         self.conv = _ConvParams(c_in, c_out, k, False, norm == "weight_norm")
-        self.norm = _AffineParams(c_out) if norm == "time_group_norm" else nn.Identity()
+        self.norm = _AffineParams(c_out) if norm in _AFFINE_NORMS else nn.Identity()
         self.norm_type = norm
 
 
@@ -62,7 +64,7 @@ class NormConvTranspose1d(nn.Module):
     def __init__(self, c_in, c_out, k, norm: str):
         super().__init__()
         self.convtr = _ConvParams(c_in, c_out, k, True, norm == "weight_norm")
-        self.norm = _AffineParams(c_out) if norm == "time_group_norm" else nn.Identity()
+        self.norm = _AffineParams(c_out) if norm in _AFFINE_NORMS else nn.Identity()
         self.norm_type = norm
 
 
@@ -127,8 +129,8 @@ def _check_common(activation, activation_params, norm, norm_params, n_residual_l
         raise NotImplementedError("encodec_b200: needs n_residual_layers=1, true_skip=False, pad_mode='reflect'")
     if (kernel_size, last_kernel_size, residual_kernel_size, compress) != (7, 7, 3, 2):
         raise NotImplementedError("encodec_b200: needs kernel_size=7, last_kernel_size=7, residual_kernel_size=3, compress=2")
-    if n_filters != 32 or dimension != 128:
-        raise NotImplementedError("encodec_b200: needs n_filters=32 and dimension=128")
+    if n_filters != 32 or dimension not in (128, 256):
+        raise NotImplementedError("encodec_b200: needs n_filters=32 and dimension 128 or 256")
 
 
 class _NativeStack(nn.Module):
@@ -147,7 +149,7 @@ class _NativeStack(nn.Module):
         return tuple(sig)
 
     def _spec(self) -> nat.EcbSpec:
-        return nat.make_spec(self.channels, self.causal, self.norm == "time_group_norm", self.n_filters, self.dimension,
+        return nat.make_spec(self.channels, self.causal, _NORM_CODE[self.norm], self.n_filters, self.dimension,
                              self._dec_ratios, 7, 7, 3, 2, self.lstm_layers, 128, 1)
 
     def native(self) -> nat.Codec:

@@ -82,8 +82,8 @@ class ResidualVectorQuantizer(nn.Module):
         super().__init__()
         if codebook_dim != dimension:
             raise NotImplementedError("encodec_b200: project_in/project_out (codebook_dim != dimension) is not implemented")
-        if dimension != 128:
-            raise NotImplementedError("encodec_b200: only dimension=128 is implemented")
+        if dimension not in (128, 256):
+            raise NotImplementedError("encodec_b200: only dimension 128 or 256 is implemented")
         if bins % 128 != 0:
             raise NotImplementedError("encodec_b200: bins must be a multiple of 128")
         self.n_q = n_q
@@ -110,7 +110,7 @@ class ResidualVectorQuantizer(nn.Module):
                     raise RuntimeError(
                         f"encodec_b200: codebook {i} is not initialised (inited == 0). The reference would run k-means "
                         "on the first batch (core_vq.py:143-153); load a state_dict or set embed and inited first.")
-            spec = nat.make_spec(1, True, False, 32, self.dimension, [8, 5, 4, 2], 7, 7, 3, 2, 2, self.bins, self.n_q)
+            spec = nat.make_spec(1, True, 0, 32, self.dimension, [8, 5, 4, 2], 7, 7, 3, 2, 2, self.bins, self.n_q)
             codec = nat.Codec(spec, embeds[0].device)
             codec.load({f"quantizer.vq.layers.{i}._codebook.embed": e for i, e in enumerate(embeds)})
             self.__dict__["_codec"] = codec

@@ -70,8 +70,9 @@ def test_no_cpu_fallback_and_unsupported_hyperparameters():
         m(torch.zeros(1, 1, 24000))
     with pytest.raises(RuntimeError, match="CUDA"):
         m.encoder(torch.zeros(1, 1, 24000))
+    eb.SEANetEncoder(norm="layer_norm", causal=True, ratios=[5, 5, 4, 1], dimension=256)   # the fork's configs build
     with pytest.raises(NotImplementedError):
-        eb.SEANetEncoder(norm="layer_norm")
+        eb.SEANetEncoder(norm="time_layer_norm")
     with pytest.raises(NotImplementedError):
         eb.SEANetEncoder(n_filters=64)
     with pytest.raises(ValueError):

@@ -21,7 +21,7 @@ def _oracle_elu(x):
     return orc.elu(x.astype(np.float32))
 
 
-@pytest.mark.parametrize("name", gc.MODEL_CASES)
+@pytest.mark.parametrize("name", gc.MODEL_CASES + gc.FORK_CASES[:1])
 def test_encoder_stages_match_oracle(name):
     """Every stage of the encoder stack against the oracle's taps (first segment only, for speed)."""
     case = gc.load_model_case(name)
@@ -33,7 +33,7 @@ def test_encoder_stages_match_oracle(name):
         mono = x.mean(axis=1, keepdims=True)
         x = (x / (1e-8 + np.sqrt((mono ** 2).mean(axis=2, keepdims=True)))).astype(np.float32)
     taps = {}
-    p = orc.Params(case["sd"], np.float32)
+    p = orc.Params(case["sd"], np.float32, spec.norm)
     emb_o = orc.seanet_encoder(x, p, spec, taps)
     xt = torch.from_numpy(x).cuda()
     bsz = x.shape[0]
@@ -53,13 +53,14 @@ def test_encoder_stages_match_oracle(name):
         got = ug.tap_stage(lambda: m.encoder(xt), stage, ref_cl.size).reshape(ref_cl.shape)
         err = ug.rel_err(got, ref_cl)
         worst = max(worst, err)
+        print(f"[{name}] encoder stage {stage} {key}: rel err {err:.3e}")
         assert err < 2e-5, (name, stage, key, err)
     emb = m.encoder(xt).cpu().numpy()
     assert ug.rel_err(emb, emb_o) < 2e-5
     assert emb.shape == (bsz, spec.dimension, -(-seg // spec.hop_length))
 
 
-@pytest.mark.parametrize("name", gc.MODEL_CASES)
+@pytest.mark.parametrize("name", gc.MODEL_CASES + gc.FORK_CASES[:1])
 def test_decoder_stages_match_oracle(name):
     case = gc.load_model_case(name)
     spec = case["spec"]
@@ -67,7 +68,7 @@ def test_decoder_stages_match_oracle(name):
     t_f = -(-(spec.segment_length or case["x"].shape[-1]) // spec.hop_length)
     z = np.ascontiguousarray(case["quantized"][:, :, :t_f])
     taps = {}
-    p = orc.Params(case["sd"], np.float32)
+    p = orc.Params(case["sd"], np.float32, spec.norm)
     out_o = orc.seanet_decoder(z, p, spec, taps)
     zt = torch.from_numpy(z).cuda()
     stages = [(101, "decoder.model.1", True)]
@@ -83,15 +84,17 @@ def test_decoder_stages_match_oracle(name):
         ref_cl = np.ascontiguousarray(np.transpose(ref, (0, 2, 1)))
         got = ug.tap_stage(lambda: m.decoder(zt), stage, ref_cl.size).reshape(ref_cl.shape)
         err = ug.rel_err(got, ref_cl)
+        print(f"[{name}] decoder stage {stage} {key}: rel err {err:.3e}")
         assert err < 5e-5, (name, stage, key, err)
     out = m.decoder(zt).cpu().numpy()
     assert out.shape == out_o.shape
     assert np.abs(out - out_o).max() < 1e-4
 
 
-@pytest.mark.parametrize("name", gc.MODEL_CASES)
+@pytest.mark.parametrize("name", gc.MODEL_CASES + gc.FORK_CASES[:1])
 def test_forward_matches_reference_golden(name):
-    """EncodecModel.forward against the unmodified reference's outputs."""
+    """EncodecModel.forward against the unmodified reference's outputs (BASELINE configs and, SURVEY 8f row 3, the fork's own
+    10 Hz layer_norm configuration)."""
     case = gc.load_model_case(name)
     spec = case["spec"]
     m = ug.build_model(spec, case["sd"], case["bandwidth"], case["distinct"])
