@@ -35,6 +35,10 @@ WORKLOADS = {
                  desc="EnCodec 24 kHz causal mono, 6 kbps (n_q=8), 1 x 1 s"),
     "cfg3": dict(model="48k", bandwidth=24.0, batch=32, seconds=30.0,
                  desc="EnCodec 48 kHz stereo, 24 kbps (n_q=16), 1 s segments 1% overlap, batch 32 x 30 s per GPU"),
+    # the fork's own training configuration (params/091224_l1.yaml): 32 x 4 hours of a 10 Hz signal
+    "fork10hz": dict(model="fork10hz", bandwidth=0.08, batch=32, seconds=14400.0,
+                     desc="the fork's 10 Hz model (layer_norm, ratios 6,5,5,2,1, dimension 256, 1024-wide LSTM), 0.08 kbps (n_q=8), "
+                          "batch 32 x 144000 samples (4 h each)"),
     "cfg5": dict(model="24k", bandwidth=6.0, batch=256, seconds=10.0,
                  desc="EnCodec 24 kHz causal mono, 6 kbps (n_q=8), 256 x 10 s clips per GPU (long-form shard)"),
 }
@@ -42,7 +46,16 @@ WORKLOADS = {
 
 def make_spec(kind):
     from encodec_b200 import synth
-    return synth.spec_24khz() if kind == "24k" else synth.spec_48khz()
+    return {"24k": synth.spec_24khz, "48k": synth.spec_48khz, "fork10hz": synth.spec_fork10hz}[kind]()
+
+
+def cpu_sample(wl):
+    """Bounded sample of the workload for the CPU legs: (clips, seconds per clip)."""
+    if wl["model"] == "24k":
+        return min(8, wl["batch"]), min(wl["seconds"], 10.0)
+    if wl["model"] == "fork10hz":
+        return min(2, wl["batch"]), wl["seconds"]          # 2 x 144000 samples: a few seconds of CPU work
+    return min(2, wl["batch"]), min(wl["seconds"], 10.0)
 
 
 def read_peaks():
@@ -107,7 +120,7 @@ def cpu_port_throughput(spec, sd, bandwidth, clips, seconds, repeats=1):
     torch.set_num_threads(os.cpu_count() or 1)
     length = int(seconds * spec.sample_rate)
     x = synth.make_audio(999, clips, spec.channels, length)
-    params = _PORT_PARAMS.setdefault(id(sd), port.TorchParams(sd))   # weight-norm folded once, outside the timed call
+    params = _PORT_PARAMS.setdefault(id(sd), port.TorchParams(sd, spec.norm))   # weight-norm folded once, outside the timed call
     best = None
     for _ in range(repeats):
         t0 = time.perf_counter()
@@ -124,10 +137,9 @@ def run_reference_arm(args, wl, rank, world):
     from encodec_b200 import synth
     spec = make_spec(wl["model"])
     sd = synth.make_state_dict(spec, seed=0)
-    clips, seconds = (8, min(wl["seconds"], 10.0)) if wl["model"] == "24k" else (2, min(wl["seconds"], 10.0))
-    clips = min(clips, wl["batch"])
+    clips, seconds = cpu_sample(wl)
     for _ in range(args.warmup):
-        cpu_port_throughput(spec, sd, wl["bandwidth"], 1, min(seconds, 1.0))
+        cpu_port_throughput(spec, sd, wl["bandwidth"], 1, min(seconds, 1.0) if wl["model"] != "fork10hz" else 1000.0)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         cpu_port_throughput(spec, sd, wl["bandwidth"], clips, seconds)
@@ -303,7 +315,7 @@ def main():
 
         # ---- opt-in variant: single-pass TF32 decoder (fp32-accurate encoder + quantiser unchanged) ------------------
         variants = {}
-        if rank == 0 and world == 1 and spec.norm == "weight_norm":
+        if rank == 0 and world == 1 and spec.norm == "weight_norm" and wl["model"] == "24k":
             model.decoder.tf32 = True
             step(0, gather=False)
             torch.cuda.synchronize(dev)
@@ -397,9 +409,8 @@ def main():
                 roofline = roof(top_name)
         cpu_baseline = None
         if world == 1 and not args.no_cpu_baseline:
-            clips, seconds = (8, min(wl["seconds"], 10.0)) if wl["model"] == "24k" else (2, min(wl["seconds"], 10.0))
-            clips = min(clips, wl["batch"])
-            cpu_port_throughput(spec, sd, wl["bandwidth"], 1, 1.0)  # warm-up
+            clips, seconds = cpu_sample(wl)
+            cpu_port_throughput(spec, sd, wl["bandwidth"], 1, 1.0 if wl["model"] != "fork10hz" else 1000.0)  # warm-up
             v, spent = cpu_port_throughput(spec, sd, wl["bandwidth"], clips, seconds)
             cpu_baseline = {"value": v, "unit": "audio-s/s", "cores": os.cpu_count() or 1, "kind": "port",
                             "sample": f"{clips} clip(s) x {seconds:g} s of the same workload, {spent:.1f} s of CPU work "

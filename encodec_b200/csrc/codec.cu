@@ -364,6 +364,8 @@ struct Plan {
   size_t total_bytes;
 };
 
+inline int top_width(const ecb_spec& s) { return s.n_filters << s.n_ratios; }   // channels at the LSTM: n_filters * 2^n_ratios
+
 Plan make_plan(const ecb_codec* c, long long n_items, long long length) {
   Plan p;
   const long long t_pad = length + 2LL * c->hop;
@@ -383,7 +385,7 @@ Plan make_plan(const ecb_codec* c, long long n_items, long long length) {
   p.act_floats = (size_t)n_items * per_item;
   p.n_act = c->spec.group_norm ? 5 : 4;
   p.stat_doubles = c->spec.group_norm == 1 ? (size_t)n_items * (ceil_div_ll(length, 128) + 64) * 16 : 0;
-  p.lstm_floats = (size_t)lstm_recurrent_workspace_floats((int)n_items);
+  p.lstm_floats = (size_t)lstm_recurrent_workspace_floats((int)n_items, top_width(c->spec));
   p.total_bytes = (p.act_floats * p.n_act + p.lstm_floats) * sizeof(float) + 2 * p.stat_doubles * sizeof(double) +
                   256 * 16;
   return p;
@@ -801,7 +803,7 @@ int tc_res(Ctx& x, const ResW& r, const Act& X, const Act& E, float* hbuf, Act& 
 
 // SLSTM (modules/lstm.py:22-28): X raw [item][T][512] -> out = ELU(lstm(X) + X). pre / h0 are plain scratch.
 int tc_lstm(Ctx& x, const std::vector<LstmLayerW>& layers, const Act& X, float* pre_buf, float* h0_buf, Act& out, int split) {
-  const int H = 512, L = (int)layers.size();
+  const int H = top_width(x.c->spec), L = (int)layers.size();
   Act pre = act_of(pre_buf, 4 * H, X.T, 0);
   Act h0 = act_of(h0_buf, H, X.T, 0);
   const Act* cur = &X;
@@ -1208,7 +1210,7 @@ int ecb_codec_create(const ecb_spec* spec, ecb_codec** out) {
     ECB_REQUIRE(spec->ratios[i] >= 2 || spec->group_norm == 2, "a stride-1 stage is only implemented for layer_norm models");
     top *= 2;
   }
-  ECB_REQUIRE(spec->lstm_layers == 0 || top == 512, "LSTM width %d unsupported (512 only)", top);
+  ECB_REQUIRE(spec->lstm_layers == 0 || top == 512 || top == 1024, "LSTM width %d unsupported (512 or 1024)", top);
   ECB_REQUIRE(spec->bins % 128 == 0 && spec->n_q >= 1, "bins=%d must be a multiple of 128", spec->bins);
   ecb_codec* c = new ecb_codec();
   c->spec = *spec;
@@ -1273,14 +1275,14 @@ int ecb_codec_finalize(ecb_codec* c, void* stream) {
     for (int i = 0; i < s.n_ratios; ++i)
       if (prepare_res(c, c->enc_res[i], st) || prepare_conv(c, c->enc_down[i], st)) return 1;
     if (s.lstm_layers &&
-        prepare_lstm(c, "encoder.model." + std::to_string(1 + 3 * s.n_ratios), 512, c->enc_lstm, st))
+        prepare_lstm(c, "encoder.model." + std::to_string(1 + 3 * s.n_ratios), top_width(s), c->enc_lstm, st))
       return 1;
   }
   if (c->has_dec) {
     if (prepare_conv(c, c->dec_in, st) || prepare_conv(c, c->dec_out, st)) return 1;
     for (int i = 0; i < s.n_ratios; ++i)
       if (prepare_conv(c, c->dec_up[i], st) || prepare_res(c, c->dec_res[i], st)) return 1;
-    if (s.lstm_layers && prepare_lstm(c, "decoder.model.1", 512, c->dec_lstm, st)) return 1;
+    if (s.lstm_layers && prepare_lstm(c, "decoder.model.1", top_width(s), c->dec_lstm, st)) return 1;
   }
   c->tc_ready = false;
   {
@@ -1397,7 +1399,7 @@ int ecb_encoder_forward(ecb_codec* c, const float* xin, int64_t n_items, int64_t
   const float* top = A;
   int top_elu_pending = 1;  // the ELU before the last conv (seanet.py:138)
   if (s.lstm_layers) {
-    if (run_lstm(x, c->enc_lstm, 512, A, T, B, C)) return 1;             // A -> C = ELU(lstm(A) + A)
+    if (run_lstm(x, c->enc_lstm, top_width(s), A, T, B, C)) return 1;             // A -> C = ELU(lstm(A) + A)
     top = C;
     top_elu_pending = 0;
     if (tap(x.st, 50, C, n_items * T * ch)) return 1;
@@ -1447,9 +1449,9 @@ int ecb_decoder_forward(ecb_codec* c, const float* z, const float* z_frames, int
   if (tap(x.st, 100, A, n_items * T * c->dec_in.c_out)) return 1;
   const float* cur = A;
   if (s.lstm_layers) {
-    if (run_lstm(x, c->dec_lstm, 512, A, T, B, C)) return 1;                  // -> C = ELU(lstm(A) + A)
+    if (run_lstm(x, c->dec_lstm, top_width(s), A, T, B, C)) return 1;                  // -> C = ELU(lstm(A) + A)
     cur = C;
-    if (tap(x.st, 101, C, n_items * T * 512)) return 1;
+    if (tap(x.st, 101, C, n_items * T * top_width(s))) return 1;
   } else {
     // no LSTM: the ELU before the first transposed conv still has to happen; fold it into a copy-free path
     set_error("decoder without LSTM is not supported yet");

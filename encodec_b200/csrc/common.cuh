@@ -305,7 +305,7 @@ int launch_unpack_codes(const unsigned char* in, long long n_bytes, int K, long 
 // Pre-gates pre[b][t][4H] (input projection + both biases already added) -> h sequence. w_hh is the reference's
 // [4H][H] tensor. If skip != nullptr the written output is act(h + skip) (SLSTM skip connection, lstm.py:25-26) and
 // the raw h stays in the recurrent state only.
-int lstm_recurrent_workspace_floats(int batch);
+int lstm_recurrent_workspace_floats(int batch, int H);
 // skip / out rows of item b start at + b*skip_item_stride / + b*out_item_stride floats (0 means the dense T*H).
 int launch_lstm_recurrent(const float* pre, const float* w_hh_packed, const float* skip, long long skip_item_stride,
                           float* out, long long out_item_stride, int batch, int T, int H, int out_elu,

@@ -1,4 +1,6 @@
-// SLSTM recurrence (reference modules/lstm.py:12-28 -> nn.LSTM(512, 512, 2), gates i,f,g,o, zero state).
+// SLSTM recurrence (reference modules/lstm.py:12-28 -> nn.LSTM(H, H, 2), gates i,f,g,o, zero state; H = 512 for the EnCodec
+// models, 1024 for the fork's 5-ratio 10 Hz models -- described below for H = 512, the 1024 variant keeps the per-CTA
+// weight slice at 32 K floats by owning 8 units of all items: 128 unit blocks x 1 batch group, K split over 32 lanes).
 //
 // The input projection W_ih x_t + b_ih + b_hh of ALL time steps is one tensor-core GEMM (tc_conv.cu, 1 tap);
 // this file holds the part that is sequential in time: gates_t = pre_t + W_hh h_{t-1}, the cell update
@@ -24,17 +26,26 @@
 namespace ecb {
 namespace {
 
-constexpr int LH = 512;               // hidden size
-constexpr int L_UNITS = 16;           // hidden units per CTA
-constexpr int L_UB = LH / L_UNITS;    // 32 unit blocks
-constexpr int L_NQ = 4;               // batch quarters
-constexpr int L_CTAS = L_UB * L_NQ;   // 128
+constexpr int L_CTAS = 128;
 constexpr int L_SB = 4;               // items per sub-group
 constexpr int L_THREADS = 512;        // 4 warpgroups: 2 x compute, cell teams, loader
-constexpr int L_HLD = LH + 4;         // padded h row in smem (floats)
 constexpr int L_STAGES = 8;           // h ring depth
 constexpr int L_LOADERS = 4;          // loader warps; loader k fills the stages of running indices n = k (mod 4)
 constexpr int L_TEAMS = 4;
+
+// Geometry as a function of the hidden size: every compute thread holds 4 gate rows x 32 k of W_hh (128 registers).
+template <int LH>
+struct Geo {
+  static constexpr int KS = LH / 32;              // lanes a dot product is split over (16 | 32)
+  static constexpr int RGS = 8 * (32 / KS);       // row groups of 4 gate rows per CTA (16 | 8)
+  static constexpr int UNITS = RGS;               // hidden units per CTA: 4 gates x UNITS rows = 4 x RGS
+  static constexpr int UQ = UNITS / 4;            // unit quads per gate
+  static constexpr int UB = LH / UNITS;           // unit blocks (32 | 128)
+  static constexpr int NQ = L_CTAS / UB;          // batch groups (4 | 1)
+  static constexpr int HLD = LH + 4;              // padded h row in smem (floats)
+  static constexpr int GROW = 4 * UNITS;          // gate values per item in the gs exchange
+  static constexpr int PAIRS = L_SB * UNITS / 32; // (item, unit) pairs per cell-team lane (2 | 1)
+};
 
 struct LstmParams {
   const float* pre;    // [B][T][4H]
@@ -71,12 +82,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   } while (!done);
 }
 
+template <int LH>
 __global__ void __launch_bounds__(L_THREADS, 1)
 lstm_recurrent_kernel(const LstmParams p) {
+  using G = Geo<LH>;
+  constexpr int L_HLD = G::HLD, L_UNITS = G::UNITS, L_UB = G::UB, L_NQ = G::NQ, GROW = G::GROW;
   extern __shared__ __align__(16) float smem[];
   float* hs = smem;                                   // [L_STAGES][L_SB][L_HLD]  h_{t-1} ring
-  float* gs = hs + L_STAGES * L_SB * L_HLD;           // [L_TEAMS][L_SB][64]      reduced gate pre-activations
-  float* cs = gs + L_TEAMS * L_SB * 64;               // [q_items][16]            cell state of this CTA's (items, units)
+  float* gs = hs + L_STAGES * L_SB * L_HLD;           // [L_TEAMS][L_SB][GROW]    reduced gate pre-activations
+  float* cs = gs + L_TEAMS * L_SB * GROW;             // [q_items][UNITS]         cell state of this CTA's (items, units)
   uint64_t* bars = reinterpret_cast<uint64_t*>(cs + p.q_items * L_UNITS);   // 8-byte aligned: all counts above are even
   const uint32_t bar0 = smem_addr(bars);
   auto h_full = [&](int s) { return bar0 + 8u * s; };
@@ -120,10 +134,10 @@ lstm_recurrent_kernel(const LstmParams p) {
   if (warp < 8) {
     // ================================ compute warps ================================
     // row group rg (4 gate rows: gate rg >> 2, units 4 (rg & 3) .. + 3), k split ks (k = (16 j + ks) 4 + e)
-    const int ks = lane & 15;
-    const int rg = warp * 2 + (lane >> 4);
-    const int gate = rg >> 2;
-    const int uq = rg & 3;
+    const int ks = lane & (G::KS - 1);
+    const int rg = warp * (32 / G::KS) + lane / G::KS;
+    const int gate = rg / G::UQ;
+    const int uq = rg % G::UQ;
     // weights as packed fp32 pairs (k, k+1): the dot products run on fma.rn.f32x2 (two FMAs per issue slot), which
     // keeps even-k and odd-k partial sums in the two halves of a 64-bit accumulator
     unsigned long long w2[4][8][2];
@@ -132,7 +146,7 @@ lstm_recurrent_kernel(const LstmParams p) {
       const float* wr = p.w_hh + ((long long)gate * LH + ub * L_UNITS + uq * 4 + r) * LH;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(wr + (j * 16 + ks) * 4));
+        const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(wr + (j * G::KS + ks) * 4));
         w2[r][j][0] = v.x;
         w2[r][j][1] = v.y;
       }
@@ -153,7 +167,7 @@ lstm_recurrent_kernel(const LstmParams p) {
         for (int i = 0; i < L_SB; ++i) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const ulonglong2 hv = *reinterpret_cast<const ulonglong2*>(hsg + i * L_HLD + (j * 16 + ks) * 4);
+            const ulonglong2 hv = *reinterpret_cast<const ulonglong2*>(hsg + i * L_HLD + (j * G::KS + ks) * 4);
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
               asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2[r][i]) : "l"(w2[r][j][0]), "l"(hv.x));
@@ -169,8 +183,9 @@ lstm_recurrent_kernel(const LstmParams p) {
             acc[r][i] = __uint_as_float((unsigned int)(acc2[r][i] & 0xffffffffull)) + __uint_as_float((unsigned int)(acc2[r][i] >> 32));
         __syncwarp();
         if (lane == 0) mbar_arrive(h_empty(st));   // this warp is done reading the ring slot
-        // butterfly over the 16 k splits (lanes ks): after 4 exchange steps lane ks holds the complete sum of
-        // value index ks (= r * 4 + i) -- 15 shuffles instead of 64
+        // butterfly over 16 k splits: after 4 exchange steps lane (ks & 15) holds the sum over those 16 lanes of value
+        // index ks & 15 (= r * 4 + i) -- 15 shuffles instead of 64; with 32 k splits (H = 1024) one more exchange
+        // adds the two halves
         float v16[16];
 #pragma unroll
         for (int r = 0; r < 4; ++r)
@@ -179,7 +194,7 @@ lstm_recurrent_kernel(const LstmParams p) {
 #pragma unroll
         for (int step = 0; step < 4; ++step) {
           const int m = 8 >> step;
-          const bool upper = (ks & m) != 0;      // lanes with the bit set keep values [m, 2m), the others [0, m)
+          const bool upper = (lane & m) != 0;    // lanes with the bit set keep values [m, 2m), the others [0, m)
 #pragma unroll
           for (int k = 0; k < m; ++k) {
             const float send = upper ? v16[k] : v16[k + m];
@@ -187,10 +202,13 @@ lstm_recurrent_kernel(const LstmParams p) {
             v16[k] = (upper ? v16[k + m] : v16[k]) + recv;
           }
         }
+        if (G::KS == 32) v16[0] += __shfl_xor_sync(0xffffffffu, v16[0], 16);
         const int team = sg % L_TEAMS;
         mbar_wait(g_empty(team), (team_use[team] & 1u) ^ 1u);   // the team has consumed its previous gates
-        // lane ks holds value index ks: row r = ks >> 2 of the row group, item i = ks & 3
-        gs[team * (L_SB * 64) + (ks & 3) * 64 + gate * 16 + uq * 4 + (ks >> 2)] = v16[0];
+        // lane holds value index vi = lane & 15: row r = vi >> 2 of the row group, item i = vi & 3
+        const int vi = lane & 15;
+        if (G::KS == 16 || lane < 16)
+          gs[team * (L_SB * GROW) + (vi & 3) * GROW + gate * L_UNITS + uq * 4 + (vi >> 2)] = v16[0];
         __syncwarp();
         if (lane == 0) mbar_arrive(g_full(team));
         ++team_use[team];
@@ -205,13 +223,13 @@ lstm_recurrent_kernel(const LstmParams p) {
       for (int sg = team; sg < n_sub; sg += L_TEAMS, ++use) {
         const int b0 = b_first + sg * L_SB;
         // this lane's two (item, unit) pairs; their pre-gates / skip inputs do not depend on the recurrence
-        float pg[2][4], skipv[2];
-        bool valid[2];
+        float pg[G::PAIRS][4], skipv[G::PAIRS];
+        bool valid[G::PAIRS];
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
+        for (int e = 0; e < G::PAIRS; ++e) {
           const int pi = lane + 32 * e;
-          const int bg = b0 + (pi >> 4);
-          const int unit = ub * L_UNITS + (pi & 15);
+          const int bg = b0 + pi / L_UNITS;
+          const int unit = ub * L_UNITS + pi % L_UNITS;
           valid[e] = bg < p.B;
           skipv[e] = 0.f;
 #pragma unroll
@@ -224,17 +242,17 @@ lstm_recurrent_kernel(const LstmParams p) {
           }
         }
         mbar_wait(g_full(team), use & 1u);
-        const float* g4 = gs + team * (L_SB * 64);
+        const float* g4 = gs + team * (L_SB * GROW);
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
+        for (int e = 0; e < G::PAIRS; ++e) {
           const int pi = lane + 32 * e;
-          const int ci = pi >> 4, cu = pi & 15;
+          const int ci = pi / L_UNITS, cu = pi % L_UNITS;
           const int bg = b0 + ci;
           const int unit = ub * L_UNITS + cu;
-          const float gi = sigmoidf_acc(pg[e][0] + g4[ci * 64 + 0 * 16 + cu]);
-          const float gf = sigmoidf_acc(pg[e][1] + g4[ci * 64 + 1 * 16 + cu]);
-          const float gg = tanhf(pg[e][2] + g4[ci * 64 + 2 * 16 + cu]);
-          const float go = sigmoidf_acc(pg[e][3] + g4[ci * 64 + 3 * 16 + cu]);
+          const float gi = sigmoidf_acc(pg[e][0] + g4[ci * GROW + 0 * L_UNITS + cu]);
+          const float gf = sigmoidf_acc(pg[e][1] + g4[ci * GROW + 1 * L_UNITS + cu]);
+          const float gg = tanhf(pg[e][2] + g4[ci * GROW + 2 * L_UNITS + cu]);
+          const float go = sigmoidf_acc(pg[e][3] + g4[ci * GROW + 3 * L_UNITS + cu]);
           if (valid[e]) {
             float* cptr = cs + (sg * L_SB + ci) * L_UNITS + cu;
             const float c_new = gf * (*cptr) + gi * gg;
@@ -271,11 +289,11 @@ lstm_recurrent_kernel(const LstmParams p) {
       const int b0 = b_first + sg * L_SB;
       if (t == 0) {
         for (int f = lane; f < L_SB * (LH / 4); f += 32)
-          *reinterpret_cast<float4*>(dst + (f >> 7) * L_HLD + (f & 127) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+          *reinterpret_cast<float4*>(dst + (f / (LH / 4)) * L_HLD + (f % (LH / 4)) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
         mbar_arrive(h_full(st));
       } else {
         if (lane == 0) {
-          // all 32 unit blocks have published h_{t-1} of this sub-group once the counter reaches 32 t
+          // all unit blocks have published h_{t-1} of this sub-group once the counter reaches UB * t
           const unsigned int target = (unsigned int)L_UB * (unsigned int)t;
           unsigned int v, spins = 0;
           do {
@@ -285,8 +303,8 @@ lstm_recurrent_kernel(const LstmParams p) {
         }
         __syncwarp();
         for (int f = lane; f < L_SB * (LH / 4); f += 32) {
-          const float* src = hprev + (long long)(b0 + (f >> 7)) * LH + (f & 127) * 4;
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst + (f >> 7) * L_HLD + (f & 127) * 4)),
+          const float* src = hprev + (long long)(b0 + f / (LH / 4)) * LH + (f % (LH / 4)) * 4;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(dst + (f / (LH / 4)) * L_HLD + (f % (LH / 4)) * 4)),
                        "l"(src)
                        : "memory");
         }
@@ -296,35 +314,28 @@ lstm_recurrent_kernel(const LstmParams p) {
   }
 }
 
+template <int LH>
 size_t lstm_smem_bytes(int q_items) {
-  return sizeof(float) * (size_t)(L_STAGES * L_SB * L_HLD + L_TEAMS * L_SB * 64 + q_items * L_UNITS) +
+  using G = Geo<LH>;
+  return sizeof(float) * (size_t)(L_STAGES * L_SB * G::HLD + L_TEAMS * L_SB * G::GROW + q_items * G::UNITS) +
          8 * (2 * L_STAGES + 2 * L_TEAMS);
 }
 
-int quarter_items(int batch) {
-  const int per = (batch + L_NQ - 1) / L_NQ;
+int group_items(int batch, int nq) {
+  const int per = (batch + nq - 1) / nq;
   return (per + L_SB - 1) / L_SB * L_SB;
 }
 
-}  // namespace
-
-// 2 x B_pad x H state + one counter per sub-group
-int lstm_recurrent_workspace_floats(int batch) {
-  const int qi = quarter_items(batch);
-  return 2 * L_NQ * qi * LH + L_NQ * qi / L_SB + 64;
-}
-
-int launch_lstm_recurrent(const float* pre, const float* w_hh, const float* skip, long long skip_item_stride, float* out,
-                          long long out_item_stride, int batch, int T, int H, int out_elu, float* workspace,
-                          cudaStream_t s) {
-  ECB_REQUIRE(H == LH, "lstm: hidden size %d unsupported (only %d)", H, LH);
-  ECB_REQUIRE(batch > 0 && T > 0, "lstm: bad batch %d / T %d", batch, T);
-  const int qi = quarter_items(batch);
-  const size_t smem = lstm_smem_bytes(qi);
+template <int LH>
+int launch_impl(const float* pre, const float* w_hh, const float* skip, long long skip_item_stride, float* out,
+                long long out_item_stride, int batch, int T, int out_elu, float* workspace, cudaStream_t s) {
+  using G = Geo<LH>;
+  const int qi = group_items(batch, G::NQ);
+  const size_t smem = lstm_smem_bytes<LH>(qi);
   ECB_REQUIRE(smem <= 200 * 1024, "lstm: batch %d needs %zu bytes of shared memory; split the batch", batch, smem);
   static bool attr_set = false;
   if (!attr_set) {
-    ECB_CUDA(cudaFuncSetAttribute(lstm_recurrent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    ECB_CUDA(cudaFuncSetAttribute(lstm_recurrent_kernel<LH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
   LstmParams p;
@@ -335,18 +346,36 @@ int launch_lstm_recurrent(const float* pre, const float* w_hh, const float* skip
   p.skip_stride = skip_item_stride ? skip_item_stride : (long long)T * LH;
   p.out_stride = out_item_stride ? out_item_stride : (long long)T * LH;
   p.hbuf = workspace;
-  p.cnt = reinterpret_cast<unsigned int*>(workspace + 2LL * L_NQ * qi * LH);
+  p.cnt = reinterpret_cast<unsigned int*>(workspace + 2LL * G::NQ * qi * LH);
   p.B = batch;
   p.T = T;
   p.out_elu = out_elu;
   p.q_items = qi;
-  ECB_CUDA(cudaMemsetAsync(p.cnt, 0, sizeof(unsigned int) * (size_t)(L_NQ * qi / L_SB + 64), s));
+  ECB_CUDA(cudaMemsetAsync(p.cnt, 0, sizeof(unsigned int) * (size_t)(G::NQ * qi / L_SB + 64), s));
   const double bt = (double)batch * T;
-  ProfScope prof(PROF_LSTM_REC, s, 2.0 * bt * 4 * H * H, 4.0 * (bt * 4 * H + bt * H * (skip ? 2 : 1) + 4.0 * H * H));
+  ProfScope prof(PROF_LSTM_REC, s, 2.0 * bt * 4 * LH * LH, 4.0 * (bt * 4 * LH + bt * LH * (skip ? 2 : 1) + 4.0 * LH * LH));
   void* args[] = {(void*)&p};
-  ECB_CUDA(cudaLaunchCooperativeKernel((void*)lstm_recurrent_kernel, dim3(L_CTAS), dim3(L_THREADS), args, smem, s));
+  ECB_CUDA(cudaLaunchCooperativeKernel((void*)lstm_recurrent_kernel<LH>, dim3(L_CTAS), dim3(L_THREADS), args, smem, s));
   ECB_LAUNCHED();
   return 0;
+}
+
+}  // namespace
+
+// 2 x B_pad x H state + one counter per sub-group
+int lstm_recurrent_workspace_floats(int batch, int H) {
+  const int nq = H == 1024 ? Geo<1024>::NQ : Geo<512>::NQ;
+  const int qi = group_items(batch, nq);
+  return 2 * nq * qi * H + nq * qi / L_SB + 64;
+}
+
+int launch_lstm_recurrent(const float* pre, const float* w_hh, const float* skip, long long skip_item_stride, float* out,
+                          long long out_item_stride, int batch, int T, int H, int out_elu, float* workspace,
+                          cudaStream_t s) {
+  ECB_REQUIRE(H == 512 || H == 1024, "lstm: hidden size %d unsupported (512 or 1024)", H);
+  ECB_REQUIRE(batch > 0 && T > 0, "lstm: bad batch %d / T %d", batch, T);
+  if (H == 512) return launch_impl<512>(pre, w_hh, skip, skip_item_stride, out, out_item_stride, batch, T, out_elu, workspace, s);
+  return launch_impl<1024>(pre, w_hh, skip, skip_item_stride, out, out_item_stride, batch, T, out_elu, workspace, s);
 }
 
 }  // namespace ecb

@@ -34,11 +34,13 @@ extern "C" {
 typedef struct ecb_spec {
   int32_t channels;             /* audio channels, 1 or 2 */
   int32_t causal;               /* 1: causal padding/trim rules, 0: asymmetric (conv.py:211-219,252-262) */
-  int32_t group_norm;           /* 0: weight_norm (folded at load), 1: time_group_norm = GroupNorm(1, C) */
+  int32_t group_norm;           /* norm after every conv (conv.py:38-52): 0 weight_norm (folded at load, Identity norm),
+                                 * 1 time_group_norm = GroupNorm(1, C), 2 layer_norm = ConvLayerNorm (norm.py:16-30) */
   int32_t n_filters;            /* 32 */
-  int32_t dimension;            /* latent dimension, 128 */
+  int32_t dimension;            /* latent dimension, 128 (EnCodec) or 256 (the fork's 10 Hz models) */
   int32_t n_ratios;             /* number of up/down-sampling stages */
-  int32_t ratios[ECB_MAX_RATIOS]; /* decoder order, e.g. {8,5,4,2}; the encoder uses them reversed */
+  int32_t ratios[ECB_MAX_RATIOS]; /* decoder order, e.g. {8,5,4,2} or the fork's {6,5,5,2,1}; the encoder uses them reversed.
+                                   * n_filters * 2^n_ratios (the LSTM width) must be 512 or 1024 */
   int32_t kernel_size;          /* 7 */
   int32_t last_kernel_size;     /* 7 */
   int32_t residual_kernel_size; /* 3 */

@@ -21,7 +21,7 @@ def _oracle_elu(x):
     return orc.elu(x.astype(np.float32))
 
 
-@pytest.mark.parametrize("name", gc.MODEL_CASES + gc.FORK_CASES[:1])
+@pytest.mark.parametrize("name", gc.MODEL_CASES + gc.FORK_CASES)
 def test_encoder_stages_match_oracle(name):
     """Every stage of the encoder stack against the oracle's taps (first segment only, for speed)."""
     case = gc.load_model_case(name)
@@ -60,7 +60,7 @@ def test_encoder_stages_match_oracle(name):
     assert emb.shape == (bsz, spec.dimension, -(-seg // spec.hop_length))
 
 
-@pytest.mark.parametrize("name", gc.MODEL_CASES + gc.FORK_CASES[:1])
+@pytest.mark.parametrize("name", gc.MODEL_CASES + gc.FORK_CASES)
 def test_decoder_stages_match_oracle(name):
     case = gc.load_model_case(name)
     spec = case["spec"]
@@ -91,7 +91,7 @@ def test_decoder_stages_match_oracle(name):
     assert np.abs(out - out_o).max() < 1e-4
 
 
-@pytest.mark.parametrize("name", gc.MODEL_CASES + gc.FORK_CASES[:1])
+@pytest.mark.parametrize("name", gc.MODEL_CASES + gc.FORK_CASES)
 def test_forward_matches_reference_golden(name):
     """EncodecModel.forward against the unmodified reference's outputs (BASELINE configs and, SURVEY 8f row 3, the fork's own
     10 Hz layer_norm configuration)."""
