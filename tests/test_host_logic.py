@@ -14,7 +14,8 @@ def _model(spec, **kw):
                                       name="unset", ratios=spec.ratios, bins=spec.bins, dimension=spec.dimension, **kw)
 
 
-@pytest.mark.parametrize("spec", [synth.spec_24khz(), synth.spec_48khz()], ids=["24k", "48k"])
+@pytest.mark.parametrize("spec", [synth.spec_24khz(), synth.spec_48khz(), synth.spec_fork10hz(), synth.spec_fork10hz((5, 5, 4, 1))],
+                         ids=["24k", "48k", "fork10hz", "fork10hz_4ratios"])
 def test_state_dict_layout_matches_reference(spec):
     """synth.make_state_dict was loaded with strict=True into the reference (oracle/make_golden.py); the
     drop-in must accept exactly the same keys and shapes."""
@@ -26,7 +27,10 @@ def test_state_dict_layout_matches_reference(spec):
         assert tuple(own[k].shape) == tuple(v.shape), k
     res = m.load_state_dict({k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in sd.items()}, strict=True)
     assert not res.missing_keys and not res.unexpected_keys
-    assert len(sd) == (251 if spec.channels == 1 else 222)  # SURVEY.md section 8b [measured]
+    if spec.norm != "layer_norm":
+        assert len(sd) == (251 if spec.channels == 1 else 222)  # SURVEY.md section 8b [measured]
+    else:   # the fork's configs: frame rate 1 Hz, 0.08 kbps -> 8 codebooks; hop 300 (or 100)
+        assert (m.frame_rate, m.n_q, m.encoder.hop_length) == (1, 8, int(np.prod(spec.ratios)))
 
 
 def test_shared_codebook_aliases_like_the_fork():
