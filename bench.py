@@ -67,6 +67,37 @@ def read_peaks():
     return dict(hbm_gbs=6650.0, tflops=1400.0, source="fallback")
 
 
+def measure_tf32_peak(dev, seconds=0.4):
+    """Dense TF32 GEMM rate of this GPU (cuBLAS through torch, 8192^3, run for ~`seconds`): the denominator for the
+    3xTF32 kernels -- MEASURED_PEAKS.json holds the bf16 figure only ('TF32 peak ... measure it')."""
+    import torch
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a = torch.randn(n, n, device=dev)
+        b = torch.randn(n, n, device=dev)
+        c = torch.empty(n, n, device=dev)
+        for _ in range(3):
+            torch.matmul(a, b, out=c)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 0
+        e0.record()
+        t0 = time.perf_counter()
+        while True:
+            for _ in range(5):
+                torch.matmul(a, b, out=c)
+            reps += 5
+            if time.perf_counter() - t0 > seconds and reps >= 20:
+                break
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return 2.0 * n ** 3 * reps / (e0.elapsed_time(e1) * 1e-3) / 1e12
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clocks and throttle reasons through NVML while the timed region runs."""
 
@@ -384,9 +415,20 @@ def main():
                     "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
                     "share_of_step": v["ms"] / total_ms}
 
+        tf32_peak = measure_tf32_peak(dev)
+
+        def tf32_view(alg_tflops):
+            return {"bound": "tensor_tf32", "achieved": 3.0 * alg_tflops, "peak": tf32_peak, "unit": "TFLOP/s",
+                    "frac": 3.0 * alg_tflops / tf32_peak,
+                    "note": "executed TF32 products (3 per algorithmic multiply-add: a_hi*w_hi, a_hi*w_lo, a_lo*w_hi) against "
+                            "the dense TF32 GEMM rate measured in this run (cuBLAS 8192^3 through torch)"}
+
         rooflines = {}
         if top_name:
             rooflines = {name: roof(name) for name in prof if prof[name]["ms"] / total_ms >= 0.02}
+            for name in ("tc_conv_wide", "rvq_encode"):
+                if name in rooflines:
+                    rooflines[name]["tf32"] = tf32_view(rooflines[name]["achieved"])
             # The dominant KERNEL is tc_conv_kernel (one template, profiled as two classes by channel width); its roofline
             # is taken over all of its launches, against the roof it sits closer to.
             tc = [n for n in ("tc_conv_narrow", "tc_conv_wide") if n in prof]
@@ -429,7 +471,7 @@ def main():
                                       "api": "encodec_b200.pipeline.HostPipeline(model, depth=2).run(pinned host batches)",
                                       "single_stream_ms_per_step": ms_e2e_serial / args.steps},
             "gpu_launches": launches, "roofline": roofline, "rooflines": rooflines, "kernels": breakdown,
-            "cpu_baseline": cpu_baseline, "host_link": pcie, "variants": variants,
+            "cpu_baseline": cpu_baseline, "host_link": pcie, "variants": variants, "tf32_gemm_tflops_measured": tf32_peak,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
