@@ -446,6 +446,9 @@ def main():
                        "note": "algorithmic bytes: activations and weights read once, outputs written once; ncu DRAM traffic "
                                "of the <=64-channel launches equals the algorithmic bytes (profiles/r01_tc_res32b1_ncu.txt); "
                                "the >=128-channel launches run at 66 % tensor-pipe activity (profiles/r01_tc_down256_ncu.txt)"}
+                if "tc_conv_wide" in rooflines:
+                    hbm["wide_launches_tf32"] = rooflines["tc_conv_wide"].get("tf32")
+                    hbm["narrow_launches_hbm_frac"] = rooflines.get("tc_conv_narrow", {}).get("frac")
                 roofline = hbm
             else:
                 roofline = roof(top_name)
