@@ -6,11 +6,11 @@
 // per block (X and ELU(X) written by the producer, ELU(X) read, H written and read, X read, Y written); this level holds
 // a third of the codec's activation bytes. Fused, the block reads X once and writes Y once:
 //   * warp 0 TMA-loads the raw X tile ([128 + 8 rows x 32 ch], halo-padded input, so the 3 taps are row shifts of it),
-//   * warps 2-5 turn it into the tensor-core operands in shared memory: x_lo, e = ELU(x), e_lo (split-operand TF32),
+//   * warps 2-9 turn it into the tensor-core operands in shared memory: x_lo, e = ELU(x), e_lo (split-operand TF32),
 //   * warp 1 issues GEMM 1 (3 taps x 4 K steps, [W1_hi | W1_lo] and the a_lo correction) into TMEM,
-//   * warps 6-9 read it back, add the bias, apply ELU and write H / H_lo to shared memory as the A operand of GEMM 2,
+//   * warps 10-13 read it back, add the bias, apply ELU and write H / H_lo to shared memory as the A operand of GEMM 2,
 //   * warp 1 issues GEMM 2: H * W3 + X * Ws (the shortcut reads the SAME X tile, shifted by the conv's left padding),
-//   * warps 10-13 read the result, add the biases, apply ELU and store Y (plus its reflected halo rows).
+//   * warps 14-17 read the result, add the biases, apply ELU and store Y (plus its reflected halo rows).
 // Both weight matrices (28 KB as hi/lo K-major tiles) stay resident in shared memory for the whole kernel; raw X tiles sit
 // in a 3-deep TMA ring, the processed operands and both TMEM accumulators are double-buffered, so loads run ahead and
 // GEMM 1 of tile i+1 runs while tile i is between its two GEMMs.
@@ -34,7 +34,7 @@ constexpr int W1CH = 2 * RH * RC * 4;     // one block.1 weight chunk: hi tile [
 constexpr int WCCH = 2 * RC * RC * 4;     // one [block.3 ; shortcut] chunk: hi tile [32 x 32] + lo tile = 8192 B
 constexpr int NRAW = 3;                   // raw X ring (TMA runs this many tiles ahead of GEMM 2)
 constexpr int P_STAGE = 3 * XT;           // processed stage: x_lo | e | e_lo
-constexpr int R_THREADS = 448;
+constexpr int R_THREADS = 576;   // 18 warps: producer, MMA issuer, 8 transform, 4 mid-epilogue, 4 final-epilogue
 constexpr int OFF_P = NRAW * XT;                    // 2 processed stages
 constexpr int OFF_H = OFF_P + 2 * P_STAGE;          // H | H_lo
 constexpr int OFF_W = OFF_H + 2 * HT;               // 3 chunks of W1, 2 chunks of Wcat
@@ -84,7 +84,7 @@ tc_res_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
       mbar_init(xr_empty(r), 1);
     }
     for (int s = 0; s < 2; ++s) {
-      mbar_init(p_ready(s), 4);
+      mbar_init(p_ready(s), 8);
       mbar_init(p_empty(s), 1);
       mbar_init(a1_full(s), 1);
       mbar_init(a1_empty(s), 4);
@@ -204,9 +204,10 @@ tc_res_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
       if (sel == 2) gemm2(i2++);
       else if (sel == 1) gemm1(i1++);
     }
-  } else if (warp < 6) {
+  } else if (warp < 10) {
     // ================================ transform: x -> x_lo, e = ELU(x), e_lo ================================
-    const int tt = threadIdx.x - 64;   // 0..127
+    // eight warps: the transform is the longest stage of the per-tile chain (ELU + two operand splits per element)
+    const int tt = threadIdx.x - 64;   // 0..255
     for (int i = 0; i < n_my; ++i) {
       const int s = i & 1;
       const int r = i % NRAW;
@@ -222,19 +223,19 @@ tc_res_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
       };
       // three float4 per step: their 12 ELUs run interleaved (elu_vec) instead of as 12 serial dependency chains
 #pragma unroll 1
-      for (int q0 = tt; q0 < XT / 16; q0 += 3 * 128) {
+      for (int q0 = tt; q0 < XT / 16; q0 += 3 * 256) {
         float4 v[3];
         float e[12];
 #pragma unroll
         for (int u = 0; u < 3; ++u) {
-          const int q = q0 + u * 128;
+          const int q = q0 + u * 256;
           v[u] = q < XT / 16 ? xr[q] : make_float4(0.f, 0.f, 0.f, 0.f);
           e[u * 4 + 0] = v[u].x; e[u * 4 + 1] = v[u].y; e[u * 4 + 2] = v[u].z; e[u * 4 + 3] = v[u].w;
         }
         elu_vec<12>(e);
 #pragma unroll
         for (int u = 0; u < 3; ++u) {
-          const int q = q0 + u * 128;
+          const int q = q0 + u * 256;
           if (q < XT / 16) {
             const float4 ev = make_float4(e[u * 4 + 0], e[u * 4 + 1], e[u * 4 + 2], e[u * 4 + 3]);
             xl[q] = split4(v[u]);
@@ -247,7 +248,7 @@ tc_res_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
       __syncwarp();
       if (lane == 0) mbar_arrive(p_ready(s));
     }
-  } else if (warp < 10) {
+  } else if (warp < 14) {
     // ================================ mid epilogue: GEMM 1 -> H = ELU(. + b1) as the A operand of GEMM 2 ================================
     const int quad = warp & 3;
     const int r = quad * 32 + lane;   // tile row of this thread (= TMEM lane)
@@ -291,7 +292,7 @@ tc_res_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
     // ================================ final epilogue: GEMM 2 -> Y = ELU(. + b3 + bs) -> global ================================
     const int quad = warp & 3;
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16);
-    uint8_t* slot = sg + OFF_STG + (warp - 10) * 2048;   // [32 rows x 64 B]
+    uint8_t* slot = sg + OFF_STG + (warp - 14) * 2048;   // [32 rows x 64 B]
     for (int i = 0; i < n_my; ++i) {
       const int tile = blockIdx.x + i * gridDim.x;
       const int mt = tile % p.tiles_m;
