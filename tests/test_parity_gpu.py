@@ -373,3 +373,26 @@ def test_host_pipeline_matches_direct_forward():
         assert torch.equal(a, wa) and torch.equal(c, wc)
     with pytest.raises(ValueError):
         list(HostPipeline(m).run([batches[0].cuda()]))
+
+
+@pytest.mark.parametrize("length", [1, 5, 319, 321, 2000, 10239, 10240, 10241])
+def test_short_and_threshold_lengths_match_oracle(length):
+    """Inputs shorter than a kernel's padding (the reference zero-extends before reflecting, conv.py:88-95), a single latent
+    frame, and the lengths either side of the switch between the CUDA-core path (< 32 latent frames) and the tensor-core
+    path: codes and audio against the oracle."""
+    from encodec_b200 import synth
+    case = gc.load_model_case("24k_24kbps_ragged")
+    spec = case["spec"]
+    m = ug.build_model(spec, case["sd"], 6.0, case["distinct"])
+    xn = synth.make_audio(900 + length, 2, 1, length)
+    audio, codes, _, _ = m(torch.from_numpy(xn).cuda())
+    o_audio, o_codes, o_frames = orc.forward(xn, case["sd"], spec, 6.0, np.float32)
+    assert audio.shape == (2, 1, length) and tuple(codes.shape) == o_codes.shape
+    n_q = o_codes.shape[1]
+    score = orc.score_codes(gc.frames_of(o_frames[0]["emb"]), orc.codebooks_from_state_dict(case["sd"], n_q),
+                            np.transpose(o_codes, (1, 0, 2)).reshape(n_q, -1),
+                            np.transpose(codes.cpu().numpy(), (1, 0, 2)).reshape(n_q, -1))
+    assert score["hard"] == 0, (length, score)
+    if score["mismatched"] == 0:
+        d = np.abs(audio.cpu().numpy() - o_audio)
+        assert d.max() < AUDIO_MAX_ABS and np.sqrt((d ** 2).mean()) < AUDIO_RMS, (length, d.max())
