@@ -42,7 +42,8 @@ struct Geo {
   static constexpr int UQ = UNITS / 4;            // unit quads per gate
   static constexpr int UB = LH / UNITS;           // unit blocks (32 | 128)
   static constexpr int NQ = L_CTAS / UB;          // batch groups (4 | 1)
-  static constexpr int HLD = LH + 4;              // padded h row in smem (floats)
+  static constexpr int HLD = LH;                  // h row in smem (floats): unpadded, so that lanes reading different items
+                                                  // at the same k offset still hit distinct banks (see the slot permutation)
   static constexpr int GROW = 4 * UNITS;          // gate values per item in the gs exchange
   static constexpr int PAIRS = L_SB * UNITS / 32; // (item, unit) pairs per cell-team lane (2 | 1)
 };
@@ -140,10 +141,15 @@ lstm_recurrent_kernel(const LstmParams p) {
     const int uq = rg % G::UQ;
     // weights as packed fp32 pairs (k, k+1): the dot products run on fma.rn.f32x2 (two FMAs per issue slot), which
     // keeps even-k and odd-k partial sums in the two halves of a 64-bit accumulator
+    // Slot permutation: accumulator slot (rs, is) of this lane works on row rs ^ pr and item is ^ pi with (pr, pi) taken
+    // from the lane index. The transposing butterfly below then needs no selects: at exchange distance m every lane
+    // keeps its lower slots and sends its upper slots, because the partner's upper slots hold exactly the logical
+    // values of this lane's lower slots.
+    const int pr = (lane >> 2) & 3, pi = lane & 3;
     unsigned long long w2[4][8][2];
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-      const float* wr = p.w_hh + ((long long)gate * LH + ub * L_UNITS + uq * 4 + r) * LH;
+      const float* wr = p.w_hh + ((long long)gate * LH + ub * L_UNITS + uq * 4 + (r ^ pr)) * LH;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(wr + (j * G::KS + ks) * 4));
@@ -167,7 +173,7 @@ lstm_recurrent_kernel(const LstmParams p) {
         for (int i = 0; i < L_SB; ++i) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const ulonglong2 hv = *reinterpret_cast<const ulonglong2*>(hsg + i * L_HLD + (j * G::KS + ks) * 4);
+            const ulonglong2 hv = *reinterpret_cast<const ulonglong2*>(hsg + (i ^ pi) * L_HLD + (j * G::KS + ks) * 4);
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
               asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2[r][i]) : "l"(w2[r][j][0]), "l"(hv.x));
@@ -183,9 +189,9 @@ lstm_recurrent_kernel(const LstmParams p) {
             acc[r][i] = __uint_as_float((unsigned int)(acc2[r][i] & 0xffffffffull)) + __uint_as_float((unsigned int)(acc2[r][i] >> 32));
         __syncwarp();
         if (lane == 0) mbar_arrive(h_empty(st));   // this warp is done reading the ring slot
-        // butterfly over 16 k splits: after 4 exchange steps lane (ks & 15) holds the sum over those 16 lanes of value
-        // index ks & 15 (= r * 4 + i) -- 15 shuffles instead of 64; with 32 k splits (H = 1024) one more exchange
-        // adds the two halves
+        // butterfly over 16 k splits: after 4 exchange steps slot 0 of lane l holds the sum over those 16 lanes of the
+        // logical value index l & 15 (= row * 4 + item) -- 15 shuffles instead of 64; with 32 k splits (H = 1024) one
+        // more exchange adds the two halves
         float v16[16];
 #pragma unroll
         for (int r = 0; r < 4; ++r)
@@ -194,13 +200,8 @@ lstm_recurrent_kernel(const LstmParams p) {
 #pragma unroll
         for (int step = 0; step < 4; ++step) {
           const int m = 8 >> step;
-          const bool upper = (lane & m) != 0;    // lanes with the bit set keep values [m, 2m), the others [0, m)
 #pragma unroll
-          for (int k = 0; k < m; ++k) {
-            const float send = upper ? v16[k] : v16[k + m];
-            const float recv = __shfl_xor_sync(0xffffffffu, send, m);
-            v16[k] = (upper ? v16[k + m] : v16[k]) + recv;
-          }
+          for (int k = 0; k < m; ++k) v16[k] += __shfl_xor_sync(0xffffffffu, v16[k + m], m);
         }
         if (G::KS == 32) v16[0] += __shfl_xor_sync(0xffffffffu, v16[0], 16);
         const int team = sg % L_TEAMS;
