@@ -446,6 +446,14 @@ def main():
                        "note": "algorithmic bytes: activations and weights read once, outputs written once; ncu DRAM traffic "
                                "of the <=64-channel launches equals the algorithmic bytes (profiles/r01_tc_res32b1_ncu.txt); "
                                "the >=128-channel launches run at 66 % tensor-pipe activity (profiles/r01_tc_down256_ncu.txt)"}
+                hbm["traffic_evidence"] = {
+                    "note": "ncu --set full DRAM bytes of single launches of this build's kernels (profiles/), per launch",
+                    "tc_conv_kernel<32,3> res32.b1 (64 x 240000 rows)": {"dram_bytes": 1.966e9 + 1.928e9, "algorithmic_bytes": 3.93e9,
+                                                                          "file": "profiles/r01_tc_res32b1_ncu.txt"},
+                    "tc_conv_kernel<128,3> down256 (64 x 6000 rows)": {"dram_bytes": 0.56e9, "algorithmic_bytes": 0.55e9,
+                                                                        "file": "profiles/r01_tc_down256_ncu.txt"},
+                    "tc_res_kernel (64 x 240000 rows)": {"dram_bytes": 1.966e9 + 1.923e9, "algorithmic_bytes": 3.93e9,
+                                                         "file": "profiles/r01_tc_res_fused_ncu.txt"}}
                 if "tc_conv_wide" in rooflines:
                     hbm["wide_launches_tf32"] = rooflines["tc_conv_wide"].get("tf32")
                     hbm["narrow_launches_hbm_frac"] = rooflines.get("tc_conv_narrow", {}).get("frac")

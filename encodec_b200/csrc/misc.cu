@@ -295,27 +295,47 @@ ln_apply_kernel(const GnSrc a, const GnSrc b, int has_b, float* __restrict__ out
       x[v].w = x[v].w * rstd * g[v].w + be[v].w;
     }
   };
-  for (long long r0 = warp * RPW; r0 < rows; r0 += n_warps * RPW) {
-    const long long r = r0 + sub;
-    const bool live = r < rows;   // whole sub-groups go idle together, the shuffles below stay inside a sub-group
-    float4 x[V], y[V];
+  // U independent row groups per warp step (more for narrow rows): their loads are issued together
+  constexpr int U = V >= 4 ? 1 : (V == 2 ? 2 : 4);
+  for (long long r0 = warp * (RPW * U); r0 < rows; r0 += n_warps * (RPW * U)) {
+    float4 x[U][V], y[U][V];
+    bool live[U];
 #pragma unroll
-    for (int v = 0; v < V; ++v) {
-      x[v] = live ? __ldcs(reinterpret_cast<const float4*>(xa + r * C) + li + v * LPR) : make_float4(0.f, 0.f, 0.f, 0.f);
-      if (has_b) y[v] = live ? __ldcs(reinterpret_cast<const float4*>(xb + r * C) + li + v * LPR) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int u = 0; u < U; ++u) {
+      const long long r = r0 + u * RPW + sub;
+      live[u] = r < rows;   // whole sub-groups go idle together, the shuffles below stay inside a sub-group
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        x[u][v] = live[u] ? __ldcs(reinterpret_cast<const float4*>(xa + r * C) + li + v * LPR) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (has_b)
+          y[u][v] = live[u] ? __ldcs(reinterpret_cast<const float4*>(xb + r * C) + li + v * LPR) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
-    normalise(x, ga, ba);
-    if (has_b) {
-      normalise(y, gb, bb);
 #pragma unroll
-      for (int v = 0; v < V; ++v) { x[v].x += y[v].x; x[v].y += y[v].y; x[v].z += y[v].z; x[v].w += y[v].w; }
+    for (int u = 0; u < U; ++u) {
+      normalise(x[u], ga, ba);
+      if (has_b) {
+        normalise(y[u], gb, bb);
+#pragma unroll
+        for (int v = 0; v < V; ++v) { x[u][v].x += y[u][v].x; x[u][v].y += y[u][v].y; x[u][v].z += y[u][v].z; x[u][v].w += y[u][v].w; }
+      }
     }
-    if (!live) continue;
 #pragma unroll
-    for (int v = 0; v < V; ++v) {
-      if (o_raw) *(reinterpret_cast<float4*>(o_raw + r * C) + li + v * LPR) = x[v];
-      if (o_elu)
-        *(reinterpret_cast<float4*>(o_elu + r * C) + li + v * LPR) = make_float4(elu1(x[v].x), elu1(x[v].y), elu1(x[v].z), elu1(x[v].w));
+    for (int u = 0; u < U; ++u) {
+      if (!live[u]) continue;
+      const long long r = r0 + u * RPW + sub;
+      float e[4 * V];
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        if (o_raw) *(reinterpret_cast<float4*>(o_raw + r * C) + li + v * LPR) = x[u][v];
+        e[4 * v + 0] = x[u][v].x; e[4 * v + 1] = x[u][v].y; e[4 * v + 2] = x[u][v].z; e[4 * v + 3] = x[u][v].w;
+      }
+      if (o_elu) {
+        elu_vec<4 * V>(e);
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+          *(reinterpret_cast<float4*>(o_elu + r * C) + li + v * LPR) = make_float4(e[4 * v + 0], e[4 * v + 1], e[4 * v + 2], e[4 * v + 3]);
+      }
     }
   }
 }
@@ -436,8 +456,10 @@ int launch_ln_apply2(const GnSrc& a, const GnSrc* b, float* out_raw, float* out_
                      long long rows, int C, int c_real, float eps, cudaStream_t s) {
   ECB_REQUIRE((out_raw || out_elu) && c_real >= 1 && c_real <= C, "ln_apply: bad argument (C=%d, real %d)", C, c_real);
   const int lpr = C / 4 < 32 ? C / 4 : 32;
-  const long long warps = cdiv(rows, 32 / lpr);
-  dim3 grid((unsigned)min(cdiv(warps, 8), 2048LL), (unsigned)n_items);
+  const int vv = C / (4 * lpr);
+  const int uu = vv >= 4 ? 1 : (vv == 2 ? 2 : 4);
+  const long long warps = cdiv(rows, (32 / lpr) * uu);
+  dim3 grid((unsigned)min(cdiv(warps, 8), 4096LL), (unsigned)n_items);
   ProfScope prof(PROF_GN_APPLY, s, 0.0,
                  4.0 * (double)rows * C * n_items * ((b ? 2 : 1) + (out_raw ? 1 : 0) + (out_elu ? 1 : 0)));
   const GnSrc bb = b ? *b : a;
