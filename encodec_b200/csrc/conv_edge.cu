@@ -108,7 +108,8 @@ conv_in_kernel(const ConvInParams p) {
     const int t = f >> 3;
     const int q = f & 7;
     const float4 v = *reinterpret_cast<const float4*>(&os[t * NF + ((q ^ (t & 7)) << 2)]);
-    const float4 e = make_float4(elu1(v.x), elu1(v.y), elu1(v.z), elu1(v.w));
+    float4 e = v;
+    if (p.out_elu) e = make_float4(elu1(v.x), elu1(v.y), elu1(v.z), elu1(v.w));   // the fused residual block reads X only
     const int g = t0 + t;   // row inside the item
     int mir[2] = {0x7fffffff, 0x7fffffff};
     if (p.halo > 0) {
