@@ -39,8 +39,9 @@ WORKLOADS = {
     "fork10hz": dict(model="fork10hz", bandwidth=0.08, batch=32, seconds=14400.0,
                      desc="the fork's 10 Hz model (layer_norm, ratios 6,5,5,2,1, dimension 256, 1024-wide LSTM), 0.08 kbps (n_q=8), "
                           "batch 32 x 144000 samples (4 h each)"),
-    "cfg5": dict(model="24k", bandwidth=6.0, batch=256, seconds=10.0,
-                 desc="EnCodec 24 kHz causal mono, 6 kbps (n_q=8), 256 x 10 s clips per GPU (long-form shard)"),
+    "cfg5": dict(model="24k", bandwidth=6.0, batch=512, seconds=10.0,
+                 desc="EnCodec 24 kHz causal mono, 6 kbps (n_q=8), 512 x 10 s clips per GPU and step (long-form shard, "
+                      "micro-batch sized to HBM)"),
 }
 
 

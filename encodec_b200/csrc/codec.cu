@@ -87,6 +87,8 @@ struct LstmLayerW {
   float* w_hh = nullptr;  // [4H][H]
   float* t_hi = nullptr;  // tensor-core input projection: [4H][H_in] K-major split weights
   float* t_lo = nullptr;
+  float* r_hi = nullptr;  // recurrent weights W_hh in the same form, for the step-wise (large-batch) recurrence
+  float* r_lo = nullptr;
 };
 
 }  // namespace
@@ -218,6 +220,10 @@ int prepare_lstm(ecb_codec* c, const std::string& prefix, int H, std::vector<Lst
     if (dev_alloc(c, &lw.w_hh, 4LL * H * H)) return 1;   // reference layout [4H][H]; the kernel slices it itself
     ECB_CUDA(cudaMemcpyAsync(lw.w_hh, whh, sizeof(float) * 4 * H * H, cudaMemcpyDeviceToDevice, st));
     if (prepare_tc(c, lw.w_ih, nullptr, H, 4 * H, 4 * H, &lw.t_hi, &lw.t_lo, nullptr, st)) return 1;
+    float* whh_t = nullptr;
+    if (dev_alloc(c, &whh_t, 4LL * H * H)) return 1;
+    if (launch_transpose(whh, whh_t, 1, 4 * H, H, st)) return 1;  // [4H][H] -> [H][4H]
+    if (prepare_tc(c, whh_t, nullptr, H, 4 * H, 4 * H, &lw.r_hi, &lw.r_lo, nullptr, st)) return 1;
   }
   return 0;
 }
@@ -712,8 +718,9 @@ int tap_act(cudaStream_t st, int stage, const Act& a, int n_items) {
 int tc_run(Ctx& x, const float* hi, const float* lo, const float* bias, int K, int N, const Act& in, int C0, int taps,
            int stride, int pad_left, bool zero_pad, const Act* in1, float* out_raw, float* out_elu,
            long long out_item_stride, long long M, int mirror_halo, int split, int round_out, double* stats = nullptr,
-           int* stat_slots = nullptr) {
+           int* stat_slots = nullptr, int n_items_override = 0, int bn_max = 0) {
   TcConvParams p;
+  p.bn_max = bn_max;
   p.C0 = C0;
   p.taps = taps;
   p.stride = stride;
@@ -744,7 +751,7 @@ int tc_run(Ctx& x, const float* hi, const float* lo, const float* bias, int K, i
   p.out_item_stride = out_item_stride;
   p.N = N;
   p.M = M;
-  p.n_items = x.n_items;
+  p.n_items = n_items_override ? n_items_override : x.n_items;
   p.halo = mirror_halo;
   p.round_out = round_out;
   p.split = split;
@@ -801,21 +808,115 @@ int tc_res(Ctx& x, const ResW& r, const Act& X, const Act& E, float* hbuf, Act& 
                 Y.stride(), X.T, Y.halo, split, split == 1);
 }
 
+// ---- step-wise recurrence (large batches): per time step one tensor-core GEMM rec = h_{t-1} W_hh^T over ALL items and
+// one element-wise cell kernel (lstm.cu). The 2 T launches of a layer are recorded once into a CUDA graph (captured on a
+// private stream, replayed on the caller's) and cached while shapes and buffers stay the same.
+struct LstmGraphKey {
+  const void *w, *pre, *skip, *out, *ws;
+  long long pre_stride, skip_stride, out_stride;
+  int B, T, H, split, out_elu;
+  bool operator==(const LstmGraphKey& o) const {
+    return w == o.w && pre == o.pre && skip == o.skip && out == o.out && ws == o.ws && pre_stride == o.pre_stride &&
+           skip_stride == o.skip_stride && out_stride == o.out_stride && B == o.B && T == o.T && H == o.H && split == o.split &&
+           out_elu == o.out_elu;
+  }
+};
+struct LstmGraph {
+  LstmGraphKey key;
+  cudaGraphExec_t exec;
+};
+std::vector<LstmGraph> g_lstm_graphs;   // a handful of entries (layers x shapes); oldest dropped beyond 16
+cudaStream_t g_capture_stream = nullptr;
+
+int lstm_stepwise_mode() {
+  const char* e = getenv("ECB_LSTM_STEPWISE");   // 0: never, 1: always, unset: automatic (>= 320 items per launch)
+  if (!e || !e[0]) return -1;
+  return e[0] == '0' ? 0 : 1;
+}
+
+int lstm_steps_eager(Ctx& x, const LstmLayerW& lw, const float* pre, long long pre_stride, const float* skip, long long skip_stride,
+                     float* out, long long out_stride, int T, int H, int split, int out_elu, cudaStream_t st) {
+  const int B = x.n_items;
+  float* rec = x.lstm_ws;
+  float* hb[2] = {rec + 4LL * H * B, rec + 5LL * H * B};
+  float* cst = rec + 6LL * H * B;
+  Ctx y = x;
+  y.st = st;
+  // tile width of the per-step GEMM: about one tile per SM (the launch is latency-bound: 128 x 128 tiles would leave
+  // most SMs idle and serialise 16 K chunks of wide MMAs on the few that work)
+  const long long m_tiles = (B + 127) / 128;
+  const int bn_max = m_tiles * (4 * H / 128) >= 120 ? 128 : (m_tiles * (4 * H / 64) >= 120 ? 64 : 32);
+  for (int t = 0; t < T; ++t) {
+    if (t > 0) {
+      Act hin = act_of(hb[(t - 1) & 1], H, B, 0);
+      if (tc_run(y, lw.r_hi, lw.r_lo, nullptr, H, 4 * H, hin, H, 1, 1, 0, true, nullptr, rec, nullptr, (long long)B * 4 * H, B, 0, split, 0,
+                 nullptr, nullptr, 1, bn_max))
+        return 1;
+    }
+    if (launch_lstm_cell(pre + (long long)t * 4 * H, pre_stride, rec, cst, hb[t & 1], skip ? skip + (long long)t * H : nullptr, skip_stride,
+                         out + (long long)t * H, out_stride, B, H, t == 0 ? 1 : 0, out_elu, st))
+      return 1;
+  }
+  return 0;
+}
+
+int lstm_steps(Ctx& x, const LstmLayerW& lw, const float* pre, long long pre_stride, const float* skip, long long skip_stride, float* out,
+               long long out_stride, int T, int H, int split, int out_elu) {
+  if (prof_enabled())   // per-kernel timing needs real launches on the caller's stream
+    return lstm_steps_eager(x, lw, pre, pre_stride, skip, skip_stride, out, out_stride, T, H, split, out_elu, x.st);
+  LstmGraphKey key{lw.r_hi, pre, skip, out, x.lstm_ws, pre_stride, skip_stride, out_stride, x.n_items, T, H, split, out_elu};
+  for (auto& g : g_lstm_graphs)
+    if (g.key == key) {
+      ECB_CUDA(cudaGraphLaunch(g.exec, x.st));
+      return 0;
+    }
+  if (!g_capture_stream) ECB_CUDA(cudaStreamCreateWithFlags(&g_capture_stream, cudaStreamNonBlocking));
+  // warm the launch path once outside the capture (function attributes, lazily loaded modules)
+  ECB_CUDA(cudaStreamBeginCapture(g_capture_stream, cudaStreamCaptureModeRelaxed));
+  const int rc = lstm_steps_eager(x, lw, pre, pre_stride, skip, skip_stride, out, out_stride, T, H, split, out_elu, g_capture_stream);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t ce = cudaStreamEndCapture(g_capture_stream, &graph);
+  if (rc) {
+    if (graph) cudaGraphDestroy(graph);
+    return 1;
+  }
+  ECB_CUDA(ce);
+  cudaGraphExec_t exec = nullptr;
+  const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  ECB_CUDA(ie);
+  if (g_lstm_graphs.size() >= 16) {
+    cudaGraphExecDestroy(g_lstm_graphs.front().exec);
+    g_lstm_graphs.erase(g_lstm_graphs.begin());
+  }
+  g_lstm_graphs.push_back({key, exec});
+  ECB_CUDA(cudaGraphLaunch(exec, x.st));
+  return 0;
+}
+
 // SLSTM (modules/lstm.py:22-28): X raw [item][T][512] -> out = ELU(lstm(X) + X). pre / h0 are plain scratch.
 int tc_lstm(Ctx& x, const std::vector<LstmLayerW>& layers, const Act& X, float* pre_buf, float* h0_buf, Act& out, int split) {
   const int H = top_width(x.c->spec), L = (int)layers.size();
   Act pre = act_of(pre_buf, 4 * H, X.T, 0);
   Act h0 = act_of(h0_buf, H, X.T, 0);
   const Act* cur = &X;
+  const int mode = lstm_stepwise_mode();
+  // measured: the persistent FFMA kernel costs ~0.067 us per item and step, the step-wise form ~17 us per step + little per item
+  const bool stepwise = mode == 1 || (mode < 0 && x.n_items >= 320);
   for (int l = 0; l < L; ++l) {
     if (tc_run(x, layers[l].t_hi, layers[l].t_lo, layers[l].bias, H, 4 * H, *cur, H, 1, 1, 0, true, nullptr, pre.row0(), nullptr,
                pre.stride(), X.T, 0, split, 0))
       return 1;
     const bool last = (l == L - 1);
     Act& dst = last ? out : h0;
-    if (launch_lstm_recurrent(pre.row0(), layers[l].w_hh, last ? X.row0() : nullptr, X.stride(), dst.row0(), dst.stride(),
-                              x.n_items, (int)X.T, H, last ? 1 : 0, x.lstm_ws, x.st))
+    if (stepwise) {
+      if (lstm_steps(x, layers[l], pre.row0(), pre.stride(), last ? X.row0() : nullptr, X.stride(), dst.row0(), dst.stride(), (int)X.T, H,
+                     split, last ? 1 : 0))
+        return 1;
+    } else if (launch_lstm_recurrent(pre.row0(), layers[l].w_hh, last ? X.row0() : nullptr, X.stride(), dst.row0(), dst.stride(),
+                                     x.n_items, (int)X.T, H, last ? 1 : 0, x.lstm_ws, x.st)) {
       return 1;
+    }
     cur = &h0;
   }
   if (out.halo > 0 && launch_halo_fill(nullptr, out.row0(), out.stride(), out.T, out.C, x.n_items, out.halo, 0, x.st)) return 1;

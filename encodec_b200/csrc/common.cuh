@@ -235,13 +235,15 @@ struct TcConvParams {
   int halo;                   // also write the reflected rows -1..-halo and M..M+halo-1 of each output (0: none)
   int round_out;              // round stored values to TF32 (for split == 1 consumers)
   int split;                  // 3: fp32-accurate split operands; 1: single TF32 pass
+  int bn_max = 0;             // 0: widest N tile that divides N; else cap (32 | 64 | 128): more, shorter tiles for
+                              // latency-bound launches with few rows (the per-step GEMM of the step-wise LSTM)
   double* stats;              // nullptr, or [item][tc_stat_slots(p)][2] partial (sum, sum of squares) of the raw output
                               // (GroupNorm statistics; requires out_elu == nullptr, halo == 0, round_out == 0)
 };
 int tc_stat_slots(const TcConvParams& p);   // partial-statistics slots per item a launch writes
 int launch_tc_conv(const TcConvParams& p, cudaStream_t stream);
 int launch_split_weights(const float* w, float* hi, float* lo, int K, int N, int K_pad, int N_pad, cudaStream_t s);
-int tc_pick_bn(int N, int split);
+int tc_pick_bn(int N, int split, int bn_max = 0);
 
 // Fused SEANetResnetBlock at 32 channels (tc_res.cu): Y = ELU(shortcut(X) + block3(ELU(block1(ELU(X))))), X read once.
 struct TcResParams {
@@ -346,6 +348,10 @@ int launch_unpack_codes(const unsigned char* in, long long n_bytes, int K, long 
 // [4H][H] tensor. If skip != nullptr the written output is act(h + skip) (SLSTM skip connection, lstm.py:25-26) and
 // the raw h stays in the recurrent state only.
 int lstm_recurrent_workspace_floats(int batch, int H);
+// one step of the step-wise (large-batch) recurrence: gates = pre_t + rec -> c, h_out, out_t = h (+ skip_t) (ELU)
+int launch_lstm_cell(const float* pre_t, long long pre_item_stride, const float* rec, float* c, float* h_out, const float* skip_t,
+                     long long skip_item_stride, float* out_t, long long out_item_stride, int batch, int H, int first, int out_elu,
+                     cudaStream_t s);
 // skip / out rows of item b start at + b*skip_item_stride / + b*out_item_stride floats (0 means the dense T*H).
 int launch_lstm_recurrent(const float* pre, const float* w_hh_packed, const float* skip, long long skip_item_stride,
                           float* out, long long out_item_stride, int batch, int T, int H, int out_elu,

@@ -361,13 +361,69 @@ int launch_impl(const float* pre, const float* w_hh, const float* skip, long lon
   return 0;
 }
 
+// ---- step-wise recurrence for large batches ------------------------------------------------------------------------
+// With hundreds of items per launch the recurrence is FMA-throughput bound on the CUDA cores (67 ns per item step); the
+// recurrent product h_{t-1} W_hh^T of ALL items is then a well-shaped GEMM for the tensor-core conv kernel (tc_conv.cu,
+// split-operand TF32, fp32-accurate), launched once per time step (from a CUDA graph, codec.cu) and followed by this
+// element-wise cell update: gates = pre_t + rec (i, f, g, o), c = f c + i g, h = o tanh(c), y = h (+ skip) (ELU).
+__global__ void __launch_bounds__(256)
+lstm_cell_kernel(const float* __restrict__ pre, long long pre_item_stride, const float* __restrict__ rec,
+                 float* __restrict__ c, float* __restrict__ h_out, const float* __restrict__ skip, long long skip_stride,
+                 float* __restrict__ out, long long out_stride, int B, int H, int first, int out_elu) {
+  const long long i4 = blockIdx.x * (long long)blockDim.x + threadIdx.x;   // (item, unit quad)
+  const int q4 = H / 4;
+  if (i4 >= (long long)B * q4) return;
+  const int b = (int)(i4 / q4), u = (int)(i4 % q4) * 4;
+  float4 g[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    g[k] = __ldg(reinterpret_cast<const float4*>(pre + (long long)b * pre_item_stride + k * H + u));
+    if (!first) {
+      const float4 r = __ldg(reinterpret_cast<const float4*>(rec + (long long)b * 4 * H + k * H + u));
+      g[k].x += r.x; g[k].y += r.y; g[k].z += r.z; g[k].w += r.w;
+    }
+  }
+  float4 cv = first ? make_float4(0.f, 0.f, 0.f, 0.f) : *reinterpret_cast<const float4*>(c + (long long)b * H + u);
+  float4 hv;
+#define ECB_CELL(f)                                                                 \
+  {                                                                                 \
+    const float gi = sigmoidf_acc(g[0].f), gf = sigmoidf_acc(g[1].f), gg = tanhf(g[2].f), go = sigmoidf_acc(g[3].f); \
+    cv.f = gf * cv.f + gi * gg;                                                     \
+    hv.f = go * tanhf(cv.f);                                                        \
+  }
+  ECB_CELL(x) ECB_CELL(y) ECB_CELL(z) ECB_CELL(w)
+#undef ECB_CELL
+  *reinterpret_cast<float4*>(c + (long long)b * H + u) = cv;
+  *reinterpret_cast<float4*>(h_out + (long long)b * H + u) = hv;
+  float4 y = hv;
+  if (skip) {
+    const float4 sv = __ldg(reinterpret_cast<const float4*>(skip + (long long)b * skip_stride + u));
+    y.x += sv.x; y.y += sv.y; y.z += sv.z; y.w += sv.w;
+  }
+  if (out_elu) y = make_float4(elu1(y.x), elu1(y.y), elu1(y.z), elu1(y.w));
+  *reinterpret_cast<float4*>(out + (long long)b * out_stride + u) = y;
+}
+
 }  // namespace
+
+int launch_lstm_cell(const float* pre_t, long long pre_item_stride, const float* rec, float* c, float* h_out, const float* skip_t,
+                     long long skip_item_stride, float* out_t, long long out_item_stride, int batch, int H, int first, int out_elu,
+                     cudaStream_t s) {
+  const long long n4 = (long long)batch * (H / 4);
+  ProfScope prof(PROF_LSTM_REC, s, 0.0, 4.0 * (double)batch * H * (first ? 6 : 12));
+  lstm_cell_kernel<<<(unsigned)cdiv(n4, 256), 256, 0, s>>>(pre_t, pre_item_stride, rec, c, h_out, skip_t, skip_item_stride, out_t,
+                                                          out_item_stride, batch, H, first, out_elu);
+  ECB_LAUNCHED();
+  return 0;
+}
 
 // 2 x B_pad x H state + one counter per sub-group
 int lstm_recurrent_workspace_floats(int batch, int H) {
   const int nq = H == 1024 ? Geo<1024>::NQ : Geo<512>::NQ;
   const int qi = group_items(batch, nq);
-  return 2 * nq * qi * H + nq * qi / L_SB + 64;
+  const int persistent = 2 * nq * qi * H + nq * qi / L_SB + 64;
+  const int stepwise = 7 * H * batch + 64;   // rec [B][4H], h [2][B][H], c [B][H]
+  return persistent > stepwise ? persistent : stepwise;
 }
 
 int launch_lstm_recurrent(const float* pre, const float* w_hh, const float* skip, long long skip_item_stride, float* out,

@@ -582,13 +582,15 @@ int launch_split_weights(const float* w, float* hi, float* lo, int K, int N, int
   return 0;
 }
 
-int tc_pick_bn(int N, int split) {
-  if (split == 3) return N % 128 == 0 ? 128 : (N % 64 == 0 ? 64 : 32);
-  return N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : (N % 64 == 0 ? 64 : 32));
+int tc_pick_bn(int N, int split, int bn_max) {
+  int bn = split == 3 ? (N % 128 == 0 ? 128 : (N % 64 == 0 ? 64 : 32))
+                      : (N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : (N % 64 == 0 ? 64 : 32)));
+  while (bn_max > 0 && bn > bn_max && bn > 32) bn /= 2;
+  return bn;
 }
 
 int tc_stat_slots(const TcConvParams& p) {
-  return (int)(cdiv(p.M, BM) * (p.N / tc_pick_bn(p.N, p.split)) * 8);
+  return (int)(cdiv(p.M, BM) * (p.N / tc_pick_bn(p.N, p.split, p.bn_max)) * 8);
 }
 
 int launch_tc_conv(const TcConvParams& p, cudaStream_t stream) {
@@ -600,7 +602,7 @@ int launch_tc_conv(const TcConvParams& p, cudaStream_t stream) {
   ECB_REQUIRE(p.out_raw || p.out_elu, "tc_conv: no output");
   ECB_REQUIRE(p.halo == 0 || p.M > p.halo, "tc_conv: %lld rows are too few for a %d-row reflected halo", p.M, p.halo);
   ECB_REQUIRE(!p.stats || (p.out_raw && !p.out_elu && p.halo == 0 && !p.round_out), "tc_conv: statistics need a plain raw output");
-  const int bn = tc_pick_bn(p.N, p.split);
+  const int bn = tc_pick_bn(p.N, p.split, p.bn_max);
   const int s = p.stride;
   const int ktot = p.taps * p.C0 + (p.a1 ? p.C1 : 0);
   ECB_REQUIRE(p.taps % s == 0, "tc_conv: kernel size %d must be a multiple of the stride %d", p.taps, s);

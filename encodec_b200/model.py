@@ -70,8 +70,9 @@ class EncodecModel(nn.Module):
         assert 2 ** self.bits_per_codebook == self.quantizer.bins, \
             "quantizer bins must be a power of 2."
         # largest number of (batch item, segment) windows pushed through the stacks in one launch sequence;
-        # bounds the activation workspace (n_items * length * 32 floats * 3-4 buffers)
-        self.max_items_bytes = 48 << 30
+        # bounds the activation workspace (n_items * length * 32 floats * 3-4 buffers). 72 GB of a B200's 180 GB: large
+        # launches matter, the LSTM recurrence switches to its tensor-core form from 320 items per launch
+        self.max_items_bytes = 72 << 30
 
     # ---- reference properties ------------------------------------------------------------------
     @property

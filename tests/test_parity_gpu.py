@@ -396,3 +396,28 @@ def test_short_and_threshold_lengths_match_oracle(length):
     if score["mismatched"] == 0:
         d = np.abs(audio.cpu().numpy() - o_audio)
         assert d.max() < AUDIO_MAX_ABS and np.sqrt((d ** 2).mean()) < AUDIO_RMS, (length, d.max())
+
+
+@pytest.mark.parametrize("name", ["24k_24kbps_ragged", "48k_24kbps_3seg", "fork10hz_ln_r65521"])
+def test_stepwise_tensor_core_lstm_matches_reference_golden(name, monkeypatch):
+    """The large-batch form of the recurrence (one tensor-core GEMM + one cell kernel per time step, replayed from a CUDA
+    graph) forced on for the small golden cases: same codes and audio as the unmodified reference; a second call replays the
+    cached graph and must give the same bits."""
+    monkeypatch.setenv("ECB_LSTM_STEPWISE", "1")
+    case = gc.load_model_case(name)
+    spec = case["spec"]
+    m = ug.build_model(spec, case["sd"], case["bandwidth"], case["distinct"])
+    x = torch.from_numpy(case["x"]).cuda()
+    audio, codes, _, _ = m(x)
+    audio2, codes2, _, _ = m(x)
+    assert torch.equal(audio, audio2) and torch.equal(codes, codes2)
+    n_q = case["n_q"]
+    score = orc.score_codes(gc.frames_of(case["emb"]), orc.codebooks_from_state_dict(case["sd"], n_q),
+                            np.transpose(case["codes"], (1, 0, 2)).reshape(n_q, -1),
+                            np.transpose(codes.cpu().numpy(), (1, 0, 2)).reshape(n_q, -1))
+    print(f"\n[{name}] step-wise LSTM: code score vs reference {score}")
+    assert score["hard"] == 0, score
+    assert score["near_tie"] <= max(2, 1e-3 * score["compared"]), score
+    if score["mismatched"] == 0:
+        d = np.abs(audio.cpu().numpy() - case["audio"])
+        assert d.max() < AUDIO_MAX_ABS and np.sqrt((d ** 2).mean()) < AUDIO_RMS
