@@ -222,7 +222,7 @@ int prepare_lstm(ecb_codec* c, const std::string& prefix, int H, std::vector<Lst
     if (prepare_tc(c, lw.w_ih, nullptr, H, 4 * H, 4 * H, &lw.t_hi, &lw.t_lo, nullptr, st)) return 1;
     float* whh_t = nullptr;
     if (dev_alloc(c, &whh_t, 4LL * H * H)) return 1;
-    if (launch_transpose(whh, whh_t, 1, 4 * H, H, st)) return 1;  // [4H][H] -> [H][4H]
+    if (launch_lstm_gate_interleave(whh, whh_t, H, st)) return 1;  // [4H][H] -> [H][4H], gate-interleaved columns (TcCell)
     if (prepare_tc(c, whh_t, nullptr, H, 4 * H, 4 * H, &lw.r_hi, &lw.r_lo, nullptr, st)) return 1;
   }
   return 0;
@@ -718,9 +718,10 @@ int tap_act(cudaStream_t st, int stage, const Act& a, int n_items) {
 int tc_run(Ctx& x, const float* hi, const float* lo, const float* bias, int K, int N, const Act& in, int C0, int taps,
            int stride, int pad_left, bool zero_pad, const Act* in1, float* out_raw, float* out_elu,
            long long out_item_stride, long long M, int mirror_halo, int split, int round_out, double* stats = nullptr,
-           int* stat_slots = nullptr, int n_items_override = 0, int bn_max = 0) {
+           int* stat_slots = nullptr, int n_items_override = 0, int bn_max = 0, const TcCell* cell = nullptr) {
   TcConvParams p;
   p.bn_max = bn_max;
+  p.cell = cell;
   p.C0 = C0;
   p.taps = taps;
   p.stride = stride;
@@ -847,14 +848,26 @@ int lstm_steps_eager(Ctx& x, const LstmLayerW& lw, const float* pre, long long p
   const long long m_tiles = (B + 127) / 128;
   const int bn_max = m_tiles * (4 * H / 128) >= 120 ? 128 : (m_tiles * (4 * H / 64) >= 120 ? 64 : 32);
   for (int t = 0; t < T; ++t) {
-    if (t > 0) {
-      Act hin = act_of(hb[(t - 1) & 1], H, B, 0);
-      if (tc_run(y, lw.r_hi, lw.r_lo, nullptr, H, 4 * H, hin, H, 1, 1, 0, true, nullptr, rec, nullptr, (long long)B * 4 * H, B, 0, split, 0,
-                 nullptr, nullptr, 1, bn_max))
-        return 1;
+    const float* skip_t = skip ? skip + (long long)t * H : nullptr;
+    if (t == 0) {   // h_{-1} = 0: no recurrent product, the stand-alone cell kernel starts the state
+      if (launch_lstm_cell(pre, pre_stride, rec, cst, hb[0], skip_t, skip_stride, out, out_stride, B, H, 1, out_elu, st)) return 1;
+      continue;
     }
-    if (launch_lstm_cell(pre + (long long)t * 4 * H, pre_stride, rec, cst, hb[t & 1], skip ? skip + (long long)t * H : nullptr, skip_stride,
-                         out + (long long)t * H, out_stride, B, H, t == 0 ? 1 : 0, out_elu, st))
+    // one launch per step: rec = h_{t-1} W_hh^T on the tensor cores, cell update in its epilogue
+    TcCell cell;
+    cell.pre = pre + (long long)t * 4 * H;
+    cell.pre_stride = pre_stride;
+    cell.c = cst;
+    cell.h_out = hb[t & 1];
+    cell.skip = skip_t;
+    cell.skip_stride = skip_stride;
+    cell.out = out + (long long)t * H;
+    cell.out_stride = out_stride;
+    cell.H = H;
+    cell.out_elu = out_elu;
+    Act hin = act_of(hb[(t - 1) & 1], H, B, 0);
+    if (tc_run(y, lw.r_hi, lw.r_lo, nullptr, H, 4 * H, hin, H, 1, 1, 0, true, nullptr, nullptr, nullptr, (long long)B * 4 * H, B, 0, split, 0,
+               nullptr, nullptr, 1, bn_max, &cell))
       return 1;
   }
   return 0;

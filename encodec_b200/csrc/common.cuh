@@ -210,6 +210,23 @@ int conv_gemm_stat_slots(const ConvParams& p);  // gridDim.x*gridDim.y the launc
 // ------------------------------------------------------------------------------------------------
 constexpr int ACT_HALO = 16;  // reflected rows kept before and after every item of a halo-padded activation
 
+// LSTM cell epilogue of the step-wise recurrence (tc_conv as rec = h_{t-1} W_hh^T with gate-interleaved weight columns:
+// column (u / 4) * 16 + g * 4 + u % 4 holds gate g (i, f, g, o) of unit u, so every 16-column chunk carries the four gates
+// of four units). The epilogue then finishes the step in registers instead of storing rec: gates = pre_t + rec,
+// c = f c + i g, h = o tanh(c), out_t = h (+ skip_t) (ELU) -- reference modules/lstm.py:22-28 / nn.LSTM.
+struct TcCell {
+  const float* pre;        // pre-gates of this step, (item b) at pre + b * pre_stride, [4H] in reference gate order
+  long long pre_stride;
+  float* c;                // [B][H] cell state, updated in place
+  float* h_out;            // [B][H] h_t (the next step's A operand)
+  const float* skip;       // skip input of this step (item b at skip + b * skip_stride, [H]) or nullptr
+  long long skip_stride;
+  float* out;              // layer output of this step, item b at out + b * out_stride, [H]
+  long long out_stride;
+  int H;
+  int out_elu;
+};
+
 struct TcConvParams {
   // source 0: channels-last rows; a0 points at (item 0, sample a0_first, channel 0) and a0_rows samples are
   // addressable from there (reads outside are zero). Output row m reads samples m*stride - pad_left ... + taps - 1.
@@ -235,6 +252,7 @@ struct TcConvParams {
   int halo;                   // also write the reflected rows -1..-halo and M..M+halo-1 of each output (0: none)
   int round_out;              // round stored values to TF32 (for split == 1 consumers)
   int split;                  // 3: fp32-accurate split operands; 1: single TF32 pass
+  const TcCell* cell = nullptr;  // LSTM cell epilogue instead of storing the output (out_raw / out_elu / bias unused)
   int bn_max = 0;             // 0: widest N tile that divides N; else cap (32 | 64 | 128): more, shorter tiles for
                               // latency-bound launches with few rows (the per-step GEMM of the step-wise LSTM)
   double* stats;              // nullptr, or [item][tc_stat_slots(p)][2] partial (sum, sum of squares) of the raw output
@@ -330,6 +348,8 @@ int launch_gn_apply2(const GnSrc& a, const GnSrc* b, float* out_raw, float* out_
 // the stored row width, c_real <= C the channels that exist (the rest is zero padding, kept zero).
 int launch_ln_apply2(const GnSrc& a, const GnSrc* b, float* out_raw, float* out_elu, long long out_item_stride, int n_items,
                      long long rows, int C, int c_real, float eps, cudaStream_t s);
+// W_hh [4H][H] (reference layout) -> [H][4H] with gate-interleaved columns (see TcCell)
+int launch_lstm_gate_interleave(const float* whh, float* out, int H, cudaStream_t s);
 int launch_overlap_add(const float* frames, const int* seg_lens, long long batch, int channels, int n_seg,
                        int seg_len, int stride, float* out, long long total, cudaStream_t s);
 

@@ -84,6 +84,16 @@ __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict
   }
 }
 
+// W_hh [4H][H] -> out [H][4H'], column n' = (u / 4) * 16 + g * 4 + u % 4 for gate g of unit u (TcCell, common.cuh)
+__global__ void gate_interleave_kernel(const float* __restrict__ whh, float* __restrict__ out, int H) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (idx >= 4LL * H * H) return;
+  const int k = (int)(idx / (4 * H)), np = (int)(idx % (4 * H));
+  const int chunk = np >> 4, g = (np >> 2) & 3, j = np & 3;
+  const int u = chunk * 4 + j;
+  out[idx] = whh[((long long)g * H + u) * H + k];
+}
+
 // Halo-padded activation layout of the tensor-core path: (item i, row r) at row0 + i*item_stride + r*C with
 // r in [-halo, T + halo); rows outside [0, T) hold the reflected samples of pad1d (reference modules/conv.py:80-97):
 // row -j = row j, row T-1+j = row T-1-j. With src != nullptr the interior is first copied from a plain
@@ -476,6 +486,11 @@ int launch_ln_apply2(const GnSrc& a, const GnSrc* b, float* out_raw, float* out_
       ECB_REQUIRE(false, "ln_apply: C=%d unsupported (32, 64, ..., 1024)", C);
   }
 #undef ECB_LN_CASE
+  ECB_LAUNCHED();
+  return 0;
+}
+int launch_lstm_gate_interleave(const float* whh, float* out, int H, cudaStream_t s) {
+  gate_interleave_kernel<<<(unsigned)cdiv(4LL * H * H, 256), 256, 0, s>>>(whh, out, H);
   ECB_LAUNCHED();
   return 0;
 }

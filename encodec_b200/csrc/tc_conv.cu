@@ -73,6 +73,8 @@ struct TcArgs {
   int a_rows;               // rows per A tile box: BM (+ 8 when shifts > 1)
   int row_base0, row_base1; // row coordinate of output row 0's window start in each source's map
   int round_out, halo;
+  int cell_on;              // 1: LSTM cell epilogue (cell) instead of the output stores
+  TcCell cell;
   double* stats;            // [item][tiles_m][tiles_n][8 warps][2] or nullptr
   int group;                // K chunks per main-accumulator group (SPLIT == 1: all of them)
 };
@@ -400,6 +402,41 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         }
       };
 
+      // LSTM cell epilogue (step-wise recurrence): this thread's 16 columns are the four gates of four units of item
+      // m_warp + lane; everything else of the step happens here, in registers (TcCell, common.cuh).
+      auto finish_cell = [&](const float* o, int cc) {
+        const int n0 = nt * BN + cc + half * 16;
+        const int u0 = (n0 >> 4) << 2;
+        const int m = m_warp + lane;
+        if (m >= p.M) return;
+        const TcCell& q = p.cell;
+        const float* pr = q.pre + (long long)m * q.pre_stride + u0;
+        const float4 pi = __ldg(reinterpret_cast<const float4*>(pr));
+        const float4 pf = __ldg(reinterpret_cast<const float4*>(pr + q.H));
+        const float4 pg = __ldg(reinterpret_cast<const float4*>(pr + 2 * q.H));
+        const float4 po = __ldg(reinterpret_cast<const float4*>(pr + 3 * q.H));
+        float4 cv = *reinterpret_cast<const float4*>(q.c + (long long)m * q.H + u0);
+        float4 hv;
+        auto sig = [](float x) { return 1.f / (1.f + expf(-x)); };
+#define ECB_CELL(f, j)                                                                                         \
+  {                                                                                                            \
+    const float gi = sig(pi.f + o[0 + j]), gf = sig(pf.f + o[4 + j]), gg = tanhf(pg.f + o[8 + j]), go = sig(po.f + o[12 + j]); \
+    cv.f = gf * cv.f + gi * gg;                                                                                \
+    hv.f = go * tanhf(cv.f);                                                                                   \
+  }
+        ECB_CELL(x, 0) ECB_CELL(y, 1) ECB_CELL(z, 2) ECB_CELL(w, 3)
+#undef ECB_CELL
+        *reinterpret_cast<float4*>(q.c + (long long)m * q.H + u0) = cv;
+        *reinterpret_cast<float4*>(q.h_out + (long long)m * q.H + u0) = hv;
+        float4 y = hv;
+        if (q.skip) {
+          const float4 sv = __ldg(reinterpret_cast<const float4*>(q.skip + (long long)m * q.skip_stride + u0));
+          y.x += sv.x; y.y += sv.y; y.z += sv.z; y.w += sv.w;
+        }
+        if (q.out_elu) y = make_float4(elu1(y.x), elu1(y.y), elu1(y.z), elu1(y.w));
+        *reinterpret_cast<float4*>(q.out + (long long)m * q.out_stride + u0) = y;
+      };
+
       // Where the finished fp32 tile is read from: TMEM columns src_col (+ the correction columns BN further when
       // they still have to be added), this warp's 16 columns of every 32-column block.
       const int n_groups = (nch + p.group - 1) / p.group;
@@ -465,7 +502,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           __syncwarp();
           if (lane == 0) mbar_arrive(maine_bar(mb_last));
         }
-        finish_block(o, cc);
+        if (p.cell_on) finish_cell(o, cc);
+        else finish_block(o, cc);
       }
       if (p.stats) {
         // deterministic two-stage reduction: per-warp partials here, summed per item in gn_apply (misc.cu)
@@ -599,7 +637,8 @@ int launch_tc_conv(const TcConvParams& p, cudaStream_t stream) {
   ECB_REQUIRE(p.C0 % 32 == 0 && p.taps >= 1 && p.stride >= 1, "tc_conv: C0=%d must be a multiple of 32", p.C0);
   ECB_REQUIRE(p.a1 == nullptr || p.C1 % 32 == 0, "tc_conv: C1=%d must be a multiple of 32", p.C1);
   ECB_REQUIRE(p.M > 0 && p.n_items > 0, "tc_conv: bad M=%lld / items=%d", p.M, p.n_items);
-  ECB_REQUIRE(p.out_raw || p.out_elu, "tc_conv: no output");
+  ECB_REQUIRE(p.out_raw || p.out_elu || p.cell, "tc_conv: no output");
+  ECB_REQUIRE(!p.cell || (p.n_items == 1 && p.N == 4 * p.cell->H && !p.stats && p.halo == 0), "tc_conv: bad LSTM cell epilogue setup");
   ECB_REQUIRE(p.halo == 0 || p.M > p.halo, "tc_conv: %lld rows are too few for a %d-row reflected halo", p.M, p.halo);
   ECB_REQUIRE(!p.stats || (p.out_raw && !p.out_elu && p.halo == 0 && !p.round_out), "tc_conv: statistics need a plain raw output");
   const int bn = tc_pick_bn(p.N, p.split, p.bn_max);
@@ -659,6 +698,8 @@ int launch_tc_conv(const TcConvParams& p, cudaStream_t stream) {
   a.round_out = p.round_out;
   a.halo = p.halo;
   a.stats = p.stats;
+  a.cell_on = p.cell ? 1 : 0;
+  if (p.cell) a.cell = *p.cell;
   {
     const int nch = a.n_cb0 * a.shifts + a.n_cb1;
     a.group = (p.split == 3 && nch > 6) ? 4 : nch;   // <= 24 truncating accumulation steps per group
