@@ -718,10 +718,12 @@ int tap_act(cudaStream_t st, int stage, const Act& a, int n_items) {
 int tc_run(Ctx& x, const float* hi, const float* lo, const float* bias, int K, int N, const Act& in, int C0, int taps,
            int stride, int pad_left, bool zero_pad, const Act* in1, float* out_raw, float* out_elu,
            long long out_item_stride, long long M, int mirror_halo, int split, int round_out, double* stats = nullptr,
-           int* stat_slots = nullptr, int n_items_override = 0, int bn_max = 0, const TcCell* cell = nullptr) {
+           int* stat_slots = nullptr, int n_items_override = 0, int bn_max = 0, const TcCell* cell = nullptr,
+           const float* a0_lo = nullptr) {
   TcConvParams p;
   p.bn_max = bn_max;
   p.cell = cell;
+  p.a0_lo = a0_lo;
   p.C0 = C0;
   p.taps = taps;
   p.stride = stride;
@@ -815,11 +817,11 @@ int tc_res(Ctx& x, const ResW& r, const Act& X, const Act& E, float* hbuf, Act& 
 struct LstmGraphKey {
   const void *w, *pre, *skip, *out, *ws;
   long long pre_stride, skip_stride, out_stride;
-  int B, T, H, split, out_elu;
+  int B, T, H, split, out_elu, variant;
   bool operator==(const LstmGraphKey& o) const {
     return w == o.w && pre == o.pre && skip == o.skip && out == o.out && ws == o.ws && pre_stride == o.pre_stride &&
            skip_stride == o.skip_stride && out_stride == o.out_stride && B == o.B && T == o.T && H == o.H && split == o.split &&
-           out_elu == o.out_elu;
+           out_elu == o.out_elu && variant == o.variant;
   }
 };
 struct LstmGraph {
@@ -841,16 +843,26 @@ int lstm_steps_eager(Ctx& x, const LstmLayerW& lw, const float* pre, long long p
   float* rec = x.lstm_ws;
   float* hb[2] = {rec + 4LL * H * B, rec + 5LL * H * B};
   float* cst = rec + 6LL * H * B;
+  float* hl[2] = {rec + 7LL * H * B, rec + 8LL * H * B};   // TF32 remainders of h (split == 3): written with h, read by TMA
+  const bool lo_tma = split == 3 && !(getenv("ECB_LSTM_LO_TMA") && getenv("ECB_LSTM_LO_TMA")[0] == '0');
   Ctx y = x;
   y.st = st;
   // tile width of the per-step GEMM: about one tile per SM (the launch is latency-bound: 128 x 128 tiles would leave
   // most SMs idle and serialise 16 K chunks of wide MMAs on the few that work)
   const long long m_tiles = (B + 127) / 128;
-  const int bn_max = m_tiles * (4 * H / 128) >= 120 ? 128 : (m_tiles * (4 * H / 64) >= 120 ? 64 : 32);
+  int bn_max = 128;   // the narrowest tile that still fits the launch into one wave of CTAs
+  {
+    const int sms = 148;
+    if (m_tiles * (4 * H / 32) <= sms) bn_max = 32;
+    else if (m_tiles * (4 * H / 64) <= sms) bn_max = 64;
+    const char* e = getenv("ECB_LSTM_BN");   // diagnostic override
+    if (e && atoi(e) > 0) bn_max = atoi(e);
+  }
   for (int t = 0; t < T; ++t) {
     const float* skip_t = skip ? skip + (long long)t * H : nullptr;
     if (t == 0) {   // h_{-1} = 0: no recurrent product, the stand-alone cell kernel starts the state
-      if (launch_lstm_cell(pre, pre_stride, rec, cst, hb[0], skip_t, skip_stride, out, out_stride, B, H, 1, out_elu, st)) return 1;
+      if (launch_lstm_cell(pre, pre_stride, rec, cst, hb[0], lo_tma ? hl[0] : nullptr, skip_t, skip_stride, out, out_stride, B, H, 1, out_elu, st))
+        return 1;
       continue;
     }
     // one launch per step: rec = h_{t-1} W_hh^T on the tensor cores, cell update in its epilogue
@@ -859,6 +871,7 @@ int lstm_steps_eager(Ctx& x, const LstmLayerW& lw, const float* pre, long long p
     cell.pre_stride = pre_stride;
     cell.c = cst;
     cell.h_out = hb[t & 1];
+    cell.h_lo_out = lo_tma ? hl[t & 1] : nullptr;
     cell.skip = skip_t;
     cell.skip_stride = skip_stride;
     cell.out = out + (long long)t * H;
@@ -867,7 +880,7 @@ int lstm_steps_eager(Ctx& x, const LstmLayerW& lw, const float* pre, long long p
     cell.out_elu = out_elu;
     Act hin = act_of(hb[(t - 1) & 1], H, B, 0);
     if (tc_run(y, lw.r_hi, lw.r_lo, nullptr, H, 4 * H, hin, H, 1, 1, 0, true, nullptr, nullptr, nullptr, (long long)B * 4 * H, B, 0, split, 0,
-               nullptr, nullptr, 1, bn_max, &cell))
+               nullptr, nullptr, 1, bn_max, &cell, lo_tma ? hl[(t - 1) & 1] : nullptr))
       return 1;
   }
   return 0;
@@ -877,7 +890,10 @@ int lstm_steps(Ctx& x, const LstmLayerW& lw, const float* pre, long long pre_str
                long long out_stride, int T, int H, int split, int out_elu) {
   if (prof_enabled())   // per-kernel timing needs real launches on the caller's stream
     return lstm_steps_eager(x, lw, pre, pre_stride, skip, skip_stride, out, out_stride, T, H, split, out_elu, x.st);
-  LstmGraphKey key{lw.r_hi, pre, skip, out, x.lstm_ws, pre_stride, skip_stride, out_stride, x.n_items, T, H, split, out_elu};
+  int variant = 0;   // diagnostic switches that change the captured launches
+  if (getenv("ECB_LSTM_LO_TMA")) variant |= getenv("ECB_LSTM_LO_TMA")[0] == '0' ? 1 : 2;
+  if (getenv("ECB_LSTM_BN")) variant |= atoi(getenv("ECB_LSTM_BN")) << 4;
+  LstmGraphKey key{lw.r_hi, pre, skip, out, x.lstm_ws, pre_stride, skip_stride, out_stride, x.n_items, T, H, split, out_elu, variant};
   for (auto& g : g_lstm_graphs)
     if (g.key == key) {
       ECB_CUDA(cudaGraphLaunch(g.exec, x.st));
@@ -1693,6 +1709,33 @@ int ecb_overlap_add(const float* frames, const int32_t* seg_lens, int64_t batch,
   ECB_REQUIRE(total > stride * (n_seg - 1) && total <= stride * (n_seg - 1) + seg_len, "overlap_add: bad total");
   return launch_overlap_add(frames, seg_lens, batch, (int)channels, (int)n_seg, (int)seg_len, (int)stride, out, total,
                             reinterpret_cast<cudaStream_t>(stream));
+}
+
+// Diagnostic: the encoder's SLSTM alone (input projections + recurrences + skip + ELU) on x [B][T][H] -> out [B][T][H], for
+// timing the recurrence variants (tools/lstm_bench.py). workspace >= ecb_debug_lstm_workspace_bytes.
+size_t ecb_debug_lstm_workspace_bytes(const ecb_codec* c, int64_t batch, int64_t T) {
+  if (!c || batch <= 0 || T <= 0) return 0;
+  const int H = top_width(c->spec);
+  return sizeof(float) * ((size_t)batch * T * 5 * H + (size_t)lstm_recurrent_workspace_floats((int)batch, H)) + 1024;
+}
+int ecb_debug_lstm(ecb_codec* c, const float* x_in, float* out, int64_t batch, int64_t T, void* workspace, size_t ws_bytes,
+                   void* stream) {
+  ECB_REQUIRE(c && c->finalized && c->has_enc && c->spec.lstm_layers > 0 && c->tc_ready, "debug_lstm: codec has no encoder LSTM");
+  ECB_REQUIRE(x_in && out && workspace && ws_bytes >= ecb_debug_lstm_workspace_bytes(c, batch, T), "debug_lstm: bad argument");
+  const int H = top_width(c->spec);
+  Ctx x;
+  x.c = c;
+  x.st = reinterpret_cast<cudaStream_t>(stream);
+  x.n_items = (int)batch;
+  Arena a{reinterpret_cast<char*>(workspace), ws_bytes};
+  float* pre = a.take<float>((size_t)batch * T * 4 * H);
+  float* h0 = a.take<float>((size_t)batch * T * H);
+  x.lstm_ws = a.take<float>((size_t)lstm_recurrent_workspace_floats((int)batch, H));
+  for (int i = 0; i < 5; ++i) x.buf[i] = nullptr;
+  x.stat[0] = x.stat[1] = nullptr;
+  Act X = act_of(const_cast<float*>(x_in), H, T, 0);
+  Act O = act_of(out, H, T, 0);
+  return tc_lstm(x, c->enc_lstm, X, pre, h0, O, 3);
 }
 
 int ecb_debug_tc_conv(const float* a0, int64_t a0_item_stride, int32_t C0, int64_t a0_first, int64_t a0_rows,

@@ -219,6 +219,7 @@ struct TcCell {
   long long pre_stride;
   float* c;                // [B][H] cell state, updated in place
   float* h_out;            // [B][H] h_t (the next step's A operand)
+  float* h_lo_out;         // [B][H] its TF32 remainder rn_tf32(h - trunc_tf32(h)) (the next step's a0_lo)
   const float* skip;       // skip input of this step (item b at skip + b * skip_stride, [H]) or nullptr
   long long skip_stride;
   float* out;              // layer output of this step, item b at out + b * out_stride, [H]
@@ -252,6 +253,9 @@ struct TcConvParams {
   int halo;                   // also write the reflected rows -1..-halo and M..M+halo-1 of each output (0: none)
   int round_out;              // round stored values to TF32 (for split == 1 consumers)
   int split;                  // 3: fp32-accurate split operands; 1: single TF32 pass
+  const float* a0_lo = nullptr;  // optional: the TF32 remainder of source 0, rn_tf32(a - trunc_tf32(a)), same layout as a0,
+                              // written by the producer of a0 (split == 3, no second source): the tile then comes in
+                              // by TMA as well and the in-kernel operand transform is skipped
   const TcCell* cell = nullptr;  // LSTM cell epilogue instead of storing the output (out_raw / out_elu / bias unused)
   int bn_max = 0;             // 0: widest N tile that divides N; else cap (32 | 64 | 128): more, shorter tiles for
                               // latency-bound launches with few rows (the per-step GEMM of the step-wise LSTM)
@@ -369,7 +373,8 @@ int launch_unpack_codes(const unsigned char* in, long long n_bytes, int K, long 
 // the raw h stays in the recurrent state only.
 int lstm_recurrent_workspace_floats(int batch, int H);
 // one step of the step-wise (large-batch) recurrence: gates = pre_t + rec -> c, h_out, out_t = h (+ skip_t) (ELU)
-int launch_lstm_cell(const float* pre_t, long long pre_item_stride, const float* rec, float* c, float* h_out, const float* skip_t,
+int launch_lstm_cell(const float* pre_t, long long pre_item_stride, const float* rec, float* c, float* h_out, float* h_lo_out,
+                     const float* skip_t,
                      long long skip_item_stride, float* out_t, long long out_item_stride, int batch, int H, int first, int out_elu,
                      cudaStream_t s);
 // skip / out rows of item b start at + b*skip_item_stride / + b*out_item_stride floats (0 means the dense T*H).

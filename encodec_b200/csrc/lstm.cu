@@ -368,7 +368,8 @@ int launch_impl(const float* pre, const float* w_hh, const float* skip, long lon
 // element-wise cell update: gates = pre_t + rec (i, f, g, o), c = f c + i g, h = o tanh(c), y = h (+ skip) (ELU).
 __global__ void __launch_bounds__(256)
 lstm_cell_kernel(const float* __restrict__ pre, long long pre_item_stride, const float* __restrict__ rec,
-                 float* __restrict__ c, float* __restrict__ h_out, const float* __restrict__ skip, long long skip_stride,
+                 float* __restrict__ c, float* __restrict__ h_out, float* __restrict__ h_lo_out, const float* __restrict__ skip,
+                 long long skip_stride,
                  float* __restrict__ out, long long out_stride, int B, int H, int first, int out_elu) {
   const long long i4 = blockIdx.x * (long long)blockDim.x + threadIdx.x;   // (item, unit quad)
   const int q4 = H / 4;
@@ -395,6 +396,12 @@ lstm_cell_kernel(const float* __restrict__ pre, long long pre_item_stride, const
 #undef ECB_CELL
   *reinterpret_cast<float4*>(c + (long long)b * H + u) = cv;
   *reinterpret_cast<float4*>(h_out + (long long)b * H + u) = hv;
+  if (h_lo_out) {   // TF32 remainder of h: the next step's GEMM takes both operand halves by TMA (tc_conv a0_lo)
+    auto lo = [](float v) {
+      return __uint_as_float((__float_as_uint(v - __uint_as_float(__float_as_uint(v) & 0xffffe000u)) + 0x1000u) & 0xffffe000u);
+    };
+    *reinterpret_cast<float4*>(h_lo_out + (long long)b * H + u) = make_float4(lo(hv.x), lo(hv.y), lo(hv.z), lo(hv.w));
+  }
   float4 y = hv;
   if (skip) {
     const float4 sv = __ldg(reinterpret_cast<const float4*>(skip + (long long)b * skip_stride + u));
@@ -406,12 +413,13 @@ lstm_cell_kernel(const float* __restrict__ pre, long long pre_item_stride, const
 
 }  // namespace
 
-int launch_lstm_cell(const float* pre_t, long long pre_item_stride, const float* rec, float* c, float* h_out, const float* skip_t,
+int launch_lstm_cell(const float* pre_t, long long pre_item_stride, const float* rec, float* c, float* h_out, float* h_lo_out,
+                     const float* skip_t,
                      long long skip_item_stride, float* out_t, long long out_item_stride, int batch, int H, int first, int out_elu,
                      cudaStream_t s) {
   const long long n4 = (long long)batch * (H / 4);
   ProfScope prof(PROF_LSTM_REC, s, 0.0, 4.0 * (double)batch * H * (first ? 6 : 12));
-  lstm_cell_kernel<<<(unsigned)cdiv(n4, 256), 256, 0, s>>>(pre_t, pre_item_stride, rec, c, h_out, skip_t, skip_item_stride, out_t,
+  lstm_cell_kernel<<<(unsigned)cdiv(n4, 256), 256, 0, s>>>(pre_t, pre_item_stride, rec, c, h_out, h_lo_out, skip_t, skip_item_stride, out_t,
                                                           out_item_stride, batch, H, first, out_elu);
   ECB_LAUNCHED();
   return 0;
@@ -422,7 +430,7 @@ int lstm_recurrent_workspace_floats(int batch, int H) {
   const int nq = H == 1024 ? Geo<1024>::NQ : Geo<512>::NQ;
   const int qi = group_items(batch, nq);
   const int persistent = 2 * nq * qi * H + nq * qi / L_SB + 64;
-  const int stepwise = 7 * H * batch + 64;   // rec [B][4H], h [2][B][H], c [B][H]
+  const int stepwise = 9 * H * batch + 64;   // rec [B][4H], h [2][B][H], c [B][H], h_lo [2][B][H]
   return persistent > stepwise ? persistent : stepwise;
 }
 

@@ -73,6 +73,7 @@ struct TcArgs {
   int a_rows;               // rows per A tile box: BM (+ 8 when shifts > 1)
   int row_base0, row_base1; // row coordinate of output row 0's window start in each source's map
   int round_out, halo;
+  int lo_tma;               // 1: the A_lo tile is loaded by TMA (map_a0lo) instead of being computed by the transform warps
   int cell_on;              // 1: LSTM cell epilogue (cell) instead of the output stores
   TcCell cell;
   double* stats;            // [item][tiles_m][tiles_n][8 warps][2] or nullptr
@@ -134,7 +135,7 @@ template <int BN, int SPLIT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
-               const TcArgs p) {
+               const __grid_constant__ CUtensorMap map_a0lo, const TcArgs p) {
   using C = Cfg<BN, SPLIT>;
   constexpr int SA = C::A_STAGES, SB = C::B_STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -208,10 +209,12 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           const int sa = (int)(ia % SA);
           mbar_wait(aempty_bar(sa), ((ia / SA) & 1u) ^ 1u);
           if (elect_one()) {
-            mbar_expect_tx(afull_bar(sa), a_bytes);
-            if (ag < p.n_cb0)
+            mbar_expect_tx(afull_bar(sa), (SPLIT == 3 && p.lo_tma) ? 2 * a_bytes : a_bytes);
+            if (ag < p.n_cb0) {
               tma_load_3d(a_ring + sa * C::A_STAGE, &map_a0, afull_bar(sa), ag * BK, mt * BM + p.row_base0, item);
-            else
+              if (SPLIT == 3 && p.lo_tma)   // the producer of a0 also wrote its TF32 remainder: no transform needed
+                tma_load_3d(a_ring + sa * C::A_STAGE + A_TILE, &map_a0lo, afull_bar(sa), ag * BK, mt * BM + p.row_base0, item);
+            } else
               tma_load_3d(a_ring + sa * C::A_STAGE, &map_a1, afull_bar(sa), (ag - p.n_cb0) * BK, mt * BM + p.row_base1, item);
           }
           __syncwarp();
@@ -301,6 +304,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           mbar_wait(afull_bar(sa), (ia / SA) & 1u);
           const float4* a = reinterpret_cast<const float4*>(smem_gen + sa * C::A_STAGE);
           float4* alo = reinterpret_cast<float4*>(smem_gen + sa * C::A_STAGE + A_TILE);
+          if (p.lo_tma) {   // a_lo arrived by TMA together with a
+            __syncwarp();
+            if (lane == 0) mbar_arrive(aready_bar(sa));
+            continue;
+          }
 #pragma unroll 4
           for (int i = tt; i < n4; i += 64) {
             const float4 v = a[i];
@@ -428,6 +436,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 #undef ECB_CELL
         *reinterpret_cast<float4*>(q.c + (long long)m * q.H + u0) = cv;
         *reinterpret_cast<float4*>(q.h_out + (long long)m * q.H + u0) = hv;
+        if (q.h_lo_out)
+          *reinterpret_cast<float4*>(q.h_lo_out + (long long)m * q.H + u0) =
+              make_float4(rn_tf32(hv.x - trunc_tf32(hv.x)), rn_tf32(hv.y - trunc_tf32(hv.y)), rn_tf32(hv.z - trunc_tf32(hv.z)),
+                          rn_tf32(hv.w - trunc_tf32(hv.w)));
         float4 y = hv;
         if (q.skip) {
           const float4 sv = __ldg(reinterpret_cast<const float4*>(q.skip + (long long)m * q.skip_stride + u0));
@@ -559,7 +571,7 @@ int launch_one(const CUtensorMap* maps, const TcArgs& a, int grid, cudaStream_t 
     ECB_CUDA(cudaFuncSetAttribute(tc_conv_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
-  tc_conv_kernel<BN, SPLIT><<<grid, TC_THREADS, C::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], a);
+  tc_conv_kernel<BN, SPLIT><<<grid, TC_THREADS, C::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], a);
   ECB_LAUNCHED();
   return 0;
 }
@@ -645,8 +657,10 @@ int launch_tc_conv(const TcConvParams& p, cudaStream_t stream) {
   const int s = p.stride;
   const int ktot = p.taps * p.C0 + (p.a1 ? p.C1 : 0);
   ECB_REQUIRE(p.taps % s == 0, "tc_conv: kernel size %d must be a multiple of the stride %d", p.taps, s);
-  CUtensorMap maps[4];
+  CUtensorMap maps[5];
   TcArgs a;
+  ECB_REQUIRE(!p.a0_lo || (p.split == 3 && !p.a1), "tc_conv: a0_lo needs split == 3 and a single source");
+  a.lo_tma = p.a0_lo ? 1 : 0;
   // the taps of the conv are row shifts of one [a_rows x 32] tile per 32-channel block of the (folded) input row
   a.shifts = p.taps / s;
   a.n_cb0 = s * p.C0 / BK;
@@ -666,6 +680,11 @@ int launch_tc_conv(const TcConvParams& p, cudaStream_t stream) {
     const cuuint64_t strides[2] = {(cuuint64_t)s * p.C0 * 4, (cuuint64_t)p.a0_item_stride * 4};
     const cuuint32_t box[3] = {BK, (cuuint32_t)a.a_rows, 1};
     if (make_tensor_map(&maps[0], p.a0 + d * p.C0, 3, dims, strides, box)) return 1;
+    if (p.a0_lo) {
+      if (make_tensor_map(&maps[4], p.a0_lo + d * p.C0, 3, dims, strides, box)) return 1;
+    } else {
+      maps[4] = maps[0];
+    }
   }
   if (p.a1) {
     const cuuint64_t dims[3] = {(cuuint64_t)p.C1, (cuuint64_t)p.a1_rows, (cuuint64_t)p.n_items};

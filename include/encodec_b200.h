@@ -161,6 +161,10 @@ void ecb_debug_tap(float* buf, int64_t capacity, int32_t stage);
  * m*stride - pad_left ... + taps - 1 of source 0, then row m of the optional 1-tap source a1. w is [taps*C0 + C1][N]
  * (N contiguous). out_raw / out_elu point at (item 0, row 0) of [M][N] outputs with `halo` reflected rows written
  * before and after each item. split = 3: fp32-accurate split-operand TF32, 1: single TF32 pass. Synchronises. */
+/* Diagnostic: the encoder's SLSTM alone on x [B][T][H] -> out [B][T][H] (tools/lstm_bench.py). */
+size_t ecb_debug_lstm_workspace_bytes(const ecb_codec* codec, int64_t batch, int64_t T);
+int ecb_debug_lstm(ecb_codec* codec, const float* x, float* out, int64_t batch, int64_t T, void* workspace,
+                   size_t workspace_bytes, void* stream);
 int ecb_debug_tc_conv(const float* a0, int64_t a0_item_stride, int32_t C0, int64_t a0_first, int64_t a0_rows,
                       int32_t taps, int32_t stride, int32_t pad_left, const float* a1, int64_t a1_item_stride,
                       int32_t C1, int64_t a1_rows, const float* w, const float* bias, int32_t N, int64_t M,
