@@ -828,7 +828,7 @@ struct LstmGraph {
   LstmGraphKey key;
   cudaGraphExec_t exec;
 };
-std::vector<LstmGraph> g_lstm_graphs;   // a handful of entries (layers x shapes); oldest dropped beyond 16
+std::vector<LstmGraph> g_lstm_graphs;   // a handful of entries (layers x shapes); oldest dropped beyond 32
 cudaStream_t g_capture_stream = nullptr;
 
 int lstm_stepwise_mode() {
@@ -914,7 +914,7 @@ int lstm_steps(Ctx& x, const LstmLayerW& lw, const float* pre, long long pre_str
   const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
   cudaGraphDestroy(graph);
   ECB_CUDA(ie);
-  if (g_lstm_graphs.size() >= 16) {
+  if (g_lstm_graphs.size() >= 32) {
     cudaGraphExecDestroy(g_lstm_graphs.front().exec);
     g_lstm_graphs.erase(g_lstm_graphs.begin());
   }
