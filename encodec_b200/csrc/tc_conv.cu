@@ -73,6 +73,7 @@ struct TcArgs {
   int a_rows;               // rows per A tile box: BM (+ 8 when shifts > 1)
   int row_base0, row_base1; // row coordinate of output row 0's window start in each source's map
   int round_out, halo;
+  int w_resident;           // 1: all weight chunks of the layer fit the B ring and the CTA keeps one N tile: load them once
   int lo_tma;               // 1: the A_lo tile is loaded by TMA (map_a0lo) instead of being computed by the transform warps
   int cell_on;              // 1: LSTM cell epilogue (cell) instead of the output stores
   TcCell cell;
@@ -220,6 +221,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           __syncwarp();
           const int nj = ag < p.n_cb0 ? p.shifts : 1;
           for (int j = 0; j < nj; ++j, ++ib) {
+            if (p.w_resident && ib >= (uint32_t)nch) continue;   // the weights of this CTA's only N tile are already resident
             const int sb = (int)(ib % SB);
             mbar_wait(bempty_bar(sb), ((ib / SB) & 1u) ^ 1u);
             const int k0 = ag < p.n_cb0 ? (j * p.n_cb0 + ag) * BK : (nch0 + (ag - p.n_cb0)) * BK;
@@ -261,8 +263,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           for (int j = 0; j < nj; ++j, ++ib, ++c) {
             if (in_group == 0) mbar_wait(maine_bar((int)(gcount & 1u)), ((gcount >> 1) & 1u) ^ 1u);   // accumulator drained
             const uint32_t d_main = tmem_base + main_col((int)(gcount & 1u));
-            const int sb = (int)(ib % SB);
-            mbar_wait(bfull_bar(sb), (ib / SB) & 1u);
+            const int sb = p.w_resident ? c : (int)(ib % SB);
+            mbar_wait(bfull_bar(sb), p.w_resident ? 0u : ((ib / SB) & 1u));   // resident: phase 0 completed once, for good
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const bool close_group = (in_group + 1 == p.group) || (c + 1 == nch);
             if (elect_one()) {
@@ -278,7 +280,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                 tcgen05_mma_tf32(d_main, da0 + 2u * k, db0 + 2u * k, idesc2, (in_group > 0 || k > 0) ? 1u : 0u);
                 if (SPLIT == 3) tcgen05_mma_tf32(d_main + BN, dal0 + 2u * k, db0 + 2u * k, idesc, 1u);
               }
-              tcgen05_commit(bempty_bar(sb));                                  // weight stage free once these MMAs have read it
+              if (!p.w_resident) tcgen05_commit(bempty_bar(sb));               // weight stage free once these MMAs have read it
               if (close_group) tcgen05_commit(mainf_bar((int)(gcount & 1u)));  // K group complete -> epilogue
               if (j + 1 == nj) tcgen05_commit(aempty_bar(sa));                 // A tile free once all its taps are done
             }
@@ -571,7 +573,19 @@ int launch_one(const CUtensorMap* maps, const TcArgs& a, int grid, cudaStream_t 
     ECB_CUDA(cudaFuncSetAttribute(tc_conv_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
-  tc_conv_kernel<BN, SPLIT><<<grid, TC_THREADS, C::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], a);
+  TcArgs b = a;
+  {
+    // small layers: every weight chunk fits the B ring, and with a single N tile each CTA needs the same ones for all
+    // of its tiles -> load them once (saves the TMA refill and the L2 reads of the weights per output tile)
+    static int off = -1;
+    if (off < 0) {
+      const char* e = getenv("ECB_TC_WRES");   // diagnostic: ECB_TC_WRES=0 reloads the weights for every tile
+      off = (e && e[0] == '0') ? 1 : 0;
+    }
+    const int nch = a.n_cb0 * a.shifts + a.n_cb1;
+    b.w_resident = (!off && a.tiles_n == 1 && nch <= C::B_STAGES) ? 1 : 0;
+  }
+  tc_conv_kernel<BN, SPLIT><<<grid, TC_THREADS, C::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], b);
   ECB_LAUNCHED();
   return 0;
 }
