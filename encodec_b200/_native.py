@@ -37,6 +37,7 @@ SIGNATURES = {
     "ecb_version": (C.c_int, []),
     "ecb_launch_count": (C.c_int64, []),
     "ecb_debug_tap": (None, [C.c_void_p, C.c_int64, C.c_int32]),
+    "ecb_debug_lstm_trace": (None, [C.c_void_p]),
     "ecb_debug_lstm_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int64, C.c_int64]),
     "ecb_debug_lstm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p]),
     "ecb_debug_tc_conv": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_int32,

@@ -89,6 +89,7 @@ struct LstmLayerW {
   float* t_lo = nullptr;
   float* r_hi = nullptr;  // recurrent weights W_hh in the same form, for the step-wise (large-batch) recurrence
   float* r_lo = nullptr;
+  float* r_f16 = nullptr; // fp16 split slices of W_hh for the persistent tensor-core recurrence (lstm_tc.cu), H = 512
 };
 
 }  // namespace
@@ -224,6 +225,10 @@ int prepare_lstm(ecb_codec* c, const std::string& prefix, int H, std::vector<Lst
     if (dev_alloc(c, &whh_t, 4LL * H * H)) return 1;
     if (launch_lstm_gate_interleave(whh, whh_t, H, st)) return 1;  // [4H][H] -> [H][4H], gate-interleaved columns (TcCell)
     if (prepare_tc(c, whh_t, nullptr, H, 4 * H, 4 * H, &lw.r_hi, &lw.r_lo, nullptr, st)) return 1;
+    if (lstm_tc_supported(1, H)) {
+      if (dev_alloc(c, &lw.r_f16, 4LL * H * H)) return 1;   // 2 x [4H][H] halves
+      if (launch_lstm_tc_pack(whh, lw.r_f16, H, st)) return 1;
+    }
   }
   return 0;
 }
@@ -831,6 +836,12 @@ struct LstmGraph {
 std::vector<LstmGraph> g_lstm_graphs;   // a handful of entries (layers x shapes); oldest dropped beyond 32
 cudaStream_t g_capture_stream = nullptr;
 
+int lstm_tc_mode() {
+  const char* e = getenv("ECB_LSTM_TC");   // 0: off, 1 (default): launches below 320 items, 2: every supported launch
+  if (!e || !e[0]) return 1;
+  return e[0] == '0' ? 0 : (e[0] == '2' ? 2 : 1);
+}
+
 int lstm_stepwise_mode() {
   const char* e = getenv("ECB_LSTM_STEPWISE");   // 0: never, 1: always, unset: automatic (>= 320 items per launch)
   if (!e || !e[0]) return -1;
@@ -932,13 +943,20 @@ int tc_lstm(Ctx& x, const std::vector<LstmLayerW>& layers, const Act& X, float* 
   const int mode = lstm_stepwise_mode();
   // measured: the persistent FFMA kernel costs ~0.067 us per item and step, the step-wise form ~17 us per step + little per item
   const bool stepwise = mode == 1 || (mode < 0 && x.n_items >= 320);
+  // the persistent tensor-core recurrence (lstm_tc.cu); ECB_LSTM_TC=0 keeps the CUDA-core / step-wise forms
+  const bool tcrec = !(mode == 1) && lstm_tc_mode() && layers[0].r_f16 && lstm_tc_supported(x.n_items, H) &&
+                     (lstm_tc_mode() == 2 || x.n_items < 320);
   for (int l = 0; l < L; ++l) {
     if (tc_run(x, layers[l].t_hi, layers[l].t_lo, layers[l].bias, H, 4 * H, *cur, H, 1, 1, 0, true, nullptr, pre.row0(), nullptr,
                pre.stride(), X.T, 0, split, 0))
       return 1;
     const bool last = (l == L - 1);
     Act& dst = last ? out : h0;
-    if (stepwise) {
+    if (tcrec) {
+      if (launch_lstm_tc(pre.row0(), pre.stride(), layers[l].r_f16, last ? X.row0() : nullptr, X.stride(), dst.row0(), dst.stride(),
+                         x.n_items, (int)X.T, last ? 1 : 0, x.lstm_ws, x.st))
+        return 1;
+    } else if (stepwise) {
       if (lstm_steps(x, layers[l], pre.row0(), pre.stride(), last ? X.row0() : nullptr, X.stride(), dst.row0(), dst.stride(), (int)X.T, H,
                      split, last ? 1 : 0))
         return 1;
@@ -1316,6 +1334,8 @@ int ecb_profile_end(ecb_prof_entry* out, int capacity) {
     if (acc[i].launches) out[n++] = acc[i];
   return n;
 }
+void ecb_debug_lstm_trace(long long* buf) { ecb::g_lstm_tc_trace = buf; }
+
 void ecb_debug_tap(float* buf, int64_t capacity, int32_t stage) {
   g_tap.buf = buf;
   g_tap.cap = capacity;

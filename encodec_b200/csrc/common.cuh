@@ -163,6 +163,19 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 static inline long long cdiv(long long a, long long b) { return (a + b - 1) / b; }
 
+// Per-device once-flags: function attributes (dynamic shared memory opt-in) belong to a device, and a process may drive
+// several. The flag is set after the attribute call, so a concurrent first use merely sets the attribute twice.
+struct DeviceOnce {
+  std::atomic<unsigned long long> mask{0};
+  static unsigned long long bit() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return 1ull << (dev & 63);
+  }
+  bool done() const { return (mask.load(std::memory_order_acquire) & bit()) != 0; }
+  void mark() { mask.fetch_or(bit(), std::memory_order_release); }
+};
+
 // Reflection length for a signal of T samples padded by (left, right): pad1d, reference conv.py:80-97.
 static inline int reflect_length(long long T, long long left, long long right) {
   const long long max_pad = left > right ? left : right;
@@ -381,6 +394,15 @@ int launch_lstm_cell(const float* pre_t, long long pre_item_stride, const float*
 int launch_lstm_recurrent(const float* pre, const float* w_hh_packed, const float* skip, long long skip_item_stride,
                           float* out, long long out_item_stride, int batch, int T, int H, int out_elu,
                           float* workspace, cudaStream_t s);
+
+// lstm_tc.cu: the recurrence on the tensor cores (H = 512, up to 1024 items per launch). w_packed comes from
+// launch_lstm_tc_pack (fp16 split slices of W_hh, 4H * H * 2 halves); same pre / skip / out conventions as above.
+extern long long* g_lstm_tc_trace;
+bool lstm_tc_supported(int batch, int H);
+int lstm_tc_workspace_floats(int batch);
+int launch_lstm_tc_pack(const float* whh, void* packed, int H, cudaStream_t s);
+int launch_lstm_tc(const float* pre, long long pre_item_stride, const void* w_packed, const float* skip, long long skip_item_stride,
+                   float* out, long long out_item_stride, int batch, int T, int out_elu, float* workspace, cudaStream_t s);
 
 // ------------------------------------------------------------------------------------------------
 // rvq.cu

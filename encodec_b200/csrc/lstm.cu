@@ -334,10 +334,10 @@ int launch_impl(const float* pre, const float* w_hh, const float* skip, long lon
   const int qi = group_items(batch, G::NQ);
   const size_t smem = lstm_smem_bytes<LH>(qi);
   ECB_REQUIRE(smem <= 200 * 1024, "lstm: batch %d needs %zu bytes of shared memory; split the batch", batch, smem);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  if (!attr_set.done()) {
     ECB_CUDA(cudaFuncSetAttribute(lstm_recurrent_kernel<LH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
+    attr_set.mark();
   }
   LstmParams p;
   p.pre = pre;
@@ -431,7 +431,9 @@ int lstm_recurrent_workspace_floats(int batch, int H) {
   const int qi = group_items(batch, nq);
   const int persistent = 2 * nq * qi * H + nq * qi / L_SB + 64;
   const int stepwise = 9 * H * batch + 64;   // rec [B][4H], h [2][B][H], c [B][H], h_lo [2][B][H]
-  return persistent > stepwise ? persistent : stepwise;
+  int need = persistent > stepwise ? persistent : stepwise;
+  if (lstm_tc_supported(batch, H) && lstm_tc_workspace_floats(batch) > need) need = lstm_tc_workspace_floats(batch);
+  return need;
 }
 
 int launch_lstm_recurrent(const float* pre, const float* w_hh, const float* skip, long long skip_item_stride, float* out,

@@ -264,11 +264,11 @@ int launch_rvq_encode(const float* frames, long long n, const float* codebooks, 
   const int RD = dim;
   ECB_REQUIRE(n > 0 && n_q > 0, "rvq: empty input (n=%lld, n_q=%d)", n, n_q);
   ECB_REQUIRE(bins % R_EC == 0, "rvq: bins=%d must be a multiple of %d", bins, R_EC);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  if (!attr_set.done()) {
     ECB_CUDA(cudaFuncSetAttribute(rvq_encode_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rvq_smem(128)));
     ECB_CUDA(cudaFuncSetAttribute(rvq_encode_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rvq_smem(256)));
-    attr_set = true;
+    attr_set.mark();
   }
   RvqParams p;
   p.frames = frames;

@@ -348,10 +348,10 @@ int launch_rvq_encode_tc(const float* frames, long long n, const float* codebook
   const cuuint32_t box[2] = {KC, EB};
   if (make_tensor_map(&mh, cb_hi, 2, dims, strides, box)) return 1;
   if (make_tensor_map(&ml, cb_lo, 2, dims, strides, box)) return 1;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  if (!attr_set.done()) {
     ECB_CUDA(cudaFuncSetAttribute(rvq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
+    attr_set.mark();
   }
   RvqTcArgs a;
   a.frames = frames;

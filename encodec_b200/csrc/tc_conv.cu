@@ -568,10 +568,10 @@ __global__ void split_weights_kernel(const float* __restrict__ w, float* __restr
 template <int BN, int SPLIT>
 int launch_one(const CUtensorMap* maps, const TcArgs& a, int grid, cudaStream_t stream) {
   using C = Cfg<BN, SPLIT>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  if (!attr_set.done()) {
     ECB_CUDA(cudaFuncSetAttribute(tc_conv_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_set = true;
+    attr_set.mark();
   }
   TcArgs b = a;
   {
@@ -627,13 +627,30 @@ int make_tensor_map(CUtensorMap* map, const float* base, int rank, const cuuint6
   return 0;
 }
 
+// same for fp16 tensors (lstm_tc.cu: recurrent state / weight slices), SWIZZLE_128B
+int make_tensor_map_f16(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                        const cuuint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  ECB_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  ECB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (fp16) failed with CUresult %d (rank %d, base %p)", (int)r, rank, base);
+  return 0;
+}
+
+// SM count of the current device (cached per device: a process may drive several GPUs)
 int sm_count() {
-  static int n = 0;
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  int n = cache[dev].load(std::memory_order_relaxed);
   if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
+    cache[dev].store(n, std::memory_order_relaxed);
   }
   return n;
 }

@@ -140,6 +140,8 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32(int m, int n) {
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no libcuda link dependency); fp32, SWIZZLE_128B.
 int make_tensor_map(CUtensorMap* map, const float* base, int rank, const cuuint64_t* dims,
                     const cuuint64_t* strides_bytes, const cuuint32_t* box);
+int make_tensor_map_f16(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                        const cuuint32_t* box);
 int sm_count();
 
 }  // namespace ecb

@@ -396,10 +396,10 @@ int launch_tc_res32(const TcResParams& p, cudaStream_t stream) {
   a.row_base = (int)(-p.pad_left - p.x_first);
   a.pad_left = p.pad_left;
   a.halo = p.halo;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static DeviceOnce attr_set;
+  if (!attr_set.done()) {
     ECB_CUDA(cudaFuncSetAttribute(tc_res_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, R_SMEM));
-    attr_set = true;
+    attr_set.mark();
   }
   const int grid = (int)(total < sm_count() ? total : sm_count());
   const double rows = (double)p.M * p.n_items;

@@ -154,6 +154,9 @@ int ecb_transpose_btc_to_bct(const float* in, float* out, int64_t batch, int64_t
  * skip + ELU); decoder: 100 first conv, 101 LSTM, 102+2i transposed conv i, 103+2i residual block i) into
  * buf (at most `capacity` floats). buf == NULL disables the tap. */
 void ecb_debug_tap(float* buf, int64_t capacity, int32_t stage);
+/* Diagnostic: while buf != NULL the persistent tensor-core LSTM kernel (lstm_tc.cu) records clock64 stamps of CTA 0 for
+ * steps 20..27 into buf ([3 roles][8 steps][16 events] int64, device memory); tools/lstm_trace.py prints them. */
+void ecb_debug_lstm_trace(long long* buf);
 
 /* Diagnostic (tests only): one launch of the tensor-core implicit-GEMM convolution (csrc/tc_conv.cu) on caller
  * buffers. a0 points at (item 0, sample a0_first, channel 0) of a channels-last activation from which a0_rows

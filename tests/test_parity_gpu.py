@@ -423,11 +423,12 @@ def test_stepwise_tensor_core_lstm_matches_reference_golden(name, monkeypatch):
         assert d.max() < AUDIO_MAX_ABS and np.sqrt((d ** 2).mean()) < AUDIO_RMS
 
 
-@pytest.mark.parametrize("batch,steps", [(5, 40), (130, 24), (330, 16)])
+@pytest.mark.parametrize("batch,steps", [(5, 40), (64, 48), (130, 24), (330, 16)])
 def test_lstm_recurrence_forms_agree(batch, steps, monkeypatch):
-    """The two implementations of the SLSTM recurrence -- the persistent fp32 FFMA kernel and the step-wise tensor-core form
-    (3xTF32 GEMM + fused cell epilogue from a CUDA graph) -- on the same random input at batch sizes that exercise ragged
-    sub-groups, several M tiles and the automatic switch; and against a float64 LSTM computed on the CPU."""
+    """The three implementations of the SLSTM recurrence -- the persistent tensor-core kernel (fp16 split operands, lstm_tc.cu),
+    the persistent fp32 FFMA kernel and the step-wise tensor-core form (3xTF32 GEMM + fused cell epilogue from a CUDA graph) --
+    on the same random input at batch sizes that exercise ragged groups, several M tiles and the automatic switch; and
+    against a float64 LSTM computed on the CPU."""
     from encodec_b200 import _native as nat, synth
     case = gc.load_model_case("24k_24kbps_ragged")
     m = ug.build_model(case["spec"], case["sd"], 6.0, case["distinct"])
@@ -436,19 +437,21 @@ def test_lstm_recurrence_forms_agree(batch, steps, monkeypatch):
     x = torch.from_numpy(synth.hash_normal(77, "lstm-x", (batch, steps, H))).cuda()
     ws = torch.empty(nat.lib.ecb_debug_lstm_workspace_bytes(codec.handle, batch, steps), dtype=torch.uint8, device="cuda")
     outs = {}
-    for mode in ("0", "1"):
-        monkeypatch.setenv("ECB_LSTM_STEPWISE", mode)
+    for name, tc_mode, step_mode in (("tensor", "2", "0"), ("ffma", "0", "0"), ("stepwise", "0", "1")):
+        monkeypatch.setenv("ECB_LSTM_TC", tc_mode)
+        monkeypatch.setenv("ECB_LSTM_STEPWISE", step_mode)
         out = torch.empty_like(x)
         nat.check(nat.lib.ecb_debug_lstm(codec.handle, x.data_ptr(), out.data_ptr(), batch, steps, ws.data_ptr(), ws.numel(),
                                          nat.stream_ptr(x.device)))
         torch.cuda.synchronize()
-        outs[mode] = out.cpu().numpy()
+        outs[name] = out.cpu().numpy()
     # float64 truth: ELU(lstm(x) + x) with the encoder's LSTM weights (reference modules/lstm.py:22-28, seanet.py:126)
     p = orc.Params(case["sd"], np.float64)
     xin = np.transpose(x.cpu().numpy().astype(np.float64), (0, 2, 1))          # [B, C, T]
     idx = 1 + 3 * len(case["spec"].ratios)
     want = orc.elu(orc.slstm(xin, p, f"encoder.model.{idx}", case["spec"].lstm))
     want = np.transpose(want, (0, 2, 1))
-    for mode, got in outs.items():
-        assert ug.rel_err(got, want) < 5e-6, (mode, ug.rel_err(got, want))
-    assert ug.rel_err(outs["0"], outs["1"]) < 5e-6
+    for name, got in outs.items():
+        assert ug.rel_err(got, want) < 5e-6, (name, ug.rel_err(got, want))
+    assert ug.rel_err(outs["ffma"], outs["stepwise"]) < 5e-6
+    assert ug.rel_err(outs["ffma"], outs["tensor"]) < 5e-6

@@ -26,14 +26,15 @@ dev = torch.device("cuda")
 st = nat.stream_ptr(dev)
 T, H = int(os.environ.get("LSTM_T", "150")), 512
 print(f"{'B':>5s} {'mode':>10s} {'ms':>8s} {'us/step':>8s}")
-for B in (64, 128, 256, 384, 512, 960):
+for B in [int(v) for v in os.environ.get("LSTM_B", "64,128,256,512,960").split(",")]:
     x = torch.randn(B, T, H, device=dev)
     out = torch.empty_like(x)
     ws = torch.empty(nat.lib.ecb_debug_lstm_workspace_bytes(codec.handle, B, T), dtype=torch.uint8, device=dev)
     ref = None
-    for mode, lo in (("0", "1"), ("1", "0"), ("1", "1")):
+    for mode, lo, tcm in (("0", "1", "0"), ("0", "1", "2"), ("1", "1", "0")):
         os.environ["ECB_LSTM_STEPWISE"] = mode
         os.environ["ECB_LSTM_LO_TMA"] = lo
+        os.environ["ECB_LSTM_TC"] = tcm
 
         def run():
             nat.check(nat.lib.ecb_debug_lstm(codec.handle, x.data_ptr(), out.data_ptr(), B, T, ws.data_ptr(), ws.numel(), st))
@@ -52,5 +53,5 @@ for B in (64, 128, 256, 384, 512, 960):
             err = 0.0
         else:
             err = float((out - ref).abs().max())
-        print(f"{B:5d} {('stepwise' + ('+lo' if lo == '1' else '')) if mode == '1' else 'persistent':>11s} {ms:8.3f} {ms * 1e3 / (2 * T):8.2f}   max |diff| vs persistent {err:.2e}",
+        print(f"{B:5d} {'stepwise' if mode == '1' else ('tensor' if tcm == '2' else 'ffma'):>11s} {ms:8.3f} {ms * 1e3 / (2 * T):8.2f}   max |diff| vs persistent {err:.2e}",
               flush=True)
