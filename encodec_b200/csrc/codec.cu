@@ -941,11 +941,16 @@ int tc_lstm(Ctx& x, const std::vector<LstmLayerW>& layers, const Act& X, float* 
   Act h0 = act_of(h0_buf, H, X.T, 0);
   const Act* cur = &X;
   const int mode = lstm_stepwise_mode();
-  // measured: the persistent FFMA kernel costs ~0.067 us per item and step, the step-wise form ~17 us per step + little per item
-  const bool stepwise = mode == 1 || (mode < 0 && x.n_items >= 320);
-  // the persistent tensor-core recurrence (lstm_tc.cu); ECB_LSTM_TC=0 keeps the CUDA-core / step-wise forms
-  const bool tcrec = !(mode == 1) && lstm_tc_mode() && layers[0].r_f16 && lstm_tc_supported(x.n_items, H) &&
-                     (lstm_tc_mode() == 2 || x.n_items < 320);
+  // Three forms of the recurrence, chosen by items per launch (tools/lstm_bench.py on a B200, us per layer step, T = 750):
+  //   items        1     16     32     64    128    256    384    960
+  //   FFMA       3.3    4.0    4.9    5.7    9.5   19.1   28.6   71.2    persistent CUDA-core kernel (lstm.cu)
+  //   tensor     4.3    4.6    4.6    5.3    7.0   12.9   19.3   48.0    persistent tcgen05 kernel (lstm_tc.cu)
+  //   step-wise   -      -      -    14.5   17.1   19.3   25.2   43.0    one tc_conv launch per step from a CUDA graph
+  // ECB_LSTM_TC=0 / ECB_LSTM_STEPWISE=0|1 force a form (diagnostics, parity tests).
+  const int tc_mode = lstm_tc_mode();
+  const bool tcrec = mode != 1 && tc_mode && layers[0].r_f16 && lstm_tc_supported(x.n_items, H) &&
+                     (tc_mode == 2 || (x.n_items >= 24 && x.n_items <= 640));
+  const bool stepwise = mode == 1 || (mode < 0 && !tcrec && x.n_items >= 320);
   for (int l = 0; l < L; ++l) {
     if (tc_run(x, layers[l].t_hi, layers[l].t_lo, layers[l].bias, H, 4 * H, *cur, H, 1, 1, 0, true, nullptr, pre.row0(), nullptr,
                pre.stride(), X.T, 0, split, 0))

@@ -13,9 +13,15 @@
 //     h = h1 + 2^-11 h2,  h1 = fp16(h), h2 = fp16((h - h1) 2^11)        (written by the producer of h)
 //     w = w1 + 2^-11 w2                                                 (split once at load, lstm_tc_pack)
 //     rec = sum h1 w1  +  2^-11 (sum h1 w2 + sum h2 w1)                 (h2 w2 2^-22 dropped, as in the 3xTF32 scheme)
-// fp16 x fp16 products are exact in the fp32 accumulator. Per K step of 16: one MMA with N = 32, D[main | corr] (+)=
-// h1 . [w1 | w2], and one with N = 16, D[corr] += h2 . w1. The tensor core truncates when it adds into its accumulator
-// (tc_conv.cu), so each K half gets its own accumulator pair (16 accumulating MMAs each) and the epilogue adds the halves.
+// fp16 x fp16 products are exact in the fp32 accumulator. Small MMAs cost ~55 cycles each whatever their shape (measured:
+// the first version issued two M = 64 MMAs per K step and spent 3500 of its 9000 cycles per step in the tensor pipe), so
+// all three products come from ONE M = 128, N = 32 MMA per K step of 16: the A tile stacks the h1 rows and the h2 rows of
+// the 64 items (rows 32 q + r = h1 of item 16 q + r, rows 32 q + 16 + r = its h2, so both land in the same TMEM lane
+// quadrant), B = [w1 | w2]; D rows of h1 give [h1 w1 | h1 w2], D rows of h2 give [h2 w1 | (h2 w2, unused)], and the epilogue
+// adds the pieces with one warp shuffle. Back-to-back MMAs into the SAME accumulator columns serialise on the tensor pipe's
+// latency (~100 cycles each at this size), so the four K sub-steps of a tile go to four independent accumulators which the
+// epilogue sums; that also keeps every accumulator at 8 accumulating MMAs (the tensor core truncates when it adds into its
+// accumulator, tc_conv.cu).
 //
 // Roles (12 warps): warp 0 = loader (polls the 8 per-K-tile arrival counters of the group with one coalesced acquire load,
 // then TMA-loads h1 / h2 tiles [64 items x 64 units], SWIZZLE_128B, into an 8-stage ring), warp 1 = MMA issuer, warps 4-11 =
@@ -36,15 +42,16 @@ constexpr int LT_H = 512;
 constexpr int LT_CTAS = 128;        // unit blocks
 constexpr int LT_UNITS = 4;         // hidden units per CTA
 constexpr int LT_NCOL = 16;         // gate columns per CTA: n = unit * 4 + gate
-constexpr int LT_ITEMS = 64;        // items per group = MMA M
+constexpr int LT_ITEMS = 64;        // most items per group (IG = 64: MMA M = 128; IG = 32: M = 64)
 constexpr int LT_KT = 64;           // K elements per shared-memory tile (128 bytes of fp16)
 constexpr int LT_NKT = LT_H / LT_KT;   // 8
 constexpr int LT_STAGES = 8;
 constexpr int LT_THREADS = 384;
-constexpr int LT_A_TILE = LT_ITEMS * 128;         // 8 KB
-constexpr int LT_STAGE_BYTES = 2 * LT_A_TILE;     // h1 tile + h2 tile
+constexpr int LT_ROWS = 2 * LT_ITEMS;             // most A rows per group: h1 and h2 row of every item
+constexpr int LT_STAGE_BYTES = LT_ROWS * 128;     // ring slot: one [128 rows x 64 k] tile, 16 KB (IG = 32 uses half of it)
 constexpr int LT_W_TILE = 2 * LT_NCOL * 128;      // [w1 (16 rows) | w2 (16 rows)] x 64 k = 4 KB
-constexpr int LT_ACC_COLS = 64;                   // per accumulator buffer: 2 K halves x [main 16 | corr 16]
+constexpr int LT_NACC = 4;                        // independent accumulators per buffer (K sub-step k of every tile -> accumulator k)
+constexpr int LT_ACC_COLS = LT_NACC * 32;         // per accumulator buffer: LT_NACC x [main 16 | corr 16]
 constexpr int LT_MAX_GROUPS = 16;
 constexpr float LT_LO_SCALE = 2048.f;             // 2^11
 
@@ -55,10 +62,11 @@ struct LstmTcParams {
   long long skip_stride;
   float* out;            // item b at out + b * out_stride, [T][H]
   long long out_stride;
-  __half* h1g;           // [2][G * 64][512] exchange buffers (L2-resident)
-  __half* h2g;
+  __half* hg;            // [2][G * 2 IG][512] exchange buffers (L2-resident); row 32 q + 16 part + r of a group = split part
+                         // `part` (0: h1, 1: h2) of item 16 q + r
   unsigned int* cnt;     // [G][8] arrival counters (one per group and K tile), zeroed by the host
   int B, T, G, out_elu;
+  int dbg;               // diagnostic switches (ECB_LSTM_DBG): 1 = no per-tile stage release (single group only)
   long long* trace;      // diagnostic: [3 roles][LT_TR_STEPS][16] clock64 stamps of CTA 0, or nullptr
 };
 constexpr int LT_TR_STEPS = 8, LT_TR_T0 = 20;
@@ -66,7 +74,34 @@ constexpr int LT_TR_STEPS = 8, LT_TR_T0 = 20;
   if (p.trace && cta == 0 && (t) >= LT_TR_T0 && (t) < LT_TR_T0 + LT_TR_STEPS && lane == 0)                           \
     p.trace[((role) * LT_TR_STEPS + ((t) - LT_TR_T0)) * 16 + (ev)] = clock64();
 
-__device__ __forceinline__ float sigmoid_acc(float x) { return 1.f / (1.f + expf(-x)); }
+// sigmoid of two values on packed fp32 pairs (fma.rn.f32x2: two IEEE FMAs per issue slot): e^-x by range reduction
+// -x = n ln2 + r and the degree-7 expm1 polynomial of elu1 (about 1 ulp), then 1 / (1 + 2^n (1 + expm1(r))) with a
+// correctly rounded reciprocal. Absolute error about 1e-7; tanh(x) = 2 sigmoid(2 x) - 1 inherits it (absolute, which is
+// what the cell update needs: gates and states are O(1)).
+__device__ __forceinline__ void sigmoid_pair(float (&v)[2]) {
+#define LT_F2C(x) f2_pack((x), (x))
+  const unsigned long long y = f2_pack(fminf(fmaxf(-v[0], -87.f), 87.f), fminf(fmaxf(-v[1], -87.f), 87.f));
+  const unsigned long long t = f2_fma(y, LT_F2C(1.4426950408889634f), LT_F2C(12582912.f));
+  const unsigned long long n = f2_add(t, LT_F2C(-12582912.f));
+  unsigned long long r = f2_fma(n, LT_F2C(-0.693145751953125f), y);
+  r = f2_fma(n, LT_F2C(-1.428606765330187e-06f), r);
+  unsigned long long q = f2_fma(LT_F2C(1.9841270e-4f), r, LT_F2C(1.3888889e-3f));
+  q = f2_fma(q, r, LT_F2C(8.3333333e-3f));
+  q = f2_fma(q, r, LT_F2C(4.1666667e-2f));
+  q = f2_fma(q, r, LT_F2C(1.6666667e-1f));
+  q = f2_fma(q, r, LT_F2C(0.5f));
+  q = f2_fma(f2_mul(q, r), r, r);   // expm1(r)
+  float t0, t1;
+  f2_unpack(t, t0, t1);
+  const unsigned long long s = f2_pack(__int_as_float((__float_as_int(t0) << 23) + 0x3f800000),
+                                       __int_as_float((__float_as_int(t1) << 23) + 0x3f800000));   // 2^n
+  const unsigned long long d = f2_fma(q, s, f2_add(s, LT_F2C(1.f)));   // 1 + e^-x
+  float d0, d1;
+  f2_unpack(d, d0, d1);
+  v[0] = __frcp_rn(d0);
+  v[1] = __frcp_rn(d1);
+#undef LT_F2C
+}
 
 __device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -86,12 +121,30 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 // kind::f16 instruction descriptor: D fp32 (bits [4,6) = 1), A / B fp16 (format 0), both K-major, N >> 3 in [17,23), M >> 4 in [24,29)
 constexpr uint32_t idesc_f16(int m, int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24); }
 
+// CL = cluster size (1, 2, 4): the CTAs of a cluster need the same h tiles, so each loads 1 / CL of the rows of every tile
+// and TMA-multicasts them to all. IG = items per group (64 | 32). What paces a step is the tensor pipe streaming the A rows
+// (~0.8 cycles per row and MMA, whatever N is) inside a chain of ~1000-cycle hops (publish, poll, TMA, commit); a batch of
+// <= 64 items therefore runs as TWO groups of 32 (M = 64 MMAs): each group's chain is shorter and the two interleave.
+template <int CL, int IG>
 __global__ void __launch_bounds__(LT_THREADS, 1)
-lstm_tc_kernel(const __grid_constant__ CUtensorMap map_h1, const __grid_constant__ CUtensorMap map_h2,
-               const __grid_constant__ CUtensorMap map_w, const LstmTcParams p) {
+lstm_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ CUtensorMap map_w, const LstmTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;             // SWIZZLE_128B tiles: 1024-byte aligned
@@ -100,32 +153,41 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap map_h1, const __grid_constant
   const uint32_t w_smem = base + LT_STAGES * LT_STAGE_BYTES;      // [LT_NKT][LT_W_TILE]
   constexpr int CS_OFF = LT_STAGES * LT_STAGE_BYTES + LT_NKT * LT_W_TILE;
   float* cs = reinterpret_cast<float*>(smem_gen + CS_OFF);        // [G][64 items][4 units] cell state
-  const int cs_bytes = p.G * LT_ITEMS * LT_UNITS * 4;
-  const uint32_t bar_base = base + CS_OFF + cs_bytes;
+  const int cs_bytes = p.G * IG * LT_UNITS * 4;
+  constexpr int XS_BYTES = 4 * 16 * 8 * 4;
+  float* xs = reinterpret_cast<float*>(smem_gen + CS_OFF + cs_bytes);   // [4 warp pairs][16][8] h2-part exchange (IG = 32)
+  const uint32_t bar_base = base + CS_OFF + cs_bytes + XS_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (LT_STAGES + s); };
   auto accf_bar = [&](int b) { return bar_base + 8u * (2 * LT_STAGES + b); };
   auto acce_bar = [&](int b) { return bar_base + 8u * (2 * LT_STAGES + 2 + b); };
   const uint32_t w_bar = bar_base + 8u * (2 * LT_STAGES + 4);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + CS_OFF + cs_bytes + 8 * (2 * LT_STAGES + 5));
+  auto hst_bar = [&](int b) { return bar_base + 8u * (2 * LT_STAGES + 5 + b); };   // the epilogue warps have stored h_t
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + CS_OFF + cs_bytes + XS_BYTES + 8 * (2 * LT_STAGES + 7));
+  constexpr int ROWS = 2 * IG;                  // A rows per group = MMA M
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int cta = blockIdx.x;
+  uint32_t crank = 0;
+  if (CL > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+  constexpr uint16_t MC_MASK = (uint16_t)((1u << CL) - 1u);
+  constexpr int ROWS_PER_CTA = ROWS / CL;       // rows of every h tile this CTA fetches for the cluster
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < LT_STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), CL);   // every CTA of the cluster writes into this stage: all their MMA warps release it
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(accf_bar(b), 1);
       mbar_init(acce_bar(b), 8);   // one arrive per epilogue warp
+      mbar_init(hst_bar(b), IG == 64 ? 8 : 4);   // the warps that store h
     }
     mbar_init(w_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < p.G * LT_ITEMS * LT_UNITS; i += LT_THREADS) cs[i] = 0.f;
+  for (int i = threadIdx.x; i < p.G * IG * LT_UNITS; i += LT_THREADS) cs[i] = 0.f;
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * LT_ACC_COLS)
                  : "memory");
@@ -133,9 +195,10 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap map_h1, const __grid_constant
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (CL > 1) cluster_sync_all();   // barriers of every CTA are initialised before any remote arrive / multicast write
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
-  const int rows_per_buf = p.G * LT_ITEMS;
+  const int rows_per_buf = p.G * ROWS;
 
   if (warp == 0) {
     // ================================ loader ================================
@@ -161,14 +224,22 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap map_h1, const __grid_constant
             if (++spins > (1u << 22)) __trap();   // a lost arrival must not hang the device
             continue;
           }
+          // h was written through the generic proxy (by other SMs) and is read by TMA: one cross-proxy fence per poll
+          // (~1000 cycles each -- per tile it was most of the step)
+          if (g == 0 && next == 0) LT_TRACE(0, t, 9)
+          if (t > 0) asm volatile("fence.proxy.async.global;" ::: "memory");
+          if (g == 0 && next == 0) LT_TRACE(0, t, 10)
           while (next < LT_NKT && ((ready >> next) & 1u)) {
             const int st = (int)(it % LT_STAGES);
             mbar_wait(empty_bar(st), ((it / LT_STAGES) & 1u) ^ 1u);
             if (elect_one()) {
-              asm volatile("fence.proxy.async;" ::: "memory");   // h was written through the generic proxy (other SMs), read by TMA
-              mbar_expect_tx(full_bar(st), LT_STAGE_BYTES);
-              tma_load_2d(a_ring + st * LT_STAGE_BYTES, &map_h1, full_bar(st), next * LT_KT, row0 + g * LT_ITEMS);
-              tma_load_2d(a_ring + st * LT_STAGE_BYTES + LT_A_TILE, &map_h2, full_bar(st), next * LT_KT, row0 + g * LT_ITEMS);
+              mbar_expect_tx(full_bar(st), ROWS * 128);
+              if (CL == 1) {
+                tma_load_2d(a_ring + st * LT_STAGE_BYTES, &map_h, full_bar(st), next * LT_KT, row0 + g * ROWS);
+              } else {   // this CTA's row slice of the tile, delivered to the same offset in every CTA of the cluster
+                tma_load_2d_mc(a_ring + st * LT_STAGE_BYTES + crank * (ROWS_PER_CTA * 128), &map_h, full_bar(st), next * LT_KT,
+                               row0 + g * ROWS + (int)crank * ROWS_PER_CTA, MC_MASK);
+              }
             }
             __syncwarp();
             if (g == 0) LT_TRACE(0, t, 1 + next)
@@ -180,8 +251,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap map_h1, const __grid_constant
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    constexpr uint32_t idesc32 = idesc_f16(LT_ITEMS, 2 * LT_NCOL);
-    constexpr uint32_t idesc16 = idesc_f16(LT_ITEMS, LT_NCOL);
+    constexpr uint32_t idesc = idesc_f16(ROWS, 2 * LT_NCOL);   // M = 128 | 64, N = 32
     constexpr uint32_t DESC_HI = 64u | (1u << 14) | (2u << 29);   // SBO 1024 B, version 1, SWIZZLE_128B
     auto mk_desc = [](uint32_t addr) { return ((uint64_t)DESC_HI << 32) | (uint64_t)(((addr & 0x3FFFFu) >> 4) | (1u << 16)); };
     mbar_wait(w_bar, 0);
@@ -196,16 +266,18 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap map_h1, const __grid_constant
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           if (g == 0) LT_TRACE(1, t, j)
           if (elect_one()) {
-            const uint32_t d = tmem_base + (uint32_t)(acc * LT_ACC_COLS + (j / (LT_NKT / 2)) * 32);
-            const uint64_t da1 = mk_desc(a_ring + st * LT_STAGE_BYTES);
-            const uint64_t da2 = mk_desc(a_ring + st * LT_STAGE_BYTES + LT_A_TILE);
+            const uint32_t d = tmem_base + (uint32_t)(acc * LT_ACC_COLS);
+            const uint64_t da = mk_desc(a_ring + st * LT_STAGE_BYTES);
             const uint64_t db = mk_desc(w_smem + j * LT_W_TILE);
 #pragma unroll
-            for (int k = 0; k < LT_KT / 16; ++k) {
-              mma_f16(d, da1 + 2u * k, db + 2u * k, idesc32, (j % (LT_NKT / 2) != 0 || k != 0) ? 1u : 0u);   // [main | corr] (+)= h1 [w1 | w2]
-              mma_f16(d + LT_NCOL, da2 + 2u * k, db + 2u * k, idesc16, 1u);                                    // corr += h2 w1
+            for (int k = 0; k < LT_KT / 16; ++k)   // rows of h1: [main | corr] (+)= h1 [w1 | w2]; rows of h2: [corr | -] (+)= h2 [w1 | w2]
+              mma_f16(d + 32u * k, da + 2u * k, db + 2u * k, idesc, j != 0 ? 1u : 0u);
+            if (g == 0 && j < 7 && p.trace && cta == 0 && t >= LT_TR_T0 && t < LT_TR_T0 + LT_TR_STEPS)
+              p.trace[(1 * LT_TR_STEPS + (t - LT_TR_T0)) * 16 + 9 + j] = clock64();
+            if (!(p.dbg & 1)) {
+              if (CL == 1) tcgen05_commit(empty_bar(st));
+              else commit_mc(empty_bar(st), MC_MASK);
             }
-            tcgen05_commit(empty_bar(st));
             if (j + 1 == LT_NKT) tcgen05_commit(accf_bar(acc));
           }
           __syncwarp();
@@ -213,26 +285,46 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap map_h1, const __grid_constant
         }
       }
     }
+  } else if (warp == 2) {
+    // ================================ publisher ================================
+    // Once the 8 epilogue warps have stored their part of h_t (mbarrier: release.cta arrive / acquire.cta wait), ONE
+    // release-increment at gpu scope publishes it: the release is cumulative over the stores observed through the barrier.
+    // A separate warp, so that the epilogue warps go on to the layer-output stores and the next group instead of sitting
+    // in the ~1000-cycle fence.
+    uint32_t n = 0;
+    for (int t = 0; t < p.T; ++t) {
+      for (int g = 0; g < p.G; ++g, ++n) {
+        mbar_wait(hst_bar((int)(n & 1u)), (n >> 1) & 1u);
+        if (t + 1 < p.T && lane == 0)
+          asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.cnt + g * LT_NKT + cta / 16) : "memory");
+        __syncwarp();
+        if (g == 0) LT_TRACE(2, t, 6)
+      }
+    }
   } else if (warp >= 4) {
     // ================================ cell epilogue ================================
-    // M = 64 accumulator layout: item row r of the group sits in TMEM lane 32 (r / 16) + r % 16. Warp w reads lane quadrant
-    // w % 4 (hardware rule), lanes 0-15 hold items; warps 4-7 take units 0-1 (columns 0-7), warps 8-11 units 2-3. The values
-    // of the second unit move to lanes 16-31, so every lane finishes one (item, unit) pair.
+    // A row block b (16 rows) = split part b % 2 (0: h1, 1: h2) of items 16 (b / 2) .. + 15. M = 128 (IG = 64): accumulator row
+    // m sits in TMEM lane m, so quadrant q holds the h1 rows of items 16 q .. in lanes 0-15 and their h2 rows in lanes 16-31
+    // (one shuffle adds the parts). M = 64 (IG = 32): block b sits in lanes 0-15 of quadrant b, so the h2 part comes from
+    // the neighbouring warp through shared memory. Warp w reads quadrant w % 4 (hardware rule); warps 4-7 take units 0-1
+    // (columns 0-7 of the main and correction blocks), warps 8-11 units 2-3. In the end lane r of a storing warp finishes
+    // unit 2 half of its item r and lane 16 + r unit 2 half + 1.
     const int quad = warp & 3;
     const int half = (warp - 4) >> 2;
     const int r = lane & 15;
     const int u = 2 * half + (lane >> 4);
     const int unit = cta * LT_UNITS + u;
+    const bool storing = IG == 64 || (quad & 1) == 0;          // this warp finishes items (IG = 32: the h1-row warps)
+    const int il = (IG == 64 ? quad * 16 : (quad >> 1) * 16) + r;   // item within the group
+    const int pair = (warp - 4) >> 1;                          // IG = 32: warps (4,5) (6,7) (8,9) (10,11) exchange
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(8 * half);
     uint32_t n = 0;
     for (int t = 0; t < p.T; ++t) {
-      __half* h1n = p.h1g + (long long)((t + 1) & 1) * rows_per_buf * LT_H;
-      __half* h2n = p.h2g + (long long)((t + 1) & 1) * rows_per_buf * LT_H;
+      __half* hn = p.hg + (long long)((t + 1) & 1) * rows_per_buf * LT_H;
       for (int g = 0; g < p.G; ++g, ++n) {
         const int acc = (int)(n & 1u);
-        const int il = quad * 16 + r;               // item within the group
-        const int item = g * LT_ITEMS + il;
-        const bool valid = item < p.B;
+        const int item = g * IG + il;
+        const bool valid = storing && item < p.B;
         // pre-gates / skip input of this step: independent of the recurrence, in flight while we wait for the MMAs
         float pg[4] = {0.f, 0.f, 0.f, 0.f}, skipv = 0.f;
         if (valid) {
@@ -245,65 +337,89 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap map_h1, const __grid_constant
         mbar_wait(accf_bar(acc), (n >> 1) & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (g == 0 && warp == 4) LT_TRACE(2, t, 1)
-        float ma[8], mb[8], ca[8], cb[8];
+        float mm[LT_NACC][8], cc[LT_NACC][8];
         const uint32_t a0 = lane_base + (uint32_t)(acc * LT_ACC_COLS);
-        tmem_ld8(a0, ma);
-        tmem_ld8(a0 + LT_NCOL, ca);
-        tmem_ld8(a0 + 32, mb);
-        tmem_ld8(a0 + 32 + LT_NCOL, cb);
+#pragma unroll
+        for (int a = 0; a < LT_NACC; ++a) {
+          tmem_ld8(a0 + 32 * a, mm[a]);             // columns [0,16) of accumulator a (h1 rows: h1 w1, h2 rows: h2 w1)
+          tmem_ld8(a0 + 32 * a + LT_NCOL, cc[a]);   // columns [16,32) (h1 rows: h1 w2)
+        }
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(acce_bar(acc));
         if (g == 0 && warp == 4) LT_TRACE(2, t, 2)
+        // h1 rows: main + corr / 2^11 with corr = h1 w2; h2 rows: their "main" columns are h2 w1
+        float part[8];
+        const bool h1_row = IG == 64 ? lane < 16 : (quad & 1) == 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float m = (mm[0][k] + mm[1][k]) + (mm[2][k] + mm[3][k]);
+          const float c = (cc[0][k] + cc[1][k]) + (cc[2][k] + cc[3][k]);
+          part[k] = h1_row ? m + c * (1.f / LT_LO_SCALE) : m * (1.f / LT_LO_SCALE);
+        }
+        if (IG == 64) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) part[k] += __shfl_xor_sync(0xffffffffu, part[k], 16);
+        } else {
+          float* x = xs + (pair * 16 + r) * 8;
+          if (!storing && lane < 16) {
+            *reinterpret_cast<float4*>(x) = make_float4(part[0], part[1], part[2], part[3]);
+            *reinterpret_cast<float4*>(x + 4) = make_float4(part[4], part[5], part[6], part[7]);
+          }
+          asm volatile("bar.sync %0, 64;" ::"r"(2 + pair) : "memory");   // the pair's h2 part is in shared memory
+          if (storing) {
+            const float4 x0 = *reinterpret_cast<const float4*>(x), x1 = *reinterpret_cast<const float4*>(x + 4);
+            part[0] += x0.x; part[1] += x0.y; part[2] += x0.z; part[3] += x0.w;
+            part[4] += x1.x; part[5] += x1.y; part[6] += x1.z; part[7] += x1.w;
+          }
+          asm volatile("bar.sync %0, 64;" ::"r"(2 + pair) : "memory");   // ... and has been read: the slot may be rewritten
+          if (!storing) continue;
+#pragma unroll
+          for (int k = 4; k < 8; ++k) part[k] = __shfl_sync(0xffffffffu, part[k], r);   // second unit -> lanes 16-31
+        }
         float rec[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float lo = (ma[k] + mb[k]) + (ca[k] + cb[k]) * (1.f / LT_LO_SCALE);
-          const float hi = (ma[4 + k] + mb[4 + k]) + (ca[4 + k] + cb[4 + k]) * (1.f / LT_LO_SCALE);
-          const float other = __shfl_sync(0xffffffffu, hi, r);   // second unit of the item, computed by lane r
-          rec[k] = lane < 16 ? lo : other;
-        }
-        const float gi = sigmoid_acc(pg[0] + rec[0]);
-        const float gf = sigmoid_acc(pg[1] + rec[1]);
-        const float gg = tanhf(pg[2] + rec[2]);
-        const float go = sigmoid_acc(pg[3] + rec[3]);
-        float* cptr = cs + (g * LT_ITEMS + il) * LT_UNITS + u;
-        const float c_new = gf * (*cptr) + gi * gg;
+        for (int k = 0; k < 4; ++k) rec[k] = lane < 16 ? part[k] : part[4 + k];
+        if (g == 0 && warp == 4) LT_TRACE(2, t, 4)
+        // gates i, f, o = sigmoid, g = tanh = 2 sigmoid(2 x) - 1: four sigmoids on two packed pairs
+        float s_if[2] = {pg[0] + rec[0], pg[1] + rec[1]};
+        float s_go[2] = {2.f * (pg[2] + rec[2]), pg[3] + rec[3]};
+        sigmoid_pair(s_if);
+        sigmoid_pair(s_go);
+        float* cptr = cs + (g * IG + il) * LT_UNITS + u;
+        const float c_new = s_if[1] * (*cptr) + s_if[0] * (2.f * s_go[0] - 1.f);
         *cptr = c_new;
-        const float h_new = go * tanhf(c_new);
+        float s_c[2] = {2.f * c_new, 0.f};
+        sigmoid_pair(s_c);
+        const float h_new = s_go[1] * (2.f * s_c[0] - 1.f);
+        if (g == 0 && warp == 4) LT_TRACE(2, t, 5)
         const __half q1 = __float2half_rn(h_new);
         const __half q2 = __float2half_rn((h_new - __half2float(q1)) * LT_LO_SCALE);
         const unsigned int own = (unsigned int)__half_as_ushort(q1) | ((unsigned int)__half_as_ushort(q2) << 16);
         const unsigned int oth = __shfl_down_sync(0xffffffffu, own, 16);
         if (lane < 16 && t + 1 < p.T) {   // units (2 half, 2 half + 1) of this item: one 4-byte store per split part
-          const long long off = (long long)(g * LT_ITEMS + il) * LT_H + cta * LT_UNITS + 2 * half;
+          const long long off = (long long)(g * ROWS + (il >> 4) * 32 + r) * LT_H + cta * LT_UNITS + 2 * half;
           const unsigned int v1 = (own & 0xffffu) | (oth << 16);
           const unsigned int v2 = (own >> 16) | (oth & 0xffff0000u);
-          asm volatile("st.global.cg.b32 [%0], %1;" ::"l"(h1n + off), "r"(v1) : "memory");
-          asm volatile("st.global.cg.b32 [%0], %1;" ::"l"(h2n + off), "r"(v2) : "memory");
+          asm volatile("st.global.cg.b32 [%0], %1;" ::"l"(hn + off), "r"(v1) : "memory");                // h1 row
+          asm volatile("st.global.cg.b32 [%0], %1;" ::"l"(hn + off + 16 * LT_H), "r"(v2) : "memory");    // h2 row
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(hst_bar(acc));   // -> publisher warp
+        if (g == 0 && warp == 4) LT_TRACE(2, t, 3)
+        // the layer output is nobody's business inside this kernel: stored after h_t is on its way
         if (valid) {
           float y = h_new + skipv;
           if (p.out_elu) y = elu1(y);
           p.out[(long long)item * p.out_stride + (long long)t * LT_H + unit] = y;
-        }
-        if (g == 0 && warp == 4) LT_TRACE(2, t, 3)
-        if (t + 1 < p.T) {
-          asm volatile("bar.sync 1, 256;" ::: "memory");   // all 8 epilogue warps have stored their part of h_t
-          if (g == 0 && warp == 4) LT_TRACE(2, t, 4)
-          if (warp == 4 && lane == 0) {
-            __threadfence();
-            if (g == 0) LT_TRACE(2, t, 5)
-            asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.cnt + g * LT_NKT + cta / 16) : "memory");
-            if (g == 0) LT_TRACE(2, t, 6)
-          }
         }
       }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (CL > 1) cluster_sync_all();   // nobody leaves while a neighbour may still multicast into it / arrive on its barriers
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * LT_ACC_COLS) : "memory");
@@ -324,8 +440,9 @@ __global__ void lstm_tc_pack_kernel(const float* __restrict__ whh, __half* __res
   }
 }
 
-size_t lt_smem_bytes(int G) {
-  return 1024 + LT_STAGES * LT_STAGE_BYTES + LT_NKT * LT_W_TILE + (size_t)G * LT_ITEMS * LT_UNITS * 4 + 8 * (2 * LT_STAGES + 5) + 16;
+size_t lt_smem_bytes(int G, int ig) {
+  return 1024 + LT_STAGES * LT_STAGE_BYTES + LT_NKT * LT_W_TILE + (size_t)G * ig * LT_UNITS * 4 + 8 * (2 * LT_STAGES + 7) + 16 +
+         4 * 16 * 8 * 4;
 }
 
 }  // namespace
@@ -341,22 +458,32 @@ long long* g_lstm_tc_trace = nullptr;   // diagnostic (ecb_debug_lstm_trace): de
 
 bool lstm_tc_supported(int batch, int H) { return H == LT_H && batch >= 1 && batch <= LT_MAX_GROUPS * LT_ITEMS; }
 
-// floats of workspace: h1g + h2g ([2][G * 64][512] fp16 each) + counters
+// group size: batches of up to 64 items run as (up to) two groups of 32, larger ones as groups of 64
+static int lt_group_items(int batch) {
+  if (const char* e = getenv("ECB_LSTM_GROUP")) {   // diagnostic override
+    const int v = atoi(e);
+    if (v == 32 || v == 64) return v;
+  }
+  return batch <= 64 ? 32 : 64;
+}
+
+// floats of workspace: exchange buffers ([2][G * 2 IG][512] fp16) + counters; bounded by the IG = 32 split of 64 items
 int lstm_tc_workspace_floats(int batch) {
-  const int G = (batch + LT_ITEMS - 1) / LT_ITEMS;
-  return G * LT_ITEMS * LT_H * 2 + G * LT_NKT + 64;
+  const int G = 2 * ((batch + 63) / 64);
+  return G * 32 * LT_H * 2 + G * LT_NKT + 64;
 }
 
 int launch_lstm_tc(const float* pre, long long pre_item_stride, const void* w_packed, const float* skip, long long skip_item_stride,
                    float* out, long long out_item_stride, int batch, int T, int out_elu, float* workspace, cudaStream_t s) {
   ECB_REQUIRE(lstm_tc_supported(batch, LT_H) && T > 0, "lstm_tc: bad batch %d / T %d", batch, T);
-  const int G = (batch + LT_ITEMS - 1) / LT_ITEMS;
-  const size_t smem = lt_smem_bytes(G);
-  static DeviceOnce attr_set;
-  if (!attr_set.done()) {
-    ECB_CUDA(cudaFuncSetAttribute(lstm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lt_smem_bytes(LT_MAX_GROUPS)));
-    attr_set.mark();
-  }
+  int ig = lt_group_items(batch);
+  if ((batch + ig - 1) / ig > LT_MAX_GROUPS) ig = 64;
+  const int G = (batch + ig - 1) / ig;
+  const int rows = 2 * ig;
+  const size_t smem = lt_smem_bytes(G, ig);
+  int cl = G >= 4 ? 4 : 1;   // cluster size: CTAs that share their h tiles through TMA multicast (pays once L2 -> SM traffic matters)
+  if (const char* e = getenv("ECB_LSTM_CLUSTER")) cl = atoi(e);
+  ECB_REQUIRE(cl == 1 || cl == 2 || cl == 4, "lstm_tc: ECB_LSTM_CLUSTER=%d (1, 2 or 4)", cl);
   LstmTcParams p;
   p.pre = pre;
   p.pre_stride = pre_item_stride;
@@ -364,36 +491,66 @@ int launch_lstm_tc(const float* pre, long long pre_item_stride, const void* w_pa
   p.skip_stride = skip_item_stride;
   p.out = out;
   p.out_stride = out_item_stride;
-  const long long hbuf = 2LL * G * LT_ITEMS * LT_H;   // halves per split part
-  p.h1g = reinterpret_cast<__half*>(workspace);
-  p.h2g = p.h1g + hbuf;
-  p.cnt = reinterpret_cast<unsigned int*>(p.h2g + hbuf);
+  const long long hbuf = 2LL * G * rows * LT_H;   // halves
+  p.hg = reinterpret_cast<__half*>(workspace);
+  p.cnt = reinterpret_cast<unsigned int*>(p.hg + hbuf);
   p.B = batch;
   p.T = T;
   p.G = G;
   p.out_elu = out_elu;
   p.trace = g_lstm_tc_trace;
+  p.dbg = getenv("ECB_LSTM_DBG") ? atoi(getenv("ECB_LSTM_DBG")) : 0;
+  if (G > 1 || cl > 1) p.dbg &= ~1;
   // h_{-1} = 0 (both buffers: padding rows of the last group stay finite) and the arrival counters
-  ECB_CUDA(cudaMemsetAsync(workspace, 0, sizeof(__half) * 2 * hbuf + sizeof(unsigned int) * (size_t)(G * LT_NKT), s));
-  CUtensorMap maps[3];
+  ECB_CUDA(cudaMemsetAsync(workspace, 0, sizeof(__half) * hbuf + sizeof(unsigned int) * (size_t)(G * LT_NKT), s));
+  CUtensorMap maps[2];
   {
-    const cuuint64_t dims[2] = {(cuuint64_t)LT_H, (cuuint64_t)(2 * G * LT_ITEMS)};
+    const cuuint64_t dims[2] = {(cuuint64_t)LT_H, (cuuint64_t)(2 * G * rows)};
     const cuuint64_t strides[1] = {(cuuint64_t)LT_H * 2};
-    const cuuint32_t box[2] = {LT_KT, LT_ITEMS};
-    if (make_tensor_map_f16(&maps[0], p.h1g, 2, dims, strides, box)) return 1;
-    if (make_tensor_map_f16(&maps[1], p.h2g, 2, dims, strides, box)) return 1;
+    const cuuint32_t box[2] = {LT_KT, (cuuint32_t)(rows / cl)};
+    if (make_tensor_map_f16(&maps[0], p.hg, 2, dims, strides, box)) return 1;
   }
   {
     const cuuint64_t dims[2] = {(cuuint64_t)LT_H, (cuuint64_t)(LT_CTAS * 2 * LT_NCOL)};
     const cuuint64_t strides[1] = {(cuuint64_t)LT_H * 2};
     const cuuint32_t box[2] = {LT_KT, 2 * LT_NCOL};
-    if (make_tensor_map_f16(&maps[2], w_packed, 2, dims, strides, box)) return 1;
+    if (make_tensor_map_f16(&maps[1], w_packed, 2, dims, strides, box)) return 1;
   }
   const double bt = (double)batch * T;
   ProfScope prof(PROF_LSTM_REC, s, 2.0 * bt * 4 * LT_H * LT_H, 4.0 * (bt * 4 * LT_H + bt * LT_H * (skip ? 2 : 1) + 4.0 * LT_H * LT_H));
-  void* args[] = {(void*)&maps[0], (void*)&maps[1], (void*)&maps[2], (void*)&p};
-  // all 128 CTAs spin on each other's arrivals: they must be co-resident
-  ECB_CUDA(cudaLaunchCooperativeKernel((void*)lstm_tc_kernel, dim3(LT_CTAS), dim3(LT_THREADS), args, smem, s));
+  // all 128 CTAs spin on each other's arrivals: they must be co-resident (cooperative launch), in clusters of `cl`
+  void* args[] = {(void*)&maps[0], (void*)&maps[1], (void*)&p};
+  const void* fns[3][2] = {{(const void*)lstm_tc_kernel<1, 32>, (const void*)lstm_tc_kernel<1, 64>},
+                           {(const void*)lstm_tc_kernel<2, 32>, (const void*)lstm_tc_kernel<2, 64>},
+                           {(const void*)lstm_tc_kernel<4, 32>, (const void*)lstm_tc_kernel<4, 64>}};
+  const int ci = cl == 4 ? 2 : cl == 2 ? 1 : 0, gi = ig == 64 ? 1 : 0;
+  const void* fn = fns[ci][gi];
+  static DeviceOnce attr_set[3][2];
+  DeviceOnce& once = attr_set[ci][gi];
+  if (!once.done()) {
+    ECB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lt_smem_bytes(LT_MAX_GROUPS, 64)));
+    once.mark();
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(LT_CTAS);
+  cfg.blockDim = dim3(LT_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attrs[2];
+  int na = 0;
+  attrs[na].id = cudaLaunchAttributeCooperative;
+  attrs[na].val.cooperative = 1;
+  ++na;
+  if (cl > 1) {
+    attrs[na].id = cudaLaunchAttributeClusterDimension;
+    attrs[na].val.clusterDim.x = (unsigned)cl;
+    attrs[na].val.clusterDim.y = 1;
+    attrs[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  cfg.attrs = attrs;
+  cfg.numAttrs = (unsigned)na;
+  ECB_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
   ECB_LAUNCHED();
   return 0;
 }

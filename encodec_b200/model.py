@@ -26,6 +26,23 @@ from .quantization import QuantizedResult, ResidualVectorQuantizer  # noqa: F401
 EncodedFrame = tp.Dict[str, tp.Optional[torch.Tensor]]
 
 
+def _version_of(t):
+    """Version counter of a tensor (None for None; -1 where autograd keeps none, e.g. inference tensors)."""
+    if t is None:
+        return None
+    try:
+        return t._version
+    except RuntimeError:
+        return -1
+
+
+def _untouched(frame, tag) -> bool:
+    _, _, q, qv, sc, scv = tag
+    if qv == -1 or scv == -1:
+        return False
+    return frame.get('quantized') is q and _version_of(q) == qv and frame.get('scale') is sc and _version_of(sc) == scv
+
+
 class _Batched:
     """Private side-channel from encode() to decode(): the batched, frames-major tensors of one call."""
 
@@ -181,7 +198,9 @@ class EncodecModel(nn.Module):
                     'codebook_loss': loss,
                     'scale': scale[:, s:s + 1] if scale is not None else None,
                 })
-                fr._batched = (batched, len(frames))
+                # side channel for decode(): valid only while 'quantized' / 'scale' are still these tensors, unmodified
+                fr._batched = (batched, len(frames), fr['quantized'], _version_of(fr['quantized']), fr['scale'],
+                               _version_of(fr['scale']))
                 frames.append(fr)
         return frames
 
@@ -205,11 +224,15 @@ class EncodecModel(nn.Module):
         if segment_length is None:
             assert len(encoded_frames) == 1
         # fast path: frames straight from our own encode() -> reuse the batched frames-major tensors
+        # (the fork decodes frame['quantized'], delta D3, so editing or replacing the latents between encode and decode is
+        # a supported use: the cached tensors are only used while the dict still holds the very tensors encode() put
+        # there, with unchanged version counters)
         tag = [getattr(f, '_batched', None) for f in encoded_frames]
         groups = None
         if tag and all(t is not None for t in tag) and all(t[0] is tag[0][0] for t in tag) and \
                 [t[1] for t in tag] == list(range(len(tag))) and \
-                sum(g["n_seg"] for g in tag[0][0].groups) == len(tag):
+                sum(g["n_seg"] for g in tag[0][0].groups) == len(tag) and \
+                all(_untouched(f, t) for f, t in zip(encoded_frames, tag)):
             groups = tag[0][0].groups
         else:
             groups = []

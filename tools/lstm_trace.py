@@ -39,9 +39,10 @@ for i in range(3):
 nat.lib.ecb_debug_lstm_trace(None)
 tr = trace.cpu().numpy().reshape(3, 8, 16)
 t0 = tr[0, 0, 0]
-names = {0: ["poll"] + [f"tma{j}" for j in range(8)], 1: [f"full{j}" for j in range(8)] + ["commit"],
-         2: ["wait", "accf", "ld", "stored", "bar", "fence", "red"]}
+names = {0: ["poll"] + [f"tma{j}" for j in range(8)] + ["polled", "fenced"],
+         1: [f"full{j}" for j in range(8)] + ["commit"] + [f"issued{j}" for j in range(7)],
+         2: ["wait", "accf", "ld", "h_stored", "rec", "math", "published"]}
 for step in range(8):
     print(f"--- step {20 + step} (second layer of the SLSTM; cycles since the loader's first stamp)")
     for role, rn in ((0, "loader"), (1, "mma"), (2, "cell")):
-        print(f"  {rn:7s}", "  ".join(f"{n}={int(tr[role, step, i] - t0)}" for i, n in enumerate(names[role])))
+        print(f"  {rn:7s}", "  ".join(f"{n}={int(tr[role, step, i] - t0)}" for i, n in enumerate(names[role]) if n))
