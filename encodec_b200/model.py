@@ -14,6 +14,7 @@ from __future__ import annotations
 
 import math
 import typing as tp
+import warnings
 
 import numpy as np
 import torch
@@ -56,7 +57,8 @@ class _Frame(dict):
 
 
 class EncodecModel(nn.Module):
-    """EnCodec model operating on the raw waveform (same constructor as reference model.py:99-110)."""
+    """EnCodec model operating on the raw waveform (same constructor as reference model.py:99-110). Inference only."""
+    _warned_training = False
 
     def __init__(self,
                  encoder: SEANetEncoder,
@@ -120,8 +122,15 @@ class EncodecModel(nn.Module):
         return [(off, min(seg, length - off)) for off in range(0, length, stride)], stride
 
     def _batch_chunk(self, n_seg: int, length: int, batch: int) -> int:
-        per_item = (length + 2 * self.encoder.hop_length) * 32 * 4 * 4 * max(1, n_seg)
-        return max(1, min(batch, int(self.max_items_bytes // per_item)))
+        """Clips per launch sequence: bounded by the activation workspace (``max_items_bytes``) and by the native limits on
+        items per launch -- 65 535 (grid dimension; codec.cu setup_ctx) and, for inputs shorter than 32 latent frames (the
+        CUDA-core path with its shared-memory resident LSTM state), 256."""
+        n_seg = max(1, n_seg)
+        per_item = (length + 2 * self.encoder.hop_length) * 32 * 4 * 4 * n_seg
+        cap = 65535 // n_seg
+        if -(-length // self.encoder.hop_length) < 32:
+            cap = min(cap, max(1, 256 // n_seg))
+        return max(1, min(batch, cap, int(self.max_items_bytes // per_item)))
 
     def _n_q(self) -> int:
         return self.quantizer.get_num_quantizers_for_bandwidth(self.frame_rate, self.bandwidth)
@@ -178,7 +187,14 @@ class EncodecModel(nn.Module):
     def encode(self, x: torch.Tensor) -> tp.List[EncodedFrame]:
         """Same contract as reference model.py:146-210: one dict per segment with keys
         ``quantized [B,D,T_f]``, ``codes [B,K,T_f]``, ``soft_targets``, ``commit_loss [K,1]``,
-        ``codebook_loss`` (the same tensor object) and ``scale [B,1]`` (or None)."""
+        ``codebook_loss`` (the same tensor object) and ``scale [B,1]`` (or None).
+
+        Inference only: eval semantics whatever ``self.training`` says (commit loss zero, no EMA / k-means / code expiry, no
+        autograd graph) -- a training loop pointed at this class would run and learn nothing, hence the warning."""
+        if self.training and torch.is_grad_enabled() and not EncodecModel._warned_training:
+            EncodecModel._warned_training = True
+            warnings.warn("encodec_b200.EncodecModel is inference-only: it always runs the reference's eval() forward (zero commit "
+                          "loss, frozen codebooks, no gradients), also in train mode with autograd enabled", RuntimeWarning, stacklevel=2)
         groups, n_q = self._encode_batched(x)
         batched = _Batched()
         batched.groups = groups

@@ -292,15 +292,18 @@ class SEANetDecoder(_NativeStack):
         self.model = nn.ModuleDict(model)
         self._init_native()
 
-    #: ``True`` runs the decoder convs as one TF32 pass instead of fp32-accurate split operands (weight-norm models):
-    #: ~1.6x faster decoder convs, audio within ~1e-4 max-abs of the fp32 result (see ecb_codec_set_decoder_precision).
-    tf32 = False
+    #: Operand scheme of the decoder's tensor-core convs (weight-norm models; GroupNorm / LayerNorm models always run the
+    #: fp32-accurate form). ``None`` (default) = ``True``: ONE TF32 pass -- nothing downstream of the decoder is discrete, the
+    #: decoded audio stays within ~1e-4 max-abs / 2.5e-5 RMS of the reference (bar 1e-3 / 1e-4; tests on the golden cases
+    #: and on real speech at three loudness levels), decoder convs ~1.6x faster. ``False``: split operands (3xTF32,
+    #: fp32-accurate), as the encoder and the quantiser always use.
+    tf32: tp.Optional[bool] = None
 
     @torch.no_grad()
     def decode_items(self, z: tp.Optional[torch.Tensor], z_frames: tp.Optional[torch.Tensor], n_items: int,
                      n_frames: int, scale: tp.Optional[torch.Tensor], out: tp.Optional[torch.Tensor] = None):
         codec = self.native()
-        nat.check(nat.lib.ecb_codec_set_decoder_precision(codec.handle, 1 if self.tf32 else 0))
+        nat.check(nat.lib.ecb_codec_set_decoder_precision(codec.handle, 0 if self.tf32 is False else 1))
         src = z if z is not None else z_frames
         dev = src.device
         if out is None:
