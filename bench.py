@@ -26,6 +26,7 @@ import glob
 import json
 import math
 import os
+import re
 import sys
 import threading
 import time
@@ -49,6 +50,9 @@ WORKLOADS = {
     "cfg5": dict(model="24k", bandwidth=6.0, batch=512, seconds=10.0, total_clips=8192, scaling="strong",
                  desc="EnCodec 24 kHz causal mono, 6 kbps (n_q=8), 8192 x 10 s clips in total sharded by clip across the GPUs, "
                       "micro-batches of 512 clips, codes+audio gathered to rank 0"),
+    # one micro-batch of cfg5 per GPU and step (weak scaling), with the per-kernel profile: explains the cfg5 number
+    "cfg5shard": dict(model="24k", bandwidth=6.0, batch=512, seconds=10.0, scaling="weak",
+                      desc="EnCodec 24 kHz causal mono, 6 kbps (n_q=8), 512 x 10 s clips per GPU and step (one micro-batch of cfg5)"),
     # the fork's own training configuration (params/091224_l1.yaml): 32 x 4 hours of a 10 Hz signal
     "fork10hz": dict(model="fork10hz", bandwidth=0.08, batch=32, seconds=14400.0, scaling="weak",
                      desc="the fork's 10 Hz model (layer_norm, ratios 6,5,5,2,1, dimension 256, 1024-wide LSTM), 0.08 kbps (n_q=8), "
@@ -315,7 +319,8 @@ def parse_step_dram(path_glob):
     for r in rows[1:]:
         if not r[i_metric].startswith("dram__bytes"):
             continue
-        name = r[i_name].replace("(anonymous namespace)", "").split("(")[0].split("<")[0].split("::")[-1].split()[-1]
+        m = re.search(r"([A-Za-z_]\w*_kernel)", r[i_name])   # this library's kernels all end in _kernel
+        name = m.group(1) if m else "other"
         per[name] = per.get(name, 0.0) + float(r[i_val].replace(",", "")) * scale.get(r[i_unit], 1.0)
     return per, files[-1]
 

@@ -479,7 +479,6 @@ int run_conv(Ctx& x, const ConvW& cw, const float* in, long long T_in, int in_el
   if (launch_conv_gemm(p, x.st)) return 1;
   if (s.group_norm) {
     GnSrc a;
-  a.item_stride = 0;
     a.item_stride = 0;
     a.x = out;
     a.partial = x.stat[0];
@@ -627,7 +626,6 @@ int run_convtr(Ctx& x, const ConvW& cw, const float* in, long long L, float* out
   if (launch_conv_gemm(p, x.st)) return 1;
   if (s.group_norm) {
     GnSrc a;
-  a.item_stride = 0;
     a.item_stride = 0;
     a.x = out;
     a.partial = x.stat[0];
@@ -693,8 +691,8 @@ bool tc_disabled_by_env() {
 int tc_split(const ecb_codec* c, bool decoder) {
   static int dec = -1;
   if (dec < 0) {
-    const char* e = getenv("ECB_DEC_SPLIT");   // 1: single-pass TF32 in the decoder (default 3: fp32-accurate everywhere)
-    dec = (e && e[0] == '1') ? 1 : 3;
+    const char* e = getenv("ECB_DEC_SPLIT");   // 3: fp32-accurate split operands in the decoder too (default 1: one TF32 pass)
+    dec = (e && e[0] == '3') ? 3 : 1;
   }
   if (!decoder) return 3;   // the encoder feeds the quantiser: always fp32-accurate
   return c->dec_split ? c->dec_split : dec;
@@ -781,8 +779,8 @@ bool fused_res32_enabled() {
 
 // true when the residual block of this width runs as ONE kernel that reads only X (no ELU(X) tensor needed)
 bool res_is_fused(const ecb_codec* c, int dim, int split) {
-  return fused_res32_enabled() && !c->spec.group_norm && dim == 32 && split == 3 && c->spec.residual_kernel_size == 3 &&
-         c->spec.compress == 2;
+  (void)split;   // both operand schemes have a fused kernel (tc_res.cu)
+  return fused_res32_enabled() && !c->spec.group_norm && dim == 32 && c->spec.residual_kernel_size == 3 && c->spec.compress == 2;
 }
 
 int tc_res(Ctx& x, const ResW& r, const Act& X, const Act& E, float* hbuf, Act& Y, int split) {
@@ -806,6 +804,8 @@ int tc_res(Ctx& x, const ResW& r, const Act& X, const Act& E, float* hbuf, Act& 
     p.M = X.T;
     p.n_items = x.n_items;
     p.halo = Y.halo;
+    p.split = split;
+    p.round_out = split == 1;
     return launch_tc_res32(p, x.st);
   }
   Act H = act_of(hbuf, r.hid_pad, X.T, 0);
@@ -836,6 +836,13 @@ struct LstmGraph {
 std::vector<LstmGraph> g_lstm_graphs;   // a handful of entries (layers x shapes); oldest dropped beyond 32
 cudaStream_t g_capture_stream = nullptr;
 
+// The step-wise recurrence's CUDA graphs are keyed on raw device pointers (weights, workspace): they are dropped whenever a
+// codec frees or rebuilds its weights, so that a recycled address can never replay a stale graph.
+void drop_lstm_graphs() {
+  for (auto& g : g_lstm_graphs) cudaGraphExecDestroy(g.exec);
+  g_lstm_graphs.clear();
+}
+
 int lstm_tc_mode() {
   const char* e = getenv("ECB_LSTM_TC");   // 0: off, 1 (default): launches below 320 items, 2: every supported launch
   if (!e || !e[0]) return 1;
@@ -863,7 +870,7 @@ int lstm_steps_eager(Ctx& x, const LstmLayerW& lw, const float* pre, long long p
   const long long m_tiles = (B + 127) / 128;
   int bn_max = 128;   // the narrowest tile that still fits the launch into one wave of CTAs
   {
-    const int sms = 148;
+    const int sms = sm_count();
     if (m_tiles * (4 * H / 32) <= sms) bn_max = 32;
     else if (m_tiles * (4 * H / 64) <= sms) bn_max = 64;
     const char* e = getenv("ECB_LSTM_BN");   // diagnostic override
@@ -942,14 +949,16 @@ int tc_lstm(Ctx& x, const std::vector<LstmLayerW>& layers, const Act& X, float* 
   const Act* cur = &X;
   const int mode = lstm_stepwise_mode();
   // Three forms of the recurrence, chosen by items per launch (tools/lstm_bench.py on a B200, us per layer step, T = 750):
-  //   items        1     16     32     64    128    256    384    960
-  //   FFMA       3.3    4.0    4.9    5.7    9.5   19.1   28.6   71.2    persistent CUDA-core kernel (lstm.cu)
-  //   tensor     4.3    4.6    4.6    5.3    7.0   12.9   19.3   48.0    persistent tcgen05 kernel (lstm_tc.cu)
-  //   step-wise   -      -      -    14.5   17.1   19.3   25.2   43.0    one tc_conv launch per step from a CUDA graph
-  // ECB_LSTM_TC=0 / ECB_LSTM_STEPWISE=0|1 force a form (diagnostics, parity tests).
+  //   items        1      8     16     32     64    128    256    384    512    960
+  //   FFMA       3.0    3.8    4.0    4.9    5.7    9.5   19.1   28.6   36.6   71.2    persistent CUDA-core kernel (lstm.cu)
+  //   tensor     3.3    3.4    3.5    3.7    4.3    6.8   12.9   19.3   23.6   48.0    persistent tcgen05 kernel (lstm_tc.cu)
+  //   step-wise   -      -      -      -    14.5   17.1   19.3   25.2   26.9   43.0    one tc_conv launch per step from a CUDA graph
+  // The tensor-core kernel takes every launch of up to 640 items (one arithmetic for all batch sizes up to 64, so results
+  // do not depend on how a batch is split), the step-wise form the larger ones. ECB_LSTM_TC=0 / ECB_LSTM_STEPWISE=0|1
+  // force a form (diagnostics, parity tests).
   const int tc_mode = lstm_tc_mode();
   const bool tcrec = mode != 1 && tc_mode && layers[0].r_f16 && lstm_tc_supported(x.n_items, H) &&
-                     (tc_mode == 2 || (x.n_items >= 24 && x.n_items <= 640));
+                     (tc_mode == 2 || x.n_items <= 640);
   const bool stepwise = mode == 1 || (mode < 0 && !tcrec && x.n_items >= 320);
   for (int l = 0; l < L; ++l) {
     if (tc_run(x, layers[l].t_hi, layers[l].t_lo, layers[l].bias, H, 4 * H, *cur, H, 1, 1, 0, true, nullptr, pre.row0(), nullptr,
@@ -1126,25 +1135,27 @@ inline bool norm_is_ln(const ecb_spec& s) { return s.group_norm == 2; }   // Con
 
 // GroupNorm(1, C) over the whole item, or LayerNorm over the channels of each row, of one or two raw conv outputs.
 int norm_apply(Ctx& x, const GnSrc& a, const GnSrc* b, float* out_raw, float* out_elu, long long out_item_stride, long long rows,
-               int C, int c_real = 0) {
+               int C, int c_real = 0, int round_out = 0) {
   if (norm_is_ln(x.c->spec))
     return launch_ln_apply2(a, b, out_raw, out_elu, out_item_stride, x.n_items, rows, C, c_real ? c_real : C, 1e-5f, x.st);
-  return launch_gn_apply2(a, b, out_raw, out_elu, out_item_stride, x.n_items, rows, C, 1e-5f, x.st);
+  return launch_gn_apply2(a, b, out_raw, out_elu, out_item_stride, x.n_items, rows, C, 1e-5f, x.st, round_out);
 }
 
 // conv (+ bias) -> GroupNorm -> {raw, ELU} for a plain (non-transposed) conv. The raw conv output goes to `dst`'s
 // layout first (dst = out_raw if given, else out_elu) and is normalised in place.
+// split = operand scheme of THIS conv (3: fp32-accurate, 1: one TF32 pass); next_split = scheme of the convs that read the
+// normalised result (1: the normalise pass stores TF32-rounded values, as single-pass consumers expect of their producer).
 int tc_conv_gn(Ctx& x, const ConvW& cw, const Act& in, int C0, bool zero_pad, long long M, Act* out_raw, Act* out_elu,
-               int stat_idx = 0) {
+               int stat_idx = 0, int split = 3, int next_split = 3) {
   const ecb_spec& s = x.c->spec;
   Act& dst = out_raw ? *out_raw : *out_elu;
   int slots = 0;
   if (tc_run(x, cw.t_hi, cw.t_lo, cw.t_bias, cw.t_K, cw.t_N, in, C0, cw.k, cw.stride, pad_left_of(s, cw.k, cw.stride), zero_pad,
-             nullptr, dst.row0(), nullptr, dst.stride(), M, 0, 3, 0, norm_is_ln(s) ? nullptr : x.stat[stat_idx], &slots))
+             nullptr, dst.row0(), nullptr, dst.stride(), M, 0, split, 0, norm_is_ln(s) ? nullptr : x.stat[stat_idx], &slots))
     return 1;
   GnSrc a = gn_src(dst.row0(), dst.stride(), x.stat[stat_idx], slots, (double)M * cw.c_out, cw.t_gamma, cw.t_beta);
   if (norm_apply(x, a, nullptr, out_raw ? out_raw->row0() : nullptr, out_elu ? out_elu->row0() : nullptr, dst.stride(), M, cw.t_N,
-                 cw.c_out))
+                 cw.c_out, next_split == 1))
     return 1;
   if (out_elu && out_elu->halo > 0 &&
       launch_halo_fill(nullptr, out_elu->row0(), out_elu->stride(), out_elu->T, out_elu->C, x.n_items, out_elu->halo, 0, x.st))
@@ -1153,22 +1164,22 @@ int tc_conv_gn(Ctx& x, const ConvW& cw, const Act& in, int C0, bool zero_pad, lo
 }
 
 // SEANetResnetBlock with GroupNorm: Y = ELU(GN(shortcut(X)) + GN(block3(ELU(GN(block1(E)))))). hbuf / sbuf are scratch.
-int tc_res_gn(Ctx& x, const ResW& r, const Act& X, const Act& E, float* hbuf, float* sbuf, Act& Y) {
+int tc_res_gn(Ctx& x, const ResW& r, const Act& X, const Act& E, float* hbuf, float* sbuf, Act& Y, int split = 3) {
   const int dim = r.sc.c_out;
   const bool ln = norm_is_ln(x.c->spec);
   Act H = act_of(hbuf, r.hid_pad, X.T, 0);
-  if (tc_conv_gn(x, r.b1, E, dim, false, X.T, nullptr, &H, 0)) return 1;
+  if (tc_conv_gn(x, r.b1, E, dim, false, X.T, nullptr, &H, 0, split, split)) return 1;
   Act S = act_of(sbuf, dim, X.T, 0);
   int slots3 = 0, slots_s = 0;
   if (tc_run(x, r.b3.t_hi, r.b3.t_lo, r.b3.t_bias, r.b3.t_K, r.b3.t_N, H, r.hid_pad, 1, 1, 0, true, nullptr, Y.row0(), nullptr,
-             Y.stride(), X.T, 0, 3, 0, ln ? nullptr : x.stat[0], &slots3))
+             Y.stride(), X.T, 0, split, 0, ln ? nullptr : x.stat[0], &slots3))
     return 1;
   if (tc_run(x, r.sc.t_hi, r.sc.t_lo, r.sc.t_bias, r.sc.t_K, r.sc.t_N, X, dim, 1, 1, 0, true, nullptr, S.row0(), nullptr,
-             S.stride(), X.T, 0, 3, 0, ln ? nullptr : x.stat[1], &slots_s))
+             S.stride(), X.T, 0, split, 0, ln ? nullptr : x.stat[1], &slots_s))
     return 1;
   GnSrc a = gn_src(S.row0(), S.stride(), x.stat[1], slots_s, (double)X.T * dim, r.sc.t_gamma, r.sc.t_beta);
   GnSrc b = gn_src(Y.row0(), Y.stride(), x.stat[0], slots3, (double)X.T * dim, r.b3.t_gamma, r.b3.t_beta);
-  if (norm_apply(x, a, &b, nullptr, Y.row0(), Y.stride(), X.T, dim)) return 1;   // shortcut + block
+  if (norm_apply(x, a, &b, nullptr, Y.row0(), Y.stride(), X.T, dim, 0, split == 1)) return 1;   // shortcut + block
   if (Y.halo > 0 && launch_halo_fill(nullptr, Y.row0(), Y.stride(), Y.T, Y.C, x.n_items, Y.halo, 0, x.st)) return 1;
   return 0;
 }
@@ -1246,11 +1257,18 @@ int decoder_forward_tc_gn(Ctx& x, const float* z_frames, int64_t n_frames, const
   if (launch_halo_fill(z_frames, Q.row0(), Q.stride(), T, s.dimension, x.n_items, ACT_HALO, 0, x.st)) return 1;
   int ch = c->dec_in.c_out;
   Act X = act_of(B, ch, T, 0);
-  if (tc_conv_gn(x, c->dec_in, Q, s.dimension, false, T, &X, nullptr, 0)) return 1;
+  // GroupNorm decoder: the convs that read >= 128 channels (tensor-bound) run as one TF32 pass unless the fp32-accurate
+  // scheme is requested; the 64- and 32-channel levels next to the output keep split operands -- all-TF32 measured 1.6e-4
+  // RMS against the reference on the 48 kHz golden case (bar 1e-4), and those levels are bandwidth-bound anyway. LayerNorm
+  // models keep split operands throughout. The first conv reads the unrounded latents and always runs split.
+  const int dsplit = norm_is_ln(s) ? 3 : tc_split(c, true);
+  auto split_of = [&](int channels) { return (dsplit == 1 && channels >= 128) ? 1 : 3; };
+  int split = split_of(ch);
+  if (tc_conv_gn(x, c->dec_in, Q, s.dimension, false, T, &X, nullptr, 0, 3, split)) return 1;
   if (tap_act(x.st, 100, X, x.n_items)) return 1;
   Act cur = act_of(A, ch, T, 0);
   if (s.lstm_layers) {
-    if (tc_lstm(x, c->dec_lstm, X, Cb, D, cur, 3)) return 1;
+    if (tc_lstm(x, c->dec_lstm, X, Cb, D, cur, split)) return 1;
     if (tap_act(x.st, 101, cur, x.n_items)) return 1;
   } else {
     if (launch_halo_fill(X.row0(), cur.row0(), cur.stride(), T, ch, x.n_items, 0, 1, x.st)) return 1;
@@ -1266,19 +1284,21 @@ int decoder_forward_tc_gn(Ctx& x, const float* z_frames, int64_t n_frames, const
     // untrimmed transposed conv [T + 1][s*Co] -> scratch (statistics cover all of it: the norm precedes unpad1d, conv.py:162)
     Act R = act_of(Cb, sN, T + 1, 0);
     int slots = 0;
+    split = split_of(ch);                        // this transposed conv reads `ch` channels
+    const int bsplit = split_of(uw.c_out);       // the residual block and the next conv read `c_out` channels
     if (tc_run(x, uw.t_hi, uw.t_lo, uw.t_bias, uw.t_K, uw.t_N, cur, ch, 2, 1, 1, true, nullptr, R.row0(), nullptr, R.stride(),
-               T + 1, 0, 3, 0, norm_is_ln(s) ? nullptr : x.stat[0], &slots))
+               T + 1, 0, split, 0, norm_is_ln(s) ? nullptr : x.stat[0], &slots))
       return 1;
     Act X2 = act_of(B, uw.c_out, T2, ACT_HALO), E2 = act_of(D, uw.c_out, T2, ACT_HALO);
     GnSrc a = gn_src(R.row0() + (long long)trim_left * uw.c_out, R.stride(), x.stat[0], slots, (double)(T + 1) * sN, uw.t_gamma,
                      uw.t_beta);
-    if (norm_apply(x, a, nullptr, X2.row0(), E2.row0(), X2.stride(), T2, uw.c_out)) return 1;
+    if (norm_apply(x, a, nullptr, X2.row0(), E2.row0(), X2.stride(), T2, uw.c_out, 0, bsplit == 1)) return 1;
     if (launch_halo_fill(nullptr, E2.row0(), E2.stride(), T2, uw.c_out, x.n_items, ACT_HALO, 0, x.st)) return 1;
     T = T2;
     ch = uw.c_out;
     if (tap_act(x.st, 102 + 2 * i, X2, x.n_items)) return 1;
     Act Y = act_of(A, ch, T, 0);
-    if (tc_res_gn(x, c->dec_res[i], X2, E2, Cb, F, Y)) return 1;
+    if (tc_res_gn(x, c->dec_res[i], X2, E2, Cb, F, Y, bsplit)) return 1;
     if (tap_act(x.st, 103 + 2 * i, Y, x.n_items)) return 1;
     cur = Y;
   }
@@ -1376,6 +1396,7 @@ int ecb_codec_create(const ecb_spec* spec, ecb_codec** out) {
 
 void ecb_codec_destroy(ecb_codec* c) {
   if (!c) return;
+  drop_lstm_graphs();   // the cached graphs hold raw pointers into this codec's weights
   for (auto& kv : c->raw) cudaFree(kv.second.p);
   for (float* p : c->owned) cudaFree(p);
   delete c;
@@ -1415,6 +1436,7 @@ int ecb_codec_set_decoder_precision(ecb_codec* c, int32_t tf32_single_pass) {
 int ecb_codec_finalize(ecb_codec* c, void* stream) {
   ECB_REQUIRE(c, "null codec");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  drop_lstm_graphs();
   for (float* p : c->owned) cudaFree(p);
   c->owned.clear();
   const ecb_spec& s = c->spec;
@@ -1531,7 +1553,6 @@ int ecb_encoder_forward(ecb_codec* c, const float* xin, int64_t n_items, int64_t
   if (launch_conv_in(ci, x.st)) return 1;
   if (s.group_norm) {
     GnSrc a;
-  a.item_stride = 0;
     a.item_stride = 0;
     a.x = A;
     a.partial = x.stat[0];

@@ -161,6 +161,8 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+int sm_count();   // SMs of the current device (tc_conv.cu)
+
 static inline long long cdiv(long long a, long long b) { return (a + b - 1) / b; }
 
 // Per-device once-flags: function attributes (dynamic shared memory opt-in) belong to a device, and a process may drive
@@ -297,6 +299,8 @@ struct TcResParams {
   long long M;
   int n_items;
   int halo;                   // reflected rows to write around Y
+  int split = 3;              // 3: fp32-accurate split operands; 1: one TF32 pass (x must arrive TF32-rounded)
+  int round_out = 0;          // store TF32-rounded Y
 };
 int launch_tc_res32(const TcResParams& p, cudaStream_t stream);
 
@@ -358,8 +362,9 @@ struct GnSrc {
 int launch_gn_apply(const GnSrc& a, const GnSrc* b, float* out, int n_items, long long rows, int C, int out_elu,
                     float eps, cudaStream_t s);
 // general form: strided items, raw and/or ELU output (either may alias a.x / b->x element for element)
+// round_out: store TF32-rounded values (the consumer is a single-pass TF32 conv)
 int launch_gn_apply2(const GnSrc& a, const GnSrc* b, float* out_raw, float* out_elu, long long out_item_stride, int n_items,
-                     long long rows, int C, float eps, cudaStream_t s);
+                     long long rows, int C, float eps, cudaStream_t s, int round_out = 0);
 // ConvLayerNorm (reference modules/norm.py:16-30, conv.py:44-46): LayerNorm over the C channels of every time step.
 // out = act(LN(a) [+ LN(b)]) over [n_items][rows][C]; GnSrc::partial / slots / count are unused. C in {32,...,1024} is
 // the stored row width, c_real <= C the channels that exist (the rest is zero padding, kept zero).

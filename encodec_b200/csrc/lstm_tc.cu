@@ -50,8 +50,7 @@ constexpr int LT_THREADS = 384;
 constexpr int LT_ROWS = 2 * LT_ITEMS;             // most A rows per group: h1 and h2 row of every item
 constexpr int LT_STAGE_BYTES = LT_ROWS * 128;     // ring slot: one [128 rows x 64 k] tile, 16 KB (IG = 32 uses half of it)
 constexpr int LT_W_TILE = 2 * LT_NCOL * 128;      // [w1 (16 rows) | w2 (16 rows)] x 64 k = 4 KB
-constexpr int LT_NACC = 4;                        // independent accumulators per buffer (K sub-step k of every tile -> accumulator k)
-constexpr int LT_ACC_COLS = LT_NACC * 32;         // per accumulator buffer: LT_NACC x [main 16 | corr 16]
+constexpr int LT_TMEM_COLS = 256;                 // two accumulator buffers of up to 128 columns
 constexpr int LT_MAX_GROUPS = 16;
 constexpr float LT_LO_SCALE = 2048.f;             // 2^11
 
@@ -62,11 +61,13 @@ struct LstmTcParams {
   long long skip_stride;
   float* out;            // item b at out + b * out_stride, [T][H]
   long long out_stride;
-  __half* hg;            // [2][G * 2 IG][512] exchange buffers (L2-resident); row 32 q + 16 part + r of a group = split part
-                         // `part` (0: h1, 1: h2) of item 16 q + r
+  __half* hg;            // [2][G][8 K tiles][2 IG rows][64] exchange buffers (L2-resident), stored as the SWIZZLE_128B shared-memory
+                         // image of each K tile (16-byte chunk c of row r sits at chunk c ^ (r & 7)): a tile, and the KP tiles of
+                         // a stage, are then ONE contiguous bulk copy -- a tensor-map box of 128-byte rows at a 1 KB pitch
+                         // moved only ~35 B per cycle into the SM and was the longest stretch of the step. Row 32 q + 16 part + r
+                         // of a group = split part `part` (0: h1, 1: h2) of item 16 q + r
   unsigned int* cnt;     // [G][8] arrival counters (one per group and K tile), zeroed by the host
   int B, T, G, out_elu;
-  int dbg;               // diagnostic switches (ECB_LSTM_DBG): 1 = no per-tile stage release (single group only)
   long long* trace;      // diagnostic: [3 roles][LT_TR_STEPS][16] clock64 stamps of CTA 0, or nullptr
 };
 constexpr int LT_TR_STEPS = 8, LT_TR_T0 = 20;
@@ -127,6 +128,17 @@ __device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* 
       ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y), "h"(mask)
       : "memory");
 }
+// 1-D bulk copies global -> shared (the exchange buffers are stored as ready-made shared-memory images, see below)
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+               "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_load_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar), "h"(mask)
+               : "memory");
+}
 __device__ __forceinline__ void commit_mc(uint32_t bar, uint16_t mask) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
                : "memory");
@@ -139,12 +151,16 @@ __device__ __forceinline__ void cluster_sync_all() {
 constexpr uint32_t idesc_f16(int m, int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24); }
 
 // CL = cluster size (1, 2, 4): the CTAs of a cluster need the same h tiles, so each loads 1 / CL of the rows of every tile
-// and TMA-multicasts them to all. IG = items per group (64 | 32). What paces a step is the tensor pipe streaming the A rows
-// (~0.8 cycles per row and MMA, whatever N is) inside a chain of ~1000-cycle hops (publish, poll, TMA, commit); a batch of
-// <= 64 items therefore runs as TWO groups of 32 (M = 64 MMAs): each group's chain is shorter and the two interleave.
+// and TMA-multicasts them to all. IG = items per group (64 | 32 | 16). A step is a chain of ~1000-cycle hops (publish, poll,
+// TMA, commit) around the MMAs, and an MMA of this size costs ~110 cycles whatever its M and N (measured) -- so the K loop
+// is shortened by STACKING K tiles along M: a group of IG items has R = 2 IG operand rows, KP = 128 / R consecutive K tiles
+// of it form one 128-row A tile, and B holds the KP matching weight tiles side by side (N = 32 KP). One MMA then covers
+// KP x 16 of K; its diagonal blocks D[rows of tile i][columns of tile i] are the useful ones, the epilogue warps of the
+// KP row blocks add their parts through shared memory. A group-step costs 32 / KP MMAs; a batch of <= 64 items runs as
+// groups of 32 or 16 items whose chains interleave.
 template <int CL, int IG>
 __global__ void __launch_bounds__(LT_THREADS, 1)
-lstm_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ CUtensorMap map_w, const LstmTcParams p) {
+lstm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const LstmTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;             // SWIZZLE_128B tiles: 1024-byte aligned
@@ -154,8 +170,8 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant_
   constexpr int CS_OFF = LT_STAGES * LT_STAGE_BYTES + LT_NKT * LT_W_TILE;
   float* cs = reinterpret_cast<float*>(smem_gen + CS_OFF);        // [G][64 items][4 units] cell state
   const int cs_bytes = p.G * IG * LT_UNITS * 4;
-  constexpr int XS_BYTES = 4 * 16 * 8 * 4;
-  float* xs = reinterpret_cast<float*>(smem_gen + CS_OFF + cs_bytes);   // [4 warp pairs][16][8] h2-part exchange (IG = 32)
+  constexpr int XS_BYTES = 8 * 16 * 8 * 4;
+  float* xs = reinterpret_cast<float*>(smem_gen + CS_OFF + cs_bytes);   // [slots][16][8] K-part exchange between epilogue warps (KP > 1)
   const uint32_t bar_base = base + CS_OFF + cs_bytes + XS_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (LT_STAGES + s); };
@@ -164,7 +180,11 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant_
   const uint32_t w_bar = bar_base + 8u * (2 * LT_STAGES + 4);
   auto hst_bar = [&](int b) { return bar_base + 8u * (2 * LT_STAGES + 5 + b); };   // the epilogue warps have stored h_t
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + CS_OFF + cs_bytes + XS_BYTES + 8 * (2 * LT_STAGES + 7));
-  constexpr int ROWS = 2 * IG;                  // A rows per group = MMA M
+  constexpr int ROWS = 2 * IG;                  // operand rows per group: h1 and h2 row of every item
+  constexpr int KP = 128 / ROWS;                // K tiles stacked along M in one MMA (1 | 2 | 4)
+  constexpr int NACC = KP == 1 ? 2 : 1;         // accumulators per buffer (<= 16 accumulating MMAs each: the tensor core truncates)
+  constexpr int ACC_COLS = NACC * 32 * KP;      // TMEM columns per accumulator buffer
+  constexpr int QPG = IG / 16;                  // TMEM lane quadrants per K part
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -182,14 +202,14 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant_
     for (int b = 0; b < 2; ++b) {
       mbar_init(accf_bar(b), 1);
       mbar_init(acce_bar(b), 8);   // one arrive per epilogue warp
-      mbar_init(hst_bar(b), IG == 64 ? 8 : 4);   // the warps that store h
+      mbar_init(hst_bar(b), 2 * QPG);   // the warps that store h
     }
     mbar_init(w_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = threadIdx.x; i < p.G * IG * LT_UNITS; i += LT_THREADS) cs[i] = 0.f;
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * LT_ACC_COLS)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(LT_TMEM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -207,38 +227,47 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant_
       for (int j = 0; j < LT_NKT; ++j) tma_load_2d(w_smem + j * LT_W_TILE, &map_w, w_bar, j * LT_KT, cta * 2 * LT_NCOL);
     }
     __syncwarp();
+    constexpr unsigned int STAGE_MASK = (1u << KP) - 1u;
+    // When all groups' stages fit the ring at once, group g owns stages g * 8 / KP ..: a stage is then known to be free when
+    // its counters say that h_t is complete (this CTA's own epilogue of step t - 1 came after its MMAs), and the empty
+    // barriers -- ~150 cycles per stage on the step's critical path -- are not used at all.
+    const bool private_ring = p.G * (LT_NKT / KP) <= LT_STAGES;
     uint32_t it = 0;
     for (int t = 0; t < p.T; ++t) {
       const unsigned int target = 16u * (unsigned int)t;   // 16 CTAs publish each K tile of 64 units
-      const int row0 = (t & 1) * rows_per_buf;
       for (int g = 0; g < p.G; ++g) {
-        int next = 0;
+        const uint8_t* src_g = reinterpret_cast<const uint8_t*>(p.hg) + ((long long)(t & 1) * p.G + g) * (LT_NKT * ROWS * 128);
+        int next = 0;   // next stage (KP K tiles) of this group-step
         unsigned int spins = 0;
         if (g == 0) LT_TRACE(0, t, 0)
-        while (next < LT_NKT) {
+        while (next < LT_NKT / KP) {
           unsigned int v = 0xffffffffu;
           if (t > 0 && lane < LT_NKT)
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.cnt + g * LT_NKT + lane) : "memory");
           const unsigned int ready = __ballot_sync(0xffffffffu, v >= target);
-          if (!((ready >> next) & 1u)) {
+          if (((ready >> (next * KP)) & STAGE_MASK) != STAGE_MASK) {
             if (++spins > (1u << 22)) __trap();   // a lost arrival must not hang the device
             continue;
           }
-          // h was written through the generic proxy (by other SMs) and is read by TMA: one cross-proxy fence per poll
-          // (~1000 cycles each -- per tile it was most of the step)
+          // h was written through the generic proxy (by other SMs) and is read through the async proxy: one fence per poll
           if (g == 0 && next == 0) LT_TRACE(0, t, 9)
           if (t > 0) asm volatile("fence.proxy.async.global;" ::: "memory");
           if (g == 0 && next == 0) LT_TRACE(0, t, 10)
-          while (next < LT_NKT && ((ready >> next) & 1u)) {
-            const int st = (int)(it % LT_STAGES);
-            mbar_wait(empty_bar(st), ((it / LT_STAGES) & 1u) ^ 1u);
+          while (next < LT_NKT / KP && ((ready >> (next * KP)) & STAGE_MASK) == STAGE_MASK) {
+            const int st = private_ring ? g * (LT_NKT / KP) + next : (int)(it % LT_STAGES);
+            if (!private_ring) mbar_wait(empty_bar(st), ((it / LT_STAGES) & 1u) ^ 1u);
             if (elect_one()) {
-              mbar_expect_tx(full_bar(st), ROWS * 128);
+              mbar_expect_tx(full_bar(st), LT_STAGE_BYTES);
+              const uint32_t dst = a_ring + st * LT_STAGE_BYTES;
+              const uint8_t* src = src_g + (long long)next * LT_STAGE_BYTES;   // the KP tiles of a stage are contiguous
               if (CL == 1) {
-                tma_load_2d(a_ring + st * LT_STAGE_BYTES, &map_h, full_bar(st), next * LT_KT, row0 + g * ROWS);
-              } else {   // this CTA's row slice of the tile, delivered to the same offset in every CTA of the cluster
-                tma_load_2d_mc(a_ring + st * LT_STAGE_BYTES + crank * (ROWS_PER_CTA * 128), &map_h, full_bar(st), next * LT_KT,
-                               row0 + g * ROWS + (int)crank * ROWS_PER_CTA, MC_MASK);
+                bulk_load(dst, src, LT_STAGE_BYTES, full_bar(st));
+              } else {   // this CTA's row slice of every tile, delivered to the same offset in every CTA of the cluster
+#pragma unroll
+                for (int sub = 0; sub < KP; ++sub) {
+                  const uint32_t o = (uint32_t)(sub * ROWS + (int)crank * ROWS_PER_CTA) * 128u;
+                  bulk_load_mc(dst + o, src + o, ROWS_PER_CTA * 128, full_bar(st), MC_MASK);
+                }
               }
             }
             __syncwarp();
@@ -251,37 +280,40 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant_
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    constexpr uint32_t idesc = idesc_f16(ROWS, 2 * LT_NCOL);   // M = 128 | 64, N = 32
+    constexpr uint32_t idesc = idesc_f16(128, 2 * LT_NCOL * KP);   // M = 128, N = 32 KP
     constexpr uint32_t DESC_HI = 64u | (1u << 14) | (2u << 29);   // SBO 1024 B, version 1, SWIZZLE_128B
     auto mk_desc = [](uint32_t addr) { return ((uint64_t)DESC_HI << 32) | (uint64_t)(((addr & 0x3FFFFu) >> 4) | (1u << 16)); };
     mbar_wait(w_bar, 0);
+    const bool private_ring = p.G * (LT_NKT / KP) <= LT_STAGES;
     uint32_t it = 0, n = 0;
     for (int t = 0; t < p.T; ++t) {
       for (int g = 0; g < p.G; ++g, ++n) {
         const int acc = (int)(n & 1u);
         mbar_wait(acce_bar(acc), ((n >> 1) & 1u) ^ 1u);   // the epilogue has drained this accumulator buffer
-        for (int j = 0; j < LT_NKT; ++j, ++it) {
-          const int st = (int)(it % LT_STAGES);
-          mbar_wait(full_bar(st), (it / LT_STAGES) & 1u);
+        for (int j = 0; j < LT_NKT / KP; ++j, ++it) {
+          const int st = private_ring ? g * (LT_NKT / KP) + j : (int)(it % LT_STAGES);
+          mbar_wait(full_bar(st), private_ring ? ((uint32_t)t & 1u) : ((it / LT_STAGES) & 1u));
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           if (g == 0) LT_TRACE(1, t, j)
           if (elect_one()) {
-            const uint32_t d = tmem_base + (uint32_t)(acc * LT_ACC_COLS);
+            const uint32_t d = tmem_base + (uint32_t)(acc * ACC_COLS);
             const uint64_t da = mk_desc(a_ring + st * LT_STAGE_BYTES);
-            const uint64_t db = mk_desc(w_smem + j * LT_W_TILE);
+            const uint64_t db = mk_desc(w_smem + j * KP * LT_W_TILE);   // KP weight tiles side by side: N = 32 KP rows
 #pragma unroll
-            for (int k = 0; k < LT_KT / 16; ++k)   // rows of h1: [main | corr] (+)= h1 [w1 | w2]; rows of h2: [corr | -] (+)= h2 [w1 | w2]
-              mma_f16(d + 32u * k, da + 2u * k, db + 2u * k, idesc, j != 0 ? 1u : 0u);
+            for (int k = 0; k < LT_KT / 16; ++k) {   // rows of h1: [main | corr] (+)= h1 [w1 | w2]; rows of h2: [corr | -] (+)= h2 [w1 | w2]
+              const int mm = j * (LT_KT / 16) + k;
+              mma_f16(d + (uint32_t)((mm % NACC) * 32 * KP), da + 2u * k, db + 2u * k, idesc, mm >= NACC ? 1u : 0u);
+            }
             if (g == 0 && j < 7 && p.trace && cta == 0 && t >= LT_TR_T0 && t < LT_TR_T0 + LT_TR_STEPS)
               p.trace[(1 * LT_TR_STEPS + (t - LT_TR_T0)) * 16 + 9 + j] = clock64();
-            if (!(p.dbg & 1)) {
+            if (!private_ring) {
               if (CL == 1) tcgen05_commit(empty_bar(st));
               else commit_mc(empty_bar(st), MC_MASK);
             }
-            if (j + 1 == LT_NKT) tcgen05_commit(accf_bar(acc));
+            if (j + 1 == LT_NKT / KP) tcgen05_commit(accf_bar(acc));
           }
           __syncwarp();
-          if (g == 0 && j + 1 == LT_NKT) LT_TRACE(1, t, 8)
+          if (g == 0 && j + 1 == LT_NKT / KP) LT_TRACE(1, t, 8)
         }
       }
     }
@@ -303,10 +335,10 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant_
     }
   } else if (warp >= 4) {
     // ================================ cell epilogue ================================
-    // A row block b (16 rows) = split part b % 2 (0: h1, 1: h2) of items 16 (b / 2) .. + 15. M = 128 (IG = 64): accumulator row
-    // m sits in TMEM lane m, so quadrant q holds the h1 rows of items 16 q .. in lanes 0-15 and their h2 rows in lanes 16-31
-    // (one shuffle adds the parts). M = 64 (IG = 32): block b sits in lanes 0-15 of quadrant b, so the h2 part comes from
-    // the neighbouring warp through shared memory. Warp w reads quadrant w % 4 (hardware rule); warps 4-7 take units 0-1
+    // Operand row block b (16 rows) of a group = split part b % 2 (0: h1, 1: h2) of items 16 (b / 2) .. + 15, and K tile i of a
+    // stage sits in MMA rows i R .. (accumulator row m = TMEM lane m). A lane quadrant therefore holds, for one K part and 16
+    // items, the h1 rows in lanes 0-15 and the h2 rows in lanes 16-31 (one shuffle adds them); the KP quadrants of the same
+    // items add their K parts through shared memory. Warp w reads quadrant w % 4 (hardware rule); warps 4-7 take units 0-1
     // (columns 0-7 of the main and correction blocks), warps 8-11 units 2-3. In the end lane r of a storing warp finishes
     // unit 2 half of its item r and lane 16 + r unit 2 half + 1.
     const int quad = warp & 3;
@@ -314,10 +346,12 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant_
     const int r = lane & 15;
     const int u = 2 * half + (lane >> 4);
     const int unit = cta * LT_UNITS + u;
-    const bool storing = IG == 64 || (quad & 1) == 0;          // this warp finishes items (IG = 32: the h1-row warps)
-    const int il = (IG == 64 ? quad * 16 : (quad >> 1) * 16) + r;   // item within the group
-    const int pair = (warp - 4) >> 1;                          // IG = 32: warps (4,5) (6,7) (8,9) (10,11) exchange
-    const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(8 * half);
+    const int kpart = quad / QPG;                 // which K tile of a stage this quadrant's rows belong to
+    const int iq = quad % QPG;                    // 16-item block of the group
+    const bool storing = kpart == 0;              // this warp finishes items; the others hand their K part over
+    const int il = iq * 16 + r;                   // item within the group
+    const int team = half * QPG + iq;             // the KP warps that share (units, items)
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(32 * kpart + 8 * half);
     uint32_t n = 0;
     for (int t = 0; t < p.T; ++t) {
       __half* hn = p.hg + (long long)((t + 1) & 1) * rows_per_buf * LT_H;
@@ -337,46 +371,49 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant_
         mbar_wait(accf_bar(acc), (n >> 1) & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (g == 0 && warp == 4) LT_TRACE(2, t, 1)
-        float mm[LT_NACC][8], cc[LT_NACC][8];
-        const uint32_t a0 = lane_base + (uint32_t)(acc * LT_ACC_COLS);
+        float mm[NACC][8], cc[NACC][8];
+        const uint32_t a0 = lane_base + (uint32_t)(acc * ACC_COLS);
 #pragma unroll
-        for (int a = 0; a < LT_NACC; ++a) {
-          tmem_ld8(a0 + 32 * a, mm[a]);             // columns [0,16) of accumulator a (h1 rows: h1 w1, h2 rows: h2 w1)
-          tmem_ld8(a0 + 32 * a + LT_NCOL, cc[a]);   // columns [16,32) (h1 rows: h1 w2)
+        for (int a = 0; a < NACC; ++a) {
+          tmem_ld8(a0 + 32 * KP * a, mm[a]);             // columns [0,16) of this K part (h1 rows: h1 w1, h2 rows: h2 w1)
+          tmem_ld8(a0 + 32 * KP * a + LT_NCOL, cc[a]);   // columns [16,32) (h1 rows: h1 w2)
         }
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(acce_bar(acc));
         if (g == 0 && warp == 4) LT_TRACE(2, t, 2)
-        // h1 rows: main + corr / 2^11 with corr = h1 w2; h2 rows: their "main" columns are h2 w1
+        // h1 rows (lanes 0-15): main + corr / 2^11 with corr = h1 w2; h2 rows (lanes 16-31): their "main" columns are h2 w1
         float part[8];
-        const bool h1_row = IG == 64 ? lane < 16 : (quad & 1) == 0;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          const float m = (mm[0][k] + mm[1][k]) + (mm[2][k] + mm[3][k]);
-          const float c = (cc[0][k] + cc[1][k]) + (cc[2][k] + cc[3][k]);
-          part[k] = h1_row ? m + c * (1.f / LT_LO_SCALE) : m * (1.f / LT_LO_SCALE);
+          float m = mm[0][k], c = cc[0][k];
+          if (NACC == 2) {
+            m += mm[NACC - 1][k];
+            c += cc[NACC - 1][k];
+          }
+          part[k] = lane < 16 ? m + c * (1.f / LT_LO_SCALE) : m * (1.f / LT_LO_SCALE);
         }
-        if (IG == 64) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) part[k] += __shfl_xor_sync(0xffffffffu, part[k], 16);
-        } else {
-          float* x = xs + (pair * 16 + r) * 8;
+        for (int k = 0; k < 8; ++k) part[k] += __shfl_xor_sync(0xffffffffu, part[k], 16);
+        if (KP > 1) {   // add the K parts of the other quadrants (same units, same items)
           if (!storing && lane < 16) {
+            float* x = xs + ((team * (KP - 1) + (kpart - 1)) * 16 + r) * 8;
             *reinterpret_cast<float4*>(x) = make_float4(part[0], part[1], part[2], part[3]);
             *reinterpret_cast<float4*>(x + 4) = make_float4(part[4], part[5], part[6], part[7]);
           }
-          asm volatile("bar.sync %0, 64;" ::"r"(2 + pair) : "memory");   // the pair's h2 part is in shared memory
+          asm volatile("bar.sync %0, %1;" ::"r"(2 + team), "r"(32 * KP) : "memory");   // the team's K parts are in shared memory
           if (storing) {
-            const float4 x0 = *reinterpret_cast<const float4*>(x), x1 = *reinterpret_cast<const float4*>(x + 4);
-            part[0] += x0.x; part[1] += x0.y; part[2] += x0.z; part[3] += x0.w;
-            part[4] += x1.x; part[5] += x1.y; part[6] += x1.z; part[7] += x1.w;
-          }
-          asm volatile("bar.sync %0, 64;" ::"r"(2 + pair) : "memory");   // ... and has been read: the slot may be rewritten
-          if (!storing) continue;
 #pragma unroll
-          for (int k = 4; k < 8; ++k) part[k] = __shfl_sync(0xffffffffu, part[k], r);   // second unit -> lanes 16-31
+            for (int o = 0; o < KP - 1; ++o) {
+              const float* x = xs + ((team * (KP - 1) + o) * 16 + r) * 8;
+              const float4 x0 = *reinterpret_cast<const float4*>(x), x1 = *reinterpret_cast<const float4*>(x + 4);
+              part[0] += x0.x; part[1] += x0.y; part[2] += x0.z; part[3] += x0.w;
+              part[4] += x1.x; part[5] += x1.y; part[6] += x1.z; part[7] += x1.w;
+            }
+          }
+          asm volatile("bar.sync %0, %1;" ::"r"(2 + team), "r"(32 * KP) : "memory");   // ... and read: the slots may be rewritten
+          if (!storing) continue;
         }
         float rec[4];
 #pragma unroll
@@ -399,11 +436,14 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant_
         const unsigned int own = (unsigned int)__half_as_ushort(q1) | ((unsigned int)__half_as_ushort(q2) << 16);
         const unsigned int oth = __shfl_down_sync(0xffffffffu, own, 16);
         if (lane < 16 && t + 1 < p.T) {   // units (2 half, 2 half + 1) of this item: one 4-byte store per split part
-          const long long off = (long long)(g * ROWS + (il >> 4) * 32 + r) * LT_H + cta * LT_UNITS + 2 * half;
+          // shared-memory image of K tile cta / 16: row (g, iq, r), 16-byte chunk ((4 cta + 2 half) % 64) / 8 swizzled by r & 7
+          const int kk = (cta * LT_UNITS + 2 * half) % LT_KT;
+          const long long row = ((long long)g * LT_NKT + cta / 16) * ROWS + iq * 32 + r;
+          uint8_t* dst = reinterpret_cast<uint8_t*>(hn) + row * 128 + (((kk >> 3) ^ (r & 7)) << 4) + (kk & 7) * 2;
           const unsigned int v1 = (own & 0xffffu) | (oth << 16);
           const unsigned int v2 = (own >> 16) | (oth & 0xffff0000u);
-          asm volatile("st.global.cg.b32 [%0], %1;" ::"l"(hn + off), "r"(v1) : "memory");                // h1 row
-          asm volatile("st.global.cg.b32 [%0], %1;" ::"l"(hn + off + 16 * LT_H), "r"(v2) : "memory");    // h2 row
+          asm volatile("st.global.cg.b32 [%0], %1;" ::"l"(dst), "r"(v1) : "memory");                // h1 row
+          asm volatile("st.global.cg.b32 [%0], %1;" ::"l"(dst + 16 * 128), "r"(v2) : "memory");     // h2 row (same r & 7)
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(hst_bar(acc));   // -> publisher warp
@@ -422,7 +462,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant_
   if (CL > 1) cluster_sync_all();   // nobody leaves while a neighbour may still multicast into it / arrive on its barriers
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * LT_ACC_COLS) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(LT_TMEM_COLS) : "memory");
   }
 }
 
@@ -442,7 +482,7 @@ __global__ void lstm_tc_pack_kernel(const float* __restrict__ whh, __half* __res
 
 size_t lt_smem_bytes(int G, int ig) {
   return 1024 + LT_STAGES * LT_STAGE_BYTES + LT_NKT * LT_W_TILE + (size_t)G * ig * LT_UNITS * 4 + 8 * (2 * LT_STAGES + 7) + 16 +
-         4 * 16 * 8 * 4;
+         8 * 16 * 8 * 4;
 }
 
 }  // namespace
@@ -462,7 +502,7 @@ bool lstm_tc_supported(int batch, int H) { return H == LT_H && batch >= 1 && bat
 static int lt_group_items(int batch) {
   if (const char* e = getenv("ECB_LSTM_GROUP")) {   // diagnostic override
     const int v = atoi(e);
-    if (v == 32 || v == 64) return v;
+    if (v == 16 || v == 32 || v == 64) return v;
   }
   return batch <= 64 ? 32 : 64;
 }
@@ -499,58 +539,61 @@ int launch_lstm_tc(const float* pre, long long pre_item_stride, const void* w_pa
   p.G = G;
   p.out_elu = out_elu;
   p.trace = g_lstm_tc_trace;
-  p.dbg = getenv("ECB_LSTM_DBG") ? atoi(getenv("ECB_LSTM_DBG")) : 0;
-  if (G > 1 || cl > 1) p.dbg &= ~1;
+
   // h_{-1} = 0 (both buffers: padding rows of the last group stay finite) and the arrival counters
   ECB_CUDA(cudaMemsetAsync(workspace, 0, sizeof(__half) * hbuf + sizeof(unsigned int) * (size_t)(G * LT_NKT), s));
-  CUtensorMap maps[2];
-  {
-    const cuuint64_t dims[2] = {(cuuint64_t)LT_H, (cuuint64_t)(2 * G * rows)};
-    const cuuint64_t strides[1] = {(cuuint64_t)LT_H * 2};
-    const cuuint32_t box[2] = {LT_KT, (cuuint32_t)(rows / cl)};
-    if (make_tensor_map_f16(&maps[0], p.hg, 2, dims, strides, box)) return 1;
-  }
+  CUtensorMap map_w;
   {
     const cuuint64_t dims[2] = {(cuuint64_t)LT_H, (cuuint64_t)(LT_CTAS * 2 * LT_NCOL)};
     const cuuint64_t strides[1] = {(cuuint64_t)LT_H * 2};
     const cuuint32_t box[2] = {LT_KT, 2 * LT_NCOL};
-    if (make_tensor_map_f16(&maps[1], w_packed, 2, dims, strides, box)) return 1;
+    if (make_tensor_map_f16(&map_w, w_packed, 2, dims, strides, box)) return 1;
   }
   const double bt = (double)batch * T;
   ProfScope prof(PROF_LSTM_REC, s, 2.0 * bt * 4 * LT_H * LT_H, 4.0 * (bt * 4 * LT_H + bt * LT_H * (skip ? 2 : 1) + 4.0 * LT_H * LT_H));
-  // all 128 CTAs spin on each other's arrivals: they must be co-resident (cooperative launch), in clusters of `cl`
-  void* args[] = {(void*)&maps[0], (void*)&maps[1], (void*)&p};
-  const void* fns[3][2] = {{(const void*)lstm_tc_kernel<1, 32>, (const void*)lstm_tc_kernel<1, 64>},
-                           {(const void*)lstm_tc_kernel<2, 32>, (const void*)lstm_tc_kernel<2, 64>},
-                           {(const void*)lstm_tc_kernel<4, 32>, (const void*)lstm_tc_kernel<4, 64>}};
-  const int ci = cl == 4 ? 2 : cl == 2 ? 1 : 0, gi = ig == 64 ? 1 : 0;
-  const void* fn = fns[ci][gi];
-  static DeviceOnce attr_set[3][2];
-  DeviceOnce& once = attr_set[ci][gi];
-  if (!once.done()) {
-    ECB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lt_smem_bytes(LT_MAX_GROUPS, 64)));
-    once.mark();
-  }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(LT_CTAS);
-  cfg.blockDim = dim3(LT_THREADS);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = s;
-  cudaLaunchAttribute attrs[2];
-  int na = 0;
-  attrs[na].id = cudaLaunchAttributeCooperative;
-  attrs[na].val.cooperative = 1;
-  ++na;
-  if (cl > 1) {
-    attrs[na].id = cudaLaunchAttributeClusterDimension;
-    attrs[na].val.clusterDim.x = (unsigned)cl;
-    attrs[na].val.clusterDim.y = 1;
-    attrs[na].val.clusterDim.z = 1;
+  // all 128 CTAs spin on each other's arrivals: they must be co-resident (cooperative launch), in clusters of `cl`. Where a
+  // clustered cooperative launch is refused (seen under ncu), the same kernel runs unclustered.
+  void* args[] = {(void*)&map_w, (void*)&p};
+  const void* fns[3][3] = {{(const void*)lstm_tc_kernel<1, 16>, (const void*)lstm_tc_kernel<1, 32>, (const void*)lstm_tc_kernel<1, 64>},
+                           {(const void*)lstm_tc_kernel<2, 16>, (const void*)lstm_tc_kernel<2, 32>, (const void*)lstm_tc_kernel<2, 64>},
+                           {(const void*)lstm_tc_kernel<4, 16>, (const void*)lstm_tc_kernel<4, 32>, (const void*)lstm_tc_kernel<4, 64>}};
+  static DeviceOnce attr_set[3][3];
+  for (;;) {
+    const int ci = cl == 4 ? 2 : cl == 2 ? 1 : 0, gi = ig == 64 ? 2 : ig == 32 ? 1 : 0;
+    const void* fn = fns[ci][gi];
+    DeviceOnce& once = attr_set[ci][gi];
+    if (!once.done()) {
+      ECB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lt_smem_bytes(LT_MAX_GROUPS, 64)));
+      once.mark();
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(LT_CTAS);
+    cfg.blockDim = dim3(LT_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attrs[2];
+    int na = 0;
+    attrs[na].id = cudaLaunchAttributeCooperative;
+    attrs[na].val.cooperative = 1;
     ++na;
+    if (cl > 1) {
+      attrs[na].id = cudaLaunchAttributeClusterDimension;
+      attrs[na].val.clusterDim.x = (unsigned)cl;
+      attrs[na].val.clusterDim.y = 1;
+      attrs[na].val.clusterDim.z = 1;
+      ++na;
+    }
+    cfg.attrs = attrs;
+    cfg.numAttrs = (unsigned)na;
+    const cudaError_t le = cudaLaunchKernelExC(&cfg, fn, args);
+    if (le != cudaSuccess && cl > 1) {
+      cudaGetLastError();   // not sticky: retry without clusters
+      cl = 1;
+      continue;
+    }
+    ECB_CUDA(le);
+    break;
   }
-  cfg.attrs = attrs;
-  cfg.numAttrs = (unsigned)na;
-  ECB_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
   ECB_LAUNCHED();
   return 0;
 }

@@ -184,6 +184,9 @@ __global__ void __launch_bounds__(256) gn_finalize_kernel(GnSrc a, GnSrc b, floa
   }
 }
 
+// round-to-nearest TF32 (operands of a single-pass TF32 consumer are rounded by their producer, tc_conv.cu)
+__device__ __forceinline__ float gn_rn_tf32(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
+
 __device__ __forceinline__ float4 gn_affine(const float4& v, float mean, float rstd, const float4& g, const float4& be) {
   return make_float4((v.x - mean) * rstd * g.x + be.x, (v.y - mean) * rstd * g.y + be.y, (v.z - mean) * rstd * g.z + be.z,
                      (v.w - mean) * rstd * g.w + be.w);
@@ -192,7 +195,7 @@ __device__ __forceinline__ float4 gn_affine(const float4& v, float mean, float r
 template <bool HAS_B, bool RAW, bool ELU>
 __global__ void __launch_bounds__(256)
 gn_apply_kernel(const GnSrc a, const GnSrc b, float* __restrict__ out_raw, float* __restrict__ out_elu,
-                long long out_item_stride, long long rows, int C) {
+                long long out_item_stride, long long rows, int C, int round_out) {
   const int item = blockIdx.y;
   const float mean_a = (float)a.partial[(long long)item * a.slots * 2], rstd_a = (float)a.partial[(long long)item * a.slots * 2 + 1];
   const float mean_b = HAS_B ? (float)b.partial[(long long)item * b.slots * 2] : 0.f;
@@ -228,7 +231,7 @@ gn_apply_kernel(const GnSrc a, const GnSrc b, float* __restrict__ out_raw, float
                                      __ldg(reinterpret_cast<const float4*>(b.beta + c)));
           v[k].x += w.x; v[k].y += w.y; v[k].z += w.z; v[k].w += w.w;
         }
-        if (RAW) o_raw[i] = v[k];
+        if (RAW) o_raw[i] = round_out ? make_float4(gn_rn_tf32(v[k].x), gn_rn_tf32(v[k].y), gn_rn_tf32(v[k].z), gn_rn_tf32(v[k].w)) : v[k];
       }
       e[4 * k + 0] = v[k].x; e[4 * k + 1] = v[k].y; e[4 * k + 2] = v[k].z; e[4 * k + 3] = v[k].w;
     }
@@ -237,7 +240,9 @@ gn_apply_kernel(const GnSrc a, const GnSrc b, float* __restrict__ out_raw, float
 #pragma unroll
       for (int k = 0; k < U; ++k) {
         const long long i = base + threadIdx.x + k * 256;
-        if (i < n4) o_elu[i] = make_float4(e[4 * k + 0], e[4 * k + 1], e[4 * k + 2], e[4 * k + 3]);
+        if (i < n4)
+          o_elu[i] = round_out ? make_float4(gn_rn_tf32(e[4 * k + 0]), gn_rn_tf32(e[4 * k + 1]), gn_rn_tf32(e[4 * k + 2]), gn_rn_tf32(e[4 * k + 3]))
+                               : make_float4(e[4 * k + 0], e[4 * k + 1], e[4 * k + 2], e[4 * k + 3]);
       }
     }
   }
@@ -436,7 +441,7 @@ int launch_segment_scale(const float* x, long long batch_stride, long long seg_s
   return 0;
 }
 int launch_gn_apply2(const GnSrc& a, const GnSrc* b, float* out_raw, float* out_elu, long long out_item_stride, int n_items,
-                     long long rows, int C, float eps, cudaStream_t s) {
+                     long long rows, int C, float eps, cudaStream_t s, int round_out) {
   ECB_REQUIRE(C % 4 == 0 && (out_raw || out_elu), "gn_apply: C=%d", C);
   const long long n4 = rows * C / 4;
   dim3 grid((unsigned)min(cdiv(n4, 256 * 4), 4096LL), (unsigned)n_items);
@@ -444,7 +449,7 @@ int launch_gn_apply2(const GnSrc& a, const GnSrc* b, float* out_raw, float* out_
                  4.0 * (double)rows * C * n_items * ((b ? 2 : 1) + (out_raw ? 1 : 0) + (out_elu ? 1 : 0)));
   gn_finalize_kernel<<<dim3((unsigned)n_items, b ? 2 : 1), 256, 0, s>>>(a, b ? *b : a, eps);
   const GnSrc bb = b ? *b : a;
-#define ECB_GN_LAUNCH(HB, R, E) gn_apply_kernel<HB, R, E><<<grid, 256, 0, s>>>(a, bb, out_raw, out_elu, out_item_stride, rows, C)
+#define ECB_GN_LAUNCH(HB, R, E) gn_apply_kernel<HB, R, E><<<grid, 256, 0, s>>>(a, bb, out_raw, out_elu, out_item_stride, rows, C, round_out)
   if (b) {
     if (out_raw && out_elu) ECB_GN_LAUNCH(true, true, true);
     else if (out_raw) ECB_GN_LAUNCH(true, true, false);

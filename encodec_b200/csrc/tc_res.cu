@@ -15,6 +15,9 @@
 // in a 3-deep TMA ring, the processed operands and both TMEM accumulators are double-buffered, so loads run ahead and
 // GEMM 1 of tile i+1 runs while tile i is between its two GEMMs.
 // The element-wise work (three ELUs per element, ~16 instructions each) is what bounds it: ~2250 issue cycles per tile.
+// SPLIT = 3: split-operand TF32 (fp32-accurate; the encoder). SPLIT = 1: one TF32 pass (the decoder's default scheme): X
+// arrives TF32-rounded from its producer, e = rn_tf32(ELU(x)) and H = rn_tf32(ELU(.)) are rounded when they are written,
+// the *_lo operands, their MMAs and the correction accumulators do not exist.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -52,8 +55,10 @@ struct ResArgs {
   int row_base;          // row coordinate of output row 0's first tap in the X map
   int pad_left;          // left padding of the k3 conv (2 causal, 1 otherwise): row shift of the shortcut's X rows
   int halo;              // reflected rows to write around Y
+  int round_out;         // store TF32-rounded Y (its consumer is a single-pass TF32 conv)
 };
 
+template <int SPLIT>
 __global__ void __launch_bounds__(R_THREADS, 1)
 tc_res_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w1h,
               const __grid_constant__ CUtensorMap map_w1l, const __grid_constant__ CUtensorMap map_wch,
@@ -113,14 +118,14 @@ tc_res_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (elect_one()) {
-      mbar_expect_tx(w_full, 3 * W1CH + 2 * WCCH);
+      mbar_expect_tx(w_full, SPLIT == 3 ? 3 * W1CH + 2 * WCCH : (3 * W1CH + 2 * WCCH) / 2);
       for (int c = 0; c < 3; ++c) {
         tma_load_2d(sb + OFF_W + c * W1CH, &map_w1h, w_full, c * RC, 0);
-        tma_load_2d(sb + OFF_W + c * W1CH + W1CH / 2, &map_w1l, w_full, c * RC, 0);
+        if (SPLIT == 3) tma_load_2d(sb + OFF_W + c * W1CH + W1CH / 2, &map_w1l, w_full, c * RC, 0);
       }
       for (int c = 0; c < 2; ++c) {
         tma_load_2d(sb + OFF_W + 3 * W1CH + c * WCCH, &map_wch, w_full, c * RC, 0);
-        tma_load_2d(sb + OFF_W + 3 * W1CH + c * WCCH + WCCH / 2, &map_wcl, w_full, c * RC, 0);
+        if (SPLIT == 3) tma_load_2d(sb + OFF_W + 3 * W1CH + c * WCCH + WCCH / 2, &map_wcl, w_full, c * RC, 0);
       }
     }
     __syncwarp();
@@ -155,8 +160,12 @@ tc_res_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
           const uint64_t da = mk(e_hi + j * 128), dl = mk(e_lo + j * 128), db = mk(sb + OFF_W + j * W1CH);
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            tcgen05_mma_tf32(d, da + 2u * k, db + 2u * k, idesc32, (j > 0 || k > 0) ? 1u : 0u);   // [main | corr] (+)= e * [W1_hi | W1_lo]
-            tcgen05_mma_tf32(d + RH, dl + 2u * k, db + 2u * k, idesc16, 1u);                      // corr += e_lo * W1_hi
+            if (SPLIT == 3) {
+              tcgen05_mma_tf32(d, da + 2u * k, db + 2u * k, idesc32, (j > 0 || k > 0) ? 1u : 0u);   // [main | corr] (+)= e * [W1_hi | W1_lo]
+              tcgen05_mma_tf32(d + RH, dl + 2u * k, db + 2u * k, idesc16, 1u);                      // corr += e_lo * W1_hi
+            } else {
+              tcgen05_mma_tf32(d, da + 2u * k, db + 2u * k, idesc16, (j > 0 || k > 0) ? 1u : 0u);   // main (+)= e * W1_hi
+            }
           }
         }
         tcgen05_commit(a1_full(s));
@@ -174,13 +183,13 @@ tc_res_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
         const uint64_t dx = mk(x_hi), dxl = mk(x_lo), db1 = mk(sb + OFF_W + 3 * W1CH + WCCH);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          tcgen05_mma_tf32(d, dh + 2u * k, db0 + 2u * k, idesc64, k > 0 ? 1u : 0u);   // H * [W3_hi | W3_lo]
-          tcgen05_mma_tf32(d + RC, dhl + 2u * k, db0 + 2u * k, idesc32, 1u);
+          tcgen05_mma_tf32(d, dh + 2u * k, db0 + 2u * k, SPLIT == 3 ? idesc64 : idesc32, k > 0 ? 1u : 0u);   // H * [W3_hi | W3_lo]
+          if (SPLIT == 3) tcgen05_mma_tf32(d + RC, dhl + 2u * k, db0 + 2u * k, idesc32, 1u);
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          tcgen05_mma_tf32(d, dx + 2u * k, db1 + 2u * k, idesc64, 1u);                 // + X * [Ws_hi | Ws_lo]
-          tcgen05_mma_tf32(d + RC, dxl + 2u * k, db1 + 2u * k, idesc32, 1u);
+          tcgen05_mma_tf32(d, dx + 2u * k, db1 + 2u * k, SPLIT == 3 ? idesc64 : idesc32, 1u);                 // + X * [Ws_hi | Ws_lo]
+          if (SPLIT == 3) tcgen05_mma_tf32(d + RC, dxl + 2u * k, db1 + 2u * k, idesc32, 1u);
         }
         tcgen05_commit(a2_full(s));
         tcgen05_commit(h_empty);
@@ -238,9 +247,13 @@ tc_res_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
           const int q = q0 + u * 256;
           if (q < XT / 16) {
             const float4 ev = make_float4(e[u * 4 + 0], e[u * 4 + 1], e[u * 4 + 2], e[u * 4 + 3]);
-            xl[q] = split4(v[u]);
-            eh[q] = ev;
-            el[q] = split4(ev);
+            if (SPLIT == 3) {
+              xl[q] = split4(v[u]);
+              eh[q] = ev;
+              el[q] = split4(ev);
+            } else {
+              eh[q] = make_float4(rn_tf32(ev.x), rn_tf32(ev.y), rn_tf32(ev.z), rn_tf32(ev.w));
+            }
           }
         }
       }
@@ -259,8 +272,12 @@ tc_res_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       uint32_t vm[16], vc[16];
       tcgen05_ld16(lane_base + (uint32_t)(s * 32), vm);
-      tcgen05_ld16(lane_base + (uint32_t)(s * 32 + RH), vc);
+      if (SPLIT == 3) tcgen05_ld16(lane_base + (uint32_t)(s * 32 + RH), vc);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (SPLIT != 3) {
+#pragma unroll
+        for (int g = 0; g < 16; ++g) vc[g] = 0u;
+      }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(a1_empty(s));
@@ -280,9 +297,13 @@ tc_res_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         const float4 h = make_float4(hv[g * 4 + 0], hv[g * 4 + 1], hv[g * 4 + 2], hv[g * 4 + 3]);
-        hh[g ^ (r & 7)] = h;
-        hl[g ^ (r & 7)] = make_float4(rn_tf32(h.x - trunc_tf32(h.x)), rn_tf32(h.y - trunc_tf32(h.y)),
-                                      rn_tf32(h.z - trunc_tf32(h.z)), rn_tf32(h.w - trunc_tf32(h.w)));
+        if (SPLIT == 3) {
+          hh[g ^ (r & 7)] = h;
+          hl[g ^ (r & 7)] = make_float4(rn_tf32(h.x - trunc_tf32(h.x)), rn_tf32(h.y - trunc_tf32(h.y)),
+                                        rn_tf32(h.z - trunc_tf32(h.z)), rn_tf32(h.w - trunc_tf32(h.w)));
+        } else {
+          hh[g ^ (r & 7)] = make_float4(rn_tf32(h.x), rn_tf32(h.y), rn_tf32(h.z), rn_tf32(h.w));
+        }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
@@ -302,8 +323,12 @@ tc_res_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       uint32_t vm[32], vc[32];
       tcgen05_ld32(lane_base + (uint32_t)(64 + s * 64), vm);
-      tcgen05_ld32(lane_base + (uint32_t)(64 + s * 64 + RC), vc);
+      if (SPLIT == 3) tcgen05_ld32(lane_base + (uint32_t)(64 + s * 64 + RC), vc);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (SPLIT != 3) {
+#pragma unroll
+        for (int g = 0; g < 32; ++g) vc[g] = 0u;
+      }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(a2_empty(s));
@@ -338,7 +363,8 @@ tc_res_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
           const int rr = (lane >> 2) + 8 * q;
           const int m = m_warp + rr;
           if (m >= p.M) break;
-          const float4 y = make_float4(yv[q * 4 + 0], yv[q * 4 + 1], yv[q * 4 + 2], yv[q * 4 + 3]);
+          const float4 y = p.round_out ? make_float4(rn_tf32(yv[q * 4 + 0]), rn_tf32(yv[q * 4 + 1]), rn_tf32(yv[q * 4 + 2]), rn_tf32(yv[q * 4 + 3]))
+                                       : make_float4(yv[q * 4 + 0], yv[q * 4 + 1], yv[q * 4 + 2], yv[q * 4 + 3]);
           *reinterpret_cast<float4*>(base + (long long)m * RC) = y;
           if (mirrors) {
             if (m >= 1 && m <= p.halo) *reinterpret_cast<float4*>(base - (long long)m * RC) = y;
@@ -360,6 +386,7 @@ tc_res_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
 }  // namespace
 
 int launch_tc_res32(const TcResParams& p, cudaStream_t stream) {
+  ECB_REQUIRE(p.split == 1 || p.split == 3, "tc_res: split must be 1 or 3");
   ECB_REQUIRE(p.x && p.out && p.w1_hi && p.w1_lo && p.wc_hi && p.wc_lo && p.b1 && p.bcat, "tc_res: null argument");
   ECB_REQUIRE(p.M > ACT_HALO && p.n_items > 0, "tc_res: bad M=%lld / items=%d", p.M, p.n_items);
   ECB_REQUIRE(p.pad_left >= 0 && p.pad_left <= 2 && p.x_first <= -p.pad_left, "tc_res: bad padding");
@@ -396,15 +423,18 @@ int launch_tc_res32(const TcResParams& p, cudaStream_t stream) {
   a.row_base = (int)(-p.pad_left - p.x_first);
   a.pad_left = p.pad_left;
   a.halo = p.halo;
+  a.round_out = p.round_out;
   static DeviceOnce attr_set;
   if (!attr_set.done()) {
-    ECB_CUDA(cudaFuncSetAttribute(tc_res_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, R_SMEM));
+    ECB_CUDA(cudaFuncSetAttribute(tc_res_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, R_SMEM));
+    ECB_CUDA(cudaFuncSetAttribute(tc_res_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, R_SMEM));
     attr_set.mark();
   }
   const int grid = (int)(total < sm_count() ? total : sm_count());
   const double rows = (double)p.M * p.n_items;
   ProfScope prof(PROF_TC_RES, stream, 2.0 * rows * (3 * RC * RH + RH * RC + RC * RC), 4.0 * rows * RC * 2);
-  tc_res_kernel<<<grid, R_THREADS, R_SMEM, stream>>>(mx, w1h, w1l, wch, wcl, a);
+  if (p.split == 3) tc_res_kernel<3><<<grid, R_THREADS, R_SMEM, stream>>>(mx, w1h, w1l, wch, wcl, a);
+  else tc_res_kernel<1><<<grid, R_THREADS, R_SMEM, stream>>>(mx, w1h, w1l, wch, wcl, a);
   ECB_LAUNCHED();
   return 0;
 }

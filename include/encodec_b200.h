@@ -72,10 +72,12 @@ int ecb_codec_load_tensor(ecb_codec* codec, const char* key, const float* data, 
  * Fails if a tensor the spec requires was never loaded. */
 int ecb_codec_finalize(ecb_codec* codec, void* stream);
 
-/* Decoder operand scheme of the tensor-core convolutions (weight-norm models). 0 (default): split-operand TF32,
- * fp32-accurate, like the encoder. 1: one TF32 pass with operands rounded to TF32 by their producers -- about 1.6x
- * faster decoder convs, decoded audio within 1e-4 max-abs / 2.3e-5 RMS of the fp32 result on the golden cases
- * (the north_star bar is 1e-3 / 1e-4). The encoder and the quantiser are always fp32-accurate. */
+/* Decoder operand scheme of the tensor-core convolutions (weight-norm and GroupNorm models; LayerNorm models always
+ * run split operands). 1 (the default of a fresh codec): one TF32 pass with operands rounded to TF32 by their producers
+ * -- nothing downstream of the decoder is discrete; decoded audio within ~1e-4 max-abs / 2.5e-5 RMS of the reference on
+ * the golden cases and on real speech at three loudness levels (the north_star bar is 1e-3 / 1e-4), decoder convs about
+ * 1.6x faster. 0: split-operand TF32 (3 products, fp32-accurate), like the encoder. The encoder and the quantiser are
+ * always fp32-accurate. The environment variable ECB_DEC_SPLIT=3 forces the accurate scheme for codecs that never call this. */
 int ecb_codec_set_decoder_precision(ecb_codec* codec, int32_t tf32_single_pass);
 
 /* ---- SEANetEncoder.forward (modules/seanet.py:145-146; SConv1d conv.py:202-221; SLSTM lstm.py:22-28)
@@ -158,16 +160,17 @@ void ecb_debug_tap(float* buf, int64_t capacity, int32_t stage);
  * steps 20..27 into buf ([3 roles][8 steps][16 events] int64, device memory); tools/lstm_trace.py prints them. */
 void ecb_debug_lstm_trace(long long* buf);
 
+/* Diagnostic: the encoder's SLSTM alone on x [B][T][H] -> out [B][T][H] (tools/lstm_bench.py). */
+size_t ecb_debug_lstm_workspace_bytes(const ecb_codec* codec, int64_t batch, int64_t T);
+int ecb_debug_lstm(ecb_codec* codec, const float* x, float* out, int64_t batch, int64_t T, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
 /* Diagnostic (tests only): one launch of the tensor-core implicit-GEMM convolution (csrc/tc_conv.cu) on caller
  * buffers. a0 points at (item 0, sample a0_first, channel 0) of a channels-last activation from which a0_rows
  * samples per item are addressable (reads outside are zero); output row m reads samples
  * m*stride - pad_left ... + taps - 1 of source 0, then row m of the optional 1-tap source a1. w is [taps*C0 + C1][N]
  * (N contiguous). out_raw / out_elu point at (item 0, row 0) of [M][N] outputs with `halo` reflected rows written
  * before and after each item. split = 3: fp32-accurate split-operand TF32, 1: single TF32 pass. Synchronises. */
-/* Diagnostic: the encoder's SLSTM alone on x [B][T][H] -> out [B][T][H] (tools/lstm_bench.py). */
-size_t ecb_debug_lstm_workspace_bytes(const ecb_codec* codec, int64_t batch, int64_t T);
-int ecb_debug_lstm(ecb_codec* codec, const float* x, float* out, int64_t batch, int64_t T, void* workspace,
-                   size_t workspace_bytes, void* stream);
 int ecb_debug_tc_conv(const float* a0, int64_t a0_item_stride, int32_t C0, int64_t a0_first, int64_t a0_rows,
                       int32_t taps, int32_t stride, int32_t pad_left, const float* a1, int64_t a1_item_stride,
                       int32_t C1, int64_t a1_rows, const float* w, const float* bias, int32_t N, int64_t M,

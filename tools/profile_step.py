@@ -54,7 +54,8 @@ else:
         audio, codes, _, _ = model(x)
         if os.environ.get("PROFILE_ECDC"):
             from encodec_b200 import compress
-            compress.compress(model, x[0].cpu())
+            blob = compress.compress(model, x[0])
+            compress.decompress(blob, model)
         torch.cuda.synchronize()
         rt.cudaProfilerStop()
 print("profiled one step of", name, "batch", wl.get("batch"))
