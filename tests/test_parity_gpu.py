@@ -497,6 +497,7 @@ def test_lstm_recurrence_forms_agree(batch, steps, monkeypatch):
     want = orc.elu(orc.slstm(xin, p, f"encoder.model.{idx}", case["spec"].lstm))
     want = np.transpose(want, (0, 2, 1))
     for name, got in outs.items():
+        print(f"[lstm {batch}x{steps}] {name}: max error vs float64 relative to max |y|: {ug.rel_err(got, want):.3e}")
         assert ug.rel_err(got, want) < 5e-6, (name, ug.rel_err(got, want))
     assert ug.rel_err(outs["ffma"], outs["stepwise"]) < 5e-6
     assert ug.rel_err(outs["ffma"], outs["tensor"]) < 5e-6
