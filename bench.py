@@ -601,15 +601,32 @@ def run_cfg4(wl, dev, rank, world, steps, warmup, check):
     return res
 
 
+_REAL_STDOUT = None
+
+
 def init_dist(dev, world):
+    """NCCL over the GPUs of this node. NCCL_DEBUG stays whatever the caller set; since NCCL logs to stdout, file descriptor 1
+    is pointed at stderr for the rest of the run and the one JSON line is written to the saved real stdout at the end."""
+    global _REAL_STDOUT
     if world == 1:
         return
     import torch.distributed as dist
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-    # NCCL's own log (NCCL_DEBUG is the caller's choice) goes to stderr: stdout carries the one JSON line
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     dist.init_process_group("nccl", device_id=dev)
     dist.barrier()
+
+
+def emit(line):
+    text = json.dumps(line) + "\n"
+    if _REAL_STDOUT is None:
+        sys.stdout.write(text)
+        sys.stdout.flush()
+    else:
+        sys.stdout.flush()
+        os.write(_REAL_STDOUT, text.encode())
 
 
 def main():
@@ -770,7 +787,7 @@ def main():
                 "tf32_gemm_tflops_measured": tf32_peak, "also": also,
             }
     if rank == 0 and line is not None:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

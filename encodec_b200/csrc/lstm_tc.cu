@@ -1,34 +1,42 @@
 // SLSTM recurrence on the tensor cores (reference modules/lstm.py:12-28 -> nn.LSTM(512, 512, 2), gates i,f,g,o, zero
 // state), H = 512. One persistent kernel per LSTM layer; the input projection of all steps is a tc_conv GEMM (pre).
 //
-// Geometry: 128 CTAs, CTA j owns hidden units 4j .. 4j+3 = 16 gate rows of W_hh for ALL items. Its [16 x 512] slice sits in
-// shared memory for the whole sequence (un-replicated: 128 slices = W_hh exactly once on the chip), and the recurrent
-// product of a group of 64 items is ONE tensor-core contraction per step,
-//     rec[64 items][16 gate columns] = h_{t-1}[64][512] . W_slice^T        (tcgen05.mma, M = 64, N = 16 | 32, K = 512)
-// with the accumulator in TMEM. What moves per step is h_{t-1} (all 128 CTAs need all of it): every CTA publishes its 4
-// units of h_t to an L2-resident buffer, bumps an arrival counter, and pulls the complete h_t back with TMA.
+// Geometry: 128 CTAs = NU unit blocks x NB batch parts. A unit block owns UPC hidden units (4 UPC gate rows of W_hh); its
+// [4 UPC x 512] slice sits in shared memory for the whole sequence (un-replicated inside a batch part), and the recurrent
+// product of a GROUP of items is a tensor-core contraction per step,
+//     rec[items][4 UPC gate columns] = h_{t-1}[items][512] . W_slice^T        (tcgen05.mma, accumulator in TMEM).
+// What moves per step is h_{t-1}: every CTA publishes its UPC units of h_t to an L2-resident buffer, bumps an arrival
+// counter, and pulls the complete h_t of its groups back with bulk copies. UPC = 4: 128 unit blocks, one batch part (the
+// shortest chain: launches below 192 items). UPC = 8: 64 unit blocks x 2 batch parts -- an MMA of this size costs little
+// more with twice the N, so the groups of a large batch are split over two sets of SMs that step independently (15-18 %
+// more throughput at 512-960 items).
 //
 // fp32 accuracy from fp16 tensor-core operands. fp16 has the 11-bit significand of TF32 at half the bytes and twice the
 // MMA rate, and h in (-1, 1) / LSTM weights fit its range. Operands are split the way tc_conv splits TF32:
 //     h = h1 + 2^-11 h2,  h1 = fp16(h), h2 = fp16((h - h1) 2^11)        (written by the producer of h)
 //     w = w1 + 2^-11 w2                                                 (split once at load, lstm_tc_pack)
 //     rec = sum h1 w1  +  2^-11 (sum h1 w2 + sum h2 w1)                 (h2 w2 2^-22 dropped, as in the 3xTF32 scheme)
-// fp16 x fp16 products are exact in the fp32 accumulator. Small MMAs cost ~55 cycles each whatever their shape (measured:
-// the first version issued two M = 64 MMAs per K step and spent 3500 of its 9000 cycles per step in the tensor pipe), so
-// all three products come from ONE M = 128, N = 32 MMA per K step of 16: the A tile stacks the h1 rows and the h2 rows of
-// the 64 items (rows 32 q + r = h1 of item 16 q + r, rows 32 q + 16 + r = its h2, so both land in the same TMEM lane
-// quadrant), B = [w1 | w2]; D rows of h1 give [h1 w1 | h1 w2], D rows of h2 give [h2 w1 | (h2 w2, unused)], and the epilogue
-// adds the pieces with one warp shuffle. Back-to-back MMAs into the SAME accumulator columns serialise on the tensor pipe's
-// latency (~100 cycles each at this size), so the four K sub-steps of a tile go to four independent accumulators which the
-// epilogue sums; that also keeps every accumulator at 8 accumulating MMAs (the tensor core truncates when it adds into its
-// accumulator, tc_conv.cu).
+// fp16 x fp16 products are exact in the fp32 accumulator. All three products come from ONE MMA per K step of 16: the A
+// tile stacks the h1 rows and the h2 rows of the items (rows 32 q + r = h1 of item 16 q + r, rows 32 q + 16 + r = its h2, so
+// both land in the same TMEM lane quadrant), B = [w1 | w2]; D rows of h1 give [h1 w1 | h1 w2], D rows of h2 give
+// [h2 w1 | (h2 w2, unused)], and the epilogue adds the pieces with one warp shuffle.
 //
-// Roles (12 warps): warp 0 = loader (polls the 8 per-K-tile arrival counters of the group with one coalesced acquire load,
-// then TMA-loads h1 / h2 tiles [64 items x 64 units], SWIZZLE_128B, into an 8-stage ring), warp 1 = MMA issuer, warps 4-11 =
-// cell epilogue: tcgen05.ld the 16 gate columns, + pre-gates, cell update (c stays in shared memory), h_t -> (h1, h2) fp16 to
-// L2, layer output y = h (+ skip) (ELU) to HBM; one CTA barrier, one fence, one release-increment of the counter.
-// Batches above 64 items run as independent groups of 64 through the same ring (two TMEM accumulator buffers), so the
-// exchange latency of one group hides behind the loads and MMAs of the others.
+// A step is a chain of ~1000-cycle hops (publish, poll, copy, commit) around the MMAs, so the K loop is shortened by STACKING
+// K tiles along M: a group of IG items has R = 2 IG operand rows, KP = 128 / R consecutive K tiles of it form one 128-row A
+// tile, and B holds the KP matching weight tiles side by side. One MMA then covers KP x 16 of K; its diagonal blocks
+// D[rows of tile i][columns of tile i] are the useful ones, the epilogue warps of the KP row blocks add their parts through
+// shared memory. A batch of <= 64 items runs as groups of 32 (KP = 2, 16 MMAs per group-step), larger ones as groups of 64.
+//
+// The exchange buffers hold the SWIZZLE_128B shared-memory image of every K tile (the epilogue stores into swizzled
+// positions), so the KP tiles of a stage are ONE contiguous 16 KB bulk copy: a tensor-map box of 128-byte rows at a 1 KB
+// pitch moved only ~35 B per cycle into the SM and was the longest stretch of the step.
+//
+// Roles (12 warps): warp 0 = loader (polls the 8 per-K-tile arrival counters of a group with one coalesced acquire load,
+// one cross-proxy fence, then the bulk copies into an 8-stage ring), warp 1 = MMA issuer, warp 2 = publisher (one
+// release-increment per group-step once the epilogue warps have stored h_t), warps 4-11 = cell epilogue: tcgen05.ld the gate
+// columns, + pre-gates, cell update (c stays in shared memory), h_t -> (h1, h2) fp16 to L2, layer output y = h (+ skip)
+// (ELU) to HBM. Groups run through the same ring with two TMEM accumulator buffers, so the exchange latency of one group
+// hides behind the copies and MMAs of the others.
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -39,17 +47,12 @@ namespace {
 using namespace tc;
 
 constexpr int LT_H = 512;
-constexpr int LT_CTAS = 128;        // unit blocks
-constexpr int LT_UNITS = 4;         // hidden units per CTA
-constexpr int LT_NCOL = 16;         // gate columns per CTA: n = unit * 4 + gate
-constexpr int LT_ITEMS = 64;        // most items per group (IG = 64: MMA M = 128; IG = 32: M = 64)
+constexpr int LT_CTAS = 128;
 constexpr int LT_KT = 64;           // K elements per shared-memory tile (128 bytes of fp16)
 constexpr int LT_NKT = LT_H / LT_KT;   // 8
 constexpr int LT_STAGES = 8;
 constexpr int LT_THREADS = 384;
-constexpr int LT_ROWS = 2 * LT_ITEMS;             // most A rows per group: h1 and h2 row of every item
-constexpr int LT_STAGE_BYTES = LT_ROWS * 128;     // ring slot: one [128 rows x 64 k] tile, 16 KB (IG = 32 uses half of it)
-constexpr int LT_W_TILE = 2 * LT_NCOL * 128;      // [w1 (16 rows) | w2 (16 rows)] x 64 k = 4 KB
+constexpr int LT_STAGE_BYTES = 128 * 128;         // ring slot: one [128 rows x 64 k] A tile = KP K tiles of a group, 16 KB
 constexpr int LT_TMEM_COLS = 256;                 // two accumulator buffers of up to 128 columns
 constexpr int LT_MAX_GROUPS = 16;
 constexpr float LT_LO_SCALE = 2048.f;             // 2^11
@@ -61,11 +64,9 @@ struct LstmTcParams {
   long long skip_stride;
   float* out;            // item b at out + b * out_stride, [T][H]
   long long out_stride;
-  __half* hg;            // [2][G][8 K tiles][2 IG rows][64] exchange buffers (L2-resident), stored as the SWIZZLE_128B shared-memory
-                         // image of each K tile (16-byte chunk c of row r sits at chunk c ^ (r & 7)): a tile, and the KP tiles of
-                         // a stage, are then ONE contiguous bulk copy -- a tensor-map box of 128-byte rows at a 1 KB pitch
-                         // moved only ~35 B per cycle into the SM and was the longest stretch of the step. Row 32 q + 16 part + r
-                         // of a group = split part `part` (0: h1, 1: h2) of item 16 q + r
+  __half* hg;            // [2][G][8 K tiles][2 IG rows][64] exchange buffers (L2-resident), each K tile stored as its SWIZZLE_128B
+                         // shared-memory image (16-byte chunk c of row r at chunk c ^ (r & 7)). Row 32 q + 16 part + r of a group
+                         // = split part `part` (0: h1, 1: h2) of item 16 q + r
   unsigned int* cnt;     // [G][8] arrival counters (one per group and K tile), zeroed by the host
   int B, T, G, out_elu;
   long long* trace;      // diagnostic: [3 roles][LT_TR_STEPS][16] clock64 stamps of CTA 0, or nullptr
@@ -113,7 +114,10 @@ __device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64
       "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+template <int W>
+__device__ __forceinline__ void tmem_ldw(uint32_t taddr, float (&v)[W]);
+template <>
+__device__ __forceinline__ void tmem_ldw<8>(uint32_t taddr, float (&v)[8]) {
   uint32_t r[8];
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
@@ -122,13 +126,14 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
-__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int x, int y, uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y), "h"(mask)
-      : "memory");
+template <>
+__device__ __forceinline__ void tmem_ldw<16>(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  tcgen05_ld16(taddr, r);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
-// 1-D bulk copies global -> shared (the exchange buffers are stored as ready-made shared-memory images, see below)
+// 1-D bulk copies global -> shared (the exchange buffers are ready-made shared-memory images)
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
                "r"(bar)
@@ -150,28 +155,41 @@ __device__ __forceinline__ void cluster_sync_all() {
 // kind::f16 instruction descriptor: D fp32 (bits [4,6) = 1), A / B fp16 (format 0), both K-major, N >> 3 in [17,23), M >> 4 in [24,29)
 constexpr uint32_t idesc_f16(int m, int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24); }
 
-// CL = cluster size (1, 2, 4): the CTAs of a cluster need the same h tiles, so each loads 1 / CL of the rows of every tile
-// and TMA-multicasts them to all. IG = items per group (64 | 32 | 16). A step is a chain of ~1000-cycle hops (publish, poll,
-// TMA, commit) around the MMAs, and an MMA of this size costs ~110 cycles whatever its M and N (measured) -- so the K loop
-// is shortened by STACKING K tiles along M: a group of IG items has R = 2 IG operand rows, KP = 128 / R consecutive K tiles
-// of it form one 128-row A tile, and B holds the KP matching weight tiles side by side (N = 32 KP). One MMA then covers
-// KP x 16 of K; its diagonal blocks D[rows of tile i][columns of tile i] are the useful ones, the epilogue warps of the
-// KP row blocks add their parts through shared memory. A group-step costs 32 / KP MMAs; a batch of <= 64 items runs as
-// groups of 32 or 16 items whose chains interleave.
-template <int CL, int IG>
+// CL = cluster size (1, 2, 4): the CTAs of a cluster need the same h tiles, so each copies 1 / CL of the rows of every tile and
+// multicasts them to all. IG = items per group (64 | 32). UPC = hidden units per CTA (4 | 8).
+template <int CL, int IG, int UPC>
 __global__ void __launch_bounds__(LT_THREADS, 1)
 lstm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const LstmTcParams p) {
+  constexpr int NCOL = 4 * UPC;                 // gate columns per CTA: n = unit * 4 + gate
+  constexpr int W_TILE = 2 * NCOL * 128;        // [w1 (NCOL rows) | w2 (NCOL rows)] x 64 k
+  constexpr int NU = LT_H / UPC;                // unit blocks
+  constexpr int NB = LT_CTAS / NU;              // batch parts: groups g = part, part + NB, ... belong to a part
+  constexpr int ROWS = 2 * IG;                  // operand rows per group: h1 and h2 row of every item
+  constexpr int KP = 128 / ROWS;                // K tiles stacked along M in one MMA (1 | 2)
+  constexpr int NACC = KP == 1 ? 2 : 1;         // accumulators per buffer (<= 16 accumulating MMAs each: the tensor core truncates)
+  constexpr int NMMA = 2 * NCOL * KP;           // N of one MMA
+  constexpr int ACC_COLS = NACC * NMMA;         // TMEM columns per accumulator buffer
+  constexpr int QPG = IG / 16;                  // TMEM lane quadrants per K part
+  constexpr int UW = UPC / 2;                   // units per epilogue warp (2 | 4)
+  constexpr int PP = UW / 2;                    // (item, unit) pairs per epilogue lane (1 | 2)
+  constexpr int CW = 4 * UW;                    // gate columns per epilogue warp (8 | 16)
+  static_assert(2 * ACC_COLS <= LT_TMEM_COLS, "TMEM budget");
+
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;             // SWIZZLE_128B tiles: 1024-byte aligned
   uint8_t* smem_gen = smem_raw + (base - raw_addr);
-  const uint32_t a_ring = base;                                   // [LT_STAGES][h1 tile | h2 tile]
-  const uint32_t w_smem = base + LT_STAGES * LT_STAGE_BYTES;      // [LT_NKT][LT_W_TILE]
-  constexpr int CS_OFF = LT_STAGES * LT_STAGE_BYTES + LT_NKT * LT_W_TILE;
-  float* cs = reinterpret_cast<float*>(smem_gen + CS_OFF);        // [G][64 items][4 units] cell state
-  const int cs_bytes = p.G * IG * LT_UNITS * 4;
-  constexpr int XS_BYTES = 8 * 16 * 8 * 4;
-  float* xs = reinterpret_cast<float*>(smem_gen + CS_OFF + cs_bytes);   // [slots][16][8] K-part exchange between epilogue warps (KP > 1)
+  const uint32_t a_ring = base;                                   // [LT_STAGES][128 rows x 128 B]
+  const uint32_t w_smem = base + LT_STAGES * LT_STAGE_BYTES;      // [LT_NKT][W_TILE]
+  constexpr int CS_OFF = LT_STAGES * LT_STAGE_BYTES + LT_NKT * W_TILE;
+  const int cta = blockIdx.x;
+  const int ub = cta % NU;                       // unit block
+  const int bp = cta / NU;                       // batch part
+  const int n_local = p.G > bp ? (p.G - bp + NB - 1) / NB : 0;   // groups of this batch part
+  float* cs = reinterpret_cast<float*>(smem_gen + CS_OFF);        // [n_local][IG items][UPC units] cell state
+  const int cs_bytes = ((p.G + NB - 1) / NB) * IG * UPC * 4;
+  constexpr int XS_BYTES = 4 * 16 * CW * 4;
+  float* xs = reinterpret_cast<float*>(smem_gen + CS_OFF + cs_bytes);   // [teams][16][CW] K-part exchange between epilogue warps (KP = 2)
   const uint32_t bar_base = base + CS_OFF + cs_bytes + XS_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (LT_STAGES + s); };
@@ -180,15 +198,9 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const LstmTcParams p) 
   const uint32_t w_bar = bar_base + 8u * (2 * LT_STAGES + 4);
   auto hst_bar = [&](int b) { return bar_base + 8u * (2 * LT_STAGES + 5 + b); };   // the epilogue warps have stored h_t
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + CS_OFF + cs_bytes + XS_BYTES + 8 * (2 * LT_STAGES + 7));
-  constexpr int ROWS = 2 * IG;                  // operand rows per group: h1 and h2 row of every item
-  constexpr int KP = 128 / ROWS;                // K tiles stacked along M in one MMA (1 | 2 | 4)
-  constexpr int NACC = KP == 1 ? 2 : 1;         // accumulators per buffer (<= 16 accumulating MMAs each: the tensor core truncates)
-  constexpr int ACC_COLS = NACC * 32 * KP;      // TMEM columns per accumulator buffer
-  constexpr int QPG = IG / 16;                  // TMEM lane quadrants per K part
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int cta = blockIdx.x;
   uint32_t crank = 0;
   if (CL > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
   constexpr uint16_t MC_MASK = (uint16_t)((1u << CL) - 1u);
@@ -201,13 +213,13 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const LstmTcParams p) 
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(accf_bar(b), 1);
-      mbar_init(acce_bar(b), 8);   // one arrive per epilogue warp
+      mbar_init(acce_bar(b), 8);        // one arrive per epilogue warp
       mbar_init(hst_bar(b), 2 * QPG);   // the warps that store h
     }
     mbar_init(w_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < p.G * IG * LT_UNITS; i += LT_THREADS) cs[i] = 0.f;
+  for (int i = threadIdx.x; i < n_local * IG * UPC; i += LT_THREADS) cs[i] = 0.f;
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(LT_TMEM_COLS)
                  : "memory");
@@ -218,28 +230,29 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const LstmTcParams p) 
   if (CL > 1) cluster_sync_all();   // barriers of every CTA are initialised before any remote arrive / multicast write
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
-  const int rows_per_buf = p.G * ROWS;
+  const long long buf_bytes = (long long)p.G * LT_NKT * ROWS * 128;   // one exchange buffer
+  // When all of this CTA's groups' stages fit the ring at once, local group gl owns stages gl * 8 / KP ..: a stage is then
+  // known to be free when its counters say that h_t is complete (this CTA's own epilogue of step t - 1 came after its
+  // MMAs), and the empty barriers -- ~150 cycles per stage on the step's critical path -- are not used at all.
+  const bool private_ring = n_local * (LT_NKT / KP) <= LT_STAGES;
 
   if (warp == 0) {
     // ================================ loader ================================
-    if (elect_one()) {   // this CTA's weight slice, once: 8 tiles [32 rows x 64 k]
-      mbar_expect_tx(w_bar, LT_NKT * LT_W_TILE);
-      for (int j = 0; j < LT_NKT; ++j) tma_load_2d(w_smem + j * LT_W_TILE, &map_w, w_bar, j * LT_KT, cta * 2 * LT_NCOL);
+    if (elect_one()) {   // this CTA's weight slice, once: 8 tiles [2 NCOL rows x 64 k]
+      mbar_expect_tx(w_bar, LT_NKT * W_TILE);
+      for (int j = 0; j < LT_NKT; ++j) tma_load_2d(w_smem + j * W_TILE, &map_w, w_bar, j * LT_KT, ub * 2 * NCOL);
     }
     __syncwarp();
     constexpr unsigned int STAGE_MASK = (1u << KP) - 1u;
-    // When all groups' stages fit the ring at once, group g owns stages g * 8 / KP ..: a stage is then known to be free when
-    // its counters say that h_t is complete (this CTA's own epilogue of step t - 1 came after its MMAs), and the empty
-    // barriers -- ~150 cycles per stage on the step's critical path -- are not used at all.
-    const bool private_ring = p.G * (LT_NKT / KP) <= LT_STAGES;
     uint32_t it = 0;
     for (int t = 0; t < p.T; ++t) {
-      const unsigned int target = 16u * (unsigned int)t;   // 16 CTAs publish each K tile of 64 units
-      for (int g = 0; g < p.G; ++g) {
-        const uint8_t* src_g = reinterpret_cast<const uint8_t*>(p.hg) + ((long long)(t & 1) * p.G + g) * (LT_NKT * ROWS * 128);
+      const unsigned int target = (unsigned int)(LT_KT / UPC) * (unsigned int)t;   // the CTAs that publish one K tile of 64 units
+      for (int gl = 0; gl < n_local; ++gl) {
+        const int g = bp + gl * NB;
+        const uint8_t* src_g = reinterpret_cast<const uint8_t*>(p.hg) + (long long)(t & 1) * buf_bytes + (long long)g * (LT_NKT * ROWS * 128);
         int next = 0;   // next stage (KP K tiles) of this group-step
         unsigned int spins = 0;
-        if (g == 0) LT_TRACE(0, t, 0)
+        if (gl == 0) LT_TRACE(0, t, 0)
         while (next < LT_NKT / KP) {
           unsigned int v = 0xffffffffu;
           if (t > 0 && lane < LT_NKT)
@@ -250,11 +263,11 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const LstmTcParams p) 
             continue;
           }
           // h was written through the generic proxy (by other SMs) and is read through the async proxy: one fence per poll
-          if (g == 0 && next == 0) LT_TRACE(0, t, 9)
+          if (gl == 0 && next == 0) LT_TRACE(0, t, 9)
           if (t > 0) asm volatile("fence.proxy.async.global;" ::: "memory");
-          if (g == 0 && next == 0) LT_TRACE(0, t, 10)
+          if (gl == 0 && next == 0) LT_TRACE(0, t, 10)
           while (next < LT_NKT / KP && ((ready >> (next * KP)) & STAGE_MASK) == STAGE_MASK) {
-            const int st = private_ring ? g * (LT_NKT / KP) + next : (int)(it % LT_STAGES);
+            const int st = private_ring ? gl * (LT_NKT / KP) + next : (int)(it % LT_STAGES);
             if (!private_ring) mbar_wait(empty_bar(st), ((it / LT_STAGES) & 1u) ^ 1u);
             if (elect_one()) {
               mbar_expect_tx(full_bar(st), LT_STAGE_BYTES);
@@ -271,7 +284,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const LstmTcParams p) 
               }
             }
             __syncwarp();
-            if (g == 0) LT_TRACE(0, t, 1 + next)
+            if (gl == 0) LT_TRACE(0, t, 1 + next)
             ++next;
             ++it;
           }
@@ -280,32 +293,29 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const LstmTcParams p) 
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    constexpr uint32_t idesc = idesc_f16(128, 2 * LT_NCOL * KP);   // M = 128, N = 32 KP
+    constexpr uint32_t idesc = idesc_f16(128, NMMA);
     constexpr uint32_t DESC_HI = 64u | (1u << 14) | (2u << 29);   // SBO 1024 B, version 1, SWIZZLE_128B
     auto mk_desc = [](uint32_t addr) { return ((uint64_t)DESC_HI << 32) | (uint64_t)(((addr & 0x3FFFFu) >> 4) | (1u << 16)); };
     mbar_wait(w_bar, 0);
-    const bool private_ring = p.G * (LT_NKT / KP) <= LT_STAGES;
     uint32_t it = 0, n = 0;
     for (int t = 0; t < p.T; ++t) {
-      for (int g = 0; g < p.G; ++g, ++n) {
+      for (int gl = 0; gl < n_local; ++gl, ++n) {
         const int acc = (int)(n & 1u);
         mbar_wait(acce_bar(acc), ((n >> 1) & 1u) ^ 1u);   // the epilogue has drained this accumulator buffer
         for (int j = 0; j < LT_NKT / KP; ++j, ++it) {
-          const int st = private_ring ? g * (LT_NKT / KP) + j : (int)(it % LT_STAGES);
+          const int st = private_ring ? gl * (LT_NKT / KP) + j : (int)(it % LT_STAGES);
           mbar_wait(full_bar(st), private_ring ? ((uint32_t)t & 1u) : ((it / LT_STAGES) & 1u));
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          if (g == 0) LT_TRACE(1, t, j)
+          if (gl == 0) LT_TRACE(1, t, j)
           if (elect_one()) {
             const uint32_t d = tmem_base + (uint32_t)(acc * ACC_COLS);
             const uint64_t da = mk_desc(a_ring + st * LT_STAGE_BYTES);
-            const uint64_t db = mk_desc(w_smem + j * KP * LT_W_TILE);   // KP weight tiles side by side: N = 32 KP rows
+            const uint64_t db = mk_desc(w_smem + j * KP * W_TILE);   // KP weight tiles side by side: N = 2 NCOL KP rows
 #pragma unroll
             for (int k = 0; k < LT_KT / 16; ++k) {   // rows of h1: [main | corr] (+)= h1 [w1 | w2]; rows of h2: [corr | -] (+)= h2 [w1 | w2]
               const int mm = j * (LT_KT / 16) + k;
-              mma_f16(d + (uint32_t)((mm % NACC) * 32 * KP), da + 2u * k, db + 2u * k, idesc, mm >= NACC ? 1u : 0u);
+              mma_f16(d + (uint32_t)((mm % NACC) * NMMA), da + 2u * k, db + 2u * k, idesc, mm >= NACC ? 1u : 0u);
             }
-            if (g == 0 && j < 7 && p.trace && cta == 0 && t >= LT_TR_T0 && t < LT_TR_T0 + LT_TR_STEPS)
-              p.trace[(1 * LT_TR_STEPS + (t - LT_TR_T0)) * 16 + 9 + j] = clock64();
             if (!private_ring) {
               if (CL == 1) tcgen05_commit(empty_bar(st));
               else commit_mc(empty_bar(st), MC_MASK);
@@ -313,24 +323,25 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const LstmTcParams p) 
             if (j + 1 == LT_NKT / KP) tcgen05_commit(accf_bar(acc));
           }
           __syncwarp();
-          if (g == 0 && j + 1 == LT_NKT / KP) LT_TRACE(1, t, 8)
+          if (gl == 0 && j + 1 == LT_NKT / KP) LT_TRACE(1, t, 8)
         }
       }
     }
   } else if (warp == 2) {
     // ================================ publisher ================================
-    // Once the 8 epilogue warps have stored their part of h_t (mbarrier: release.cta arrive / acquire.cta wait), ONE
+    // Once the storing epilogue warps have written their part of h_t (mbarrier: release.cta arrive / acquire.cta wait), ONE
     // release-increment at gpu scope publishes it: the release is cumulative over the stores observed through the barrier.
     // A separate warp, so that the epilogue warps go on to the layer-output stores and the next group instead of sitting
     // in the ~1000-cycle fence.
     uint32_t n = 0;
     for (int t = 0; t < p.T; ++t) {
-      for (int g = 0; g < p.G; ++g, ++n) {
+      for (int gl = 0; gl < n_local; ++gl, ++n) {
+        const int g = bp + gl * NB;
         mbar_wait(hst_bar((int)(n & 1u)), (n >> 1) & 1u);
         if (t + 1 < p.T && lane == 0)
-          asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.cnt + g * LT_NKT + cta / 16) : "memory");
+          asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.cnt + g * LT_NKT + (ub * UPC) / LT_KT) : "memory");
         __syncwarp();
-        if (g == 0) LT_TRACE(2, t, 6)
+        if (gl == 0) LT_TRACE(2, t, 6)
       }
     }
   } else if (warp >= 4) {
@@ -338,55 +349,63 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const LstmTcParams p) 
     // Operand row block b (16 rows) of a group = split part b % 2 (0: h1, 1: h2) of items 16 (b / 2) .. + 15, and K tile i of a
     // stage sits in MMA rows i R .. (accumulator row m = TMEM lane m). A lane quadrant therefore holds, for one K part and 16
     // items, the h1 rows in lanes 0-15 and the h2 rows in lanes 16-31 (one shuffle adds them); the KP quadrants of the same
-    // items add their K parts through shared memory. Warp w reads quadrant w % 4 (hardware rule); warps 4-7 take units 0-1
-    // (columns 0-7 of the main and correction blocks), warps 8-11 units 2-3. In the end lane r of a storing warp finishes
-    // unit 2 half of its item r and lane 16 + r unit 2 half + 1.
+    // items add their K parts through shared memory. Warp w reads quadrant w % 4 (hardware rule); warps 4-7 take the first
+    // UW units of the CTA, warps 8-11 the other UW. In the end lane r of a storing warp finishes its first PP units of
+    // item r and lane 16 + r the other PP.
     const int quad = warp & 3;
     const int half = (warp - 4) >> 2;
     const int r = lane & 15;
-    const int u = 2 * half + (lane >> 4);
-    const int unit = cta * LT_UNITS + u;
+    const int lg = lane >> 4;
     const int kpart = quad / QPG;                 // which K tile of a stage this quadrant's rows belong to
     const int iq = quad % QPG;                    // 16-item block of the group
     const bool storing = kpart == 0;              // this warp finishes items; the others hand their K part over
     const int il = iq * 16 + r;                   // item within the group
     const int team = half * QPG + iq;             // the KP warps that share (units, items)
-    const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(32 * kpart + 8 * half);
+    const int u0 = half * UW + lg * PP;           // this lane's first unit within the CTA
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(2 * NCOL * kpart + CW * half);
     uint32_t n = 0;
     for (int t = 0; t < p.T; ++t) {
-      __half* hn = p.hg + (long long)((t + 1) & 1) * rows_per_buf * LT_H;
-      for (int g = 0; g < p.G; ++g, ++n) {
+      uint8_t* hn = reinterpret_cast<uint8_t*>(p.hg) + (long long)((t + 1) & 1) * buf_bytes;
+      for (int gl = 0; gl < n_local; ++gl, ++n) {
+        const int g = bp + gl * NB;
         const int acc = (int)(n & 1u);
         const int item = g * IG + il;
         const bool valid = storing && item < p.B;
         // pre-gates / skip input of this step: independent of the recurrence, in flight while we wait for the MMAs
-        float pg[4] = {0.f, 0.f, 0.f, 0.f}, skipv = 0.f;
-        if (valid) {
-          const float* pr = p.pre + (long long)item * p.pre_stride + (long long)t * (4 * LT_H) + unit;
+        float pg[PP][4], skipv[PP];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) pg[k] = __ldg(pr + k * LT_H);
-          if (p.skip) skipv = __ldg(p.skip + (long long)item * p.skip_stride + (long long)t * LT_H + unit);
+        for (int e = 0; e < PP; ++e) {
+          skipv[e] = 0.f;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) pg[e][k] = 0.f;
+          if (valid) {
+            const int unit = ub * UPC + u0 + e;
+            const float* pr = p.pre + (long long)item * p.pre_stride + (long long)t * (4 * LT_H) + unit;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) pg[e][k] = __ldg(pr + k * LT_H);
+            if (p.skip) skipv[e] = __ldg(p.skip + (long long)item * p.skip_stride + (long long)t * LT_H + unit);
+          }
         }
-        if (g == 0 && warp == 4) LT_TRACE(2, t, 0)
+        if (gl == 0 && warp == 4) LT_TRACE(2, t, 0)
         mbar_wait(accf_bar(acc), (n >> 1) & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (g == 0 && warp == 4) LT_TRACE(2, t, 1)
-        float mm[NACC][8], cc[NACC][8];
+        if (gl == 0 && warp == 4) LT_TRACE(2, t, 1)
+        float mm[NACC][CW], cc[NACC][CW];
         const uint32_t a0 = lane_base + (uint32_t)(acc * ACC_COLS);
 #pragma unroll
         for (int a = 0; a < NACC; ++a) {
-          tmem_ld8(a0 + 32 * KP * a, mm[a]);             // columns [0,16) of this K part (h1 rows: h1 w1, h2 rows: h2 w1)
-          tmem_ld8(a0 + 32 * KP * a + LT_NCOL, cc[a]);   // columns [16,32) (h1 rows: h1 w2)
+          tmem_ldw<CW>(a0 + NMMA * a, mm[a]);          // main columns of this K part (h1 rows: h1 w1, h2 rows: h2 w1)
+          tmem_ldw<CW>(a0 + NMMA * a + NCOL, cc[a]);   // correction columns (h1 rows: h1 w2)
         }
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(acce_bar(acc));
-        if (g == 0 && warp == 4) LT_TRACE(2, t, 2)
+        if (gl == 0 && warp == 4) LT_TRACE(2, t, 2)
         // h1 rows (lanes 0-15): main + corr / 2^11 with corr = h1 w2; h2 rows (lanes 16-31): their "main" columns are h2 w1
-        float part[8];
+        float part[CW];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
+        for (int k = 0; k < CW; ++k) {
           float m = mm[0][k], c = cc[0][k];
           if (NACC == 2) {
             m += mm[NACC - 1][k];
@@ -395,64 +414,82 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const LstmTcParams p) 
           part[k] = lane < 16 ? m + c * (1.f / LT_LO_SCALE) : m * (1.f / LT_LO_SCALE);
         }
 #pragma unroll
-        for (int k = 0; k < 8; ++k) part[k] += __shfl_xor_sync(0xffffffffu, part[k], 16);
+        for (int k = 0; k < CW; ++k) part[k] += __shfl_xor_sync(0xffffffffu, part[k], 16);
         if (KP > 1) {   // add the K parts of the other quadrants (same units, same items)
+          float* x = xs + (team * 16 + r) * CW;
           if (!storing && lane < 16) {
-            float* x = xs + ((team * (KP - 1) + (kpart - 1)) * 16 + r) * 8;
-            *reinterpret_cast<float4*>(x) = make_float4(part[0], part[1], part[2], part[3]);
-            *reinterpret_cast<float4*>(x + 4) = make_float4(part[4], part[5], part[6], part[7]);
+#pragma unroll
+            for (int k = 0; k < CW; k += 4) *reinterpret_cast<float4*>(x + k) = make_float4(part[k], part[k + 1], part[k + 2], part[k + 3]);
           }
           asm volatile("bar.sync %0, %1;" ::"r"(2 + team), "r"(32 * KP) : "memory");   // the team's K parts are in shared memory
           if (storing) {
 #pragma unroll
-            for (int o = 0; o < KP - 1; ++o) {
-              const float* x = xs + ((team * (KP - 1) + o) * 16 + r) * 8;
-              const float4 x0 = *reinterpret_cast<const float4*>(x), x1 = *reinterpret_cast<const float4*>(x + 4);
-              part[0] += x0.x; part[1] += x0.y; part[2] += x0.z; part[3] += x0.w;
-              part[4] += x1.x; part[5] += x1.y; part[6] += x1.z; part[7] += x1.w;
+            for (int k = 0; k < CW; k += 4) {
+              const float4 xv = *reinterpret_cast<const float4*>(x + k);
+              part[k] += xv.x; part[k + 1] += xv.y; part[k + 2] += xv.z; part[k + 3] += xv.w;
             }
           }
-          asm volatile("bar.sync %0, %1;" ::"r"(2 + team), "r"(32 * KP) : "memory");   // ... and read: the slots may be rewritten
+          asm volatile("bar.sync %0, %1;" ::"r"(2 + team), "r"(32 * KP) : "memory");   // ... and read: the slot may be rewritten
           if (!storing) continue;
         }
-        float rec[4];
+        if (gl == 0 && warp == 4) LT_TRACE(2, t, 4)
+        unsigned int own[PP];
+        float h_new[PP];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) rec[k] = lane < 16 ? part[k] : part[4 + k];
-        if (g == 0 && warp == 4) LT_TRACE(2, t, 4)
-        // gates i, f, o = sigmoid, g = tanh = 2 sigmoid(2 x) - 1: four sigmoids on two packed pairs
-        float s_if[2] = {pg[0] + rec[0], pg[1] + rec[1]};
-        float s_go[2] = {2.f * (pg[2] + rec[2]), pg[3] + rec[3]};
-        sigmoid_pair(s_if);
-        sigmoid_pair(s_go);
-        float* cptr = cs + (g * IG + il) * LT_UNITS + u;
-        const float c_new = s_if[1] * (*cptr) + s_if[0] * (2.f * s_go[0] - 1.f);
-        *cptr = c_new;
-        float s_c[2] = {2.f * c_new, 0.f};
-        sigmoid_pair(s_c);
-        const float h_new = s_go[1] * (2.f * s_c[0] - 1.f);
-        if (g == 0 && warp == 4) LT_TRACE(2, t, 5)
-        const __half q1 = __float2half_rn(h_new);
-        const __half q2 = __float2half_rn((h_new - __half2float(q1)) * LT_LO_SCALE);
-        const unsigned int own = (unsigned int)__half_as_ushort(q1) | ((unsigned int)__half_as_ushort(q2) << 16);
-        const unsigned int oth = __shfl_down_sync(0xffffffffu, own, 16);
-        if (lane < 16 && t + 1 < p.T) {   // units (2 half, 2 half + 1) of this item: one 4-byte store per split part
-          // shared-memory image of K tile cta / 16: row (g, iq, r), 16-byte chunk ((4 cta + 2 half) % 64) / 8 swizzled by r & 7
-          const int kk = (cta * LT_UNITS + 2 * half) % LT_KT;
-          const long long row = ((long long)g * LT_NKT + cta / 16) * ROWS + iq * 32 + r;
-          uint8_t* dst = reinterpret_cast<uint8_t*>(hn) + row * 128 + (((kk >> 3) ^ (r & 7)) << 4) + (kk & 7) * 2;
-          const unsigned int v1 = (own & 0xffffu) | (oth << 16);
-          const unsigned int v2 = (own >> 16) | (oth & 0xffff0000u);
-          asm volatile("st.global.cg.b32 [%0], %1;" ::"l"(dst), "r"(v1) : "memory");                // h1 row
-          asm volatile("st.global.cg.b32 [%0], %1;" ::"l"(dst + 16 * 128), "r"(v2) : "memory");     // h2 row (same r & 7)
+        for (int e = 0; e < PP; ++e) {
+          float rec[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {   // columns of unit lg PP + e of this warp (compile-time indices: both candidates, then select)
+            const float lo = part[e * 4 + k], hi = part[(PP + e) * 4 + k];
+            rec[k] = lane < 16 ? lo : hi;
+          }
+          // gates i, f, o = sigmoid, g = tanh = 2 sigmoid(2 x) - 1: four sigmoids on two packed pairs
+          float s_if[2] = {pg[e][0] + rec[0], pg[e][1] + rec[1]};
+          float s_go[2] = {2.f * (pg[e][2] + rec[2]), pg[e][3] + rec[3]};
+          sigmoid_pair(s_if);
+          sigmoid_pair(s_go);
+          float* cptr = cs + (gl * IG + il) * UPC + u0 + e;
+          const float c_new = s_if[1] * (*cptr) + s_if[0] * (2.f * s_go[0] - 1.f);
+          *cptr = c_new;
+          float s_c[2] = {2.f * c_new, 0.f};
+          sigmoid_pair(s_c);
+          h_new[e] = s_go[1] * (2.f * s_c[0] - 1.f);
+          const __half q1 = __float2half_rn(h_new[e]);
+          const __half q2 = __float2half_rn((h_new[e] - __half2float(q1)) * LT_LO_SCALE);
+          own[e] = (unsigned int)__half_as_ushort(q1) | ((unsigned int)__half_as_ushort(q2) << 16);
+        }
+        if (gl == 0 && warp == 4) LT_TRACE(2, t, 5)
+        unsigned int oth[PP];
+#pragma unroll
+        for (int e = 0; e < PP; ++e) oth[e] = __shfl_down_sync(0xffffffffu, own[e], 16);
+        if (lane < 16 && t + 1 < p.T) {   // the UW units of this item: one store per split part
+          // shared-memory image of K tile (UPC ub) / 64: row (g, iq, r), 16-byte chunk (unit % 64) / 8 swizzled by r & 7
+          const int kk = (ub * UPC + half * UW) % LT_KT;
+          const long long row = ((long long)g * LT_NKT + (ub * UPC) / LT_KT) * ROWS + iq * 32 + r;
+          uint8_t* dst = hn + row * 128 + (((kk >> 3) ^ (r & 7)) << 4) + (kk & 7) * 2;
+          if (PP == 1) {
+            const unsigned int v1 = (own[0] & 0xffffu) | (oth[0] << 16);
+            const unsigned int v2 = (own[0] >> 16) | (oth[0] & 0xffff0000u);
+            asm volatile("st.global.cg.b32 [%0], %1;" ::"l"(dst), "r"(v1) : "memory");                // h1 row
+            asm volatile("st.global.cg.b32 [%0], %1;" ::"l"(dst + 16 * 128), "r"(v2) : "memory");     // h2 row (same r & 7)
+          } else {
+            const unsigned int a1 = (own[0] & 0xffffu) | (own[PP - 1] << 16), b1 = (oth[0] & 0xffffu) | (oth[PP - 1] << 16);
+            const unsigned int a2 = (own[0] >> 16) | (own[PP - 1] & 0xffff0000u), b2 = (oth[0] >> 16) | (oth[PP - 1] & 0xffff0000u);
+            asm volatile("st.global.cg.v2.b32 [%0], {%1, %2};" ::"l"(dst), "r"(a1), "r"(b1) : "memory");
+            asm volatile("st.global.cg.v2.b32 [%0], {%1, %2};" ::"l"(dst + 16 * 128), "r"(a2), "r"(b2) : "memory");
+          }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(hst_bar(acc));   // -> publisher warp
-        if (g == 0 && warp == 4) LT_TRACE(2, t, 3)
+        if (gl == 0 && warp == 4) LT_TRACE(2, t, 3)
         // the layer output is nobody's business inside this kernel: stored after h_t is on its way
         if (valid) {
-          float y = h_new + skipv;
-          if (p.out_elu) y = elu1(y);
-          p.out[(long long)item * p.out_stride + (long long)t * LT_H + unit] = y;
+#pragma unroll
+          for (int e = 0; e < PP; ++e) {
+            float y = h_new[e] + skipv[e];
+            if (p.out_elu) y = elu1(y);
+            p.out[(long long)item * p.out_stride + (long long)t * LT_H + ub * UPC + u0 + e] = y;
+          }
         }
       }
     }
@@ -466,13 +503,14 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const LstmTcParams p) 
   }
 }
 
-// W_hh [4H][H] (reference layout) -> fp16 split slices [128 CTAs][w1: 16 rows | w2: 16 rows][512], row n = unit * 4 + gate
-__global__ void lstm_tc_pack_kernel(const float* __restrict__ whh, __half* __restrict__ wp) {
-  const int row = blockIdx.x;                 // 0 .. 128 * 32 - 1
-  const int cta = row / (2 * LT_NCOL);
-  const int part = (row % (2 * LT_NCOL)) / LT_NCOL;
-  const int n = row % LT_NCOL;
-  const int src = (n % 4) * LT_H + cta * LT_UNITS + n / 4;
+// W_hh [4H][H] (reference layout) -> fp16 split slices [unit blocks][w1: 4 upc rows | w2: 4 upc rows][512], row n = unit * 4 + gate
+__global__ void lstm_tc_pack_kernel(const float* __restrict__ whh, __half* __restrict__ wp, int upc) {
+  const int ncol = 4 * upc;
+  const int row = blockIdx.x;                 // 0 .. 2 * 4H - 1
+  const int ub = row / (2 * ncol);
+  const int part = (row % (2 * ncol)) / ncol;
+  const int n = row % ncol;
+  const int src = (n % 4) * LT_H + ub * upc + n / 4;
   for (int k = threadIdx.x; k < LT_H; k += blockDim.x) {
     const float w = whh[(long long)src * LT_H + k];
     const __half w1 = __float2half_rn(w);
@@ -480,34 +518,29 @@ __global__ void lstm_tc_pack_kernel(const float* __restrict__ whh, __half* __res
   }
 }
 
-size_t lt_smem_bytes(int G, int ig) {
-  return 1024 + LT_STAGES * LT_STAGE_BYTES + LT_NKT * LT_W_TILE + (size_t)G * ig * LT_UNITS * 4 + 8 * (2 * LT_STAGES + 7) + 16 +
-         8 * 16 * 8 * 4;
+size_t lt_smem_bytes(int G, int ig, int upc) {
+  const int nb = upc == 8 ? 2 : 1;
+  return 1024 + LT_STAGES * LT_STAGE_BYTES + LT_NKT * (2 * 4 * upc * 128) + (size_t)((G + nb - 1) / nb) * ig * upc * 4 + 4 * 16 * (2 * upc) * 4 +
+         8 * (2 * LT_STAGES + 7) + 16;
 }
 
 }  // namespace
 
+// packed: 2 x [8H][H] halves: the UPC = 4 slices followed by the UPC = 8 slices
 int launch_lstm_tc_pack(const float* whh, void* packed, int H, cudaStream_t s) {
   ECB_REQUIRE(H == LT_H, "lstm_tc: hidden size %d unsupported", H);
-  lstm_tc_pack_kernel<<<LT_CTAS * 2 * LT_NCOL, 128, 0, s>>>(whh, reinterpret_cast<__half*>(packed));
+  __half* wp = reinterpret_cast<__half*>(packed);
+  lstm_tc_pack_kernel<<<8 * LT_H, 128, 0, s>>>(whh, wp, 4);
+  lstm_tc_pack_kernel<<<8 * LT_H, 128, 0, s>>>(whh, wp + 8LL * LT_H * LT_H, 8);
   ECB_LAUNCHED();
   return 0;
 }
 
 long long* g_lstm_tc_trace = nullptr;   // diagnostic (ecb_debug_lstm_trace): device buffer of 3 * 8 * 16 stamps
 
-bool lstm_tc_supported(int batch, int H) { return H == LT_H && batch >= 1 && batch <= LT_MAX_GROUPS * LT_ITEMS; }
+bool lstm_tc_supported(int batch, int H) { return H == LT_H && batch >= 1 && batch <= LT_MAX_GROUPS * 64; }
 
-// group size: batches of up to 64 items run as (up to) two groups of 32, larger ones as groups of 64
-static int lt_group_items(int batch) {
-  if (const char* e = getenv("ECB_LSTM_GROUP")) {   // diagnostic override
-    const int v = atoi(e);
-    if (v == 16 || v == 32 || v == 64) return v;
-  }
-  return batch <= 64 ? 32 : 64;
-}
-
-// floats of workspace: exchange buffers ([2][G * 2 IG][512] fp16) + counters; bounded by the IG = 32 split of 64 items
+// floats of workspace: exchange buffers ([2][G][8][2 IG][64] fp16) + counters
 int lstm_tc_workspace_floats(int batch) {
   const int G = 2 * ((batch + 63) / 64);
   return G * 32 * LT_H * 2 + G * LT_NKT + 64;
@@ -516,12 +549,26 @@ int lstm_tc_workspace_floats(int batch) {
 int launch_lstm_tc(const float* pre, long long pre_item_stride, const void* w_packed, const float* skip, long long skip_item_stride,
                    float* out, long long out_item_stride, int batch, int T, int out_elu, float* workspace, cudaStream_t s) {
   ECB_REQUIRE(lstm_tc_supported(batch, LT_H) && T > 0, "lstm_tc: bad batch %d / T %d", batch, T);
-  int ig = lt_group_items(batch);
+  // group size: batches of up to 64 items run as groups of 32, larger ones as groups of 64; units per CTA: 8 (64 unit
+  // blocks x 2 batch parts) from 192 items -- measured (us per layer step, UPC 4 / 8): 64 items 4.5 / 5.1, 128: 6.8 / 7.7,
+  // 256: 12.5 / 11.2, 512: 24.8 / 20.2, 960: 46.3 / 39.3 (the wider MMA and the doubled cell work per lane are not free)
+  int ig = batch <= 64 ? 32 : 64;
+  int upc = batch < 192 ? 4 : 8;
+  if (const char* e = getenv("ECB_LSTM_GROUP")) {   // diagnostic overrides
+    const int v = atoi(e);
+    if (v == 32 || v == 64) ig = v;
+  }
+  if (const char* e = getenv("ECB_LSTM_UPC")) {
+    const int v = atoi(e);
+    if (v == 4 || v == 8) upc = v;
+  }
   if ((batch + ig - 1) / ig > LT_MAX_GROUPS) ig = 64;
   const int G = (batch + ig - 1) / ig;
   const int rows = 2 * ig;
-  const size_t smem = lt_smem_bytes(G, ig);
-  int cl = G >= 4 ? 4 : 1;   // cluster size: CTAs that share their h tiles through TMA multicast (pays once L2 -> SM traffic matters)
+  const int nb = upc == 8 ? 2 : 1;
+  const size_t smem = lt_smem_bytes(G, ig, upc);
+  ECB_REQUIRE(smem <= 227 * 1024, "lstm_tc: %zu bytes of shared memory for %d groups", smem, G);
+  int cl = (G + nb - 1) / nb >= 4 ? 4 : 1;   // cluster size: CTAs that share their h tiles through multicast (pays once L2 -> SM traffic matters)
   if (const char* e = getenv("ECB_LSTM_CLUSTER")) cl = atoi(e);
   ECB_REQUIRE(cl == 1 || cl == 2 || cl == 4, "lstm_tc: ECB_LSTM_CLUSTER=%d (1, 2 or 4)", cl);
   LstmTcParams p;
@@ -539,31 +586,31 @@ int launch_lstm_tc(const float* pre, long long pre_item_stride, const void* w_pa
   p.G = G;
   p.out_elu = out_elu;
   p.trace = g_lstm_tc_trace;
-
   // h_{-1} = 0 (both buffers: padding rows of the last group stay finite) and the arrival counters
   ECB_CUDA(cudaMemsetAsync(workspace, 0, sizeof(__half) * hbuf + sizeof(unsigned int) * (size_t)(G * LT_NKT), s));
   CUtensorMap map_w;
   {
-    const cuuint64_t dims[2] = {(cuuint64_t)LT_H, (cuuint64_t)(LT_CTAS * 2 * LT_NCOL)};
+    const cuuint64_t dims[2] = {(cuuint64_t)LT_H, (cuuint64_t)(8 * LT_H)};
     const cuuint64_t strides[1] = {(cuuint64_t)LT_H * 2};
-    const cuuint32_t box[2] = {LT_KT, 2 * LT_NCOL};
-    if (make_tensor_map_f16(&map_w, w_packed, 2, dims, strides, box)) return 1;
+    const cuuint32_t box[2] = {LT_KT, (cuuint32_t)(2 * 4 * upc)};
+    const __half* wp = reinterpret_cast<const __half*>(w_packed) + (upc == 8 ? 8LL * LT_H * LT_H : 0LL);
+    if (make_tensor_map_f16(&map_w, wp, 2, dims, strides, box)) return 1;
   }
   const double bt = (double)batch * T;
   ProfScope prof(PROF_LSTM_REC, s, 2.0 * bt * 4 * LT_H * LT_H, 4.0 * (bt * 4 * LT_H + bt * LT_H * (skip ? 2 : 1) + 4.0 * LT_H * LT_H));
   // all 128 CTAs spin on each other's arrivals: they must be co-resident (cooperative launch), in clusters of `cl`. Where a
   // clustered cooperative launch is refused (seen under ncu), the same kernel runs unclustered.
   void* args[] = {(void*)&map_w, (void*)&p};
-  const void* fns[3][3] = {{(const void*)lstm_tc_kernel<1, 16>, (const void*)lstm_tc_kernel<1, 32>, (const void*)lstm_tc_kernel<1, 64>},
-                           {(const void*)lstm_tc_kernel<2, 16>, (const void*)lstm_tc_kernel<2, 32>, (const void*)lstm_tc_kernel<2, 64>},
-                           {(const void*)lstm_tc_kernel<4, 16>, (const void*)lstm_tc_kernel<4, 32>, (const void*)lstm_tc_kernel<4, 64>}};
-  static DeviceOnce attr_set[3][3];
+#define LT_FN(CL_, IG_) {(const void*)lstm_tc_kernel<CL_, IG_, 4>, (const void*)lstm_tc_kernel<CL_, IG_, 8>}
+  const void* fns[3][2][2] = {{LT_FN(1, 32), LT_FN(1, 64)}, {LT_FN(2, 32), LT_FN(2, 64)}, {LT_FN(4, 32), LT_FN(4, 64)}};
+#undef LT_FN
+  static DeviceOnce attr_set[3][2][2];
   for (;;) {
-    const int ci = cl == 4 ? 2 : cl == 2 ? 1 : 0, gi = ig == 64 ? 2 : ig == 32 ? 1 : 0;
-    const void* fn = fns[ci][gi];
-    DeviceOnce& once = attr_set[ci][gi];
+    const int ci = cl == 4 ? 2 : cl == 2 ? 1 : 0, gi = ig == 64 ? 1 : 0, ui = upc == 8 ? 1 : 0;
+    const void* fn = fns[ci][gi][ui];
+    DeviceOnce& once = attr_set[ci][gi][ui];
     if (!once.done()) {
-      ECB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lt_smem_bytes(LT_MAX_GROUPS, 64)));
+      ECB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       once.mark();
     }
     cudaLaunchConfig_t cfg = {};

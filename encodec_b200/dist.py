@@ -197,3 +197,74 @@ def forward_shard(model, x_local: torch.Tensor, counts: tp.Sequence[int], dst: i
     codes_all = torch.cat([t for k in range(world) for t in per_rank_codes[k]], dim=0)
     audio_all = torch.cat([t for k in range(world) for t in per_rank_audio[k]], dim=0)
     return audio_all, codes_all
+
+
+def segment_shards(n_clips: int, n_seg: int, world: int) -> tp.List[tp.List[tp.Tuple[int, int, int]]]:
+    """Contiguous split of the flattened (clip, segment) list over ``world`` ranks: for every rank a list of
+    ``(clip, first segment, end segment)`` pieces (when there are fewer clips than GPUs the segments
+    of a clip, which are independent, are what gets sharded)."""
+    out = []
+    for r in range(world):
+        lo, hi = shard_range(n_clips * n_seg, r, world)
+        pieces = []
+        while lo < hi:
+            clip, s0 = divmod(lo, n_seg)
+            s1 = min(n_seg, s0 + (hi - lo))
+            pieces.append((clip, s0, s1))
+            lo += s1 - s0
+        out.append(pieces)
+    return out
+
+
+def encode_decode_pieces(model, x: torch.Tensor, pieces: tp.Sequence[tp.Tuple[int, int, int]]):
+    """This rank's part of ``forward_sharded_segments``: for every ``(clip, s0, s1)`` piece the codes of its segments
+    (``[n, K, T_f max]`` int64, zero-padded) and their decoded audio (``[n, C, segment_length]``, zero-padded)."""
+    c = x.shape[1]
+    hop, seg_len, n_q = model.encoder.hop_length, model.segment_length, model._n_q()
+    tf_max = -(-seg_len // hop)
+    dev = x.device
+    codes_parts, audio_parts = [], []
+    for clip, s0, s1 in pieces:
+        frames = model.encode_segments(x[clip:clip + 1], s0, s1)
+        seg_audio, _ = model.decode_segments(frames)                        # [1, n, C, seg_len]
+        cp = torch.zeros((s1 - s0, n_q, tf_max), dtype=torch.int64, device=dev)
+        for k, f in enumerate(frames):
+            cp[k, :, :f["codes"].shape[-1]] = f["codes"][0]
+        codes_parts.append(cp)
+        audio_parts.append(seg_audio[0])
+    if codes_parts:
+        return torch.cat(codes_parts, dim=0), torch.cat(audio_parts, dim=0)
+    return (torch.zeros((0, n_q, tf_max), dtype=torch.int64, device=dev),
+            torch.zeros((0, c, seg_len), dtype=torch.float32, device=dev))
+
+
+def assemble_segments(model, codes_all: torch.Tensor, audio_all: torch.Tensor, b: int, c: int, length: int):
+    """The destination rank's part: ``codes_all [B * n_seg, K, T_f max]`` / ``audio_all [B * n_seg, C, segment_length]`` in
+    (clip, segment) order -> ``(audio [B, C, T], codes [B, K, sum T_f])`` with the reference's linear overlap-add."""
+    segs, _ = model._segments(length)
+    n_seg, hop, seg_len = len(segs), model.encoder.hop_length, model.segment_length
+    lens = [n for _, n in segs]
+    t_f = [-(-n // hop) for n in lens]
+    codes_all = codes_all.view(b, n_seg, codes_all.shape[1], codes_all.shape[2])
+    codes = torch.cat([codes_all[:, s, :, :t_f[s]] for s in range(n_seg)], dim=-1)
+    audio = model._overlap_add(audio_all.view(b, n_seg, c, seg_len), lens)
+    return audio[:, :, :length], codes
+
+
+def forward_sharded_segments(model, x: torch.Tensor, dst: int = 0):
+    """``model.forward`` of a SEGMENTED model (48 kHz: 1 s segments, 1 % overlap) with the (clip, segment) list sharded over
+    the ranks -- the partition for fewer clips than GPUs. Every rank encodes and decodes its segments
+    (``encode_segments`` / ``decode_segments``), codes and decoded segments are gathered on ``dst`` (one collective), and the
+    linear overlap-add (reference utils.py:17-56) runs there over the complete segment list of every clip. Returns
+    ``(audio [B, C, T], codes [B, K, sum T_f])`` on ``dst`` -- bit-identical to ``model(x)`` -- and ``(None, None)`` elsewhere."""
+    rank, world = _world()
+    assert model.segment_length is not None, "forward_sharded_segments needs a segmented model"
+    b, c, length = x.shape
+    n_seg = len(model._segments(length)[0])
+    shards = segment_shards(b, n_seg, world)
+    counts = [sum(s1 - s0 for _, s0, s1 in pieces) for pieces in shards]
+    codes_r, audio_r = encode_decode_pieces(model, x, shards[rank])
+    codes_all, audio_all = gather_results(codes_r, audio_r, dst, counts, getattr(model.quantizer, "bins", None))
+    if rank != dst:
+        return None, None
+    return assemble_segments(model, codes_all, audio_all, b, c, length)

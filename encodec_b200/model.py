@@ -137,14 +137,19 @@ class EncodecModel(nn.Module):
 
     # ---- encode --------------------------------------------------------------------------------
     @torch.no_grad()
-    def _encode_batched(self, x: torch.Tensor):
-        """All segments of all batch items. Returns per segment-length group the batched results."""
+    def _encode_batched(self, x: torch.Tensor, seg_range: tp.Optional[tp.Tuple[int, int]] = None):
+        """All segments of all batch items (or segments ``seg_range = (s0, s1)`` of every item: the segments of the 48 kHz
+        model are independent, reference model.py:157-170, which is what multi-GPU partitioning by segment relies on).
+        Returns per segment-length group the batched results."""
         nat.require_cuda(x, "EncodecModel input")
         assert x.dim() == 3
         batch, channels, length = x.shape
         assert channels > 0 and channels <= 2
         x = x.contiguous()
         segs, stride = self._segments(length)
+        if seg_range is not None:
+            assert self.segment is not None and 0 <= seg_range[0] < seg_range[1] <= len(segs), (seg_range, len(segs))
+            segs = segs[seg_range[0]:seg_range[1]]
         n_q = self._n_q()
         hop = self.encoder.hop_length
         dim = self.encoder.dimension
@@ -184,7 +189,13 @@ class EncodecModel(nn.Module):
                                    quantized=quant, quantized_frames=qf, scale=scale, batch=batch))
         return out_groups, n_q
 
-    def encode(self, x: torch.Tensor) -> tp.List[EncodedFrame]:
+    def encode_segments(self, x: torch.Tensor, s0: int, s1: int) -> tp.List[EncodedFrame]:
+        """``encode`` restricted to segments ``s0 .. s1 - 1`` of every clip (segmented models). ``decode_segments`` turns the
+        frames into per-segment audio; the overlap-add happens wherever all segments of a clip meet
+        (``encodec_b200.dist.forward_sharded_segments``)."""
+        return self.encode(x, _seg_range=(s0, s1))
+
+    def encode(self, x: torch.Tensor, _seg_range: tp.Optional[tp.Tuple[int, int]] = None) -> tp.List[EncodedFrame]:
         """Same contract as reference model.py:146-210: one dict per segment with keys
         ``quantized [B,D,T_f]``, ``codes [B,K,T_f]``, ``soft_targets``, ``commit_loss [K,1]``,
         ``codebook_loss`` (the same tensor object) and ``scale [B,1]`` (or None).
@@ -195,7 +206,7 @@ class EncodecModel(nn.Module):
             EncodecModel._warned_training = True
             warnings.warn("encodec_b200.EncodecModel is inference-only: it always runs the reference's eval() forward (zero commit "
                           "loss, frozen codebooks, no gradients), also in train mode with autograd enabled", RuntimeWarning, stacklevel=2)
-        groups, n_q = self._encode_batched(x)
+        groups, n_q = self._encode_batched(x, _seg_range)
         batched = _Batched()
         batched.groups = groups
         frames: tp.List[EncodedFrame] = []
@@ -239,6 +250,21 @@ class EncodecModel(nn.Module):
         segment_length = self.segment_length
         if segment_length is None:
             assert len(encoded_frames) == 1
+        outs = self._decode_groups(encoded_frames)
+        if segment_length is None:
+            return outs[0][1]
+        frames, lens = self._stack_segments(outs)
+        return self._overlap_add(frames, lens)
+
+    @torch.no_grad()
+    def decode_segments(self, encoded_frames: tp.List[EncodedFrame]) -> tp.Tuple[torch.Tensor, tp.List[int]]:
+        """Decoded segments WITHOUT the overlap-add: ``(frames [B, n, C, segment_length] zero-padded, lengths)``."""
+        assert self.segment_length is not None
+        return self._stack_segments(self._decode_groups(encoded_frames), self.segment_length)
+
+    @torch.no_grad()
+    def _decode_groups(self, encoded_frames: tp.List[EncodedFrame]):
+        segment_length = self.segment_length
         # fast path: frames straight from our own encode() -> reuse the batched frames-major tensors
         # (the fork decodes frame['quantized'], delta D3, so editing or replacing the latents between encode and decode is
         # a supported use: the cached tensors are only used while the dict still holds the very tensors encode() put
@@ -286,20 +312,20 @@ class EncodecModel(nn.Module):
                 sc = g["scale"][sl] if g["scale"] is not None else None
                 self.decoder.decode_items(z, zf, (b1 - b0) * n_seg, t_f, sc, out[sl])
             outs.append((g, out))
-        if segment_length is None:
-            return outs[0][1]
-        return self._overlap_add(outs)
+        return outs
 
-    def _overlap_add(self, outs) -> torch.Tensor:
-        """utils._linear_overlap_add (reference utils.py:17-56) as one kernel."""
-        stride = self.segment_stride or 1
+    def _stack_segments(self, outs, seg_len: tp.Optional[int] = None) -> tp.Tuple[torch.Tensor, tp.List[int]]:
+        """Per segment-length group outputs -> one [B, n_seg, C, seg_len] tensor (short segments zero-padded) + lengths.
+        ``seg_len`` defaults to the first frame's length, which is what the reference's overlap-add builds its window
+        from (utils.py:40-44)."""
         g0, o0 = outs[0]
         b = g0["batch"]
-        seg_len = o0.shape[-1]
+        if seg_len is None:
+            seg_len = o0.shape[-1]
         n_seg_total = sum(g["n_seg"] for g, _ in outs)
         dev = o0.device
-        if len(outs) == 1:
-            frames = o0  # [B * n_seg, C, seg_len] == [B, n_seg, C, seg_len]
+        if len(outs) == 1 and o0.shape[-1] == seg_len:
+            frames = o0.view(b, n_seg_total, self.channels, seg_len)  # [B * n_seg, C, seg_len] == [B, n_seg, C, seg_len]
             lens = [seg_len] * n_seg_total
         else:
             frames = torch.zeros((b, n_seg_total, self.channels, seg_len), dtype=torch.float32, device=dev)
@@ -310,9 +336,17 @@ class EncodecModel(nn.Module):
                 frames[:, pos:pos + g["n_seg"], :, :n] = o.view(b, g["n_seg"], self.channels, n)
                 lens += [n] * g["n_seg"]
                 pos += g["n_seg"]
+        return frames, lens
+
+    def _overlap_add(self, frames: torch.Tensor, lens: tp.Sequence[int]) -> torch.Tensor:
+        """utils._linear_overlap_add (reference utils.py:17-56) as one kernel over ``frames [B, n_seg, C, segment_length]``."""
+        stride = self.segment_stride or 1
+        b, n_seg_total, _, seg_len = frames.shape
+        dev = frames.device
         total = stride * (n_seg_total - 1) + lens[-1]
-        seg_lens = torch.tensor(lens, dtype=torch.int32, device=dev)
+        seg_lens = torch.tensor(list(lens), dtype=torch.int32, device=dev)
         out = torch.empty((b, self.channels, total), dtype=torch.float32, device=dev)
+        frames = frames.contiguous()
         with torch.cuda.device(dev):
             nat.check(nat.lib.ecb_overlap_add(nat.ptr(frames), nat.ptr(seg_lens), b, self.channels, n_seg_total, seg_len,
                                               stride, nat.ptr(out), total, nat.stream_ptr(dev)))

@@ -292,18 +292,19 @@ class SEANetDecoder(_NativeStack):
         self.model = nn.ModuleDict(model)
         self._init_native()
 
-    #: Operand scheme of the decoder's tensor-core convs (weight-norm models; GroupNorm / LayerNorm models always run the
-    #: fp32-accurate form). ``None`` (default) = ``True``: ONE TF32 pass -- nothing downstream of the decoder is discrete, the
-    #: decoded audio stays within ~1e-4 max-abs / 2.5e-5 RMS of the reference (bar 1e-3 / 1e-4; tests on the golden cases
-    #: and on real speech at three loudness levels), decoder convs ~1.6x faster. ``False``: split operands (3xTF32,
-    #: fp32-accurate), as the encoder and the quantiser always use.
+    #: Operand scheme of the decoder's tensor-core convs. ``None`` (default) = automatic: weight-norm models run ONE TF32
+    #: pass -- nothing downstream of the decoder is discrete, the decoded audio stays within ~1e-4 max-abs / 2.5e-5 RMS of
+    #: the reference (bar 1e-3 / 1e-4; tests on the golden cases and on real speech at three loudness levels), decoder convs
+    #: ~1.6x faster -- while GroupNorm (48 kHz) and LayerNorm models keep split operands (their O(1) output puts TF32's
+    #: ~3e-4 relative error outside the absolute RMS bar). ``False``: split operands (3xTF32, fp32-accurate) everywhere, as
+    #: the encoder and the quantiser always use. ``True``: TF32 also in the >= 128-channel convs of a GroupNorm decoder.
     tf32: tp.Optional[bool] = None
 
     @torch.no_grad()
     def decode_items(self, z: tp.Optional[torch.Tensor], z_frames: tp.Optional[torch.Tensor], n_items: int,
                      n_frames: int, scale: tp.Optional[torch.Tensor], out: tp.Optional[torch.Tensor] = None):
         codec = self.native()
-        nat.check(nat.lib.ecb_codec_set_decoder_precision(codec.handle, 0 if self.tf32 is False else 1))
+        nat.check(nat.lib.ecb_codec_set_decoder_precision(codec.handle, -1 if self.tf32 is None else int(bool(self.tf32))))
         src = z if z is not None else z_frames
         dev = src.device
         if out is None:

@@ -72,12 +72,14 @@ int ecb_codec_load_tensor(ecb_codec* codec, const char* key, const float* data, 
  * Fails if a tensor the spec requires was never loaded. */
 int ecb_codec_finalize(ecb_codec* codec, void* stream);
 
-/* Decoder operand scheme of the tensor-core convolutions (weight-norm and GroupNorm models; LayerNorm models always
- * run split operands). 1 (the default of a fresh codec): one TF32 pass with operands rounded to TF32 by their producers
- * -- nothing downstream of the decoder is discrete; decoded audio within ~1e-4 max-abs / 2.5e-5 RMS of the reference on
- * the golden cases and on real speech at three loudness levels (the north_star bar is 1e-3 / 1e-4), decoder convs about
- * 1.6x faster. 0: split-operand TF32 (3 products, fp32-accurate), like the encoder. The encoder and the quantiser are
- * always fp32-accurate. The environment variable ECB_DEC_SPLIT=3 forces the accurate scheme for codecs that never call this. */
+/* Decoder operand scheme of the tensor-core convolutions. 1: one TF32 pass with operands rounded to TF32 by their
+ * producers (nothing downstream of the decoder is discrete). 0: split-operand TF32 (3 products, fp32-accurate), like the
+ * encoder. -1 (the state of a fresh codec): automatic -- weight-norm models (24 kHz) run one TF32 pass: decoded audio within
+ * ~1e-4 max-abs / 2.5e-5 RMS of the reference on the golden cases and on real speech at three loudness levels (north_star
+ * bar 1e-3 / 1e-4), decoder convs ~1.6x faster (ECB_DEC_SPLIT=3 in the environment turns this off); GroupNorm models
+ * (48 kHz, whose output is scaled back to the segment's loudness) and LayerNorm models keep split operands, because TF32's
+ * ~3e-4 relative error measured 1.3e-4 .. 1.6e-4 RMS there. With an explicit 1 a GroupNorm decoder runs its >= 128-channel
+ * convs in TF32 (+10 % throughput, outside the RMS bar). The encoder and the quantiser are always fp32-accurate. */
 int ecb_codec_set_decoder_precision(ecb_codec* codec, int32_t tf32_single_pass);
 
 /* ---- SEANetEncoder.forward (modules/seanet.py:145-146; SConv1d conv.py:202-221; SLSTM lstm.py:22-28)

@@ -640,3 +640,28 @@ def test_rvq_three_way_near_tie_is_never_a_hard_mismatch():
     print(f"[rvq 3-way ties] relative spread of the three distances: median {np.median(spread):.2e}; score {score}")
     assert np.median(spread) < 1e-5          # the construction really produces three candidates inside the re-rank window
     assert score["hard"] == 0, score
+
+
+@pytest.mark.parametrize("world", [1, 3, 8])
+def test_segment_sharded_forward_is_bit_identical(world):
+    """48 kHz model with fewer clips than GPUs: the (clip, segment) list is what gets sharded. The ranks
+    are emulated in one process -- every rank's pieces are encoded / decoded separately, concatenated the way the gather
+    delivers them and overlap-added on the destination -- and the result must equal model(x) bit for bit (2 clips, 2 full +
+    1 short segment each, per-segment scales)."""
+    from encodec_b200 import dist as ebdist
+    case = gc.load_model_case("48k_24kbps_3seg")
+    m = ug.build_model(case["spec"], case["sd"], case["bandwidth"], case["distinct"])
+    x = torch.from_numpy(case["x"]).cuda()
+    audio, codes, _, _ = m(x)
+    b, c, length = x.shape
+    n_seg = len(m._segments(length)[0])
+    shards = ebdist.segment_shards(b, n_seg, world)
+    assert sum(s1 - s0 for pieces in shards for _, s0, s1 in pieces) == b * n_seg
+    parts = [ebdist.encode_decode_pieces(m, x, pieces) for pieces in shards]
+    codes_all = torch.cat([p[0] for p in parts], dim=0)
+    audio_all = torch.cat([p[1] for p in parts], dim=0)
+    audio2, codes2 = ebdist.assemble_segments(m, codes_all, audio_all, b, c, length)
+    assert torch.equal(codes2, codes) and torch.equal(audio2, audio)
+    if world == 1:
+        a3, c3 = ebdist.forward_sharded_segments(m, x)
+        assert torch.equal(c3, codes) and torch.equal(a3, audio)
