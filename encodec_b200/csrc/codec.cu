@@ -90,6 +90,8 @@ struct LstmLayerW {
   float* r_hi = nullptr;  // recurrent weights W_hh in the same form, for the step-wise (large-batch) recurrence
   float* r_lo = nullptr;
   float* r_f16 = nullptr; // fp16 split slices of W_hh for the persistent tensor-core recurrence (lstm_tc.cu), H = 512
+  float* r_f16_16 = nullptr; // the same in slices of 16 units per CTA (large launches)
+  float* x_f16 = nullptr;    // fp16 split slices (8 units per CTA) of W_ih: the x part of the second layer in the two-layer wavefront kernel
 };
 
 }  // namespace
@@ -229,6 +231,8 @@ int prepare_lstm(ecb_codec* c, const std::string& prefix, int H, std::vector<Lst
     if (lstm_tc_supported(1, H)) {
       if (dev_alloc(c, &lw.r_f16, 8LL * H * H)) return 1;   // two packings (4 and 8 units per CTA) of 2 x [4H][H] halves each
       if (launch_lstm_tc_pack(whh, lw.r_f16, H, st)) return 1;
+      if (dev_alloc(c, &lw.r_f16_16, 4LL * H * H) || launch_lstm_tc_pack_upc(whh, lw.r_f16_16, H, 16, st)) return 1;
+      if (dev_alloc(c, &lw.x_f16, 4LL * H * H) || launch_lstm_tc_pack_upc(wih, lw.x_f16, H, 8, st)) return 1;
     }
   }
   return 0;
@@ -942,6 +946,8 @@ int lstm_steps(Ctx& x, const LstmLayerW& lw, const float* pre, long long pre_str
   return 0;
 }
 
+constexpr int LSTM_WAVE_MAX = 64;    // items per launch up to which the two-layer wavefront kernel runs
+constexpr int LSTM_U16_MIN = 256;    // items per launch from which a layer runs with 16 units per CTA
 // SLSTM (modules/lstm.py:22-28): X raw [item][T][512] -> out = ELU(lstm(X) + X). pre / h0 are plain scratch.
 int tc_lstm(Ctx& x, const std::vector<LstmLayerW>& layers, const Act& X, float* pre_buf, float* h0_buf, Act& out, int split) {
   const int H = top_width(x.c->spec), L = (int)layers.size();
@@ -961,13 +967,35 @@ int tc_lstm(Ctx& x, const std::vector<LstmLayerW>& layers, const Act& X, float* 
   const bool tcrec = mode != 1 && tc_mode && layers[0].r_f16 && lstm_tc_supported(x.n_items, H) &&
                      (tc_mode == 2 || x.n_items <= 1024);
   const bool stepwise = mode == 1 || (mode < 0 && !tcrec && x.n_items >= 320);
+  // ECB_LSTM_FORM (diagnostic): 0 = lstm_tc_kernel only, 2 = two-layer wavefront wherever it is supported, 16 = 16 units per CTA
+  // for every launch; default: wavefront up to LSTM_WAVE_MAX items, 16 units per CTA from LSTM_U16_MIN items
+  const char* form_env = getenv("ECB_LSTM_FORM");
+  const int form = form_env ? atoi(form_env) : -1;
+  const bool wave = tcrec && L == 2 && layers[1].x_f16 && lstm_tc2_supported(x.n_items, H) &&
+                    (form == 2 || (form < 0 && x.n_items <= LSTM_WAVE_MAX));
+  const bool u16 = tcrec && !wave && layers[0].r_f16_16 && (form == 16 || (form < 0 && x.n_items >= LSTM_U16_MIN));
+  if (wave) {
+    if (tc_run(x, layers[0].t_hi, layers[0].t_lo, layers[0].bias, H, 4 * H, X, H, 1, 1, 0, true, nullptr, pre.row0(), nullptr,
+               pre.stride(), X.T, 0, split, 0))
+      return 1;
+    const float* u8 = layers[0].r_f16 + 4LL * H * H;   // second packing of launch_lstm_tc_pack: 8 units per CTA
+    if (launch_lstm_tc2(pre.row0(), pre.stride(), u8, layers[1].x_f16, layers[1].r_f16 + 4LL * H * H, layers[1].bias, X.row0(), X.stride(),
+                        out.row0(), out.stride(), x.n_items, (int)X.T, 1, x.lstm_ws, x.st))
+      return 1;
+    if (out.halo > 0 && launch_halo_fill(nullptr, out.row0(), out.stride(), out.T, out.C, x.n_items, out.halo, 0, x.st)) return 1;
+    return 0;
+  }
   for (int l = 0; l < L; ++l) {
     if (tc_run(x, layers[l].t_hi, layers[l].t_lo, layers[l].bias, H, 4 * H, *cur, H, 1, 1, 0, true, nullptr, pre.row0(), nullptr,
                pre.stride(), X.T, 0, split, 0))
       return 1;
     const bool last = (l == L - 1);
     Act& dst = last ? out : h0;
-    if (tcrec) {
+    if (u16) {
+      if (launch_lstm_tc16(pre.row0(), pre.stride(), layers[l].r_f16_16, last ? X.row0() : nullptr, X.stride(), dst.row0(), dst.stride(),
+                           x.n_items, (int)X.T, last ? 1 : 0, x.lstm_ws, x.st))
+        return 1;
+    } else if (tcrec) {
       if (launch_lstm_tc(pre.row0(), pre.stride(), layers[l].r_f16, last ? X.row0() : nullptr, X.stride(), dst.row0(), dst.stride(),
                          x.n_items, (int)X.T, last ? 1 : 0, x.lstm_ws, x.st))
         return 1;

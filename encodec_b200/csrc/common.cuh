@@ -408,6 +408,16 @@ int lstm_tc_workspace_floats(int batch);
 int launch_lstm_tc_pack(const float* whh, void* packed, int H, cudaStream_t s);
 int launch_lstm_tc(const float* pre, long long pre_item_stride, const void* w_packed, const float* skip, long long skip_item_stride,
                    float* out, long long out_item_stride, int batch, int T, int out_elu, float* workspace, cudaStream_t s);
+// second form of the kernel (lstm_tcw_kernel): both SLSTM layers as one wavefront kernel (up to 128 items; packings of 8 units per
+// CTA from launch_lstm_tc_pack_upc: W_hh of layer 1, W_ih and W_hh of layer 2; bias2 = b_ih + b_hh of layer 2), and one layer
+// with 16 units per CTA for large launches (packing of 16 units per CTA)
+int launch_lstm_tc_pack_upc(const float* w, void* packed, int H, int upc, cudaStream_t s);
+bool lstm_tc2_supported(int batch, int H);
+int launch_lstm_tc2(const float* pre, long long pre_item_stride, const void* w1h, const void* w2x, const void* w2h, const float* bias2,
+                    const float* skip, long long skip_item_stride, float* out, long long out_item_stride, int batch, int T, int out_elu,
+                    float* workspace, cudaStream_t s);
+int launch_lstm_tc16(const float* pre, long long pre_item_stride, const void* w_packed, const float* skip, long long skip_item_stride,
+                     float* out, long long out_item_stride, int batch, int T, int out_elu, float* workspace, cudaStream_t s);
 
 // ------------------------------------------------------------------------------------------------
 // rvq.cu

@@ -503,6 +503,475 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap map_w, const LstmTcParams p) 
   }
 }
 
+
+// ====================================================================================================
+// Second form: `lstm_tcw_kernel<CL, IG, UPC, TWO>` -- the same step (exchange through L2, one MMA per K step, fp16 split
+// operands), with the shared-memory budget spent differently:
+//
+// TWO = true, UPC = 8 (launches of up to 64 / 128 items): BOTH layers of the SLSTM in one kernel, as a wavefront. CTAs 0-63
+// run layer 1, CTAs 64-127 layer 2; layer 2 is one step behind. What bounds the single-layer kernel is the chain publish ->
+// poll -> copy -> MMA -> cell of one step (~6500 cycles at 64 items), so running step t of layer 2 beside step t + 1 of layer 1
+// halves the number of sequential hops of the block (4 x T -> 2 x (T + 1) for encoder + decoder). A layer-2 CTA holds its
+// slices of W_ih AND W_hh (128 KB): the input projection of layer 2 is not hoisted any more, it is the "x part" of the step,
+//     gates_2(t) = b + y1_t W_ih^T (x part, accumulator X) + h2_{t-1} W_hh^T (h part, accumulator H),
+// and y1_t = h1_t is read from the very exchange buffer layer 1 publishes for its own next step -- the layer-1 output never
+// goes to HBM, nor do the layer-2 pre-gates (2 x 393 MB written and read per config-2 layer before). The x part only needs
+// h1_t, which exists a whole step before h2_{t-1}: its copies and MMAs run while the layer-2 chain waits for the exchange.
+// h1 lives in a ring of 4 slots so that layer 1 may run ahead; it re-uses a slot only when layer 2's arrival counters show
+// that every layer-2 CTA has consumed it (flow control: one more coalesced acquire load in the poll).
+//
+// TWO = false, UPC = 16 (large launches): 32 unit blocks x 4 batch parts. Every CTA of a unit block has to pull the complete
+// h_t of its items into its SM (measured: 32-57 B / cycle / SM, the bound of the UPC = 8 geometry from 256 items: 512 KB per
+// CTA and step at 512 items); 16 units per CTA halve that volume per step, and the MMAs get N = 128.
+constexpr int LW_CS_OFF = 5 * LT_STAGE_BYTES + 16 * 8192;   // 208 KB: ring + weights of the largest layout
+constexpr int LW_RING1 = 4;                                  // exchange slots of h1 (TWO)
+constexpr int LW_TMEM_COLS = 512;
+
+struct LstmTcwParams {
+  const float* pre;      // (first layer) item b at pre + b * pre_stride, [T][4H] in reference gate order
+  long long pre_stride;
+  const float* bias2;    // TWO: [4H] b_ih + b_hh of the second layer (reference gate order)
+  const float* skip;     // item b at skip + b * skip_stride, [T][H], or nullptr
+  long long skip_stride;
+  float* out;            // output of the last layer
+  long long out_stride;
+  __half* h1;            // [TWO ? LW_RING1 : 2][G][8 K tiles][2 IG rows][64]: swizzled K-tile images as in LstmTcParams::hg
+  __half* h2;            // TWO: [2][G][8][2 IG][64]
+  unsigned int* cnt1;    // [G][8] arrival counters of h1
+  unsigned int* cnt2;    // TWO: [G][8] arrival counters of h2
+  int B, T, G, out_elu;
+  long long* trace;
+};
+#define LW_TRACE(role, t, ev)                                                                                     \
+  if (p.trace && cta == trace_cta && (t) >= LT_TR_T0 && (t) < LT_TR_T0 + LT_TR_STEPS && lane == 0)                 \
+    p.trace[((role) * LT_TR_STEPS + ((t) - LT_TR_T0)) * 16 + (ev)] = clock64();
+
+// mbarrier wait that cannot hang the device: a lost arrival traps after ~2^31 cycles
+__device__ __forceinline__ void mbar_wait_g(uint32_t bar, uint32_t parity) {
+  if (mbar_test(bar, parity)) return;
+  const long long t0 = clock64();
+  unsigned int n = 0;
+  while (!mbar_test(bar, parity)) {
+    if ((++n & 0xfffu) == 0 && clock64() - t0 > (1LL << 31)) __trap();
+  }
+}
+
+template <int W>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float* v) {   // W = 8 | 16 | 32 columns of this warp's lanes
+  if (W == 8) {
+    float t[8];
+    tmem_ldw<8>(taddr, t);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = t[i];
+  } else {
+#pragma unroll
+    for (int c = 0; c < W; c += 16) {
+      float t[16];
+      tmem_ldw<16>(taddr + (uint32_t)c, t);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[c + i] = t[i];
+    }
+  }
+}
+
+template <int CL, int IG, int UPC, bool TWO>
+__global__ void __launch_bounds__(LT_THREADS, 1)
+lstm_tcw_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtensorMap map_w2x,
+                const __grid_constant__ CUtensorMap map_w2h, const LstmTcwParams p) {
+  constexpr int NCOL = 4 * UPC;                 // gate columns per CTA: n = unit * 4 + gate
+  constexpr int W_TILE = 2 * NCOL * 128;        // [w1 (NCOL rows) | w2 (NCOL rows)] x 64 k
+  constexpr int NU = LT_H / UPC;                // unit blocks (= CTAs of a layer when TWO)
+  constexpr int NB = TWO ? 1 : LT_CTAS / NU;    // batch parts
+  constexpr int ROWS = 2 * IG;
+  constexpr int KP = 128 / ROWS;                // K tiles stacked along M in one MMA (1 | 2)
+  constexpr int NST = LT_NKT / KP;              // ring stages per group-step and operand part
+  constexpr int NACC = KP == 1 ? 2 : 1;
+  constexpr int NMMA = 2 * NCOL * KP;
+  constexpr int ACC_COLS = NACC * NMMA;
+  constexpr int BUF_COLS = TWO ? 2 * ACC_COLS : ACC_COLS;   // accumulator buffer: [H part | X part]
+  constexpr int QPG = IG / 16;
+  constexpr int UW = UPC / 2;                   // units per epilogue warp
+  constexpr int PP = UW / 2;                    // (item, unit) pairs per epilogue lane
+  constexpr int CW = 4 * UW;                    // gate columns per epilogue warp
+  static_assert(2 * BUF_COLS <= LW_TMEM_COLS, "TMEM budget");
+  static_assert(!TWO || UPC == 8, "the two-layer form is built for 64 + 64 CTAs");
+  static_assert(NU % CL == 0, "clusters must not straddle batch parts");
+  static_assert(PP == 2 || PP == 4, "8 or 16 units per CTA");
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (base - raw_addr);
+  const int cta = blockIdx.x;
+  const bool second = TWO && cta >= NU;          // this CTA runs layer 2
+  const int ub = TWO ? cta % NU : cta % NU;
+  const int bp = TWO ? 0 : cta / NU;
+  const int n_local = p.G > bp ? (p.G - bp + NB - 1) / NB : 0;
+  const int n_wt = second ? 2 * LT_NKT : LT_NKT;                       // weight tiles
+  const int n_stages = (n_wt * W_TILE + 8 * LT_STAGE_BYTES <= LW_CS_OFF) ? 8 : 5;
+  const uint32_t a_ring = base;
+  const uint32_t w_smem = base + (uint32_t)(n_stages * LT_STAGE_BYTES);
+  float* cs = reinterpret_cast<float*>(smem_gen + LW_CS_OFF);          // [n_local][IG][UPC] cell state
+  const int cs_bytes = ((p.G + NB - 1) / NB) * IG * UPC * 4;
+  constexpr int XS_BYTES = KP > 1 ? 4 * 16 * CW * 4 : 0;
+  float* xs = reinterpret_cast<float*>(smem_gen + LW_CS_OFF + cs_bytes);
+  const uint32_t bar_base = base + LW_CS_OFF + cs_bytes + XS_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (LT_STAGES + s); };
+  auto accf_bar = [&](int b) { return bar_base + 8u * (2 * LT_STAGES + b); };
+  auto acce_bar = [&](int b) { return bar_base + 8u * (2 * LT_STAGES + 2 + b); };
+  const uint32_t w_bar = bar_base + 8u * (2 * LT_STAGES + 4);
+  auto hst_bar = [&](int b) { return bar_base + 8u * (2 * LT_STAGES + 5 + b); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_gen + LW_CS_OFF + cs_bytes + XS_BYTES + 8 * (2 * LT_STAGES + 7));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int trace_cta = TWO ? NU : 0;
+  uint32_t crank = 0;
+  if (CL > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+  constexpr uint16_t MC_MASK = (uint16_t)((1u << CL) - 1u);
+  constexpr int ROWS_PER_CTA = ROWS / CL;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < LT_STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), CL);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(accf_bar(b), 1);
+      mbar_init(acce_bar(b), 8);
+      mbar_init(hst_bar(b), 2 * QPG);
+    }
+    mbar_init(w_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < n_local * IG * UPC; i += LT_THREADS) cs[i] = 0.f;
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(LW_TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (CL > 1) cluster_sync_all();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  const long long grp_bytes = (long long)LT_NKT * ROWS * 128;        // one group's h: 8 K-tile images
+  const long long buf_bytes = (long long)p.G * grp_bytes;            // one exchange slot
+  // operand parts of a step, in issue order: layer 2 first takes its x part (h1_t, ready a step early), then the h part
+  const int part0 = second ? 0 : 1;   // 0: x part, 1: h part
+  // private ring (no empty barriers): every (group, stage) of a step has its own slot. Only without an x part.
+  const bool private_ring = !second && n_local * NST <= n_stages;
+  // exchange slot that holds h_{t-1} of THIS layer for step t / that h1_t is written to
+  auto slot_h = [&](int t) { return second ? (t & 1) : (TWO ? t % LW_RING1 : (t & 1)); };
+
+  if (warp == 0) {
+    // ================================ loader ================================
+    if (elect_one()) {
+      mbar_expect_tx(w_bar, (uint32_t)(n_wt * W_TILE));
+      if (!second) {
+        for (int j = 0; j < LT_NKT; ++j) tma_load_2d(w_smem + j * W_TILE, &map_w1, w_bar, j * LT_KT, ub * 2 * NCOL);
+      } else {   // tiles 0-7: W_ih of layer 2 (x part), tiles 8-15: its W_hh
+        for (int j = 0; j < LT_NKT; ++j) tma_load_2d(w_smem + j * W_TILE, &map_w2x, w_bar, j * LT_KT, ub * 2 * NCOL);
+        for (int j = 0; j < LT_NKT; ++j) tma_load_2d(w_smem + (LT_NKT + j) * W_TILE, &map_w2h, w_bar, j * LT_KT, ub * 2 * NCOL);
+      }
+    }
+    __syncwarp();
+    constexpr unsigned int STAGE_MASK = (1u << KP) - 1u;
+    constexpr unsigned int PER_TILE = LT_KT / UPC;   // CTAs that publish one K tile
+    uint32_t it = 0;
+    for (int t = 0; t < p.T; ++t) {
+      for (int part = part0; part < 2; ++part) {
+        // x part: h1_t (slot of layer-1 step t + 1), complete when cnt1 = PER_TILE (t + 1); h part: h_{t-1} of this layer
+        const __half* src_buf = part == 0 ? p.h1 : (second ? p.h2 : p.h1);
+        const int slot = part == 0 ? (t + 1) % LW_RING1 : slot_h(t);
+        const unsigned int* cnt = (part == 0 || !second) ? p.cnt1 : p.cnt2;
+        const unsigned int target = PER_TILE * (unsigned int)(part == 0 ? t + 1 : t);
+        const bool need_poll = part == 0 || t > 0;
+        // flow control (layer 1 of TWO): h1_t goes to the slot that held h1_{t - RING}: every layer-2 CTA must have published
+        // h2_{t - RING} (its MMAs of that step have read the slot)
+        const bool flow = TWO && !second && t >= LW_RING1;
+        const unsigned int flow_target = PER_TILE * (unsigned int)(t - LW_RING1 + 1);
+        for (int gl = 0; gl < n_local; ++gl) {
+          const int g = bp + gl * NB;
+          const uint8_t* src_g = reinterpret_cast<const uint8_t*>(src_buf) + (long long)slot * buf_bytes + (long long)g * grp_bytes;
+          int next = 0;
+          bool flow_ok = !flow;
+          long long t_spin = 0;
+          unsigned int spins = 0;
+          if (gl == 0 && part == 1) LW_TRACE(0, t, 0)
+          while (next < NST) {
+            unsigned int v = 0xffffffffu, tgt = 0;
+            if (need_poll && lane < LT_NKT) {
+              asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(cnt + g * LT_NKT + lane) : "memory");
+              tgt = target;
+            } else if (!flow_ok && lane >= 8 && lane < 8 + LT_NKT) {
+              asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.cnt2 + g * LT_NKT + (lane - 8)) : "memory");
+              tgt = flow_target;
+            }
+            const unsigned int ready = __ballot_sync(0xffffffffu, v >= tgt);
+            if (!flow_ok && ((ready >> 8) & 0xffu) == 0xffu) flow_ok = true;
+            if (!flow_ok || ((ready >> (next * KP)) & STAGE_MASK) != STAGE_MASK) {
+              if ((++spins & 0x3ffu) == 0) {   // a lost arrival must not hang the device
+                if (t_spin == 0) t_spin = clock64();
+                else if (clock64() - t_spin > (1LL << 31)) __trap();
+              }
+              continue;
+            }
+            if (gl == 0 && next == 0 && part == 1) LW_TRACE(0, t, 9)
+            if (need_poll) asm volatile("fence.proxy.async.global;" ::: "memory");
+            if (gl == 0 && next == 0 && part == 1) LW_TRACE(0, t, 10)
+            while (next < NST && ((ready >> (next * KP)) & STAGE_MASK) == STAGE_MASK) {
+              const int st = private_ring ? gl * NST + next : (int)(it % (uint32_t)n_stages);
+              if (!private_ring) mbar_wait_g(empty_bar(st), ((it / (uint32_t)n_stages) & 1u) ^ 1u);
+              if (elect_one()) {
+                mbar_expect_tx(full_bar(st), LT_STAGE_BYTES);
+                const uint32_t dst = a_ring + st * LT_STAGE_BYTES;
+                const uint8_t* src = src_g + (long long)next * LT_STAGE_BYTES;
+                if (CL == 1) {
+                  bulk_load(dst, src, LT_STAGE_BYTES, full_bar(st));
+                } else {
+#pragma unroll
+                  for (int sub = 0; sub < KP; ++sub) {
+                    const uint32_t o = (uint32_t)(sub * ROWS + (int)crank * ROWS_PER_CTA) * 128u;
+                    bulk_load_mc(dst + o, src + o, ROWS_PER_CTA * 128, full_bar(st), MC_MASK);
+                  }
+                }
+              }
+              __syncwarp();
+              if (gl == 0 && part == 1) LW_TRACE(0, t, 1 + next)
+              ++next;
+              ++it;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    constexpr uint32_t idesc = idesc_f16(128, NMMA);
+    constexpr uint32_t DESC_HI = 64u | (1u << 14) | (2u << 29);
+    auto mk_desc = [](uint32_t addr) { return ((uint64_t)DESC_HI << 32) | (uint64_t)(((addr & 0x3FFFFu) >> 4) | (1u << 16)); };
+    mbar_wait_g(w_bar, 0);
+    uint32_t it = 0;
+    for (int t = 0; t < p.T; ++t) {
+      for (int part = part0; part < 2; ++part) {
+        for (int gl = 0; gl < n_local; ++gl) {
+          const uint32_t n = (uint32_t)t * (uint32_t)n_local + (uint32_t)gl;
+          const int acc = (int)(n & 1u);
+          if (part == part0) mbar_wait_g(acce_bar(acc), ((n >> 1) & 1u) ^ 1u);   // the epilogue has drained this buffer (both parts)
+          const uint32_t d = tmem_base + (uint32_t)(acc * BUF_COLS + (part == 0 ? ACC_COLS : 0));
+          const int wt0 = (second && part == 1) ? LT_NKT : 0;
+          for (int j = 0; j < NST; ++j, ++it) {
+            const int st = private_ring ? gl * NST + j : (int)(it % (uint32_t)n_stages);
+            mbar_wait_g(full_bar(st), private_ring ? ((uint32_t)t & 1u) : ((it / (uint32_t)n_stages) & 1u));
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (gl == 0 && part == 1) LW_TRACE(1, t, j)
+            if (elect_one()) {
+              const uint64_t da = mk_desc(a_ring + st * LT_STAGE_BYTES);
+              const uint64_t db = mk_desc(w_smem + (uint32_t)((wt0 + j * KP) * W_TILE));
+#pragma unroll
+              for (int k = 0; k < LT_KT / 16; ++k) {
+                const int mm = j * (LT_KT / 16) + k;
+                mma_f16(d + (uint32_t)((mm % NACC) * NMMA), da + 2u * k, db + 2u * k, idesc, mm >= NACC ? 1u : 0u);
+              }
+              if (!private_ring) {
+                if (CL == 1) tcgen05_commit(empty_bar(st));
+                else commit_mc(empty_bar(st), MC_MASK);
+              }
+              if (part == 1 && j + 1 == NST) tcgen05_commit(accf_bar(acc));
+            }
+            __syncwarp();
+            if (gl == 0 && part == 1 && j + 1 == NST) LW_TRACE(1, t, 8)
+          }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ================================ publisher ================================
+    // layer 1 of TWO publishes every step (layer 2 still needs h1_{T-1}); otherwise the last h is nobody's operand
+    unsigned int* cnt = second ? p.cnt2 : p.cnt1;
+    uint32_t n = 0;
+    for (int t = 0; t < p.T; ++t) {
+      for (int gl = 0; gl < n_local; ++gl, ++n) {
+        const int g = bp + gl * NB;
+        mbar_wait_g(hst_bar((int)(n & 1u)), (n >> 1) & 1u);
+        if ((t + 1 < p.T || (TWO && !second)) && lane == 0)
+          asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(cnt + g * LT_NKT + (ub * UPC) / LT_KT) : "memory");
+        __syncwarp();
+        if (gl == 0) LW_TRACE(2, t, 6)
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================ cell epilogue (as in lstm_tc_kernel) ================================
+    const int quad = warp & 3;
+    const int half = (warp - 4) >> 2;
+    const int r = lane & 15;
+    const int lg = lane >> 4;
+    const int kpart = quad / QPG;
+    const int iq = quad % QPG;
+    const bool storing = kpart == 0;
+    const int il = iq * 16 + r;
+    const int team = half * QPG + iq;
+    const int u0 = half * UW + lg * PP;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(2 * NCOL * kpart + CW * half);
+    const bool last_layer = !TWO || second;
+    float bias_r[PP][4];
+#pragma unroll
+    for (int e = 0; e < PP; ++e)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) bias_r[e][k] = second ? __ldg(p.bias2 + k * LT_H + ub * UPC + u0 + e) : 0.f;
+    uint32_t n = 0;
+    for (int t = 0; t < p.T; ++t) {
+      const bool store_h = t + 1 < p.T || (TWO && !second);
+      uint8_t* hn = reinterpret_cast<uint8_t*>(second ? p.h2 : p.h1) + (long long)slot_h(t + 1) * buf_bytes;
+      for (int gl = 0; gl < n_local; ++gl, ++n) {
+        const int g = bp + gl * NB;
+        const int acc = (int)(n & 1u);
+        const int item = g * IG + il;
+        const bool valid = storing && item < p.B;
+        float pg[PP][4], skipv[PP];
+#pragma unroll
+        for (int e = 0; e < PP; ++e) {
+          skipv[e] = 0.f;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) pg[e][k] = bias_r[e][k];
+          if (valid) {
+            const int unit = ub * UPC + u0 + e;
+            if (!second) {
+              const float* pr = p.pre + (long long)item * p.pre_stride + (long long)t * (4 * LT_H) + unit;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) pg[e][k] = __ldg(pr + k * LT_H);
+            }
+            if (last_layer && p.skip) skipv[e] = __ldg(p.skip + (long long)item * p.skip_stride + (long long)t * LT_H + unit);
+          }
+        }
+        if (gl == 0 && warp == 4) LW_TRACE(2, t, 0)
+        mbar_wait_g(accf_bar(acc), (n >> 1) & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (gl == 0 && warp == 4) LW_TRACE(2, t, 1)
+        // h1 rows (lanes 0-15): main + corr / 2^11 with corr = h1 w2; h2 rows (lanes 16-31): their "main" columns are h2 w1.
+        // Sources: the accumulators of the h part, then (layer 2) those of the x part.
+        float part[CW];
+#pragma unroll
+        for (int k = 0; k < CW; ++k) part[k] = 0.f;
+        const uint32_t a0 = lane_base + (uint32_t)(acc * BUF_COLS);
+#pragma unroll
+        for (int srcp = 0; srcp < (TWO ? 2 : 1); ++srcp) {
+          if (srcp == 1 && !second) break;
+#pragma unroll
+          for (int a = 0; a < NACC; ++a) {
+            float mt[CW], ct[CW];
+            tmem_ld_cols<CW>(a0 + (uint32_t)(srcp * ACC_COLS + NMMA * a), mt);
+            tmem_ld_cols<CW>(a0 + (uint32_t)(srcp * ACC_COLS + NMMA * a + NCOL), ct);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int k = 0; k < CW; ++k)
+              part[k] += lane < 16 ? fmaf(ct[k], 1.f / LT_LO_SCALE, mt[k]) : mt[k] * (1.f / LT_LO_SCALE);
+          }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acce_bar(acc));
+        if (gl == 0 && warp == 4) LW_TRACE(2, t, 2)
+#pragma unroll
+        for (int k = 0; k < CW; ++k) part[k] += __shfl_xor_sync(0xffffffffu, part[k], 16);
+        if (KP > 1) {
+          float* x = xs + (team * 16 + r) * CW;
+          if (!storing && lane < 16) {
+#pragma unroll
+            for (int k = 0; k < CW; k += 4) *reinterpret_cast<float4*>(x + k) = make_float4(part[k], part[k + 1], part[k + 2], part[k + 3]);
+          }
+          asm volatile("bar.sync %0, %1;" ::"r"(2 + team), "r"(32 * KP) : "memory");
+          if (storing) {
+#pragma unroll
+            for (int k = 0; k < CW; k += 4) {
+              const float4 xv = *reinterpret_cast<const float4*>(x + k);
+              part[k] += xv.x; part[k + 1] += xv.y; part[k + 2] += xv.z; part[k + 3] += xv.w;
+            }
+          }
+          asm volatile("bar.sync %0, %1;" ::"r"(2 + team), "r"(32 * KP) : "memory");
+          if (!storing) continue;
+        }
+        if (gl == 0 && warp == 4) LW_TRACE(2, t, 4)
+        unsigned int own[PP];
+        float h_new[PP];
+#pragma unroll
+        for (int e = 0; e < PP; ++e) {
+          float rec[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float lo = part[e * 4 + k], hi = part[(PP + e) * 4 + k];
+            rec[k] = lane < 16 ? lo : hi;
+          }
+          float s_if[2] = {pg[e][0] + rec[0], pg[e][1] + rec[1]};
+          float s_go[2] = {2.f * (pg[e][2] + rec[2]), pg[e][3] + rec[3]};
+          sigmoid_pair(s_if);
+          sigmoid_pair(s_go);
+          float* cptr = cs + (gl * IG + il) * UPC + u0 + e;
+          const float c_new = s_if[1] * (*cptr) + s_if[0] * (2.f * s_go[0] - 1.f);
+          *cptr = c_new;
+          float s_c[2] = {2.f * c_new, 0.f};
+          sigmoid_pair(s_c);
+          h_new[e] = s_go[1] * (2.f * s_c[0] - 1.f);
+          const __half q1 = __float2half_rn(h_new[e]);
+          const __half q2 = __float2half_rn((h_new[e] - __half2float(q1)) * LT_LO_SCALE);
+          own[e] = (unsigned int)__half_as_ushort(q1) | ((unsigned int)__half_as_ushort(q2) << 16);
+        }
+        if (gl == 0 && warp == 4) LW_TRACE(2, t, 5)
+        unsigned int oth[PP];
+#pragma unroll
+        for (int e = 0; e < PP; ++e) oth[e] = __shfl_down_sync(0xffffffffu, own[e], 16);
+        if (lane < 16 && store_h) {   // the UW units of this item: one store per split part
+          const int kk = (ub * UPC + half * UW) % LT_KT;
+          const long long row = ((long long)g * LT_NKT + (ub * UPC) / LT_KT) * ROWS + iq * 32 + r;
+          uint8_t* dst = hn + row * 128 + (((kk >> 3) ^ (r & 7)) << 4) + (kk & 7) * 2;
+          {
+            // words of the h1 row: this lane's PP units, then the PP units of lane + 16; same for the h2 row
+            unsigned int w1[PP], w2[PP];
+#pragma unroll
+            for (int i = 0; i < PP / 2; ++i) {
+              w1[i] = (own[2 * i] & 0xffffu) | (own[2 * i + 1] << 16);
+              w1[PP / 2 + i] = (oth[2 * i] & 0xffffu) | (oth[2 * i + 1] << 16);
+              w2[i] = (own[2 * i] >> 16) | (own[2 * i + 1] & 0xffff0000u);
+              w2[PP / 2 + i] = (oth[2 * i] >> 16) | (oth[2 * i + 1] & 0xffff0000u);
+            }
+            if (PP == 2) {
+              asm volatile("st.global.cg.v2.b32 [%0], {%1, %2};" ::"l"(dst), "r"(w1[0]), "r"(w1[1]) : "memory");
+              asm volatile("st.global.cg.v2.b32 [%0], {%1, %2};" ::"l"(dst + 16 * 128), "r"(w2[0]), "r"(w2[1]) : "memory");
+            } else {
+              asm volatile("st.global.cg.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(w1[0]), "r"(w1[1]), "r"(w1[PP == 4 ? 2 : 0]),
+                           "r"(w1[PP == 4 ? 3 : 0])
+                           : "memory");
+              asm volatile("st.global.cg.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 16 * 128), "r"(w2[0]), "r"(w2[1]),
+                           "r"(w2[PP == 4 ? 2 : 0]), "r"(w2[PP == 4 ? 3 : 0])
+                           : "memory");
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(hst_bar(acc));   // -> publisher warp
+        if (gl == 0 && warp == 4) LW_TRACE(2, t, 3)
+        if (valid && last_layer) {
+#pragma unroll
+          for (int e = 0; e < PP; ++e) {
+            float y = h_new[e] + skipv[e];
+            if (p.out_elu) y = elu1(y);
+            p.out[(long long)item * p.out_stride + (long long)t * LT_H + ub * UPC + u0 + e] = y;
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (CL > 1) cluster_sync_all();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(LW_TMEM_COLS) : "memory");
+  }
+}
+
 // W_hh [4H][H] (reference layout) -> fp16 split slices [unit blocks][w1: 4 upc rows | w2: 4 upc rows][512], row n = unit * 4 + gate
 __global__ void lstm_tc_pack_kernel(const float* __restrict__ whh, __half* __restrict__ wp, int upc) {
   const int ncol = 4 * upc;
@@ -536,14 +1005,24 @@ int launch_lstm_tc_pack(const float* whh, void* packed, int H, cudaStream_t s) {
   return 0;
 }
 
+// one [4H][H] matrix (W_hh or W_ih) -> [8H][H] halves in the slice order of `upc` units per CTA
+int launch_lstm_tc_pack_upc(const float* w, void* packed, int H, int upc, cudaStream_t s) {
+  ECB_REQUIRE(H == LT_H && (upc == 4 || upc == 8 || upc == 16), "lstm_tc: pack H %d / upc %d unsupported", H, upc);
+  lstm_tc_pack_kernel<<<8 * LT_H, 128, 0, s>>>(w, reinterpret_cast<__half*>(packed), upc);
+  ECB_LAUNCHED();
+  return 0;
+}
+
 long long* g_lstm_tc_trace = nullptr;   // diagnostic (ecb_debug_lstm_trace): device buffer of 3 * 8 * 16 stamps
 
 bool lstm_tc_supported(int batch, int H) { return H == LT_H && batch >= 1 && batch <= LT_MAX_GROUPS * 64; }
 
 // floats of workspace: exchange buffers ([2][G][8][2 IG][64] fp16) + counters
 int lstm_tc_workspace_floats(int batch) {
-  const int G = 2 * ((batch + 63) / 64);
-  return G * 32 * LT_H * 2 + G * LT_NKT + 64;
+  // exchange buffers of 2 (single layer) or 4 + 2 (two-layer wavefront, up to 128 items) slots of [items rounded up to 64][2 parts][512]
+  // halves, + arrival counters
+  const int rb = (batch + 63) / 64 * 64;
+  return rb * (batch <= 128 ? 3072 : 1024) + 1024;
 }
 
 int launch_lstm_tc(const float* pre, long long pre_item_stride, const void* w_packed, const float* skip, long long skip_item_stride,
@@ -641,6 +1120,145 @@ int launch_lstm_tc(const float* pre, long long pre_item_stride, const void* w_pa
     ECB_CUDA(le);
     break;
   }
+  ECB_LAUNCHED();
+  return 0;
+}
+
+
+namespace {
+template <int CL, int IG, int UPC, bool TWO>
+int launch_tcw_one(const CUtensorMap* maps, const LstmTcwParams& p, int cl_req, size_t smem, cudaStream_t s) {
+  const void* fn = (const void*)lstm_tcw_kernel<CL, IG, UPC, TWO>;
+  static DeviceOnce once;
+  if (!once.done()) {
+    ECB_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    once.mark();
+  }
+  (void)cl_req;
+  void* args[] = {(void*)&maps[0], (void*)&maps[1], (void*)&maps[2], (void*)&p};
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(LT_CTAS);
+  cfg.blockDim = dim3(LT_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attrs[2];
+  int na = 0;
+  attrs[na].id = cudaLaunchAttributeCooperative;   // all CTAs spin on each other's arrivals: they must be co-resident
+  attrs[na].val.cooperative = 1;
+  ++na;
+  if (CL > 1) {
+    attrs[na].id = cudaLaunchAttributeClusterDimension;
+    attrs[na].val.clusterDim.x = (unsigned)CL;
+    attrs[na].val.clusterDim.y = 1;
+    attrs[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  cfg.attrs = attrs;
+  cfg.numAttrs = (unsigned)na;
+  const cudaError_t le = cudaLaunchKernelExC(&cfg, fn, args);
+  if (le != cudaSuccess) {
+    cudaGetLastError();
+    return CL > 1 ? -1 : (set_error("lstm_tcw launch failed: %s", cudaGetErrorString(le)), 1);   // -1: retry without clusters
+  }
+  return 0;
+}
+
+int make_w_map(CUtensorMap* map, const void* packed, int upc) {
+  const cuuint64_t dims[2] = {(cuuint64_t)LT_H, (cuuint64_t)(8 * LT_H)};
+  const cuuint64_t strides[1] = {(cuuint64_t)LT_H * 2};
+  const cuuint32_t box[2] = {LT_KT, (cuuint32_t)(2 * 4 * upc)};
+  return make_tensor_map_f16(map, packed, 2, dims, strides, box);
+}
+}  // namespace
+
+bool lstm_tc2_supported(int batch, int H) { return H == LT_H && batch >= 1 && batch <= 128; }
+
+// Both layers of the SLSTM as one wavefront kernel (lstm_tcw_kernel<.., TWO = true>). pre: first layer's pre-gates; w1h / w2x / w2h:
+// UPC = 8 packings (launch_lstm_tc_pack_upc) of W_hh(layer 1), W_ih(layer 2), W_hh(layer 2); bias2 = b_ih + b_hh of layer 2.
+int launch_lstm_tc2(const float* pre, long long pre_item_stride, const void* w1h, const void* w2x, const void* w2h, const float* bias2,
+                    const float* skip, long long skip_item_stride, float* out, long long out_item_stride, int batch, int T, int out_elu,
+                    float* workspace, cudaStream_t s) {
+  ECB_REQUIRE(lstm_tc2_supported(batch, LT_H) && T > 0, "lstm_tc2: bad batch %d / T %d", batch, T);
+  int ig = batch <= 64 ? 32 : 64;
+  if (const char* e = getenv("ECB_LSTM_GROUP")) {
+    const int v = atoi(e);
+    if (v == 64 || (v == 32 && batch <= 64)) ig = v;
+  }
+  const int G = (batch + ig - 1) / ig;
+  const int rows = 2 * ig;
+  LstmTcwParams p;
+  p.pre = pre;
+  p.pre_stride = pre_item_stride;
+  p.bias2 = bias2;
+  p.skip = skip;
+  p.skip_stride = skip_item_stride;
+  p.out = out;
+  p.out_stride = out_item_stride;
+  const long long slot = (long long)G * rows * LT_H;   // halves per exchange slot
+  p.h1 = reinterpret_cast<__half*>(workspace);
+  p.h2 = p.h1 + LW_RING1 * slot;
+  p.cnt1 = reinterpret_cast<unsigned int*>(p.h2 + 2 * slot);
+  p.cnt2 = p.cnt1 + G * LT_NKT;
+  p.B = batch;
+  p.T = T;
+  p.G = G;
+  p.out_elu = out_elu;
+  p.trace = g_lstm_tc_trace;
+  ECB_CUDA(cudaMemsetAsync(workspace, 0, sizeof(__half) * (LW_RING1 + 2) * slot + sizeof(unsigned int) * (size_t)(2 * G * LT_NKT), s));
+  CUtensorMap maps[3];
+  if (make_w_map(&maps[0], w1h, 8) || make_w_map(&maps[1], w2x, 8) || make_w_map(&maps[2], w2h, 8)) return 1;
+  const size_t smem = 1024 + LW_CS_OFF + (size_t)G * ig * 8 * 4 + 4 * 16 * 16 * 4 + 8 * (2 * LT_STAGES + 7) + 16;
+  ECB_REQUIRE(smem <= 227 * 1024, "lstm_tc2: %zu bytes of shared memory", smem);
+  const double bt = (double)batch * T;
+  ProfScope prof(PROF_LSTM_REC, s, 2.0 * bt * 4 * LT_H * LT_H * 3, 4.0 * (bt * 4 * LT_H + bt * LT_H * 2 + 12.0 * LT_H * LT_H));
+  const int rc = ig == 32 ? launch_tcw_one<1, 32, 8, true>(maps, p, 1, smem, s) : launch_tcw_one<1, 64, 8, true>(maps, p, 1, smem, s);
+  if (rc) return 1;
+  ECB_LAUNCHED();
+  return 0;
+}
+
+// One layer, 16 units per CTA (32 unit blocks x 4 batch parts): large launches. w_packed = UPC 16 packing of W_hh.
+int launch_lstm_tc16(const float* pre, long long pre_item_stride, const void* w_packed, const float* skip, long long skip_item_stride,
+                     float* out, long long out_item_stride, int batch, int T, int out_elu, float* workspace, cudaStream_t s) {
+  ECB_REQUIRE(lstm_tc_supported(batch, LT_H) && T > 0, "lstm_tc16: bad batch %d / T %d", batch, T);
+  constexpr int ig = 64, nb = 4;
+  const int G = (batch + ig - 1) / ig;
+  const int rows = 2 * ig;
+  LstmTcwParams p;
+  p.pre = pre;
+  p.pre_stride = pre_item_stride;
+  p.bias2 = nullptr;
+  p.skip = skip;
+  p.skip_stride = skip_item_stride;
+  p.out = out;
+  p.out_stride = out_item_stride;
+  const long long slot = (long long)G * rows * LT_H;
+  p.h1 = reinterpret_cast<__half*>(workspace);
+  p.h2 = nullptr;
+  p.cnt1 = reinterpret_cast<unsigned int*>(p.h1 + 2 * slot);
+  p.cnt2 = nullptr;
+  p.B = batch;
+  p.T = T;
+  p.G = G;
+  p.out_elu = out_elu;
+  p.trace = g_lstm_tc_trace;
+  ECB_CUDA(cudaMemsetAsync(workspace, 0, sizeof(__half) * 2 * slot + sizeof(unsigned int) * (size_t)(G * LT_NKT), s));
+  CUtensorMap maps[3];
+  if (make_w_map(&maps[0], w_packed, 16)) return 1;
+  maps[1] = maps[0];
+  maps[2] = maps[0];
+  const size_t smem = 1024 + LW_CS_OFF + (size_t)((G + nb - 1) / nb) * ig * 16 * 4 + 8 * (2 * LT_STAGES + 7) + 16;
+  ECB_REQUIRE(smem <= 227 * 1024, "lstm_tc16: %zu bytes of shared memory for %d groups", smem, G);
+  int cl = (G + nb - 1) / nb >= 2 ? 4 : 1;
+  if (const char* e = getenv("ECB_LSTM_CLUSTER")) cl = atoi(e);
+  ECB_REQUIRE(cl == 1 || cl == 2 || cl == 4, "lstm_tc16: ECB_LSTM_CLUSTER=%d (1, 2 or 4)", cl);
+  const double bt = (double)batch * T;
+  ProfScope prof(PROF_LSTM_REC, s, 2.0 * bt * 4 * LT_H * LT_H, 4.0 * (bt * 4 * LT_H + bt * LT_H * (skip ? 2 : 1) + 4.0 * LT_H * LT_H));
+  int rc = -1;
+  if (cl == 4) rc = launch_tcw_one<4, 64, 16, false>(maps, p, cl, smem, s);
+  else if (cl == 2) rc = launch_tcw_one<2, 64, 16, false>(maps, p, cl, smem, s);
+  if (rc < 0) rc = launch_tcw_one<1, 64, 16, false>(maps, p, 1, smem, s);   // also the retry where a clustered cooperative launch is refused
+  if (rc) return 1;
   ECB_LAUNCHED();
   return 0;
 }

@@ -468,10 +468,11 @@ def test_stepwise_tensor_core_lstm_matches_reference_golden(name, monkeypatch):
         assert d.max() < AUDIO_MAX_ABS and np.sqrt((d ** 2).mean()) < AUDIO_RMS
 
 
-@pytest.mark.parametrize("batch,steps", [(5, 40), (64, 48), (130, 24), (330, 16)])
+@pytest.mark.parametrize("batch,steps", [(1, 9), (5, 40), (33, 21), (64, 48), (100, 12), (130, 24), (330, 16), (1000, 6)])
 def test_lstm_recurrence_forms_agree(batch, steps, monkeypatch):
-    """The three implementations of the SLSTM recurrence -- the persistent tensor-core kernel (fp16 split operands, lstm_tc.cu),
-    the persistent fp32 FFMA kernel and the step-wise tensor-core form (3xTF32 GEMM + fused cell epilogue from a CUDA graph) --
+    """The implementations of the SLSTM recurrence -- the persistent tensor-core kernel (fp16 split operands, lstm_tc.cu), its
+    16-units-per-CTA form and its two-layer wavefront form, the persistent fp32 FFMA kernel and the step-wise tensor-core form
+    (3xTF32 GEMM + fused cell epilogue from a CUDA graph) --
     on the same random input at batch sizes that exercise ragged groups, several M tiles and the automatic switch; and
     against a float64 LSTM computed on the CPU."""
     from encodec_b200 import _native as nat, synth
@@ -482,9 +483,13 @@ def test_lstm_recurrence_forms_agree(batch, steps, monkeypatch):
     x = torch.from_numpy(synth.hash_normal(77, "lstm-x", (batch, steps, H))).cuda()
     ws = torch.empty(nat.lib.ecb_debug_lstm_workspace_bytes(codec.handle, batch, steps), dtype=torch.uint8, device="cuda")
     outs = {}
-    for name, tc_mode, step_mode in (("tensor", "2", "0"), ("ffma", "0", "0"), ("stepwise", "0", "1")):
+    forms = [("tensor", "2", "0", "0"), ("ffma", "0", "0", "0"), ("stepwise", "0", "1", "0"), ("tensor16", "2", "0", "16")]
+    if batch <= 128:
+        forms.append(("wavefront", "2", "0", "2"))   # both layers in one kernel, layer 2 a step behind layer 1
+    for name, tc_mode, step_mode, form in forms:
         monkeypatch.setenv("ECB_LSTM_TC", tc_mode)
         monkeypatch.setenv("ECB_LSTM_STEPWISE", step_mode)
+        monkeypatch.setenv("ECB_LSTM_FORM", form)
         out = torch.empty_like(x)
         nat.check(nat.lib.ecb_debug_lstm(codec.handle, x.data_ptr(), out.data_ptr(), batch, steps, ws.data_ptr(), ws.numel(),
                                          nat.stream_ptr(x.device)))
@@ -501,6 +506,9 @@ def test_lstm_recurrence_forms_agree(batch, steps, monkeypatch):
         assert ug.rel_err(got, want) < 5e-6, (name, ug.rel_err(got, want))
     assert ug.rel_err(outs["ffma"], outs["stepwise"]) < 5e-6
     assert ug.rel_err(outs["ffma"], outs["tensor"]) < 5e-6
+    assert ug.rel_err(outs["ffma"], outs["tensor16"]) < 5e-6
+    if "wavefront" in outs:
+        assert ug.rel_err(outs["ffma"], outs["wavefront"]) < 5e-6
 
 
 def _score_against_port(emb, sd, ref_codes, got_codes, tag):

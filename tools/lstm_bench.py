@@ -31,10 +31,13 @@ for B in [int(v) for v in os.environ.get("LSTM_B", "64,128,256,512,960").split("
     out = torch.empty_like(x)
     ws = torch.empty(nat.lib.ecb_debug_lstm_workspace_bytes(codec.handle, B, T), dtype=torch.uint8, device=dev)
     ref = None
-    for mode, lo, tcm in (("0", "1", "0"), ("0", "1", "2"), ("1", "1", "0")):
+    for mode, lo, tcm, form in (("0", "1", "0", "0"), ("0", "1", "2", "0"), ("1", "1", "0", "0"), ("0", "1", "2", "16"), ("0", "1", "2", "2")):
+        if form == "2" and B > 128:
+            continue
         os.environ["ECB_LSTM_STEPWISE"] = mode
         os.environ["ECB_LSTM_LO_TMA"] = lo
         os.environ["ECB_LSTM_TC"] = tcm
+        os.environ["ECB_LSTM_FORM"] = form
 
         def run():
             nat.check(nat.lib.ecb_debug_lstm(codec.handle, x.data_ptr(), out.data_ptr(), B, T, ws.data_ptr(), ws.numel(), st))
@@ -53,5 +56,5 @@ for B in [int(v) for v in os.environ.get("LSTM_B", "64,128,256,512,960").split("
             err = 0.0
         else:
             err = float((out - ref).abs().max())
-        print(f"{B:5d} {'stepwise' if mode == '1' else ('tensor' if tcm == '2' else 'ffma'):>11s} {ms:8.3f} {ms * 1e3 / (2 * T):8.2f}   max |diff| vs persistent {err:.2e}",
+        print(f"{B:5d} {'stepwise' if mode == '1' else (('tensor' if form == '0' else 'tensor16' if form == '16' else 'wavefront') if tcm == '2' else 'ffma'):>11s} {ms:8.3f} {ms * 1e3 / (2 * T):8.2f}   max |diff| vs persistent {err:.2e}",
               flush=True)
