@@ -946,8 +946,8 @@ int lstm_steps(Ctx& x, const LstmLayerW& lw, const float* pre, long long pre_str
   return 0;
 }
 
-constexpr int LSTM_WAVE_MAX = 64;    // items per launch up to which the two-layer wavefront kernel runs
-constexpr int LSTM_U16_MIN = 256;    // items per launch from which a layer runs with 16 units per CTA
+constexpr int LSTM_WAVE_MAX = 128;   // items per launch up to which the two-layer wavefront kernel runs
+constexpr int LSTM_U16_MIN = 384;    // items per launch from which a layer runs with 16 units per CTA
 // SLSTM (modules/lstm.py:22-28): X raw [item][T][512] -> out = ELU(lstm(X) + X). pre / h0 are plain scratch.
 int tc_lstm(Ctx& x, const std::vector<LstmLayerW>& layers, const Act& X, float* pre_buf, float* h0_buf, Act& out, int split) {
   const int H = top_width(x.c->spec), L = (int)layers.size();

@@ -679,7 +679,8 @@ lstm_tcw_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_constan
     __syncwarp();
     constexpr unsigned int STAGE_MASK = (1u << KP) - 1u;
     constexpr unsigned int PER_TILE = LT_KT / UPC;   // CTAs that publish one K tile
-    uint32_t it = 0;
+    int ring_st = 0;            // shared ring: next stage and its phase, stepped without divisions (they cost ~100 cycles each)
+    uint32_t ring_ph = 0;
     for (int t = 0; t < p.T; ++t) {
       for (int part = part0; part < 2; ++part) {
         // x part: h1_t (slot of layer-1 step t + 1), complete when cnt1 = PER_TILE (t + 1); h part: h_{t-1} of this layer
@@ -722,8 +723,8 @@ lstm_tcw_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_constan
             if (need_poll) asm volatile("fence.proxy.async.global;" ::: "memory");
             if (gl == 0 && next == 0 && part == 1) LW_TRACE(0, t, 10)
             while (next < NST && ((ready >> (next * KP)) & STAGE_MASK) == STAGE_MASK) {
-              const int st = private_ring ? gl * NST + next : (int)(it % (uint32_t)n_stages);
-              if (!private_ring) mbar_wait_g(empty_bar(st), ((it / (uint32_t)n_stages) & 1u) ^ 1u);
+              const int st = private_ring ? gl * NST + next : ring_st;
+              if (!private_ring) mbar_wait_g(empty_bar(st), ring_ph ^ 1u);
               if (elect_one()) {
                 mbar_expect_tx(full_bar(st), LT_STAGE_BYTES);
                 const uint32_t dst = a_ring + st * LT_STAGE_BYTES;
@@ -741,7 +742,10 @@ lstm_tcw_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_constan
               __syncwarp();
               if (gl == 0 && part == 1) LW_TRACE(0, t, 1 + next)
               ++next;
-              ++it;
+              if (++ring_st == n_stages) {
+                ring_st = 0;
+                ring_ph ^= 1u;
+              }
             }
           }
         }
@@ -753,7 +757,8 @@ lstm_tcw_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_constan
     constexpr uint32_t DESC_HI = 64u | (1u << 14) | (2u << 29);
     auto mk_desc = [](uint32_t addr) { return ((uint64_t)DESC_HI << 32) | (uint64_t)(((addr & 0x3FFFFu) >> 4) | (1u << 16)); };
     mbar_wait_g(w_bar, 0);
-    uint32_t it = 0;
+    int ring_st = 0;
+    uint32_t ring_ph = 0;
     for (int t = 0; t < p.T; ++t) {
       for (int part = part0; part < 2; ++part) {
         for (int gl = 0; gl < n_local; ++gl) {
@@ -762,9 +767,13 @@ lstm_tcw_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_constan
           if (part == part0) mbar_wait_g(acce_bar(acc), ((n >> 1) & 1u) ^ 1u);   // the epilogue has drained this buffer (both parts)
           const uint32_t d = tmem_base + (uint32_t)(acc * BUF_COLS + (part == 0 ? ACC_COLS : 0));
           const int wt0 = (second && part == 1) ? LT_NKT : 0;
-          for (int j = 0; j < NST; ++j, ++it) {
-            const int st = private_ring ? gl * NST + j : (int)(it % (uint32_t)n_stages);
-            mbar_wait_g(full_bar(st), private_ring ? ((uint32_t)t & 1u) : ((it / (uint32_t)n_stages) & 1u));
+          for (int j = 0; j < NST; ++j) {
+            const int st = private_ring ? gl * NST + j : ring_st;
+            mbar_wait_g(full_bar(st), private_ring ? ((uint32_t)t & 1u) : ring_ph);
+            if (++ring_st == n_stages) {
+              ring_st = 0;
+              ring_ph ^= 1u;
+            }
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (gl == 0 && part == 1) LW_TRACE(1, t, j)
             if (elect_one()) {
