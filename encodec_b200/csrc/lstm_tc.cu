@@ -541,6 +541,7 @@ struct LstmTcwParams {
   unsigned int* cnt2;    // TWO: [G][8] arrival counters of h2
   int B, T, G, out_elu;
   long long* trace;
+  int trace_cta;         // diagnostic: the CTA whose stamps are recorded (ECB_LSTM_TRACE_CTA; default: first CTA of the last layer)
 };
 #define LW_TRACE(role, t, ev)                                                                                     \
   if (p.trace && cta == trace_cta && (t) >= LT_TR_T0 && (t) < LT_TR_T0 + LT_TR_STEPS && lane == 0)                 \
@@ -613,7 +614,7 @@ lstm_tcw_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_constan
   const uint32_t w_smem = base + (uint32_t)(n_stages * LT_STAGE_BYTES);
   float* cs = reinterpret_cast<float*>(smem_gen + LW_CS_OFF);          // [n_local][IG][UPC] cell state
   const int cs_bytes = ((p.G + NB - 1) / NB) * IG * UPC * 4;
-  constexpr int XS_BYTES = KP > 1 ? 4 * 16 * CW * 4 : 0;
+  constexpr int XS_BYTES = KP > 1 ? 4 * 2 * 16 * (CW / 2) * 4 : 0;   // [teams][K part][16 items][columns of the partner's units]
   float* xs = reinterpret_cast<float*>(smem_gen + LW_CS_OFF + cs_bytes);
   const uint32_t bar_base = base + LW_CS_OFF + cs_bytes + XS_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -626,7 +627,7 @@ lstm_tcw_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_constan
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int trace_cta = TWO ? NU : 0;
+  const int trace_cta = p.trace_cta;
   uint32_t crank = 0;
   if (CL > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
   constexpr uint16_t MC_MASK = (uint16_t)((1u << CL) - 1u);
@@ -640,7 +641,7 @@ lstm_tcw_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_constan
     for (int b = 0; b < 2; ++b) {
       mbar_init(accf_bar(b), 1);
       mbar_init(acce_bar(b), 8);
-      mbar_init(hst_bar(b), 2 * QPG);
+      mbar_init(hst_bar(b), 8);          // every epilogue warp stores a part of h
     }
     mbar_init(w_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -812,22 +813,31 @@ lstm_tcw_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_constan
       }
     }
   } else if (warp >= 4) {
-    // ================================ cell epilogue (as in lstm_tc_kernel) ================================
+    // ================================ cell epilogue ================================
+    // Accumulator layout as in lstm_tc_kernel: a lane quadrant holds, for one K part and 16 items, the h1 rows in lanes 0-15 and
+    // the h2 rows in lanes 16-31; warp w reads quadrant w % 4, warps 4-7 the first UW units of the CTA, warps 8-11 the others.
+    // KP == 2: the two warps of a team (same units and items, one K part each) hand each other the partial sums of HALF of
+    // the team's units through shared memory and both go on to the cell update -- every lane finishes ONE (item, unit) pair
+    // (PPL = PP / 2) instead of the K-part-0 warp finishing two while its partner idles: the cell math (three dependent
+    // sigmoid evaluations) is the longest stretch of the epilogue.
+    constexpr int PPL = KP == 2 ? PP / 2 : PP;    // (item, unit) pairs per lane
+    constexpr int UWW = KP == 2 ? UW / 2 : UW;    // units finished by one warp
+    static_assert(KP == 1 || PP == 2, "the shared epilogue is written for 8 units per CTA");
     const int quad = warp & 3;
     const int half = (warp - 4) >> 2;
     const int r = lane & 15;
     const int lg = lane >> 4;
     const int kpart = quad / QPG;
     const int iq = quad % QPG;
-    const bool storing = kpart == 0;
     const int il = iq * 16 + r;
     const int team = half * QPG + iq;
-    const int u0 = half * UW + lg * PP;
+    const int uw0 = half * UW + (KP == 2 ? kpart * UWW : 0);   // first unit (within the CTA) this warp finishes
+    const int u0 = uw0 + lg * PPL;                             // ... and this lane
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(2 * NCOL * kpart + CW * half);
     const bool last_layer = !TWO || second;
-    float bias_r[PP][4];
+    float bias_r[PPL][4];
 #pragma unroll
-    for (int e = 0; e < PP; ++e)
+    for (int e = 0; e < PPL; ++e)
 #pragma unroll
       for (int k = 0; k < 4; ++k) bias_r[e][k] = second ? __ldg(p.bias2 + k * LT_H + ub * UPC + u0 + e) : 0.f;
     uint32_t n = 0;
@@ -838,10 +848,10 @@ lstm_tcw_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_constan
         const int g = bp + gl * NB;
         const int acc = (int)(n & 1u);
         const int item = g * IG + il;
-        const bool valid = storing && item < p.B;
-        float pg[PP][4], skipv[PP];
+        const bool valid = item < p.B;
+        float pg[PPL][4], skipv[PPL];
 #pragma unroll
-        for (int e = 0; e < PP; ++e) {
+        for (int e = 0; e < PPL; ++e) {
           skipv[e] = 0.f;
 #pragma unroll
           for (int k = 0; k < 4; ++k) pg[e][k] = bias_r[e][k];
@@ -885,36 +895,49 @@ lstm_tcw_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_constan
         if (gl == 0 && warp == 4) LW_TRACE(2, t, 2)
 #pragma unroll
         for (int k = 0; k < CW; ++k) part[k] += __shfl_xor_sync(0xffffffffu, part[k], 16);
-        if (KP > 1) {
-          float* x = xs + (team * 16 + r) * CW;
-          if (!storing && lane < 16) {
+        // rec[e][k]: recurrent (+ x part) sum of gate k of this lane's pair e
+        float rec[PPL][4];
+        if (KP == 2) {
+          // columns [4 UWW kp', 4 UWW (kp' + 1)) of `part` belong to the units warp kp' of the team finishes: hand the partner's
+          // columns over, add the partner's contribution to the own ones
+          constexpr int HC = 4 * UWW;                                     // 8 columns per warp
+          float* xw = xs + ((team * 2 + (1 - kpart)) * 16 + r) * HC;      // slot read by the partner
+          const float* xr = xs + ((team * 2 + kpart) * 16 + r) * HC;      // slot written by the partner
+          if (lane < 16) {
 #pragma unroll
-            for (int k = 0; k < CW; k += 4) *reinterpret_cast<float4*>(x + k) = make_float4(part[k], part[k + 1], part[k + 2], part[k + 3]);
-          }
-          asm volatile("bar.sync %0, %1;" ::"r"(2 + team), "r"(32 * KP) : "memory");
-          if (storing) {
-#pragma unroll
-            for (int k = 0; k < CW; k += 4) {
-              const float4 xv = *reinterpret_cast<const float4*>(x + k);
-              part[k] += xv.x; part[k + 1] += xv.y; part[k + 2] += xv.z; part[k + 3] += xv.w;
+            for (int k = 0; k < HC; k += 4) {
+              float4 v;
+              if (kpart == 0) v = make_float4(part[HC + k], part[HC + k + 1], part[HC + k + 2], part[HC + k + 3]);
+              else v = make_float4(part[k], part[k + 1], part[k + 2], part[k + 3]);
+              *reinterpret_cast<float4*>(xw + k) = v;
             }
           }
-          asm volatile("bar.sync %0, %1;" ::"r"(2 + team), "r"(32 * KP) : "memory");
-          if (!storing) continue;
-        }
-        if (gl == 0 && warp == 4) LW_TRACE(2, t, 4)
-        unsigned int own[PP];
-        float h_new[PP];
-#pragma unroll
-        for (int e = 0; e < PP; ++e) {
-          float rec[4];
+          asm volatile("bar.sync %0, %1;" ::"r"(2 + team), "r"(64) : "memory");   // both K parts are in shared memory
+          const float4 xv = *reinterpret_cast<const float4*>(xr + lg * 4);        // the partner's part of this lane's unit
+          asm volatile("bar.sync %0, %1;" ::"r"(2 + team), "r"(64) : "memory");   // ... and read: the slots may be rewritten
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const float lo = part[e * 4 + k], hi = part[(PP + e) * 4 + k];
-            rec[k] = lane < 16 ? lo : hi;
+            const float o0 = part[k], o1 = part[4 + k], o2 = part[HC + k], o3 = part[HC + 4 + k];   // own sums of the team's 4 units
+            const float own = kpart == 0 ? (lane < 16 ? o0 : o1) : (lane < 16 ? o2 : o3);
+            rec[0][k] = own + (k == 0 ? xv.x : k == 1 ? xv.y : k == 2 ? xv.z : xv.w);
           }
-          float s_if[2] = {pg[e][0] + rec[0], pg[e][1] + rec[1]};
-          float s_go[2] = {2.f * (pg[e][2] + rec[2]), pg[e][3] + rec[3]};
+        } else {
+#pragma unroll
+          for (int e = 0; e < PPL; ++e)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float lo = part[e * 4 + k], hi = part[(PPL + e) * 4 + k];
+              rec[e][k] = lane < 16 ? lo : hi;
+            }
+        }
+        if (gl == 0 && warp == 4) LW_TRACE(2, t, 4)
+        unsigned int own[PPL];
+        float h_new[PPL];
+#pragma unroll
+        for (int e = 0; e < PPL; ++e) {
+          // gates i, f, o = sigmoid, g = tanh = 2 sigmoid(2 x) - 1: four sigmoids on two packed pairs
+          float s_if[2] = {pg[e][0] + rec[e][0], pg[e][1] + rec[e][1]};
+          float s_go[2] = {2.f * (pg[e][2] + rec[e][2]), pg[e][3] + rec[e][3]};
           sigmoid_pair(s_if);
           sigmoid_pair(s_go);
           float* cptr = cs + (gl * IG + il) * UPC + u0 + e;
@@ -928,32 +951,39 @@ lstm_tcw_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_constan
           own[e] = (unsigned int)__half_as_ushort(q1) | ((unsigned int)__half_as_ushort(q2) << 16);
         }
         if (gl == 0 && warp == 4) LW_TRACE(2, t, 5)
-        unsigned int oth[PP];
+        unsigned int oth[PPL];
 #pragma unroll
-        for (int e = 0; e < PP; ++e) oth[e] = __shfl_down_sync(0xffffffffu, own[e], 16);
-        if (lane < 16 && store_h) {   // the UW units of this item: one store per split part
-          const int kk = (ub * UPC + half * UW) % LT_KT;
+        for (int e = 0; e < PPL; ++e) oth[e] = __shfl_down_sync(0xffffffffu, own[e], 16);
+        if (lane < 16 && store_h) {   // the UWW units of this item this warp finished: one store per split part
+          // shared-memory image of K tile (UPC ub) / 64: row (g, iq, r), 16-byte chunk (unit % 64) / 8 swizzled by r & 7
+          const int kk = (ub * UPC + uw0) % LT_KT;
           const long long row = ((long long)g * LT_NKT + (ub * UPC) / LT_KT) * ROWS + iq * 32 + r;
           uint8_t* dst = hn + row * 128 + (((kk >> 3) ^ (r & 7)) << 4) + (kk & 7) * 2;
-          {
-            // words of the h1 row: this lane's PP units, then the PP units of lane + 16; same for the h2 row
-            unsigned int w1[PP], w2[PP];
+          if (PPL == 1) {
+            const unsigned int v1 = (own[0] & 0xffffu) | (oth[0] << 16);
+            const unsigned int v2 = (own[0] >> 16) | (oth[0] & 0xffff0000u);
+            asm volatile("st.global.cg.b32 [%0], %1;" ::"l"(dst), "r"(v1) : "memory");                // h1 row
+            asm volatile("st.global.cg.b32 [%0], %1;" ::"l"(dst + 16 * 128), "r"(v2) : "memory");     // h2 row (same r & 7)
+          } else {
+            // words of the h1 row: this lane's PPL units, then the PPL units of lane + 16; same for the h2 row
+            constexpr int PW = PPL >= 2 ? PPL : 2;
+            unsigned int w1[PW], w2[PW];
 #pragma unroll
-            for (int i = 0; i < PP / 2; ++i) {
+            for (int i = 0; i < PPL / 2; ++i) {
               w1[i] = (own[2 * i] & 0xffffu) | (own[2 * i + 1] << 16);
-              w1[PP / 2 + i] = (oth[2 * i] & 0xffffu) | (oth[2 * i + 1] << 16);
+              w1[PPL / 2 + i] = (oth[2 * i] & 0xffffu) | (oth[2 * i + 1] << 16);
               w2[i] = (own[2 * i] >> 16) | (own[2 * i + 1] & 0xffff0000u);
-              w2[PP / 2 + i] = (oth[2 * i] >> 16) | (oth[2 * i + 1] & 0xffff0000u);
+              w2[PPL / 2 + i] = (oth[2 * i] >> 16) | (oth[2 * i + 1] & 0xffff0000u);
             }
-            if (PP == 2) {
+            if (PPL == 2) {
               asm volatile("st.global.cg.v2.b32 [%0], {%1, %2};" ::"l"(dst), "r"(w1[0]), "r"(w1[1]) : "memory");
               asm volatile("st.global.cg.v2.b32 [%0], {%1, %2};" ::"l"(dst + 16 * 128), "r"(w2[0]), "r"(w2[1]) : "memory");
             } else {
-              asm volatile("st.global.cg.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(w1[0]), "r"(w1[1]), "r"(w1[PP == 4 ? 2 : 0]),
-                           "r"(w1[PP == 4 ? 3 : 0])
+              asm volatile("st.global.cg.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "r"(w1[0]), "r"(w1[1]), "r"(w1[PPL == 4 ? 2 : 0]),
+                           "r"(w1[PPL == 4 ? 3 : 0])
                            : "memory");
               asm volatile("st.global.cg.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 16 * 128), "r"(w2[0]), "r"(w2[1]),
-                           "r"(w2[PP == 4 ? 2 : 0]), "r"(w2[PP == 4 ? 3 : 0])
+                           "r"(w2[PPL == 4 ? 2 : 0]), "r"(w2[PPL == 4 ? 3 : 0])
                            : "memory");
             }
           }
@@ -961,9 +991,10 @@ lstm_tcw_kernel(const __grid_constant__ CUtensorMap map_w1, const __grid_constan
         __syncwarp();
         if (lane == 0) mbar_arrive(hst_bar(acc));   // -> publisher warp
         if (gl == 0 && warp == 4) LW_TRACE(2, t, 3)
+        // the layer output is nobody's business inside this kernel: stored after h_t is on its way
         if (valid && last_layer) {
 #pragma unroll
-          for (int e = 0; e < PP; ++e) {
+          for (int e = 0; e < PPL; ++e) {
             float y = h_new[e] + skipv[e];
             if (p.out_elu) y = elu1(y);
             p.out[(long long)item * p.out_stride + (long long)t * LT_H + ub * UPC + u0 + e] = y;
@@ -1213,6 +1244,7 @@ int launch_lstm_tc2(const float* pre, long long pre_item_stride, const void* w1h
   p.G = G;
   p.out_elu = out_elu;
   p.trace = g_lstm_tc_trace;
+  p.trace_cta = getenv("ECB_LSTM_TRACE_CTA") ? atoi(getenv("ECB_LSTM_TRACE_CTA")) : 64;
   ECB_CUDA(cudaMemsetAsync(workspace, 0, sizeof(__half) * (LW_RING1 + 2) * slot + sizeof(unsigned int) * (size_t)(2 * G * LT_NKT), s));
   CUtensorMap maps[3];
   if (make_w_map(&maps[0], w1h, 8) || make_w_map(&maps[1], w2x, 8) || make_w_map(&maps[2], w2h, 8)) return 1;
@@ -1251,6 +1283,7 @@ int launch_lstm_tc16(const float* pre, long long pre_item_stride, const void* w_
   p.G = G;
   p.out_elu = out_elu;
   p.trace = g_lstm_tc_trace;
+  p.trace_cta = getenv("ECB_LSTM_TRACE_CTA") ? atoi(getenv("ECB_LSTM_TRACE_CTA")) : 0;
   ECB_CUDA(cudaMemsetAsync(workspace, 0, sizeof(__half) * 2 * slot + sizeof(unsigned int) * (size_t)(G * LT_NKT), s));
   CUtensorMap maps[3];
   if (make_w_map(&maps[0], w_packed, 16)) return 1;
