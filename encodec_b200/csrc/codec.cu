@@ -403,7 +403,7 @@ Plan make_plan(const ecb_codec* c, long long n_items, long long length) {
   p.stat_doubles = c->spec.group_norm == 1 ? (size_t)n_items * (ceil_div_ll(length, 128) + 64) * 16 : 0;
   p.lstm_floats = (size_t)lstm_recurrent_workspace_floats((int)n_items, top_width(c->spec));
   p.total_bytes = (p.act_floats * p.n_act + p.lstm_floats) * sizeof(float) + 2 * p.stat_doubles * sizeof(double) +
-                  256 * 16;
+                  2 * ((size_t)n_items * 2 * sizeof(float) + 256) + 256 * 16;
   return p;
 }
 
@@ -429,6 +429,7 @@ struct Ctx {
   int n_items;
   float* buf[5];
   double* stat[2];
+  float* norm[2];   // [item][2] (mean, rstd) of the two raw tensors whose GroupNorm is applied by their consumers (tc_conv norm_mr)
   float* lstm_ws;
 };
 
@@ -654,6 +655,8 @@ int setup_ctx(Ctx& x, ecb_codec* c, long long n_items, long long length, void* w
   x.stat[0] = a.take<double>(pl.stat_doubles);
   x.stat[1] = a.take<double>(pl.stat_doubles);
   x.lstm_ws = a.take<float>(pl.lstm_floats);
+  x.norm[0] = a.take<float>((size_t)n_items * 2);
+  x.norm[1] = a.take<float>((size_t)n_items * 2);
   ECB_REQUIRE(a.ok, "internal: workspace plan overflow");
   x.c = c;
   x.st = reinterpret_cast<cudaStream_t>(stream);
@@ -720,6 +723,13 @@ int tap_act(cudaStream_t st, int stage, const Act& a, int n_items) {
   return 0;
 }
 
+// a raw conv output whose GroupNorm is applied by the convs that read it (tc_conv normalise-on-load)
+struct NormRef {
+  const float* mr;      // [item][2] (mean, rstd)
+  const float* gamma;   // [C]
+  const float* beta;
+};
+
 // One conv through the tensor-core kernel. `in` is read with reflect padding through its halo (zero_pad: plain
 // rows, out-of-range reads are zero); in1 is the optional fused 1x1 shortcut source. out_raw / out_elu are views
 // [M][N] per item that share one layout; with mirror_halo their reflected halo rows are written too.
@@ -727,8 +737,14 @@ int tc_run(Ctx& x, const float* hi, const float* lo, const float* bias, int K, i
            int stride, int pad_left, bool zero_pad, const Act* in1, float* out_raw, float* out_elu,
            long long out_item_stride, long long M, int mirror_halo, int split, int round_out, double* stats = nullptr,
            int* stat_slots = nullptr, int n_items_override = 0, int bn_max = 0, const TcCell* cell = nullptr,
-           const float* a0_lo = nullptr) {
+           const float* a0_lo = nullptr, const NormRef* norm = nullptr, int norm_elu = 0) {
   TcConvParams p;
+  if (norm) {
+    p.norm_mr = norm->mr;
+    p.norm_gamma = norm->gamma;
+    p.norm_beta = norm->beta;
+    p.norm_elu = norm_elu;
+  }
   p.bn_max = bn_max;
   p.cell = cell;
   p.a0_lo = a0_lo;
@@ -1193,19 +1209,59 @@ int tc_conv_gn(Ctx& x, const ConvW& cw, const Act& in, int C0, bool zero_pad, lo
 }
 
 // SEANetResnetBlock with GroupNorm: Y = ELU(GN(shortcut(X)) + GN(block3(ELU(GN(block1(E)))))). hbuf / sbuf are scratch.
-int tc_res_gn(Ctx& x, const ResW& r, const Act& X, const Act& E, float* hbuf, float* sbuf, Act& Y, int split = 3) {
+// GroupNorm applied by the consumers: up to this many channels a conv output that
+// feeds tensor-core convs stays RAW in HBM and is normalised (+ ELU) on the staged operand tile of each reader. The
+// bandwidth-bound levels gain (one write + one read of the tensor less, no ELU copy); above, the tensor-bound layers would pay
+// for the heavier operand transform. ECB_GN_FUSE_MAXC=0 restores the separate normalise pass everywhere.
+int gn_fuse_max_channels() {
+  const char* e = getenv("ECB_GN_FUSE_MAXC");
+  return e ? atoi(e) : 64;
+}
+bool gn_fused(const ecb_codec* c, int channels, int split) {
+  return c->spec.group_norm == 1 && split == 3 && channels <= gn_fuse_max_channels();
+}
+
+// for the per-stage taps of the tests: the normalised form of a raw tensor, materialised into scratch
+int tap_normed(Ctx& x, int stage, const Act& X, const GnSrc& a, float* scratch) {
+  if (!(g_tap.buf && g_tap.stage == stage)) return 0;
+  Act Nn = act_of(scratch, X.C, X.T, 0);
+  if (launch_gn_apply2(a, nullptr, Nn.row0(), nullptr, Nn.stride(), x.n_items, X.T, X.C, 1e-5f, x.st, 0, /*finalized=*/1)) return 1;
+  return tap_act(x.st, stage, Nn, x.n_items);
+}
+
+// nx != nullptr: X is a RAW conv output (halo-padded) and nx its statistics / affine parameters; E is not used
+int tc_res_gn(Ctx& x, const ResW& r, const Act& X, const Act& E, float* hbuf, float* sbuf, Act& Y, int split = 3,
+              const NormRef* nx = nullptr) {
   const int dim = r.sc.c_out;
   const bool ln = norm_is_ln(x.c->spec);
+  const ecb_spec& s = x.c->spec;
   Act H = act_of(hbuf, r.hid_pad, X.T, 0);
-  if (tc_conv_gn(x, r.b1, E, dim, false, X.T, nullptr, &H, 0, split, split)) return 1;
   Act S = act_of(sbuf, dim, X.T, 0);
   int slots3 = 0, slots_s = 0;
+  if (nx) {
+    // block1 reads ELU(GN(X)) through the reflected halo of the raw tensor; its raw output H is normalised (+ ELU) by block3
+    int slots1 = 0;
+    if (tc_run(x, r.b1.t_hi, r.b1.t_lo, r.b1.t_bias, r.b1.t_K, r.b1.t_N, X, dim, r.b1.k, 1, pad_left_of(s, r.b1.k, 1), false, nullptr,
+               H.row0(), nullptr, H.stride(), X.T, 0, 3, 0, x.stat[0], &slots1, 0, 0, nullptr, nullptr, nx, 1))
+      return 1;
+    GnSrc ah = gn_src(H.row0(), H.stride(), x.stat[0], slots1, (double)X.T * r.b1.c_out, r.b1.t_gamma, r.b1.t_beta);
+    if (launch_gn_finalize(ah, x.norm[1], x.n_items, 1e-5f, x.st)) return 1;
+    const NormRef nh{x.norm[1], r.b1.t_gamma, r.b1.t_beta};
+    if (tc_run(x, r.b3.t_hi, r.b3.t_lo, r.b3.t_bias, r.b3.t_K, r.b3.t_N, H, r.hid_pad, 1, 1, 0, true, nullptr, Y.row0(), nullptr,
+               Y.stride(), X.T, 0, 3, 0, x.stat[0], &slots3, 0, 0, nullptr, nullptr, &nh, 1))
+      return 1;
+    if (tc_run(x, r.sc.t_hi, r.sc.t_lo, r.sc.t_bias, r.sc.t_K, r.sc.t_N, X, dim, 1, 1, 0, true, nullptr, S.row0(), nullptr,
+               S.stride(), X.T, 0, 3, 0, x.stat[1], &slots_s, 0, 0, nullptr, nullptr, nx, 0))
+      return 1;
+  } else {
+  if (tc_conv_gn(x, r.b1, E, dim, false, X.T, nullptr, &H, 0, split, split)) return 1;
   if (tc_run(x, r.b3.t_hi, r.b3.t_lo, r.b3.t_bias, r.b3.t_K, r.b3.t_N, H, r.hid_pad, 1, 1, 0, true, nullptr, Y.row0(), nullptr,
              Y.stride(), X.T, 0, split, 0, ln ? nullptr : x.stat[0], &slots3))
     return 1;
   if (tc_run(x, r.sc.t_hi, r.sc.t_lo, r.sc.t_bias, r.sc.t_K, r.sc.t_N, X, dim, 1, 1, 0, true, nullptr, S.row0(), nullptr,
              S.stride(), X.T, 0, split, 0, ln ? nullptr : x.stat[1], &slots_s))
     return 1;
+  }
   GnSrc a = gn_src(S.row0(), S.stride(), x.stat[1], slots_s, (double)X.T * dim, r.sc.t_gamma, r.sc.t_beta);
   GnSrc b = gn_src(Y.row0(), Y.stride(), x.stat[0], slots3, (double)X.T * dim, r.b3.t_gamma, r.b3.t_beta);
   if (norm_apply(x, a, &b, nullptr, Y.row0(), Y.stride(), X.T, dim, 0, split == 1)) return 1;   // shortcut + block
@@ -1243,26 +1299,47 @@ int encoder_forward_tc_gn(Ctx& x, const float* xin, int64_t n_seg, int64_t lengt
   ci.halo = 0;
   ci.stats = norm_is_ln(s) ? nullptr : x.stat[0];
   if (launch_conv_in(ci, x.st)) return 1;
+  bool xf = gn_fused(c, ch, 3);   // X stays raw: the block's convs normalise it on load
+  NormRef nx{x.norm[0], c->enc_in.gamma, c->enc_in.beta};
   {
     GnSrc a = gn_src(X.row0(), X.stride(), x.stat[0], conv_in_stat_slots(ci), (double)length * ch, c->enc_in.gamma, c->enc_in.beta);
-    if (norm_apply(x, a, nullptr, X.row0(), E.row0(), X.stride(), length, ch)) return 1;
-    if (launch_halo_fill(nullptr, E.row0(), E.stride(), T, ch, x.n_items, ACT_HALO, 0, x.st)) return 1;
+    if (xf) {
+      if (launch_gn_finalize(a, x.norm[0], x.n_items, 1e-5f, x.st)) return 1;
+      if (launch_halo_fill(nullptr, X.row0(), X.stride(), T, ch, x.n_items, ACT_HALO, 0, x.st)) return 1;
+      if (tap_normed(x, 0, X, a, B)) return 1;
+    } else {
+      if (norm_apply(x, a, nullptr, X.row0(), E.row0(), X.stride(), length, ch)) return 1;
+      if (launch_halo_fill(nullptr, E.row0(), E.stride(), T, ch, x.n_items, ACT_HALO, 0, x.st)) return 1;
+      if (tap_act(x.st, 0, X, x.n_items)) return 1;
+    }
   }
-  if (tap_act(x.st, 0, X, x.n_items)) return 1;
   for (int i = 0; i < s.n_ratios; ++i) {
     Act Y = act_of(D, ch, T, ACT_HALO);
-    if (tc_res_gn(x, c->enc_res[i], X, E, Cb, F, Y)) return 1;
+    if (tc_res_gn(x, c->enc_res[i], X, E, Cb, F, Y, 3, xf ? &nx : nullptr)) return 1;
     if (tap_act(x.st, 1 + 2 * i, Y, x.n_items)) return 1;
     const ConvW& dw = c->enc_down[i];
     const long long T2 = ceil_div_ll(T, dw.stride);
     const bool last = (i == s.n_ratios - 1);
     Act X2 = act_of(A, dw.c_out, T2, ACT_HALO), E2 = act_of(B, dw.c_out, T2, ACT_HALO);
-    if (tc_conv_gn(x, dw, Y, ch, false, T2, &X2, last ? nullptr : &E2, 0)) return 1;
+    xf = !last && gn_fused(c, dw.c_out, 3);
+    if (xf) {
+      int slots = 0;
+      if (tc_run(x, dw.t_hi, dw.t_lo, dw.t_bias, dw.t_K, dw.t_N, Y, ch, dw.k, dw.stride, pad_left_of(s, dw.k, dw.stride), false, nullptr,
+                 X2.row0(), nullptr, X2.stride(), T2, 0, 3, 0, x.stat[0], &slots))
+        return 1;
+      GnSrc a = gn_src(X2.row0(), X2.stride(), x.stat[0], slots, (double)T2 * dw.c_out, dw.t_gamma, dw.t_beta);
+      if (launch_gn_finalize(a, x.norm[0], x.n_items, 1e-5f, x.st)) return 1;
+      if (launch_halo_fill(nullptr, X2.row0(), X2.stride(), T2, dw.c_out, x.n_items, ACT_HALO, 0, x.st)) return 1;
+      nx = NormRef{x.norm[0], dw.t_gamma, dw.t_beta};
+      if (tap_normed(x, 2 + 2 * i, X2, a, B)) return 1;
+    } else {
+      if (tc_conv_gn(x, dw, Y, ch, false, T2, &X2, last ? nullptr : &E2, 0)) return 1;
+      if (tap_act(x.st, 2 + 2 * i, X2, x.n_items)) return 1;
+    }
     X = X2;
     E = E2;
     T = T2;
     ch = dw.c_out;
-    if (tap_act(x.st, 2 + 2 * i, X, x.n_items)) return 1;
   }
   Act top = act_of(D, ch, T, ACT_HALO);
   if (s.lstm_layers) {
@@ -1317,6 +1394,27 @@ int decoder_forward_tc_gn(Ctx& x, const float* z_frames, int64_t n_frames, const
     int slots = 0;
     split = split_of(ch);                        // this transposed conv reads `ch` channels
     const int bsplit = split_of(uw.c_out);       // the residual block and the next conv read `c_out` channels
+    if (gn_fused(c, uw.c_out, bsplit)) {
+      // the raw transposed-conv output goes straight to its halo-padded place (left trim = shift of the store base, the
+      // spill-over on both sides lands in halo rows that halo_fill rewrites); statistics still cover the UNtrimmed output
+      Act X2 = act_of(B, uw.c_out, T2, ACT_HALO), E2 = act_of(D, uw.c_out, T2, ACT_HALO);
+      const long long shift = (long long)trim_left * uw.c_out;
+      if (tc_run(x, uw.t_hi, uw.t_lo, uw.t_bias, uw.t_K, uw.t_N, cur, ch, 2, 1, 1, true, nullptr, X2.row0() - shift, nullptr, X2.stride(),
+                 T + 1, 0, split, 0, x.stat[0], &slots))
+        return 1;
+      GnSrc a = gn_src(X2.row0(), X2.stride(), x.stat[0], slots, (double)(T + 1) * sN, uw.t_gamma, uw.t_beta);
+      if (launch_gn_finalize(a, x.norm[0], x.n_items, 1e-5f, x.st)) return 1;
+      if (launch_halo_fill(nullptr, X2.row0(), X2.stride(), T2, uw.c_out, x.n_items, ACT_HALO, 0, x.st)) return 1;
+      const NormRef nx{x.norm[0], uw.t_gamma, uw.t_beta};
+      T = T2;
+      ch = uw.c_out;
+      if (tap_normed(x, 102 + 2 * i, X2, a, D)) return 1;
+      Act Y = act_of(A, ch, T, 0);
+      if (tc_res_gn(x, c->dec_res[i], X2, E2, Cb, F, Y, 3, &nx)) return 1;
+      if (tap_act(x.st, 103 + 2 * i, Y, x.n_items)) return 1;
+      cur = Y;
+      continue;
+    }
     if (tc_run(x, uw.t_hi, uw.t_lo, uw.t_bias, uw.t_K, uw.t_N, cur, ch, 2, 1, 1, true, nullptr, R.row0(), nullptr, R.stride(),
                T + 1, 0, split, 0, norm_is_ln(s) ? nullptr : x.stat[0], &slots))
       return 1;

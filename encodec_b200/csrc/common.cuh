@@ -276,6 +276,13 @@ struct TcConvParams {
                               // latency-bound launches with few rows (the per-step GEMM of the step-wise LSTM)
   double* stats;              // nullptr, or [item][tc_stat_slots(p)][2] partial (sum, sum of squares) of the raw output
                               // (GroupNorm statistics; requires out_elu == nullptr, halo == 0, round_out == 0)
+  // GroupNorm of source 0 applied ON LOAD (split == 3, no a0_lo): a0 holds the RAW output of the producing conv and the operand
+  // the tensor core sees is act(((a - mean) * rstd) * gamma[c] + beta[c]), computed by the transform warps on the staged tile
+  // (the separate normalise pass and its tensor disappear). norm_mr = [item][2] (mean, rstd) from launch_gn_finalize.
+  const float* norm_mr = nullptr;
+  const float* norm_gamma = nullptr;   // [C0]
+  const float* norm_beta = nullptr;    // [C0]
+  int norm_elu = 0;                    // act = ELU (1) or identity (0)
 };
 int tc_stat_slots(const TcConvParams& p);   // partial-statistics slots per item a launch writes
 int launch_tc_conv(const TcConvParams& p, cudaStream_t stream);
@@ -364,7 +371,8 @@ int launch_gn_apply(const GnSrc& a, const GnSrc* b, float* out, int n_items, lon
 // general form: strided items, raw and/or ELU output (either may alias a.x / b->x element for element)
 // round_out: store TF32-rounded values (the consumer is a single-pass TF32 conv)
 int launch_gn_apply2(const GnSrc& a, const GnSrc* b, float* out_raw, float* out_elu, long long out_item_stride, int n_items,
-                     long long rows, int C, float eps, cudaStream_t s, int round_out = 0);
+                     long long rows, int C, float eps, cudaStream_t s, int round_out = 0, int finalized = 0);
+int launch_gn_finalize(const GnSrc& a, float* mr_out, int n_items, float eps, cudaStream_t s);
 // ConvLayerNorm (reference modules/norm.py:16-30, conv.py:44-46): LayerNorm over the C channels of every time step.
 // out = act(LN(a) [+ LN(b)]) over [n_items][rows][C]; GnSrc::partial / slots / count are unused. C in {32,...,1024} is
 // the stored row width, c_real <= C the channels that exist (the rest is zero padding, kept zero).

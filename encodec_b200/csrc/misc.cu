@@ -150,7 +150,7 @@ __global__ void segment_scale_kernel(const float* __restrict__ x, long long batc
 // nn.GroupNorm(1, C) applied after the fact (reference modules/conv.py:50,125,162): the conv kernels emit per-CTA partial
 // (sum, sumsq) in fp64; gn_finalize reduces an item's partials ONCE (one CTA per item and source) and leaves (mean, rstd)
 // in the first slot, which the streaming apply kernel then reads -- two doubles per CTA instead of the whole partial list.
-__global__ void __launch_bounds__(256) gn_finalize_kernel(GnSrc a, GnSrc b, float eps) {
+__global__ void __launch_bounds__(256) gn_finalize_kernel(GnSrc a, GnSrc b, float eps, float* mr_out = nullptr) {
   __shared__ double red[16];
   const GnSrc& s = blockIdx.y ? b : a;
   const int item = blockIdx.x;
@@ -181,6 +181,10 @@ __global__ void __launch_bounds__(256) gn_finalize_kernel(GnSrc a, GnSrc b, floa
     if (var < 0.0) var = 0.0;
     pp[0] = mean;
     pp[1] = 1.0 / sqrt(var + (double)eps);
+    if (mr_out && blockIdx.y == 0) {   // the float pair a consumer that normalises on load reads (tc_conv: TcConvParams::norm_mr)
+      mr_out[2 * item] = (float)pp[0];
+      mr_out[2 * item + 1] = (float)pp[1];
+    }
   }
 }
 
@@ -441,13 +445,13 @@ int launch_segment_scale(const float* x, long long batch_stride, long long seg_s
   return 0;
 }
 int launch_gn_apply2(const GnSrc& a, const GnSrc* b, float* out_raw, float* out_elu, long long out_item_stride, int n_items,
-                     long long rows, int C, float eps, cudaStream_t s, int round_out) {
+                     long long rows, int C, float eps, cudaStream_t s, int round_out, int finalized) {
   ECB_REQUIRE(C % 4 == 0 && (out_raw || out_elu), "gn_apply: C=%d", C);
   const long long n4 = rows * C / 4;
   dim3 grid((unsigned)min(cdiv(n4, 256 * 4), 4096LL), (unsigned)n_items);
   ProfScope prof(PROF_GN_APPLY, s, 0.0,
                  4.0 * (double)rows * C * n_items * ((b ? 2 : 1) + (out_raw ? 1 : 0) + (out_elu ? 1 : 0)));
-  gn_finalize_kernel<<<dim3((unsigned)n_items, b ? 2 : 1), 256, 0, s>>>(a, b ? *b : a, eps);
+  if (!finalized) gn_finalize_kernel<<<dim3((unsigned)n_items, b ? 2 : 1), 256, 0, s>>>(a, b ? *b : a, eps);
   const GnSrc bb = b ? *b : a;
 #define ECB_GN_LAUNCH(HB, R, E) gn_apply_kernel<HB, R, E><<<grid, 256, 0, s>>>(a, bb, out_raw, out_elu, out_item_stride, rows, C, round_out)
   if (b) {
@@ -460,6 +464,12 @@ int launch_gn_apply2(const GnSrc& a, const GnSrc* b, float* out_raw, float* out_
     else ECB_GN_LAUNCH(false, false, true);
   }
 #undef ECB_GN_LAUNCH
+  ECB_LAUNCHED();
+  return 0;
+}
+// statistics only: (mean, rstd) of every item -> mr_out [n_items][2] floats (and slot 0 of the partial list, as gn_apply expects)
+int launch_gn_finalize(const GnSrc& a, float* mr_out, int n_items, float eps, cudaStream_t s) {
+  gn_finalize_kernel<<<dim3((unsigned)n_items, 1), 256, 0, s>>>(a, a, eps, mr_out);
   ECB_LAUNCHED();
   return 0;
 }

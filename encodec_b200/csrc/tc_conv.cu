@@ -39,7 +39,7 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 32;                      // fp32 per K chunk = one 128-byte swizzle row
-constexpr int TC_THREADS = 384;              // 12 warps: TMA, MMA, 2 x transform, 8 x epilogue
+constexpr int TC_THREADS = 384;              // 12 warps: TMA, MMA, 2 x transform, 8 x epilogue (NT = 2; NT = 4: 14 warps)
 constexpr int STAGING_BYTES = 8 * 2048;     // 8 epilogue warps x [32 rows x 64 B]
 
 constexpr int A_ROWS = BM + 8;               // an A tile carries up to 8 extra rows: the taps of a conv are row shifts of it
@@ -79,6 +79,11 @@ struct TcArgs {
   TcCell cell;
   double* stats;            // [item][tiles_m][tiles_n][8 warps][2] or nullptr
   int group;                // K chunks per main-accumulator group (SPLIT == 1: all of them)
+  const float* norm_mr;     // GroupNorm of source 0 on load (TcConvParams::norm_mr), or nullptr
+  const float* norm_gamma;
+  const float* norm_beta;
+  int norm_elu;
+  int C0;                   // channels of source 0 (before folding)
 };
 
 using namespace tc;
@@ -132,8 +137,11 @@ __device__ __forceinline__ void copy_out_rows(const uint8_t* slot, int lane, flo
   }
 }
 
-template <int BN, int SPLIT>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// NT = transform warps (2 | 4). The narrow split-operand layers are bound by the transform role (remainder of every staged
+// element, and affine + ELU when GroupNorm is applied on load): they run with four; 448 threads leave 146 registers each, which
+// only the BN <= 64 instances fit.
+template <int BN, int SPLIT, int NT>
+__global__ void __launch_bounds__(TC_THREADS + 32 * (NT - 2), 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                const __grid_constant__ CUtensorMap map_bhi, const __grid_constant__ CUtensorMap map_blo,
                const __grid_constant__ CUtensorMap map_a0lo, const TcArgs p) {
@@ -167,7 +175,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   if (threadIdx.x == 0) {
     for (int s = 0; s < SA; ++s) {
       mbar_init(afull_bar(s), 1);
-      mbar_init(aready_bar(s), 2);   // one arrive per transform warp
+      mbar_init(aready_bar(s), NT);   // one arrive per transform warp
       mbar_init(aempty_bar(s), 1);
     }
     for (int s = 0; s < SB; ++s) {
@@ -294,13 +302,20 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         }
       }
     }
-  } else if (warp < 4) {
+  } else if (warp < 2 + NT) {
     // ================================ transform: a_lo = rn_tf32(a - trunc_tf32(a)) ================================
     if (SPLIT == 3) {
-      const int tt = threadIdx.x - 64;  // 0..63
+      constexpr int NTT = 32 * NT;      // transform threads
+      const int tt = threadIdx.x - 64;  // 0..NTT-1
       const int n4 = p.a_rows * (BK / 4);   // float4 per A tile (a multiple of 64)
       uint32_t ia = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        float nm_mean = 0.f, nm_rstd = 0.f;
+        if (p.norm_mr) {
+          const int item = (tile / p.tiles_n) / p.tiles_m;
+          nm_mean = __ldg(p.norm_mr + 2 * item);
+          nm_rstd = __ldg(p.norm_mr + 2 * item + 1);
+        }
         for (int ag = 0; ag < n_groups_a; ++ag, ++ia) {
           const int sa = (int)(ia % SA);
           mbar_wait(afull_bar(sa), (ia / SA) & 1u);
@@ -311,8 +326,45 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             if (lane == 0) mbar_arrive(aready_bar(sa));
             continue;
           }
+          if (p.norm_mr && ag < p.n_cb0) {
+            // GroupNorm on load: a <- act(((a - mean) * rstd) * gamma + beta) in place (the arithmetic of gn_apply, misc.cu),
+            // then the remainder. Thread tt always meets the same logical 16-byte chunk of a row: its float4s are 8 or 16 rows
+            // apart (NTT threads x 16 B = NTT / 8 rows of 128 B) and the 128-byte swizzle depends on the row only through row & 7.
+            const float mean = nm_mean, rstd = nm_rstd;
+            const int lc = (tt & 7) ^ ((tt >> 3) & 7);
+            const int c0 = (ag * BK) % p.C0 + lc * 4;
+            const float4 g = __ldg(reinterpret_cast<const float4*>(p.norm_gamma + c0));
+            const float4 be = __ldg(reinterpret_cast<const float4*>(p.norm_beta + c0));
+            float4* aw = reinterpret_cast<float4*>(smem_gen + sa * C::A_STAGE);
+            for (int i0 = tt; i0 < n4; i0 += 4 * NTT) {
+              float e[16];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int i = i0 + NTT * u;
+                const float4 v = i < n4 ? aw[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+                e[4 * u + 0] = (v.x - mean) * rstd * g.x + be.x;
+                e[4 * u + 1] = (v.y - mean) * rstd * g.y + be.y;
+                e[4 * u + 2] = (v.z - mean) * rstd * g.z + be.z;
+                e[4 * u + 3] = (v.w - mean) * rstd * g.w + be.w;
+              }
+              if (p.norm_elu) elu_vec<16>(e);
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int i = i0 + NTT * u;
+                if (i < n4) {
+                  aw[i] = make_float4(e[4 * u + 0], e[4 * u + 1], e[4 * u + 2], e[4 * u + 3]);
+                  alo[i] = make_float4(rn_tf32(e[4 * u + 0] - trunc_tf32(e[4 * u + 0])), rn_tf32(e[4 * u + 1] - trunc_tf32(e[4 * u + 1])),
+                                       rn_tf32(e[4 * u + 2] - trunc_tf32(e[4 * u + 2])), rn_tf32(e[4 * u + 3] - trunc_tf32(e[4 * u + 3])));
+                }
+              }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(aready_bar(sa));
+            continue;
+          }
 #pragma unroll 4
-          for (int i = tt; i < n4; i += 64) {
+          for (int i = tt; i < n4; i += NTT) {
             const float4 v = a[i];
             float4 r;
             r.x = rn_tf32(v.x - trunc_tf32(v.x));
@@ -332,10 +384,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     // Eight warps: warp w reads TMEM lane quadrant w % 4 (hardware rule) and, of every 32-column block, the 16-column
     // half (w - 4) / 4. The element-wise work (bias, ELU, optional TF32 rounding) is ~20 instructions per output
     // element, which is what sizes this warp group.
+    constexpr int EW0 = 2 + NT;   // first epilogue warp; the eight of them cover every (lane quadrant, column half) pair once
     const int quad = warp & 3;
-    const int half = (warp - 4) >> 2;
+    const int half = (warp - EW0) >> 2;
     const uint32_t lane_base = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 16);
-    uint8_t* slot_gen = smem_gen + STAGING_OFF + (warp - 4) * 2048;   // this warp's [32 rows x 64 B] staging slot
+    uint8_t* slot_gen = smem_gen + STAGING_OFF + (warp - EW0) * 2048;   // this warp's [32 rows x 64 B] staging slot
     uint32_t gcount = 0;
     const int out_mode = (p.out_raw ? 1 : 0) | (p.out_elu ? 2 : 0) | (p.round_out ? 4 : 0);
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -528,7 +581,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           dq += __shfl_xor_sync(0xffffffffu, dq, off);
         }
         if (lane == 0) {
-          double* sp = p.stats + (((long long)item * p.tiles_m + mt) * p.tiles_n + nt) * 16 + (warp - 4) * 2;
+          double* sp = p.stats + (((long long)item * p.tiles_m + mt) * p.tiles_n + nt) * 16 + (warp - EW0) * 2;
           sp[0] = ds;
           sp[1] = dq;
         }
@@ -565,12 +618,12 @@ __global__ void split_weights_kernel(const float* __restrict__ w, float* __restr
   }
 }
 
-template <int BN, int SPLIT>
+template <int BN, int SPLIT, int NT = 2>
 int launch_one(const CUtensorMap* maps, const TcArgs& a, int grid, cudaStream_t stream) {
   using C = Cfg<BN, SPLIT>;
   static DeviceOnce attr_set;
   if (!attr_set.done()) {
-    ECB_CUDA(cudaFuncSetAttribute(tc_conv_kernel<BN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    ECB_CUDA(cudaFuncSetAttribute(tc_conv_kernel<BN, SPLIT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set.mark();
   }
   TcArgs b = a;
@@ -585,7 +638,7 @@ int launch_one(const CUtensorMap* maps, const TcArgs& a, int grid, cudaStream_t 
     const int nch = a.n_cb0 * a.shifts + a.n_cb1;
     b.w_resident = (!off && a.tiles_n == 1 && nch <= C::B_STAGES) ? 1 : 0;
   }
-  tc_conv_kernel<BN, SPLIT><<<grid, TC_THREADS, C::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], b);
+  tc_conv_kernel<BN, SPLIT, NT><<<grid, TC_THREADS + 32 * (NT - 2), C::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], b);
   ECB_LAUNCHED();
   return 0;
 }
@@ -691,6 +744,13 @@ int launch_tc_conv(const TcConvParams& p, cudaStream_t stream) {
   CUtensorMap maps[5];
   TcArgs a;
   ECB_REQUIRE(!p.a0_lo || (p.split == 3 && !p.a1), "tc_conv: a0_lo needs split == 3 and a single source");
+  ECB_REQUIRE(!p.norm_mr || (p.split == 3 && !p.a0_lo && p.norm_gamma && p.norm_beta),
+              "tc_conv: normalise-on-load needs split == 3, no a0_lo, gamma and beta");
+  a.norm_mr = p.norm_mr;
+  a.norm_gamma = p.norm_gamma;
+  a.norm_beta = p.norm_beta;
+  a.norm_elu = p.norm_elu;
+  a.C0 = p.C0;
   a.lo_tma = p.a0_lo ? 1 : 0;
   // the taps of the conv are row shifts of one [a_rows x 32] tile per 32-channel block of the (folded) input row
   a.shifts = p.taps / s;
@@ -763,6 +823,18 @@ int launch_tc_conv(const TcConvParams& p, cudaStream_t stream) {
                         rows * p.N * ((p.out_raw ? 1 : 0) + (p.out_elu ? 1 : 0))));
 #define ECB_TC_CASE(BN_, SP_) \
   if (bn == BN_ && p.split == SP_) return launch_one<BN_, SP_>(maps, a, grid, stream);
+  {
+    // four transform warps for the narrow split-operand layers (ECB_TC_NT=2 keeps two: diagnostic)
+    static int nt4 = -1;
+    if (nt4 < 0) {
+      const char* e = getenv("ECB_TC_NT");
+      nt4 = (e && e[0] == '2') ? 0 : 1;
+    }
+    if (nt4 && p.split == 3 && !p.a0_lo && !p.cell) {
+      if (bn == 32) return launch_one<32, 3, 4>(maps, a, grid, stream);
+      if (bn == 64) return launch_one<64, 3, 4>(maps, a, grid, stream);
+    }
+  }
   ECB_TC_CASE(32, 3)
   ECB_TC_CASE(64, 3)
   ECB_TC_CASE(128, 3)
