@@ -783,6 +783,17 @@ int tc_run(Ctx& x, const float* hi, const float* lo, const float* bias, int K, i
   p.round_out = round_out;
   p.split = split;
   p.stats = stats;
+  if (bn_max == 0 && !stats && !cell) {
+    // latency-bound launch (few rows: a 1 s clip has 75 frames at the top of the stack): with the widest N tile a handful of
+    // CTAs would each stream megabytes of weights through one SM's ~50 B / cycle; narrower tiles spread the weight stream
+    // over more SMs. The arithmetic of an output element does not depend on the tile width. (Not with GroupNorm statistics:
+    // their partial sums are laid out per tile.)
+    const long long mt = ((M + 127) / 128) * p.n_items;
+    int bn = tc_pick_bn(N, split, 0);
+    const int sms = sm_count();
+    while (bn > 32 && mt * (N / bn) < sms) bn /= 2;
+    p.bn_max = bn;
+  }
   if (stat_slots) *stat_slots = tc_stat_slots(p);
   return launch_tc_conv(p, x.st);
 }
