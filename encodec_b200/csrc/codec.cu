@@ -1001,10 +1001,19 @@ int tc_lstm(Ctx& x, const std::vector<LstmLayerW>& layers, const Act& X, float* 
   const bool wave = tcrec && L == 2 && layers[1].x_f16 && lstm_tc2_supported(x.n_items, H) &&
                     (form == 2 || (form < 0 && x.n_items <= LSTM_WAVE_MAX));
   const bool u16 = tcrec && !wave && layers[0].r_f16_16 && (form == 16 || (form < 0 && x.n_items >= LSTM_U16_MIN));
+  // The input projection is a 1-tap GEMM over independent rows: when input and pre-gates are dense (no halo rows between
+  // items) all items form ONE row space, so a 150-frame segment of the 48 kHz model does not cost two 128-row tiles.
+  auto project = [&](const LstmLayerW& lw, const Act& in) {
+    if (in.halo == 0 && in.stride() == in.T * in.C && x.n_items > 1) {
+      Act flat = act_of(in.base, in.C, in.T * x.n_items, 0);
+      return tc_run(x, lw.t_hi, lw.t_lo, lw.bias, H, 4 * H, flat, H, 1, 1, 0, true, nullptr, pre.row0(), nullptr, 0, flat.T, 0, split, 0,
+                    nullptr, nullptr, /*n_items_override=*/1);
+    }
+    return tc_run(x, lw.t_hi, lw.t_lo, lw.bias, H, 4 * H, in, H, 1, 1, 0, true, nullptr, pre.row0(), nullptr, pre.stride(), in.T, 0, split,
+                  0);
+  };
   if (wave) {
-    if (tc_run(x, layers[0].t_hi, layers[0].t_lo, layers[0].bias, H, 4 * H, X, H, 1, 1, 0, true, nullptr, pre.row0(), nullptr,
-               pre.stride(), X.T, 0, split, 0))
-      return 1;
+    if (project(layers[0], X)) return 1;
     const float* u8 = layers[0].r_f16 + 4LL * H * H;   // second packing of launch_lstm_tc_pack: 8 units per CTA
     if (launch_lstm_tc2(pre.row0(), pre.stride(), u8, layers[1].x_f16, layers[1].r_f16 + 4LL * H * H, layers[1].bias, X.row0(), X.stride(),
                         out.row0(), out.stride(), x.n_items, (int)X.T, 1, x.lstm_ws, x.st))
@@ -1013,9 +1022,7 @@ int tc_lstm(Ctx& x, const std::vector<LstmLayerW>& layers, const Act& X, float* 
     return 0;
   }
   for (int l = 0; l < L; ++l) {
-    if (tc_run(x, layers[l].t_hi, layers[l].t_lo, layers[l].bias, H, 4 * H, *cur, H, 1, 1, 0, true, nullptr, pre.row0(), nullptr,
-               pre.stride(), X.T, 0, split, 0))
-      return 1;
+    if (project(layers[l], *cur)) return 1;
     const bool last = (l == L - 1);
     Act& dst = last ? out : h0;
     if (u16) {

@@ -137,7 +137,7 @@ __device__ __forceinline__ void copy_out_rows(const uint8_t* slot, int lane, flo
   }
 }
 
-// NT = transform warps (2 | 4). The narrow split-operand layers are bound by the transform role (remainder of every staged
+// NT = transform warps (2 | 4; eight were measured slower on the 48 kHz model: 61 vs 56 ms of narrow convs per config-3 step). The narrow split-operand layers are bound by the transform role (remainder of every staged
 // element, and affine + ELU when GroupNorm is applied on load): they run with four; 448 threads leave 146 registers each, which
 // only the BN <= 64 instances fit.
 template <int BN, int SPLIT, int NT>
