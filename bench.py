@@ -785,6 +785,9 @@ def main():
                 "clocks": out["clocks"], "e2e": out["e2e"], "gpu_launches": out["gpu_launches"], "roofline": roofline,
                 "kernels": classes, "whole_step": whole, "cpu_baseline": cpu_baseline, "variants": out.get("variants", {}),
                 "tf32_gemm_tflops_measured": tf32_peak, "also": also,
+                # operand tiles in which the fp16 pair conversion of the fp32-accurate convs clipped a value over this whole run
+                # (0: every activation stayed inside the fp16 range; ecb_f16_saturation_count)
+                "f16_pair_saturated_tiles": nat.f16_saturation_count(),
             }
     if rank == 0 and line is not None:
         emit(line)

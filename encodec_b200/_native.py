@@ -38,6 +38,7 @@ SIGNATURES = {
     "ecb_launch_count": (C.c_int64, []),
     "ecb_debug_tap": (None, [C.c_void_p, C.c_int64, C.c_int32]),
     "ecb_debug_lstm_trace": (None, [C.c_void_p]),
+    "ecb_f16_saturation_count": (C.c_int64, [C.c_int32]),
     "ecb_debug_lstm_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int64, C.c_int64]),
     "ecb_debug_lstm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p]),
     "ecb_debug_tc_conv": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_int32,
@@ -204,6 +205,12 @@ def shared_workspace(device: torch.device, nbytes: int) -> torch.Tensor:
 
 def release_workspaces() -> None:
     _WORKSPACES.clear()
+
+
+def f16_saturation_count(reset: bool = False) -> int:
+    """Operand tiles in which the fp16 pair conversion of the fp32-accurate convs clipped a value (|a| > 65504) since the last
+    reset; 0 unless a model's activations leave the fp16 range (then run with ECB_F16_PAIR=0)."""
+    return int(lib.ecb_f16_saturation_count(1 if reset else 0))
 
 
 def profile_begin() -> None:

@@ -8,6 +8,9 @@
 #include <vector>
 
 #include "../../include/encodec_b200.h"
+#include <mutex>
+#include <unordered_map>
+
 #include "common.cuh"
 
 namespace ecb {
@@ -242,10 +245,24 @@ inline int round_up32(int v) { return (v + 31) / 32 * 32; }
 
 // Split weights for the tensor-core kernel from the CUDA-core packing w [K][N] (+ bias [N]); N padded to n_pad
 // with zero rows (a 16-wide hidden layer runs as 32 columns whose upper half is exactly zero).
+// fp16 pair of a layer's weights, found through its TF32 `hi` array (tc_run switches a split-operand layer to the fp16 scheme
+// without every call site carrying two more pointers). Entries are overwritten when an address is reused by a later codec.
+std::mutex g_f16_mu;
+std::unordered_map<const float*, std::pair<const void*, const void*>> g_f16_of;
+
 int prepare_tc(ecb_codec* c, const float* w, const float* bias, int K, int N, int n_pad, float** hi, float** lo,
                float** bias_pad, cudaStream_t st) {
   if (dev_alloc(c, hi, (long long)K * n_pad) || dev_alloc(c, lo, (long long)K * n_pad)) return 1;
   if (launch_split_weights(w, *hi, *lo, K, N, K, n_pad, st)) return 1;
+  {
+    float* h12 = nullptr;   // two [n_pad][K] half arrays = K * n_pad floats
+    if (dev_alloc(c, &h12, (long long)K * n_pad)) return 1;
+    void* h1 = h12;
+    void* h2 = reinterpret_cast<char*>(h12) + (size_t)K * n_pad * 2;
+    if (launch_split_weights_f16(w, h1, h2, K, N, K, n_pad, st)) return 1;
+    std::lock_guard<std::mutex> lk(g_f16_mu);
+    g_f16_of[*hi] = {h1, h2};
+  }
   if (bias_pad) {
     if (dev_alloc(c, bias_pad, n_pad)) return 1;
     ECB_CUDA(cudaMemsetAsync(*bias_pad, 0, sizeof(float) * n_pad, st));
@@ -730,6 +747,21 @@ struct NormRef {
   const float* beta;
 };
 
+// Which fp32-accurate layers run on fp16 pair operands instead of split TF32 (tc_conv.cu, SPLIT = 2): ECB_F16_PAIR=0 none,
+// 1 the tensor-bound ones (>= 128 channels on either side), 2 (default) all. Measured (B200, config 2 / config 3 step):
+// 31.0 / 152.3 ms with 0, 29.9 / 145.1 with 1, 29.8 / 143.4 with 2 (before the four-warp transform of the wide tiles).
+bool f16_pair_wanted(int K, int N, int C0, int C1) {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("ECB_F16_PAIR");
+    mode = e ? atoi(e) : 2;
+  }
+  (void)K;
+  if (mode <= 0) return false;
+  if (mode >= 2) return true;
+  return !(C0 <= 64 && N <= 64 && C1 <= 64);
+}
+
 // One conv through the tensor-core kernel. `in` is read with reflect padding through its halo (zero_pad: plain
 // rows, out-of-range reads are zero); in1 is the optional fused 1x1 shortcut source. out_raw / out_elu are views
 // [M][N] per item that share one layout; with mirror_halo their reflected halo rows are written too.
@@ -772,6 +804,15 @@ int tc_run(Ctx& x, const float* hi, const float* lo, const float* bias, int K, i
   ECB_REQUIRE(K == taps * C0 + p.C1, "tc_run: weight K=%d does not match taps*C0 + C1 = %d", K, taps * C0 + p.C1);
   p.w_hi = hi;
   p.w_lo = lo;
+  if (split == 3 && !cell && !a0_lo && f16_pair_wanted(K, N, C0, in1 ? in1->C : 0)) {
+    std::lock_guard<std::mutex> lk(g_f16_mu);
+    auto it = g_f16_of.find(hi);
+    if (it != g_f16_of.end()) {
+      split = 2;
+      p.w_hi = reinterpret_cast<const float*>(it->second.first);
+      p.w_lo = reinterpret_cast<const float*>(it->second.second);
+    }
+  }
   p.bias = bias;
   p.out_raw = out_raw;
   p.out_elu = out_elu;
@@ -1942,7 +1983,8 @@ int ecb_debug_tc_conv(const float* a0, int64_t a0_item_stride, int32_t C0, int64
   float *hi = nullptr, *lo = nullptr;
   ECB_CUDA(cudaMalloc((void**)&hi, sizeof(float) * (size_t)ktot * N));
   ECB_CUDA(cudaMalloc((void**)&lo, sizeof(float) * (size_t)ktot * N));
-  int rc = launch_split_weights(w, hi, lo, ktot, N, ktot, N, st);
+  int rc = split == 2 ? launch_split_weights_f16(w, hi, lo, ktot, N, ktot, N, st)   // the two half arrays fit the float buffers
+                      : launch_split_weights(w, hi, lo, ktot, N, ktot, N, st);
   if (!rc) {
     TcConvParams p;
     p.a0 = a0; p.a0_item_stride = a0_item_stride; p.C0 = C0; p.a0_first = a0_first; p.a0_rows = a0_rows;
@@ -1964,6 +2006,8 @@ int ecb_debug_tc_conv(const float* a0, int64_t a0_item_stride, int32_t C0, int64
   }
   return rc;
 }
+
+int64_t ecb_f16_saturation_count(int32_t reset) { return tc_f16_saturation_count(reset); }
 
 int64_t ecb_packed_bytes(int64_t n_codebooks, int64_t n_frames, int32_t bits) {
   return (n_codebooks * n_frames * bits + 7) / 8;

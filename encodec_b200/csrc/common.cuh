@@ -267,7 +267,9 @@ struct TcConvParams {
   int n_items;
   int halo;                   // also write the reflected rows -1..-halo and M..M+halo-1 of each output (0: none)
   int round_out;              // round stored values to TF32 (for split == 1 consumers)
-  int split;                  // 3: fp32-accurate split operands; 1: single TF32 pass
+  int split;                  // 3: fp32-accurate split TF32 operands; 1: single TF32 pass; 2: fp32-accurate fp16 PAIR operands
+                              // (w_hi / w_lo then point at the [N][Ktot] __half arrays of launch_split_weights_f16; activations
+                              // beyond +-65504 saturate, so callers use it for tensors whose range they know)
   const float* a0_lo = nullptr;  // optional: the TF32 remainder of source 0, rn_tf32(a - trunc_tf32(a)), same layout as a0,
                               // written by the producer of a0 (split == 3, no second source): the tile then comes in
                               // by TMA as well and the in-kernel operand transform is skipped
@@ -287,6 +289,8 @@ struct TcConvParams {
 int tc_stat_slots(const TcConvParams& p);   // partial-statistics slots per item a launch writes
 int launch_tc_conv(const TcConvParams& p, cudaStream_t stream);
 int launch_split_weights(const float* w, float* hi, float* lo, int K, int N, int K_pad, int N_pad, cudaStream_t s);
+int launch_split_weights_f16(const float* w, void* h1, void* h2, int K, int N, int K_pad, int N_pad, cudaStream_t s);
+long long tc_f16_saturation_count(int reset);
 int tc_pick_bn(int N, int split, int bn_max = 0);
 
 // Fused SEANetResnetBlock at 32 channels (tc_res.cu): Y = ELU(shortcut(X) + block3(ELU(block1(ELU(X))))), X read once.

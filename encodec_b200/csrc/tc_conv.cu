@@ -29,6 +29,7 @@
 //     an output may be written raw, ELU'd or both (a residual block consumes x through its shortcut and
 //     ELU(x) through its first conv) and its reflected halo rows are written directly.
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -45,18 +46,30 @@ constexpr int STAGING_BYTES = 8 * 2048;     // 8 epilogue warps x [32 rows x 64 
 constexpr int A_ROWS = BM + 8;               // an A tile carries up to 8 extra rows: the taps of a conv are row shifts of it
 constexpr int A_TILE = A_ROWS * BK * 4;      // 17 KB
 
+constexpr int A16_TILE = A_ROWS * BK * 2;    // fp16 image of an A tile: rows of 64 bytes (SWIZZLE_64B)
+
+// fp16 pair operands: how many operand tiles held a value that the saturating conversion clipped to +-65504 (a model whose
+// activations leave the fp16 range must run with ECB_F16_PAIR=0). Read and cleared through ecb_f16_saturation_count.
+__device__ unsigned int g_f16_sat_tiles = 0;
+
+// SPLIT = 3: split-operand TF32 (a, a_lo; w_hi, w_lo). SPLIT = 1: one TF32 pass. SPLIT = 2: fp16 PAIR operands (the scheme of
+// lstm_tc.cu): a = a1 + 2^-11 a2, w = w1 + 2^-11 w2 with fp16 a1, a2, w1, w2 -- the same three products and the same dropped
+// 2^-22 term as SPLIT = 3 (fp16 carries TF32's 11 significand bits; its products are exact in the fp32 accumulator), but one
+// tcgen05.mma.kind::f16 covers K = 16 instead of 8 and reads half the operand bytes: half the tensor time of the wide layers.
+// fp16 spans 6e-5 .. 65504 at full precision, below that its subnormals (the remainder a2 keeps the absolute error at
+// 2^-35); values beyond +-65504 saturate (satfinite conversion) -- see TcConvParams::split.
 template <int BN, int SPLIT>
 struct Cfg {
-  static constexpr int B_BYTES = BN * BK * 4;
-  static constexpr int A_STAGE = (SPLIT == 3) ? 2 * A_TILE : A_TILE;     // a (+ a_lo)
-  static constexpr int B_STAGE = (SPLIT == 3) ? 2 * B_BYTES : B_BYTES;   // w_hi (+ w_lo, directly behind it)
+  static constexpr int B_BYTES = (SPLIT == 2) ? BN * BK * 2 : BN * BK * 4;
+  static constexpr int A_STAGE = (SPLIT == 3) ? 2 * A_TILE : (SPLIT == 2 ? A_TILE + 2 * A16_TILE : A_TILE);   // a (+ a_lo | + a1, a2)
+  static constexpr int B_STAGE = (SPLIT != 1) ? 2 * B_BYTES : B_BYTES;   // w_hi (+ w_lo, directly behind it) | w1, w2
   static constexpr int BUDGET = 227 * 1024 - STAGING_BYTES - 1024 - 512;
   // A ring: 3 stages with wide tiles, 4 otherwise; the B ring takes what is left (at most 8 stages)
   static constexpr int A_STAGES = (BN >= 128) ? 3 : 4;
   static constexpr int SB0 = (BUDGET - A_STAGES * A_STAGE) / B_STAGE;
   static constexpr int B_STAGES = SB0 > 8 ? 8 : SB0;
   static constexpr int SMEM_BYTES = A_STAGES * A_STAGE + B_STAGES * B_STAGE + STAGING_BYTES + 1024 + 512;
-  static constexpr int TMEM_COLS = (SPLIT == 3) ? 4 * BN : 2 * BN;   // two main (+ two correction) accumulators
+  static constexpr int TMEM_COLS = (SPLIT != 1) ? 4 * BN : 2 * BN;   // two main (+ two correction) accumulators
   static_assert(B_STAGES >= 2, "pipeline too shallow");
   static_assert(TMEM_COLS <= 512, "TMEM overflow");
 };
@@ -199,7 +212,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
   // TMEM columns of accumulator buffer b: SPLIT == 3: [main | correction] = 2 BN columns, SPLIT == 1: BN columns
-  constexpr int ACC_COLS = (SPLIT == 3) ? 2 * BN : BN;
+  constexpr int ACC_COLS = (SPLIT != 1) ? 2 * BN : BN;
   auto main_col = [&](int b) { return (uint32_t)(b * ACC_COLS); };
 
   if (warp == 0) {
@@ -237,7 +250,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             if (elect_one()) {
               mbar_expect_tx(bfull_bar(sb), C::B_STAGE);
               tma_load_2d(dst, &map_bhi, bfull_bar(sb), k0, nt * BN);
-              if (SPLIT == 3) tma_load_2d(dst + C::B_BYTES, &map_blo, bfull_bar(sb), k0, nt * BN);
+              if (SPLIT != 1) tma_load_2d(dst + C::B_BYTES, &map_blo, bfull_bar(sb), k0, nt * BN);
             }
             __syncwarp();
           }
@@ -253,10 +266,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     // TMEM buffers. Per K step: D[main | corr] (+)= a * [w_hi | w_lo] (one MMA, N = 2 BN: w_lo's tile follows w_hi's
     // in shared memory) and D[corr] += a_lo * w_hi. The whole warp stays converged and one elected lane issues.
     {
-      constexpr uint32_t idesc = umma_idesc_tf32(BM, BN);
-      constexpr uint32_t idesc2 = umma_idesc_tf32(BM, SPLIT == 3 ? 2 * BN : BN);
-      // descriptors: constant high word (SBO, version, SWIZZLE_128B) + start address >> 4 in the low word
-      constexpr uint32_t DESC_HI = 64u | (1u << 14) | (2u << 29);
+      // kind::f16 instruction descriptor: D fp32, A / B fp16 (format 0), K-major
+      constexpr uint32_t idesc = SPLIT == 2 ? ((1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24)) : umma_idesc_tf32(BM, BN);
+      constexpr uint32_t idesc2 = SPLIT == 2 ? ((1u << 4) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)(BM >> 4) << 24))
+                                             : umma_idesc_tf32(BM, SPLIT == 3 ? 2 * BN : BN);
+      // descriptors: constant high word (SBO, version, swizzle mode) + start address >> 4 in the low word. fp16 tiles have rows of
+      // 64 bytes: SWIZZLE_64B (layout type 4), 8-row groups 512 bytes apart
+      constexpr uint32_t DESC_HI = SPLIT == 2 ? (32u | (1u << 14) | (4u << 29)) : (64u | (1u << 14) | (2u << 29));
       auto mk_desc = [](uint32_t addr, uint32_t hi) { return ((uint64_t)hi << 32) | (uint64_t)(((addr & 0x3FFFFu) >> 4) | (1u << 16)); };
       uint32_t ia = 0, ib = 0, gcount = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -265,7 +281,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         for (int ag = 0; ag < n_groups_a; ++ag, ++ia) {
           const int sa = (int)(ia % SA);
           mbar_wait(afull_bar(sa), (ia / SA) & 1u);
-          if (SPLIT == 3) mbar_wait(aready_bar(sa), (ia / SA) & 1u);
+          if (SPLIT != 1) mbar_wait(aready_bar(sa), (ia / SA) & 1u);
           const uint32_t a_addr = a_ring + sa * C::A_STAGE;
           const int nj = ag < p.n_cb0 ? p.shifts : 1;
           for (int j = 0; j < nj; ++j, ++ib, ++c) {
@@ -279,14 +295,27 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
               // tap j of the conv = the A tile read j rows further down: the start moves by j * 128 bytes. The 128-byte
               // swizzle is a function of the absolute shared-memory address (verified on B200: with the descriptor's
               // base-offset field left 0 every row shift reads the rows TMA wrote), so nothing else changes.
+              const uint64_t db0 = mk_desc(b_ring + sb * C::B_STAGE, DESC_HI);
+              if (SPLIT == 2) {
+                // fp16 pair: rows of 64 bytes (a tap = 64 bytes further), K = 16 per instruction: two steps per 32-channel chunk.
+                // D[main | corr] (+)= a1 [w1 | w2], D[corr] += a2 w1; the epilogue adds corr 2^-11.
+                const uint32_t a_sh = a_addr + A_TILE + (uint32_t)j * 64u;
+                const uint64_t da1 = mk_desc(a_sh, DESC_HI);
+                const uint64_t da2 = mk_desc(a_sh + A16_TILE, DESC_HI);
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) {
+                  tcgen05_mma_f16(d_main, da1 + 2u * k, db0 + 2u * k, idesc2, (in_group > 0 || k > 0) ? 1u : 0u);
+                  tcgen05_mma_f16(d_main + BN, da2 + 2u * k, db0 + 2u * k, idesc, 1u);
+                }
+              } else {
               const uint32_t a_sh = a_addr + (uint32_t)j * 128u;
               const uint64_t da0 = mk_desc(a_sh, DESC_HI);
               const uint64_t dal0 = mk_desc(a_sh + A_TILE, DESC_HI);
-              const uint64_t db0 = mk_desc(b_ring + sb * C::B_STAGE, DESC_HI);
 #pragma unroll
               for (int k = 0; k < BK / 8; ++k) {
                 tcgen05_mma_tf32(d_main, da0 + 2u * k, db0 + 2u * k, idesc2, (in_group > 0 || k > 0) ? 1u : 0u);
                 if (SPLIT == 3) tcgen05_mma_tf32(d_main + BN, dal0 + 2u * k, db0 + 2u * k, idesc, 1u);
+              }
               }
               if (!p.w_resident) tcgen05_commit(bempty_bar(sb));               // weight stage free once these MMAs have read it
               if (close_group) tcgen05_commit(mainf_bar((int)(gcount & 1u)));  // K group complete -> epilogue
@@ -304,7 +333,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     }
   } else if (warp < 2 + NT) {
     // ================================ transform: a_lo = rn_tf32(a - trunc_tf32(a)) ================================
-    if (SPLIT == 3) {
+    if (SPLIT != 1) {
       constexpr int NTT = 32 * NT;      // transform threads
       const int tt = threadIdx.x - 64;  // 0..NTT-1
       const int n4 = p.a_rows * (BK / 4);   // float4 per A tile (a multiple of 64)
@@ -326,6 +355,25 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             if (lane == 0) mbar_arrive(aready_bar(sa));
             continue;
           }
+          // SPLIT == 2: the fp16 pair of one float4 (four channels of row i >> 3): a1 = fp16(v) (saturating), a2 = fp16((v - a1) 2^11),
+          // stored at the SWIZZLE_64B position of logical 8-byte slot lc8 of the 64-byte row
+          uint8_t* a16 = smem_gen + sa * C::A_STAGE + A_TILE;
+          __half2 hmax = __float2half2_rn(0.f);   // largest |a1| this thread wrote to the tile: 65504 = the conversion saturated
+          auto store_pair = [&](int i, const float4& v) {
+            const int r = i >> 3;
+            const int lc8 = (i & 7) ^ (r & 7);
+            uint32_t h01, h23, l01, l23;
+            asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h01) : "f"(v.y), "f"(v.x));
+            asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h23) : "f"(v.w), "f"(v.z));
+            const float2 f01 = __half22float2(*reinterpret_cast<const __half2*>(&h01));
+            const float2 f23 = __half22float2(*reinterpret_cast<const __half2*>(&h23));
+            asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(l01) : "f"((v.y - f01.y) * 2048.f), "f"((v.x - f01.x) * 2048.f));
+            asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(l23) : "f"((v.w - f23.y) * 2048.f), "f"((v.z - f23.x) * 2048.f));
+            const uint32_t off = (uint32_t)r * 64u + ((uint32_t)((lc8 >> 1) ^ ((r >> 1) & 3)) << 4) + ((uint32_t)(lc8 & 1) << 3);
+            hmax = __hmax2(hmax, __hmax2(__habs2(*reinterpret_cast<const __half2*>(&h01)), __habs2(*reinterpret_cast<const __half2*>(&h23))));
+            *reinterpret_cast<uint2*>(a16 + off) = make_uint2(h01, h23);
+            *reinterpret_cast<uint2*>(a16 + A16_TILE + off) = make_uint2(l01, l23);
+          };
           if (p.norm_mr && ag < p.n_cb0) {
             // GroupNorm on load: a <- act(((a - mean) * rstd) * gamma + beta) in place (the arithmetic of gn_apply, misc.cu),
             // then the remainder. Thread tt always meets the same logical 16-byte chunk of a row: its float4s are 8 or 16 rows
@@ -351,18 +399,44 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
 #pragma unroll
               for (int u = 0; u < 4; ++u) {
                 const int i = i0 + NTT * u;
-                if (i < n4) {
+                if (i < n4 && SPLIT == 2) {
+                  store_pair(i, make_float4(e[4 * u + 0], e[4 * u + 1], e[4 * u + 2], e[4 * u + 3]));
+                } else if (i < n4) {
                   aw[i] = make_float4(e[4 * u + 0], e[4 * u + 1], e[4 * u + 2], e[4 * u + 3]);
                   alo[i] = make_float4(rn_tf32(e[4 * u + 0] - trunc_tf32(e[4 * u + 0])), rn_tf32(e[4 * u + 1] - trunc_tf32(e[4 * u + 1])),
                                        rn_tf32(e[4 * u + 2] - trunc_tf32(e[4 * u + 2])), rn_tf32(e[4 * u + 3] - trunc_tf32(e[4 * u + 3])));
                 }
               }
             }
+            if (SPLIT == 2 && __hge(__hmax(__low2half(hmax), __high2half(hmax)), __ushort_as_half((unsigned short)0x7BFF)))
+              atomicAdd(&g_f16_sat_tiles, 1u);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(aready_bar(sa));
             continue;
           }
+          if (SPLIT == 2) {
+            // thread tt meets the same swizzled slot of every row it visits (its rows are NTT / 8 = 8 or 16 apart, the swizzles
+            // depend on row & 7): the store address just advances by a constant
+            const int r0 = tt >> 3;
+            const int lc8 = (tt & 7) ^ (r0 & 7);
+            uint8_t* d = a16 + r0 * 64 + ((((lc8 >> 1) ^ ((r0 >> 1) & 3)) << 4) + ((lc8 & 1) << 3));
+#pragma unroll 4
+            for (int i = tt; i < n4; i += NTT, d += (NTT / 8) * 64) {
+              const float4 v = a[i];
+              uint32_t h01, h23, l01, l23;
+              asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h01) : "f"(v.y), "f"(v.x));
+              asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h23) : "f"(v.w), "f"(v.z));
+              const float2 f01 = __half22float2(*reinterpret_cast<const __half2*>(&h01));
+              const float2 f23 = __half22float2(*reinterpret_cast<const __half2*>(&h23));
+              asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(l01) : "f"((v.y - f01.y) * 2048.f), "f"((v.x - f01.x) * 2048.f));
+              asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(l23) : "f"((v.w - f23.y) * 2048.f), "f"((v.z - f23.x) * 2048.f));
+              *reinterpret_cast<uint2*>(d) = make_uint2(h01, h23);
+              *reinterpret_cast<uint2*>(d + A16_TILE) = make_uint2(l01, l23);
+              hmax = __hmax2(hmax, __hmax2(__habs2(*reinterpret_cast<const __half2*>(&h01)), __habs2(*reinterpret_cast<const __half2*>(&h23))));
+            }
+            if (__hge(__hmax(__low2half(hmax), __high2half(hmax)), __ushort_as_half((unsigned short)0x7BFF))) atomicAdd(&g_f16_sat_tiles, 1u);
+          } else {
 #pragma unroll 4
           for (int i = tt; i < n4; i += NTT) {
             const float4 v = a[i];
@@ -372,6 +446,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             r.z = rn_tf32(v.z - trunc_tf32(v.z));
             r.w = rn_tf32(v.w - trunc_tf32(v.w));
             alo[i] = r;   // same offset => same swizzled position
+          }
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the tensor core
           __syncwarp();
@@ -509,8 +584,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       const int n_groups = (nch + p.group - 1) / p.group;
       const int mb_last = (int)((gcount + (uint32_t)n_groups - 1u) & 1u);
       const uint32_t src_col = main_col(mb_last);
-      bool add_corr = (SPLIT == 3);
-      if (SPLIT == 3 && n_groups > 1) {
+      bool add_corr = (SPLIT != 1);
+      if (SPLIT != 1 && n_groups > 1) {
         // several K groups: re-accumulate main + correction in registers (round-to-nearest), park the sum back in the
         // last group's TMEM buffer and stream it out from there
         float acc[BN / 2];
@@ -526,7 +601,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              const float t = __uint_as_float(v[i]) + __uint_as_float(w[i]);
+              const float t = SPLIT == 2 ? fmaf(__uint_as_float(w[i]), 1.f / 2048.f, __uint_as_float(v[i]))
+                                         : __uint_as_float(v[i]) + __uint_as_float(w[i]);
               acc[cc / 2 + i] = g == 0 ? t : acc[cc / 2 + i] + t;
             }
           }
@@ -562,7 +638,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           tcgen05_ld16(lane_base + src_col + (uint32_t)(BN + cc), v);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-          for (int i = 0; i < 16; ++i) o[i] += __uint_as_float(v[i]);
+          for (int i = 0; i < 16; ++i) o[i] = SPLIT == 2 ? fmaf(__uint_as_float(v[i]), 1.f / 2048.f, o[i]) : o[i] + __uint_as_float(v[i]);
         }
         if (cc + 32 >= BN) {   // accumulator fully read: hand it back before the stores
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -614,6 +690,27 @@ __global__ void split_weights_kernel(const float* __restrict__ w, float* __restr
       const float h = rn_tf32(v);
       hi[(long long)n * K_pad + k] = h;
       lo[(long long)n * K_pad + k] = rn_tf32(v - h);
+    }
+  }
+}
+
+// the fp16 pair of the same weights: h1 = fp16(w), h2 = fp16((w - h1) 2^11), both [N_pad][K_pad] halves, K contiguous
+__global__ void split_weights_f16_kernel(const float* __restrict__ w, __half* __restrict__ h1, __half* __restrict__ h2, int K, int N,
+                                         int K_pad, int N_pad) {
+  __shared__ float tile[32][33];
+  const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int k = k0 + i, n = n0 + threadIdx.x;
+    tile[i][threadIdx.x] = (k < K && n < N) ? w[(long long)k * N + n] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int n = n0 + i, k = k0 + threadIdx.x;
+    if (n < N_pad && k < K_pad) {
+      const float v = tile[threadIdx.x][i];
+      const __half a = __float2half_rn(v);
+      h1[(long long)n * K_pad + k] = a;
+      h2[(long long)n * K_pad + k] = __float2half_rn((v - __half2float(a)) * 2048.f);
     }
   }
 }
@@ -682,12 +779,13 @@ int make_tensor_map(CUtensorMap* map, const float* base, int rank, const cuuint6
 
 // same for fp16 tensors (lstm_tc.cu: recurrent state / weight slices), SWIZZLE_128B
 int make_tensor_map_f16(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                        const cuuint32_t* box) {
+                        const cuuint32_t* box, int swizzle_bytes) {
   EncodeTiledFn fn = get_encode_fn();
   ECB_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   ECB_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (fp16) failed with CUresult %d (rank %d, base %p)", (int)r, rank, base);
   return 0;
@@ -716,8 +814,26 @@ int launch_split_weights(const float* w, float* hi, float* lo, int K, int N, int
   return 0;
 }
 
+// number of operand tiles (since the last reset) in which the fp16 pair conversion saturated; synchronises the device
+long long tc_f16_saturation_count(int reset) {
+  unsigned int v = 0;
+  if (cudaMemcpyFromSymbol(&v, g_f16_sat_tiles, sizeof(v)) != cudaSuccess) return -1;
+  if (reset) {
+    const unsigned int z = 0;
+    cudaMemcpyToSymbol(g_f16_sat_tiles, &z, sizeof(z));
+  }
+  return (long long)v;
+}
+
+int launch_split_weights_f16(const float* w, void* h1, void* h2, int K, int N, int K_pad, int N_pad, cudaStream_t s) {
+  dim3 grid((unsigned)cdiv(K_pad, 32), (unsigned)cdiv(N_pad, 32));
+  split_weights_f16_kernel<<<grid, dim3(32, 8), 0, s>>>(w, reinterpret_cast<__half*>(h1), reinterpret_cast<__half*>(h2), K, N, K_pad, N_pad);
+  ECB_LAUNCHED();
+  return 0;
+}
+
 int tc_pick_bn(int N, int split, int bn_max) {
-  int bn = split == 3 ? (N % 128 == 0 ? 128 : (N % 64 == 0 ? 64 : 32))
+  int bn = split != 1 ? (N % 128 == 0 ? 128 : (N % 64 == 0 ? 64 : 32))
                       : (N % 256 == 0 ? 256 : (N % 128 == 0 ? 128 : (N % 64 == 0 ? 64 : 32)));
   while (bn_max > 0 && bn > bn_max && bn > 32) bn /= 2;
   return bn;
@@ -728,7 +844,7 @@ int tc_stat_slots(const TcConvParams& p) {
 }
 
 int launch_tc_conv(const TcConvParams& p, cudaStream_t stream) {
-  ECB_REQUIRE(p.split == 1 || p.split == 3, "tc_conv: split must be 1 or 3");
+  ECB_REQUIRE(p.split == 1 || p.split == 2 || p.split == 3, "tc_conv: split must be 1, 2 or 3");
   ECB_REQUIRE(p.N % 32 == 0 && p.N > 0, "tc_conv: N=%d must be a multiple of 32", p.N);
   ECB_REQUIRE(p.C0 % 32 == 0 && p.taps >= 1 && p.stride >= 1, "tc_conv: C0=%d must be a multiple of 32", p.C0);
   ECB_REQUIRE(p.a1 == nullptr || p.C1 % 32 == 0, "tc_conv: C1=%d must be a multiple of 32", p.C1);
@@ -744,8 +860,9 @@ int launch_tc_conv(const TcConvParams& p, cudaStream_t stream) {
   CUtensorMap maps[5];
   TcArgs a;
   ECB_REQUIRE(!p.a0_lo || (p.split == 3 && !p.a1), "tc_conv: a0_lo needs split == 3 and a single source");
-  ECB_REQUIRE(!p.norm_mr || (p.split == 3 && !p.a0_lo && p.norm_gamma && p.norm_beta),
-              "tc_conv: normalise-on-load needs split == 3, no a0_lo, gamma and beta");
+  ECB_REQUIRE(!p.norm_mr || (p.split != 1 && !p.a0_lo && p.norm_gamma && p.norm_beta),
+              "tc_conv: normalise-on-load needs split operands, no a0_lo, gamma and beta");
+  ECB_REQUIRE(p.split != 2 || !p.cell, "tc_conv: the LSTM cell epilogue runs with TF32 operands");
   a.norm_mr = p.norm_mr;
   a.norm_gamma = p.norm_gamma;
   a.norm_beta = p.norm_beta;
@@ -789,8 +906,14 @@ int launch_tc_conv(const TcConvParams& p, cudaStream_t stream) {
     const cuuint64_t dims[2] = {(cuuint64_t)ktot, (cuuint64_t)p.N};
     const cuuint64_t strides[1] = {(cuuint64_t)ktot * 4};
     const cuuint32_t box[2] = {BK, (cuuint32_t)bn};
-    if (make_tensor_map(&maps[2], p.w_hi, 2, dims, strides, box)) return 1;
-    if (make_tensor_map(&maps[3], p.split == 3 ? p.w_lo : p.w_hi, 2, dims, strides, box)) return 1;
+    if (p.split == 2) {   // fp16 pair [N][Ktot] halves, rows of the box = 64 bytes: SWIZZLE_64B
+      const cuuint64_t hstrides[1] = {(cuuint64_t)ktot * 2};
+      if (make_tensor_map_f16(&maps[2], p.w_hi, 2, dims, hstrides, box, 64)) return 1;
+      if (make_tensor_map_f16(&maps[3], p.w_lo, 2, dims, hstrides, box, 64)) return 1;
+    } else {
+      if (make_tensor_map(&maps[2], p.w_hi, 2, dims, strides, box)) return 1;
+      if (make_tensor_map(&maps[3], p.split == 3 ? p.w_lo : p.w_hi, 2, dims, strides, box)) return 1;
+    }
   }
   a.bias = p.bias;
   a.out_raw = p.out_raw;
@@ -812,7 +935,8 @@ int launch_tc_conv(const TcConvParams& p, cudaStream_t stream) {
   if (p.cell) a.cell = *p.cell;
   {
     const int nch = a.n_cb0 * a.shifts + a.n_cb1;
-    a.group = (p.split == 3 && nch > 6) ? 4 : nch;   // <= 24 truncating accumulation steps per group
+    // <= 24 truncating accumulation steps per group (a chunk is 4 TF32 or 2 fp16 K steps)
+    a.group = (p.split == 3 && nch > 6) ? 4 : ((p.split == 2 && nch > 12) ? 8 : nch);
   }
   const int grid = (int)(total < sm_count() ? total : sm_count());
   const double rows = (double)p.M * p.n_items;
@@ -828,13 +952,24 @@ int launch_tc_conv(const TcConvParams& p, cudaStream_t stream) {
     static int nt4 = -1;
     if (nt4 < 0) {
       const char* e = getenv("ECB_TC_NT");
-      nt4 = (e && e[0] == '2') ? 0 : 1;
+      nt4 = (e && e[0] == '2') ? 0 : ((e && e[0] == '3') ? 3 : 1);   // 3: four warps only for BN <= 64
     }
     if (nt4 && p.split == 3 && !p.a0_lo && !p.cell) {
       if (bn == 32) return launch_one<32, 3, 4>(maps, a, grid, stream);
       if (bn == 64) return launch_one<64, 3, 4>(maps, a, grid, stream);
     }
+    if (nt4 && p.split == 2) {
+      if (bn == 32) return launch_one<32, 2, 4>(maps, a, grid, stream);
+      if (bn == 64) return launch_one<64, 2, 4>(maps, a, grid, stream);
+      // BN = 128 with four transform warps: 448 threads leave 128 registers (44 bytes of spills), still 20-30 % faster on the
+      // 1- and 2-tap layers, which are bound by the transform (down256 0.87 -> 0.68 ms, lstm.proj 0.78 -> 0.55 ms); the TF32
+      // split instance gets slower with the same change and keeps two
+      if (bn == 128 && nt4 == 1) return launch_one<128, 2, 4>(maps, a, grid, stream);
+    }
   }
+  ECB_TC_CASE(32, 2)
+  ECB_TC_CASE(64, 2)
+  ECB_TC_CASE(128, 2)
   ECB_TC_CASE(32, 3)
   ECB_TC_CASE(64, 3)
   ECB_TC_CASE(128, 3)

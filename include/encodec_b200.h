@@ -162,6 +162,14 @@ void ecb_debug_tap(float* buf, int64_t capacity, int32_t stage);
  * steps 20..27 into buf ([3 roles][8 steps][16 events] int64, device memory); tools/lstm_trace.py prints them. */
 void ecb_debug_lstm_trace(long long* buf);
 
+/* The fp32-accurate convs run on fp16 PAIR operands (a = a1 + 2^-11 a2 with fp16 a1, a2: the accuracy of the split-TF32
+ * scheme at half the tensor-core time; csrc/tc_conv.cu, SPLIT = 2). fp16 ends at +-65504: a model whose activations exceed
+ * that would be clipped. Returns the number of operand tiles in which the conversion saturated since the last reset on the
+ * current device (0 for every configuration of SURVEY section 8; a non-zero count means: run with ECB_F16_PAIR=0, the
+ * split-TF32 scheme, which has the fp32 range). Synchronises the device. Replaces nothing in the reference (its CPU path is
+ * plain fp32, /root/reference/encodec/modules/conv.py:116). */
+int64_t ecb_f16_saturation_count(int32_t reset);
+
 /* Diagnostic: the encoder's SLSTM alone on x [B][T][H] -> out [B][T][H] (tools/lstm_bench.py). */
 size_t ecb_debug_lstm_workspace_bytes(const ecb_codec* codec, int64_t batch, int64_t T);
 int ecb_debug_lstm(ecb_codec* codec, const float* x, float* out, int64_t batch, int64_t T, void* workspace,

@@ -23,9 +23,9 @@ def _elu(x):
 
 
 def _run_case(T, C0, taps, stride, pad_left, N, items, zero_pad=False, C1=0, split=3, out_halo=0, seed=0,
-              both=False, round_out=0):
+              both=False, round_out=0, x_scale=1.0, check=True):
     rng = np.random.default_rng(seed)
-    x = rng.standard_normal((items, T, C0)).astype(np.float32)
+    x = (rng.standard_normal((items, T, C0)) * x_scale).astype(np.float32)
     M = -(-T // stride) if not zero_pad else T
     ktot = taps * C0 + C1
     w = (rng.standard_normal((ktot, N)) / np.sqrt(ktot)).astype(np.float32)
@@ -72,8 +72,10 @@ def _run_case(T, C0, taps, stride, pad_left, N, items, zero_pad=False, C1=0, spl
         nat.stream_ptr(dev))
     nat.check(rc)
     torch.cuda.synchronize()
+    if not check:
+        return {}
     scale = np.abs(ref).max()
-    tol = (4 * err32 + 1e-6) if split == 3 else 2e-3
+    tol = (4 * err32 + 1e-6) if split in (2, 3) else 2e-3
     res = {"fp32_blas": err32}
     for name, t in outs.items():
         got = t.cpu().numpy().astype(np.float64)
@@ -91,40 +93,61 @@ def _run_case(T, C0, taps, stride, pad_left, N, items, zero_pad=False, C1=0, spl
     return res
 
 
-def test_k3_conv_narrow_dual_output_with_halo():
+# fp32-accurate operand schemes: 3 = split TF32 (a, a_lo; w_hi, w_lo), 2 = fp16 pair (a1 + 2^-11 a2, w1 + 2^-11 w2)
+ACCURATE = [3, 2]
+
+
+@pytest.mark.parametrize("split", ACCURATE)
+def test_k3_conv_narrow_dual_output_with_halo(split):
     # SEANetResnetBlock first conv at 32 channels (hidden padded to 32), ragged length, both outputs + halos
-    r = _run_case(T=1000, C0=32, taps=3, stride=1, pad_left=2, N=32, items=3, out_halo=HALO, both=True)
-    print("k3 narrow", r)
+    r = _run_case(T=1000, C0=32, taps=3, stride=1, pad_left=2, N=32, items=3, out_halo=HALO, both=True, split=split)
+    print("k3 narrow", split, r)
 
 
-def test_fused_shortcut_two_sources():
-    r = _run_case(T=777, C0=32, taps=1, stride=1, pad_left=0, N=64, items=2, C1=64, both=True, out_halo=HALO)
-    print("fused shortcut", r)
+@pytest.mark.parametrize("split", ACCURATE)
+def test_fused_shortcut_two_sources(split):
+    r = _run_case(T=777, C0=32, taps=1, stride=1, pad_left=0, N=64, items=2, C1=64, both=True, out_halo=HALO, split=split)
+    print("fused shortcut", split, r)
 
 
-def test_strided_down_conv_causal_extra_padding():
+@pytest.mark.parametrize("split", ACCURATE)
+def test_strided_down_conv_causal_extra_padding(split):
     # k = 2s = 8, causal pad_left = 4, T not a multiple of the stride -> reflected "extra" padding on the right
-    r = _run_case(T=4001, C0=64, taps=8, stride=4, pad_left=4, N=128, items=2, out_halo=HALO)
-    print("down conv", r)
+    r = _run_case(T=4001, C0=64, taps=8, stride=4, pad_left=4, N=128, items=2, out_halo=HALO, split=split)
+    print("down conv", split, r)
 
 
-def test_strided_down_conv_noncausal():
+@pytest.mark.parametrize("split", ACCURATE)
+def test_strided_down_conv_noncausal(split):
     # non-causal: padding_total = 5 split 3 left / 2 right (conv.py:215-219)
-    r = _run_case(T=3003, C0=128, taps=10, stride=5, pad_left=3, N=256, items=2)
-    print("down conv s5", r)
+    r = _run_case(T=3003, C0=128, taps=10, stride=5, pad_left=3, N=256, items=2, split=split)
+    print("down conv s5", split, r)
 
 
-def test_transposed_conv_as_two_tap_gemm_zero_padded():
-    r = _run_case(T=600, C0=256, taps=2, stride=1, pad_left=1, N=5 * 128, items=3, zero_pad=True)
-    print("convtr", r)
+@pytest.mark.parametrize("split", ACCURATE)
+def test_transposed_conv_as_two_tap_gemm_zero_padded(split):
+    r = _run_case(T=600, C0=256, taps=2, stride=1, pad_left=1, N=5 * 128, items=3, zero_pad=True, split=split)
+    print("convtr", split, r)
 
 
-def test_k7_conv_wide():
-    r = _run_case(T=300, C0=512, taps=7, stride=1, pad_left=6, N=128, items=2)
-    print("k7 wide", r)
+@pytest.mark.parametrize("split", ACCURATE)
+def test_k7_conv_wide(split):
+    r = _run_case(T=300, C0=512, taps=7, stride=1, pad_left=6, N=128, items=2, split=split)
+    print("k7 wide", split, r)
+
+
+def test_fp16_pair_range():
+    """fp16 pair operands over the range the scheme is specified for: activations scaled to ~1e-4 (fp16 subnormals in a1, the
+    remainder keeps the absolute error) and to ~1e4 (close to the saturation point 65504) stay fp32-accurate relative to the
+    output scale."""
+    for scale in (1e-4, 1.0, 1e4):
+        r = _run_case(T=640, C0=128, taps=3, stride=1, pad_left=1, N=128, items=2, split=2, seed=5, x_scale=scale)
+        print("fp16 pair, activation scale", scale, r)
 
 
 def test_lstm_projection_shape_split3_and_split1():
+    r2 = _run_case(T=750, C0=512, taps=1, stride=1, pad_left=0, N=2048, items=2, zero_pad=True, split=2)
+    print("lstm proj fp16 pair", r2)
     r3 = _run_case(T=750, C0=512, taps=1, stride=1, pad_left=0, N=2048, items=2, zero_pad=True)
     r1 = _run_case(T=750, C0=512, taps=1, stride=1, pad_left=0, N=2048, items=2, zero_pad=True, split=1)
     print("lstm proj", r3, r1)
@@ -140,3 +163,14 @@ def test_many_tiles_persistent_schedule():
     # more tiles than SMs so every CTA loops (accumulator double buffering, stage phase wrap-around)
     r = _run_case(T=128 * 40 + 5, C0=32, taps=3, stride=1, pad_left=2, N=32, items=9, out_halo=HALO, both=True)
     print("many tiles", r)
+
+
+def test_fp16_pair_saturation_is_counted():
+    """Activations beyond the fp16 range are clipped by the pair conversion -- and counted, so that a caller can tell
+    (ecb_f16_saturation_count): none on ordinary inputs, some when the input is scaled past 65504."""
+    nat.f16_saturation_count(reset=True)
+    _run_case(T=640, C0=64, taps=3, stride=1, pad_left=1, N=64, items=2, split=2, seed=6)
+    assert nat.f16_saturation_count() == 0
+    _run_case(T=640, C0=64, taps=3, stride=1, pad_left=1, N=64, items=2, split=2, seed=6, x_scale=1e5, check=False)
+    assert nat.f16_saturation_count(reset=True) > 0
+    assert nat.f16_saturation_count() == 0

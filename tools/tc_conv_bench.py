@@ -59,7 +59,7 @@ def main():
         b = torch.randn(N, device=dev)
         o1 = torch.empty(items, M + 2 * HALO, N, device=dev)
         o2 = torch.empty(items, M + 2 * HALO, N, device=dev) if dual else None
-        for split in (3, 1):
+        for split in (3, 2, 1):
             def run():
                 nat.check(nat.lib.ecb_debug_tc_conv(
                     x.data_ptr(), rows_in * C0, C0, 0 if zp else -HALO, rows_in, taps, s, pl,
