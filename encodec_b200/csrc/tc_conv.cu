@@ -150,7 +150,7 @@ __device__ __forceinline__ void copy_out_rows(const uint8_t* slot, int lane, flo
   }
 }
 
-// NT = transform warps (2 | 4; eight were measured slower on the 48 kHz model: 61 vs 56 ms of narrow convs per config-3 step). The narrow split-operand layers are bound by the transform role (remainder of every staged
+// NT = transform warps (2 | 4 | 6; eight were measured slower on the 48 kHz model: 61 vs 56 ms of narrow convs per config-3 step). The narrow split-operand layers are bound by the transform role (remainder of every staged
 // element, and affine + ELU when GroupNorm is applied on load): they run with four; 448 threads leave 146 registers each, which
 // only the BN <= 64 instances fit.
 template <int BN, int SPLIT, int NT>
@@ -964,7 +964,8 @@ int launch_tc_conv(const TcConvParams& p, cudaStream_t stream) {
       // BN = 128 with four transform warps: 448 threads leave 128 registers (44 bytes of spills), still 20-30 % faster on the
       // 1- and 2-tap layers, which are bound by the transform (down256 0.87 -> 0.68 ms, lstm.proj 0.78 -> 0.55 ms); the TF32
       // split instance gets slower with the same change and keeps two
-      if (bn == 128 && nt4 == 1) return launch_one<128, 2, 4>(maps, a, grid, stream);
+      // ... and six are another 3-8 % on those layers (lstm.proj 0.56 -> 0.51 ms); ECB_TC_NT=3 keeps two at BN = 128
+      if (bn == 128 && nt4 == 1) return launch_one<128, 2, 6>(maps, a, grid, stream);
     }
   }
   ECB_TC_CASE(32, 2)

@@ -8,24 +8,24 @@ M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,gpu__dram_th
 step() {   # name, then the profile_step.py arguments
   local name=$1; shift
   timeout 300 env "$@" python tools/profile_step.py $ARGS > $OUT/plain_$name.log 2>&1 &&
-  timeout 1500 env "$@" ncu --profile-from-start off --metrics $M --clock-control none --csv --log-file $OUT/r02_step_$name.csv \
+  timeout 900 env "$@" ncu --profile-from-start off --metrics $M --clock-control none --csv --log-file $OUT/r02_step_$name.csv \
       python tools/profile_step.py $ARGS > $OUT/ncu_$name.log 2>&1
   echo "step $name rc=$?"
+  python tools/ncu_step_summary.py $OUT/r02_step_$name.csv > $OUT/r02_step_$name.txt 2>/dev/null
 }
-full() {   # name, kernel regex
-  local name=$1 re=$2
-  timeout 1500 ncu --profile-from-start off --set full --clock-control none -k regex:$re -c 1 -o $OUT/r02_full_$name -f \
+full() {   # name, kernel regex, launch to capture (skip count)
+  local name=$1 re=$2 skip=${3:-0}
+  timeout 900 ncu --profile-from-start off --set full --clock-control none -k regex:$re -s $skip -c 1 -o $OUT/r02_full_$name -f \
       python tools/profile_step.py $ARGS > $OUT/ncu_full_$name.log 2>&1
   echo "full $name rc=$?"
-  ncu -i $OUT/r02_full_$name.ncu-rep --page raw --csv > $OUT/r02_full_$name.csv 2>/dev/null
   ncu -i $OUT/r02_full_$name.ncu-rep --page details > $OUT/r02_full_$name.txt 2>/dev/null
   rm -f $OUT/r02_full_$name.ncu-rep
 }
 ARGS="cfg2";        step cfg2 X=1
-ARGS="cfg2";        for k in lstm_tc_kernel rvq_tc_kernel tc_res_kernel conv_in_kernel conv_out_kernel; do full $k $k; done
-ARGS="cfg2";        full tc_conv_128_3 "tc_conv_kernel<128,.3>"
+ARGS="cfg2";        full lstm_tcw_kernel lstm_tcw_kernel
+ARGS="cfg2";        full tc_conv_128_2 "tc_conv_kernel<128,.2" 3
+ARGS="cfg2";        full tc_conv_64_2 "tc_conv_kernel<64,.2" 1
 ARGS="cfg3 8";      step cfg3 X=1
-ARGS="fork10hz 4";  step fork10hz X=1
-ARGS="cfg4";        step cfg4 X=1
+ARGS="cfg3 8";      full tc_conv_32_2_gn_on_load "tc_conv_kernel<32,.2" 0
 ARGS="cfg1";        step cfg1_ecdc PROFILE_ECDC=1
 ls -la $OUT | grep r02_
