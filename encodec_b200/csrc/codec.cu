@@ -123,6 +123,7 @@ struct ecb_codec {
   float* e2 = nullptr;         // [n_q][bins]
   float* cb_hi = nullptr;      // TF32 split of the codebooks for the tensor-core quantiser
   float* cb_lo = nullptr;
+  float* cb_f16 = nullptr;     // fp16 pair of the codebooks: two half arrays (e1, then e2) in one float array of the same count
   int hop = 1;
   bool tc_ready = false;       // tensor-core weights prepared
   int dec_split = 0;           // decoder operand scheme: 0 = automatic (weight-norm models: one TF32 pass unless ECB_DEC_SPLIT=3;
@@ -1677,6 +1678,9 @@ int ecb_codec_finalize(ecb_codec* c, void* stream) {
     if (launch_rvq_prepare(c->codebooks, s.n_q, s.bins, s.dimension, c->e2, st)) return 1;
     if (dev_alloc(c, &c->cb_hi, per * s.n_q) || dev_alloc(c, &c->cb_lo, per * s.n_q)) return 1;
     if (launch_rvq_split(c->codebooks, c->cb_hi, c->cb_lo, per * s.n_q, st)) return 1;
+    if (dev_alloc(c, &c->cb_f16, per * s.n_q)) return 1;
+    if (launch_rvq_split_f16(c->codebooks, c->cb_f16, reinterpret_cast<char*>(c->cb_f16) + (size_t)per * s.n_q * 2, per * s.n_q, st))
+      return 1;
   }
   // conv_in / conv_out use their own packings: [K][C_in][32] is what pack_conv produced; conv_out wants
   // [K][32][C_out], which is also pack_conv's [K][Ci][Co] -- nothing more to do.
@@ -1899,8 +1903,14 @@ int ecb_codec_rvq_forward(ecb_codec* c, const float* xin, const float* x_frames,
     stack_tmp = quantized_stack;
   }
   if (!tc_disabled_by_env() && c->spec.bins % 128 == 0 && D == 128) {
-    if (launch_rvq_encode_tc(x_frames, n, c->codebooks, c->cb_hi, c->cb_lo, c->e2, c->spec.n_q, (int)n_q, c->spec.bins,
-                             reinterpret_cast<long long*>(codes), qf, stack_tmp, st))
+    // distances on fp16 pair operands (rvq_tc_kernel<2>) unless ECB_F16_PAIR=0 asks for split TF32
+    const bool pair = c->cb_f16 && f16_pair_wanted(128, c->spec.bins, 128, 0);
+    const float* b1 = pair ? c->cb_f16 : c->cb_hi;
+    const float* b2 = pair ? reinterpret_cast<const float*>(reinterpret_cast<const char*>(c->cb_f16) +
+                                                            (size_t)c->spec.bins * c->spec.dimension * c->spec.n_q * 2)
+                           : c->cb_lo;
+    if (launch_rvq_encode_tc(x_frames, n, c->codebooks, b1, b2, c->e2, c->spec.n_q, (int)n_q, c->spec.bins,
+                             reinterpret_cast<long long*>(codes), qf, stack_tmp, st, pair ? 1 : 0))
       return 1;
   } else if (launch_rvq_encode(x_frames, n, c->codebooks, c->e2, (int)n_q, c->spec.bins, D, reinterpret_cast<long long*>(codes),
                                qf, stack_tmp, st)) {
@@ -2007,7 +2017,10 @@ int ecb_debug_tc_conv(const float* a0, int64_t a0_item_stride, int32_t C0, int64
   return rc;
 }
 
-int64_t ecb_f16_saturation_count(int32_t reset) { return tc_f16_saturation_count(reset); }
+int64_t ecb_f16_saturation_count(int32_t reset) {
+  const long long a = tc_f16_saturation_count(reset), b = rvq_f16_saturation_count(reset);
+  return (a < 0 || b < 0) ? -1 : a + b;
+}
 
 int64_t ecb_packed_bytes(int64_t n_codebooks, int64_t n_frames, int32_t bits) {
   return (n_codebooks * n_frames * bits + 7) / 8;

@@ -439,9 +439,12 @@ int launch_rvq_encode(const float* frames, long long n, const float* codebooks, 
                       long long* codes, float* quantized, float* stack, cudaStream_t s);
 // tensor-core variant (rvq_tc.cu): cb_hi / cb_lo = split codebooks from launch_rvq_split, [n_q_total][bins][128]
 int launch_rvq_split(const float* codebooks, float* hi, float* lo, long long numel, cudaStream_t s);
+int launch_rvq_split_f16(const float* codebooks, void* e1, void* e2, long long numel, cudaStream_t s);
+long long rvq_f16_saturation_count(int reset);
+// f16_pair != 0: cb_hi / cb_lo are the half arrays of launch_rvq_split_f16 (fp16 pair operands, as tc_conv's split == 2)
 int launch_rvq_encode_tc(const float* frames, long long n, const float* codebooks, const float* cb_hi, const float* cb_lo,
                          const float* e2, int n_q_total, int n_q, int bins, long long* codes, float* quantized, float* stack,
-                         cudaStream_t s);
+                         cudaStream_t s, int f16_pair = 0);
 int launch_rvq_decode(const long long* codes, long long n, const float* codebooks, int n_q, int bins, int dim,
                       float* quantized, cudaStream_t s);
 

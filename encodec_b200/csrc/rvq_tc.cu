@@ -19,6 +19,7 @@
 //     `quantized` is bit-identical to decode(codes).
 // Nothing but the codes (and the final quantised frames) goes back to HBM.
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 #include "tc_ptx.cuh"
@@ -40,6 +41,12 @@ constexpr int THREADS = 320;                 // warp 0 TMA, warp 1 MMA, warps 2-
 constexpr int ACC_COLS = 2 * EB;             // [main | correction]
 constexpr int TMEM_COLS = 2 * ACC_COLS;      // double-buffered: 512
 constexpr int SMEM_BYTES = 2 * NKC * A_TILE + STAGES * STAGE_BYTES + 8192 + 1024;
+// SPLIT = 2 (fp16 pair operands, the scheme of tc_conv.cu: R = R1 + 2^-11 R2, E = E1 + 2^-11 E2 in fp16, kind::f16 MMAs with
+// K = 16): the fp32 residual stays where it is (exact update arithmetic, re-rank operand) but is no MMA operand any more; R1 / R2
+// are two [128 rows x 64 dims] half tiles each (SWIZZLE_128B rows of 128 bytes) in the place of R_lo, a codebook stage is
+// [E1 | E2] x 64 dims (the same 32 KB), so a 128-entry block is 2 stages and 8 K steps instead of 4 and 16.
+constexpr int H_TILE = FT * 64 * 2;          // 16 KB: [128 rows x 64 halves]
+__device__ unsigned int g_rvq_f16_sat = 0;   // residual tiles in which the fp16 conversion saturated (see ecb_f16_saturation_count)
 
 struct RvqTcArgs {
   const float* frames;     // [n][128]
@@ -52,8 +59,10 @@ struct RvqTcArgs {
   int n_q, bins, n_tiles;
 };
 
+template <int SPLIT>
 __global__ void __launch_bounds__(THREADS, 1)
 rvq_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, const RvqTcArgs p) {
+  constexpr int KCH = SPLIT == 2 ? 2 : NKC;   // codebook stages (K chunks) per entry block
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -107,14 +116,14 @@ rvq_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         for (int layer = 0; layer < p.n_q; ++layer) {
           for (int blk = 0; blk < n_blocks; ++blk) {
-            for (int kc = 0; kc < NKC; ++kc, ++it) {
+            for (int kc = 0; kc < KCH; ++kc, ++it) {
               const int s = (int)(it % STAGES);
               mbar_wait(empty_bar(s), ((it / STAGES) & 1u) ^ 1u);
               const uint32_t dst = b_ring + s * STAGE_BYTES;
               mbar_expect_tx(full_bar(s), STAGE_BYTES);
               const int row = layer * p.bins + blk * EB;
-              tma_load_2d(dst, &map_hi, full_bar(s), kc * KC, row);
-              tma_load_2d(dst + B_TILE, &map_lo, full_bar(s), kc * KC, row);
+              tma_load_2d(dst, &map_hi, full_bar(s), kc * (SPLIT == 2 ? 64 : KC), row);
+              tma_load_2d(dst + B_TILE, &map_lo, full_bar(s), kc * (SPLIT == 2 ? 64 : KC), row);
             }
           }
         }
@@ -123,8 +132,8 @@ rvq_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
     if (lane == 0) {
-      constexpr uint32_t idesc2 = umma_idesc_tf32(FT, 2 * EB);
-      constexpr uint32_t idesc1 = umma_idesc_tf32(FT, EB);
+      constexpr uint32_t idesc2 = SPLIT == 2 ? ((1u << 4) | ((uint32_t)((2 * EB) >> 3) << 17) | ((uint32_t)(FT >> 4) << 24)) : umma_idesc_tf32(FT, 2 * EB);
+      constexpr uint32_t idesc1 = SPLIT == 2 ? ((1u << 4) | ((uint32_t)(EB >> 3) << 17) | ((uint32_t)(FT >> 4) << 24)) : umma_idesc_tf32(FT, EB);
       uint32_t it = 0, bc = 0, lc = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         for (int layer = 0; layer < p.n_q; ++layer, ++lc) {
@@ -135,13 +144,26 @@ rvq_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
             mbar_wait(acce_bar(ab), ((bc >> 1) & 1u) ^ 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t d_main = tmem_base + (uint32_t)(ab * ACC_COLS);
-            for (int kc = 0; kc < NKC; ++kc, ++it) {
+            for (int kc = 0; kc < KCH; ++kc, ++it) {
               const int s = (int)(it % STAGES);
               mbar_wait(full_bar(s), (it / STAGES) & 1u);
               asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+              const uint32_t b_addr = b_ring + s * STAGE_BYTES;
+              if (SPLIT == 2) {
+                // [main | corr] (+)= R1 * [E1 | E2], corr += R2 * E1 (the epilogue adds corr 2^-11): four K steps of 16 per 64 dims
+                const uint32_t a1_addr = r_lo + kc * H_TILE;
+                const uint32_t a2_addr = r_lo + 2 * H_TILE + kc * H_TILE;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const uint64_t da = umma_desc_sw128(a1_addr + k * 32);
+                  const uint64_t dal = umma_desc_sw128(a2_addr + k * 32);
+                  const uint64_t db = umma_desc_sw128(b_addr + k * 32);
+                  tcgen05_mma_f16(d_main, da, db, idesc2, (kc > 0 || k > 0) ? 1u : 0u);
+                  tcgen05_mma_f16(d_main + EB, dal, db, idesc1, 1u);
+                }
+              } else {
               const uint32_t a_addr = r_hi + kc * A_TILE;
               const uint32_t alo_addr = r_lo + kc * A_TILE;
-              const uint32_t b_addr = b_ring + s * STAGE_BYTES;
 #pragma unroll
               for (int k = 0; k < KC / 8; ++k) {
                 const uint64_t da = umma_desc_sw128(a_addr + k * 32);
@@ -149,6 +171,7 @@ rvq_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
                 const uint64_t db = umma_desc_sw128(b_addr + k * 32);
                 tcgen05_mma_tf32(d_main, da, db, idesc2, (kc > 0 || k > 0) ? 1u : 0u);   // [main | corr] (+)= R * [E_hi | E_lo]
                 tcgen05_mma_tf32(d_main + EB, dal, db, idesc1, 1u);                       // corr += R_lo * E_hi
+              }
               }
               tcgen05_commit(empty_bar(s));
             }
@@ -167,6 +190,28 @@ rvq_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
     uint32_t bc = 0;
     // element (row f, dim d) of the residual: chunk tile d / 32, row f, 16-byte chunk ((d % 32) / 4) ^ (f & 7)
     auto r_off = [&](int d4) { return (d4 >> 3) * A_TILE + f * 128 + (((d4 & 7) ^ (f & 7)) << 4); };
+    // the second operand image of float4 d4 of this row: SPLIT == 3 the TF32 remainder at the same offset in R_lo; SPLIT == 2 the
+    // fp16 pair: tile d4 / 16 of R1 (and of R2, two tiles further), row f, 16-byte chunk ((d4 % 16) / 2) ^ (f & 7), 8-byte half d4 & 1
+    __half2 hmax = __float2half2_rn(0.f);
+    auto store_operand = [&](int d4, const float4& v) {
+      if (SPLIT == 2) {
+        uint32_t h01, h23, l01, l23;
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h01) : "f"(v.y), "f"(v.x));
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h23) : "f"(v.w), "f"(v.z));
+        const float2 f01 = __half22float2(*reinterpret_cast<const __half2*>(&h01));
+        const float2 f23 = __half22float2(*reinterpret_cast<const __half2*>(&h23));
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(l01) : "f"((v.y - f01.y) * 2048.f), "f"((v.x - f01.x) * 2048.f));
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(l23) : "f"((v.w - f23.y) * 2048.f), "f"((v.z - f23.x) * 2048.f));
+        hmax = __hmax2(hmax, __hmax2(__habs2(*reinterpret_cast<const __half2*>(&h01)), __habs2(*reinterpret_cast<const __half2*>(&h23))));
+        const int off = NKC * A_TILE + (d4 >> 4) * H_TILE + f * 128 + ((((d4 & 15) >> 1) ^ (f & 7)) << 4) + ((d4 & 1) << 3);
+        *reinterpret_cast<uint2*>(smem_gen + off) = make_uint2(h01, h23);
+        *reinterpret_cast<uint2*>(smem_gen + off + 2 * H_TILE) = make_uint2(l01, l23);
+      } else {
+        *reinterpret_cast<float4*>(smem_gen + NKC * A_TILE + r_off(d4)) =
+            make_float4(rn_tf32(v.x - trunc_tf32(v.x)), rn_tf32(v.y - trunc_tf32(v.y)), rn_tf32(v.z - trunc_tf32(v.z)),
+                        rn_tf32(v.w - trunc_tf32(v.w)));
+      }
+    };
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       const long long fg = (long long)tile * FT + f;
       const bool live = fg < p.n;
@@ -179,9 +224,7 @@ rvq_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (live) v = __ldg(reinterpret_cast<const float4*>(p.frames + fg * RD) + d4);
         *reinterpret_cast<float4*>(smem_gen + r_off(d4)) = v;
-        *reinterpret_cast<float4*>(smem_gen + NKC * A_TILE + r_off(d4)) =
-            make_float4(rn_tf32(v.x - trunc_tf32(v.x)), rn_tf32(v.y - trunc_tf32(v.y)), rn_tf32(v.z - trunc_tf32(v.z)),
-                        rn_tf32(v.w - trunc_tf32(v.w)));
+        store_operand(d4, v);
         x2p += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
         qacc[j * 4 + 0] = 0.f; qacc[j * 4 + 1] = 0.f; qacc[j * 4 + 2] = 0.f; qacc[j * 4 + 3] = 0.f;
       }
@@ -209,7 +252,8 @@ rvq_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
             const int j0 = blk * EB + half * 64 + c;
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              const float dot = __uint_as_float(vm[i]) + __uint_as_float(vc[i]);
+              const float dot = SPLIT == 2 ? fmaf(__uint_as_float(vc[i]), 1.f / 2048.f, __uint_as_float(vm[i]))
+                                           : __uint_as_float(vm[i]) + __uint_as_float(vc[i]);
               const float t = __fsub_rn(x2, 2.f * dot);                 // core_vq.py:183-187 association order
               const float d = __fadd_rn(t, __ldg(e2 + j0 + i));
               if (d < sec_d) {
@@ -288,9 +332,7 @@ rvq_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
           float4 v = *reinterpret_cast<float4*>(smem_gen + r_off(d4));
           v.x -= q.x; v.y -= q.y; v.z -= q.z; v.w -= q.w;                                   // core_vq.py:402
           *reinterpret_cast<float4*>(smem_gen + r_off(d4)) = v;
-          *reinterpret_cast<float4*>(smem_gen + NKC * A_TILE + r_off(d4)) =
-              make_float4(rn_tf32(v.x - trunc_tf32(v.x)), rn_tf32(v.y - trunc_tf32(v.y)), rn_tf32(v.z - trunc_tf32(v.z)),
-                          rn_tf32(v.w - trunc_tf32(v.w)));
+          store_operand(d4, v);
           qacc[j * 4 + 0] += q.x; qacc[j * 4 + 1] += q.y; qacc[j * 4 + 2] += q.z; qacc[j * 4 + 3] += q.w;   // core_vq.py:404
           if (p.stack && live)
             *(reinterpret_cast<float4*>(p.stack + ((long long)layer * p.n + fg) * RD) + d4) = q;
@@ -301,6 +343,10 @@ rvq_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant_
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (layer + 1 < p.n_q && lane == 0) mbar_arrive(rready_bar);
+      }
+      if (SPLIT == 2 && __hge(__hmax(__low2half(hmax), __high2half(hmax)), __ushort_as_half((unsigned short)0x7BFF))) {
+        atomicAdd(&g_rvq_f16_sat, 1u);
+        hmax = __float2half2_rn(0.f);
       }
       if (p.quantized && live) {
 #pragma unroll
@@ -329,7 +375,34 @@ __global__ void split_codebook_kernel(const float* __restrict__ cb, float* __res
   }
 }
 
+// codebooks [rows][128] -> fp16 pair: e1 = fp16(e), e2 = fp16((e - e1) 2^11), both [rows][128] halves
+__global__ void split_codebook_f16_kernel(const float* __restrict__ cb, __half* __restrict__ e1, __half* __restrict__ e2, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = cb[i];
+    const __half h = __float2half_rn(v);
+    e1[i] = h;
+    e2[i] = __float2half_rn((v - __half2float(h)) * 2048.f);
+  }
+}
+
 }  // namespace
+
+long long rvq_f16_saturation_count(int reset) {
+  unsigned int v = 0;
+  if (cudaMemcpyFromSymbol(&v, g_rvq_f16_sat, sizeof(v)) != cudaSuccess) return -1;
+  if (reset) {
+    const unsigned int z = 0;
+    cudaMemcpyToSymbol(g_rvq_f16_sat, &z, sizeof(z));
+  }
+  return (long long)v;
+}
+
+// the two half arrays of numel elements each fit one float array of numel elements
+int launch_rvq_split_f16(const float* codebooks, void* e1, void* e2, long long numel, cudaStream_t s) {
+  split_codebook_f16_kernel<<<1024, 256, 0, s>>>(codebooks, reinterpret_cast<__half*>(e1), reinterpret_cast<__half*>(e2), numel);
+  ECB_LAUNCHED();
+  return 0;
+}
 
 int launch_rvq_split(const float* codebooks, float* hi, float* lo, long long numel, cudaStream_t s) {
   split_codebook_kernel<<<1024, 256, 0, s>>>(codebooks, hi, lo, numel);
@@ -337,20 +410,29 @@ int launch_rvq_split(const float* codebooks, float* hi, float* lo, long long num
   return 0;
 }
 
+// f16_pair != 0: cb_hi / cb_lo point at the half arrays of launch_rvq_split_f16 and the distances run on fp16 pair operands
 int launch_rvq_encode_tc(const float* frames, long long n, const float* codebooks, const float* cb_hi, const float* cb_lo,
                          const float* e2, int n_q_total, int n_q, int bins, long long* codes, float* quantized, float* stack,
-                         cudaStream_t s) {
+                         cudaStream_t s, int f16_pair) {
   ECB_REQUIRE(n > 0 && n_q > 0 && n_q <= n_q_total, "rvq: empty input (n=%lld, n_q=%d)", n, n_q);
   ECB_REQUIRE(bins % EB == 0, "rvq: bins=%d must be a multiple of %d", bins, EB);
   CUtensorMap mh, ml;
   const cuuint64_t dims[2] = {(cuuint64_t)RD, (cuuint64_t)n_q_total * bins};
-  const cuuint64_t strides[1] = {(cuuint64_t)RD * 4};
-  const cuuint32_t box[2] = {KC, EB};
-  if (make_tensor_map(&mh, cb_hi, 2, dims, strides, box)) return 1;
-  if (make_tensor_map(&ml, cb_lo, 2, dims, strides, box)) return 1;
+  if (f16_pair) {
+    const cuuint64_t strides[1] = {(cuuint64_t)RD * 2};
+    const cuuint32_t box[2] = {64, EB};
+    if (make_tensor_map_f16(&mh, cb_hi, 2, dims, strides, box)) return 1;
+    if (make_tensor_map_f16(&ml, cb_lo, 2, dims, strides, box)) return 1;
+  } else {
+    const cuuint64_t strides[1] = {(cuuint64_t)RD * 4};
+    const cuuint32_t box[2] = {KC, EB};
+    if (make_tensor_map(&mh, cb_hi, 2, dims, strides, box)) return 1;
+    if (make_tensor_map(&ml, cb_lo, 2, dims, strides, box)) return 1;
+  }
   static DeviceOnce attr_set;
   if (!attr_set.done()) {
-    ECB_CUDA(cudaFuncSetAttribute(rvq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    ECB_CUDA(cudaFuncSetAttribute(rvq_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    ECB_CUDA(cudaFuncSetAttribute(rvq_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_set.mark();
   }
   RvqTcArgs a;
@@ -367,7 +449,8 @@ int launch_rvq_encode_tc(const float* frames, long long n, const float* codebook
   const int grid = a.n_tiles < sm_count() ? a.n_tiles : sm_count();
   ProfScope prof(PROF_RVQ, s, 2.0 * (double)n * n_q * bins * RD,
                  4.0 * ((double)n * RD * (quantized ? 2 : 1) + (double)n_q * bins * RD) + 8.0 * (double)n * n_q);
-  rvq_tc_kernel<<<grid, THREADS, SMEM_BYTES, s>>>(mh, ml, a);
+  if (f16_pair) rvq_tc_kernel<2><<<grid, THREADS, SMEM_BYTES, s>>>(mh, ml, a);
+  else rvq_tc_kernel<3><<<grid, THREADS, SMEM_BYTES, s>>>(mh, ml, a);
   ECB_LAUNCHED();
   return 0;
 }
