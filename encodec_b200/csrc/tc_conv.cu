@@ -139,7 +139,7 @@ __device__ __forceinline__ void copy_out_rows(const uint8_t* slot, int lane, flo
     for (int i = 0; i < 4; ++i) {
       e[i * 4 + 0] = v[i].x; e[i * 4 + 1] = v[i].y; e[i * 4 + 2] = v[i].z; e[i * 4 + 3] = v[i].w;
     }
-    elu_vec<16>(e);
+    elu_any<ROUND, 16>(e);   // ROUND: the stored value is TF32-rounded (single-pass consumers): the fast exp is exact enough
 #pragma unroll
     for (int i = 0; i < 4; ++i)
       if (rr0 + 8 * i < rows_left) {

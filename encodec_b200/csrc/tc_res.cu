@@ -241,7 +241,7 @@ tc_res_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
           v[u] = q < XT / 16 ? xr[q] : make_float4(0.f, 0.f, 0.f, 0.f);
           e[u * 4 + 0] = v[u].x; e[u * 4 + 1] = v[u].y; e[u * 4 + 2] = v[u].z; e[u * 4 + 3] = v[u].w;
         }
-        elu_vec<12>(e);
+        elu_any<SPLIT == 1, 12>(e);   // SPLIT == 1: every ELU of this kernel feeds a TF32-rounded operand / output
 #pragma unroll
         for (int u = 0; u < 3; ++u) {
           const int q = q0 + u * 256;
@@ -293,7 +293,7 @@ tc_res_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
         hv[g * 4 + 2] = __uint_as_float(vm[g * 4 + 2]) + __uint_as_float(vc[g * 4 + 2]) + bb.z;
         hv[g * 4 + 3] = __uint_as_float(vm[g * 4 + 3]) + __uint_as_float(vc[g * 4 + 3]) + bb.w;
       }
-      elu_vec<16>(hv);
+      elu_any<SPLIT == 1, 16>(hv);
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         const float4 h = make_float4(hv[g * 4 + 0], hv[g * 4 + 1], hv[g * 4 + 2], hv[g * 4 + 3]);
@@ -357,7 +357,7 @@ tc_res_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
           const float4 v = *reinterpret_cast<const float4*>(slot + rr * 64 + ((c16 ^ ((rr >> 1) & 3)) << 4));
           yv[q * 4 + 0] = v.x; yv[q * 4 + 1] = v.y; yv[q * 4 + 2] = v.z; yv[q * 4 + 3] = v.w;
         }
-        elu_vec<16>(yv);
+        elu_any<SPLIT == 1, 16>(yv);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int rr = (lane >> 2) + 8 * q;
