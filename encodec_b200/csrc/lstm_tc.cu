@@ -1,5 +1,7 @@
 // SLSTM recurrence on the tensor cores (reference modules/lstm.py:12-28 -> nn.LSTM(512, 512, 2), gates i,f,g,o, zero
-// state), H = 512. One persistent kernel per LSTM layer; the input projection of all steps is a tc_conv GEMM (pre).
+// state), H = 512. Two kernels share the step described here: lstm_tc_kernel (one persistent kernel per LSTM layer; the
+// input projection of all steps is a tc_conv GEMM, `pre`) and, further down, lstm_tcw_kernel (both layers as one wavefront
+// kernel for launches of up to 128 items, or one layer with 16 units per CTA for large launches).
 //
 // Geometry: 128 CTAs = NU unit blocks x NB batch parts. A unit block owns UPC hidden units (4 UPC gate rows of W_hh); its
 // [4 UPC x 512] slice sits in shared memory for the whole sequence (un-replicated inside a batch part), and the recurrent

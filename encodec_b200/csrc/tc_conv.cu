@@ -14,20 +14,20 @@
 //     K-major canonical layout tcgen05.mma reads. A strided k = 2s conv addresses its input through the folded
 //     view [T/s][s*C], so its window is two consecutive folded rows. Zero padding (transposed convs) is TMA
 //     out-of-bounds fill.
-//   * products run on the 5th-generation tensor cores: tcgen05.mma.cta_group::1.kind::tf32, M = 128, N = BN,
-//     K = 8 per instruction, fp32 accumulators in TMEM, issued by one elected thread.
-//   * fp32-level accuracy with split operands (SPLIT = 3): a = a_hi + a_lo with a_hi = the TF32 truncation
-//     the tensor core applies itself and a_lo = rn_tf32(a - a_hi) computed on chip by two transform warps;
-//     w = w_hi + w_lo with w_hi = rn_tf32(w), w_lo = rn_tf32(w - w_hi) computed once at load.
-//     D += a*w_hi + a_lo*w_hi + a*w_lo; the dropped a_lo*w_lo term is zero-mean (w_lo is symmetric) and
-//     below 2^-22 relative. SPLIT = 1 issues the first product only (operands rounded to TF32 by their
-//     producers).
-//   * persistent, warp-specialised: warp 0 TMA producer, warp 1 MMA issuer (owns TMEM), warps 2-3 transform,
-//     warps 4-7 epilogue. Two TMEM accumulator buffers let the epilogue of tile i overlap the main loop of
-//     tile i+1. The epilogue reads TMEM (tcgen05.ld 32x32b), adds the bias, optionally applies ELU, stages
-//     32x32 blocks in swizzled shared memory and writes them with TMA stores (row clipping by the tensor map);
-//     an output may be written raw, ELU'd or both (a residual block consumes x through its shortcut and
-//     ELU(x) through its first conv) and its reflected halo rows are written directly.
+//   * products run on the 5th-generation tensor cores: tcgen05.mma.cta_group::1, M = 128, N = BN, fp32 accumulators in
+//     TMEM, issued by one elected thread; kind::tf32 (K = 8 per instruction) or kind::f16 (K = 16).
+//   * three operand schemes (template parameter SPLIT, see Cfg): 2 = fp16 PAIR operands, the default of the fp32-accurate
+//     layers (a = a1 + 2^-11 a2, w = w1 + 2^-11 w2; a1 w1 -> main accumulator, a1 w2 + a2 w1 -> correction accumulator);
+//     3 = split TF32 (a = a_hi + a_lo with a_hi = the truncation the tensor core applies itself, a_lo = rn_tf32(a - a_hi);
+//     the same three products at K = 8; the fp32-range alternative, ECB_F16_PAIR=0); 1 = one TF32 pass (operands rounded
+//     to TF32 by their producers: the weight-norm decoder). The dropped lo x lo term is zero-mean and below 2^-22 relative.
+//   * persistent, warp-specialised: warp 0 TMA producer, warp 1 MMA issuer (owns TMEM), NT = 2 / 4 / 6 transform warps
+//     (operand remainder or fp16 pair of every staged element; GroupNorm + ELU of the input when it is applied on load),
+//     then 8 epilogue warps. Two TMEM accumulator buffers let the epilogue of tile i overlap the main loop of tile i+1.
+//     The epilogue reads TMEM (tcgen05.ld 32x32b), adds the bias, optionally applies ELU, stages 32-row blocks in swizzled
+//     shared memory and writes them with coalesced 16-byte stores; an output may be written raw, ELU'd or both (a residual
+//     block consumes x through its shortcut and ELU(x) through its first conv), its reflected halo rows are written
+//     directly, and GroupNorm partial statistics are taken on the way.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <stdlib.h>
