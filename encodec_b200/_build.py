@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libencodec_b200.so")
-SOURCES = ["codec.cu", "conv_gemm.cu", "tc_conv.cu", "tc_res.cu", "conv_edge.cu", "lstm.cu", "lstm_tc.cu", "rvq.cu", "rvq_tc.cu", "misc.cu", "bitpack.cu"]
+SOURCES = ["codec.cu", "conv_gemm.cu", "tc_conv.cu", "tc_res.cu", "conv_edge.cu", "lstm.cu", "lstm_tc.cu", "rvq.cu", "rvq_tc.cu", "misc.cu", "bitpack.cu", "lm.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "--expt-relaxed-constexpr", "-cudart", "static"]
 

@@ -26,6 +26,11 @@ class EcbSpec(C.Structure):
     ]
 
 
+class EcbLmSpec(C.Structure):
+    _fields_ = [("n_q", C.c_int32), ("card", C.c_int32), ("dim", C.c_int32), ("n_layers", C.c_int32),
+                ("n_heads", C.c_int32), ("hidden", C.c_int32), ("past_context", C.c_int32), ("max_period", C.c_float)]
+
+
 class EcbProfEntry(C.Structure):
     _fields_ = [("name", C.c_char * 32), ("launches", C.c_int64), ("ms", C.c_double), ("flops", C.c_double),
                 ("bytes", C.c_double)]
@@ -76,6 +81,21 @@ SIGNATURES = {
     "ecb_pack_codes": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p]),
     "ecb_unpack_codes": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.c_int64,
                                    C.c_void_p]),
+    "ecb_lm_create": (C.c_int, [C.POINTER(EcbLmSpec), C.POINTER(C.c_void_p)]),
+    "ecb_lm_destroy": (None, [C.c_void_p]),
+    "ecb_lm_load_tensor": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "ecb_lm_finalize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ecb_lm_cache_bytes": (C.c_size_t, [C.c_void_p, C.c_int64, C.c_int64]),
+    "ecb_lm_workspace_bytes": (C.c_size_t, [C.c_void_p, C.c_int64, C.c_int64]),
+    "ecb_lm_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int64, C.c_int64,
+                                 C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_size_t, C.c_void_p]),
+    "ecb_lm_decode_frame": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p,
+                                      C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "ecb_quantized_cdf": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "ecb_ac_encode": (C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
+    "ecb_ac_decode": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
+                                C.POINTER(C.c_int64)]),
     "ecb_transpose_bct_to_btc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p]),
     "ecb_transpose_btc_to_bct": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_void_p]),
 }

@@ -1,0 +1,192 @@
+// Range arithmetic of the entropy-coded .ecdc stream, shared by the host coder and the device decoder.
+//
+// Restates ArithmeticCoder / ArithmeticDecoder of the reference (encodec/quantization/ac.py:56-260) on 64-bit integers:
+// the reference keeps (low, high[, current]) as Python integers below 2^(max_bit + 1) with max_bit <= 61 asserted
+// (ac.py:156), so uint64 holds every value it can reach. The two places where the reference leaves integers are
+//   effective_low  = ceil (range_low  * (delta / 2^total_range_bits))     (ac.py:145, 240)
+//   effective_high = floor(range_high * (delta / 2^total_range_bits))     (ac.py:146, 241)
+// in Python floats: `delta / 2^bits` is the correctly rounded double of delta scaled by a power of two, the product is ONE
+// IEEE double multiplication. Both are reproduced operation for operation (explicitly rounded intrinsics on the device,
+// so that no contraction can change them). Bits travel through BitPacker(bits=1) (binary.py:55-89): bit i of the stream
+// is bit (i % 8) of byte i / 8.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define ECB_AC_HD __host__ __device__ __forceinline__
+#else
+#define ECB_AC_HD inline
+#endif
+
+namespace ecb {
+namespace ac {
+
+enum Status { AC_OK = 0, AC_EOF = 1, AC_SEARCH_FAILED = 2, AC_RANGE_OVERFLOW = 3, AC_BAD_CDF = 4 };
+
+ECB_AC_HD double scaled_delta(uint64_t delta, int bits) {
+  // delta / 2**bits (ac.py:145): conversion rounds to nearest-even like Python's int / int, the scaling is exact
+#if defined(__CUDA_ARCH__)
+  return __dmul_rn(__ull2double_rn((unsigned long long)delta), 1.0 / (double)(1ull << bits));
+#else
+  return (double)delta * (1.0 / (double)(1ull << bits));
+#endif
+}
+ECB_AC_HD uint64_t eff_low(int64_t range_low, double ratio) {
+#if defined(__CUDA_ARCH__)
+  return (uint64_t)ceil(__dmul_rn((double)range_low, ratio));
+#else
+  volatile double p = (double)range_low * ratio;   // volatile: one rounded product, never fused or kept in extended precision
+  return (uint64_t)ceil(p);
+#endif
+}
+ECB_AC_HD uint64_t eff_high(int64_t range_high, double ratio) {
+#if defined(__CUDA_ARCH__)
+  return (uint64_t)floor(__dmul_rn((double)range_high, ratio));
+#else
+  volatile double p = (double)range_high * ratio;
+  return (uint64_t)floor(p);
+#endif
+}
+
+// ---- decoder (host and device) -------------------------------------------------------------------------------------
+struct Decoder {
+  uint64_t low, high, current;
+  int64_t bit_pos;      // next stream bit
+  int32_t max_bit;
+  int32_t status;       // sticky Status
+};
+
+ECB_AC_HD void decoder_init(Decoder& d, int64_t first_bit) {
+  d.low = 0;
+  d.high = 0;
+  d.current = 0;
+  d.bit_pos = first_bit;
+  d.max_bit = -1;
+  d.status = AC_OK;
+}
+
+// ArithmeticDecoder.pull (ac.py:214-260). cdf: int32 [card], the quantised cdf of this symbol (cdf[i] = upper bound,
+// exclusive, of symbol i's range). Returns the symbol, or -1 with d.status set (AC_EOF: "the stream ended sooner than
+// expected", compress.py:143-144).
+ECB_AC_HD int pull(Decoder& d, const uint8_t* data, int64_t n_bits, const int32_t* cdf, int card, int bits) {
+  if (d.status != AC_OK) return -1;
+  const uint64_t full = 1ull << bits;
+  while (d.high - d.low + 1 < full) {                                    // ac.py:224-231
+    if (d.bit_pos >= n_bits) {
+      d.status = AC_EOF;
+      return -1;
+    }
+    if (d.max_bit >= 61) {
+      d.status = AC_RANGE_OVERFLOW;
+      return -1;
+    }
+    const uint64_t bit = (data[d.bit_pos >> 3] >> (d.bit_pos & 7)) & 1u;
+    ++d.bit_pos;
+    d.low *= 2;
+    d.high = d.high * 2 + 1;
+    d.current = d.current * 2 + bit;
+    ++d.max_bit;
+  }
+  const double ratio = scaled_delta(d.high - d.low + 1, bits);
+  int lo_idx = 0, hi_idx = card - 1, mid = 0;
+  uint64_t low = 0, high = 0;
+  for (;;) {                                                             // bin_search, ac.py:233-251
+    if (hi_idx < lo_idx) {
+      d.status = AC_SEARCH_FAILED;
+      return -1;
+    }
+    mid = (lo_idx + hi_idx) / 2;
+    const int64_t range_low = mid > 0 ? cdf[mid - 1] : 0;
+    const int64_t range_high = (int64_t)cdf[mid] - 1;
+    if (range_high < range_low) {                                        // an empty range cannot be produced by the cdf builder
+      d.status = AC_BAD_CDF;
+      return -1;
+    }
+    low = eff_low(range_low, ratio) + d.low;
+    high = eff_high(range_high, ratio) + d.low;
+    if (d.current >= low) {
+      if (d.current <= high) break;
+      lo_idx = mid + 1;
+    } else {
+      hi_idx = mid - 1;
+    }
+  }
+  d.low = low;
+  d.high = high;
+  while (d.max_bit >= 0) {                                               // _flush_common_prefix, ac.py:195-212
+    const uint64_t b1 = d.low >> d.max_bit;
+    const uint64_t b2 = d.high >> d.max_bit;
+    if (b1 != b2) break;
+    d.low -= b1 << d.max_bit;
+    d.high -= b1 << d.max_bit;
+    d.current -= b1 << d.max_bit;
+    --d.max_bit;
+  }
+  return mid;
+}
+
+ECB_AC_HD int64_t bytes_consumed(const Decoder& d) { return (d.bit_pos + 7) >> 3; }   // BitUnpacker reads whole bytes
+
+// ---- coder (host) --------------------------------------------------------------------------------------------------
+struct Encoder {
+  uint64_t low = 0, high = 0;
+  int32_t max_bit = -1;
+  int32_t status = AC_OK;
+  uint8_t* out = nullptr;
+  int64_t cap = 0, n_bytes = 0;
+  uint32_t cur = 0;
+  int32_t n_cur = 0;
+  bool overflow = false;
+
+  void push_bit(uint64_t b) {                                            // BitPacker.push with bits = 1 (binary.py:69-77)
+    cur |= (uint32_t)(b & 1u) << n_cur;
+    if (++n_cur == 8) {
+      if (n_bytes < cap) out[n_bytes] = (uint8_t)cur; else overflow = true;
+      ++n_bytes;
+      cur = 0;
+      n_cur = 0;
+    }
+  }
+  // ArithmeticCoder.push (ac.py:127-157): the symbol's range is [range_low, range_high_excl) of the quantised cdf
+  bool push(int64_t range_low, int64_t range_high_excl, int bits) {
+    if (status != AC_OK) return false;
+    const uint64_t full = 1ull << bits;
+    while (high - low + 1 < full) {
+      if (max_bit >= 61) { status = AC_RANGE_OVERFLOW; return false; }   // the reference asserts max_bit <= 61 (ac.py:156)
+      low *= 2;
+      high = high * 2 + 1;
+      ++max_bit;
+    }
+    if (range_high_excl - 1 < range_low || range_low < 0) { status = AC_BAD_CDF; return false; }
+    const double ratio = scaled_delta(high - low + 1, bits);
+    const uint64_t el = eff_low(range_low, ratio), eh = eff_high(range_high_excl - 1, ratio);
+    high = low + eh;
+    low = low + el;
+    if (low > high) { status = AC_BAD_CDF; return false; }
+    while (max_bit >= 0) {                                               // _flush_common_prefix, ac.py:109-125
+      const uint64_t b1 = low >> max_bit, b2 = high >> max_bit;
+      if (b1 != b2) break;
+      low -= b1 << max_bit;
+      high -= b1 << max_bit;
+      --max_bit;
+      push_bit(b1);
+    }
+    return true;
+  }
+  void flush() {                                                         // ac.py:159-166 + BitPacker.flush (binary.py:79-86)
+    while (max_bit >= 0) {
+      push_bit((low >> max_bit) & 1u);
+      --max_bit;
+    }
+    if (n_cur) {
+      if (n_bytes < cap) out[n_bytes] = (uint8_t)cur; else overflow = true;
+      ++n_bytes;
+      cur = 0;
+      n_cur = 0;
+    }
+  }
+};
+
+}  // namespace ac
+}  // namespace ecb

@@ -1,0 +1,827 @@
+// Language model + arithmetic coder of the entropy-coded .ecdc stream.
+//
+// Replaces, for compress_to_file / decompress_from_file with use_lm=True (reference encodec/compress.py:63-87,125-152):
+//   LMModel.forward (model.py:65-83): sum of per-codebook embeddings -> StreamingTransformerEncoder
+//   (modules/transformer.py:62-119: LayerNorm, sinusoidal positions, post-norm nn.TransformerEncoderLayer x num_layers with
+//   a causal window of past_context rows) -> one Linear(dim, card) + softmax per codebook;
+//   build_stable_quantized_cdf (quantization/ac.py:18-53) and ArithmeticCoder / ArithmeticDecoder (ac.py:56-260).
+//
+// Design. The reference evaluates the LM one time step at a time in both directions. Here
+//   * COMPRESSION knows every code, so all steps of all frames are rows of ONE batched pass (38 launches per call whatever
+//     the length); the logits kernel forms softmax -> quantised cdf on chip and emits only the two cdf values the coder
+//     needs per symbol (8 bytes instead of a 4 KB distribution); the coder itself is the sequential integer recurrence of
+//     ac_core.h on the host.
+//   * DECOMPRESSION is sequential by construction (step t + 1 is conditioned on the symbols decoded at step t), so the whole
+//     loop stays on the device: the same kernels with one row, the keys / values of earlier steps in a cache, and a
+//     one-thread kernel that runs ArithmeticDecoder.pull for the K codebooks of the step and writes the codes the next
+//     step's embedding kernel reads. No host round trip per step (the reference makes K .item() calls per step).
+//   * Both directions MUST see bit-identical probabilities or the stream decodes to garbage. Every kernel therefore computes
+//     an output element with the same instruction sequence whatever the number of rows in the launch: one warp per
+//     (row, output) dot product with a fixed lane partition of K and a fixed shuffle tree, one warp per (row, head)
+//     attention over keys in window order, per-row softmax reductions. tests/test_lm_gpu.py asserts the identity.
+// The state of a stream is its key / value cache: row 0 of an item holds the projections of the all-zero row the reference
+// seeds its state with (transformer.py:103-104; it is attended like a real position until the window drops it), row p + 1
+// position p. These are CUDA-core kernels: the work is a few MFLOP per step and latency-bound (decode) or a few GFLOP per
+// call (compress); what matters is the launch count and that nothing returns to the host inside the loop.
+#include <math.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/encodec_b200.h"
+#include "ac_core.h"
+#include "common.cuh"
+
+namespace ecb {
+namespace {
+
+constexpr int kWarps = 8;        // warps per block of the row kernels
+constexpr int kRowTile = 8;      // rows that share one weight fetch in lm_linear
+constexpr int kColsPerWarp = 4;  // output columns a warp walks in lm_linear
+constexpr int kLogitRows = 4;    // rows per block in lm_logits
+constexpr int kMaxDimPerLane = 8;  // dim <= 256
+
+struct CdfParams {
+  float roundoff;   // ac.py:19 (1e-8 as float32: the reference's pdf is a float32 tensor)
+  float scale;      // (1 - alpha) * total_range as float32, alpha = min_range * card / total_range (ac.py:40-44)
+  int min_range;
+};
+
+struct Tokens {
+  const long long* p;   // element (item, k, t) at p[item * item_stride + k * k_stride + t * t_stride]
+  long long item_stride, k_stride, t_stride;
+  int are_codes;        // 1: p holds the codes of the frame, step t reads 1 + code[t - 1] (0 at t = 0; compress.py:69,78)
+                        // 0: p holds the LM's input indices of steps t0 .. t0 + n_t - 1 (LMModel.forward's `indices`)
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ long long token_index(const Tokens& tk, long long item, int k, long long t, long long t0, int card) {
+  long long v;
+  if (tk.are_codes) v = t == 0 ? 0 : 1 + tk.p[item * tk.item_stride + k * tk.k_stride + (t - 1) * tk.t_stride];
+  else v = tk.p[item * tk.item_stride + k * tk.k_stride + (t - t0) * tk.t_stride];
+  return v < 0 ? 0 : (v > card ? card : v);
+}
+
+// LayerNorm of one row held as dim / 32 values per lane (nn.LayerNorm, eps inside the square root, biased variance)
+__device__ __forceinline__ void warp_layer_norm(float (&v)[kMaxDimPerLane], int dim, int lane, const float* __restrict__ w,
+                                                const float* __restrict__ b, float eps) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxDimPerLane; ++i) s += (lane + 32 * i < dim) ? v[i] : 0.f;
+  const float mean = warp_sum(s) / (float)dim;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxDimPerLane; ++i) {
+    const float d = (lane + 32 * i < dim) ? v[i] - mean : 0.f;
+    q = fmaf(d, d, q);
+  }
+  const float rstd = 1.f / sqrtf(warp_sum(q) / (float)dim + eps);
+#pragma unroll
+  for (int i = 0; i < kMaxDimPerLane; ++i) {
+    const int d = lane + 32 * i;
+    if (d < dim) v[i] = (v[i] - mean) * rstd * w[d] + b[d];
+  }
+}
+
+// model.py:79 (sum of embeddings) + transformer.py:106-111 (norm_in, + sinusoidal position embedding). One warp per row.
+__global__ void lm_embed_kernel(Tokens tk, const float* __restrict__ emb, const float* __restrict__ nw,
+                                const float* __restrict__ nb, const float* __restrict__ pos_div, float* __restrict__ x,
+                                long long n_rows, int n_t, long long t0, int K, int card, int dim, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5);
+  if (row >= n_rows) return;
+  const long long item = row / n_t;
+  const long long t = t0 + row % n_t;
+  float v[kMaxDimPerLane];
+#pragma unroll
+  for (int i = 0; i < kMaxDimPerLane; ++i) v[i] = 0.f;
+  for (int k = 0; k < K; ++k) {
+    const long long idx = token_index(tk, item, k, t, t0, card);
+    const float* e = emb + ((size_t)k * (card + 1) + (size_t)idx) * dim;
+#pragma unroll
+    for (int i = 0; i < kMaxDimPerLane; ++i) {
+      const int d = lane + 32 * i;
+      if (d < dim) v[i] += e[d];
+    }
+  }
+  warp_layer_norm(v, dim, lane, nw, nb, eps);
+  const int half = dim >> 1;
+#pragma unroll
+  for (int i = 0; i < kMaxDimPerLane; ++i) {
+    const int d = lane + 32 * i;
+    if (d < dim) {
+      // create_sin_embedding (transformer.py:16-27): float32 phase = position / max_period^(j / (half - 1)), cat(cos, sin)
+      const float phase = __fdiv_rn((float)t, pos_div[d < half ? d : d - half]);
+      x[row * dim + d] = v[i] + (d < half ? cosf(phase) : sinf(phase));
+    }
+  }
+}
+
+// In-place-capable LayerNorm of rows (norm1 / norm2 of the post-norm layer, transformer.py:38-39). One warp per row.
+__global__ void lm_ln_kernel(const float* __restrict__ in, float* __restrict__ out, const float* __restrict__ w,
+                             const float* __restrict__ b, long long n_rows, int dim, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5);
+  if (row >= n_rows) return;
+  float v[kMaxDimPerLane];
+#pragma unroll
+  for (int i = 0; i < kMaxDimPerLane; ++i) {
+    const int d = lane + 32 * i;
+    v[i] = d < dim ? in[row * dim + d] : 0.f;
+  }
+  warp_layer_norm(v, dim, lane, w, b, eps);
+#pragma unroll
+  for (int i = 0; i < kMaxDimPerLane; ++i) {
+    const int d = lane + 32 * i;
+    if (d < dim) out[row * dim + d] = v[i];
+  }
+}
+
+enum { EPI_QKV = 0, EPI_GELU = 1, EPI_RESID = 2 };
+struct LinArgs {
+  const float* x;       // [n_rows][K]
+  const float* W;       // [N][K] (nn.Linear layout)
+  const float* b;       // [N]
+  int K, N;
+  long long n_rows;
+  float* out;           // GELU / RESID: [n_rows][N]; QKV: q [n_rows][dim]
+  const float* resid;   // RESID: out = resid + (W x + b)
+  float* cache;         // QKV: this layer's cache, [n_items][capacity + 1][2 * dim]
+  long long capacity;
+  int n_t;
+  long long t0;
+  int dim;
+};
+
+// y[r][n] = epilogue(b[n] + sum_k W[n][k] x[r][k]). A warp owns an output column: the weight row sits in registers (KPL values
+// per lane, k = lane + 32 i), the rows of the tile come from shared memory; lane-local fmaf chain in i order, then the xor
+// tree -- the same sequence for every row, whatever the launch shape.
+template <int KPL, int EPI>
+__global__ void __launch_bounds__(kWarps * 32) lm_linear_kernel(LinArgs a) {
+  extern __shared__ float xs[];   // [kRowTile][K]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long r0 = (long long)blockIdx.y * kRowTile;
+  const int nr = (int)((a.n_rows - r0) < kRowTile ? (a.n_rows - r0) : kRowTile);
+  for (int i = threadIdx.x; i < nr * a.K; i += blockDim.x) xs[i] = a.x[r0 * a.K + i];
+  __syncthreads();
+  for (int c = 0; c < kColsPerWarp; ++c) {
+    const int n = (blockIdx.x * kWarps + warp) * kColsPerWarp + c;
+    if (n >= a.N) break;   // warp-uniform
+    float w[KPL];
+#pragma unroll
+    for (int i = 0; i < KPL; ++i) {
+      const int k = lane + 32 * i;
+      w[i] = k < a.K ? a.W[(size_t)n * a.K + k] : 0.f;
+    }
+    const float bias = a.b[n];
+    for (int r = 0; r < nr; ++r) {
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < KPL; ++i) {
+        const int k = lane + 32 * i;
+        if (k < a.K) acc = fmaf(w[i], xs[r * a.K + k], acc);
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) {
+        const long long row = r0 + r;
+        const float v = acc + bias;
+        if (EPI == EPI_GELU) {
+          a.out[row * a.N + n] = 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));   // F.gelu (exact, erf form)
+        } else if (EPI == EPI_RESID) {
+          a.out[row * a.N + n] = a.resid[row * a.N + n] + v;
+        } else {
+          if (n < a.dim) {
+            a.out[row * a.dim + n] = v;
+          } else {
+            const long long item = row / a.n_t, t = a.t0 + row % a.n_t;
+            float* base = a.cache + (size_t)item * (a.capacity + 1) * 2 * a.dim;
+            base[(size_t)(t + 1) * 2 * a.dim + (n - a.dim)] = v;
+            if (t == 0) base[n - a.dim] = bias;   // projections of the reference's all-zero seed row: W 0 + b
+          }
+        }
+      }
+    }
+  }
+}
+
+// _sa_block (transformer.py:42-59) for one (row, head) per warp: keys / values = cache rows [lo, t + 1], lo = t + 1 - min(t + 1,
+// past_context) (the rows the streaming state still holds, transformer.py:116-117) -- scores by lanes over keys, softmax,
+// weighted values by lanes over the head dimension, keys in window order.
+__global__ void lm_attn_kernel(const float* __restrict__ q, const float* __restrict__ cache, float* __restrict__ out,
+                               long long n_rows, int n_t, long long t0, long long capacity, int dim, int heads,
+                               int past_context) {
+  extern __shared__ float sm[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* sc = sm + (size_t)warp * (past_context + 1 + 32);
+  float* sq = sc + past_context + 1;
+  const long long w = (long long)blockIdx.x * kWarps + warp;
+  if (w >= n_rows * heads) return;
+  const long long row = w / heads;
+  const int h = (int)(w % heads);
+  const long long item = row / n_t, t = t0 + row % n_t;
+  const int hd = dim / heads;
+  const long long n_past = (t + 1) < past_context ? (t + 1) : past_context;
+  const long long lo = t + 1 - n_past;
+  const int nk = (int)n_past + 1;
+  const float* kv = cache + ((size_t)item * (capacity + 1) + (size_t)lo) * 2 * dim + h * hd;
+  if (lane < hd) sq[lane] = q[row * dim + h * hd + lane];
+  __syncwarp();
+  const float scale = 1.f / sqrtf((float)hd);
+  float m = -INFINITY;
+  for (int i = lane; i < nk; i += 32) {
+    const float* kr = kv + (size_t)i * 2 * dim;
+    float s = 0.f;
+    for (int d = 0; d < hd; ++d) s = fmaf(sq[d], kr[d], s);
+    s *= scale;
+    sc[i] = s;
+    m = fmaxf(m, s);
+  }
+  m = warp_max(m);
+  float l = 0.f;
+  for (int i = lane; i < nk; i += 32) {
+    const float e = expf(sc[i] - m);
+    sc[i] = e;
+    l += e;
+  }
+  l = warp_sum(l);
+  __syncwarp();
+  if (lane < hd) {
+    const float* vr = kv + dim + lane;
+    float acc = 0.f;
+    for (int i = 0; i < nk; ++i) acc = fmaf(sc[i], vr[(size_t)i * 2 * dim], acc);
+    out[row * dim + h * hd + lane] = acc / l;
+  }
+}
+
+// pdf -> range width of build_stable_quantized_cdf (ac.py:36-45) in the float32 arithmetic of the torch CPU kernels
+__device__ __forceinline__ int pdf_to_range(float p, const CdfParams& cp) {
+  const float fl = __fmul_rn(floorf(__fdiv_rn(p, cp.roundoff)), cp.roundoff);
+  return (int)floorf(__fmul_rn(cp.scale, fl)) + cp.min_range;
+}
+
+// Inclusive scan of the `card` range widths in vals[] (one contiguous chunk per thread) -> cdf in vals[] (ac.py:46).
+__device__ __forceinline__ void block_cumsum(int* vals, int card, int* wsum) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x;
+  const int per = (card + nthr - 1) / nthr;
+  const int c0 = min(tid * per, card), c1 = min(c0 + per, card);
+  int local = 0;
+  for (int n = c0; n < c1; ++n) local += vals[n];
+  int inc = local;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int u = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += u;
+  }
+  if (lane == 31) wsum[warp] = inc;
+  __syncthreads();
+  int run = inc - local;
+  for (int w2 = 0; w2 < warp; ++w2) run += wsum[w2];
+  for (int n = c0; n < c1; ++n) {
+    run += vals[n];
+    vals[n] = run;
+  }
+  __syncthreads();
+}
+
+// model.py:81-83 (per-codebook Linear + softmax over the codebook) + ac.py:18-53 for kLogitRows rows and ONE codebook per
+// block. Outputs (each optional): probabilities, the quantised cdf, and for compression the coder's pair
+// (cdf[s - 1], cdf[s]) of the symbol s actually coded at (item, k, t).
+template <int KPL>
+__global__ void __launch_bounds__(kWarps * 32) lm_logits_kernel(const float* __restrict__ x, const float* __restrict__ W,
+                                                                 const float* __restrict__ B, long long n_rows, int dim, int card,
+                                                                 int K, Tokens tk, int n_t, long long t0, CdfParams cp,
+                                                                 float* __restrict__ probas, int* __restrict__ cdf,
+                                                                 int* __restrict__ sym_ranges) {
+  extern __shared__ float sm[];
+  float* xs = sm;                                  // [kLogitRows][dim]
+  float* lg = xs + kLogitRows * dim;               // [kLogitRows][card]
+  __shared__ float red[kWarps];
+  __shared__ int wsum[kWarps];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int k = blockIdx.y;
+  const long long r0 = (long long)blockIdx.x * kLogitRows;
+  const int nr = (int)((n_rows - r0) < kLogitRows ? (n_rows - r0) : kLogitRows);
+  for (int i = tid; i < nr * dim; i += blockDim.x) xs[i] = x[r0 * dim + i];
+  __syncthreads();
+  const float* Wk = W + (size_t)k * card * dim;
+  const float* Bk = B + (size_t)k * card;
+  for (int n = warp; n < card; n += kWarps) {
+    float w[KPL];
+#pragma unroll
+    for (int i = 0; i < KPL; ++i) {
+      const int kk = lane + 32 * i;
+      w[i] = kk < dim ? Wk[(size_t)n * dim + kk] : 0.f;
+    }
+    const float bias = Bk[n];
+    for (int r = 0; r < nr; ++r) {
+      float acc = 0.f;
+#pragma unroll
+      for (int i = 0; i < KPL; ++i) {
+        const int kk = lane + 32 * i;
+        if (kk < dim) acc = fmaf(w[i], xs[r * dim + kk], acc);
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) lg[r * card + n] = acc + bias;
+    }
+  }
+  __syncthreads();
+  for (int r = 0; r < nr; ++r) {
+    float* row = lg + r * card;
+    const long long grow = r0 + r;
+    // softmax over the codebook (model.py:83)
+    float m = -INFINITY;
+    for (int n = tid; n < card; n += blockDim.x) m = fmaxf(m, row[n]);
+    m = warp_max(m);
+    if (lane == 0) red[warp] = m;
+    __syncthreads();
+    m = red[0];
+#pragma unroll
+    for (int w2 = 1; w2 < kWarps; ++w2) m = fmaxf(m, red[w2]);
+    __syncthreads();
+    float s = 0.f;
+    for (int n = tid; n < card; n += blockDim.x) {
+      const float e = expf(row[n] - m);
+      row[n] = e;
+      s += e;
+    }
+    s = warp_sum(s);
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    float total = red[0];
+#pragma unroll
+    for (int w2 = 1; w2 < kWarps; ++w2) total += red[w2];
+    int* irow = reinterpret_cast<int*>(row);
+    for (int n = tid; n < card; n += blockDim.x) {
+      const float p = __fdiv_rn(row[n], total);
+      if (probas) probas[((size_t)grow * K + k) * card + n] = p;
+      irow[n] = pdf_to_range(p, cp);
+    }
+    __syncthreads();
+    block_cumsum(irow, card, wsum);
+    if (cdf)
+      for (int n = tid; n < card; n += blockDim.x) cdf[((size_t)grow * K + k) * card + n] = irow[n];
+    if (sym_ranges && tid == 0) {
+      const long long item = grow / n_t, t = t0 + grow % n_t;
+      long long sv = tk.p[item * tk.item_stride + k * tk.k_stride + t * tk.t_stride];
+      sv = sv < 0 ? 0 : (sv >= card ? card - 1 : sv);
+      sym_ranges[((size_t)grow * K + k) * 2 + 0] = sv ? irow[sv - 1] : 0;
+      sym_ranges[((size_t)grow * K + k) * 2 + 1] = irow[sv];
+    }
+    __syncthreads();
+  }
+}
+
+// build_stable_quantized_cdf alone: pdf [n_rows][card] float32 -> cdf [n_rows][card] int32. One block per row.
+__global__ void __launch_bounds__(kWarps * 32) lm_cdf_kernel(const float* __restrict__ pdf, int* __restrict__ cdf, int card,
+                                                              CdfParams cp) {
+  extern __shared__ int iv[];
+  __shared__ int wsum[kWarps];
+  const size_t row = blockIdx.x;
+  for (int n = threadIdx.x; n < card; n += blockDim.x) iv[n] = pdf_to_range(pdf[row * card + n], cp);
+  __syncthreads();
+  block_cumsum(iv, card, wsum);
+  for (int n = threadIdx.x; n < card; n += blockDim.x) cdf[row * card + n] = iv[n];
+}
+
+// ArithmeticDecoder.pull for the K codebooks of step t (compress.py:137-148): one thread, the stream and the decoder state
+// stay on the device; writes the codes the next step's embedding reads.
+__global__ void lm_ac_init_kernel(ac::Decoder* st, long long first_bit) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) ac::decoder_init(*st, first_bit);
+}
+__global__ void lm_ac_pull_kernel(ac::Decoder* st, const unsigned char* __restrict__ data, long long n_bits,
+                                  const int* __restrict__ cdf, int K, int card, int bits, long long* __restrict__ codes,
+                                  long long k_stride, long long t) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  ac::Decoder d = *st;
+  for (int k = 0; k < K; ++k) {
+    const int s = ac::pull(d, data, n_bits, cdf + (size_t)k * card, card, bits);
+    codes[k * k_stride + t] = s < 0 ? 0 : s;
+  }
+  *st = d;
+}
+__global__ void lm_ac_result_kernel(const ac::Decoder* st, long long* result) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    result[0] = st->status;
+    result[1] = ac::bytes_consumed(*st);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+struct LmSpec {
+  int n_q, card, dim, n_layers, n_heads, hidden, past_context;
+  float max_period;
+};
+
+struct Lm {
+  LmSpec spec;
+  int device = -1;
+  float* weights = nullptr;   // one allocation, slices below
+  size_t n_weights = 0;
+  std::map<std::string, std::pair<size_t, size_t>> slots;   // key -> (offset, numel)
+  std::map<std::string, bool> loaded;
+  bool finalized = false;
+  const float* w(const std::string& key) const { return weights + slots.at(key).first; }
+  size_t emb_off = 0, lin_w_off = 0, lin_b_off = 0, pos_off = 0;
+  struct LayerW {
+    const float *in_w, *in_b, *out_w, *out_b, *l1_w, *l1_b, *l2_w, *l2_b, *n1_w, *n1_b, *n2_w, *n2_b;
+  };
+  std::vector<LayerW> layers;   // resolved at finalize: no map lookups inside the decoding loop
+  const float *nin_w = nullptr, *nin_b = nullptr;
+};
+
+void add_slot(Lm& lm, const std::string& key, size_t numel, size_t& cursor) {
+  lm.slots[key] = {cursor, numel};
+  lm.loaded[key] = false;
+  cursor += (numel + 3) & ~(size_t)3;
+}
+
+template <int EPI>
+int launch_linear(const LinArgs& a, cudaStream_t s) {
+  const int kpl = (a.K + 31) / 32;
+  dim3 grid((unsigned)cdiv((long long)a.N, (long long)kWarps * kColsPerWarp), (unsigned)cdiv(a.n_rows, (long long)kRowTile));
+  const size_t smem = (size_t)kRowTile * a.K * sizeof(float);
+  ECB_REQUIRE(kpl <= 32 && smem <= 48 * 1024, "lm: linear layer with K = %d is not supported (K <= 1024)", a.K);
+  if (kpl <= 2) lm_linear_kernel<2, EPI><<<grid, kWarps * 32, smem, s>>>(a);
+  else if (kpl <= 4) lm_linear_kernel<4, EPI><<<grid, kWarps * 32, smem, s>>>(a);
+  else if (kpl <= 7) lm_linear_kernel<7, EPI><<<grid, kWarps * 32, smem, s>>>(a);
+  else if (kpl <= 8) lm_linear_kernel<8, EPI><<<grid, kWarps * 32, smem, s>>>(a);
+  else if (kpl <= 16) lm_linear_kernel<16, EPI><<<grid, kWarps * 32, smem, s>>>(a);
+  else if (kpl <= 25) lm_linear_kernel<25, EPI><<<grid, kWarps * 32, smem, s>>>(a);
+  else lm_linear_kernel<32, EPI><<<grid, kWarps * 32, smem, s>>>(a);
+  ECB_LAUNCHED();
+  return 0;
+}
+
+CdfParams cdf_params(int card, int bits) {
+  // ac.py:39-44: total_range = 2^bits, alpha = min_range * card / total_range, scale = (1 - alpha) * total_range; the
+  // Python double becomes a float32 when it multiplies the float32 pdf
+  const double total = (double)(1ull << bits);
+  const double alpha = 2.0 * card / total;
+  CdfParams cp;
+  cp.roundoff = (float)1e-8;
+  cp.scale = (float)((1.0 - alpha) * total);
+  cp.min_range = 2;
+  return cp;
+}
+
+struct Workspace {
+  float *x, *y, *q, *att, *hid;
+  int* cdf;              // decode: [K][card]
+  ac::Decoder* dec;
+};
+
+size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+size_t plan_workspace(const LmSpec& sp, long long n_rows, long long K, Workspace* ws, char* base) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    char* p = base ? base + off : nullptr;
+    off += align256(bytes);
+    return p;
+  };
+  float* x = (float*)take((size_t)n_rows * sp.dim * 4);
+  float* y = (float*)take((size_t)n_rows * sp.dim * 4);
+  float* q = (float*)take((size_t)n_rows * sp.dim * 4);
+  float* att = (float*)take((size_t)n_rows * sp.dim * 4);
+  float* hid = (float*)take((size_t)n_rows * sp.hidden * 4);
+  int* cdf = (int*)take((size_t)K * sp.card * 4);
+  ac::Decoder* dec = (ac::Decoder*)take(sizeof(ac::Decoder));
+  if (ws) *ws = Workspace{x, y, q, att, hid, cdf, dec};
+  return off;
+}
+
+// One pass of the LM over rows (item, t0 .. t0 + n_t - 1): everything up to the transformer output in ws.x.
+int lm_trunk(const Lm& lm, const Tokens& tk, long long n_items, int K, long long t0, long long n_t, float* cache,
+             long long capacity, const Workspace& ws, cudaStream_t s) {
+  const LmSpec& sp = lm.spec;
+  const long long n_rows = n_items * n_t;
+  const float eps = 1e-5f;
+  const unsigned row_blocks = (unsigned)cdiv(n_rows, (long long)kWarps);
+  lm_embed_kernel<<<row_blocks, kWarps * 32, 0, s>>>(tk, lm.weights + lm.emb_off, lm.nin_w, lm.nin_b,
+                                                    lm.weights + lm.pos_off, ws.x, n_rows,
+                                                    (int)n_t, t0, K, sp.card, sp.dim, eps);
+  ECB_LAUNCHED();
+  const size_t layer_cache = (size_t)n_items * (capacity + 1) * 2 * sp.dim;
+  for (int l = 0; l < sp.n_layers; ++l) {
+    const Lm::LayerW& lw = lm.layers[l];
+    float* lc = cache + (size_t)l * layer_cache;
+    LinArgs a{};
+    a.x = ws.x; a.W = lw.in_w; a.b = lw.in_b;
+    a.K = sp.dim; a.N = 3 * sp.dim; a.n_rows = n_rows; a.out = ws.q; a.cache = lc; a.capacity = capacity;
+    a.n_t = (int)n_t; a.t0 = t0; a.dim = sp.dim;
+    if (launch_linear<EPI_QKV>(a, s)) return 1;
+    const size_t attn_smem = (size_t)kWarps * (sp.past_context + 1 + 32) * sizeof(float);
+    lm_attn_kernel<<<(unsigned)cdiv(n_rows * sp.n_heads, (long long)kWarps), kWarps * 32, attn_smem, s>>>(
+        ws.q, lc, ws.att, n_rows, (int)n_t, t0, capacity, sp.dim, sp.n_heads, sp.past_context);
+    ECB_LAUNCHED();
+    LinArgs o{};
+    o.x = ws.att; o.W = lw.out_w; o.b = lw.out_b;
+    o.K = sp.dim; o.N = sp.dim; o.n_rows = n_rows; o.out = ws.y; o.resid = ws.x;
+    if (launch_linear<EPI_RESID>(o, s)) return 1;
+    lm_ln_kernel<<<row_blocks, kWarps * 32, 0, s>>>(ws.y, ws.x, lw.n1_w, lw.n1_b, n_rows,
+                                                   sp.dim, eps);
+    ECB_LAUNCHED();
+    LinArgs f1{};
+    f1.x = ws.x; f1.W = lw.l1_w; f1.b = lw.l1_b;
+    f1.K = sp.dim; f1.N = sp.hidden; f1.n_rows = n_rows; f1.out = ws.hid;
+    if (launch_linear<EPI_GELU>(f1, s)) return 1;
+    LinArgs f2{};
+    f2.x = ws.hid; f2.W = lw.l2_w; f2.b = lw.l2_b;
+    f2.K = sp.hidden; f2.N = sp.dim; f2.n_rows = n_rows; f2.out = ws.y; f2.resid = ws.x;
+    if (launch_linear<EPI_RESID>(f2, s)) return 1;
+    lm_ln_kernel<<<row_blocks, kWarps * 32, 0, s>>>(ws.y, ws.x, lw.n2_w, lw.n2_b, n_rows,
+                                                   sp.dim, eps);
+    ECB_LAUNCHED();
+  }
+  return 0;
+}
+
+int lm_heads(const Lm& lm, const Tokens& tk, long long n_items, int K, long long t0, long long n_t, const Workspace& ws,
+             float* probas, int* cdf, int* sym_ranges, cudaStream_t s) {
+  const LmSpec& sp = lm.spec;
+  const long long n_rows = n_items * n_t;
+  const CdfParams cp = cdf_params(sp.card, 24);
+  const size_t smem = (size_t)kLogitRows * (sp.dim + sp.card) * sizeof(float);
+  ECB_REQUIRE(smem <= 48 * 1024, "lm: card = %d is too large for the logits kernel", sp.card);
+  dim3 grid((unsigned)cdiv(n_rows, (long long)kLogitRows), (unsigned)K);
+  const int kpl = (sp.dim + 31) / 32;
+  const float* W = lm.weights + lm.lin_w_off;
+  const float* B = lm.weights + lm.lin_b_off;
+  if (kpl <= 2) lm_logits_kernel<2><<<grid, kWarps * 32, smem, s>>>(ws.x, W, B, n_rows, sp.dim, sp.card, K, tk, (int)n_t, t0, cp, probas, cdf, sym_ranges);
+  else if (kpl <= 4) lm_logits_kernel<4><<<grid, kWarps * 32, smem, s>>>(ws.x, W, B, n_rows, sp.dim, sp.card, K, tk, (int)n_t, t0, cp, probas, cdf, sym_ranges);
+  else if (kpl <= 7) lm_logits_kernel<7><<<grid, kWarps * 32, smem, s>>>(ws.x, W, B, n_rows, sp.dim, sp.card, K, tk, (int)n_t, t0, cp, probas, cdf, sym_ranges);
+  else lm_logits_kernel<8><<<grid, kWarps * 32, smem, s>>>(ws.x, W, B, n_rows, sp.dim, sp.card, K, tk, (int)n_t, t0, cp, probas, cdf, sym_ranges);
+  ECB_LAUNCHED();
+  return 0;
+}
+
+int check_call(const Lm* lm, long long n_items, long long K, long long t0, long long n_t, long long capacity) {
+  ECB_REQUIRE(lm && lm->finalized, "lm: handle is null or not finalized");
+  ECB_REQUIRE(n_items >= 1 && n_t >= 1 && t0 >= 0, "lm: bad n_items=%lld t0=%lld n_t=%lld", n_items, t0, n_t);
+  ECB_REQUIRE(K >= 1 && K <= lm->spec.n_q, "lm: %lld codebooks, the model has %d", K, lm->spec.n_q);
+  ECB_REQUIRE(t0 + n_t <= capacity, "lm: steps %lld..%lld exceed the cache capacity %lld", t0, t0 + n_t, capacity);
+  ECB_REQUIRE(n_items * n_t <= 65535ll * kRowTile, "lm: %lld rows in one call (at most %lld): split the frames", n_items * n_t,
+              65535ll * kRowTile);
+  return 0;
+}
+
+}  // namespace
+}  // namespace ecb
+
+using namespace ecb;
+
+extern "C" {
+
+int ecb_lm_create(const ecb_lm_spec* spec, ecb_lm** out) {
+  ECB_REQUIRE(spec && out, "lm_create: null argument");
+  ECB_REQUIRE(spec->dim >= 32 && spec->dim <= 32 * kMaxDimPerLane && spec->dim % 2 == 0, "lm_create: dim %d (even, 32..256)", spec->dim);
+  ECB_REQUIRE(spec->n_heads >= 1 && spec->dim % spec->n_heads == 0 && spec->dim / spec->n_heads <= 32,
+              "lm_create: head dimension must divide dim and be <= 32 (dim %d, heads %d)", spec->dim, spec->n_heads);
+  ECB_REQUIRE(spec->hidden >= 32 && spec->hidden <= 1024, "lm_create: hidden %d (32..1024)", spec->hidden);
+  ECB_REQUIRE(spec->card >= 2 && spec->card <= 2048, "lm_create: card %d (2..2048)", spec->card);
+  ECB_REQUIRE(spec->n_q >= 1 && spec->n_layers >= 1 && spec->past_context >= 1 && spec->past_context <= 1400,
+              "lm_create: n_q %d, layers %d, past_context %d (1..1400)", spec->n_q, spec->n_layers, spec->past_context);
+  ECB_REQUIRE(2.0 * spec->card <= (double)(1 << 24), "lm_create: card too large for 24 range bits");
+  Lm* lm = new Lm();
+  lm->spec = LmSpec{spec->n_q, spec->card, spec->dim, spec->n_layers, spec->n_heads, spec->hidden, spec->past_context, spec->max_period};
+  const size_t d = spec->dim, h = spec->hidden;
+  size_t cur = 0;
+  add_slot(*lm, "transformer.norm_in.weight", d, cur);
+  add_slot(*lm, "transformer.norm_in.bias", d, cur);
+  for (int l = 0; l < spec->n_layers; ++l) {
+    const std::string p = "transformer.layers." + std::to_string(l);
+    add_slot(*lm, p + ".self_attn.in_proj_weight", 3 * d * d, cur);
+    add_slot(*lm, p + ".self_attn.in_proj_bias", 3 * d, cur);
+    add_slot(*lm, p + ".self_attn.out_proj.weight", d * d, cur);
+    add_slot(*lm, p + ".self_attn.out_proj.bias", d, cur);
+    add_slot(*lm, p + ".linear1.weight", h * d, cur);
+    add_slot(*lm, p + ".linear1.bias", h, cur);
+    add_slot(*lm, p + ".linear2.weight", d * h, cur);
+    add_slot(*lm, p + ".linear2.bias", d, cur);
+    add_slot(*lm, p + ".norm1.weight", d, cur);
+    add_slot(*lm, p + ".norm1.bias", d, cur);
+    add_slot(*lm, p + ".norm2.weight", d, cur);
+    add_slot(*lm, p + ".norm2.bias", d, cur);
+  }
+  // contiguous per-codebook tables: emb [n_q][card + 1][dim], linears weight [n_q][card][dim], bias [n_q][card]
+  lm->emb_off = cur;
+  for (int k = 0; k < spec->n_q; ++k) {
+    lm->slots["emb." + std::to_string(k) + ".weight"] = {cur, (size_t)(spec->card + 1) * d};
+    lm->loaded["emb." + std::to_string(k) + ".weight"] = false;
+    cur += (size_t)(spec->card + 1) * d;
+  }
+  cur = (cur + 3) & ~(size_t)3;
+  lm->lin_w_off = cur;
+  for (int k = 0; k < spec->n_q; ++k) {
+    lm->slots["linears." + std::to_string(k) + ".weight"] = {cur, (size_t)spec->card * d};
+    lm->loaded["linears." + std::to_string(k) + ".weight"] = false;
+    cur += (size_t)spec->card * d;
+  }
+  lm->lin_b_off = cur;
+  for (int k = 0; k < spec->n_q; ++k) {
+    lm->slots["linears." + std::to_string(k) + ".bias"] = {cur, (size_t)spec->card};
+    lm->loaded["linears." + std::to_string(k) + ".bias"] = false;
+    cur += (size_t)spec->card;
+  }
+  cur = (cur + 3) & ~(size_t)3;
+  lm->pos_off = cur;
+  cur += d / 2;
+  lm->n_weights = cur;   // allocated by the first ecb_lm_load_tensor (create works without a device)
+  *out = reinterpret_cast<ecb_lm*>(lm);
+  return 0;
+}
+
+void ecb_lm_destroy(ecb_lm* h) {
+  Lm* lm = reinterpret_cast<Lm*>(h);
+  if (!lm) return;
+  if (lm->weights) cudaFree(lm->weights);
+  delete lm;
+}
+
+/* key: a key of the reference's LMModel.state_dict(); data: DEVICE float32, numel values, copied. */
+int ecb_lm_load_tensor(ecb_lm* h, const char* key, const float* data, int64_t numel, void* stream) {
+  Lm* lm = reinterpret_cast<Lm*>(h);
+  ECB_REQUIRE(lm && key && data, "lm_load_tensor: null argument");
+  if (!lm->weights) {
+    ECB_CUDA(cudaGetDevice(&lm->device));
+    ECB_CUDA(cudaMalloc(&lm->weights, lm->n_weights * sizeof(float)));
+  }
+  auto it = lm->slots.find(key);
+  ECB_REQUIRE(it != lm->slots.end(), "lm_load_tensor: unexpected key '%s'", key);
+  ECB_REQUIRE((size_t)numel == it->second.second, "lm_load_tensor: '%s' has %lld values, expected %zu", key, (long long)numel,
+              it->second.second);
+  ECB_CUDA(cudaMemcpyAsync(lm->weights + it->second.first, data, (size_t)numel * sizeof(float), cudaMemcpyDeviceToDevice,
+                           reinterpret_cast<cudaStream_t>(stream)));
+  lm->loaded[key] = true;
+  lm->finalized = false;
+  return 0;
+}
+
+/* pos_divisor: optional HOST float32 [dim / 2] = max_period ** (j / (dim / 2 - 1)) as the caller's framework rounds it
+ * (transformer.py:23: a float32 torch pow); null: computed here in double precision and rounded once. */
+int ecb_lm_finalize(ecb_lm* h, const float* pos_divisor, void* stream) {
+  Lm* lm = reinterpret_cast<Lm*>(h);
+  ECB_REQUIRE(lm, "lm_finalize: null handle");
+  for (auto& kv : lm->loaded) ECB_REQUIRE(kv.second, "lm_finalize: tensor '%s' was not loaded", kv.first.c_str());
+  const int half = lm->spec.dim / 2;
+  std::vector<float> div(half);
+  for (int j = 0; j < half; ++j)
+    div[j] = pos_divisor ? pos_divisor[j] : (float)pow((double)lm->spec.max_period, (double)((float)j / (float)(half - 1)));
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  ECB_CUDA(cudaMemcpyAsync(lm->weights + lm->pos_off, div.data(), half * sizeof(float), cudaMemcpyHostToDevice, s));
+  ECB_CUDA(cudaStreamSynchronize(s));   // div dies with this frame
+  lm->nin_w = lm->w("transformer.norm_in.weight");
+  lm->nin_b = lm->w("transformer.norm_in.bias");
+  lm->layers.clear();
+  for (int l = 0; l < lm->spec.n_layers; ++l) {
+    const std::string p = "transformer.layers." + std::to_string(l);
+    lm->layers.push_back(Lm::LayerW{lm->w(p + ".self_attn.in_proj_weight"), lm->w(p + ".self_attn.in_proj_bias"),
+                                    lm->w(p + ".self_attn.out_proj.weight"), lm->w(p + ".self_attn.out_proj.bias"),
+                                    lm->w(p + ".linear1.weight"), lm->w(p + ".linear1.bias"), lm->w(p + ".linear2.weight"),
+                                    lm->w(p + ".linear2.bias"), lm->w(p + ".norm1.weight"), lm->w(p + ".norm1.bias"),
+                                    lm->w(p + ".norm2.weight"), lm->w(p + ".norm2.bias")});
+  }
+  lm->finalized = true;
+  return 0;
+}
+
+/* K/V cache of n_items independent streams of at most `capacity` steps: float32 [n_layers][n_items][capacity + 1][2 dim]. */
+size_t ecb_lm_cache_bytes(ecb_lm* h, int64_t n_items, int64_t capacity) {
+  Lm* lm = reinterpret_cast<Lm*>(h);
+  if (!lm || n_items < 1 || capacity < 1) return 0;
+  return (size_t)lm->spec.n_layers * n_items * (capacity + 1) * 2 * lm->spec.dim * sizeof(float);
+}
+
+size_t ecb_lm_workspace_bytes(ecb_lm* h, int64_t n_rows, int64_t n_codebooks) {
+  Lm* lm = reinterpret_cast<Lm*>(h);
+  if (!lm || n_rows < 1 || n_codebooks < 1) return 0;
+  return plan_workspace(lm->spec, n_rows, n_codebooks, nullptr, nullptr);
+}
+
+/* LMModel.forward (model.py:65-83) for steps t0 .. t0 + n_t - 1 of n_items streams whose earlier steps are in `cache`.
+ * tokens (DEVICE int64): element (item, k, t) at tokens[item * item_stride + k * k_stride + t * t_stride];
+ *   tokens_are_codes = 0: the LM's input indices of the n_t steps (1 + previous code, 0 = none), t counted from t0;
+ *   tokens_are_codes = 1: the codes of the whole frame, t absolute (step t is fed 1 + code[t - 1], 0 at t = 0).
+ * Outputs, DEVICE, each optional: probas float32 [n_items][n_t][K][card] (the reference returns this permuted to
+ * [B, card, K, T]); cdf int32, same shape: build_stable_quantized_cdf(probas[...], 24, check=False) (ac.py:18-53);
+ * sym_ranges int32 [n_items][n_t][K][2] (needs tokens_are_codes = 1): (cdf[s - 1] or 0, cdf[s]) of the code s at (item, k, t),
+ * the two numbers ArithmeticCoder.push reads (ac.py:143-144). */
+int ecb_lm_forward(ecb_lm* h, const int64_t* tokens, int64_t item_stride, int64_t k_stride, int64_t t_stride,
+                   int32_t tokens_are_codes, int64_t n_items, int64_t n_codebooks, int64_t t0, int64_t n_t, float* cache,
+                   int64_t capacity, float* probas, int32_t* cdf, int32_t* sym_ranges, void* workspace,
+                   size_t workspace_bytes, void* stream) {
+  Lm* lm = reinterpret_cast<Lm*>(h);
+  if (check_call(lm, n_items, n_codebooks, t0, n_t, capacity)) return 1;
+  ECB_REQUIRE(tokens && cache && workspace, "lm_forward: null argument");
+  ECB_REQUIRE(!sym_ranges || tokens_are_codes, "lm_forward: sym_ranges needs tokens_are_codes = 1");
+  Workspace ws;
+  const size_t need = plan_workspace(lm->spec, n_items * n_t, n_codebooks, &ws, static_cast<char*>(workspace));
+  ECB_REQUIRE(workspace_bytes >= need, "lm_forward: workspace of %zu bytes, %zu needed", workspace_bytes, need);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  Tokens tk{reinterpret_cast<const long long*>(tokens), item_stride, k_stride, t_stride, tokens_are_codes ? 1 : 0};
+  if (lm_trunk(*lm, tk, n_items, (int)n_codebooks, t0, n_t, cache, capacity, ws, s)) return 1;
+  return lm_heads(*lm, tk, n_items, (int)n_codebooks, t0, n_t, ws, probas, cdf, sym_ranges, s);
+}
+
+/* The decoding loop of decompress_from_file for ONE frame (compress.py:125-152) without leaving the device: for t in
+ * 0 .. n_steps - 1: LM step -> quantised cdfs -> ArithmeticDecoder.pull for the K codebooks -> codes[k][t].
+ * data: DEVICE bytes of the stream, the frame's coder starts at byte `first_byte`; codes: DEVICE int64 [K][n_steps];
+ * result: DEVICE int64 [2] = (status: 0 ok, 1 the stream ended sooner than expected, 2 search failed, 3 range overflow,
+ * 4 bad cdf; bytes of `data` consumed up to the end of this frame -- where the next frame's scale / coder starts). */
+int ecb_lm_decode_frame(ecb_lm* h, const uint8_t* data, int64_t n_bytes, int64_t first_byte, int64_t n_codebooks,
+                        int64_t n_steps, int64_t* codes, float* cache, int64_t capacity, int64_t* result, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  Lm* lm = reinterpret_cast<Lm*>(h);
+  if (check_call(lm, 1, n_codebooks, 0, n_steps, capacity)) return 1;
+  ECB_REQUIRE(data && codes && cache && result && workspace, "lm_decode_frame: null argument");
+  ECB_REQUIRE(first_byte >= 0 && first_byte <= n_bytes, "lm_decode_frame: first_byte %lld of %lld", (long long)first_byte,
+              (long long)n_bytes);
+  Workspace ws;
+  const size_t need = plan_workspace(lm->spec, 1, n_codebooks, &ws, static_cast<char*>(workspace));
+  ECB_REQUIRE(workspace_bytes >= need, "lm_decode_frame: workspace of %zu bytes, %zu needed", workspace_bytes, need);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int K = (int)n_codebooks;
+  Tokens tk{reinterpret_cast<const long long*>(codes), 0, n_steps, 1, 1};
+  lm_ac_init_kernel<<<1, 32, 0, s>>>(ws.dec, first_byte * 8);
+  ECB_LAUNCHED();
+  for (long long t = 0; t < n_steps; ++t) {
+    if (lm_trunk(*lm, tk, 1, K, t, 1, cache, capacity, ws, s)) return 1;
+    if (lm_heads(*lm, tk, 1, K, t, 1, ws, nullptr, ws.cdf, nullptr, s)) return 1;
+    lm_ac_pull_kernel<<<1, 32, 0, s>>>(ws.dec, data, n_bytes * 8, ws.cdf, K, lm->spec.card, 24,
+                                       reinterpret_cast<long long*>(codes), n_steps, t);
+    ECB_LAUNCHED();
+  }
+  lm_ac_result_kernel<<<1, 32, 0, s>>>(ws.dec, reinterpret_cast<long long*>(result));
+  ECB_LAUNCHED();
+  return 0;
+}
+
+/* build_stable_quantized_cdf (ac.py:18-53, check=False) alone: pdf DEVICE float32 [n_rows][card] -> cdf DEVICE int32. */
+int ecb_quantized_cdf(const float* pdf, int64_t n_rows, int32_t card, int32_t total_range_bits, int32_t* cdf, void* stream) {
+  ECB_REQUIRE(pdf && cdf && n_rows >= 1 && card >= 1 && card <= 8192, "quantized_cdf: bad arguments (card <= 8192)");
+  ECB_REQUIRE(total_range_bits >= 8 && total_range_bits <= 30 && 2.0 * card <= (double)(1ull << total_range_bits),
+              "quantized_cdf: total_range_bits %d", total_range_bits);
+  lm_cdf_kernel<<<(unsigned)n_rows, kWarps * 32, (size_t)card * sizeof(int), reinterpret_cast<cudaStream_t>(stream)>>>(
+      pdf, cdf, card, cdf_params(card, total_range_bits));
+  ECB_LAUNCHED();
+  return 0;
+}
+
+/* ArithmeticCoder (ac.py:56-166) on the HOST: n symbols given as their cdf ranges [low, high_exclusive) (sym_ranges: HOST
+ * int32 [n][2], e.g. copied back from ecb_lm_forward), pushed in order, then flush(). out: HOST buffer; *out_len = bytes
+ * the reference would have written. Fails when `capacity` is too small (4 * n + 16 always suffices). */
+int ecb_ac_encode(const int32_t* sym_ranges, int64_t n, int32_t total_range_bits, uint8_t* out, int64_t capacity,
+                  int64_t* out_len) {
+  ECB_REQUIRE(sym_ranges && out && out_len && n >= 0, "ac_encode: null argument");
+  ECB_REQUIRE(total_range_bits >= 8 && total_range_bits <= 30, "ac_encode: total_range_bits %d (ac.py:100: <= 30)", total_range_bits);
+  ac::Encoder enc;
+  enc.out = out;
+  enc.cap = capacity;
+  for (int64_t i = 0; i < n; ++i)
+    if (!enc.push(sym_ranges[2 * i], sym_ranges[2 * i + 1], total_range_bits)) {
+      set_error("ac_encode: symbol %lld: %s", (long long)i,
+                enc.status == ac::AC_RANGE_OVERFLOW ? "range representation exceeds 62 bits" : "empty or inverted cdf range");
+      return 1;
+    }
+  enc.flush();
+  ECB_REQUIRE(!enc.overflow, "ac_encode: output buffer of %lld bytes is too small (%lld needed)", (long long)capacity,
+              (long long)enc.n_bytes);
+  *out_len = enc.n_bytes;
+  return 0;
+}
+
+/* ArithmeticDecoder (ac.py:169-260) on the HOST -- the very function the device decoder runs: n symbols, symbol i decoded
+ * against cdfs[i * card .. (i + 1) * card) (HOST int32). symbols: HOST int32 [n]; *bytes_consumed: bytes read from data.
+ * Returns 0, or 1 with the reference's condition in ecb_last_error(). */
+int ecb_ac_decode(const uint8_t* data, int64_t n_bytes, const int32_t* cdfs, int64_t n, int32_t card,
+                  int32_t total_range_bits, int32_t* symbols, int64_t* bytes_consumed) {
+  ECB_REQUIRE(data && cdfs && symbols && n >= 0 && card >= 1, "ac_decode: null argument");
+  ECB_REQUIRE(total_range_bits >= 8 && total_range_bits <= 30, "ac_decode: total_range_bits %d", total_range_bits);
+  ac::Decoder d;
+  ac::decoder_init(d, 0);
+  for (int64_t i = 0; i < n; ++i) {
+    const int s = ac::pull(d, data, n_bytes * 8, cdfs + (size_t)i * card, card, total_range_bits);
+    if (s < 0) {
+      set_error("ac_decode: symbol %lld: %s", (long long)i,
+                d.status == ac::AC_EOF ? "The stream ended sooner than expected." : d.status == ac::AC_SEARCH_FAILED ? "Binary search failed" : "invalid coder state");
+      return 1;
+    }
+    symbols[i] = s;
+  }
+  if (bytes_consumed) *bytes_consumed = ac::bytes_consumed(d);
+  return 0;
+}
+
+}  // extern "C"

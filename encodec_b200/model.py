@@ -56,6 +56,9 @@ class _Frame(dict):
     __slots__ = ("_batched",)
 
 
+ROOT_URL = 'https://dl.fbaipublicfiles.com/encodec/v0/'   # reference model.py:30
+
+
 class EncodecModel(nn.Module):
     """EnCodec model operating on the raw waveform (same constructor as reference model.py:99-110). Inference only."""
     _warned_training = False
@@ -367,8 +370,24 @@ class EncodecModel(nn.Module):
                              f"Select one of {self.target_bandwidths}.")
         self.bandwidth = bandwidth
 
-    def get_lm_model(self):
-        raise NotImplementedError("encodec_b200: the entropy-coding LM is outside the accelerated path (SURVEY.md 8f)")
+    def get_lm_model(self, state_dict: tp.Optional[tp.Dict[str, torch.Tensor]] = None):
+        """Return the associated LM (reference model.py:264-284): ``LMModel(n_q, bins, num_layers=5, dim=200,
+        past_context=int(3.5 * frame_rate))`` on the model's device, in eval mode. The reference downloads the pre-trained
+        checkpoint named after ``self.name``; pass ``state_dict`` to load weights held locally instead (no network here)."""
+        from .lm import LMModel
+        device = next(self.parameters()).device
+        lm = LMModel(self.quantizer.n_q, self.quantizer.bins, num_layers=5, dim=200,
+                     past_context=int(3.5 * self.frame_rate)).to(device)
+        if state_dict is None:
+            checkpoints = {'encodec_24khz': 'encodec_lm_24khz-1608e3c0.th', 'encodec_48khz': 'encodec_lm_48khz-7add9fc3.th'}
+            try:
+                checkpoint_name = checkpoints[self.name]
+            except KeyError:
+                raise RuntimeError("No LM pre-trained for the current Encodec model.")
+            state_dict = torch.hub.load_state_dict_from_url(ROOT_URL + checkpoint_name, map_location='cpu', check_hash=True)
+        lm.load_state_dict(state_dict)
+        lm.eval()
+        return lm
 
     # ---- factories (reference model.py:286-382) ------------------------------------------------------
     @staticmethod

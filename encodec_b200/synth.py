@@ -260,3 +260,53 @@ def calibrated_codebooks(seed: int, mean_vec: np.ndarray, scales: np.ndarray, bi
     cb = hash_normal(seed, "calib-codebook", (n_q, bins, d)) * np.asarray(scales, np.float32)[:, None, None]
     cb[0] += mean_vec.astype(np.float32)[None, :]
     return cb.astype(np.float32)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Language model of the entropy-coded .ecdc stream (reference model.py:45-83, modules/transformer.py:62-119)
+# ---------------------------------------------------------------------------------------------------------------------
+@dataclass
+class LMSpec:
+    """Constructor arguments of the reference's ``LMModel`` as ``EncodecModel.get_lm_model`` passes them (model.py:268-269)."""
+    n_q: int = 32
+    card: int = 1024
+    dim: int = 200
+    num_layers: int = 5
+    num_heads: int = 8
+    hidden_scale: float = 4.0
+    past_context: int = 262           # int(3.5 * frame_rate): 262 at 75 Hz, 525 at 150 Hz
+    max_period: float = 10000.0
+
+    @property
+    def hidden(self) -> int:
+        return int(self.dim * self.hidden_scale)
+
+
+def make_lm_state_dict(spec: LMSpec, seed: int = 0, logit_gain: float = 2.5) -> Dict[str, np.ndarray]:
+    """Deterministic weights with the key layout of the reference's ``LMModel.state_dict()``. ``logit_gain`` sets the
+    spread of the output logits (peaked distributions exercise the coder's minimum-range clamp)."""
+    sd: Dict[str, np.ndarray] = {}
+    d, h = spec.dim, spec.hidden
+
+    def lin(name, n_out, n_in, gain=1.0):
+        sd[name + ".weight"] = hash_symmetric(seed, name + ".weight", (n_out, n_in), gain * math.sqrt(3.0 / n_in))
+        sd[name + ".bias"] = hash_symmetric(seed, name + ".bias", (n_out,), 0.1)
+
+    def norm(name):
+        sd[name + ".weight"] = (1.0 + hash_symmetric(seed, name + ".weight", (d,), 0.2)).astype(np.float32)
+        sd[name + ".bias"] = hash_symmetric(seed, name + ".bias", (d,), 0.1)
+
+    norm("transformer.norm_in")
+    for i in range(spec.num_layers):
+        p = f"transformer.layers.{i}"
+        sd[p + ".self_attn.in_proj_weight"] = hash_symmetric(seed, p + ".in_proj_weight", (3 * d, d), 1.5 * math.sqrt(3.0 / d))
+        sd[p + ".self_attn.in_proj_bias"] = hash_symmetric(seed, p + ".in_proj_bias", (3 * d,), 0.1)
+        lin(p + ".self_attn.out_proj", d, d)
+        lin(p + ".linear1", h, d)
+        lin(p + ".linear2", d, h)
+        norm(p + ".norm1")
+        norm(p + ".norm2")
+    for k in range(spec.n_q):
+        sd[f"emb.{k}.weight"] = hash_normal(seed, f"emb.{k}.weight", (spec.card + 1, d))
+        lin(f"linears.{k}", spec.card, d, gain=logit_gain)
+    return sd

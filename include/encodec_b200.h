@@ -187,6 +187,71 @@ int ecb_debug_tc_conv(const float* a0, int64_t a0_item_stride, int32_t C0, int64
                       int32_t n_items, float* out_raw, float* out_elu, int64_t out_item_stride, int32_t halo,
                       int32_t round_out, int32_t split, void* stream);
 
+/* ---- entropy-coded .ecdc stream: LM + arithmetic coder --------------------------------
+ * compress_to_file / decompress_from_file with use_lm=True (compress.py:63-87,125-152): LMModel (model.py:45-83) over
+ * StreamingTransformerEncoder (modules/transformer.py:62-119), build_stable_quantized_cdf and ArithmeticCoder /
+ * ArithmeticDecoder (quantization/ac.py:18-260). Compression evaluates every step of every frame in one batched pass
+ * and returns the coder's two cdf values per symbol; decompression keeps the whole step loop (LM step -> cdfs -> decoder
+ * pull -> codes of the next step's input) on the device. Both produce bit-identical probabilities by construction. */
+typedef struct ecb_lm_spec {
+  int32_t n_q;            /* codebooks the model was built for (LMModel n_q, model.py:55) */
+  int32_t card;           /* codebook cardinality (2..2048) */
+  int32_t dim;            /* transformer dimension (even, 32..256) */
+  int32_t n_layers;       /* StreamingTransformerEncoder num_layers */
+  int32_t n_heads;        /* num_heads; dim / n_heads <= 32 */
+  int32_t hidden;         /* int(dim * hidden_scale) (32..1024) */
+  int32_t past_context;   /* rows of streaming state kept per layer (transformer.py:117), 1..1400 */
+  float max_period;       /* create_sin_embedding max_period (transformer.py:16) */
+} ecb_lm_spec;
+typedef struct ecb_lm ecb_lm; /* opaque: LM weights on one device */
+
+int ecb_lm_create(const ecb_lm_spec* spec, ecb_lm** out);
+void ecb_lm_destroy(ecb_lm* lm);
+/* key: a key of the reference's LMModel.state_dict() ("transformer.norm_in.weight", "transformer.layers.0.self_attn.
+ * in_proj_weight", "emb.3.weight", "linears.3.bias", ...); data: DEVICE float32, copied. Replaces load_state_dict. */
+int ecb_lm_load_tensor(ecb_lm* lm, const char* key, const float* data, int64_t numel, void* stream);
+/* All tensors present? pos_divisor: optional HOST float32 [dim / 2] = max_period ** (j / (dim / 2 - 1)) as the caller's
+ * framework rounds it (transformer.py:23 is a float32 pow); null: computed in double precision and rounded once. */
+int ecb_lm_finalize(ecb_lm* lm, const float* pos_divisor, void* stream);
+/* Streaming state of n_items independent streams of <= capacity steps (the reference's `states`, transformer.py:99-118,
+ * kept as projected keys / values): float32 [n_layers][n_items][capacity + 1][2 * dim], caller-owned, any content. */
+size_t ecb_lm_cache_bytes(ecb_lm* lm, int64_t n_items, int64_t capacity);
+size_t ecb_lm_workspace_bytes(ecb_lm* lm, int64_t n_rows, int64_t n_codebooks);
+/* LMModel.forward (model.py:65-83) for steps t0 .. t0 + n_t - 1 of n_items streams whose steps < t0 are in `cache`.
+ * tokens (DEVICE int64): element (item, k, t) at tokens[item * item_stride + k * k_stride + t * t_stride];
+ *   tokens_are_codes = 0: the LM's input indices of the n_t steps (1 + previous code, 0 = none), t counted from t0;
+ *   tokens_are_codes = 1: the codes of the whole frame, t absolute (step t is fed 1 + code[t - 1], 0 at t = 0: compress.py:69,78).
+ * Outputs (DEVICE, each may be null): probas float32 [n_items][n_t][K][card] (the reference returns it permuted to
+ * [B, card, K, T]); cdf int32, same shape = build_stable_quantized_cdf(probas[..], 24, check=False) (ac.py:18-53);
+ * sym_ranges int32 [n_items][n_t][K][2] (needs tokens_are_codes = 1) = (cdf[s - 1] or 0, cdf[s]) of the code s at
+ * (item, k, t): the two numbers ArithmeticCoder.push reads (ac.py:143-144). workspace: ecb_lm_workspace_bytes(n_items * n_t, K). */
+int ecb_lm_forward(ecb_lm* lm, const int64_t* tokens, int64_t item_stride, int64_t k_stride, int64_t t_stride,
+                   int32_t tokens_are_codes, int64_t n_items, int64_t n_codebooks, int64_t t0, int64_t n_t, float* cache,
+                   int64_t capacity, float* probas, int32_t* cdf, int32_t* sym_ranges, void* workspace,
+                   size_t workspace_bytes, void* stream);
+/* The decoding loop of decompress_from_file for ONE frame (compress.py:125-152), enqueued as a whole: for every step the LM,
+ * the quantised cdfs, ArithmeticDecoder.pull for the K codebooks, codes[k][t]. data: DEVICE bytes of the stream, this
+ * frame's coder starts at byte first_byte; codes: DEVICE int64 [K][n_steps]; cache: capacity >= n_steps, 1 item;
+ * result: DEVICE int64 [2] = (status: 0 ok, 1 "The stream ended sooner than expected", 2 "Binary search failed",
+ * 3 range overflow, 4 bad cdf; bytes of data consumed up to the end of this frame, i.e. where the next frame starts).
+ * workspace: ecb_lm_workspace_bytes(1, K). */
+int ecb_lm_decode_frame(ecb_lm* lm, const uint8_t* data, int64_t n_bytes, int64_t first_byte, int64_t n_codebooks,
+                        int64_t n_steps, int64_t* codes, float* cache, int64_t capacity, int64_t* result, void* workspace,
+                        size_t workspace_bytes, void* stream);
+/* build_stable_quantized_cdf (ac.py:18-53, check=False) alone, in the float32 arithmetic of the reference's CPU tensors:
+ * pdf DEVICE float32 [n_rows][card] -> cdf DEVICE int32 [n_rows][card]. Bit-exact. */
+int ecb_quantized_cdf(const float* pdf, int64_t n_rows, int32_t card, int32_t total_range_bits, int32_t* cdf, void* stream);
+/* ArithmeticCoder (ac.py:56-166) on the HOST (no GPU involved): n symbols given as their cdf ranges [low, high_exclusive)
+ * (sym_ranges: HOST int32 [n][2], e.g. copied back from ecb_lm_forward), pushed in order, then flush(). out: HOST buffer of
+ * `capacity` bytes (4 * n + 16 always suffices); *out_len = the bytes the reference writes. Bit-exact. */
+int ecb_ac_encode(const int32_t* sym_ranges, int64_t n, int32_t total_range_bits, uint8_t* out, int64_t capacity,
+                  int64_t* out_len);
+/* ArithmeticDecoder (ac.py:169-260) on the HOST -- the same function the device loop of ecb_lm_decode_frame runs: symbol i
+ * is decoded against cdfs[i * card .. (i + 1) * card) (HOST int32). symbols: HOST int32 [n]; *bytes_consumed (may be null):
+ * bytes read from data. Errors carry the reference's messages. */
+int ecb_ac_decode(const uint8_t* data, int64_t n_bytes, const int32_t* cdfs, int64_t n, int32_t card,
+                  int32_t total_range_bits, int32_t* symbols, int64_t* bytes_consumed);
+
 /* Per-kernel-class timing for bench.py's roofline leg. Between ecb_profile_begin() and ecb_profile_end()
  * every launch of this library is bracketed by CUDA events on its stream; ecb_profile_end() synchronises
  * them and returns one entry per kernel class that ran: launch count, summed device milliseconds, and the

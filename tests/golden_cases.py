@@ -47,3 +47,39 @@ def load_rvq_case(name=RVQ_CASE):
 def frames_of(t_bdt):
     """[B, D, T] -> [B*T, D]"""
     return np.ascontiguousarray(np.transpose(t_bdt, (0, 2, 1))).reshape(-1, t_bdt.shape[1])
+
+
+# --- entropy-coded stream (SURVEY 8f row 4): tests/golden/lm_ac.npz, made by oracle/make_golden_lm.py -----------------
+# name -> (LMSpec, K codebooks in the frame, T steps, seed). "lm24_k8": the LM EncodecModel.get_lm_model builds for the
+# 24 kHz model (model.py:268-269) on a 6 kbps frame; "lmsmall": odd sizes, window (past_context) shorter than the frame.
+LM_CASES = {
+    "lm24_k8": (synth.LMSpec(n_q=32, card=1024, dim=200, num_layers=5, num_heads=8, past_context=262), 8, 24, 11),
+    "lmsmall": (synth.LMSpec(n_q=3, card=96, dim=64, num_layers=2, num_heads=4, past_context=5), 3, 23, 12),
+}
+# name -> (cardinality, steps, seed): the shape of the reference's own coder test (ac.py:263-285)
+AC_CASES = {"ac_card2": (2, 400, 21), "ac_card37": (37, 300, 22), "ac_card1024": (1024, 200, 23), "ac_card3999": (3999, 120, 24)}
+
+
+def lm_case_codes(spec, K, T, seed):
+    """codes [K, T] int64 of an LM case."""
+    u = synth.hash_uniform(seed, "lm-codes", K * T)
+    return np.minimum((u * spec.card).astype(np.int64), spec.card - 1).reshape(K, T)
+
+
+def ac_case_pdfs(card, steps, seed):
+    """(pdfs [steps, card] float32, symbols [steps] int64); every pdf value is n / 2**20 with integer n >= 1, so the
+    float32 tensors are reproduced bit for bit anywhere; symbols are drawn from the pdf with integer arithmetic."""
+    total = 1 << 20
+    u = synth.hash_uniform(seed, "ac-pdf", steps * card).reshape(steps, card) ** 6
+    mass = total - 64                      # just under 1, so the reference's own range check (ac.py:50) holds
+    n = np.floor(u / u.sum(axis=1, keepdims=True) * (mass - card)).astype(np.int64) + 1
+    n[:, 0] += mass - n.sum(axis=1)
+    assert (n >= 1).all() and (n.sum(axis=1) == mass).all()
+    pdfs = (n.astype(np.float64) / total).astype(np.float32)
+    thr = np.minimum((synth.hash_uniform(seed, "ac-sym", steps) * mass).astype(np.int64), mass - 1)
+    symbols = np.array([int(np.searchsorted(np.cumsum(n[i]), thr[i], side="right")) for i in range(steps)], dtype=np.int64)
+    return pdfs, symbols
+
+
+def load_lm_golden():
+    return np.load(os.path.join(GOLDEN_DIR, "lm_ac.npz"))

@@ -70,5 +70,5 @@ def test_compress_decompress_round_trip(kind):
             body.write(struct.pack("!f", f["scale"].cpu().item()))
         body.write(eo.pack_frame(f["codes"][0].cpu().numpy(), m.bits_per_codebook))
     assert blob.endswith(body.getvalue())
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError, match="No LM pre-trained"):      # reference model.py:275-278: unknown model name
         ec.compress(m, wav, use_lm=True)
