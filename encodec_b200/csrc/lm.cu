@@ -24,6 +24,7 @@
 // position p. These are CUDA-core kernels: the work is a few MFLOP per step and latency-bound (decode) or a few GFLOP per
 // call (compress); what matters is the launch count and that nothing returns to the host inside the loop.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -40,7 +41,9 @@ namespace {
 constexpr int kWarps = 8;        // warps per block of the row kernels
 constexpr int kRowTile = 8;      // rows that share one weight fetch in lm_linear
 constexpr int kColsPerWarp = 4;  // output columns a warp walks in lm_linear
-constexpr int kLogitRows = 4;    // rows per block in lm_logits
+constexpr int kHeadRows = 1024;  // rows whose logits are materialised at a time ([rows][K * card] floats of workspace)
+constexpr int kAcThreads = 512;  // block of the decoder-pull kernel (stages the cdfs; warp 0 decodes)
+constexpr int kAcSmem = 160 * 1024;
 constexpr int kMaxDimPerLane = 8;  // dim <= 256
 
 struct CdfParams {
@@ -98,22 +101,29 @@ __device__ __forceinline__ void warp_layer_norm(float (&v)[kMaxDimPerLane], int 
 // model.py:79 (sum of embeddings) + transformer.py:106-111 (norm_in, + sinusoidal position embedding). One warp per row.
 __global__ void lm_embed_kernel(Tokens tk, const float* __restrict__ emb, const float* __restrict__ nw,
                                 const float* __restrict__ nb, const float* __restrict__ pos_div, float* __restrict__ x,
-                                long long n_rows, int n_t, long long t0, int K, int card, int dim, float eps) {
+                                long long n_rows, int n_t, long long t0_arg, const long long* __restrict__ t_ptr, int K,
+                                int card, int dim, float eps) {
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5);
   if (row >= n_rows) return;
+  const long long t0 = t_ptr ? *t_ptr : t0_arg;   // the decoding loop replays one captured step: t lives on the device
   const long long item = row / n_t;
   const long long t = t0 + row % n_t;
   float v[kMaxDimPerLane];
 #pragma unroll
   for (int i = 0; i < kMaxDimPerLane; ++i) v[i] = 0.f;
-  for (int k = 0; k < K; ++k) {
-    const long long idx = token_index(tk, item, k, t, t0, card);
-    const float* e = emb + ((size_t)k * (card + 1) + (size_t)idx) * dim;
+  for (int k0 = 0; k0 < K; k0 += 32) {   // the indices first (one lane per codebook), so that the row loads do not wait on them
+    const long long mine = (k0 + lane < K) ? token_index(tk, item, k0 + lane, t, t0, card) : 0;
+    const int g = (K - k0) < 32 ? (K - k0) : 32;
+#pragma unroll 4
+    for (int kk = 0; kk < g; ++kk) {       // summed in codebook order, as the reference's sum([...]) (model.py:79)
+      const long long idx = __shfl_sync(0xffffffffu, mine, kk);
+      const float* e = emb + ((size_t)(k0 + kk) * (card + 1) + (size_t)idx) * dim;
 #pragma unroll
-    for (int i = 0; i < kMaxDimPerLane; ++i) {
-      const int d = lane + 32 * i;
-      if (d < dim) v[i] += e[d];
+      for (int i = 0; i < kMaxDimPerLane; ++i) {
+        const int d = lane + 32 * i;
+        if (d < dim) v[i] += e[d];
+      }
     }
   }
   warp_layer_norm(v, dim, lane, nw, nb, eps);
@@ -149,25 +159,27 @@ __global__ void lm_ln_kernel(const float* __restrict__ in, float* __restrict__ o
   }
 }
 
-enum { EPI_QKV = 0, EPI_GELU = 1, EPI_RESID = 2 };
+enum { EPI_QKV = 0, EPI_GELU = 1, EPI_RESID = 2, EPI_PLAIN = 3 };
 struct LinArgs {
   const float* x;       // [n_rows][K]
   const float* W;       // [N][K] (nn.Linear layout)
   const float* b;       // [N]
   int K, N;
   long long n_rows;
-  float* out;           // GELU / RESID: [n_rows][N]; QKV: q [n_rows][dim]
+  float* out;           // GELU / RESID / PLAIN: [n_rows][N]; QKV: q [n_rows][dim]
   const float* resid;   // RESID: out = resid + (W x + b)
   float* cache;         // QKV: this layer's cache, [n_items][capacity + 1][2 * dim]
   long long capacity;
   int n_t;
   long long t0;
+  const long long* t_ptr;
   int dim;
 };
 
-// y[r][n] = epilogue(b[n] + sum_k W[n][k] x[r][k]). A warp owns an output column: the weight row sits in registers (KPL values
-// per lane, k = lane + 32 i), the rows of the tile come from shared memory; lane-local fmaf chain in i order, then the xor
-// tree -- the same sequence for every row, whatever the launch shape.
+// y[r][n] = epilogue(b[n] + sum_k W[n][k] x[r][k]). A warp owns kColsPerWarp output columns: their weight rows sit in
+// registers (KPL values per lane and column, k = lane + 32 i; all loads of the warp are in flight together), the rows of
+// the tile come from shared memory; per (row, column) a lane-local fmaf chain in i order, then the xor tree -- the same
+// sequence for every row, whatever the launch shape.
 template <int KPL, int EPI>
 __global__ void __launch_bounds__(kWarps * 32) lm_linear_kernel(LinArgs a) {
   extern __shared__ float xs[];   // [kRowTile][K]
@@ -176,58 +188,79 @@ __global__ void __launch_bounds__(kWarps * 32) lm_linear_kernel(LinArgs a) {
   const int nr = (int)((a.n_rows - r0) < kRowTile ? (a.n_rows - r0) : kRowTile);
   for (int i = threadIdx.x; i < nr * a.K; i += blockDim.x) xs[i] = a.x[r0 * a.K + i];
   __syncthreads();
+  const int n0 = (blockIdx.x * kWarps + warp) * kColsPerWarp;
+  if (n0 >= a.N) return;   // warp-uniform, no block-wide barrier below
+  float w[kColsPerWarp][KPL], bias[kColsPerWarp];
+#pragma unroll
   for (int c = 0; c < kColsPerWarp; ++c) {
-    const int n = (blockIdx.x * kWarps + warp) * kColsPerWarp + c;
-    if (n >= a.N) break;   // warp-uniform
-    float w[KPL];
+    const int n = n0 + c;
 #pragma unroll
     for (int i = 0; i < KPL; ++i) {
       const int k = lane + 32 * i;
-      w[i] = k < a.K ? a.W[(size_t)n * a.K + k] : 0.f;
+      w[c][i] = (n < a.N && k < a.K) ? a.W[(size_t)n * a.K + k] : 0.f;
     }
-    const float bias = a.b[n];
-    for (int r = 0; r < nr; ++r) {
-      float acc = 0.f;
+    bias[c] = n < a.N ? a.b[n] : 0.f;
+  }
+  const long long t0 = (EPI == EPI_QKV && a.t_ptr) ? *a.t_ptr : a.t0;
+  for (int r = 0; r < nr; ++r) {
+    float acc[kColsPerWarp];
 #pragma unroll
-      for (int i = 0; i < KPL; ++i) {
-        const int k = lane + 32 * i;
-        if (k < a.K) acc = fmaf(w[i], xs[r * a.K + k], acc);
+    for (int c = 0; c < kColsPerWarp; ++c) acc[c] = 0.f;
+#pragma unroll
+    for (int i = 0; i < KPL; ++i) {
+      const int k = lane + 32 * i;
+      if (k < a.K) {
+        const float xv = xs[r * a.K + k];
+#pragma unroll
+        for (int c = 0; c < kColsPerWarp; ++c) acc[c] = fmaf(w[c][i], xv, acc[c]);
       }
-      acc = warp_sum(acc);
-      if (lane == 0) {
-        const long long row = r0 + r;
-        const float v = acc + bias;
-        if (EPI == EPI_GELU) {
-          a.out[row * a.N + n] = 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));   // F.gelu (exact, erf form)
-        } else if (EPI == EPI_RESID) {
-          a.out[row * a.N + n] = a.resid[row * a.N + n] + v;
+    }
+#pragma unroll
+    for (int c = 0; c < kColsPerWarp; ++c) acc[c] = warp_sum(acc[c]);
+    float v = 0.f;   // lane c finishes column n0 + c
+#pragma unroll
+    for (int c = 0; c < kColsPerWarp; ++c)
+      if (lane == c) v = acc[c] + bias[c];
+    const int n = n0 + lane;
+    if (lane < kColsPerWarp && n < a.N) {
+      const long long row = r0 + r;
+      if (EPI == EPI_GELU) {
+        a.out[row * a.N + n] = 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));   // F.gelu (exact, erf form)
+      } else if (EPI == EPI_RESID) {
+        a.out[row * a.N + n] = a.resid[row * a.N + n] + v;
+      } else if (EPI == EPI_PLAIN) {
+        a.out[row * a.N + n] = v;
+      } else {
+        if (n < a.dim) {
+          a.out[row * a.dim + n] = v;
         } else {
-          if (n < a.dim) {
-            a.out[row * a.dim + n] = v;
-          } else {
-            const long long item = row / a.n_t, t = a.t0 + row % a.n_t;
-            float* base = a.cache + (size_t)item * (a.capacity + 1) * 2 * a.dim;
-            base[(size_t)(t + 1) * 2 * a.dim + (n - a.dim)] = v;
-            if (t == 0) base[n - a.dim] = bias;   // projections of the reference's all-zero seed row: W 0 + b
-          }
+          const long long item = row / a.n_t, t = t0 + row % a.n_t;
+          float* base = a.cache + (size_t)item * (a.capacity + 1) * 2 * a.dim;
+          base[(size_t)(t + 1) * 2 * a.dim + (n - a.dim)] = v;
+          if (t == 0) base[n - a.dim] = a.b[n];   // projections of the reference's all-zero seed row: W 0 + b
         }
       }
     }
   }
 }
 
-// _sa_block (transformer.py:42-59) for one (row, head) per warp: keys / values = cache rows [lo, t + 1], lo = t + 1 - min(t + 1,
-// past_context) (the rows the streaming state still holds, transformer.py:116-117) -- scores by lanes over keys, softmax,
-// weighted values by lanes over the head dimension, keys in window order.
-__global__ void lm_attn_kernel(const float* __restrict__ q, const float* __restrict__ cache, float* __restrict__ out,
-                               long long n_rows, int n_t, long long t0, long long capacity, int dim, int heads,
-                               int past_context) {
-  extern __shared__ float sm[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float* sc = sm + (size_t)warp * (past_context + 1 + 32);
-  float* sq = sc + past_context + 1;
-  const long long w = (long long)blockIdx.x * kWarps + warp;
-  if (w >= n_rows * heads) return;
+// _sa_block (transformer.py:42-59) for one (row, head) per block: keys / values = cache rows [lo, t + 1], lo = t + 1 - min(t + 1,
+// past_context) (the rows the streaming state still holds, transformer.py:116-117). Thread j owns keys j, j + 256, ...: its
+// scores stay in registers, max and sum are block reductions, the weighted values are per-thread partial sums per head
+// dimension reduced by the xor tree and then across the warps in warp order -- one partition for every launch shape, and
+// in the decoding loop (one row) a key costs one memory latency instead of a serial walk.
+constexpr int kAttnThreads = 256;
+constexpr int kAttnKeys = 6;   // keys per thread: past_context + 1 <= 6 * 256
+__global__ void __launch_bounds__(kAttnThreads) lm_attn_kernel(const float* __restrict__ q, const float* __restrict__ cache,
+                                                                float* __restrict__ out, int n_t, long long t0_arg,
+                                                                const long long* __restrict__ t_ptr, long long capacity, int dim,
+                                                                int heads, int past_context) {
+  __shared__ float sq[32];
+  __shared__ float red[kAttnThreads / 32];
+  __shared__ float part[kAttnThreads / 32][32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long w = blockIdx.x;
+  const long long t0 = t_ptr ? *t_ptr : t0_arg;
   const long long row = w / heads;
   const int h = (int)(w % heads);
   const long long item = row / n_t, t = t0 + row % n_t;
@@ -236,32 +269,69 @@ __global__ void lm_attn_kernel(const float* __restrict__ q, const float* __restr
   const long long lo = t + 1 - n_past;
   const int nk = (int)n_past + 1;
   const float* kv = cache + ((size_t)item * (capacity + 1) + (size_t)lo) * 2 * dim + h * hd;
-  if (lane < hd) sq[lane] = q[row * dim + h * hd + lane];
-  __syncwarp();
+  if (tid < hd) sq[tid] = q[row * dim + h * hd + tid];
+  __syncthreads();
   const float scale = 1.f / sqrtf((float)hd);
+  float sc[kAttnKeys];
   float m = -INFINITY;
-  for (int i = lane; i < nk; i += 32) {
-    const float* kr = kv + (size_t)i * 2 * dim;
-    float s = 0.f;
-    for (int d = 0; d < hd; ++d) s = fmaf(sq[d], kr[d], s);
-    s *= scale;
-    sc[i] = s;
-    m = fmaxf(m, s);
+#pragma unroll
+  for (int u = 0; u < kAttnKeys; ++u) {
+    const int i = tid + kAttnThreads * u;
+    sc[u] = -INFINITY;
+    if (i < nk) {
+      const float* kr = kv + (size_t)i * 2 * dim;
+      float s = 0.f;
+#pragma unroll
+      for (int d = 0; d < 32; ++d)
+        if (d < hd) s = fmaf(sq[d], kr[d], s);
+      s *= scale;
+      sc[u] = s;
+      m = fmaxf(m, s);
+    }
   }
   m = warp_max(m);
+  if (lane == 0) red[warp] = m;
+  __syncthreads();
+  m = red[0];
+#pragma unroll
+  for (int w2 = 1; w2 < kAttnThreads / 32; ++w2) m = fmaxf(m, red[w2]);
+  __syncthreads();
   float l = 0.f;
-  for (int i = lane; i < nk; i += 32) {
-    const float e = expf(sc[i] - m);
-    sc[i] = e;
-    l += e;
+  float acc[32];
+#pragma unroll
+  for (int d = 0; d < 32; ++d) acc[d] = 0.f;
+#pragma unroll
+  for (int u = 0; u < kAttnKeys; ++u) {
+    const int i = tid + kAttnThreads * u;
+    if (i < nk) {
+      const float e = expf(sc[u] - m);
+      l += e;
+      const float* vr = kv + dim + (size_t)i * 2 * dim;
+#pragma unroll
+      for (int d = 0; d < 32; ++d)
+        if (d < hd) acc[d] = fmaf(e, vr[d], acc[d]);
+    }
   }
   l = warp_sum(l);
-  __syncwarp();
-  if (lane < hd) {
-    const float* vr = kv + dim + lane;
-    float acc = 0.f;
-    for (int i = 0; i < nk; ++i) acc = fmaf(sc[i], vr[(size_t)i * 2 * dim], acc);
-    out[row * dim + h * hd + lane] = acc / l;
+  float o = 0.f;
+#pragma unroll
+  for (int d = 0; d < 32; ++d) {
+    if (d < hd) {   // block-uniform
+      const float r = warp_sum(acc[d]);
+      if (lane == d) o = r;
+    }
+  }
+  if (lane == 0) red[warp] = l;
+  if (lane < hd) part[warp][lane] = o;
+  __syncthreads();
+  if (tid < hd) {
+    float L = red[0], O = part[0][tid];
+#pragma unroll
+    for (int w2 = 1; w2 < kAttnThreads / 32; ++w2) {
+      L += red[w2];
+      O += part[w2][tid];
+    }
+    out[row * dim + h * hd + tid] = O / L;
   }
 }
 
@@ -295,91 +365,64 @@ __device__ __forceinline__ void block_cumsum(int* vals, int card, int* wsum) {
   __syncthreads();
 }
 
-// model.py:81-83 (per-codebook Linear + softmax over the codebook) + ac.py:18-53 for kLogitRows rows and ONE codebook per
-// block. Outputs (each optional): probabilities, the quantised cdf, and for compression the coder's pair
-// (cdf[s - 1], cdf[s]) of the symbol s actually coded at (item, k, t).
-template <int KPL>
-__global__ void __launch_bounds__(kWarps * 32) lm_logits_kernel(const float* __restrict__ x, const float* __restrict__ W,
-                                                                 const float* __restrict__ B, long long n_rows, int dim, int card,
-                                                                 int K, Tokens tk, int n_t, long long t0, CdfParams cp,
-                                                                 float* __restrict__ probas, int* __restrict__ cdf,
-                                                                 int* __restrict__ sym_ranges) {
-  extern __shared__ float sm[];
-  float* xs = sm;                                  // [kLogitRows][dim]
-  float* lg = xs + kLogitRows * dim;               // [kLogitRows][card]
+// softmax over the codebook (model.py:83) + ac.py:18-53 for one (row, codebook) per block, from the logits the per-codebook
+// Linear layers (model.py:81-82; one lm_linear launch over the concatenated [K * card][dim] weights) left in `logits`.
+// Outputs (each optional): probabilities, the quantised cdf, and for compression the coder's pair (cdf[s - 1], cdf[s]) of
+// the symbol s actually coded at (item, k, t).
+__global__ void __launch_bounds__(kWarps * 32) lm_softmax_cdf_kernel(const float* __restrict__ logits, long long row0, int card,
+                                                                      int K, Tokens tk, int n_t, long long t0_arg,
+                                                                      const long long* __restrict__ t_ptr, CdfParams cp,
+                                                                      float* __restrict__ probas, int* __restrict__ cdf,
+                                                                      int* __restrict__ sym_ranges) {
+  extern __shared__ float row[];   // [card]
   __shared__ float red[kWarps];
   __shared__ int wsum[kWarps];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int k = blockIdx.y;
-  const long long r0 = (long long)blockIdx.x * kLogitRows;
-  const int nr = (int)((n_rows - r0) < kLogitRows ? (n_rows - r0) : kLogitRows);
-  for (int i = tid; i < nr * dim; i += blockDim.x) xs[i] = x[r0 * dim + i];
+  const long long grow = row0 + blockIdx.x;
+  const float* src = logits + ((size_t)blockIdx.x * K + k) * card;
+  float m = -INFINITY;
+  for (int n = tid; n < card; n += blockDim.x) {
+    const float v = src[n];
+    row[n] = v;
+    m = fmaxf(m, v);
+  }
+  m = warp_max(m);
+  if (lane == 0) red[warp] = m;
   __syncthreads();
-  const float* Wk = W + (size_t)k * card * dim;
-  const float* Bk = B + (size_t)k * card;
-  for (int n = warp; n < card; n += kWarps) {
-    float w[KPL];
+  m = red[0];
 #pragma unroll
-    for (int i = 0; i < KPL; ++i) {
-      const int kk = lane + 32 * i;
-      w[i] = kk < dim ? Wk[(size_t)n * dim + kk] : 0.f;
-    }
-    const float bias = Bk[n];
-    for (int r = 0; r < nr; ++r) {
-      float acc = 0.f;
+  for (int w2 = 1; w2 < kWarps; ++w2) m = fmaxf(m, red[w2]);
+  __syncthreads();
+  float s = 0.f;
+  for (int n = tid; n < card; n += blockDim.x) {
+    const float e = expf(row[n] - m);
+    row[n] = e;
+    s += e;
+  }
+  s = warp_sum(s);
+  if (lane == 0) red[warp] = s;
+  __syncthreads();
+  float total = red[0];
 #pragma unroll
-      for (int i = 0; i < KPL; ++i) {
-        const int kk = lane + 32 * i;
-        if (kk < dim) acc = fmaf(w[i], xs[r * dim + kk], acc);
-      }
-      acc = warp_sum(acc);
-      if (lane == 0) lg[r * card + n] = acc + bias;
-    }
+  for (int w2 = 1; w2 < kWarps; ++w2) total += red[w2];
+  int* irow = reinterpret_cast<int*>(row);
+  for (int n = tid; n < card; n += blockDim.x) {
+    const float p = __fdiv_rn(row[n], total);
+    if (probas) probas[((size_t)grow * K + k) * card + n] = p;
+    irow[n] = pdf_to_range(p, cp);
   }
   __syncthreads();
-  for (int r = 0; r < nr; ++r) {
-    float* row = lg + r * card;
-    const long long grow = r0 + r;
-    // softmax over the codebook (model.py:83)
-    float m = -INFINITY;
-    for (int n = tid; n < card; n += blockDim.x) m = fmaxf(m, row[n]);
-    m = warp_max(m);
-    if (lane == 0) red[warp] = m;
-    __syncthreads();
-    m = red[0];
-#pragma unroll
-    for (int w2 = 1; w2 < kWarps; ++w2) m = fmaxf(m, red[w2]);
-    __syncthreads();
-    float s = 0.f;
-    for (int n = tid; n < card; n += blockDim.x) {
-      const float e = expf(row[n] - m);
-      row[n] = e;
-      s += e;
-    }
-    s = warp_sum(s);
-    if (lane == 0) red[warp] = s;
-    __syncthreads();
-    float total = red[0];
-#pragma unroll
-    for (int w2 = 1; w2 < kWarps; ++w2) total += red[w2];
-    int* irow = reinterpret_cast<int*>(row);
-    for (int n = tid; n < card; n += blockDim.x) {
-      const float p = __fdiv_rn(row[n], total);
-      if (probas) probas[((size_t)grow * K + k) * card + n] = p;
-      irow[n] = pdf_to_range(p, cp);
-    }
-    __syncthreads();
-    block_cumsum(irow, card, wsum);
-    if (cdf)
-      for (int n = tid; n < card; n += blockDim.x) cdf[((size_t)grow * K + k) * card + n] = irow[n];
-    if (sym_ranges && tid == 0) {
-      const long long item = grow / n_t, t = t0 + grow % n_t;
-      long long sv = tk.p[item * tk.item_stride + k * tk.k_stride + t * tk.t_stride];
-      sv = sv < 0 ? 0 : (sv >= card ? card - 1 : sv);
-      sym_ranges[((size_t)grow * K + k) * 2 + 0] = sv ? irow[sv - 1] : 0;
-      sym_ranges[((size_t)grow * K + k) * 2 + 1] = irow[sv];
-    }
-    __syncthreads();
+  block_cumsum(irow, card, wsum);
+  if (cdf)
+    for (int n = tid; n < card; n += blockDim.x) cdf[((size_t)grow * K + k) * card + n] = irow[n];
+  if (sym_ranges && tid == 0) {
+    const long long t0 = t_ptr ? *t_ptr : t0_arg;
+    const long long item = grow / n_t, t = t0 + grow % n_t;
+    long long sv = tk.p[item * tk.item_stride + k * tk.k_stride + t * tk.t_stride];
+    sv = sv < 0 ? 0 : (sv >= card ? card - 1 : sv);
+    sym_ranges[((size_t)grow * K + k) * 2 + 0] = sv ? irow[sv - 1] : 0;
+    sym_ranges[((size_t)grow * K + k) * 2 + 1] = irow[sv];
   }
 }
 
@@ -395,21 +438,122 @@ __global__ void __launch_bounds__(kWarps * 32) lm_cdf_kernel(const float* __rest
   for (int n = threadIdx.x; n < card; n += blockDim.x) cdf[row * card + n] = iv[n];
 }
 
-// ArithmeticDecoder.pull for the K codebooks of step t (compress.py:137-148): one thread, the stream and the decoder state
-// stay on the device; writes the codes the next step's embedding reads.
-__global__ void lm_ac_init_kernel(ac::Decoder* st, long long first_bit) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) ac::decoder_init(*st, first_bit);
-}
-__global__ void lm_ac_pull_kernel(ac::Decoder* st, const unsigned char* __restrict__ data, long long n_bits,
-                                  const int* __restrict__ cdf, int K, int card, int bits, long long* __restrict__ codes,
-                                  long long k_stride, long long t) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  ac::Decoder d = *st;
-  for (int k = 0; k < K; ++k) {
-    const int s = ac::pull(d, data, n_bits, cdf + (size_t)k * card, card, bits);
-    codes[k * k_stride + t] = s < 0 ? 0 : s;
+// ArithmeticDecoder.pull (ac.py:214-260) by one warp: every lane carries the same decoder state; the reference's binary search
+// for the symbol whose range holds `current` becomes a 32-ary search (lane j tests candidate base + j * step with one
+// rounded double product each, a ballot picks the last candidate whose lower bound is <= current). The ranges of
+// consecutive symbols are disjoint and ordered, so the last symbol whose lower bound is <= current is the only one that can
+// contain it: the symbol, the new (low, high) and the failure condition are the reference's (ac_core.h is the scalar form
+// the host runs; tests decode the reference's own streams through both).
+__device__ __forceinline__ int ac_pull_warp(ac::Decoder& d, const unsigned char* __restrict__ data, long long n_bits,
+                                            const int* cdf, int card, int bits, int lane) {
+  if (d.status != ac::AC_OK) return -1;
+  const uint64_t full = 1ull << bits;
+  while (d.high - d.low + 1 < full) {
+    if (d.bit_pos >= n_bits) {
+      d.status = ac::AC_EOF;
+      return -1;
+    }
+    if (d.max_bit >= 61) {
+      d.status = ac::AC_RANGE_OVERFLOW;
+      return -1;
+    }
+    const uint64_t bit = (data[d.bit_pos >> 3] >> (d.bit_pos & 7)) & 1u;
+    ++d.bit_pos;
+    d.low *= 2;
+    d.high = d.high * 2 + 1;
+    d.current = d.current * 2 + bit;
+    ++d.max_bit;
   }
-  *st = d;
+  const double ratio = ac::scaled_delta(d.high - d.low + 1, bits);
+  int base = 0, span = card;
+  while (span > 1) {
+    const int step = (span + 31) >> 5;
+    const int s = base + lane * step;
+    bool ok = false;
+    if (s < base + span) {
+      const int64_t range_low = s > 0 ? cdf[s - 1] : 0;
+      ok = d.current >= ac::eff_low(range_low, ratio) + d.low;
+    }
+    const unsigned mask = __ballot_sync(0xffffffffu, ok);
+    if (mask == 0) {   // cannot happen: the first candidate's lower bound is <= current by induction
+      d.status = ac::AC_SEARCH_FAILED;
+      return -1;
+    }
+    const int last = 31 - __clz(mask);
+    const int nb = base + last * step;
+    span = min(step, base + span - nb);
+    base = nb;
+  }
+  const int64_t range_low = base > 0 ? cdf[base - 1] : 0;
+  const int64_t range_high = (int64_t)cdf[base] - 1;
+  if (range_high < range_low) {
+    d.status = ac::AC_BAD_CDF;
+    return -1;
+  }
+  const uint64_t low = ac::eff_low(range_low, ratio) + d.low;
+  const uint64_t high = ac::eff_high(range_high, ratio) + d.low;
+  if (d.current < low || d.current > high) {   // "Binary search failed" (ac.py:236): current fell between two ranges
+    d.status = ac::AC_SEARCH_FAILED;
+    return -1;
+  }
+  d.low = low;
+  d.high = high;
+  while (d.max_bit >= 0) {
+    const uint64_t b1 = d.low >> d.max_bit;
+    const uint64_t b2 = d.high >> d.max_bit;
+    if (b1 != b2) break;
+    d.low -= b1 << d.max_bit;
+    d.high -= b1 << d.max_bit;
+    d.current -= b1 << d.max_bit;
+    --d.max_bit;
+  }
+  return base;
+}
+
+// The K symbols of step t (compress.py:137-148) -- or any K consecutive symbols with their cdf rows: the cdfs are staged in
+// shared memory `group` rows at a time by the whole block, warp 0 decodes them in order. The stream, the decoder state and
+// the step counter stay on the device; codes[k * k_stride + t] is what the next step's embedding kernel reads.
+__global__ void lm_ac_init_kernel(ac::Decoder* st, long long first_bit, long long* t_ptr) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    ac::decoder_init(*st, first_bit);
+    if (t_ptr) *t_ptr = 0;
+  }
+}
+__global__ void __launch_bounds__(kAcThreads) lm_ac_pull_kernel(ac::Decoder* st, const unsigned char* __restrict__ data, long long n_bits,
+                                                           const int* __restrict__ cdf, int K, int card, int bits, int group,
+                                                           long long* __restrict__ codes, long long k_stride, long long t_arg,
+                                                           long long* t_ptr) {
+  extern __shared__ __align__(16) int scdf[];   // [group][card]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long t = t_ptr ? *t_ptr : t_arg;
+  ac::Decoder d;
+  if (warp == 0) d = *st;
+  for (int k0 = 0; k0 < K; k0 += group) {
+    const int g = min(group, K - k0);
+    const int total = g * card;
+    const int* src = cdf + (size_t)k0 * card;
+    if (((size_t)src & 15) == 0 && (total & 3) == 0) {
+      const int4* s4 = reinterpret_cast<const int4*>(src);
+      int4* d4 = reinterpret_cast<int4*>(scdf);
+#pragma unroll 8
+      for (int i = tid; i < (total >> 2); i += kAcThreads) d4[i] = s4[i];
+    } else {
+#pragma unroll 8
+      for (int i = tid; i < total; i += kAcThreads) scdf[i] = src[i];
+    }
+    __syncthreads();
+    if (warp == 0) {
+      for (int k = 0; k < g; ++k) {
+        const int s = ac_pull_warp(d, data, n_bits, scdf + k * card, card, bits, lane);
+        if (lane == 0) codes[(k0 + k) * k_stride + t] = s < 0 ? 0 : s;
+      }
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    *st = d;
+    if (t_ptr) *t_ptr = t + 1;
+  }
 }
 __global__ void lm_ac_result_kernel(const ac::Decoder* st, long long* result) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
@@ -477,9 +621,10 @@ CdfParams cdf_params(int card, int bits) {
 }
 
 struct Workspace {
-  float *x, *y, *q, *att, *hid;
+  float *x, *y, *q, *att, *hid, *logits;
   int* cdf;              // decode: [K][card]
   ac::Decoder* dec;
+  long long* step;       // decode: the step counter the captured step reads and the pull kernel advances
 };
 
 size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -491,27 +636,30 @@ size_t plan_workspace(const LmSpec& sp, long long n_rows, long long K, Workspace
     off += align256(bytes);
     return p;
   };
+  const long long head_rows = n_rows < kHeadRows ? n_rows : kHeadRows;
   float* x = (float*)take((size_t)n_rows * sp.dim * 4);
   float* y = (float*)take((size_t)n_rows * sp.dim * 4);
   float* q = (float*)take((size_t)n_rows * sp.dim * 4);
   float* att = (float*)take((size_t)n_rows * sp.dim * 4);
   float* hid = (float*)take((size_t)n_rows * sp.hidden * 4);
+  float* logits = (float*)take((size_t)head_rows * K * sp.card * 4);
   int* cdf = (int*)take((size_t)K * sp.card * 4);
   ac::Decoder* dec = (ac::Decoder*)take(sizeof(ac::Decoder));
-  if (ws) *ws = Workspace{x, y, q, att, hid, cdf, dec};
+  long long* step = (long long*)take(sizeof(long long));
+  if (ws) *ws = Workspace{x, y, q, att, hid, logits, cdf, dec, step};
   return off;
 }
 
 // One pass of the LM over rows (item, t0 .. t0 + n_t - 1): everything up to the transformer output in ws.x.
-int lm_trunk(const Lm& lm, const Tokens& tk, long long n_items, int K, long long t0, long long n_t, float* cache,
-             long long capacity, const Workspace& ws, cudaStream_t s) {
+// t_ptr != null: t0 is read from the device (the captured decoding step).
+int lm_trunk(const Lm& lm, const Tokens& tk, long long n_items, int K, long long t0, const long long* t_ptr, long long n_t,
+             float* cache, long long capacity, const Workspace& ws, cudaStream_t s) {
   const LmSpec& sp = lm.spec;
   const long long n_rows = n_items * n_t;
   const float eps = 1e-5f;
   const unsigned row_blocks = (unsigned)cdiv(n_rows, (long long)kWarps);
-  lm_embed_kernel<<<row_blocks, kWarps * 32, 0, s>>>(tk, lm.weights + lm.emb_off, lm.nin_w, lm.nin_b,
-                                                    lm.weights + lm.pos_off, ws.x, n_rows,
-                                                    (int)n_t, t0, K, sp.card, sp.dim, eps);
+  lm_embed_kernel<<<row_blocks, kWarps * 32, 0, s>>>(tk, lm.weights + lm.emb_off, lm.nin_w, lm.nin_b, lm.weights + lm.pos_off,
+                                                    ws.x, n_rows, (int)n_t, t0, t_ptr, K, sp.card, sp.dim, eps);
   ECB_LAUNCHED();
   const size_t layer_cache = (size_t)n_items * (capacity + 1) * 2 * sp.dim;
   for (int l = 0; l < sp.n_layers; ++l) {
@@ -520,18 +668,16 @@ int lm_trunk(const Lm& lm, const Tokens& tk, long long n_items, int K, long long
     LinArgs a{};
     a.x = ws.x; a.W = lw.in_w; a.b = lw.in_b;
     a.K = sp.dim; a.N = 3 * sp.dim; a.n_rows = n_rows; a.out = ws.q; a.cache = lc; a.capacity = capacity;
-    a.n_t = (int)n_t; a.t0 = t0; a.dim = sp.dim;
+    a.n_t = (int)n_t; a.t0 = t0; a.t_ptr = t_ptr; a.dim = sp.dim;
     if (launch_linear<EPI_QKV>(a, s)) return 1;
-    const size_t attn_smem = (size_t)kWarps * (sp.past_context + 1 + 32) * sizeof(float);
-    lm_attn_kernel<<<(unsigned)cdiv(n_rows * sp.n_heads, (long long)kWarps), kWarps * 32, attn_smem, s>>>(
-        ws.q, lc, ws.att, n_rows, (int)n_t, t0, capacity, sp.dim, sp.n_heads, sp.past_context);
+    lm_attn_kernel<<<(unsigned)(n_rows * sp.n_heads), kAttnThreads, 0, s>>>(ws.q, lc, ws.att, (int)n_t, t0, t_ptr, capacity, sp.dim,
+                                                                         sp.n_heads, sp.past_context);
     ECB_LAUNCHED();
     LinArgs o{};
     o.x = ws.att; o.W = lw.out_w; o.b = lw.out_b;
     o.K = sp.dim; o.N = sp.dim; o.n_rows = n_rows; o.out = ws.y; o.resid = ws.x;
     if (launch_linear<EPI_RESID>(o, s)) return 1;
-    lm_ln_kernel<<<row_blocks, kWarps * 32, 0, s>>>(ws.y, ws.x, lw.n1_w, lw.n1_b, n_rows,
-                                                   sp.dim, eps);
+    lm_ln_kernel<<<row_blocks, kWarps * 32, 0, s>>>(ws.y, ws.x, lw.n1_w, lw.n1_b, n_rows, sp.dim, eps);
     ECB_LAUNCHED();
     LinArgs f1{};
     f1.x = ws.x; f1.W = lw.l1_w; f1.b = lw.l1_b;
@@ -541,31 +687,61 @@ int lm_trunk(const Lm& lm, const Tokens& tk, long long n_items, int K, long long
     f2.x = ws.hid; f2.W = lw.l2_w; f2.b = lw.l2_b;
     f2.K = sp.hidden; f2.N = sp.dim; f2.n_rows = n_rows; f2.out = ws.y; f2.resid = ws.x;
     if (launch_linear<EPI_RESID>(f2, s)) return 1;
-    lm_ln_kernel<<<row_blocks, kWarps * 32, 0, s>>>(ws.y, ws.x, lw.n2_w, lw.n2_b, n_rows,
-                                                   sp.dim, eps);
+    lm_ln_kernel<<<row_blocks, kWarps * 32, 0, s>>>(ws.y, ws.x, lw.n2_w, lw.n2_b, n_rows, sp.dim, eps);
     ECB_LAUNCHED();
   }
   return 0;
 }
 
-int lm_heads(const Lm& lm, const Tokens& tk, long long n_items, int K, long long t0, long long n_t, const Workspace& ws,
-             float* probas, int* cdf, int* sym_ranges, cudaStream_t s) {
+// model.py:81-83 + ac.py:18-53 on the transformer output in ws.x: the K Linear(dim, card) layers as ONE lm_linear launch over
+// their concatenated weights (N = K * card columns: 1024 blocks at K = 32 also when there is a single row), then softmax ->
+// quantised cdf per (row, codebook); kHeadRows rows at a time so that the logits stay a bounded scratch buffer.
+int lm_heads(const Lm& lm, const Tokens& tk, long long n_items, int K, long long t0, const long long* t_ptr, long long n_t,
+             const Workspace& ws, float* probas, int* cdf, int* sym_ranges, cudaStream_t s) {
   const LmSpec& sp = lm.spec;
   const long long n_rows = n_items * n_t;
   const CdfParams cp = cdf_params(sp.card, 24);
-  const size_t smem = (size_t)kLogitRows * (sp.dim + sp.card) * sizeof(float);
-  ECB_REQUIRE(smem <= 48 * 1024, "lm: card = %d is too large for the logits kernel", sp.card);
-  dim3 grid((unsigned)cdiv(n_rows, (long long)kLogitRows), (unsigned)K);
-  const int kpl = (sp.dim + 31) / 32;
-  const float* W = lm.weights + lm.lin_w_off;
-  const float* B = lm.weights + lm.lin_b_off;
-  if (kpl <= 2) lm_logits_kernel<2><<<grid, kWarps * 32, smem, s>>>(ws.x, W, B, n_rows, sp.dim, sp.card, K, tk, (int)n_t, t0, cp, probas, cdf, sym_ranges);
-  else if (kpl <= 4) lm_logits_kernel<4><<<grid, kWarps * 32, smem, s>>>(ws.x, W, B, n_rows, sp.dim, sp.card, K, tk, (int)n_t, t0, cp, probas, cdf, sym_ranges);
-  else if (kpl <= 7) lm_logits_kernel<7><<<grid, kWarps * 32, smem, s>>>(ws.x, W, B, n_rows, sp.dim, sp.card, K, tk, (int)n_t, t0, cp, probas, cdf, sym_ranges);
-  else lm_logits_kernel<8><<<grid, kWarps * 32, smem, s>>>(ws.x, W, B, n_rows, sp.dim, sp.card, K, tk, (int)n_t, t0, cp, probas, cdf, sym_ranges);
+  for (long long r0 = 0; r0 < n_rows; r0 += kHeadRows) {
+    const long long nr = (n_rows - r0) < kHeadRows ? (n_rows - r0) : kHeadRows;
+    LinArgs a{};
+    a.x = ws.x + (size_t)r0 * sp.dim; a.W = lm.weights + lm.lin_w_off; a.b = lm.weights + lm.lin_b_off;
+    a.K = sp.dim; a.N = K * sp.card; a.n_rows = nr; a.out = ws.logits;
+    if (launch_linear<EPI_PLAIN>(a, s)) return 1;
+    dim3 grid((unsigned)nr, (unsigned)K);
+    lm_softmax_cdf_kernel<<<grid, kWarps * 32, (size_t)sp.card * sizeof(float), s>>>(ws.logits, r0, sp.card, K, tk, (int)n_t, t0,
+                                                                                  t_ptr, cp, probas, cdf, sym_ranges);
+    ECB_LAUNCHED();
+  }
+  return 0;
+}
+
+int launch_ac_pull(ac::Decoder* st, const unsigned char* data, long long n_bytes, const int* cdf, long long K, int card, int bits,
+                   long long* codes, long long k_stride, long long t, long long* t_ptr, cudaStream_t s) {
+  int group = kAcSmem / (card * (int)sizeof(int));
+  ECB_REQUIRE(group >= 1, "ac: card = %d does not fit the decoder kernel's shared memory", card);
+  if (group > K) group = (int)K;
+  ECB_CUDA(cudaFuncSetAttribute(lm_ac_pull_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAcSmem));   // per device, cheap
+  lm_ac_pull_kernel<<<1, kAcThreads, (size_t)group * card * sizeof(int), s>>>(st, data, n_bytes * 8, cdf, (int)K, card, bits, group,
+                                                                            codes, k_stride, t, t_ptr);
   ECB_LAUNCHED();
   return 0;
 }
+
+// One captured decoding step, replayed n_steps times (ecb_lm_decode_frame); at most one is kept per LM handle.
+struct StepGraphKey {
+  const void *data, *codes, *cache, *ws;
+  long long n_bytes, K, n_steps, capacity;
+  bool operator==(const StepGraphKey& o) const {
+    return data == o.data && codes == o.codes && cache == o.cache && ws == o.ws && n_bytes == o.n_bytes && K == o.K &&
+           n_steps == o.n_steps && capacity == o.capacity;
+  }
+};
+struct StepGraph {
+  StepGraphKey key{};
+  cudaGraphExec_t exec = nullptr;
+};
+std::map<const Lm*, StepGraph> g_step_graphs;
+cudaStream_t g_lm_capture_stream = nullptr;
 
 int check_call(const Lm* lm, long long n_items, long long K, long long t0, long long n_t, long long capacity) {
   ECB_REQUIRE(lm && lm->finalized, "lm: handle is null or not finalized");
@@ -591,7 +767,7 @@ int ecb_lm_create(const ecb_lm_spec* spec, ecb_lm** out) {
               "lm_create: head dimension must divide dim and be <= 32 (dim %d, heads %d)", spec->dim, spec->n_heads);
   ECB_REQUIRE(spec->hidden >= 32 && spec->hidden <= 1024, "lm_create: hidden %d (32..1024)", spec->hidden);
   ECB_REQUIRE(spec->card >= 2 && spec->card <= 2048, "lm_create: card %d (2..2048)", spec->card);
-  ECB_REQUIRE(spec->n_q >= 1 && spec->n_layers >= 1 && spec->past_context >= 1 && spec->past_context <= 1400,
+  ECB_REQUIRE(spec->n_q >= 1 && spec->n_layers >= 1 && spec->past_context >= 1 && spec->past_context <= 1400 /* kAttnKeys * kAttnThreads - 1 = 1535 keys at most */,
               "lm_create: n_q %d, layers %d, past_context %d (1..1400)", spec->n_q, spec->n_layers, spec->past_context);
   ECB_REQUIRE(2.0 * spec->card <= (double)(1 << 24), "lm_create: card too large for 24 range bits");
   Lm* lm = new Lm();
@@ -646,6 +822,11 @@ int ecb_lm_create(const ecb_lm_spec* spec, ecb_lm** out) {
 void ecb_lm_destroy(ecb_lm* h) {
   Lm* lm = reinterpret_cast<Lm*>(h);
   if (!lm) return;
+  auto it = g_step_graphs.find(lm);
+  if (it != g_step_graphs.end()) {
+    if (it->second.exec) cudaGraphExecDestroy(it->second.exec);
+    g_step_graphs.erase(it);
+  }
   if (lm->weights) cudaFree(lm->weights);
   delete lm;
 }
@@ -731,8 +912,8 @@ int ecb_lm_forward(ecb_lm* h, const int64_t* tokens, int64_t item_stride, int64_
   ECB_REQUIRE(workspace_bytes >= need, "lm_forward: workspace of %zu bytes, %zu needed", workspace_bytes, need);
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   Tokens tk{reinterpret_cast<const long long*>(tokens), item_stride, k_stride, t_stride, tokens_are_codes ? 1 : 0};
-  if (lm_trunk(*lm, tk, n_items, (int)n_codebooks, t0, n_t, cache, capacity, ws, s)) return 1;
-  return lm_heads(*lm, tk, n_items, (int)n_codebooks, t0, n_t, ws, probas, cdf, sym_ranges, s);
+  if (lm_trunk(*lm, tk, n_items, (int)n_codebooks, t0, nullptr, n_t, cache, capacity, ws, s)) return 1;
+  return lm_heads(*lm, tk, n_items, (int)n_codebooks, t0, nullptr, n_t, ws, probas, cdf, sym_ranges, s);
 }
 
 /* The decoding loop of decompress_from_file for ONE frame (compress.py:125-152) without leaving the device: for t in
@@ -754,16 +935,68 @@ int ecb_lm_decode_frame(ecb_lm* h, const uint8_t* data, int64_t n_bytes, int64_t
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const int K = (int)n_codebooks;
   Tokens tk{reinterpret_cast<const long long*>(codes), 0, n_steps, 1, 1};
-  lm_ac_init_kernel<<<1, 32, 0, s>>>(ws.dec, first_byte * 8);
+  long long* lcodes = reinterpret_cast<long long*>(codes);
+  lm_ac_init_kernel<<<1, 32, 0, s>>>(ws.dec, first_byte * 8, ws.step);
   ECB_LAUNCHED();
-  for (long long t = 0; t < n_steps; ++t) {
-    if (lm_trunk(*lm, tk, 1, K, t, 1, cache, capacity, ws, s)) return 1;
-    if (lm_heads(*lm, tk, 1, K, t, 1, ws, nullptr, ws.cdf, nullptr, s)) return 1;
-    lm_ac_pull_kernel<<<1, 32, 0, s>>>(ws.dec, data, n_bytes * 8, ws.cdf, K, lm->spec.card, 24,
-                                       reinterpret_cast<long long*>(codes), n_steps, t);
-    ECB_LAUNCHED();
+  const char* genv = getenv("ECB_LM_GRAPH");   // diagnostic: 0 = launch every step's kernels from the host
+  const bool use_graph = (genv ? atoi(genv) != 0 : true) && n_steps >= 8;
+  if (!use_graph) {
+    for (long long t = 0; t < n_steps; ++t) {
+      if (lm_trunk(*lm, tk, 1, K, t, nullptr, 1, cache, capacity, ws, s)) return 1;
+      if (lm_heads(*lm, tk, 1, K, t, nullptr, 1, ws, nullptr, ws.cdf, nullptr, s)) return 1;
+      if (launch_ac_pull(ws.dec, data, n_bytes, ws.cdf, K, lm->spec.card, 24, lcodes, n_steps, t, nullptr, s)) return 1;
+    }
+  } else {
+    // the step's launches (39 for 5 layers) as one CUDA graph: every kernel reads the step index from ws.step, the pull kernel advances it
+    StepGraph& sg = g_step_graphs[lm];
+    const StepGraphKey key{data, codes, cache, workspace, n_bytes, K, n_steps, capacity};
+    if (!sg.exec || !(sg.key == key)) {
+      if (sg.exec) {
+        cudaGraphExecDestroy(sg.exec);
+        sg.exec = nullptr;
+      }
+      if (!g_lm_capture_stream) ECB_CUDA(cudaStreamCreateWithFlags(&g_lm_capture_stream, cudaStreamNonBlocking));
+      ECB_CUDA(cudaStreamBeginCapture(g_lm_capture_stream, cudaStreamCaptureModeRelaxed));
+      int rc = lm_trunk(*lm, tk, 1, K, 0, ws.step, 1, cache, capacity, ws, g_lm_capture_stream);
+      if (!rc) rc = lm_heads(*lm, tk, 1, K, 0, ws.step, 1, ws, nullptr, ws.cdf, nullptr, g_lm_capture_stream);
+      if (!rc) rc = launch_ac_pull(ws.dec, data, n_bytes, ws.cdf, K, lm->spec.card, 24, lcodes, n_steps, 0, ws.step, g_lm_capture_stream);
+      cudaGraph_t graph = nullptr;
+      const cudaError_t ce = cudaStreamEndCapture(g_lm_capture_stream, &graph);
+      if (rc) {
+        if (graph) cudaGraphDestroy(graph);
+        return 1;
+      }
+      ECB_CUDA(ce);
+      const cudaError_t ie = cudaGraphInstantiate(&sg.exec, graph, 0);
+      cudaGraphDestroy(graph);
+      ECB_CUDA(ie);
+      sg.key = key;
+    }
+    for (long long t = 0; t < n_steps; ++t) {
+      ECB_CUDA(cudaGraphLaunch(sg.exec, s));
+      g_launches.fetch_add(1 + 7 * lm->spec.n_layers + 3, std::memory_order_relaxed);
+    }
   }
   lm_ac_result_kernel<<<1, 32, 0, s>>>(ws.dec, reinterpret_cast<long long*>(result));
+  ECB_LAUNCHED();
+  return 0;
+}
+
+/* ArithmeticDecoder.pull on the DEVICE alone -- the warp-parallel decoder of the loop above against given cdfs: symbol i is
+ * decoded against cdfs[i * card .. (i + 1) * card) (DEVICE int32). symbols: DEVICE int64 [n]; result: DEVICE int64 [8]
+ * (result[0] = status as in ecb_lm_decode_frame, result[1] = bytes consumed; the rest is scratch). */
+int ecb_ac_decode_device(const uint8_t* data, int64_t n_bytes, const int32_t* cdfs, int64_t n, int32_t card,
+                         int32_t total_range_bits, int64_t* symbols, int64_t* result, void* stream) {
+  ECB_REQUIRE(data && cdfs && symbols && result && n >= 1 && card >= 1, "ac_decode_device: bad arguments");
+  ECB_REQUIRE(total_range_bits >= 8 && total_range_bits <= 30, "ac_decode_device: total_range_bits %d", total_range_bits);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  ac::Decoder* st = reinterpret_cast<ac::Decoder*>(result + 2);
+  static_assert(sizeof(ac::Decoder) <= 6 * sizeof(int64_t), "decoder state must fit result[2..8)");
+  lm_ac_init_kernel<<<1, 32, 0, s>>>(st, 0, nullptr);
+  ECB_LAUNCHED();
+  if (launch_ac_pull(st, data, n_bytes, cdfs, n, card, total_range_bits, reinterpret_cast<long long*>(symbols), 1, 0, nullptr, s))
+    return 1;
+  lm_ac_result_kernel<<<1, 32, 0, s>>>(st, reinterpret_cast<long long*>(result));
   ECB_LAUNCHED();
   return 0;
 }

@@ -56,6 +56,23 @@ def ac_decode(data: bytes, cdfs: np.ndarray, total_range_bits: int = TOTAL_RANGE
     return syms.astype(np.int64), int(used.value)
 
 
+def ac_decode_device(data: torch.Tensor, cdfs: torch.Tensor, total_range_bits: int = TOTAL_RANGE_BITS):
+    """The device decoder of ``LMModel.decode_frame`` alone: uint8 stream + int32 ``cdfs [n, card]`` (CUDA) ->
+    ``(symbols [n] int64, bytes consumed)``."""
+    nat.require_cuda(data, "data", torch.uint8)
+    nat.require_cuda(cdfs, "cdfs", torch.int32)
+    c = cdfs.contiguous()
+    syms = torch.zeros(c.shape[0], dtype=torch.int64, device=c.device)
+    result = torch.zeros(8, dtype=torch.int64, device=c.device)
+    with torch.cuda.device(c.device):
+        nat.check(nat.lib.ecb_ac_decode_device(nat.ptr(data), data.numel(), nat.ptr(c), c.shape[0], c.shape[1], total_range_bits,
+                                               nat.ptr(syms), nat.ptr(result), nat.stream_ptr(c.device)))
+    status, used = (int(v) for v in result[:2].cpu().tolist())
+    if status != 0:
+        raise (EOFError if status == 1 else RuntimeError)(_AC_ERRORS.get(status, f"arithmetic decoder status {status}"))
+    return syms, used
+
+
 def quantized_cdf(pdf: torch.Tensor, total_range_bits: int = TOTAL_RANGE_BITS) -> torch.Tensor:
     """build_stable_quantized_cdf(pdf, total_range_bits, check=False) (ac.py:18-53) for every row of a CUDA float32
     ``pdf [..., card]`` -> int32 cdf of the same shape, bit-exact with the reference's CPU float32 arithmetic."""

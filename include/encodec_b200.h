@@ -238,6 +238,11 @@ int ecb_lm_forward(ecb_lm* lm, const int64_t* tokens, int64_t item_stride, int64
 int ecb_lm_decode_frame(ecb_lm* lm, const uint8_t* data, int64_t n_bytes, int64_t first_byte, int64_t n_codebooks,
                         int64_t n_steps, int64_t* codes, float* cache, int64_t capacity, int64_t* result, void* workspace,
                         size_t workspace_bytes, void* stream);
+/* ArithmeticDecoder.pull on the DEVICE alone -- the warp-parallel decoder of ecb_lm_decode_frame's loop against given cdfs:
+ * symbol i is decoded against cdfs[i * card .. (i + 1) * card) (DEVICE int32). symbols: DEVICE int64 [n]; result: DEVICE
+ * int64 [8] (result[0] = status as above, result[1] = bytes consumed, the rest is scratch). Bit-exact with the reference. */
+int ecb_ac_decode_device(const uint8_t* data, int64_t n_bytes, const int32_t* cdfs, int64_t n, int32_t card,
+                         int32_t total_range_bits, int64_t* symbols, int64_t* result, void* stream);
 /* build_stable_quantized_cdf (ac.py:18-53, check=False) alone, in the float32 arithmetic of the reference's CPU tensors:
  * pdf DEVICE float32 [n_rows][card] -> cdf DEVICE int32 [n_rows][card]. Bit-exact. */
 int ecb_quantized_cdf(const float* pdf, int64_t n_rows, int32_t card, int32_t total_range_bits, int32_t* cdf, void* stream);
