@@ -133,3 +133,56 @@ def rvq_encode(frames: np.ndarray, codebooks: np.ndarray, chunk: int = 65536, th
             xx = torch.from_numpy(np.ascontiguousarray(frames[s:s + chunk].T))[None]
             out.append(rvq.encode(xx, n_q)[:, 0].numpy())
     return np.concatenate(out, axis=1)
+
+
+def lm_entropy_round_trip(lm_spec, sd, codes: np.ndarray, threads: int | None = None):
+    """The entropy-coded frame loop of the reference (compress.py:66-87 and :125-152) on `codes [K, T]`: its own LMModel one
+    step at a time, build_stable_quantized_cdf per codebook, ArithmeticCoder.push / ArithmeticDecoder.pull.
+    Returns (seconds to code the frame, seconds to decode it, bytes, decoded codes)."""
+    import io
+    import torch
+    torch.set_num_threads(threads or os.cpu_count() or 1)
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    sys.dont_write_bytecode = True
+    warnings.filterwarnings("ignore")
+    from encodec.model import LMModel
+    from encodec.quantization.ac import ArithmeticCoder, ArithmeticDecoder, build_stable_quantized_cdf
+    lm = LMModel(lm_spec.n_q, lm_spec.card, dim=lm_spec.dim, num_layers=lm_spec.num_layers, num_heads=lm_spec.num_heads,
+                 hidden_scale=lm_spec.hidden_scale, past_context=lm_spec.past_context, max_period=lm_spec.max_period).eval()
+    lm.load_state_dict({k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in sd.items()}, strict=True)
+    frame = torch.from_numpy(np.ascontiguousarray(codes))[None]
+    _, K, T = frame.shape
+    t0 = time.perf_counter()
+    fo = io.BytesIO()
+    coder = ArithmeticCoder(fo)
+    states, offset = None, 0
+    input_ = torch.zeros(1, K, 1, dtype=torch.long)
+    for t in range(T):
+        with torch.no_grad():
+            probas, states, offset = lm(input_, states, offset)
+        input_ = 1 + frame[:, :, t: t + 1]
+        for k, value in enumerate(frame[0, :, t].tolist()):
+            q_cdf = build_stable_quantized_cdf(probas[0, :, k, 0], coder.total_range_bits, check=False)
+            coder.push(value, q_cdf)
+    coder.flush()
+    t1 = time.perf_counter()
+    fo.seek(0)
+    decoder = ArithmeticDecoder(fo)
+    states, offset = None, 0
+    input_ = torch.zeros(1, K, 1, dtype=torch.long)
+    out = torch.zeros(1, K, T, dtype=torch.long)
+    for t in range(T):
+        with torch.no_grad():
+            probas, states, offset = lm(input_, states, offset)
+        code_list = []
+        for k in range(K):
+            q_cdf = build_stable_quantized_cdf(probas[0, :, k, 0], decoder.total_range_bits, check=False)
+            code = decoder.pull(q_cdf)
+            if code is None:
+                raise EOFError("The stream ended sooner than expected.")
+            code_list.append(code)
+        out[0, :, t] = torch.tensor(code_list, dtype=torch.long)
+        input_ = 1 + out[:, :, t: t + 1]
+    t2 = time.perf_counter()
+    return t1 - t0, t2 - t1, len(fo.getvalue()), out[0].numpy()

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Headline benchmark: audio-seconds encoded+decoded per wall-second (EncodecModel.forward).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg1|cfg3|cfg4|cfg5|fork10hz]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg1|cfg3|cfg4|cfg5|fork10hz|ecdc_lm]
 
 N > 1 is launched by torchrun (one rank per GPU); clips are sharded across ranks with no data-path collective, and the
 only exchange is an NCCL gather of codes and audio to rank 0 (north_star), inside the timed region, issued on a side
@@ -57,8 +57,14 @@ WORKLOADS = {
     "fork10hz": dict(model="fork10hz", bandwidth=0.08, batch=32, seconds=14400.0, scaling="weak",
                      desc="the fork's 10 Hz model (layer_norm, ratios 6,5,5,2,1, dimension 256, 1024-wide LSTM), 0.08 kbps (n_q=8), "
                           "batch 32 x 144000 samples (4 h each)"),
+    # the entropy-coded body of a .ecdc stream (LM + arithmetic coder), codes -> bytes -> codes
+    "ecdc_lm": dict(model="lm", n_q=32, frames=750, cpu_frames=300, scaling="weak",
+                    desc="entropy-coded .ecdc body of one 10 s clip of the 24 kHz model at 24 kbps per GPU: LMModel (5 layers, dim 200, "
+                         "past_context 262) + arithmetic coder over 32 codebooks x 750 latent frames, codes -> bytes -> codes, "
+                         "random-init LM weights"),
 }
 METRIC = "audio-sec/sec encode+decode"
+LM_METRIC = "latent frames/sec entropy-coded and decoded (LM + arithmetic coder, n_q=32)"
 
 
 def make_spec(kind):
@@ -80,6 +86,10 @@ def config_of(name, wl, world):
     if wl["model"] == "rvq":
         return {"workload": wl["desc"], "frames_per_gpu": wl["frames"], "n_q": wl["n_q"], "parallelism": f"dp{world} (frames sharded)",
                 "reference_sample": "65536 frames x 32 layers per step on the CPU arm"}
+    if wl["model"] == "lm":
+        return {"workload": wl["desc"], "name": name, "frames_per_gpu": wl["frames"], "n_q": wl["n_q"],
+                "parallelism": f"dp{world} (one independent stream per GPU, no collective)",
+                "reference_sample": f"a frame of {wl['cpu_frames']} latent frames x {wl['n_q']} codebooks per step on the CPU arm"}
     clips, seconds = cpu_sample(wl)
     total = wl.get("total_clips")
     return {"workload": wl["desc"], "name": name,
@@ -213,13 +223,60 @@ def cpu_rvq_throughput(frames, cbs):
     return frames.shape[0] / dt, dt, kind, codes
 
 
+def lm_codes(wl, n_frames, seed):
+    from encodec_b200 import synth
+    u = synth.hash_uniform(seed, "ecdc-lm-codes", wl["n_q"] * n_frames).reshape(wl["n_q"], n_frames)
+    return np.minimum((u ** 2 * 1024).astype(np.int64), 1023)     # skewed symbols
+
+
+def cpu_lm_throughput(wl, n_frames):
+    """(frames/s, seconds, kind, how): the reference's LM + arithmetic coder loops (compress.py:66-87,125-152) on one frame."""
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import reference_arm as ra
+    from encodec_b200 import synth
+    spec = synth.LMSpec(n_q=wl["n_q"], card=1024, past_context=262)
+    sd = _LM_SD.setdefault("sd", synth.make_lm_state_dict(spec, 3))
+    codes = lm_codes(wl, n_frames, 5)
+    cores = os.cpu_count() or 1
+    if ra.available() or ra.install():
+        tc, td, nbytes, out = ra.lm_entropy_round_trip(spec, sd, codes)
+        assert np.array_equal(out, codes)
+        return n_frames / (tc + td), tc + td, "reference", (f"the unmodified reference from baseline/_ref: LMModel step by step, "
+                                                            f"build_stable_quantized_cdf, ArithmeticCoder.push / ArithmeticDecoder.pull, "
+                                                            f"{cores} threads; coding {tc:.2f} s + decoding {td:.2f} s")
+    from oracle import lm_oracle as lo
+    t0 = time.perf_counter()
+    p = lo.lm_probas(sd, codes, num_layers=spec.num_layers, num_heads=spec.num_heads, past_context=spec.past_context, dtype=np.float32)
+    cdfs = lo.build_stable_quantized_cdf(p)
+    data = lo.encode_frame(codes, cdfs)
+    dec = lo.ArithmeticDecoder(data)
+    for t in range(n_frames):
+        for k in range(wl["n_q"]):
+            assert dec.pull(cdfs[t, k]) == codes[k, t]
+    dt = time.perf_counter() - t0
+    return n_frames / dt, dt, "port", "oracle/lm_oracle.py (baseline/_ref is missing)"
+
+
+_LM_SD = {}
+
+
 def run_reference_arm(args, name, wl, rank, world):
     """`--impl reference`: the reference's own CPU implementation of the path on this box's host cores (rank 0 only)."""
     if rank != 0:
         return
     from encodec_b200 import synth
     cores = os.cpu_count() or 1
-    if wl["model"] == "rvq":
+    if wl["model"] == "lm":
+        for _ in range(max(min(args.warmup, 1), 0)):
+            cpu_lm_throughput(wl, 2)
+        spent = 0.0
+        for _ in range(args.steps):
+            _, sec, kind, how = cpu_lm_throughput(wl, wl["cpu_frames"])
+            spent += sec                    # the coding + decoding loops only (model construction is outside, as in our arm)
+        dt = spent / args.steps
+        value, unit, metric = wl["cpu_frames"] / dt, "frames/s", LM_METRIC
+        sample = f"a frame of {wl['cpu_frames']} latent frames x {wl['n_q']} codebooks per step"
+    elif wl["model"] == "rvq":
         frames = synth.hash_normal(4, "cfg4-frames", (65536, wl["dim"]))
         cbs = synth.hash_normal(4, "cfg4-codebooks", (wl["n_q"], wl["bins"], wl["dim"]))
         for _ in range(max(args.warmup, 0)):
@@ -617,6 +674,84 @@ def run_cfg4(wl, dev, rank, world, steps, warmup, check):
     return res
 
 
+def run_ecdc_lm(wl, dev, rank, world, steps, warmup, cpu_leg):
+    """codes [32, 750] -> entropy-coded bytes (batched LM pass + host coder) -> codes (device decoding loop).
+    A step is the round trip of one frame; `value` with the codes resident on the device, `e2e` from / to pinned host memory."""
+    import torch
+    from encodec_b200 import _native as nat, synth
+    from encodec_b200.lm import LMModel
+    K, T = wl["n_q"], wl["frames"]
+    spec = synth.LMSpec(n_q=K, card=1024, past_context=262)
+    lm = LMModel(spec.n_q, spec.card, dim=spec.dim, num_layers=spec.num_layers, num_heads=spec.num_heads,
+                 past_context=spec.past_context)
+    lm.load_state_dict({k: torch.from_numpy(v) for k, v in _LM_SD.setdefault("sd", synth.make_lm_state_dict(spec, 3)).items()})
+    lm = lm.to(dev).eval()
+    host = [torch.from_numpy(lm_codes(wl, T, 10 + 3 * rank + i)).pin_memory() for i in range(3)]
+    resident = [h.to(dev) for h in host]
+    tm = Timer(dev, world)
+    detail = {}
+
+    def round_trip(codes_dev):
+        t0 = time.perf_counter()
+        data = lm.encode_frames(codes_dev[None])[0]
+        t1 = time.perf_counter()
+        buf = torch.frombuffer(bytearray(data), dtype=torch.uint8).to(dev)
+        got, end = lm.decode_frame(buf, 0, K, T)
+        t2 = time.perf_counter()
+        assert end == len(data)
+        return got, len(data), t1 - t0, t2 - t1
+
+    for i in range(max(warmup, 3)):
+        round_trip(resident[i % 3])
+    launches0 = nat.launch_count()
+    tm.start()
+    tc = td = 0.0
+    for i in range(steps):
+        got, nbytes, a, b = round_trip(resident[i % 3])
+        tc, td = tc + a, td + b
+    ms = tm.stop()
+    launches = nat.launch_count() - launches0
+    assert torch.equal(got, resident[(steps - 1) % 3]), "entropy-coded round trip changed the codes"
+    tm.start()
+    for i in range(steps):
+        got, nbytes, _, _ = round_trip(host[i % 3].to(dev, non_blocking=True))
+        back = got.cpu()
+    ms_e2e = tm.stop()
+    assert torch.equal(back, host[(steps - 1) % 3])
+    # per-kernel-class device time of one decoding loop (launched from the host while profiling) and one batched pass
+    nat.profile_begin()
+    lm.coder_ranges(resident[0][None])
+    torch.cuda.synchronize(dev)
+    prof_c = nat.profile_end()
+    data = lm.encode_frames(resident[0][None])[0]
+    buf = torch.frombuffer(bytearray(data), dtype=torch.uint8).to(dev)
+    nat.profile_begin()
+    lm.decode_frame(buf, 0, K, T)
+    torch.cuda.synchronize(dev)
+    prof_d = nat.profile_end()
+    detail = {"compress_ms": 1e3 * tc / steps, "decompress_ms": 1e3 * td / steps, "decode_us_per_latent_frame": 1e6 * td / steps / T,
+              "bytes_per_frame": nbytes, "bits_per_symbol": 8.0 * nbytes / (K * T),
+              "batched_pass_kernels": {k: {"ms": v["ms"], "launches": v["launches"]} for k, v in prof_c.items()},
+              "decoding_loop_kernels_eager": {k: {"us_per_latent_frame": 1e3 * v["ms"] / T, "launches_per_latent_frame": v["launches"] / T}
+                                              for k, v in prof_d.items()},
+              "note": "the decoding loop replays ONE captured step (29 launches) per latent frame; the per-class times above are "
+                      "from a host-launched loop with CUDA events around every launch (event overhead included)"}
+    # the chain is latency-bound: the dominant class by time is lm_linear (21 launches per latent frame); its algorithmic
+    # bytes per latent frame are the weights read once (the activations of one row are negligible)
+    w_bytes = 4.0 * (spec.num_layers * (4 * spec.dim * spec.dim + 2 * spec.dim * spec.hidden) + K * spec.card * spec.dim)
+    lin_us = detail["decoding_loop_kernels_eager"].get("lm_linear", {}).get("us_per_latent_frame")
+    res = {"value": world * T / (ms / steps / 1e3), "ms_per_step": ms / steps, "gpu_launches": launches,
+           "e2e": {"value": world * T / (ms_e2e / steps / 1e3), "unit": "frames/s", "ms_per_step": ms_e2e / steps,
+                   "h2d_bytes_per_step": K * T * 8 + nbytes, "d2h_bytes_per_step": K * T * 8 + K * T * 8},
+           "detail": detail, "weights_bytes_per_latent_frame": w_bytes, "lm_linear_us_per_latent_frame": lin_us}
+    if cpu_leg and rank == 0:
+        cpu_lm_throughput(wl, 2)
+        v, spent, kind, how = cpu_lm_throughput(wl, wl["cpu_frames"])
+        res["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": os.cpu_count() or 1, "kind": kind,
+                               "sample": f"a frame of {wl['cpu_frames']} latent frames x {K} codebooks, {spent:.1f} s of CPU work", "how": how}
+    return res
+
+
 _REAL_STDOUT = None
 
 
@@ -699,6 +834,21 @@ def main():
                                                 "3xTF32 split operands"},
                     "cpu_baseline": res.get("cpu_baseline"), "parity_sample": res.get("parity_sample"), "kernels": res["kernels"],
                     "e2e": None}
+    elif name == "ecdc_lm":
+        res = run_ecdc_lm(wl, dev, rank, world, args.steps, args.warmup, cpu_leg=not args.no_cpu_baseline)
+        if rank == 0:
+            lin_us = res["lm_linear_us_per_latent_frame"]
+            gbs = res["weights_bytes_per_latent_frame"] / (lin_us * 1e-6) / 1e9 if lin_us else None
+            line = {"metric": LM_METRIC, "value": res["value"], "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+                    "warmup": max(args.warmup, 3), "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                    "vs_baseline": None, "dtype": "f32 (LM), u64 / f64 (coder)", "data": "synthetic", "config": config_of(name, wl, world),
+                    "gpu_launches": res["gpu_launches"], "e2e": res["e2e"], "detail": res["detail"],
+                    "roofline": {"kernel": "lm_linear_kernel", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                 "frac": gbs / peaks["hbm_gbs"] if gbs else None, "traffic": None, "peak_source": peaks["source"],
+                                 "note": "decoding loop, per latent frame: the 21 lm_linear launches read every weight once (35.8 MB, "
+                                         "L2-resident) in the measured time; the step is a chain of 29 dependent launches on one row, "
+                                         "bound by launch + memory latency, not by bandwidth or the tensor pipe"},
+                    "cpu_baseline": res.get("cpu_baseline")}
     elif name == "cfg5":
         res = run_cfg5(name, wl, dev, rank, world, max(1, min(args.steps, 2)), args.warmup, wl["total_clips"])
         if rank == 0:

@@ -66,28 +66,74 @@ ECB_AC_HD void decoder_init(Decoder& d, int64_t first_bit) {
   d.status = AC_OK;
 }
 
+// The two bit loops of the reference in closed form (same result, O(1) per symbol):
+//  * refill (ac.py:224-231): `while delta < 2^bits: low *= 2; high = high * 2 + 1; current = current * 2 + bit; max_bit += 1`
+//    runs n = max(0, bits + 1 - bit_length(delta)) times; the n stream bits enter `current` first-read = most significant;
+//  * flush (ac.py:195-212): strips the c leading bits (of the max_bit + 1 wide representation) that low and high share --
+//    current lies between them, so it shares them too.
+ECB_AC_HD int clz64(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+  return __clzll((long long)x);
+#else
+  return x ? __builtin_clzll(x) : 64;
+#endif
+}
+ECB_AC_HD uint64_t brev64(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+  return __brevll(x);
+#else
+  x = ((x >> 1) & 0x5555555555555555ull) | ((x & 0x5555555555555555ull) << 1);
+  x = ((x >> 2) & 0x3333333333333333ull) | ((x & 0x3333333333333333ull) << 2);
+  x = ((x >> 4) & 0x0f0f0f0f0f0f0f0full) | ((x & 0x0f0f0f0f0f0f0f0full) << 4);
+  return __builtin_bswap64(x);
+#endif
+}
+// returns false with d.status set when the stream ends first (the reference returns None: "ended sooner than expected")
+ECB_AC_HD bool refill(Decoder& d, const uint8_t* data, int64_t n_bits, int bits) {
+  const uint64_t delta = d.high - d.low + 1;
+  const int len = 64 - clz64(delta);
+  const int n = bits + 1 - len;
+  if (n <= 0) return true;
+  if (d.bit_pos + n > n_bits) {
+    d.status = AC_EOF;
+    return false;
+  }
+  if (d.max_bit + n > 61) {
+    d.status = AC_RANGE_OVERFLOW;
+    return false;
+  }
+  const int64_t byte0 = d.bit_pos >> 3, n_bytes = (n_bits + 7) >> 3;
+  uint64_t w = 0;
+#pragma unroll
+  for (int i = 0; i < 5; ++i)   // n <= 31 bits + 7 bits of offset
+    if (byte0 + i < n_bytes) w |= (uint64_t)data[byte0 + i] << (8 * i);
+  const uint64_t chunk = (w >> (d.bit_pos & 7)) & ((1ull << n) - 1ull);   // stream order: first bit = least significant
+  d.bit_pos += n;
+  d.low <<= n;
+  d.high = ((d.high + 1) << n) - 1;
+  d.current = (d.current << n) | (brev64(chunk) >> (64 - n));
+  d.max_bit += n;
+  return true;
+}
+ECB_AC_HD void flush_prefix(Decoder& d) {
+  if (d.max_bit < 0) return;
+  const uint64_t x = d.low ^ d.high;
+  const int width = d.max_bit + 1;
+  const int c = x ? clz64(x) - (64 - width) : width;   // common leading bits of the width-bit representations
+  if (c <= 0) return;
+  const uint64_t mask = (width - c) >= 64 ? ~0ull : ((1ull << (width - c)) - 1ull);
+  d.low &= mask;
+  d.high &= mask;
+  d.current &= mask;
+  d.max_bit -= c;
+}
+
 // ArithmeticDecoder.pull (ac.py:214-260). cdf: int32 [card], the quantised cdf of this symbol (cdf[i] = upper bound,
 // exclusive, of symbol i's range). Returns the symbol, or -1 with d.status set (AC_EOF: "the stream ended sooner than
 // expected", compress.py:143-144).
 ECB_AC_HD int pull(Decoder& d, const uint8_t* data, int64_t n_bits, const int32_t* cdf, int card, int bits) {
   if (d.status != AC_OK) return -1;
-  const uint64_t full = 1ull << bits;
-  while (d.high - d.low + 1 < full) {                                    // ac.py:224-231
-    if (d.bit_pos >= n_bits) {
-      d.status = AC_EOF;
-      return -1;
-    }
-    if (d.max_bit >= 61) {
-      d.status = AC_RANGE_OVERFLOW;
-      return -1;
-    }
-    const uint64_t bit = (data[d.bit_pos >> 3] >> (d.bit_pos & 7)) & 1u;
-    ++d.bit_pos;
-    d.low *= 2;
-    d.high = d.high * 2 + 1;
-    d.current = d.current * 2 + bit;
-    ++d.max_bit;
-  }
+  if (!refill(d, data, n_bits, bits)) return -1;                          // ac.py:224-231
   const double ratio = scaled_delta(d.high - d.low + 1, bits);
   int lo_idx = 0, hi_idx = card - 1, mid = 0;
   uint64_t low = 0, high = 0;
@@ -114,15 +160,7 @@ ECB_AC_HD int pull(Decoder& d, const uint8_t* data, int64_t n_bits, const int32_
   }
   d.low = low;
   d.high = high;
-  while (d.max_bit >= 0) {                                               // _flush_common_prefix, ac.py:195-212
-    const uint64_t b1 = d.low >> d.max_bit;
-    const uint64_t b2 = d.high >> d.max_bit;
-    if (b1 != b2) break;
-    d.low -= b1 << d.max_bit;
-    d.high -= b1 << d.max_bit;
-    d.current -= b1 << d.max_bit;
-    --d.max_bit;
-  }
+  flush_prefix(d);                                                       // _flush_common_prefix, ac.py:195-212
   return mid;
 }
 

@@ -36,7 +36,8 @@ struct ProfRec {
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;
 static const char* kProfNames[PROF_NCAT] = {"conv_gemm", "conv_in", "conv_out", "lstm_recurrent", "rvq_encode",
-                                            "gn_apply", "misc", "tc_conv_narrow", "tc_conv_wide", "tc_res"};
+                                            "gn_apply", "misc", "tc_conv_narrow", "tc_conv_wide", "tc_res",
+                                            "lm_linear", "lm_attn", "lm_misc", "ac_pull"};
 bool prof_enabled() { return g_prof_on; }
 void prof_begin(int cat, cudaStream_t st, double flops, double bytes) {
   ProfRec r;

@@ -23,7 +23,7 @@ extern std::atomic<long long> g_launches;
 
 // Optional per-kernel-class timing (bench.py's roofline leg): CUDA events recorded on the launching stream
 // around every launch while enabled; off by default (no events, no overhead).
-enum ProfCat { PROF_CONV_GEMM = 0, PROF_CONV_IN, PROF_CONV_OUT, PROF_LSTM_REC, PROF_RVQ, PROF_GN_APPLY, PROF_MISC, PROF_TC_CONV_NARROW, PROF_TC_CONV_WIDE, PROF_TC_RES, PROF_NCAT };
+enum ProfCat { PROF_CONV_GEMM = 0, PROF_CONV_IN, PROF_CONV_OUT, PROF_LSTM_REC, PROF_RVQ, PROF_GN_APPLY, PROF_MISC, PROF_TC_CONV_NARROW, PROF_TC_CONV_WIDE, PROF_TC_RES, PROF_LM_LINEAR, PROF_LM_ATTN, PROF_LM_MISC, PROF_AC_PULL, PROF_NCAT };
 bool prof_enabled();
 void prof_begin(int cat, cudaStream_t st, double flops, double bytes);
 void prof_end(cudaStream_t st);

@@ -7,7 +7,7 @@
 //   build_stable_quantized_cdf (quantization/ac.py:18-53) and ArithmeticCoder / ArithmeticDecoder (ac.py:56-260).
 //
 // Design. The reference evaluates the LM one time step at a time in both directions. Here
-//   * COMPRESSION knows every code, so all steps of all frames are rows of ONE batched pass (38 launches per call whatever
+//   * COMPRESSION knows every code, so all steps of all frames are rows of ONE batched pass (28 launches per call whatever
 //     the length); the logits kernel forms softmax -> quantised cdf on chip and emits only the two cdf values the coder
 //     needs per symbol (8 bytes instead of a 4 KB distribution); the coder itself is the sequential integer recurrence of
 //     ac_core.h on the host.
@@ -115,14 +115,24 @@ __global__ void lm_embed_kernel(Tokens tk, const float* __restrict__ emb, const 
   for (int k0 = 0; k0 < K; k0 += 32) {   // the indices first (one lane per codebook), so that the row loads do not wait on them
     const long long mine = (k0 + lane < K) ? token_index(tk, item, k0 + lane, t, t0, card) : 0;
     const int g = (K - k0) < 32 ? (K - k0) : 32;
-#pragma unroll 4
-    for (int kk = 0; kk < g; ++kk) {       // summed in codebook order, as the reference's sum([...]) (model.py:79)
-      const long long idx = __shfl_sync(0xffffffffu, mine, kk);
-      const float* e = emb + ((size_t)(k0 + kk) * (card + 1) + (size_t)idx) * dim;
+    for (int k1 = 0; k1 < g; k1 += 8) {    // eight embedding rows in flight, then added in codebook order (model.py:79)
+      float e[8][kMaxDimPerLane];
 #pragma unroll
-      for (int i = 0; i < kMaxDimPerLane; ++i) {
-        const int d = lane + 32 * i;
-        if (d < dim) v[i] += e[d];
+      for (int u = 0; u < 8; ++u) {
+        const long long idx = __shfl_sync(0xffffffffu, mine, (k1 + u) & 31);
+        const float* row_e = emb + ((size_t)(k0 + k1 + u) * (card + 1) + (size_t)idx) * dim;
+#pragma unroll
+        for (int i = 0; i < kMaxDimPerLane; ++i) {
+          const int d = lane + 32 * i;
+          e[u][i] = (k1 + u < g && d < dim) ? row_e[d] : 0.f;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (k1 + u < g) {
+#pragma unroll
+          for (int i = 0; i < kMaxDimPerLane; ++i) v[i] += e[u][i];
+        }
       }
     }
   }
@@ -136,26 +146,6 @@ __global__ void lm_embed_kernel(Tokens tk, const float* __restrict__ emb, const 
       const float phase = __fdiv_rn((float)t, pos_div[d < half ? d : d - half]);
       x[row * dim + d] = v[i] + (d < half ? cosf(phase) : sinf(phase));
     }
-  }
-}
-
-// In-place-capable LayerNorm of rows (norm1 / norm2 of the post-norm layer, transformer.py:38-39). One warp per row.
-__global__ void lm_ln_kernel(const float* __restrict__ in, float* __restrict__ out, const float* __restrict__ w,
-                             const float* __restrict__ b, long long n_rows, int dim, float eps) {
-  const int lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5);
-  if (row >= n_rows) return;
-  float v[kMaxDimPerLane];
-#pragma unroll
-  for (int i = 0; i < kMaxDimPerLane; ++i) {
-    const int d = lane + 32 * i;
-    v[i] = d < dim ? in[row * dim + d] : 0.f;
-  }
-  warp_layer_norm(v, dim, lane, w, b, eps);
-#pragma unroll
-  for (int i = 0; i < kMaxDimPerLane; ++i) {
-    const int d = lane + 32 * i;
-    if (d < dim) out[row * dim + d] = v[i];
   }
 }
 
@@ -174,6 +164,10 @@ struct LinArgs {
   long long t0;
   const long long* t_ptr;
   int dim;
+  // LayerNorm applied on load (the post-norm layer's norm1 / norm2, transformer.py:38-39, never exist as a pass of their own):
+  const float *ln_w, *ln_b;     // non-null: x rows are LayerNorm(x) * ln_w + ln_b (needs K <= 256)
+  const float *rln_w, *rln_b;   // non-null (RESID): the residual rows likewise (needs N <= 256)
+  float eps;
 };
 
 // y[r][n] = epilogue(b[n] + sum_k W[n][k] x[r][k]). A warp owns kColsPerWarp output columns: their weight rows sit in
@@ -186,10 +180,9 @@ __global__ void __launch_bounds__(kWarps * 32) lm_linear_kernel(LinArgs a) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long r0 = (long long)blockIdx.y * kRowTile;
   const int nr = (int)((a.n_rows - r0) < kRowTile ? (a.n_rows - r0) : kRowTile);
-  for (int i = threadIdx.x; i < nr * a.K; i += blockDim.x) xs[i] = a.x[r0 * a.K + i];
-  __syncthreads();
+  float* rs = xs + kRowTile * a.K;   // [kRowTile][N], only with rln_w
+  // the warp's weight rows first: they do not depend on the activations, so their latency overlaps the tile load below
   const int n0 = (blockIdx.x * kWarps + warp) * kColsPerWarp;
-  if (n0 >= a.N) return;   // warp-uniform, no block-wide barrier below
   float w[kColsPerWarp][KPL], bias[kColsPerWarp];
 #pragma unroll
   for (int c = 0; c < kColsPerWarp; ++c) {
@@ -201,6 +194,43 @@ __global__ void __launch_bounds__(kWarps * 32) lm_linear_kernel(LinArgs a) {
     }
     bias[c] = n < a.N ? a.b[n] : 0.f;
   }
+  for (int i = threadIdx.x; i < nr * a.K; i += blockDim.x) xs[i] = a.x[r0 * a.K + i];
+  if (EPI == EPI_RESID && a.rln_w)
+    for (int i = threadIdx.x; i < nr * a.N; i += blockDim.x) rs[i] = a.resid[r0 * a.N + i];
+  __syncthreads();
+  if (a.ln_w || (EPI == EPI_RESID && a.rln_w)) {   // kRowTile == kWarps: warp r normalises row r, the same function for every launch shape
+    if (warp < nr) {
+      float v[kMaxDimPerLane];
+      if (a.ln_w) {
+#pragma unroll
+        for (int i = 0; i < kMaxDimPerLane; ++i) {
+          const int d = lane + 32 * i;
+          v[i] = d < a.K ? xs[warp * a.K + d] : 0.f;
+        }
+        warp_layer_norm(v, a.K, lane, a.ln_w, a.ln_b, a.eps);
+#pragma unroll
+        for (int i = 0; i < kMaxDimPerLane; ++i) {
+          const int d = lane + 32 * i;
+          if (d < a.K) xs[warp * a.K + d] = v[i];
+        }
+      }
+      if (EPI == EPI_RESID && a.rln_w) {
+#pragma unroll
+        for (int i = 0; i < kMaxDimPerLane; ++i) {
+          const int d = lane + 32 * i;
+          v[i] = d < a.N ? rs[warp * a.N + d] : 0.f;
+        }
+        warp_layer_norm(v, a.N, lane, a.rln_w, a.rln_b, a.eps);
+#pragma unroll
+        for (int i = 0; i < kMaxDimPerLane; ++i) {
+          const int d = lane + 32 * i;
+          if (d < a.N) rs[warp * a.N + d] = v[i];
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (n0 >= a.N) return;   // warp-uniform, no block-wide barrier below
   const long long t0 = (EPI == EPI_QKV && a.t_ptr) ? *a.t_ptr : a.t0;
   for (int r = 0; r < nr; ++r) {
     float acc[kColsPerWarp];
@@ -227,7 +257,7 @@ __global__ void __launch_bounds__(kWarps * 32) lm_linear_kernel(LinArgs a) {
       if (EPI == EPI_GELU) {
         a.out[row * a.N + n] = 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));   // F.gelu (exact, erf form)
       } else if (EPI == EPI_RESID) {
-        a.out[row * a.N + n] = a.resid[row * a.N + n] + v;
+        a.out[row * a.N + n] = (a.rln_w ? rs[r * a.N + n] : a.resid[row * a.N + n]) + v;
       } else if (EPI == EPI_PLAIN) {
         a.out[row * a.N + n] = v;
       } else {
@@ -245,19 +275,20 @@ __global__ void __launch_bounds__(kWarps * 32) lm_linear_kernel(LinArgs a) {
 }
 
 // _sa_block (transformer.py:42-59) for one (row, head) per block: keys / values = cache rows [lo, t + 1], lo = t + 1 - min(t + 1,
-// past_context) (the rows the streaming state still holds, transformer.py:116-117). Thread j owns keys j, j + 256, ...: its
-// scores stay in registers, max and sum are block reductions, the weighted values are per-thread partial sums per head
-// dimension reduced by the xor tree and then across the warps in warp order -- one partition for every launch shape, and
-// in the decoding loop (one row) a key costs one memory latency instead of a serial walk.
-constexpr int kAttnThreads = 256;
-constexpr int kAttnKeys = 6;   // keys per thread: past_context + 1 <= 6 * 256
+// past_context) (the rows the streaming state still holds, transformer.py:116-117). Warp w owns keys w, w + 32, ...; a key's
+// head slice (hd <= 32 contiguous floats) is read by the lanes of the warp (one coalesced request per key instead of one
+// cache line per lane), the score is the xor-tree sum of the lane products; max and sum are block reductions in warp
+// order; the weighted values are one accumulator per lane (= head dimension) and warp, summed across the warps in warp
+// order. One partition for every launch shape; in the decoding loop (one row) the keys of a head are spread over 32 warps.
+constexpr int kAttnThreads = 1024;   // 32 warps: at past_context = 262 a warp owns <= 9 keys, all of their loads in flight together
 __global__ void __launch_bounds__(kAttnThreads) lm_attn_kernel(const float* __restrict__ q, const float* __restrict__ cache,
                                                                 float* __restrict__ out, int n_t, long long t0_arg,
                                                                 const long long* __restrict__ t_ptr, long long capacity, int dim,
                                                                 int heads, int past_context) {
-  __shared__ float sq[32];
+  extern __shared__ float sc[];   // [past_context + 1] scores
   __shared__ float red[kAttnThreads / 32];
   __shared__ float part[kAttnThreads / 32][32];
+  constexpr int NW = kAttnThreads / 32;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const long long w = blockIdx.x;
   const long long t0 = t_ptr ? *t_ptr : t0_arg;
@@ -269,65 +300,37 @@ __global__ void __launch_bounds__(kAttnThreads) lm_attn_kernel(const float* __re
   const long long lo = t + 1 - n_past;
   const int nk = (int)n_past + 1;
   const float* kv = cache + ((size_t)item * (capacity + 1) + (size_t)lo) * 2 * dim + h * hd;
-  if (tid < hd) sq[tid] = q[row * dim + h * hd + tid];
-  __syncthreads();
+  const float qv = lane < hd ? q[row * dim + h * hd + lane] : 0.f;
   const float scale = 1.f / sqrtf((float)hd);
-  float sc[kAttnKeys];
   float m = -INFINITY;
-#pragma unroll
-  for (int u = 0; u < kAttnKeys; ++u) {
-    const int i = tid + kAttnThreads * u;
-    sc[u] = -INFINITY;
-    if (i < nk) {
-      const float* kr = kv + (size_t)i * 2 * dim;
-      float s = 0.f;
-#pragma unroll
-      for (int d = 0; d < 32; ++d)
-        if (d < hd) s = fmaf(sq[d], kr[d], s);
-      s *= scale;
-      sc[u] = s;
-      m = fmaxf(m, s);
-    }
+#pragma unroll 8
+  for (int i = warp; i < nk; i += NW) {
+    const float kval = lane < hd ? kv[(size_t)i * 2 * dim + lane] : 0.f;
+    const float s = warp_sum(qv * kval) * scale;
+    if (lane == 0) sc[i] = s;
+    m = fmaxf(m, s);
   }
-  m = warp_max(m);
   if (lane == 0) red[warp] = m;
   __syncthreads();
   m = red[0];
 #pragma unroll
-  for (int w2 = 1; w2 < kAttnThreads / 32; ++w2) m = fmaxf(m, red[w2]);
+  for (int w2 = 1; w2 < NW; ++w2) m = fmaxf(m, red[w2]);
   __syncthreads();
-  float l = 0.f;
-  float acc[32];
-#pragma unroll
-  for (int d = 0; d < 32; ++d) acc[d] = 0.f;
-#pragma unroll
-  for (int u = 0; u < kAttnKeys; ++u) {
-    const int i = tid + kAttnThreads * u;
-    if (i < nk) {
-      const float e = expf(sc[u] - m);
-      l += e;
-      const float* vr = kv + dim + (size_t)i * 2 * dim;
-#pragma unroll
-      for (int d = 0; d < 32; ++d)
-        if (d < hd) acc[d] = fmaf(e, vr[d], acc[d]);
-    }
-  }
-  l = warp_sum(l);
-  float o = 0.f;
-#pragma unroll
-  for (int d = 0; d < 32; ++d) {
-    if (d < hd) {   // block-uniform
-      const float r = warp_sum(acc[d]);
-      if (lane == d) o = r;
-    }
+  float l = 0.f, acc = 0.f;
+#pragma unroll 8
+  for (int i = warp; i < nk; i += NW) {
+    const float e = expf(sc[i] - m);
+    const float vval = lane < hd ? kv[(size_t)i * 2 * dim + dim + lane] : 0.f;
+    l += e;
+    acc = fmaf(e, vval, acc);
   }
   if (lane == 0) red[warp] = l;
-  if (lane < hd) part[warp][lane] = o;
+  part[warp][lane] = acc;
   __syncthreads();
   if (tid < hd) {
     float L = red[0], O = part[0][tid];
 #pragma unroll
-    for (int w2 = 1; w2 < kAttnThreads / 32; ++w2) {
+    for (int w2 = 1; w2 < NW; ++w2) {
       L += red[w2];
       O += part[w2][tid];
     }
@@ -447,23 +450,7 @@ __global__ void __launch_bounds__(kWarps * 32) lm_cdf_kernel(const float* __rest
 __device__ __forceinline__ int ac_pull_warp(ac::Decoder& d, const unsigned char* __restrict__ data, long long n_bits,
                                             const int* cdf, int card, int bits, int lane) {
   if (d.status != ac::AC_OK) return -1;
-  const uint64_t full = 1ull << bits;
-  while (d.high - d.low + 1 < full) {
-    if (d.bit_pos >= n_bits) {
-      d.status = ac::AC_EOF;
-      return -1;
-    }
-    if (d.max_bit >= 61) {
-      d.status = ac::AC_RANGE_OVERFLOW;
-      return -1;
-    }
-    const uint64_t bit = (data[d.bit_pos >> 3] >> (d.bit_pos & 7)) & 1u;
-    ++d.bit_pos;
-    d.low *= 2;
-    d.high = d.high * 2 + 1;
-    d.current = d.current * 2 + bit;
-    ++d.max_bit;
-  }
+  if (!ac::refill(d, data, n_bits, bits)) return -1;
   const double ratio = ac::scaled_delta(d.high - d.low + 1, bits);
   int base = 0, span = card;
   while (span > 1) {
@@ -498,15 +485,7 @@ __device__ __forceinline__ int ac_pull_warp(ac::Decoder& d, const unsigned char*
   }
   d.low = low;
   d.high = high;
-  while (d.max_bit >= 0) {
-    const uint64_t b1 = d.low >> d.max_bit;
-    const uint64_t b2 = d.high >> d.max_bit;
-    if (b1 != b2) break;
-    d.low -= b1 << d.max_bit;
-    d.high -= b1 << d.max_bit;
-    d.current -= b1 << d.max_bit;
-    --d.max_bit;
-  }
+  ac::flush_prefix(d);
   return base;
 }
 
@@ -595,8 +574,11 @@ template <int EPI>
 int launch_linear(const LinArgs& a, cudaStream_t s) {
   const int kpl = (a.K + 31) / 32;
   dim3 grid((unsigned)cdiv((long long)a.N, (long long)kWarps * kColsPerWarp), (unsigned)cdiv(a.n_rows, (long long)kRowTile));
-  const size_t smem = (size_t)kRowTile * a.K * sizeof(float);
+  static_assert(kRowTile == kWarps, "LayerNorm on load: one warp per row of the tile");
+  const size_t smem = (size_t)kRowTile * (a.K + (a.rln_w ? a.N : 0)) * sizeof(float);
   ECB_REQUIRE(kpl <= 32 && smem <= 48 * 1024, "lm: linear layer with K = %d is not supported (K <= 1024)", a.K);
+  ECB_REQUIRE((!a.ln_w || a.K <= 32 * kMaxDimPerLane) && (!a.rln_w || a.N <= 32 * kMaxDimPerLane), "lm: LayerNorm on load needs <= 256 channels");
+  ProfScope prof(PROF_LM_LINEAR, s, 2.0 * a.n_rows * a.N * a.K, 4.0 * ((double)a.N * a.K + (double)a.n_rows * (a.K + a.N)));
   if (kpl <= 2) lm_linear_kernel<2, EPI><<<grid, kWarps * 32, smem, s>>>(a);
   else if (kpl <= 4) lm_linear_kernel<4, EPI><<<grid, kWarps * 32, smem, s>>>(a);
   else if (kpl <= 7) lm_linear_kernel<7, EPI><<<grid, kWarps * 32, smem, s>>>(a);
@@ -658,37 +640,46 @@ int lm_trunk(const Lm& lm, const Tokens& tk, long long n_items, int K, long long
   const long long n_rows = n_items * n_t;
   const float eps = 1e-5f;
   const unsigned row_blocks = (unsigned)cdiv(n_rows, (long long)kWarps);
-  lm_embed_kernel<<<row_blocks, kWarps * 32, 0, s>>>(tk, lm.weights + lm.emb_off, lm.nin_w, lm.nin_b, lm.weights + lm.pos_off,
-                                                    ws.x, n_rows, (int)n_t, t0, t_ptr, K, sp.card, sp.dim, eps);
-  ECB_LAUNCHED();
+  {
+    ProfScope prof(PROF_LM_MISC, s, 0.0, 0.0);
+    lm_embed_kernel<<<row_blocks, kWarps * 32, 0, s>>>(tk, lm.weights + lm.emb_off, lm.nin_w, lm.nin_b, lm.weights + lm.pos_off,
+                                                      ws.x, n_rows, (int)n_t, t0, t_ptr, K, sp.card, sp.dim, eps);
+    ECB_LAUNCHED();
+  }
+  // Post-norm layer (transformer.py:34-40) with both LayerNorms applied by their readers (lm_linear's on-load form):
+  //   y  = x_in + out_proj(attn(x_in))          x_in = the embedding (layer 0) or LayerNorm2 of the previous layer's y2
+  //   y2 = LayerNorm1(y) + linear2(gelu(linear1(LayerNorm1(y))))
+  // ws.x holds x_in of layer 0, afterwards the raw y2 of the last finished layer; ws.y the raw y. The heads read
+  // LayerNorm2(y2) of the last layer the same way.
   const size_t layer_cache = (size_t)n_items * (capacity + 1) * 2 * sp.dim;
   for (int l = 0; l < sp.n_layers; ++l) {
     const Lm::LayerW& lw = lm.layers[l];
+    const float* pn_w = l ? lm.layers[l - 1].n2_w : nullptr;   // norm2 of the previous layer, pending on ws.x
+    const float* pn_b = l ? lm.layers[l - 1].n2_b : nullptr;
     float* lc = cache + (size_t)l * layer_cache;
     LinArgs a{};
-    a.x = ws.x; a.W = lw.in_w; a.b = lw.in_b;
+    a.x = ws.x; a.W = lw.in_w; a.b = lw.in_b; a.ln_w = pn_w; a.ln_b = pn_b; a.eps = eps;
     a.K = sp.dim; a.N = 3 * sp.dim; a.n_rows = n_rows; a.out = ws.q; a.cache = lc; a.capacity = capacity;
     a.n_t = (int)n_t; a.t0 = t0; a.t_ptr = t_ptr; a.dim = sp.dim;
     if (launch_linear<EPI_QKV>(a, s)) return 1;
-    lm_attn_kernel<<<(unsigned)(n_rows * sp.n_heads), kAttnThreads, 0, s>>>(ws.q, lc, ws.att, (int)n_t, t0, t_ptr, capacity, sp.dim,
-                                                                         sp.n_heads, sp.past_context);
-    ECB_LAUNCHED();
+    {
+      ProfScope prof_attn(PROF_LM_ATTN, s, 0.0, 0.0);
+      lm_attn_kernel<<<(unsigned)(n_rows * sp.n_heads), kAttnThreads, (size_t)(sp.past_context + 1) * sizeof(float), s>>>(
+          ws.q, lc, ws.att, (int)n_t, t0, t_ptr, capacity, sp.dim, sp.n_heads, sp.past_context);
+      ECB_LAUNCHED();
+    }
     LinArgs o{};
-    o.x = ws.att; o.W = lw.out_w; o.b = lw.out_b;
-    o.K = sp.dim; o.N = sp.dim; o.n_rows = n_rows; o.out = ws.y; o.resid = ws.x;
+    o.x = ws.att; o.W = lw.out_w; o.b = lw.out_b; o.eps = eps;
+    o.K = sp.dim; o.N = sp.dim; o.n_rows = n_rows; o.out = ws.y; o.resid = ws.x; o.rln_w = pn_w; o.rln_b = pn_b;
     if (launch_linear<EPI_RESID>(o, s)) return 1;
-    lm_ln_kernel<<<row_blocks, kWarps * 32, 0, s>>>(ws.y, ws.x, lw.n1_w, lw.n1_b, n_rows, sp.dim, eps);
-    ECB_LAUNCHED();
     LinArgs f1{};
-    f1.x = ws.x; f1.W = lw.l1_w; f1.b = lw.l1_b;
+    f1.x = ws.y; f1.W = lw.l1_w; f1.b = lw.l1_b; f1.ln_w = lw.n1_w; f1.ln_b = lw.n1_b; f1.eps = eps;
     f1.K = sp.dim; f1.N = sp.hidden; f1.n_rows = n_rows; f1.out = ws.hid;
     if (launch_linear<EPI_GELU>(f1, s)) return 1;
     LinArgs f2{};
-    f2.x = ws.hid; f2.W = lw.l2_w; f2.b = lw.l2_b;
-    f2.K = sp.hidden; f2.N = sp.dim; f2.n_rows = n_rows; f2.out = ws.y; f2.resid = ws.x;
+    f2.x = ws.hid; f2.W = lw.l2_w; f2.b = lw.l2_b; f2.eps = eps;
+    f2.K = sp.hidden; f2.N = sp.dim; f2.n_rows = n_rows; f2.out = ws.x; f2.resid = ws.y; f2.rln_w = lw.n1_w; f2.rln_b = lw.n1_b;
     if (launch_linear<EPI_RESID>(f2, s)) return 1;
-    lm_ln_kernel<<<row_blocks, kWarps * 32, 0, s>>>(ws.y, ws.x, lw.n2_w, lw.n2_b, n_rows, sp.dim, eps);
-    ECB_LAUNCHED();
   }
   return 0;
 }
@@ -705,12 +696,16 @@ int lm_heads(const Lm& lm, const Tokens& tk, long long n_items, int K, long long
     const long long nr = (n_rows - r0) < kHeadRows ? (n_rows - r0) : kHeadRows;
     LinArgs a{};
     a.x = ws.x + (size_t)r0 * sp.dim; a.W = lm.weights + lm.lin_w_off; a.b = lm.weights + lm.lin_b_off;
+    a.ln_w = lm.layers.back().n2_w; a.ln_b = lm.layers.back().n2_b; a.eps = 1e-5f;   // norm2 of the last layer, pending on ws.x
     a.K = sp.dim; a.N = K * sp.card; a.n_rows = nr; a.out = ws.logits;
     if (launch_linear<EPI_PLAIN>(a, s)) return 1;
     dim3 grid((unsigned)nr, (unsigned)K);
-    lm_softmax_cdf_kernel<<<grid, kWarps * 32, (size_t)sp.card * sizeof(float), s>>>(ws.logits, r0, sp.card, K, tk, (int)n_t, t0,
-                                                                                  t_ptr, cp, probas, cdf, sym_ranges);
-    ECB_LAUNCHED();
+    {
+      ProfScope prof(PROF_LM_MISC, s, 0.0, 0.0);
+      lm_softmax_cdf_kernel<<<grid, kWarps * 32, (size_t)sp.card * sizeof(float), s>>>(ws.logits, r0, sp.card, K, tk, (int)n_t, t0,
+                                                                                    t_ptr, cp, probas, cdf, sym_ranges);
+      ECB_LAUNCHED();
+    }
   }
   return 0;
 }
@@ -721,6 +716,7 @@ int launch_ac_pull(ac::Decoder* st, const unsigned char* data, long long n_bytes
   ECB_REQUIRE(group >= 1, "ac: card = %d does not fit the decoder kernel's shared memory", card);
   if (group > K) group = (int)K;
   ECB_CUDA(cudaFuncSetAttribute(lm_ac_pull_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAcSmem));   // per device, cheap
+  ProfScope prof(PROF_AC_PULL, s, 0.0, 4.0 * (double)K * card);
   lm_ac_pull_kernel<<<1, kAcThreads, (size_t)group * card * sizeof(int), s>>>(st, data, n_bytes * 8, cdf, (int)K, card, bits, group,
                                                                             codes, k_stride, t, t_ptr);
   ECB_LAUNCHED();
@@ -767,8 +763,8 @@ int ecb_lm_create(const ecb_lm_spec* spec, ecb_lm** out) {
               "lm_create: head dimension must divide dim and be <= 32 (dim %d, heads %d)", spec->dim, spec->n_heads);
   ECB_REQUIRE(spec->hidden >= 32 && spec->hidden <= 1024, "lm_create: hidden %d (32..1024)", spec->hidden);
   ECB_REQUIRE(spec->card >= 2 && spec->card <= 2048, "lm_create: card %d (2..2048)", spec->card);
-  ECB_REQUIRE(spec->n_q >= 1 && spec->n_layers >= 1 && spec->past_context >= 1 && spec->past_context <= 1400 /* kAttnKeys * kAttnThreads - 1 = 1535 keys at most */,
-              "lm_create: n_q %d, layers %d, past_context %d (1..1400)", spec->n_q, spec->n_layers, spec->past_context);
+  ECB_REQUIRE(spec->n_q >= 1 && spec->n_layers >= 1 && spec->past_context >= 1 && spec->past_context <= 8192,
+              "lm_create: n_q %d, layers %d, past_context %d (1..8192)", spec->n_q, spec->n_layers, spec->past_context);
   ECB_REQUIRE(2.0 * spec->card <= (double)(1 << 24), "lm_create: card too large for 24 range bits");
   Lm* lm = new Lm();
   lm->spec = LmSpec{spec->n_q, spec->card, spec->dim, spec->n_layers, spec->n_heads, spec->hidden, spec->past_context, spec->max_period};
@@ -939,7 +935,7 @@ int ecb_lm_decode_frame(ecb_lm* h, const uint8_t* data, int64_t n_bytes, int64_t
   lm_ac_init_kernel<<<1, 32, 0, s>>>(ws.dec, first_byte * 8, ws.step);
   ECB_LAUNCHED();
   const char* genv = getenv("ECB_LM_GRAPH");   // diagnostic: 0 = launch every step's kernels from the host
-  const bool use_graph = (genv ? atoi(genv) != 0 : true) && n_steps >= 8;
+  const bool use_graph = (genv ? atoi(genv) != 0 : true) && n_steps >= 8 && !prof_enabled();   // the profiler times launches
   if (!use_graph) {
     for (long long t = 0; t < n_steps; ++t) {
       if (lm_trunk(*lm, tk, 1, K, t, nullptr, 1, cache, capacity, ws, s)) return 1;
@@ -947,7 +943,7 @@ int ecb_lm_decode_frame(ecb_lm* h, const uint8_t* data, int64_t n_bytes, int64_t
       if (launch_ac_pull(ws.dec, data, n_bytes, ws.cdf, K, lm->spec.card, 24, lcodes, n_steps, t, nullptr, s)) return 1;
     }
   } else {
-    // the step's launches (39 for 5 layers) as one CUDA graph: every kernel reads the step index from ws.step, the pull kernel advances it
+    // the step's launches (29 for 5 layers) as one CUDA graph: every kernel reads the step index from ws.step, the pull kernel advances it
     StepGraph& sg = g_step_graphs[lm];
     const StepGraphKey key{data, codes, cache, workspace, n_bytes, K, n_steps, capacity};
     if (!sg.exec || !(sg.key == key)) {
@@ -974,7 +970,7 @@ int ecb_lm_decode_frame(ecb_lm* h, const uint8_t* data, int64_t n_bytes, int64_t
     }
     for (long long t = 0; t < n_steps; ++t) {
       ECB_CUDA(cudaGraphLaunch(sg.exec, s));
-      g_launches.fetch_add(1 + 7 * lm->spec.n_layers + 3, std::memory_order_relaxed);
+      g_launches.fetch_add(1 + 5 * lm->spec.n_layers + 3, std::memory_order_relaxed);
     }
   }
   lm_ac_result_kernel<<<1, 32, 0, s>>>(ws.dec, reinterpret_cast<long long*>(result));
