@@ -6,9 +6,10 @@
 //   effective_low  = ceil (range_low  * (delta / 2^total_range_bits))     (ac.py:145, 240)
 //   effective_high = floor(range_high * (delta / 2^total_range_bits))     (ac.py:146, 241)
 // in Python floats: `delta / 2^bits` is the correctly rounded double of delta scaled by a power of two, the product is ONE
-// IEEE double multiplication. Both are reproduced operation for operation (explicitly rounded intrinsics on the device,
-// so that no contraction can change them). Bits travel through BitPacker(bits=1) (binary.py:55-89): bit i of the stream
-// is bit (i % 8) of byte i / 8.
+// IEEE double multiplication. For the coder's default 24 range bits (the only setting compress.py uses) that product is exact
+// and both expressions are evaluated in 64-bit integers (make_scale below); otherwise they are reproduced operation for
+// operation in doubles (explicitly rounded intrinsics on the device, so that no contraction can change them). Bits travel
+// through BitPacker(bits=1) (binary.py:55-89): bit i of the stream is bit (i % 8) of byte i / 8.
 #pragma once
 #include <math.h>
 #include <stdint.h>
@@ -24,27 +25,44 @@ namespace ac {
 
 enum Status { AC_OK = 0, AC_EOF = 1, AC_SEARCH_FAILED = 2, AC_RANGE_OVERFLOW = 3, AC_BAD_CDF = 4 };
 
-ECB_AC_HD double scaled_delta(uint64_t delta, int bits) {
+// Exact integer form for bits <= 26: delta < 2^(bits + 1) whenever a symbol is coded (the refill loop stops at the first
+// delta >= 2^bits) and every cdf value is <= 2^bits + card, so range * delta < 2^53: the double product above is exact and
+// ceil / floor of it are the integer expressions below. compress.py only ever uses bits = 24. Wider settings keep the
+// reference's double arithmetic operation for operation.
+struct Scale {
+  uint64_t delta;
+  double ratio;
+  int bits;
+  bool exact_int;
+};
+ECB_AC_HD Scale make_scale(uint64_t delta, int bits) {
+  Scale s;
+  s.delta = delta;
+  s.bits = bits;
+  s.exact_int = bits <= 26 && delta < (1ull << (bits + 1));
   // delta / 2**bits (ac.py:145): conversion rounds to nearest-even like Python's int / int, the scaling is exact
 #if defined(__CUDA_ARCH__)
-  return __dmul_rn(__ull2double_rn((unsigned long long)delta), 1.0 / (double)(1ull << bits));
+  s.ratio = s.exact_int ? 0.0 : __dmul_rn(__ull2double_rn((unsigned long long)delta), 1.0 / (double)(1ull << bits));
 #else
-  return (double)delta * (1.0 / (double)(1ull << bits));
+  s.ratio = (double)delta * (1.0 / (double)(1ull << bits));
 #endif
+  return s;
 }
-ECB_AC_HD uint64_t eff_low(int64_t range_low, double ratio) {
+ECB_AC_HD uint64_t eff_low(int64_t range_low, const Scale& sc) {
+  if (sc.exact_int) return ((uint64_t)range_low * sc.delta + ((1ull << sc.bits) - 1ull)) >> sc.bits;
 #if defined(__CUDA_ARCH__)
-  return (uint64_t)ceil(__dmul_rn((double)range_low, ratio));
+  return (uint64_t)ceil(__dmul_rn((double)range_low, sc.ratio));
 #else
-  volatile double p = (double)range_low * ratio;   // volatile: one rounded product, never fused or kept in extended precision
+  volatile double p = (double)range_low * sc.ratio;   // volatile: one rounded product, never fused or kept in extended precision
   return (uint64_t)ceil(p);
 #endif
 }
-ECB_AC_HD uint64_t eff_high(int64_t range_high, double ratio) {
+ECB_AC_HD uint64_t eff_high(int64_t range_high, const Scale& sc) {
+  if (sc.exact_int) return ((uint64_t)range_high * sc.delta) >> sc.bits;
 #if defined(__CUDA_ARCH__)
-  return (uint64_t)floor(__dmul_rn((double)range_high, ratio));
+  return (uint64_t)floor(__dmul_rn((double)range_high, sc.ratio));
 #else
-  volatile double p = (double)range_high * ratio;
+  volatile double p = (double)range_high * sc.ratio;
   return (uint64_t)floor(p);
 #endif
 }
@@ -134,7 +152,7 @@ ECB_AC_HD void flush_prefix(Decoder& d) {
 ECB_AC_HD int pull(Decoder& d, const uint8_t* data, int64_t n_bits, const int32_t* cdf, int card, int bits) {
   if (d.status != AC_OK) return -1;
   if (!refill(d, data, n_bits, bits)) return -1;                          // ac.py:224-231
-  const double ratio = scaled_delta(d.high - d.low + 1, bits);
+  const Scale ratio = make_scale(d.high - d.low + 1, bits);
   int lo_idx = 0, hi_idx = card - 1, mid = 0;
   uint64_t low = 0, high = 0;
   for (;;) {                                                             // bin_search, ac.py:233-251
@@ -197,7 +215,7 @@ struct Encoder {
       ++max_bit;
     }
     if (range_high_excl - 1 < range_low || range_low < 0) { status = AC_BAD_CDF; return false; }
-    const double ratio = scaled_delta(high - low + 1, bits);
+    const Scale ratio = make_scale(high - low + 1, bits);
     const uint64_t el = eff_low(range_low, ratio), eh = eff_high(range_high_excl - 1, ratio);
     high = low + eh;
     low = low + el;

@@ -451,7 +451,7 @@ __device__ __forceinline__ int ac_pull_warp(ac::Decoder& d, const unsigned char*
                                             const int* cdf, int card, int bits, int lane) {
   if (d.status != ac::AC_OK) return -1;
   if (!ac::refill(d, data, n_bits, bits)) return -1;
-  const double ratio = ac::scaled_delta(d.high - d.low + 1, bits);
+  const ac::Scale ratio = ac::make_scale(d.high - d.low + 1, bits);
   int base = 0, span = card;
   while (span > 1) {
     const int step = (span + 31) >> 5;

@@ -96,6 +96,18 @@ def test_host_coder_errors_and_random_round_trips():
         assert got.tolist() == symbols.tolist() and used == len(data)
         with pytest.raises(EOFError, match="ended sooner"):          # compress.py:143-144
             lm.ac_decode(data[: len(data) // 2], cdfs)
+    # 28 range bits: beyond the exact-integer window of ac_core.h, the coder runs the reference's double arithmetic
+    pdf = rng.random((300, 64)).astype(np.float32) ** 6
+    pdf /= pdf.sum(axis=1, keepdims=True) * 1.0001
+    cdfs28 = lo.build_stable_quantized_cdf(pdf, total_range_bits=28)
+    sym28 = rng.integers(0, 64, 300)
+    coder = lo.ArithmeticCoder(28)
+    for sy, c in zip(sym28, cdfs28):
+        coder.push(int(sy), c)
+    want = coder.finish()
+    assert lm.ac_encode(_ranges(cdfs28, sym28), 28) == want
+    got, used = lm.ac_decode(want, cdfs28, 28)
+    assert got.tolist() == sym28.tolist() and used == len(want)
     # a buffer that is too small is an error, not an overrun
     r = _ranges(cdfs, symbols).astype(np.int32)
     out = np.zeros(8, dtype=np.uint8)
