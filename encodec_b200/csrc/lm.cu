@@ -23,6 +23,7 @@
 // seeds its state with (transformer.py:103-104; it is attended like a real position until the window drops it), row p + 1
 // position p. These are CUDA-core kernels: the work is a few MFLOP per step and latency-bound (decode) or a few GFLOP per
 // call (compress); what matters is the launch count and that nothing returns to the host inside the loop.
+#include <cooperative_groups.h>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -77,39 +78,37 @@ __device__ __forceinline__ long long token_index(const Tokens& tk, long long ite
   return v < 0 ? 0 : (v > card ? card : v);
 }
 
+// ---- arithmetic shared by the batched kernels and the one-row cluster kernel ------------------------------------------
+// Every floating-point operation below is an explicitly rounded intrinsic (or an explicit fmaf): the compiler may not
+// contract or reassociate them differently in different kernels, so a value computed by lm_step_cluster_kernel and by the
+// batched kernels is the same bit pattern -- the property the arithmetic coder needs (see the header of this file).
+
 // LayerNorm of one row held as dim / 32 values per lane (nn.LayerNorm, eps inside the square root, biased variance)
 __device__ __forceinline__ void warp_layer_norm(float (&v)[kMaxDimPerLane], int dim, int lane, const float* __restrict__ w,
                                                 const float* __restrict__ b, float eps) {
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < kMaxDimPerLane; ++i) s += (lane + 32 * i < dim) ? v[i] : 0.f;
-  const float mean = warp_sum(s) / (float)dim;
+  for (int i = 0; i < kMaxDimPerLane; ++i) s = __fadd_rn(s, (lane + 32 * i < dim) ? v[i] : 0.f);
+  const float mean = __fdiv_rn(warp_sum(s), (float)dim);
   float q = 0.f;
 #pragma unroll
   for (int i = 0; i < kMaxDimPerLane; ++i) {
-    const float d = (lane + 32 * i < dim) ? v[i] - mean : 0.f;
+    const float d = (lane + 32 * i < dim) ? __fsub_rn(v[i], mean) : 0.f;
     q = fmaf(d, d, q);
   }
-  const float rstd = 1.f / sqrtf(warp_sum(q) / (float)dim + eps);
+  const float rstd = __fdiv_rn(1.f, __fsqrt_rn(__fadd_rn(__fdiv_rn(warp_sum(q), (float)dim), eps)));
 #pragma unroll
   for (int i = 0; i < kMaxDimPerLane; ++i) {
     const int d = lane + 32 * i;
-    if (d < dim) v[i] = (v[i] - mean) * rstd * w[d] + b[d];
+    if (d < dim) v[i] = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(v[i], mean), rstd), w[d]), b[d]);
   }
 }
 
-// model.py:79 (sum of embeddings) + transformer.py:106-111 (norm_in, + sinusoidal position embedding). One warp per row.
-__global__ void lm_embed_kernel(Tokens tk, const float* __restrict__ emb, const float* __restrict__ nw,
-                                const float* __restrict__ nb, const float* __restrict__ pos_div, float* __restrict__ x,
-                                long long n_rows, int n_t, long long t0_arg, const long long* __restrict__ t_ptr, int K,
-                                int card, int dim, float eps) {
-  const int lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5);
-  if (row >= n_rows) return;
-  const long long t0 = t_ptr ? *t_ptr : t0_arg;   // the decoding loop replays one captured step: t lives on the device
-  const long long item = row / n_t;
-  const long long t = t0 + row % n_t;
-  float v[kMaxDimPerLane];
+// model.py:79 (sum of embeddings) + transformer.py:106-111 (norm_in, + sinusoidal position embedding) for one row by one warp
+__device__ __forceinline__ void embed_row(const Tokens& tk, const float* __restrict__ emb, const float* __restrict__ nw,
+                                          const float* __restrict__ nb, const float* __restrict__ pos_div, long long item,
+                                          long long t, long long t0, int K, int card, int dim, float eps, int lane,
+                                          float (&v)[kMaxDimPerLane]) {
 #pragma unroll
   for (int i = 0; i < kMaxDimPerLane; ++i) v[i] = 0.f;
   for (int k0 = 0; k0 < K; k0 += 32) {   // the indices first (one lane per codebook), so that the row loads do not wait on them
@@ -131,7 +130,7 @@ __global__ void lm_embed_kernel(Tokens tk, const float* __restrict__ emb, const 
       for (int u = 0; u < 8; ++u) {
         if (k1 + u < g) {
 #pragma unroll
-          for (int i = 0; i < kMaxDimPerLane; ++i) v[i] += e[u][i];
+          for (int i = 0; i < kMaxDimPerLane; ++i) v[i] = __fadd_rn(v[i], e[u][i]);
         }
       }
     }
@@ -144,8 +143,113 @@ __global__ void lm_embed_kernel(Tokens tk, const float* __restrict__ emb, const 
     if (d < dim) {
       // create_sin_embedding (transformer.py:16-27): float32 phase = position / max_period^(j / (half - 1)), cat(cos, sin)
       const float phase = __fdiv_rn((float)t, pos_div[d < half ? d : d - half]);
-      x[row * dim + d] = v[i] + (d < half ? cosf(phase) : sinf(phase));
+      v[i] = __fadd_rn(v[i], d < half ? cosf(phase) : sinf(phase));
     }
+  }
+}
+
+// NC weight rows of a warp in registers: k = lane + 32 i (zero beyond K or for columns n < 0)
+template <int KPL, int NC>
+__device__ __forceinline__ void load_cols(const float* __restrict__ W, const float* __restrict__ b, int K, const int (&n)[NC],
+                                          int lane, float (&w)[NC][KPL], float (&bias)[NC]) {
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+#pragma unroll
+    for (int i = 0; i < KPL; ++i) {
+      const int k = lane + 32 * i;
+      w[c][i] = (n[c] >= 0 && k < K) ? W[(size_t)n[c] * K + k] : 0.f;
+    }
+    bias[c] = n[c] >= 0 ? b[n[c]] : 0.f;
+  }
+}
+// b[n] + sum_k W[n][k] x[k] for the warp's NC columns: lane-local fmaf chain in i order, xor tree, + bias (all lanes hold it)
+template <int KPL, int NC>
+__device__ __forceinline__ void dot_cols(const float (&w)[NC][KPL], const float (&bias)[NC], const float* xs, int K, int lane,
+                                         float (&out)[NC]) {
+  float acc[NC];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) acc[c] = 0.f;
+#pragma unroll
+  for (int i = 0; i < KPL; ++i) {
+    const int k = lane + 32 * i;
+    if (k < K) {
+      const float xv = xs[k];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) acc[c] = fmaf(w[c][i], xv, acc[c]);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < NC; ++c) out[c] = __fadd_rn(warp_sum(acc[c]), bias[c]);
+}
+__device__ __forceinline__ float gelu_exact(float v) {   // F.gelu, erf form
+  return __fmul_rn(__fmul_rn(0.5f, v), __fadd_rn(1.f, erff(__fmul_rn(v, 0.70710678118654752440f))));
+}
+
+constexpr int kAttnThreads = 512;   // 16 warps per (row, head): at past_context = 262 a warp owns <= 17 keys
+// _sa_block (transformer.py:42-59) for one (row, head) by one block of kAttnThreads: keys / values = nk cache rows starting
+// at kv (already offset to the head's slice). Warp w owns keys w, w + 16, ...; a key's head slice (hd <= 32 contiguous
+// floats) is read by the lanes of the warp (one coalesced request per key), the score is the xor-tree sum of the lane
+// products; max and sum are block reductions in warp order; the weighted values are one accumulator per lane (= head
+// dimension) and warp, summed across the warps in warp order. Returns the output of dimension tid (valid for tid < hd).
+__device__ __forceinline__ float attn_head(float qv, const float* kv, int nk, int dim, int hd, float* sc,
+                                           float* red, float (*part)[32], int tid) {
+  constexpr int NW = kAttnThreads / 32;
+  const int lane = tid & 31, warp = tid >> 5;
+  const float scale = __fdiv_rn(1.f, __fsqrt_rn((float)hd));
+  float m = -INFINITY;
+#pragma unroll 8
+  for (int i = warp; i < nk; i += NW) {
+    const float kval = lane < hd ? kv[(size_t)i * 2 * dim + lane] : 0.f;
+    const float s = __fmul_rn(warp_sum(__fmul_rn(qv, kval)), scale);
+    if (lane == 0) sc[i] = s;
+    m = fmaxf(m, s);
+  }
+  if (lane == 0) red[warp] = m;
+  __syncthreads();
+  m = red[0];
+#pragma unroll
+  for (int w2 = 1; w2 < NW; ++w2) m = fmaxf(m, red[w2]);
+  __syncthreads();
+  float l = 0.f, acc = 0.f;
+#pragma unroll 8
+  for (int i = warp; i < nk; i += NW) {
+    const float e = expf(__fsub_rn(sc[i], m));
+    const float vval = lane < hd ? kv[(size_t)i * 2 * dim + dim + lane] : 0.f;
+    l = __fadd_rn(l, e);
+    acc = fmaf(e, vval, acc);
+  }
+  if (lane == 0) red[warp] = l;
+  part[warp][lane] = acc;
+  __syncthreads();
+  float o = 0.f;
+  if (tid < hd) {
+    float L = red[0], O = part[0][tid];
+#pragma unroll
+    for (int w2 = 1; w2 < NW; ++w2) {
+      L = __fadd_rn(L, red[w2]);
+      O = __fadd_rn(O, part[w2][tid]);
+    }
+    o = __fdiv_rn(O, L);
+  }
+  __syncthreads();   // sc / red / part may be reused by the caller
+  return o;
+}
+
+// ---- batched kernels (any number of rows) ----------------------------------------------------------------------------
+__global__ void lm_embed_kernel(Tokens tk, const float* __restrict__ emb, const float* __restrict__ nw,
+                                const float* __restrict__ nb, const float* __restrict__ pos_div, float* __restrict__ x,
+                                long long n_rows, int n_t, long long t0_arg, const long long* __restrict__ t_ptr, int K,
+                                int card, int dim, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5);
+  if (row >= n_rows) return;
+  const long long t0 = t_ptr ? *t_ptr : t0_arg;   // the decoding loop replays one captured step: t lives on the device
+  float v[kMaxDimPerLane];
+  embed_row(tk, emb, nw, nb, pos_div, row / n_t, t0 + row % n_t, t0, K, card, dim, eps, lane, v);
+#pragma unroll
+  for (int i = 0; i < kMaxDimPerLane; ++i) {
+    const int d = lane + 32 * i;
+    if (d < dim) x[row * dim + d] = v[i];
   }
 }
 
@@ -171,9 +275,8 @@ struct LinArgs {
 };
 
 // y[r][n] = epilogue(b[n] + sum_k W[n][k] x[r][k]). A warp owns kColsPerWarp output columns: their weight rows sit in
-// registers (KPL values per lane and column, k = lane + 32 i; all loads of the warp are in flight together), the rows of
-// the tile come from shared memory; per (row, column) a lane-local fmaf chain in i order, then the xor tree -- the same
-// sequence for every row, whatever the launch shape.
+// registers (all loads of the warp in flight together, issued before the activation tile is awaited), the rows of the tile
+// come from shared memory; per (row, column) the fixed sequence of dot_cols -- the same for every row, whatever the launch shape.
 template <int KPL, int EPI>
 __global__ void __launch_bounds__(kWarps * 32) lm_linear_kernel(LinArgs a) {
   extern __shared__ float xs[];   // [kRowTile][K]
@@ -181,19 +284,12 @@ __global__ void __launch_bounds__(kWarps * 32) lm_linear_kernel(LinArgs a) {
   const long long r0 = (long long)blockIdx.y * kRowTile;
   const int nr = (int)((a.n_rows - r0) < kRowTile ? (a.n_rows - r0) : kRowTile);
   float* rs = xs + kRowTile * a.K;   // [kRowTile][N], only with rln_w
-  // the warp's weight rows first: they do not depend on the activations, so their latency overlaps the tile load below
   const int n0 = (blockIdx.x * kWarps + warp) * kColsPerWarp;
+  int ncol[kColsPerWarp];
+#pragma unroll
+  for (int c = 0; c < kColsPerWarp; ++c) ncol[c] = (n0 + c < a.N) ? n0 + c : -1;
   float w[kColsPerWarp][KPL], bias[kColsPerWarp];
-#pragma unroll
-  for (int c = 0; c < kColsPerWarp; ++c) {
-    const int n = n0 + c;
-#pragma unroll
-    for (int i = 0; i < KPL; ++i) {
-      const int k = lane + 32 * i;
-      w[c][i] = (n < a.N && k < a.K) ? a.W[(size_t)n * a.K + k] : 0.f;
-    }
-    bias[c] = n < a.N ? a.b[n] : 0.f;
-  }
+  load_cols<KPL, kColsPerWarp>(a.W, a.b, a.K, ncol, lane, w, bias);
   for (int i = threadIdx.x; i < nr * a.K; i += blockDim.x) xs[i] = a.x[r0 * a.K + i];
   if (EPI == EPI_RESID && a.rln_w)
     for (int i = threadIdx.x; i < nr * a.N; i += blockDim.x) rs[i] = a.resid[r0 * a.N + i];
@@ -233,31 +329,19 @@ __global__ void __launch_bounds__(kWarps * 32) lm_linear_kernel(LinArgs a) {
   if (n0 >= a.N) return;   // warp-uniform, no block-wide barrier below
   const long long t0 = (EPI == EPI_QKV && a.t_ptr) ? *a.t_ptr : a.t0;
   for (int r = 0; r < nr; ++r) {
-    float acc[kColsPerWarp];
-#pragma unroll
-    for (int c = 0; c < kColsPerWarp; ++c) acc[c] = 0.f;
-#pragma unroll
-    for (int i = 0; i < KPL; ++i) {
-      const int k = lane + 32 * i;
-      if (k < a.K) {
-        const float xv = xs[r * a.K + k];
-#pragma unroll
-        for (int c = 0; c < kColsPerWarp; ++c) acc[c] = fmaf(w[c][i], xv, acc[c]);
-      }
-    }
-#pragma unroll
-    for (int c = 0; c < kColsPerWarp; ++c) acc[c] = warp_sum(acc[c]);
+    float res[kColsPerWarp];
+    dot_cols<KPL, kColsPerWarp>(w, bias, xs + r * a.K, a.K, lane, res);
     float v = 0.f;   // lane c finishes column n0 + c
 #pragma unroll
     for (int c = 0; c < kColsPerWarp; ++c)
-      if (lane == c) v = acc[c] + bias[c];
+      if (lane == c) v = res[c];
     const int n = n0 + lane;
     if (lane < kColsPerWarp && n < a.N) {
       const long long row = r0 + r;
       if (EPI == EPI_GELU) {
-        a.out[row * a.N + n] = 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));   // F.gelu (exact, erf form)
+        a.out[row * a.N + n] = gelu_exact(v);
       } else if (EPI == EPI_RESID) {
-        a.out[row * a.N + n] = (a.rln_w ? rs[r * a.N + n] : a.resid[row * a.N + n]) + v;
+        a.out[row * a.N + n] = __fadd_rn(a.rln_w ? rs[r * a.N + n] : a.resid[row * a.N + n], v);
       } else if (EPI == EPI_PLAIN) {
         a.out[row * a.N + n] = v;
       } else {
@@ -274,13 +358,6 @@ __global__ void __launch_bounds__(kWarps * 32) lm_linear_kernel(LinArgs a) {
   }
 }
 
-// _sa_block (transformer.py:42-59) for one (row, head) per block: keys / values = cache rows [lo, t + 1], lo = t + 1 - min(t + 1,
-// past_context) (the rows the streaming state still holds, transformer.py:116-117). Warp w owns keys w, w + 32, ...; a key's
-// head slice (hd <= 32 contiguous floats) is read by the lanes of the warp (one coalesced request per key instead of one
-// cache line per lane), the score is the xor-tree sum of the lane products; max and sum are block reductions in warp
-// order; the weighted values are one accumulator per lane (= head dimension) and warp, summed across the warps in warp
-// order. One partition for every launch shape; in the decoding loop (one row) the keys of a head are spread over 32 warps.
-constexpr int kAttnThreads = 1024;   // 32 warps: at past_context = 262 a warp owns <= 9 keys, all of their loads in flight together
 __global__ void __launch_bounds__(kAttnThreads) lm_attn_kernel(const float* __restrict__ q, const float* __restrict__ cache,
                                                                 float* __restrict__ out, int n_t, long long t0_arg,
                                                                 const long long* __restrict__ t_ptr, long long capacity, int dim,
@@ -288,54 +365,170 @@ __global__ void __launch_bounds__(kAttnThreads) lm_attn_kernel(const float* __re
   extern __shared__ float sc[];   // [past_context + 1] scores
   __shared__ float red[kAttnThreads / 32];
   __shared__ float part[kAttnThreads / 32][32];
-  constexpr int NW = kAttnThreads / 32;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
   const long long w = blockIdx.x;
   const long long t0 = t_ptr ? *t_ptr : t0_arg;
   const long long row = w / heads;
   const int h = (int)(w % heads);
   const long long item = row / n_t, t = t0 + row % n_t;
   const int hd = dim / heads;
+  // the rows the streaming state still holds (transformer.py:116-117): cache rows [lo, t + 1], lo = t + 1 - min(t + 1, past_context)
   const long long n_past = (t + 1) < past_context ? (t + 1) : past_context;
   const long long lo = t + 1 - n_past;
   const int nk = (int)n_past + 1;
   const float* kv = cache + ((size_t)item * (capacity + 1) + (size_t)lo) * 2 * dim + h * hd;
   const float qv = lane < hd ? q[row * dim + h * hd + lane] : 0.f;
-  const float scale = 1.f / sqrtf((float)hd);
-  float m = -INFINITY;
-#pragma unroll 8
-  for (int i = warp; i < nk; i += NW) {
-    const float kval = lane < hd ? kv[(size_t)i * 2 * dim + lane] : 0.f;
-    const float s = warp_sum(qv * kval) * scale;
-    if (lane == 0) sc[i] = s;
-    m = fmaxf(m, s);
-  }
-  if (lane == 0) red[warp] = m;
-  __syncthreads();
-  m = red[0];
+  const float o = attn_head(qv, kv, nk, dim, hd, sc, red, part, tid);
+  if (tid < hd) out[row * dim + h * hd + tid] = o;
+}
+
+// ---- the decoding step's transformer as ONE cluster kernel (one row) --------------------------------------------------
+// Eight CTAs = eight heads. CTA h computes the q / k / v columns of ITS head (so attention needs no exchange), then its eighth
+// of out_proj, linear1 and linear2; after each of the four phases of a layer the finished values are written into every
+// CTA's copy of the row (distributed shared memory) behind one hardware cluster barrier. 20 barriers replace the 25 launches
+// of lm_trunk on a single row; the arithmetic is the shared functions above, bit for bit what the batched kernels compute.
+constexpr int kClusterCtas = 8;
+constexpr int kMaxLayers = 8;
+struct ClusterArgs {
+  Tokens tk;
+  const float *emb, *nin_w, *nin_b, *pos_div;
+  const float* lw[kMaxLayers][12];   // in_w, in_b, out_w, out_b, l1_w, l1_b, l2_w, l2_b, n1_w, n1_b, n2_w, n2_b
+  int n_layers;
+  float* cache;                      // [layers][1][capacity + 1][2 dim]
+  long long capacity;
+  const long long* t_ptr;
+  long long t0;
+  int K, card, dim, heads, hidden, past_context;
+  float eps;
+  float* x_out;                      // [dim]: raw output of the last layer (norm2 pending, applied by the heads on load)
+};
+
+template <int KPL, int NC, class MapFn, class EpiFn>
+__device__ __forceinline__ void cluster_cols(const float* __restrict__ W, const float* __restrict__ b, int K, int n_local,
+                                             MapFn map, const float* xs, int lane, int warp, int n_warps, EpiFn epi) {
+  for (int g = warp; g * NC < n_local; g += n_warps) {
+    int ncol[NC];
 #pragma unroll
-  for (int w2 = 1; w2 < NW; ++w2) m = fmaxf(m, red[w2]);
-  __syncthreads();
-  float l = 0.f, acc = 0.f;
-#pragma unroll 8
-  for (int i = warp; i < nk; i += NW) {
-    const float e = expf(sc[i] - m);
-    const float vval = lane < hd ? kv[(size_t)i * 2 * dim + dim + lane] : 0.f;
-    l += e;
-    acc = fmaf(e, vval, acc);
-  }
-  if (lane == 0) red[warp] = l;
-  part[warp][lane] = acc;
-  __syncthreads();
-  if (tid < hd) {
-    float L = red[0], O = part[0][tid];
+    for (int c = 0; c < NC; ++c) ncol[c] = (g * NC + c < n_local) ? map(g * NC + c) : -1;
+    float w[NC][KPL], bias[NC], res[NC];
+    load_cols<KPL, NC>(W, b, K, ncol, lane, w, bias);
+    dot_cols<KPL, NC>(w, bias, xs, K, lane, res);
+    float v = 0.f;
+    int n = -1;
 #pragma unroll
-    for (int w2 = 1; w2 < NW; ++w2) {
-      L += red[w2];
-      O += part[w2][tid];
+    for (int c = 0; c < NC; ++c)
+      if (lane == c) {
+        v = res[c];
+        n = ncol[c];
+      }
+    if (lane < NC && n >= 0) epi(n, v);
+  }
+}
+
+template <int KPL_D, int KPL_H>
+__global__ void __cluster_dims__(kClusterCtas, 1, 1) __launch_bounds__(kAttnThreads) lm_step_cluster_kernel(ClusterArgs a) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ float sc[];                  // [past_context + 1] attention scores
+  __shared__ float X[256], XN[256], ATT[256], Y[256], YN[256], HID[1024], QL[32];
+  __shared__ float red[kAttnThreads / 32];
+  __shared__ float part[kAttnThreads / 32][32];
+  constexpr int NWARPS = kAttnThreads / 32;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int h = (int)cluster.block_rank();       // this CTA's head
+  const int dim = a.dim, hd = dim / a.heads, hidden = a.hidden;
+  const long long t = a.t_ptr ? *a.t_ptr : a.t0;
+  const size_t layer_cache = (size_t)(a.capacity + 1) * 2 * dim;
+  if (warp == 0) {   // every CTA forms the input row itself (one warp per row, as lm_embed_kernel)
+    float v[kMaxDimPerLane];
+    embed_row(a.tk, a.emb, a.nin_w, a.nin_b, a.pos_div, 0, t, t, a.K, a.card, dim, a.eps, lane, v);
+#pragma unroll
+    for (int i = 0; i < kMaxDimPerLane; ++i) {
+      const int d = lane + 32 * i;
+      if (d < dim) X[d] = v[i];
     }
-    out[row * dim + h * hd + tid] = O / L;
   }
+  cluster.sync();    // also: no CTA writes into a peer before that peer has started
+  const long long n_past = (t + 1) < a.past_context ? (t + 1) : a.past_context;
+  const long long lo = t + 1 - n_past;
+  const int nk = (int)n_past + 1;
+  for (int l = 0; l < a.n_layers; ++l) {
+    const float* const* lw = a.lw[l];
+    float* lc = a.cache + (size_t)l * layer_cache;
+    if (warp == 0) {   // XN = the layer's input: the embedding (layer 0) or norm2 of the previous layer applied to its raw output
+      float v[kMaxDimPerLane];
+#pragma unroll
+      for (int i = 0; i < kMaxDimPerLane; ++i) {
+        const int d = lane + 32 * i;
+        v[i] = d < dim ? X[d] : 0.f;
+      }
+      if (l) warp_layer_norm(v, dim, lane, a.lw[l - 1][10], a.lw[l - 1][11], a.eps);
+#pragma unroll
+      for (int i = 0; i < kMaxDimPerLane; ++i) {
+        const int d = lane + 32 * i;
+        if (d < dim) XN[d] = v[i];
+      }
+    }
+    __syncthreads();
+    // q / k / v of head h: local column j -> in_proj row (j / hd) * dim + h * hd + j % hd
+    cluster_cols<KPL_D, 5>(lw[0], lw[1], dim, 3 * hd, [&](int j) { return (j / hd) * dim + h * hd + j % hd; }, XN, lane, warp, NWARPS,
+                           [&](int n, float v) {
+                             if (n < dim) {
+                               QL[n - h * hd] = v;
+                             } else {
+                               lc[(size_t)(t + 1) * 2 * dim + (n - dim)] = v;
+                               if (t == 0) lc[n - dim] = lw[1][n];
+                             }
+                           });
+    __syncthreads();   // QL and this block's own cache writes are visible to the block
+    {
+      const float qv = lane < hd ? QL[lane] : 0.f;
+      const float o = attn_head(qv, lc + (size_t)lo * 2 * dim + h * hd, nk, dim, hd, sc, red, part, tid);
+      if (tid < hd) {
+#pragma unroll
+        for (int r = 0; r < kClusterCtas; ++r) cluster.map_shared_rank(ATT, r)[h * hd + tid] = o;
+      }
+    }
+    cluster.sync();
+    // out_proj + residual: this CTA's dim / 8 columns
+    cluster_cols<KPL_D, 2>(lw[2], lw[3], dim, dim / kClusterCtas, [&](int j) { return h * (dim / kClusterCtas) + j; }, ATT, lane, warp,
+                           NWARPS, [&](int n, float v) {
+                             const float y = __fadd_rn(XN[n], v);
+#pragma unroll
+                             for (int r = 0; r < kClusterCtas; ++r) cluster.map_shared_rank(Y, r)[n] = y;
+                           });
+    cluster.sync();
+    if (warp == 0) {   // YN = norm1(y)
+      float v[kMaxDimPerLane];
+#pragma unroll
+      for (int i = 0; i < kMaxDimPerLane; ++i) {
+        const int d = lane + 32 * i;
+        v[i] = d < dim ? Y[d] : 0.f;
+      }
+      warp_layer_norm(v, dim, lane, lw[8], lw[9], a.eps);
+#pragma unroll
+      for (int i = 0; i < kMaxDimPerLane; ++i) {
+        const int d = lane + 32 * i;
+        if (d < dim) YN[d] = v[i];
+      }
+    }
+    __syncthreads();
+    cluster_cols<KPL_D, 7>(lw[4], lw[5], dim, hidden / kClusterCtas, [&](int j) { return h * (hidden / kClusterCtas) + j; }, YN, lane,
+                           warp, NWARPS, [&](int n, float v) {
+                             const float g = gelu_exact(v);
+#pragma unroll
+                             for (int r = 0; r < kClusterCtas; ++r) cluster.map_shared_rank(HID, r)[n] = g;
+                           });
+    cluster.sync();
+    cluster_cols<KPL_H, 2>(lw[6], lw[7], hidden, dim / kClusterCtas, [&](int j) { return h * (dim / kClusterCtas) + j; }, HID, lane, warp,
+                           NWARPS, [&](int n, float v) {
+                             const float y2 = __fadd_rn(YN[n], v);
+#pragma unroll
+                             for (int r = 0; r < kClusterCtas; ++r) cluster.map_shared_rank(X, r)[n] = y2;
+                           });
+    cluster.sync();
+  }
+  if (h == 0 && tid < dim) a.x_out[tid] = X[tid];
 }
 
 // pdf -> range width of build_stable_quantized_cdf (ac.py:36-45) in the float32 arithmetic of the torch CPU kernels
@@ -684,6 +877,35 @@ int lm_trunk(const Lm& lm, const Tokens& tk, long long n_items, int K, long long
   return 0;
 }
 
+// The decoding step's transformer (one stream, one row) as one cluster launch where the shape allows it (the reference's LM:
+// 8 heads, dim 200, hidden 800); ECB_LM_CLUSTER=0 keeps the per-phase launches of lm_trunk.
+bool cluster_step_supported(const LmSpec& sp) {
+  const char* e = getenv("ECB_LM_CLUSTER");
+  if (e && atoi(e) == 0) return false;
+  return sp.n_heads == kClusterCtas && sp.dim % kClusterCtas == 0 && sp.hidden % kClusterCtas == 0 && sp.dim <= 32 * 7 &&
+         sp.hidden <= 32 * 25 && sp.n_layers <= kMaxLayers;
+}
+int lm_trunk_step(const Lm& lm, const Tokens& tk, int K, long long t0, const long long* t_ptr, float* cache, long long capacity,
+                  const Workspace& ws, cudaStream_t s) {
+  const LmSpec& sp = lm.spec;
+  if (!cluster_step_supported(sp)) return lm_trunk(lm, tk, 1, K, t0, t_ptr, 1, cache, capacity, ws, s);
+  ClusterArgs a{};
+  a.tk = tk;
+  a.emb = lm.weights + lm.emb_off; a.nin_w = lm.nin_w; a.nin_b = lm.nin_b; a.pos_div = lm.weights + lm.pos_off;
+  for (int l = 0; l < sp.n_layers; ++l) {
+    const Lm::LayerW& w = lm.layers[l];
+    const float* p[12] = {w.in_w, w.in_b, w.out_w, w.out_b, w.l1_w, w.l1_b, w.l2_w, w.l2_b, w.n1_w, w.n1_b, w.n2_w, w.n2_b};
+    for (int i = 0; i < 12; ++i) a.lw[l][i] = p[i];
+  }
+  a.n_layers = sp.n_layers; a.cache = cache; a.capacity = capacity; a.t_ptr = t_ptr; a.t0 = t0;
+  a.K = K; a.card = sp.card; a.dim = sp.dim; a.heads = sp.n_heads; a.hidden = sp.hidden; a.past_context = sp.past_context;
+  a.eps = 1e-5f; a.x_out = ws.x;
+  ProfScope prof(PROF_LM_LINEAR, s, 0.0, 0.0);
+  lm_step_cluster_kernel<7, 25><<<kClusterCtas, kAttnThreads, (size_t)(sp.past_context + 1) * sizeof(float), s>>>(a);
+  ECB_LAUNCHED();
+  return 0;
+}
+
 // model.py:81-83 + ac.py:18-53 on the transformer output in ws.x: the K Linear(dim, card) layers as ONE lm_linear launch over
 // their concatenated weights (N = K * card columns: 1024 blocks at K = 32 also when there is a single row), then softmax ->
 // quantised cdf per (row, codebook); kHeadRows rows at a time so that the logits stay a bounded scratch buffer.
@@ -727,9 +949,10 @@ int launch_ac_pull(ac::Decoder* st, const unsigned char* data, long long n_bytes
 struct StepGraphKey {
   const void *data, *codes, *cache, *ws;
   long long n_bytes, K, n_steps, capacity;
+  int cluster;
   bool operator==(const StepGraphKey& o) const {
     return data == o.data && codes == o.codes && cache == o.cache && ws == o.ws && n_bytes == o.n_bytes && K == o.K &&
-           n_steps == o.n_steps && capacity == o.capacity;
+           n_steps == o.n_steps && capacity == o.capacity && cluster == o.cluster;
   }
 };
 struct StepGraph {
@@ -938,14 +1161,14 @@ int ecb_lm_decode_frame(ecb_lm* h, const uint8_t* data, int64_t n_bytes, int64_t
   const bool use_graph = (genv ? atoi(genv) != 0 : true) && n_steps >= 8 && !prof_enabled();   // the profiler times launches
   if (!use_graph) {
     for (long long t = 0; t < n_steps; ++t) {
-      if (lm_trunk(*lm, tk, 1, K, t, nullptr, 1, cache, capacity, ws, s)) return 1;
+      if (lm_trunk_step(*lm, tk, K, t, nullptr, cache, capacity, ws, s)) return 1;
       if (lm_heads(*lm, tk, 1, K, t, nullptr, 1, ws, nullptr, ws.cdf, nullptr, s)) return 1;
       if (launch_ac_pull(ws.dec, data, n_bytes, ws.cdf, K, lm->spec.card, 24, lcodes, n_steps, t, nullptr, s)) return 1;
     }
   } else {
     // the step's launches (29 for 5 layers) as one CUDA graph: every kernel reads the step index from ws.step, the pull kernel advances it
     StepGraph& sg = g_step_graphs[lm];
-    const StepGraphKey key{data, codes, cache, workspace, n_bytes, K, n_steps, capacity};
+    const StepGraphKey key{data, codes, cache, workspace, n_bytes, K, n_steps, capacity, cluster_step_supported(lm->spec) ? 1 : 0};
     if (!sg.exec || !(sg.key == key)) {
       if (sg.exec) {
         cudaGraphExecDestroy(sg.exec);
@@ -953,7 +1176,7 @@ int ecb_lm_decode_frame(ecb_lm* h, const uint8_t* data, int64_t n_bytes, int64_t
       }
       if (!g_lm_capture_stream) ECB_CUDA(cudaStreamCreateWithFlags(&g_lm_capture_stream, cudaStreamNonBlocking));
       ECB_CUDA(cudaStreamBeginCapture(g_lm_capture_stream, cudaStreamCaptureModeRelaxed));
-      int rc = lm_trunk(*lm, tk, 1, K, 0, ws.step, 1, cache, capacity, ws, g_lm_capture_stream);
+      int rc = lm_trunk_step(*lm, tk, K, 0, ws.step, cache, capacity, ws, g_lm_capture_stream);
       if (!rc) rc = lm_heads(*lm, tk, 1, K, 0, ws.step, 1, ws, nullptr, ws.cdf, nullptr, g_lm_capture_stream);
       if (!rc) rc = launch_ac_pull(ws.dec, data, n_bytes, ws.cdf, K, lm->spec.card, 24, lcodes, n_steps, 0, ws.step, g_lm_capture_stream);
       cudaGraph_t graph = nullptr;
@@ -970,7 +1193,7 @@ int ecb_lm_decode_frame(ecb_lm* h, const uint8_t* data, int64_t n_bytes, int64_t
     }
     for (long long t = 0; t < n_steps; ++t) {
       ECB_CUDA(cudaGraphLaunch(sg.exec, s));
-      g_launches.fetch_add(1 + 5 * lm->spec.n_layers + 3, std::memory_order_relaxed);
+      g_launches.fetch_add((cluster_step_supported(lm->spec) ? 1 : 1 + 5 * lm->spec.n_layers) + 3, std::memory_order_relaxed);
     }
   }
   lm_ac_result_kernel<<<1, 32, 0, s>>>(ws.dec, reinterpret_cast<long long*>(result));

@@ -131,18 +131,21 @@ def test_entropy_coded_frames_round_trip_on_device(name):
     blob = b"".join(b"\xde\xad\xbe\xef" + c for c in chunks)
     data = torch.frombuffer(bytearray(blob), dtype=torch.uint8).cuda()
     import os
-    for graph in ("1", "0"):                                            # one captured step replayed / every launch from the host
+    # one captured step replayed / every launch from the host; the step's transformer as one cluster kernel / per-phase launches
+    for graph, cl in (("1", "1"), ("0", "1"), ("1", "0"), ("0", "0")):
         os.environ["ECB_LM_GRAPH"] = graph
+        os.environ["ECB_LM_CLUSTER"] = cl
         try:
             pos = 0
             for i, c in enumerate(chunks):
                 got, end = lm.decode_frame(data, pos + 4, K, T2)
-                assert torch.equal(got, codes[i]), (name, i, graph)
+                assert torch.equal(got, codes[i]), (name, i, graph, cl)
                 assert end == pos + 4 + len(c)
                 pos = end
             assert pos == len(blob)
         finally:
             os.environ.pop("ECB_LM_GRAPH", None)
+            os.environ.pop("ECB_LM_CLUSTER", None)
     with pytest.raises(EOFError, match="ended sooner"):
         lm.decode_frame(data[: 4 + len(chunks[0]) // 2], 4, K, T2)
     # fewer codebooks than the model has (a lower bandwidth): the first K - 1 embeddings / heads only (model.py:79-82)
@@ -224,6 +227,16 @@ def test_lm_throughput_note():
     finally:
         os.environ.pop("ECB_LM_GRAPH", None)
     assert torch.equal(got2, codes[0])
+    os.environ["ECB_LM_CLUSTER"] = "0"
+    try:
+        lm.decode_frame(buf, 0, K, T)
+        t7 = time.time()
+        got3, _ = lm.decode_frame(buf, 0, K, T)
+        t8 = time.time()
+    finally:
+        os.environ.pop("ECB_LM_CLUSTER", None)
+    assert torch.equal(got3, codes[0])
+    print(f"per-phase launches instead of the cluster kernel: {1e6 * (t8 - t7) / T:.0f} us per step")
     print(f"LM 32 x 750: batched pass {1e3 * (t1 - t0):.2f} ms, pass + host coder {1e3 * (t2 - t1):.2f} ms, "
           f"device decoding loop {1e3 * (t4 - t3):.1f} ms ({1e6 * (t4 - t3) / T:.0f} us per step; "
           f"{1e6 * (t6 - t5) / T:.0f} us per step without the step graph), {len(data)} bytes")
