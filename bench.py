@@ -734,10 +734,11 @@ def run_ecdc_lm(wl, dev, rank, world, steps, warmup, cpu_leg):
               "batched_pass_kernels": {k: {"ms": v["ms"], "launches": v["launches"]} for k, v in prof_c.items()},
               "decoding_loop_kernels_eager": {k: {"us_per_latent_frame": 1e3 * v["ms"] / T, "launches_per_latent_frame": v["launches"] / T}
                                               for k, v in prof_d.items()},
-              "note": "the decoding loop replays ONE captured step (29 launches) per latent frame; the per-class times above are "
-                      "from a host-launched loop with CUDA events around every launch (event overhead included)"}
-    # the chain is latency-bound: the dominant class by time is lm_linear (21 launches per latent frame); its algorithmic
-    # bytes per latent frame are the weights read once (the activations of one row are negligible)
+              "note": "the decoding loop replays ONE captured step per latent frame (4 launches: the transformer as one 8-CTA cluster "
+                      "kernel -- profiled under lm_linear --, the heads' linear, softmax + cdf, the decoder pull); the per-class times "
+                      "above are from a host-launched loop with CUDA events around every launch (event overhead included)"}
+    # the chain is latency-bound: the dominant class by time is lm_linear (the cluster kernel + the heads' linear); its
+    # algorithmic bytes per latent frame are the weights read once (the activations of one row are negligible)
     w_bytes = 4.0 * (spec.num_layers * (4 * spec.dim * spec.dim + 2 * spec.dim * spec.hidden) + K * spec.card * spec.dim)
     lin_us = detail["decoding_loop_kernels_eager"].get("lm_linear", {}).get("us_per_latent_frame")
     res = {"value": world * T / (ms / steps / 1e3), "ms_per_step": ms / steps, "gpu_launches": launches,
@@ -845,9 +846,9 @@ def main():
                     "gpu_launches": res["gpu_launches"], "e2e": res["e2e"], "detail": res["detail"],
                     "roofline": {"kernel": "lm_linear_kernel", "bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                  "frac": gbs / peaks["hbm_gbs"] if gbs else None, "traffic": None, "peak_source": peaks["source"],
-                                 "note": "decoding loop, per latent frame: the 21 lm_linear launches read every weight once (35.8 MB, "
-                                         "L2-resident) in the measured time; the step is a chain of 29 dependent launches on one row, "
-                                         "bound by launch + memory latency, not by bandwidth or the tensor pipe"},
+                                 "note": "decoding loop, per latent frame: the transformer (one cluster kernel) and the heads' linear read every "
+                                         "weight once (35.8 MB, L2-resident) in the measured time; the step is a chain of dependent phases "
+                                         "on one row, bound by memory + barrier latency, not by bandwidth or the tensor pipe"},
                     "cpu_baseline": res.get("cpu_baseline")}
     elif name == "cfg5":
         res = run_cfg5(name, wl, dev, rank, world, max(1, min(args.steps, 2)), args.warmup, wl["total_clips"])

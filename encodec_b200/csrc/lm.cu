@@ -12,13 +12,16 @@
 //     needs per symbol (8 bytes instead of a 4 KB distribution); the coder itself is the sequential integer recurrence of
 //     ac_core.h on the host.
 //   * DECOMPRESSION is sequential by construction (step t + 1 is conditioned on the symbols decoded at step t), so the whole
-//     loop stays on the device: the same kernels with one row, the keys / values of earlier steps in a cache, and a
-//     one-thread kernel that runs ArithmeticDecoder.pull for the K codebooks of the step and writes the codes the next
-//     step's embedding kernel reads. No host round trip per step (the reference makes K .item() calls per step).
+//     loop stays on the device: the keys / values of earlier steps in a cache, the step's transformer as ONE 8-CTA cluster
+//     kernel (one head per CTA, the row exchanged through distributed shared memory behind cluster barriers; other shapes:
+//     the batched kernels with one row), and a one-block kernel in which one warp runs ArithmeticDecoder.pull for the K
+//     codebooks of the step and writes the codes the next step's embedding reads. One captured step (4 launches) is replayed
+//     per latent frame; no host round trip per step (the reference makes K .item() calls per step).
 //   * Both directions MUST see bit-identical probabilities or the stream decodes to garbage. Every kernel therefore computes
 //     an output element with the same instruction sequence whatever the number of rows in the launch: one warp per
 //     (row, output) dot product with a fixed lane partition of K and a fixed shuffle tree, one warp per (row, head)
-//     attention over keys in window order, per-row softmax reductions. tests/test_lm_gpu.py asserts the identity.
+//     attention over keys in window order, per-row softmax reductions; the arithmetic lives in device functions of explicitly
+//     rounded intrinsics shared by all kernels. tests/test_zz_lm_gpu.py asserts the identity.
 // The state of a stream is its key / value cache: row 0 of an item holds the projections of the all-zero row the reference
 // seeds its state with (transformer.py:103-104; it is attended like a real position until the window drops it), row p + 1
 // position p. These are CUDA-core kernels: the work is a few MFLOP per step and latency-bound (decode) or a few GFLOP per
