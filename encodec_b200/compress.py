@@ -129,7 +129,7 @@ def _decompress_entropy_coded(fo: tp.IO[bytes], model, lm, audio_length: int, nu
             scale_f, = struct.unpack("!f", raw[pos: pos + 4])
             scale = torch.tensor(scale_f, device=device).view(1)
             pos += 4
-        if pos > len(raw):
+        if pos >= len(raw):
             raise EOFError("The stream ended sooner than expected.")
         codes, pos = lm.decode_frame(data[: len(raw)], pos, num_codebooks, frame_length)
         frames.append((codes[None], scale))
