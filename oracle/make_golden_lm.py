@@ -24,7 +24,7 @@ from encodec.quantization.ac import ArithmeticCoder, ArithmeticDecoder, build_st
 
 from encodec_b200 import synth  # noqa: E402
 from oracle import lm_oracle  # noqa: E402
-from tests.golden_cases import LM_CASES, AC_CASES, lm_case_codes, ac_case_pdfs  # noqa: E402
+from tests.golden_cases import LM_CASES, AC_CASES, LM_LONG, LM_LONG_STEPS, lm_case_codes, ac_case_pdfs  # noqa: E402
 
 
 def run_lm_case(spec: synth.LMSpec, K: int, T: int, seed: int):
@@ -105,6 +105,12 @@ def main():
         out[f"{name}_probas"] = probas
         out[f"{name}_bytes"] = data
         out[f"{name}_cdf_crc"] = np.int64(crc)
+    name, spec, K, T, seed = LM_LONG
+    print("LM case", name)
+    probas, data, crc = run_lm_case(spec, K, T, seed)
+    out[f"{name}_probas"] = probas[list(LM_LONG_STEPS)]
+    out[f"{name}_bytes"] = data
+    out[f"{name}_cdf_crc"] = np.int64(crc)
     for name, (card, steps, seed) in AC_CASES.items():
         data, crc = run_ac_case(card, steps, seed)
         out[f"{name}_bytes"] = data

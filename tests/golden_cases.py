@@ -56,6 +56,10 @@ LM_CASES = {
     "lm24_k8": (synth.LMSpec(n_q=32, card=1024, dim=200, num_layers=5, num_heads=8, past_context=262), 8, 24, 11),
     "lmsmall": (synth.LMSpec(n_q=3, card=96, dim=64, num_layers=2, num_heads=4, past_context=5), 3, 23, 12),
 }
+# A frame longer than the LM's window: probabilities are stored for LM_LONG_STEPS only (first steps, around the step at which
+# the all-zero seed row and then real rows leave the window of past_context = 262, and the last step).
+LM_LONG = ("lm24_long", synth.LMSpec(n_q=32, card=1024, dim=200, num_layers=5, num_heads=8, past_context=262), 4, 300, 31)
+LM_LONG_STEPS = (0, 1, 150, 260, 261, 262, 263, 264, 299)
 # name -> (cardinality, steps, seed): the shape of the reference's own coder test (ac.py:263-285)
 AC_CASES = {"ac_card2": (2, 400, 21), "ac_card37": (37, 300, 22), "ac_card1024": (1024, 200, 23), "ac_card3999": (3999, 120, 24)}
 

@@ -38,6 +38,22 @@ def test_lm_oracle_matches_reference(name):
     assert lo.encode_frame(codes, cdfs) == z[f"{name}_bytes"].tobytes()
 
 
+def test_lm_oracle_matches_reference_beyond_the_window():
+    """300 steps with past_context = 262: the seed row and then real rows drop out of the window. The reference's probabilities
+    at the stored steps; the stream the restated coder writes from the restatement's own cdfs has the reference stream's length
+    (the bytes themselves depend on the last bits of the probabilities)."""
+    name, spec, K, T, seed = gc.LM_LONG
+    z = gc.load_lm_golden()
+    sd = synth.make_lm_state_dict(spec, seed)
+    codes = gc.lm_case_codes(spec, K, T, seed)
+    p = lo.lm_probas(sd, codes, num_layers=spec.num_layers, num_heads=spec.num_heads, past_context=spec.past_context)
+    ref = z[f"{name}_probas"]
+    got = p[list(gc.LM_LONG_STEPS)]
+    assert np.all(np.abs(got - ref) <= LM_ATOL + LM_RTOL * ref), float((np.abs(got - ref) / (LM_ATOL + LM_RTOL * ref)).max())
+    mine = lo.encode_frame(codes, lo.build_stable_quantized_cdf(p.astype(np.float32)))
+    assert abs(len(mine) - len(z[f"{name}_bytes"])) <= 2          # same model of the data: the streams have the same length
+
+
 @pytest.mark.parametrize("name", list(gc.AC_CASES))
 def test_coder_oracle_matches_reference(name):
     card, steps, seed = gc.AC_CASES[name]

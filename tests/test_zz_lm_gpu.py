@@ -58,6 +58,25 @@ def test_lm_matches_reference_golden(name):
     print(f"{name}: {len(data)} bytes (reference {len(z[f'{name}_bytes'])}); {100 * same:.0f} % of the cdfs identical to the reference's")
 
 
+def test_lm_matches_reference_beyond_the_window():
+    """300 steps with past_context = 262 against the reference's probabilities at selected steps (the batched pass), and the
+    device decoding loop (cluster kernel, window sliding) returning the codes."""
+    import torch
+    name, spec, K, T, seed = gc.LM_LONG
+    z = gc.load_lm_golden()
+    lm = build_lm(spec, seed)
+    codes = torch.from_numpy(gc.lm_case_codes(spec, K, T, seed))[None].cuda()
+    p = lm.frame_outputs(codes, probas=True, sym_ranges=False)["probas"][0].cpu().numpy()[list(gc.LM_LONG_STEPS)]
+    ref = z[f"{name}_probas"]
+    frac = np.abs(p - ref) / (LM_ATOL + LM_RTOL * ref)
+    print(f"{name}: worst fraction of the tolerance per stored step {[round(float(f.max()), 3) for f in frac]}")
+    assert frac.max() <= 1.0
+    data = lm.encode_frames(codes)[0]
+    assert abs(len(data) - len(z[f"{name}_bytes"])) <= 2
+    got, end = lm.decode_frame(torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda(), 0, K, T)
+    assert torch.equal(got, codes[0]) and end == len(data)
+
+
 def test_quantized_cdf_kernel_is_bit_exact_with_reference():
     """ecb_quantized_cdf on the reference's own probabilities / the coder cases' pdfs == the reference's cdfs (checksums)."""
     import torch
