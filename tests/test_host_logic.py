@@ -103,3 +103,26 @@ def test_synth_is_reproducible():
     assert float(np.abs(a - synth.hash_normal(6, "x", (1000,))).max()) > 0.1
     # pinned values: the golden fixtures depend on this generator never changing
     np.testing.assert_allclose(synth.hash_uniform(1, "k", 3), [0.8444156203852584, 0.19804137564799584, 0.39455054998759187], rtol=0, atol=0)
+
+
+def test_native_signature_tracks_every_tensor():
+    """_NativeStack._signature (what decides whether the native weights are rebuilt) covers exactly the tensors of
+    parameters() + buffers(), and sees a replaced Parameter object and an in-place update."""
+    m = _model(synth.spec_48khz())
+    for mod in (m.encoder, m.decoder):
+        full = sorted(str((t.data_ptr(), t._version, t.device)) for t in list(mod.parameters()) + list(mod.buffers()))
+        assert sorted(map(str, mod._signature())) == full
+        name = next(n for n, _ in mod.named_parameters())
+        owner = mod
+        *path, leaf = name.split(".")
+        for part in path:
+            owner = getattr(owner, part)
+        s0 = mod._signature()
+        setattr(owner, leaf, torch.nn.Parameter(getattr(owner, leaf).detach().clone()))
+        s1 = mod._signature()
+        assert s1 != s0
+        with torch.no_grad():
+            getattr(owner, leaf).mul_(2.0)
+        assert mod._signature() != s1
+        mod.float()                                   # _apply drops the cached module list
+        assert mod.__dict__["_sig_modules"] is None
