@@ -806,6 +806,12 @@ struct Workspace {
 };
 
 size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+// rows whose logits are materialised at a time; ECB_LM_HEAD_ROWS (diagnostic, tests) lowers it to exercise the row chunks
+long long head_rows_limit() {
+  const char* e = getenv("ECB_LM_HEAD_ROWS");
+  const long long v = e ? atoll(e) : 0;
+  return v > 0 ? v : (long long)kHeadRows;
+}
 
 size_t plan_workspace(const LmSpec& sp, long long n_rows, long long K, Workspace* ws, char* base) {
   size_t off = 0;
@@ -814,7 +820,7 @@ size_t plan_workspace(const LmSpec& sp, long long n_rows, long long K, Workspace
     off += align256(bytes);
     return p;
   };
-  const long long head_rows = n_rows < kHeadRows ? n_rows : kHeadRows;
+  const long long head_rows = n_rows < head_rows_limit() ? n_rows : head_rows_limit();
   float* x = (float*)take((size_t)n_rows * sp.dim * 4);
   float* y = (float*)take((size_t)n_rows * sp.dim * 4);
   float* q = (float*)take((size_t)n_rows * sp.dim * 4);
@@ -917,8 +923,9 @@ int lm_heads(const Lm& lm, const Tokens& tk, long long n_items, int K, long long
   const LmSpec& sp = lm.spec;
   const long long n_rows = n_items * n_t;
   const CdfParams cp = cdf_params(sp.card, 24);
-  for (long long r0 = 0; r0 < n_rows; r0 += kHeadRows) {
-    const long long nr = (n_rows - r0) < kHeadRows ? (n_rows - r0) : kHeadRows;
+  const long long chunk = head_rows_limit();
+  for (long long r0 = 0; r0 < n_rows; r0 += chunk) {
+    const long long nr = (n_rows - r0) < chunk ? (n_rows - r0) : chunk;
     LinArgs a{};
     a.x = ws.x + (size_t)r0 * sp.dim; a.W = lm.weights + lm.lin_w_off; a.b = lm.weights + lm.lin_b_off;
     a.ln_w = lm.layers.back().n2_w; a.ln_b = lm.layers.back().n2_b; a.eps = 1e-5f;   // norm2 of the last layer, pending on ws.x

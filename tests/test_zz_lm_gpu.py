@@ -259,3 +259,22 @@ def test_lm_throughput_note():
     print(f"LM 32 x 750: batched pass {1e3 * (t1 - t0):.2f} ms, pass + host coder {1e3 * (t2 - t1):.2f} ms, "
           f"device decoding loop {1e3 * (t4 - t3):.1f} ms ({1e6 * (t4 - t3) / T:.0f} us per step; "
           f"{1e6 * (t6 - t5) / T:.0f} us per step without the step graph), {len(data)} bytes")
+
+
+def test_heads_in_row_chunks_are_bit_identical():
+    """Frames with more rows than fit the logits scratch buffer are processed in row chunks (1024 rows; lowered here through
+    ECB_LM_HEAD_ROWS): probabilities, cdfs and coder ranges must not depend on the chunking."""
+    import os
+    import torch
+    spec, K, T, seed = gc.LM_CASES["lm24_k8"]
+    lm = build_lm(spec, seed)
+    u = synth.hash_uniform(seed, "chunk-codes", 3 * K * 37).reshape(3, K, 37)
+    codes = torch.from_numpy(np.minimum((u * spec.card).astype(np.int64), spec.card - 1)).cuda()     # 111 rows
+    whole = lm.frame_outputs(codes, probas=True, cdf=True, sym_ranges=True)
+    os.environ["ECB_LM_HEAD_ROWS"] = "16"                                                          # 7 chunks, the last one ragged
+    try:
+        parts = lm.frame_outputs(codes, probas=True, cdf=True, sym_ranges=True)
+    finally:
+        os.environ.pop("ECB_LM_HEAD_ROWS", None)
+    for key in ("probas", "cdf", "sym_ranges"):
+        assert torch.equal(whole[key], parts[key]), key
